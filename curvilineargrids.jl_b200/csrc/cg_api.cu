@@ -1,0 +1,656 @@
+// libcurvigrid_cuda.so — C ABI (include/curvigrid_cuda.h) over the CUDA kernels.
+// Host-side handle, device memory, stream ordering, status codes.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/curvigrid_cuda.h"
+#include "cg_kernels_ref.cuh"
+#include "cg_kernels_tiled.cuh"
+#include "cg_mapped.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CG_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(e_ == cudaErrorMemoryAllocation ? CG_ERR_OOM : CG_ERR_CUDA, "%s: %s", #expr, \
+                  cudaGetErrorString(e_));                                                   \
+  } while (0)
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool owned = false;
+};
+
+}  // namespace
+
+struct cg_grid {
+  int device = 0, dim = 0, dtype = 0, nhalo = 0, scheme = 2, profile = 0;
+  int64_t ncell[3] = {1, 1, 1};
+  int64_t nw[3] = {1, 1, 1}, w0[3] = {0, 0, 0}, goff[3] = {0, 0, 0};
+  int kind = 0;  // 0 unset, 1 discrete, 2 mapped
+  int kernel_opt = 1;
+  // node source (interior node planes), either owned or caller's device memory
+  Buf src[3];
+  int64_t src_origin[3] = {0, 0, 0}, src_count[3] = {1, 1, 1};
+  Buf ext[3];
+  bool ext_valid = false;
+  Buf cell_fwd, cell_inv, face_fwd[3], face_inv[3], face_cons[3];
+  Buf node[3], centroid[3], facec[3][3], cjac, cactive[3];
+  bool valid_cell = false, valid_face = false, valid_coords = false;
+  unsigned long long* gcl_bits = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  std::vector<double> terms;
+  cg::MappedTables mtab;
+  double t = 0.0;
+
+  size_t esize() const { return dtype == CG_F64 ? 8 : 4; }
+  int64_t ncells() const { return nw[0] * nw[1] * nw[2]; }
+  int64_t nnodes() const {
+    int64_t n = 1;
+    for (int d = 0; d < dim; ++d) n *= nw[d] + 1;
+    return n;
+  }
+  int64_t next() const {
+    int64_t n = 1;
+    for (int d = 0; d < dim; ++d) n *= nw[d] + 4;
+    return n;
+  }
+  cg::Dims dims() const {
+    cg::Dims D;
+    D.dim = dim;
+    D.nhalo = nhalo;
+    int64_t s = 1;
+    for (int d = 0; d < 3; ++d) {
+      D.nw[d] = nw[d];
+      D.ne[d] = d < dim ? nw[d] + 4 : 1;
+      D.se[d] = s;
+      s *= D.ne[d];
+      D.w0[d] = w0[d] + goff[d];
+      D.gn[d] = ncell[d];
+    }
+    return D;
+  }
+};
+
+namespace {
+
+int ensure(cg_grid* g, Buf& b, size_t bytes) {
+  if (b.p) {
+    if (b.bytes < bytes) return fail(CG_ERR_ARG, "bound output buffer too small (%zu < %zu bytes)", b.bytes, bytes);
+    return CG_OK;
+  }
+  CG_CUDA(cudaSetDevice(g->device));
+  CG_CUDA(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  b.owned = true;
+  return CG_OK;
+}
+void release(Buf& b) {
+  if (b.p && b.owned) cudaFree(b.p);
+  b = Buf();
+}
+
+Buf* select(cg_grid* g, int array, int axis, size_t* bytes) {
+  const int N = g->dim;
+  const size_t es = g->esize();
+  const size_t nc = (size_t)g->ncells();
+  if (array != CG_ARR_FACE_COORD && array != CG_ARR_CELL_FORWARD && array != CG_ARR_CELL_INVERSE &&
+      array != CG_ARR_COMPACT_J && (axis < 0 || axis >= N))
+    return nullptr;
+  switch (array) {
+    case CG_ARR_CELL_FORWARD: *bytes = nc * (N * N + 1) * es; return &g->cell_fwd;
+    case CG_ARR_CELL_INVERSE: *bytes = nc * (N * N + 1) * es; return &g->cell_inv;
+    case CG_ARR_FACE_FORWARD: *bytes = nc * (N * N + 1) * es; return &g->face_fwd[axis];
+    case CG_ARR_FACE_INVERSE: *bytes = nc * (N * N + 1) * es; return &g->face_inv[axis];
+    case CG_ARR_FACE_CONSERVED: *bytes = nc * (N * N) * es; return &g->face_cons[axis];
+    case CG_ARR_NODE_COORD: *bytes = (size_t)g->nnodes() * es; return &g->node[axis];
+    case CG_ARR_CENTROID_COORD: *bytes = nc * es; return &g->centroid[axis];
+    case CG_ARR_FACE_COORD:
+      if (axis < 0 || axis >= 3 * N || axis % 3 >= N) return nullptr;
+      *bytes = nc * es;
+      return &g->facec[axis / 3][axis % 3];
+    case CG_ARR_COMPACT_J: *bytes = nc * es; return &g->cjac;
+    case CG_ARR_COMPACT_ACTIVE: *bytes = nc * N * es; return &g->cactive[axis];
+  }
+  return nullptr;
+}
+
+int launch_blocks(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148LL * 64;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <class T>
+int pad_nodes(cg_grid* g, cudaStream_t st) {
+  const size_t bytes = (size_t)g->next() * sizeof(T);
+  for (int q = 0; q < g->dim; ++q) {
+    int rc = ensure(g, g->ext[q], bytes);
+    if (rc) return rc;
+  }
+  cg::Dims D = g->dims();
+  // discrete grids ignore global_offset: nodes are addressed by window position only
+  for (int d = 0; d < 3; ++d) D.w0[d] = g->w0[d];
+  cg::NodeSrc<T> S;
+  int64_t s = 1;
+  for (int d = 0; d < 3; ++d) {
+    S.p[d] = (const T*)g->src[d].p;
+    S.s0[d] = g->src_origin[d];
+    S.sn[d] = g->src_count[d];
+    S.st[d] = s;
+    s *= g->src_count[d];
+  }
+  cg::k_pad_nodes<T><<<launch_blocks(g->next(), 256), 256, 0, st>>>(D, S, (T*)g->ext[0].p, (T*)g->ext[1].p,
+                                                                    (T*)g->ext[2].p);
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  g->ext_valid = true;
+  return CG_OK;
+}
+
+template <class T>
+int eval_impl(cg_grid* g, int what, cudaStream_t st) {
+  const int N = g->dim;
+  if (g->kind == 0) return fail(CG_ERR_STATE, "cg_grid_eval: no nodes or mapping set");
+  if (g->kind == 2) {
+    int rc = cg::mapped_prepare<T>(g->mtab, g->terms, g->t, g->dims(), st);
+    if (rc) return fail(CG_ERR_CUDA, "mapped_prepare failed (%d)", rc);
+    g_launches += g->mtab.launches;
+    g->mtab.launches = 0;
+    // MappedGrid node coordinates feed the same padded-array layout (nodes evaluated analytically)
+    const size_t bytes = (size_t)g->next() * sizeof(T);
+    for (int q = 0; q < N; ++q) {
+      int r2 = ensure(g, g->ext[q], bytes);
+      if (r2) return r2;
+    }
+    cg::k_mapped_nodes<T><<<launch_blocks(g->next(), 256), 256, 0, st>>>(g->dims(), g->mtab.dev(), (T*)g->ext[0].p,
+                                                                        (T*)g->ext[1].p, (T*)g->ext[2].p);
+    g_launches++;
+    CG_CUDA(cudaGetLastError());
+    g->ext_valid = true;
+  }
+  if (!g->ext_valid) return fail(CG_ERR_STATE, "cg_grid_eval: node data not available");
+  cg::Dims D = g->dims();
+  if (g->kind == 1)
+    for (int d = 0; d < 3; ++d) D.w0[d] = g->w0[d];
+  const T *ex = (const T*)g->ext[0].p, *ey = (const T*)g->ext[1].p, *ez = (const T*)g->ext[2].p;
+
+  if (what & CG_WHAT_COORDS) {
+    cg::CoordOut<T> C;
+    memset(&C, 0, sizeof C);
+    size_t b;
+    for (int q = 0; q < N; ++q) {
+      Buf* nb = select(g, CG_ARR_NODE_COORD, q, &b);
+      int rc = ensure(g, *nb, b);
+      if (rc) return rc;
+      C.node[q] = (T*)nb->p;
+      Buf* cb = select(g, CG_ARR_CENTROID_COORD, q, &b);
+      rc = ensure(g, *cb, b);
+      if (rc) return rc;
+      C.centroid[q] = (T*)cb->p;
+      for (int a = 0; a < N; ++a) {
+        Buf* fb = select(g, CG_ARR_FACE_COORD, 3 * a + q, &b);
+        rc = ensure(g, *fb, b);
+        if (rc) return rc;
+        C.face[a][q] = (T*)fb->p;
+      }
+    }
+    cg::k_coords<T><<<launch_blocks(g->nnodes(), 256), 256, 0, st>>>(D, ex, ey, ez, C);
+    g_launches++;
+    CG_CUDA(cudaGetLastError());
+    g->valid_coords = true;
+  }
+  if (!(what & (CG_WHAT_CELL | CG_WHAT_FACE))) return CG_OK;
+
+  cg::MetricOut<T> O;
+  memset(&O, 0, sizeof O);
+  size_t b;
+  if (g->profile == CG_PROFILE_FULL) {
+    if (what & CG_WHAT_CELL) {
+      Buf* p = select(g, CG_ARR_CELL_FORWARD, 0, &b);
+      int rc = ensure(g, *p, b);
+      if (rc) return rc;
+      O.cell_fwd = (T*)p->p;
+      p = select(g, CG_ARR_CELL_INVERSE, 0, &b);
+      rc = ensure(g, *p, b);
+      if (rc) return rc;
+      O.cell_inv = (T*)p->p;
+    }
+    if (what & CG_WHAT_FACE)
+      for (int a = 0; a < N; ++a) {
+        Buf* p = select(g, CG_ARR_FACE_FORWARD, a, &b);
+        int rc = ensure(g, *p, b);
+        if (rc) return rc;
+        O.face_fwd[a] = (T*)p->p;
+        p = select(g, CG_ARR_FACE_INVERSE, a, &b);
+        rc = ensure(g, *p, b);
+        if (rc) return rc;
+        O.face_inv[a] = (T*)p->p;
+        p = select(g, CG_ARR_FACE_CONSERVED, a, &b);
+        rc = ensure(g, *p, b);
+        if (rc) return rc;
+        O.face_cons[a] = (T*)p->p;
+      }
+  } else {
+    if (what & CG_WHAT_CELL) {
+      Buf* p = select(g, CG_ARR_COMPACT_J, 0, &b);
+      int rc = ensure(g, *p, b);
+      if (rc) return rc;
+      O.cjac = (T*)p->p;
+    }
+    if (what & CG_WHAT_FACE)
+      for (int a = 0; a < N; ++a) {
+        Buf* p = select(g, CG_ARR_COMPACT_ACTIVE, a, &b);
+        int rc = ensure(g, *p, b);
+        if (rc) return rc;
+        O.cactive[a] = (T*)p->p;
+      }
+  }
+  if (!g->ev0) {
+    CG_CUDA(cudaEventCreate(&g->ev0));
+    CG_CUDA(cudaEventCreate(&g->ev1));
+  }
+  CG_CUDA(cudaEventRecord(g->ev0, st));
+  const int64_t nc = g->ncells();
+  int nl = 0;
+  if (N == 1) {
+    cg::k_metrics1d_ref<T><<<launch_blocks(nc, 256), 256, 0, st>>>(D, ex, O, g->scheme, what);
+    nl = 1;
+  } else if (N == 2) {
+    if (g->kernel_opt == 1 && cg::tiled2d_supported<T>(D, O))
+      nl = cg::launch_metrics2d_tiled<T>(D, ex, ey, O, g->scheme, what, st);
+    else {
+      cg::k_metrics2d_ref<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, ex, ey, O, g->scheme, what);
+      nl = 1;
+    }
+  } else {
+    if (g->kernel_opt == 1 && cg::tiled3d_supported<T>(D, O))
+      nl = cg::launch_metrics3d_tiled<T>(D, ex, ey, ez, O, g->scheme, what, st);
+    else {
+      cg::k_metrics3d_ref<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, ex, ey, ez, O, g->scheme, what);
+      nl = 1;
+    }
+  }
+  if (nl < 0) return fail(CG_ERR_CUDA, "tiled kernel launch failed");
+  g_launches += nl;
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaEventRecord(g->ev1, st));
+  g->timed = true;
+  if (what & CG_WHAT_CELL) g->valid_cell = true;
+  if (what & CG_WHAT_FACE) g->valid_face = true;
+  return CG_OK;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_version(void) { return 100; }
+const char* cg_last_error(void) { return g_err.c_str(); }
+uint64_t cg_launch_count(void) { return g_launches.load(); }
+
+int cg_grid_create(int device, int dim, int dtype, const int64_t* ncell, int nhalo, int scheme, int profile,
+                   const int64_t* window_origin, const int64_t* window_cells, const int64_t* global_offset,
+                   cg_grid** out) {
+  if (!out) return fail(CG_ERR_ARG, "cg_grid_create: out is NULL");
+  *out = nullptr;
+  if (dim < 1 || dim > 3) return fail(CG_ERR_ARG, "Unsupported metric dimension N=%d", dim);
+  if (dtype != CG_F64 && dtype != CG_F32) return fail(CG_ERR_ARG, "unsupported dtype %d", dtype);
+  if (nhalo < 0) return fail(CG_ERR_ARG, "nhalo must be >= 0");
+  if (scheme < 0 || scheme > 2) return fail(CG_ERR_ARG, "unknown conserved_metric_scheme %d", scheme);
+  if (profile != CG_PROFILE_FULL && profile != CG_PROFILE_COMPACT) return fail(CG_ERR_ARG, "unknown profile %d", profile);
+  if (!ncell) return fail(CG_ERR_ARG, "ncell is NULL");
+  int ndev = 0;
+  CG_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(CG_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+  cg_grid* g = new cg_grid();
+  g->device = device;
+  g->dim = dim;
+  g->dtype = dtype;
+  g->nhalo = nhalo;
+  g->scheme = scheme;
+  g->profile = profile;
+  for (int d = 0; d < dim; ++d) {
+    if (ncell[d] < 1) {
+      delete g;
+      return fail(CG_ERR_ARG, "celldims[%d] = %lld must be >= 1", d, (long long)ncell[d]);
+    }
+    g->ncell[d] = ncell[d];
+    const int64_t nfull = ncell[d] + 2 * nhalo;
+    g->w0[d] = window_origin ? window_origin[d] : 0;
+    g->nw[d] = window_cells ? window_cells[d] : nfull;
+    g->goff[d] = global_offset ? global_offset[d] : 0;
+    if (g->w0[d] < 0 || g->nw[d] < 1 || g->w0[d] + g->nw[d] > nfull) {
+      delete g;
+      return fail(CG_ERR_ARG, "window [%lld,+%lld) outside cell.full (0..%lld) on axis %d", (long long)g->w0[d],
+                  (long long)g->nw[d], (long long)nfull, d);
+    }
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&g->gcl_bits, 3 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    delete g;
+    return fail(CG_ERR_CUDA, "cg_grid_create: %s", cudaGetErrorString(e));
+  }
+  *out = g;
+  return CG_OK;
+}
+
+int cg_grid_destroy(cg_grid* g) {
+  if (!g) return CG_OK;
+  cudaSetDevice(g->device);
+  for (int a = 0; a < 3; ++a) {
+    release(g->src[a]);
+    release(g->ext[a]);
+    release(g->face_fwd[a]);
+    release(g->face_inv[a]);
+    release(g->face_cons[a]);
+    release(g->node[a]);
+    release(g->centroid[a]);
+    release(g->cactive[a]);
+    for (int q = 0; q < 3; ++q) release(g->facec[a][q]);
+  }
+  release(g->cell_fwd);
+  release(g->cell_inv);
+  release(g->cjac);
+  g->mtab.free_all();
+  if (g->gcl_bits) cudaFree(g->gcl_bits);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  delete g;
+  return CG_OK;
+}
+
+int cg_grid_set_option(cg_grid* g, int option, int64_t value) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (option == CG_OPT_KERNEL) {
+    if (value != 0 && value != 1) return fail(CG_ERR_ARG, "CG_OPT_KERNEL must be 0 or 1");
+    g->kernel_opt = (int)value;
+    return CG_OK;
+  }
+  return fail(CG_ERR_ARG, "unknown option %d", option);
+}
+
+int cg_grid_required_node_range(const cg_grid* g, int axis, int64_t* lo, int64_t* hi) {
+  if (!g || axis < 0 || axis >= g->dim || !lo || !hi) return fail(CG_ERR_ARG, "bad argument");
+  const int64_t gn = g->ncell[axis];
+  int64_t lm = g->w0[axis] - 1 - g->nhalo, hm = g->w0[axis] + g->nw[axis] + 2 - g->nhalo;
+  int64_t l = lm < 0 ? 0 : (lm > gn ? gn : lm), h = hm < 0 ? 0 : (hm > gn ? gn : hm);
+  if (lm < 0 && h < 1) h = 1;
+  if (hm > gn && l > gn - 1) l = gn - 1;
+  *lo = l;
+  *hi = h + 1;
+  return CG_OK;
+}
+
+int cg_grid_set_nodes(cg_grid* g, const void* x, const void* y, const void* z, int halo_coords_included,
+                      const int64_t* node_origin, const int64_t* node_count, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  const void* in[3] = {x, y, z};
+  for (int q = 0; q < g->dim; ++q)
+    if (!in[q]) return fail(CG_ERR_ARG, "coordinate array %d is NULL", q);
+  CG_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t origin[3] = {0, 0, 0}, count[3] = {1, 1, 1};
+  for (int d = 0; d < g->dim; ++d) {
+    if (node_origin && node_count) {
+      origin[d] = node_origin[d];
+      count[d] = node_count[d];
+    } else if (halo_coords_included) {
+      origin[d] = -g->nhalo;  // halo nodes are present in the buffer but never read
+      count[d] = g->ncell[d] + 1 + 2 * g->nhalo;
+    } else {
+      origin[d] = 0;
+      count[d] = g->ncell[d] + 1;
+    }
+    int64_t lo, hi;
+    cg_grid_required_node_range(g, d, &lo, &hi);
+    if (origin[d] > lo || origin[d] + count[d] < hi)
+      return fail(CG_ERR_ARG, "node arrays cover [%lld,%lld) on axis %d but the window needs [%lld,%lld)",
+                  (long long)origin[d], (long long)(origin[d] + count[d]), d, (long long)lo, (long long)hi);
+    if (g->ncell[d] < 1) return fail(CG_ERR_ARG, "need at least 2 nodes per axis");
+  }
+  const size_t bytes = (size_t)(count[0] * count[1] * count[2]) * g->esize();
+  for (int q = 0; q < g->dim; ++q) {
+    if (is_device_ptr(in[q])) {
+      release(g->src[q]);
+      g->src[q].p = const_cast<void*>(in[q]);
+      g->src[q].bytes = bytes;
+      g->src[q].owned = false;
+    } else {
+      if (g->src[q].p && (!g->src[q].owned || g->src[q].bytes < bytes)) release(g->src[q]);
+      int rc = ensure(g, g->src[q], bytes);
+      if (rc) return rc;
+      CG_CUDA(cudaMemcpyAsync(g->src[q].p, in[q], bytes, cudaMemcpyHostToDevice, st));
+    }
+  }
+  for (int d = 0; d < 3; ++d) {
+    g->src_origin[d] = origin[d];
+    g->src_count[d] = count[d];
+  }
+  g->kind = 1;
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return g->dtype == CG_F64 ? pad_nodes<double>(g, st) : pad_nodes<float>(g, st);
+}
+
+int cg_grid_node_buffer(cg_grid* g, int coord, void** devptr, int64_t* origin3, int64_t* count3) {
+  if (!g || coord < 0 || coord >= g->dim || !devptr) return fail(CG_ERR_ARG, "bad argument");
+  if (!g->src[coord].p) return fail(CG_ERR_STATE, "no node buffer: call cg_grid_set_nodes first");
+  *devptr = g->src[coord].p;
+  for (int d = 0; d < 3; ++d) {
+    if (origin3) origin3[d] = g->src_origin[d];
+    if (count3) count3[d] = g->src_count[d];
+  }
+  return CG_OK;
+}
+
+int cg_grid_nodes_changed(cg_grid* g, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (g->kind != 1) return fail(CG_ERR_STATE, "not a DiscreteGrid");
+  CG_CUDA(cudaSetDevice(g->device));
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return g->dtype == CG_F64 ? pad_nodes<double>(g, (cudaStream_t)stream) : pad_nodes<float>(g, (cudaStream_t)stream);
+}
+
+int cg_grid_set_mapping_terms(cg_grid* g, int nterms, const double* table) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (nterms < 1 || !table) return fail(CG_ERR_ARG, "empty mapping");
+  for (int m = 0; m < nterms; ++m) {
+    const double* r = table + 15 * m;
+    if (r[0] < 0 || r[0] >= g->dim) return fail(CG_ERR_ARG, "term %d: coord %g out of range", m, r[0]);
+    for (int d = 0; d < 3; ++d)
+      if (r[6 + 3 * d] < 0 || r[6 + 3 * d] > 3) return fail(CG_ERR_ARG, "term %d: bad factor kind", m);
+  }
+  g->terms.assign(table, table + 15 * (size_t)nterms);
+  g->kind = 2;
+  g->mtab.dirty = true;
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return CG_OK;
+}
+
+int cg_grid_update(cg_grid* g, double t, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (g->kind == 0) return fail(CG_ERR_STATE, "cg_grid_update: no nodes or mapping set");
+  g->t = t;
+  g->mtab.dirty = true;
+  g->valid_cell = g->valid_face = false;
+  if (g->valid_coords || g->node[0].p) {
+    CG_CUDA(cudaSetDevice(g->device));
+    return g->dtype == CG_F64 ? eval_impl<double>(g, CG_WHAT_COORDS, (cudaStream_t)stream)
+                              : eval_impl<float>(g, CG_WHAT_COORDS, (cudaStream_t)stream);
+  }
+  return CG_OK;
+}
+
+int cg_grid_eval(cg_grid* g, int what, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (what <= 0 || what > 7) return fail(CG_ERR_ARG, "bad what mask %d", what);
+  CG_CUDA(cudaSetDevice(g->device));
+  return g->dtype == CG_F64 ? eval_impl<double>(g, what, (cudaStream_t)stream)
+                            : eval_impl<float>(g, what, (cudaStream_t)stream);
+}
+
+int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (cell_valid) *cell_valid = g->valid_cell;
+  if (face_valid) *face_valid = g->valid_face;
+  return CG_OK;
+}
+
+int cg_grid_invalidate(cg_grid* g, int what) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (what & CG_WHAT_CELL) g->valid_cell = false;
+  if (what & CG_WHAT_FACE) g->valid_face = false;
+  if (what & CG_WHAT_COORDS) g->valid_coords = false;
+  return CG_OK;
+}
+
+int cg_grid_get_ptr(cg_grid* g, int array, int axis, void** devptr, size_t* nbytes) {
+  if (!g || !devptr) return fail(CG_ERR_ARG, "bad argument");
+  size_t bytes = 0;
+  Buf* b = select(g, array, axis, &bytes);
+  if (!b) return fail(CG_ERR_ARG, "unknown array %d / axis %d", array, axis);
+  int rc = ensure(g, *b, bytes);
+  if (rc) return rc;
+  *devptr = b->p;
+  if (nbytes) *nbytes = bytes;
+  return CG_OK;
+}
+
+int cg_grid_bind_output(cg_grid* g, int array, int axis, void* devptr, size_t nbytes) {
+  if (!g || !devptr) return fail(CG_ERR_ARG, "bad argument");
+  size_t bytes = 0;
+  Buf* b = select(g, array, axis, &bytes);
+  if (!b) return fail(CG_ERR_ARG, "unknown array %d / axis %d", array, axis);
+  if (nbytes < bytes) return fail(CG_ERR_ARG, "buffer too small: %zu < %zu bytes", nbytes, bytes);
+  release(*b);
+  b->p = devptr;
+  b->bytes = nbytes;
+  b->owned = false;
+  return CG_OK;
+}
+
+int cg_grid_copy_out(cg_grid* g, int array, int axis, void* host_dst, size_t nbytes) {
+  if (!g || !host_dst) return fail(CG_ERR_ARG, "bad argument");
+  size_t bytes = 0;
+  Buf* b = select(g, array, axis, &bytes);
+  if (!b) return fail(CG_ERR_ARG, "unknown array %d / axis %d", array, axis);
+  if (!b->p) return fail(CG_ERR_STATE, "array %d/%d has not been computed", array, axis);
+  if (nbytes < bytes) return fail(CG_ERR_ARG, "host buffer too small: %zu < %zu bytes", nbytes, bytes);
+  CG_CUDA(cudaSetDevice(g->device));
+  CG_CUDA(cudaMemcpy(host_dst, b->p, bytes, cudaMemcpyDeviceToHost));
+  return CG_OK;
+}
+
+int cg_grid_gcl_max(cg_grid* g, double* out, void* stream) {
+  if (!g || !out) return fail(CG_ERR_ARG, "bad argument");
+  if (!g->valid_face) return fail(CG_ERR_STATE, "face metrics are not valid; call cg_grid_eval first");
+  CG_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = g->dim;
+  const bool compact = g->profile == CG_PROFILE_COMPACT;
+  // cell.domain of the global grid intersected with the window (needs I - e_axis inside the window)
+  int64_t lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  for (int d = 0; d < N; ++d) {
+    int64_t l = g->nhalo - g->w0[d], h = g->nhalo + g->ncell[d] - g->w0[d];
+    lo[d] = l < 1 ? 1 : l;
+    hi[d] = h > g->nw[d] ? g->nw[d] : h;
+    if (hi[d] <= lo[d]) {
+      for (int c = 0; c < N; ++c) out[c] = 0.0;
+      return CG_OK;
+    }
+  }
+  CG_CUDA(cudaMemsetAsync(g->gcl_bits, 0, 3 * sizeof(unsigned long long), st));
+  const void* c[3] = {nullptr, nullptr, nullptr};
+  for (int a = 0; a < N; ++a) c[a] = compact ? g->cactive[a].p : g->face_cons[a].p;
+  cg::Dims D = g->dims();
+  int64_t n = 1;
+  for (int d = 0; d < N; ++d) n *= hi[d] - lo[d];
+  if (g->dtype == CG_F64)
+    cg::k_gcl<double><<<launch_blocks(n, 256), 256, 0, st>>>(D, (const double*)c[0], (const double*)c[1],
+                                                             (const double*)c[2], compact, lo[0], lo[1], lo[2],
+                                                             hi[0], hi[1], hi[2], g->gcl_bits);
+  else
+    cg::k_gcl<float><<<launch_blocks(n, 256), 256, 0, st>>>(D, (const float*)c[0], (const float*)c[1],
+                                                            (const float*)c[2], compact, lo[0], lo[1], lo[2], hi[0],
+                                                            hi[1], hi[2], g->gcl_bits);
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  unsigned long long bits[3];
+  CG_CUDA(cudaMemcpyAsync(bits, g->gcl_bits, sizeof bits, cudaMemcpyDeviceToHost, st));
+  CG_CUDA(cudaStreamSynchronize(st));
+  for (int cc = 0; cc < N; ++cc) memcpy(&out[cc], &bits[cc], 8);
+  return CG_OK;
+}
+
+int cg_grid_sync(cg_grid* g, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  CG_CUDA(cudaSetDevice(g->device));
+  CG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return CG_OK;
+}
+
+int cg_grid_last_eval_ms(cg_grid* g, float* ms) {
+  if (!g || !ms) return fail(CG_ERR_ARG, "bad argument");
+  if (!g->timed) return fail(CG_ERR_STATE, "no eval has been timed");
+  CG_CUDA(cudaEventSynchronize(g->ev1));
+  CG_CUDA(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+  return CG_OK;
+}
+
+int cg_discrete_metrics_host(int device, int dim, int dtype, const void* x, const void* y, const void* z,
+                             const int64_t* ncell, int nhalo, int halo_coords_included, int scheme, void* cell_fwd,
+                             void* cell_inv, void* face_fwd, void* face_inv, void* face_cons) {
+  cg_grid* g = nullptr;
+  int rc = cg_grid_create(device, dim, dtype, ncell, nhalo, scheme, CG_PROFILE_FULL, nullptr, nullptr, nullptr, &g);
+  if (rc) return rc;
+  rc = cg_grid_set_nodes(g, x, y, z, halo_coords_included, nullptr, nullptr, nullptr);
+  int what = ((cell_fwd || cell_inv) ? CG_WHAT_CELL : 0) | ((face_fwd || face_inv || face_cons) ? CG_WHAT_FACE : 0);
+  if (!rc && what) rc = cg_grid_eval(g, what, nullptr);
+  const size_t es = g->esize(), nc = (size_t)g->ncells();
+  const size_t km = (size_t)(dim * dim + 1) * es * nc, kc = (size_t)(dim * dim) * es * nc;
+  if (!rc && cell_fwd) rc = cg_grid_copy_out(g, CG_ARR_CELL_FORWARD, 0, cell_fwd, km);
+  if (!rc && cell_inv) rc = cg_grid_copy_out(g, CG_ARR_CELL_INVERSE, 0, cell_inv, km);
+  for (int a = 0; a < dim && !rc; ++a) {
+    if (face_fwd) rc = cg_grid_copy_out(g, CG_ARR_FACE_FORWARD, a, (char*)face_fwd + a * km, km);
+    if (!rc && face_inv) rc = cg_grid_copy_out(g, CG_ARR_FACE_INVERSE, a, (char*)face_inv + a * km, km);
+    if (!rc && face_cons) rc = cg_grid_copy_out(g, CG_ARR_FACE_CONSERVED, a, (char*)face_cons + a * kc, kc);
+  }
+  std::string keep = g_err;
+  cg_grid_destroy(g);
+  g_err = keep;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""k-slab decomposition of a DiscreteGrid over the GPUs of one box.
+
+The reference has no communication layer: `local_grid`
+(mapped_grid.jl:344-379) gives rank-local analytic grids, and multiblock
+`interface_index_plan` (src/multiblock/transfer.jl:157-236) only lists index
+pairs for "a solver or MPI layer".  For sampled meshes a rank needs *real*
+neighbour node planes: 1 plane below and 3 above its cell
+slab.  This module is that exchange: pure index algebra + torch.distributed
+point-to-point (NCCL over NVLink on GPUs; gloo in the CPU tests).
+
+Conventions: the slab axis is the slowest axis (k for 3-D, j for 2-D) so every
+plane is one contiguous range of memory.  Cell planes are indices of the
+GLOBAL cell.full array (0 .. nk+2h-1); node planes are indices of the INTERIOR
+node array (0 .. nk).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+def partition_planes(nplanes, nranks):
+    """Split `nplanes` cell planes into `nranks` contiguous [k0,k1) ranges, sizes differing by <= 1."""
+    base, rem = divmod(nplanes, nranks)
+    out, k = [], 0
+    for r in range(nranks):
+        n = base + (1 if r < rem else 0)
+        out.append((k, k + n))
+        k += n
+    return out
+
+
+def required_node_range(k0, k1, nhalo, ncell):
+    """Interior node planes [lo,hi) a slab of cell planes [k0,k1) reads (same rule as
+    cg_grid_required_node_range): padded planes k0-1 .. k1+2, clamped to the interior,
+    plus the second boundary plane where Line() extrapolation needs a slope."""
+    lm, hm = k0 - 1 - nhalo, k1 + 2 - nhalo
+    lo = min(max(lm, 0), ncell)
+    hi = min(max(hm, 0), ncell)
+    if lm < 0 and hi < 1:
+        hi = 1
+    if hm > ncell and lo > ncell - 1:
+        lo = ncell - 1
+    return lo, hi + 1
+
+
+def owned_node_range(k0, k1, nhalo, ncell, is_first, is_last):
+    """Interior node planes a rank is the *source* of: plane m belongs to the slab holding
+    cell plane m+nhalo; the first/last ranks also own what lies below/above."""
+    lo = 0 if is_first else min(max(k0 - nhalo, 0), ncell + 1)
+    hi = ncell + 1 if is_last else min(max(k1 - nhalo, 0), ncell + 1)
+    return lo, max(hi, lo)
+
+
+@dataclass
+class SlabPlan:
+    rank: int
+    nranks: int
+    nhalo: int
+    ncell_slab: int       # interior cells along the slab axis (global)
+    cells: tuple          # (k0, k1) cell planes of this rank
+    required: tuple       # (lo, hi) interior node planes held locally
+    owned: tuple          # (lo, hi) interior node planes this rank sources
+    sends: list           # [(peer, lo, hi)] node planes (global indices) to send
+    recvs: list           # [(peer, lo, hi)] node planes to receive
+
+
+def make_plan(rank, nranks, ncell_slab, nhalo):
+    parts = partition_planes(ncell_slab + 2 * nhalo, nranks)
+    req = [required_node_range(k0, k1, nhalo, ncell_slab) for k0, k1 in parts]
+    own = [owned_node_range(k0, k1, nhalo, ncell_slab, r == 0, r == nranks - 1) for r, (k0, k1) in enumerate(parts)]
+    sends, recvs = [], []
+    for peer in range(nranks):
+        if peer == rank:
+            continue
+        lo, hi = max(own[rank][0], req[peer][0]), min(own[rank][1], req[peer][1])
+        if hi > lo:
+            sends.append((peer, lo, hi))
+        lo, hi = max(own[peer][0], req[rank][0]), min(own[peer][1], req[rank][1])
+        if hi > lo:
+            recvs.append((peer, lo, hi))
+    return SlabPlan(rank, nranks, nhalo, ncell_slab, parts[rank], req[rank], own[rank], sends, recvs)
+
+
+def exchange_node_planes(plan, buffers, dist=None, group=None):
+    """Fill the non-owned planes of each local node buffer from their owners.
+
+    buffers: list of torch tensors whose FIRST dimension is the slab axis and covers
+    plan.required (memory order, e.g. [nk_local, nj+1, ni+1]).  Returns the list of
+    pending work handles (already waited on when `dist` is None-safe)."""
+    if plan.nranks == 1:
+        return []
+    if dist is None:
+        import torch.distributed as dist
+    ops = []
+    base = plan.required[0]
+    for buf in buffers:
+        for peer, lo, hi in plan.sends:
+            ops.append(dist.P2POp(dist.isend, buf[lo - base:hi - base], peer, group=group))
+        for peer, lo, hi in plan.recvs:
+            ops.append(dist.P2POp(dist.irecv, buf[lo - base:hi - base], peer, group=group))
+    if not ops:
+        return []
+    reqs = dist.batch_isend_irecv(ops)
+    for r in reqs:
+        r.wait()
+    return reqs
+
+
+def slab_grid_kwargs(plan, inplane_celldims, nhalo):
+    """kwargs for DiscreteGrid(...) describing this rank's slab of a 2-D/3-D grid.
+    `inplane_celldims`: interior cells of the non-slab axes, fastest first."""
+    dim = len(inplane_celldims) + 1
+    celldims = tuple(inplane_celldims) + (plan.ncell_slab,)
+    nfull = tuple(c + 2 * nhalo for c in celldims)
+    k0, k1 = plan.cells
+    origin = (0,) * (dim - 1) + (k0,)
+    cells = nfull[:-1] + (k1 - k0,)
+    node_origin = (0,) * (dim - 1) + (plan.required[0],)
+    return dict(window=(origin, cells), global_celldims=celldims, node_origin=node_origin)

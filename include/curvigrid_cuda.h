@@ -1,0 +1,168 @@
+/*
+ * libcurvigrid_cuda.so — B200-native metric evaluation for CurvilinearGrids.jl
+ * (C ABI; plain pointers and sizes only, no C++/torch types).
+ *
+ * The reference has no FFI.  Its only backend seam is Julia multiple dispatch on
+ * a `backend::KernelAbstractions.Backend` first argument; each entry point below
+ * names the reference method a Julia `ccall` shim would override with it
+ * (paths relative to /root/reference/src/grids/unified_grids/).  INTEGRATION.md
+ * shows the shim.
+ *
+ * Memory layouts are byte-identical to the reference's Julia arrays
+ * (SURVEY.md Appendix B): column-major over cells (i fastest), element =
+ * N*N matrix entries column-major (F11,F21,...) followed by J for `Metric`
+ * (metrics.jl:19-22), N*N entries for `ConservedMetric` (metrics.jl:32-34).
+ * Storage index I of a face array holds the face I+1/2 (high side).
+ *
+ * Every call returns a cg_status; cg_last_error() gives the message of the last
+ * failure on the calling thread.  Nothing throws across the ABI.  A handle is
+ * bound to one device and must not be used from two host threads at once (the
+ * reference has no locking either).  `stream` arguments are cudaStream_t passed
+ * as void* (NULL = the legacy default stream); calls are stream-ordered and
+ * asynchronous unless stated otherwise.
+ */
+#ifndef CURVIGRID_CUDA_H
+#define CURVIGRID_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cg_grid cg_grid; /* opaque */
+
+enum cg_status {
+  CG_OK = 0,
+  CG_ERR_ARG = 1,    /* ArgumentError in the reference (unified_grids.jl:54-86) */
+  CG_ERR_OOM = 2,
+  CG_ERR_CUDA = 3,
+  CG_ERR_STATE = 4,  /* e.g. metrics requested with storage disabled (cache_mode=:off) */
+  CG_ERR_NCCL = 5
+};
+
+/* conserved_metric_scheme (metrics.jl:111-126) */
+enum cg_scheme { CG_ENDPOINT_AVERAGE = 0, CG_GRADIENT_CORRECTED = 1, CG_CURVATURE_CORRECTED = 2 };
+enum cg_dtype { CG_F64 = 0, CG_F32 = 1 };
+/* FULL: the reference's 107 doubles/cell (3-D).  COMPACT: J of the cell + the active conserved
+ * row per axis = what face_flux_geometry/cellvolume read (face_geometry.jl:393-416). */
+enum cg_profile { CG_PROFILE_FULL = 0, CG_PROFILE_COMPACT = 1 };
+enum cg_what { CG_WHAT_CELL = 1, CG_WHAT_FACE = 2, CG_WHAT_COORDS = 4 };
+
+/* array selectors for cg_grid_get_ptr / cg_grid_copy_out / cg_grid_bind_output */
+enum cg_array {
+  CG_ARR_CELL_FORWARD = 0,   /* cell_metrics(grid).forward            [cell][N*N+1] */
+  CG_ARR_CELL_INVERSE = 1,   /* cell_metrics(grid).inverse            [cell][N*N+1] */
+  CG_ARR_FACE_FORWARD = 2,   /* face_metrics(grid)[axis].forward      [cell][N*N+1] */
+  CG_ARR_FACE_INVERSE = 3,   /* face_metrics(grid)[axis].inverse      [cell][N*N+1] */
+  CG_ARR_FACE_CONSERVED = 4, /* face_metrics(grid)[axis].conserved    [cell][N*N]   */
+  CG_ARR_NODE_COORD = 5,     /* grid.node_coordinates[axis]           [node.full]   */
+  CG_ARR_CENTROID_COORD = 6, /* grid.centroid_coordinates[axis]       [cell.full]   */
+  CG_ARR_FACE_COORD = 7,     /* grid.face_coordinates[axis/3][axis%3] [cell.full]; axis = 3*face_axis + coord */
+  CG_ARR_COMPACT_J = 8,      /* compact profile: det(F) of the cell   [cell]        */
+  CG_ARR_COMPACT_ACTIVE = 9  /* compact profile: conserved[axis][axis,:]  [cell][N] */
+};
+
+enum cg_option {
+  CG_OPT_KERNEL = 0 /* 0 = gather reference kernels, 1 = tiled kernels (default) */
+};
+
+int cg_version(void);
+const char* cg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py `gpu_launches`) */
+uint64_t cg_launch_count(void);
+
+/*
+ * Grid storage + iterators.  Replaces _build_unified_components
+ * (generation.jl:143-183): get_iterators (:3-33) and the KernelAbstractions.zeros
+ * allocations (:37-139), which become lazily allocated device buffers.
+ *   ncell[d]          interior cells of the WHOLE grid per axis (celldims)
+ *   window_origin[d], window_cells[d]
+ *                     which part of the global cell.full array this handle
+ *                     stores (k-slab of a multi-GPU decomposition); NULL = all.
+ *   global_offset[d]  first(global_cell_indices)-1 for a MappedGrid made by
+ *                     local_grid (mapped_grid.jl:344-379); NULL = 0.
+ */
+int cg_grid_create(int device, int dim, int dtype, const int64_t* ncell, int nhalo, int scheme, int profile,
+                   const int64_t* window_origin, const int64_t* window_cells, const int64_t* global_offset,
+                   cg_grid** out);
+int cg_grid_destroy(cg_grid* g);
+int cg_grid_set_option(cg_grid* g, int option, int64_t value);
+
+/*
+ * DiscreteGrid(x[,y[,z]], nhalo; halo_coords_included) node input
+ * (discrete_grid.jl:428-590; strips halos like _strip_halo_nodes :55-61 and
+ * applies the Line() extrapolation of _linear_interpolant :63).
+ * x,y,z: host or device pointers (detected), grid dtype, column-major.  Extents:
+ *   whole grid:  ncell+1 per axis (or ncell+1+2*nhalo with halo_coords_included)
+ *   slab window: pass node_origin/node_count = the range of INTERIOR node
+ *                indices the arrays cover (must include the planes the window
+ *                needs: window cells +-1/+3, clamped to the interior).
+ * Marks cell and face metrics invalid (like update!, discrete_grid.jl:605-641).
+ */
+int cg_grid_set_nodes(cg_grid* g, const void* x, const void* y, const void* z, int halo_coords_included,
+                      const int64_t* node_origin, const int64_t* node_count, void* stream);
+/* device buffer the node planes live in before padding (for NCCL halo exchange into it) */
+int cg_grid_node_buffer(cg_grid* g, int coord, void** devptr, int64_t* origin3, int64_t* count3);
+/* (re)apply padding after the node buffer was written in place (e.g. by ncclRecv) */
+int cg_grid_nodes_changed(cg_grid* g, void* stream);
+/* interior node planes (along the slab axis) this window needs: [lo, hi) */
+int cg_grid_required_node_range(const cg_grid* g, int axis, int64_t* lo, int64_t* hi);
+
+/*
+ * MappedGrid(x[,y[,z]], params, celldims, nhalo) with a separable term-list
+ * mapping (mapped_grid.jl:421-540).  table = nterms rows of 15 doubles:
+ *   [coord, c0, c1, c2, w, ph, (kind,a,b) x 3 axes],
+ *   q_coord(t,xi) += (c0 + c1 t + c2 sin(w t + ph)) * prod_axis f(kind, a + b*xi_axis)
+ *   kind: 0 = 1, 1 = a+b*s, 2 = sin(a+b*s), 3 = cos(a+b*s)
+ */
+int cg_grid_set_mapping_terms(cg_grid* g, int nterms, const double* table);
+
+/*
+ * update!(grid, t, params) (mapped_grid.jl:551-593, discrete_grid.jl:605-647):
+ * refresh node/centroid/face coordinates (if coordinate storage is enabled) and
+ * invalidate both metric caches (metric_cache_api.jl:16-41).
+ */
+int cg_grid_update(cg_grid* g, double t, void* stream);
+
+/*
+ * refresh_cell_metrics! / refresh_face_metrics! (metric_cache_api.jl:57-127) =
+ * _fill_cell_metric_storage!(backend, ...) metrics.jl:2079 and
+ * _fill_face_metric_storage!(backend, ...) metrics.jl:2167/2209, fused in one
+ * launch; `what` = CG_WHAT_CELL | CG_WHAT_FACE | CG_WHAT_COORDS
+ * (_compute_unified_{node,centroid,face}_coordinates!, generation.jl:319-598).
+ */
+int cg_grid_eval(cg_grid* g, int what, void* stream);
+
+/* valid flags of UnifiedMetricCache (unified_grids.jl:34-52); invalidate_* (metric_cache_api.jl:16-41) */
+int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid);
+int cg_grid_invalidate(cg_grid* g, int what);
+
+/* device pointer + size of an output array (allocated on first use) */
+int cg_grid_get_ptr(cg_grid* g, int array, int axis, void** devptr, size_t* nbytes);
+/* use caller-owned device storage (CUDA.jl / torch) for an output array */
+int cg_grid_bind_output(cg_grid* g, int array, int axis, void* devptr, size_t nbytes);
+/* synchronous device->host copy of an output array */
+int cg_grid_copy_out(cg_grid* g, int array, int axis, void* host_dst, size_t nbytes);
+
+/*
+ * GridTypes.gcl(face_metrics(grid), cell.domain) reduced to max|I_c| per physical
+ * column (../gcl.jl:20-117).  Synchronises the stream; out[0..dim).
+ */
+int cg_grid_gcl_max(cg_grid* g, double* out, void* stream);
+
+int cg_grid_sync(cg_grid* g, void* stream);
+/* device time of the last cg_grid_eval on this handle in ms (CUDA events; synchronises) */
+int cg_grid_last_eval_ms(cg_grid* g, float* ms);
+
+/* one-shot host-buffer convenience: DiscreteGrid(...) eager fill, results copied to host
+ * buffers (any output pointer may be NULL).  face_* = [axis][cell][K]. */
+int cg_discrete_metrics_host(int device, int dim, int dtype, const void* x, const void* y, const void* z,
+                             const int64_t* ncell, int nhalo, int halo_coords_included, int scheme,
+                             void* cell_fwd, void* cell_inv, void* face_fwd, void* face_inv, void* face_cons);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CURVIGRID_CUDA_H */

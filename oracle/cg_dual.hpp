@@ -1,0 +1,67 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked into the product library.
+//
+// Forward-mode dual numbers, nestable to any depth, standing in for the
+// ForwardDiff.jl `Dual` type that the reference differentiates its mapping
+// closures with (DifferentiationInterface `derivative`, `value_and_derivative`,
+// `value_derivative_and_second_derivative`; call sites in
+// /root/reference/src/grids/unified_grids/metrics.jl:190-214, 251-268,
+// 367-421, 919-1113, 1547-1651).  ForwardDiff 1.3.3 / DifferentiationInterface
+// 0.7.18 are not vendored in /root/reference; forward-mode AD is exact
+// differentiation, so the restatement is the textbook dual-number algebra.
+#pragma once
+#include <cmath>
+
+namespace cgo {
+
+template <class T>
+struct Dual {
+  T v;  // value
+  T d;  // derivative part
+};
+
+// ---- construction of constants and access to the innermost primal ----------
+template <class T>
+struct dtraits {
+  static T from(double c) { return c; }
+  static double primal(const T& x) { return x; }
+};
+template <class T>
+struct dtraits<Dual<T>> {
+  static Dual<T> from(double c) { return {dtraits<T>::from(c), dtraits<T>::from(0.0)}; }
+  static double primal(const Dual<T>& x) { return dtraits<T>::primal(x.v); }
+};
+template <class T>
+inline T constant(double c) { return dtraits<T>::from(c); }
+template <class T>
+inline double primal(const T& x) { return dtraits<T>::primal(x); }
+
+// ---- arithmetic -------------------------------------------------------------
+template <class T> inline Dual<T> operator+(const Dual<T>& a, const Dual<T>& b) { return {a.v + b.v, a.d + b.d}; }
+template <class T> inline Dual<T> operator-(const Dual<T>& a, const Dual<T>& b) { return {a.v - b.v, a.d - b.d}; }
+template <class T> inline Dual<T> operator-(const Dual<T>& a) { return {-a.v, -a.d}; }
+template <class T> inline Dual<T> operator*(const Dual<T>& a, const Dual<T>& b) { return {a.v * b.v, a.v * b.d + a.d * b.v}; }
+template <class T> inline Dual<T> operator/(const Dual<T>& a, const Dual<T>& b) {
+  T q = a.v / b.v;
+  return {q, (a.d - q * b.d) / b.v};
+}
+template <class T> inline Dual<T> operator+(const Dual<T>& a, double b) { return {a.v + b, a.d}; }
+template <class T> inline Dual<T> operator+(double a, const Dual<T>& b) { return {a + b.v, b.d}; }
+template <class T> inline Dual<T> operator-(const Dual<T>& a, double b) { return {a.v - b, a.d}; }
+template <class T> inline Dual<T> operator-(double a, const Dual<T>& b) { return {a - b.v, -b.d}; }
+template <class T> inline Dual<T> operator*(const Dual<T>& a, double b) { return {a.v * b, a.d * b}; }
+template <class T> inline Dual<T> operator*(double a, const Dual<T>& b) { return {a * b.v, a * b.d}; }
+template <class T> inline Dual<T> operator/(const Dual<T>& a, double b) { return {a.v / b, a.d / b}; }
+template <class T> inline Dual<T> operator/(double a, const Dual<T>& b) {
+  T q = a / b.v;
+  return {q, -(q * b.d) / b.v};
+}
+
+// ---- elementary functions (the reference's test mappings use sin/cos/sinpi) -
+inline double sin_(double x) { return std::sin(x); }
+inline double cos_(double x) { return std::cos(x); }
+template <class T> inline Dual<T> sin_(const Dual<T>& a);
+template <class T> inline Dual<T> cos_(const Dual<T>& a);
+template <class T> inline Dual<T> sin_(const Dual<T>& a) { return {sin_(a.v), cos_(a.v) * a.d}; }
+template <class T> inline Dual<T> cos_(const Dual<T>& a) { return {cos_(a.v), -(sin_(a.v) * a.d)}; }
+
+}  // namespace cgo

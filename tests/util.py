@@ -1,0 +1,89 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+RTOL_F64 = 1e-12   # BASELINE.json north_star: FP64 relative error <= 1e-12
+RTOL_F32 = 2e-4    # FP32 variants: reference exercises Float32 at tol 1e-7 on GCL only; entries checked loosely
+
+KEYS = ("cell_fwd", "cell_inv", "face_fwd", "face_inv", "face_cons")
+
+
+def metric_err(a, b, has_j):
+    """Relative error per cell: matrix entries against the largest entry of the
+    same matrix, J against itself.  Returns max over cells."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    K = a.shape[-1] - (1 if has_j else 0)
+    ma, mb = a[..., :K], b[..., :K]
+    scale = np.abs(mb).max(axis=-1, keepdims=True)
+    scale = np.where(scale == 0, 1.0, scale)
+    e = (np.abs(ma - mb) / scale).max() if ma.size else 0.0
+    if has_j:
+        ja, jb = a[..., K], b[..., K]
+        e = max(e, (np.abs(ja - jb) / np.where(jb == 0, 1.0, np.abs(jb))).max())
+    return float(e)
+
+
+def assert_metrics_close(got, ref, rtol=RTOL_F64, keys=KEYS, where=None, label=""):
+    """got/ref: dicts with packed arrays ([ncell,K] / [N,ncell,K]).  `where`: optional
+    index array of cells to compare (e.g. cell.domain)."""
+    for k in keys:
+        if ref.get(k) is None or got.get(k) is None:
+            continue
+        a, b = np.asarray(got[k]), np.asarray(ref[k])
+        if where is not None:
+            a, b = a[..., where, :], b[..., where, :]
+        e = metric_err(a, b, has_j=k != "face_cons")
+        assert e <= rtol, f"{label} {k}: rel err {e:.3e} > {rtol:.1e}"
+
+
+def domain_indices(nfull, nhalo, shrink_axis=None):
+    """Linear (Fortran) indices of cell.domain; optionally expand(domain, axis, -1)."""
+    rngs = []
+    for d, n in enumerate(nfull):
+        lo, hi = nhalo, n - nhalo
+        if shrink_axis is not None and d == shrink_axis:
+            lo, hi = lo + 1, hi - 1
+        rngs.append(np.arange(lo, hi))
+    mesh = np.meshgrid(*rngs, indexing="ij")
+    lin = np.zeros_like(mesh[0])
+    stride = 1
+    for d, n in enumerate(nfull):
+        lin = lin + mesh[d] * stride
+        stride *= n
+    return lin.ravel(order="F")
+
+
+def grid_outputs(cg, grid):
+    """Copy a grid's FULL-profile outputs to packed numpy arrays like the oracle's."""
+    N = grid.dim
+    cm = cg.cell_metrics(grid)
+    fm = cg.face_metrics(grid)
+    KM = N * N + 1
+    out = {
+        "cell_fwd": cm.forward.reshape(-1, KM).cpu().numpy(),
+        "cell_inv": cm.inverse.reshape(-1, KM).cpu().numpy(),
+        "face_fwd": np.stack([f.forward.reshape(-1, KM).cpu().numpy() for f in fm]),
+        "face_inv": np.stack([f.inverse.reshape(-1, KM).cpu().numpy() for f in fm]),
+        "face_cons": np.stack([f.conserved.reshape(-1, N * N).cpu().numpy() for f in fm]),
+        "nfull": grid.nfull,
+    }
+    return out
+
+
+def mild_nodes(shape, seed=0, amp=0.08, noise=0.01):
+    """Well-conditioned curvilinear test mesh: unit-spaced lattice + smooth waves +
+    seeded noise (SURVEY.md §8d robustness set, numpy.random.default_rng(seed))."""
+    rng = np.random.default_rng(seed)
+    dim = len(shape)
+    idx = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in shape], indexing="ij")
+    out = []
+    for c in range(dim):
+        q = (0.7 + 0.2 * c) * idx[c]
+        for d in range(dim):
+            if d != c:
+                q = q + amp * np.sin(0.9 * idx[d] + 0.3 * c) * np.cos(0.5 * idx[(d + 1) % dim])
+        q = q + 0.05 * idx[(c + 1) % dim]  # shear
+        q = q + noise * rng.standard_normal(shape)
+        out.append(np.asfortranarray(q))
+    return out
