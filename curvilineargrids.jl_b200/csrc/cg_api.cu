@@ -286,11 +286,19 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
       nl = 1;
     }
   } else {
-    if (g->kernel_opt == 1 && cg::tiled3d_supported<T>(D, O))
-      nl = cg::launch_metrics3d_tiled<T>(D, ex, ey, ez, O, g->scheme, what, st);
-    else {
-      cg::k_metrics3d_ref<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, ex, ey, ez, O, g->scheme, what);
+    // kernel_opt: 0 gather only, 1 all marching kernels, 16+mask = marching kernels for the axes in mask
+    // (bit0 xi+cell, bit1 eta, bit2 zeta) and the gather kernel for the rest (development cross-checks)
+    int mask = g->kernel_opt == 1 ? 7 : (g->kernel_opt >= 16 ? (g->kernel_opt - 16) & 7 : 0);
+    if (!cg::tiled3d_supported<T>(D, O)) mask = 0;
+    if (mask != 7) {
+      const int rest = (~mask & 7) | ((mask & 1) ? 0 : 8);
+      cg::k_metrics3d_ref<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, ex, ey, ez, O, g->scheme, what, rest);
       nl = 1;
+    }
+    if (mask) {
+      int n2 = cg::launch_metrics3d_tiled<T>(D, ex, ey, ez, O, g->scheme, what, mask, st);
+      if (n2 < 0) return fail(CG_ERR_CUDA, "marching kernel launch failed");
+      nl += n2;
     }
   }
   if (nl < 0) return fail(CG_ERR_CUDA, "tiled kernel launch failed");
@@ -395,7 +403,7 @@ int cg_grid_destroy(cg_grid* g) {
 int cg_grid_set_option(cg_grid* g, int option, int64_t value) {
   if (!g) return fail(CG_ERR_ARG, "NULL grid");
   if (option == CG_OPT_KERNEL) {
-    if (value != 0 && value != 1) return fail(CG_ERR_ARG, "CG_OPT_KERNEL must be 0 or 1");
+    if (value != 0 && value != 1 && !(value >= 16 && value < 24)) return fail(CG_ERR_ARG, "CG_OPT_KERNEL must be 0 or 1");
     g->kernel_opt = (int)value;
     return CG_OK;
   }

@@ -408,7 +408,7 @@ CG_HD void store_metric3(T* o, const T (&M)[3][3], T J) {
 
 template <class T>
 __global__ void k_metrics3d_ref(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O, int scheme,
-                                int what) {
+                                int what, int axis_mask = 15 /* bit f: face axis f, bit 3: cell */) {
   Ext3<T> X;
   X.q[0] = ex; X.q[1] = ey; X.q[2] = ez;
   X.st[0] = D.se[0]; X.st[1] = D.se[1]; X.st[2] = D.se[2];
@@ -428,7 +428,7 @@ __global__ void k_metrics3d_ref(Dims D, const T* ex, const T* ey, const T* ez, M
 #pragma unroll
       for (int d = 0; d < 3; ++d) F[q][d] = Tq[q][1 << d];
     inv3(F, G);
-    if (what & 1) {
+    if ((what & 1) && (axis_mask & 8)) {
       T dl[3] = {clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]),
                  clamp_delta<T>(D.w0[2] + k, D.nhalo, D.gn[2])};
       T Ff[3][3];
@@ -447,6 +447,7 @@ __global__ void k_metrics3d_ref(Dims D, const T* ex, const T* ey, const T* ez, M
     }
     if (!(what & 2)) continue;
     for (int f = 0; f < 3; ++f) {
+      if (!((axis_mask >> f) & 1)) continue;
       const int s = (f + 1) % 3, t = (f + 2) % 3;
       // ---- reconstructed inverse Jacobian, forward = inv, J = det(forward) ----
       if (O.face_fwd[f] || O.face_inv[f]) {

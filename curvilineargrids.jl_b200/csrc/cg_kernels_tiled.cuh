@@ -1,10 +1,691 @@
-// Tiled / marching kernels (the fast path).  Placeholder until the tiled kernels land:
-// reports "unsupported" so cg_grid_eval uses the gather kernels.
+// Marching kernels for the 3-D DiscreteGrid metric fill (the fast path) and the
+// coalesced 2-D kernel.
+//
+// Replaces /root/reference/src/grids/unified_grids/metrics.jl:1850-1877 (cell
+// fill) and :1962-2053 (three face fills) with three warp-autonomous kernels, one
+// per face axis (the xi kernel also writes the cell metrics):
+//   * a warp owns 29 consecutive cells of one j-row (lanes 1..29; lane 0 and lanes
+//     30/31 are the -1 / +1,+2 neighbours the stencil needs) and marches along k;
+//   * xi-neighbours come from warp shuffles, eta-neighbours are recomputed from
+//     the node rows (L1 hits), zeta-neighbours are carried in registers from the
+//     previous plane or looked ahead one plane;
+//   * no shared memory, no block barriers: warps never wait for each other.
+// Math: DESIGN.md §3 (edge scalars Psi + 4-cell line stencils), same closed forms
+// as tests/closed_form_numpy.py and the gather kernels in cg_kernels_ref.cuh.
 #pragma once
+#include <cuda_runtime.h>
+
 #include "cg_kernels_ref.cuh"
+
 namespace cg {
-template <class T> inline bool tiled2d_supported(const Dims&, const MetricOut<T>&) { return false; }
-template <class T> inline bool tiled3d_supported(const Dims&, const MetricOut<T>&) { return false; }
-template <class T> inline int launch_metrics2d_tiled(const Dims&, const T*, const T*, const MetricOut<T>&, int, int, cudaStream_t) { return -1; }
-template <class T> inline int launch_metrics3d_tiled(const Dims&, const T*, const T*, const T*, const MetricOut<T>&, int, int, cudaStream_t) { return -1; }
+
+#define CG_D __device__ __forceinline__
+constexpr int WARP_OUT = 29;  // output cells per warp along xi
+constexpr unsigned FULLMASK = 0xffffffffu;
+
+template <class T>
+struct PF {
+  Form4<T> q[3];
+};
+template <class T>
+struct NodeP {
+  const T* q[3];
+  int64_t s1, s2;
+};
+
+template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
+
+// zeta-plane forms (fixed k), transverse (xi, eta)
+template <class T>
+CG_D PF<T> zplane(const NodeP<T>& N, int64_t b) {
+  PF<T> f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const T* A = N.q[q] + b;
+    f.q[q] = face_form(ldn(A), ldn(A + 1), ldn(A + N.s1), ldn(A + N.s1 + 1));
+  }
+  return f;
+}
+// eta-plane forms (fixed j), transverse (xi, zeta)
+template <class T>
+CG_D PF<T> eplane(const NodeP<T>& N, int64_t b) {
+  PF<T> f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const T* A = N.q[q] + b;
+    f.q[q] = face_form(ldn(A), ldn(A + 1), ldn(A + N.s2), ldn(A + N.s2 + 1));
+  }
+  return f;
+}
+// xi-plane forms (fixed i), transverse (eta, zeta)
+template <class T>
+CG_D PF<T> xplane(const NodeP<T>& N, int64_t b) {
+  PF<T> f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const T* A = N.q[q] + b;
+    f.q[q] = face_form(ldn(A), ldn(A + N.s1), ldn(A + N.s2), ldn(A + N.s1 + N.s2));
+  }
+  return f;
+}
+template <class T>
+CG_D PF<T> swap_uv(const PF<T>& p) {
+  PF<T> o;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) o.q[q] = {p.q[q].c0, p.q[q].cv, p.q[q].cu, p.q[q].cuv};
+  return o;
+}
+
+// cell Taylor coefficients from the two zeta-planes of the cell (bitmask: 1 xi, 2 eta, 4 zeta)
+template <class T>
+CG_D void taylor_from_z(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    c[q][0] = T(0.5) * (lo.q[q].c0 + hi.q[q].c0);
+    c[q][1] = T(0.5) * (lo.q[q].cu + hi.q[q].cu);
+    c[q][2] = T(0.5) * (lo.q[q].cv + hi.q[q].cv);
+    c[q][3] = T(0.5) * (lo.q[q].cuv + hi.q[q].cuv);
+    c[q][4] = hi.q[q].c0 - lo.q[q].c0;
+    c[q][5] = hi.q[q].cu - lo.q[q].cu;
+    c[q][6] = hi.q[q].cv - lo.q[q].cv;
+    c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
+  }
+}
+
+// Half states W+-_f of the six E^a polynomials on the a-face between cells c and
+// c+a.  P0/P1/P2: forms on the low face of c, the shared face, the high face of
+// c+a, Form4 ordered (u = f, v = t).  Index = bsel*3 + col, bsel 0: b = f, 1: b = t;
+// col selects (q1,q2) = (col+1, col+2) mod 3.       
+template <class T, int SCH>
+CG_D void eface6(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, T (&wp)[6], T (&wm)[6]) {
+  if (SCH == ENDPOINT) {
+    // E = 1/2 (P_c + P_{c+a}) with cell-centre values; W+ = W- = E/2
+    T q0c[3], q0n[3], qfc[3], qfn[3], qtc[3], qtn[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      q0c[q] = T(0.5) * (P0.q[q].c0 + P1.q[q].c0);
+      q0n[q] = T(0.5) * (P1.q[q].c0 + P2.q[q].c0);
+      qfc[q] = T(0.5) * (P0.q[q].cu + P1.q[q].cu);
+      qfn[q] = T(0.5) * (P1.q[q].cu + P2.q[q].cu);
+      qtc[q] = T(0.5) * (P0.q[q].cv + P1.q[q].cv);
+      qtn[q] = T(0.5) * (P1.q[q].cv + P2.q[q].cv);
+    }
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+      wp[col] = wm[col] = T(0.25) * (qfc[q1] * q0c[q2] + qfn[q1] * q0n[q2]);
+      wp[3 + col] = wm[3 + col] = T(0.25) * (qtc[q1] * q0c[q2] + qtn[q1] * q0n[q2]);
+    }
+    return;
+  }
+  const T lam1 = T(0.5), lam2 = SCH == CURVATURE ? T(1.0 / 12.0) : T(0);
+  const T k2 = T(0.125) - lam2;  // 2*kappa
+  Form4<T> dA[3], dB[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    dA[q] = form_dif(P1.q[q], P0.q[q]);
+    dB[q] = form_dif(P2.q[q], P1.q[q]);
+  }
+#pragma unroll
+  for (int col = 0; col < 3; ++col) {
+    const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+    const Form4<T>&A1 = P1.q[q1], &B1 = P1.q[q2];
+    const Form4<T>&a0 = dA[q1], &b0 = dA[q2], &a1 = dB[q1], &b1 = dB[q2];
+    // b = f
+    T e0 = A1.cu * B1.c0 - k2 * (a0.cu * b0.c0 + a1.cu * b1.c0);
+    T e1 = A1.cu * B1.cu - k2 * (a0.cu * b0.cu + a1.cu * b1.cu);
+    T h0 = T(0.5) * e0, h1 = (T(0.5) * lam1) * e1;
+    wp[col] = h0 + h1;
+    wm[col] = h0 - h1;
+    // b = t
+    e0 = A1.cv * B1.c0 - k2 * (a0.cv * b0.c0 + a1.cv * b1.c0);
+    e1 = A1.cv * B1.cu + A1.cuv * B1.c0 - k2 * (a0.cv * b0.cu + a0.cuv * b0.c0 + a1.cv * b1.cu + a1.cuv * b1.c0);
+    T e2 = A1.cuv * B1.cu - k2 * (a0.cuv * b0.cu + a1.cuv * b1.cu);
+    h0 = T(0.5) * e0 + lam2 * e2;
+    h1 = (T(0.5) * lam1) * e1;
+    wp[3 + col] = h0 + h1;
+    wm[3 + col] = h0 - h1;
+  }
+}
+
+template <class T> CG_D T shfl_dn(T v, int d) { return __shfl_down_sync(FULLMASK, v, d); }
+template <class T> CG_D T shfl_up(T v, int d) { return __shfl_up_sync(FULLMASK, v, d); }
+
+// line scalars of the potential (d_b q1) q2 along axis f from the cell's Taylor coefficients
+template <class T>
+CG_D LineS<T> line_from_taylor(const T (&c)[3][8], int q1, int q2, int f, int b, T lam1, T lam2) {
+  const int mb = 1 << b, mf = 1 << f;
+  T p0 = c[q1][mb] * c[q2][0];
+  T p1 = c[q1][mb] * c[q2][mf] + c[q1][mb | mf] * c[q2][0];
+  T p2 = c[q1][mb | mf] * c[q2][mf];
+  return line_scalars(p0, p1, p2, lam1, lam2);
+}
+
+template <class T>
+CG_D void store10(T* o, const T (&M)[3][3], T J) {
+  // element = 80 B (FP64) and 16-B aligned: five 16-B stores
+  if (sizeof(T) == 8) {
+    double2* p = reinterpret_cast<double2*>(o);
+    p[0] = make_double2(M[0][0], M[1][0]);
+    p[1] = make_double2(M[2][0], M[0][1]);
+    p[2] = make_double2(M[1][1], M[2][1]);
+    p[3] = make_double2(M[0][2], M[1][2]);
+    p[4] = make_double2(M[2][2], J);
+  } else {
+    o[0] = M[0][0]; o[1] = M[1][0]; o[2] = M[2][0];
+    o[3] = M[0][1]; o[4] = M[1][1]; o[5] = M[2][1];
+    o[6] = M[0][2]; o[7] = M[1][2]; o[8] = M[2][2];
+    o[9] = J;
+  }
+}
+template <class T>
+CG_D void store9(T* o, const T (&M)[3][3]) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[r + 3 * c] = M[r][c];
+}
+
+struct March {
+  int64_t i, ic, j;
+  int lane;
+  bool out_ok;
+};
+
+// ===========================================================================
+// Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
+// ===========================================================================
+template <class T, int SCH>
+__global__ void __launch_bounds__(128) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+                                                 int what, int kchunk) {
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= nw1) return;  // whole warp
+  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
+  const int64_t ic = i > nw0 + 1 ? nw0 + 1 : i;
+  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  NodeP<T> N;
+  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
+  N.s1 = D.se[1]; N.s2 = D.se[2];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const bool do_cell = what & 1, do_face = what & 2;
+  const bool full = O.face_cons[0] != nullptr;
+  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
+  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+
+  T psi_bot[6];
+  if (do_face) {
+    T wp[6], wm[6];
+    const int64_t b = nbase + (k0 - 1) * N.s2;
+    eface6<T, SCH>(zplane(N, b), zplane(N, b + N.s2), zplane(N, b + 2 * N.s2), wp, wm);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + shfl_dn(wm[e], 1);
+  }
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t b = nbase + m * N.s2;
+    const int64_t cl = i + j * cs1 + m * cs2;
+    PF<T> z0 = zplane(N, b), z1 = zplane(N, b + N.s2);
+    T c[3][8];
+    taylor_from_z(z0, z1, c);
+    T F[3][3], G[3][3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+    inv3(F, G);
+    if (do_cell) {
+      T dl[3] = {clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]),
+                 clamp_delta<T>(D.w0[2] + m, D.nhalo, D.gn[2])};
+      T Ff[3][3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const int e = (d + 1) % 3, g = (d + 2) % 3;
+          Ff[q][d] = c[q][1 << d] + c[q][(1 << d) | (1 << e)] * dl[e] + c[q][(1 << d) | (1 << g)] * dl[g] +
+                     c[q][7] * dl[e] * dl[g];
+        }
+      T J = det3(Ff);
+      if (out_ok) {
+        if (O.cell_fwd) store10(O.cell_fwd + 10 * cl, Ff, J);
+        if (O.cell_inv) store10(O.cell_inv + 10 * cl, G, J);
+        if (O.cjac) O.cjac[cl] = J;
+      }
+    }
+    if (!do_face) continue;
+    // ---- zeta-direction edge scalars: top face (m + 1/2), looked ahead one plane ----
+    T psi_top[6];
+    {
+      T wp[6], wm[6];
+      eface6<T, SCH>(z0, z1, zplane(N, b + 2 * N.s2), wp, wm);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) psi_top[e] = wp[e] + shfl_dn(wm[e], 1);
+    }
+    // ---- eta-direction edge scalars on both eta faces of the cell ----
+    T dpsi_eta[6];
+    {
+      PF<T> e0 = eplane(N, b - N.s1), e1 = eplane(N, b), e2 = eplane(N, b + N.s1), e3 = eplane(N, b + 2 * N.s1);
+      T wp[6], wm[6], wq[6], wn[6];
+      eface6<T, SCH>(e1, e2, e3, wp, wm);  // face j + 1/2
+      eface6<T, SCH>(e0, e1, e2, wq, wn);  // face j - 1/2
+#pragma unroll
+      for (int e = 0; e < 6; ++e) dpsi_eta[e] = (wp[e] - wq[e]) + shfl_dn(wm[e] - wn[e], 1);
+    }
+    T Gh[3][3];
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      Gh[0][col] = (psi_top[3 + col] - psi_bot[3 + col]) - dpsi_eta[3 + col];
+      Gh[1][col] = -(psi_top[col] - psi_bot[col]);
+      Gh[2][col] = dpsi_eta[col];
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) psi_bot[e] = psi_top[e];
+    if (O.cactive[0] && out_ok) {
+      T* o = O.cactive[0] + 3 * cl;
+      o[0] = Gh[0][0]; o[1] = Gh[0][1]; o[2] = Gh[0][2];
+    }
+    if (!full) continue;
+    // ---- xi line stencils (neighbours by shuffle): rows eta (+, b = zeta) and zeta (-, b = eta) ----
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+#pragma unroll
+      for (int bb = 1; bb <= 2; ++bb) {
+        LineS<T> s = line_from_taylor(c, q1, q2, 0, bb, lam1, lam2);
+        T v = (s.vp - T(2) * s.u) - shfl_up(s.vp, 1) + shfl_dn(T(2) * s.u - s.vm, 1) + shfl_dn(s.vm, 2);
+        if (bb == 2) Gh[1][col] += T(0.5) * v;
+        else Gh[2][col] -= T(0.5) * v;
+      }
+    }
+    // ---- reconstructed inverse Jacobian on the xi face ----
+    T Fp[3][3], L[3][3], R[3][3], Gf[3][3], Ff[3][3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      Fp[q][0] = T(0);
+      Fp[q][1] = c[q][3];
+      Fp[q][2] = c[q][5];
+    }
+    ginv_states3(G, Fp, lam1, lam2, L, R);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
+    inv3(Gf, Ff);
+    T Jf = det3(Ff);
+    if (out_ok) {
+      store10(O.face_fwd[0] + 10 * cl, Ff, Jf);
+      store10(O.face_inv[0] + 10 * cl, Gf, Jf);
+      store9(O.face_cons[0] + 9 * cl, Gh);
+    }
+  }
+}
+
+// ===========================================================================
+// Kernel B: eta-face metrics.  f = eta, s = zeta, t = xi.
+//   active row eta : +dPsi^{xi->eta}[b=zeta] across xi  - dPsi^{zeta->eta}[b=xi] across zeta
+//   row zeta       : +line_eta[b=xi]                     - dPsi^{xi->eta}[b=eta] across xi
+//   row xi         : +dPsi^{zeta->eta}[b=eta] across zeta - line_eta[b=zeta]
+// ===========================================================================
+template <class T, int SCH>
+__global__ void __launch_bounds__(128) k_face_eta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+                                                  int kchunk) {
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= nw1) return;
+  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
+  const int64_t ic = i > nw0 ? nw0 : i;  // this kernel reads node columns ic .. ic+2
+  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  NodeP<T> N;
+  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
+  N.s1 = D.se[1]; N.s2 = D.se[2];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const bool full = O.face_cons[1] != nullptr;
+  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
+  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+
+  // Psi^{zeta->eta} on the xi-edge (j+1/2, m-1/2): zeta faces of cells j and j+1, reconstructed along eta
+  auto psi_zeta = [&](int64_t b, T (&psi)[6]) {
+    // b = node (ic, j, plane below the face's lower cell)
+    T wp[6], wm[6], wq[6], wn[6];
+    eface6<T, SCH>(swap_uv(zplane(N, b)), swap_uv(zplane(N, b + N.s2)), swap_uv(zplane(N, b + 2 * N.s2)), wp, wm);
+    const int64_t bn = b + N.s1;
+    eface6<T, SCH>(swap_uv(zplane(N, bn)), swap_uv(zplane(N, bn + N.s2)), swap_uv(zplane(N, bn + 2 * N.s2)), wq, wn);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) psi[e] = wp[e] + wn[e];
+  };
+  T psi_bot[6];
+  psi_zeta(nbase + (k0 - 1) * N.s2, psi_bot);
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t b = nbase + m * N.s2;
+    const int64_t cl = i + j * cs1 + m * cs2;
+    T psi_top[6];
+    psi_zeta(b, psi_top);
+    // Psi^{xi->eta} on the zeta-edge (i+1/2, j+1/2): xi faces (i+1/2) of rows j and j+1, reconstructed along eta
+    T psi_x[6];
+    {
+      T wp[6], wm[6], wq[6], wn[6];
+      eface6<T, SCH>(xplane(N, b), xplane(N, b + 1), xplane(N, b + 2), wp, wm);
+      const int64_t bn = b + N.s1;
+      eface6<T, SCH>(xplane(N, bn), xplane(N, bn + 1), xplane(N, bn + 2), wq, wn);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) psi_x[e] = wp[e] + wn[e];
+    }
+    T Gh[3][3];  // rows: 0 xi, 1 eta, 2 zeta
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      // a = xi (= t, sigma +1, a' = zeta): bsel 1 is b = zeta, bsel 0 is b = eta
+      T dxa = psi_x[3 + col] - shfl_up(psi_x[3 + col], 1);
+      T dxf = psi_x[col] - shfl_up(psi_x[col], 1);
+      // a = zeta (= s, sigma -1, a' = xi): bsel 1 is b = xi, bsel 0 is b = eta
+      Gh[1][col] = dxa - (psi_top[3 + col] - psi_bot[3 + col]);
+      Gh[2][col] = -dxf;
+      Gh[0][col] = psi_top[col] - psi_bot[col];
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) psi_bot[e] = psi_top[e];
+    if (O.cactive[1] && out_ok) {
+      T* o = O.cactive[1] + 3 * cl;
+      o[0] = Gh[1][0]; o[1] = Gh[1][1]; o[2] = Gh[1][2];
+    }
+    if (!full) continue;
+    // ---- eta line stencils: cells j-1 .. j+2 recomputed from the eta-planes j-1 .. j+3 ----
+    {
+      PF<T> r0 = eplane(N, b - N.s1), r1 = eplane(N, b), r2 = eplane(N, b + N.s1), r3 = eplane(N, b + 2 * N.s1),
+            r4 = eplane(N, b + 3 * N.s1);
+      const PF<T>* rows[5] = {&r0, &r1, &r2, &r3, &r4};
+      // eta-plane forms are (u,v) = (xi,zeta): q_xi = cu, q_zeta = cv, eta-derivative = difference of rows
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+        T accx = T(0), accz = T(0);  // b = xi (row zeta, +) and b = zeta (row xi, -)
+#pragma unroll
+        for (int cell = 0; cell < 4; ++cell) {
+          const Form4<T>&Alo = rows[cell]->q[q1], &Ahi = rows[cell + 1]->q[q1];
+          const Form4<T>&Blo = rows[cell]->q[q2], &Bhi = rows[cell + 1]->q[q2];
+          T q20 = T(0.5) * (Blo.c0 + Bhi.c0), q2f = Bhi.c0 - Blo.c0;
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            T q1b = bb == 0 ? T(0.5) * (Alo.cu + Ahi.cu) : T(0.5) * (Alo.cv + Ahi.cv);
+            T q1bf = bb == 0 ? (Ahi.cu - Alo.cu) : (Ahi.cv - Alo.cv);
+            LineS<T> s = line_scalars(q1b * q20, q1b * q2f + q1bf * q20, q1bf * q2f, lam1, lam2);
+            T v = cell == 0 ? -s.vp : (cell == 1 ? (s.vp - T(2) * s.u) : (cell == 2 ? (T(2) * s.u - s.vm) : s.vm));
+            if (bb == 0) accx += v;
+            else accz += v;
+          }
+        }
+        Gh[2][col] += T(0.5) * accx;
+        Gh[0][col] -= T(0.5) * accz;
+      }
+    }
+    // ---- reconstructed inverse Jacobian on the eta face: cells j and j+1 ----
+    T Gf[3][3], Ff[3][3];
+    {
+      T L[3][3], R[3][3], R1[3][3];
+#pragma unroll
+      for (int cell = 0; cell < 2; ++cell) {
+        const int64_t bc = b + cell * N.s1;
+        T c[3][8];
+        taylor_from_z(zplane(N, bc), zplane(N, bc + N.s2), c);
+        T F[3][3], G[3][3], Fp[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+          Fp[q][0] = c[q][3];
+          Fp[q][1] = T(0);
+          Fp[q][2] = c[q][6];
+        }
+        inv3(F, G);
+        if (cell == 0) ginv_states3(G, Fp, lam1, lam2, L, R);
+        else ginv_states3(G, Fp, lam1, lam2, R, R1);  // R <- L of cell j+1 (unused), R1 <- R of cell j+1
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + R1[r][cc]);
+    }
+    inv3(Gf, Ff);
+    T Jf = det3(Ff);
+    if (out_ok) {
+      store10(O.face_fwd[1] + 10 * cl, Ff, Jf);
+      store10(O.face_inv[1] + 10 * cl, Gf, Jf);
+      store9(O.face_cons[1] + 9 * cl, Gh);
+    }
+  }
+}
+
+// ===========================================================================
+// Kernel C: zeta-face metrics.  f = zeta, s = xi, t = eta.  Marches with the
+// "front" cell p = m+1; the face (m + 1/2) is written at array plane m.
+//   active row zeta : +dPsi^{eta->zeta}[b=xi] across eta - dPsi^{xi->zeta}[b=eta] across xi
+//   row xi          : +line_zeta[b=eta]                   - dPsi^{eta->zeta}[b=zeta] across eta
+//   row eta         : +dPsi^{xi->zeta}[b=zeta] across xi  - line_zeta[b=xi]
+// ===========================================================================
+template <class T>
+struct CellZ {
+  T wpe[6];  // W+_zeta [E^eta(j+1/2)] - W+_zeta [E^eta(j-1/2)]   (difference across eta already taken)
+  T wme[6];
+  T wpx[6];  // W+_zeta [E^xi(i+1/2)]
+  T wmx[6];
+  LineS<T> ln[6];  // index = bb*3 + col; bb 0: b = xi, 1: b = eta
+  T L[3][3], R[3][3];
+};
+
+template <class T, int SCH>
+CG_D void cellz_compute(const NodeP<T>& N, int64_t b, bool full, T lam1, T lam2, CellZ<T>& o) {
+  // b = node (ic, j, p) of the cell's low corner
+  {
+    // eta faces j-1/2 and j+1/2: eta-planes j-1 .. j+2, forms (xi,zeta) -> need (u,v) = (zeta, xi)
+    PF<T> e0 = swap_uv(eplane(N, b - N.s1)), e1 = swap_uv(eplane(N, b)), e2 = swap_uv(eplane(N, b + N.s1)),
+          e3 = swap_uv(eplane(N, b + 2 * N.s1));
+    T wp[6], wm[6], wq[6], wn[6];
+    eface6<T, SCH>(e1, e2, e3, wp, wm);
+    eface6<T, SCH>(e0, e1, e2, wq, wn);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      o.wpe[e] = wp[e] - wq[e];
+      o.wme[e] = wm[e] - wn[e];
+    }
+  }
+  {
+    // xi face i+1/2: xi-planes i, i+1, i+2, forms (eta,zeta) -> need (u,v) = (zeta, eta)
+    eface6<T, SCH>(swap_uv(xplane(N, b)), swap_uv(xplane(N, b + 1)), swap_uv(xplane(N, b + 2)), o.wpx, o.wmx);
+  }
+  if (!full) return;
+  T c[3][8];
+  taylor_from_z(zplane(N, b), zplane(N, b + N.s2), c);
+#pragma unroll
+  for (int col = 0; col < 3; ++col) {
+    const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+    o.ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
+    o.ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
+  }
+  T F[3][3], G[3][3], Fp[3][3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+    Fp[q][0] = c[q][5];
+    Fp[q][1] = c[q][6];
+    Fp[q][2] = T(0);
+  }
+  inv3(F, G);
+  ginv_states3(G, Fp, lam1, lam2, o.L, o.R);
+}
+
+template <class T, int SCH>
+__global__ void __launch_bounds__(128) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+                                                   int kchunk) {
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= nw1) return;
+  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
+  const int64_t ic = i > nw0 ? nw0 : i;  // this kernel reads node columns ic .. ic+2
+  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  NodeP<T> N;
+  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
+  N.s1 = D.se[1]; N.s2 = D.se[2];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const bool full = O.face_cons[2] != nullptr;
+  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
+  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+
+  // carried state: W+ of the cell below the face, line partial sums, L state
+  T wpe[6], wpx[6], P1[6], vp_prev[6], Lp[3][3];
+  {
+    CellZ<T> cm;  // cell k0 - 1
+    if (full) {
+      cellz_compute<T, SCH>(N, nbase + (k0 - 1) * N.s2, true, lam1, lam2, cm);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) vp_prev[e] = cm.ln[e].vp;
+    }
+    CellZ<T> c0;  // cell k0
+    cellz_compute<T, SCH>(N, nbase + k0 * N.s2, full, lam1, lam2, c0);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      wpe[e] = c0.wpe[e];
+      wpx[e] = c0.wpx[e];
+      if (full) {
+        P1[e] = (c0.ln[e].vp - T(2) * c0.ln[e].u) - vp_prev[e];
+        vp_prev[e] = c0.ln[e].vp;
+      }
+    }
+    if (full) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Lp[r][cc] = c0.L[r][cc];
+    }
+  }
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t cl = i + j * cs1 + m * cs2;
+    CellZ<T> cf;  // front cell m + 1
+    cellz_compute<T, SCH>(N, nbase + (m + 1) * N.s2, full, lam1, lam2, cf);
+    T Gh[3][3];  // rows 0 xi, 1 eta, 2 zeta
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      // a = eta (= t, sigma +1, a' = xi): bsel 1 is b = xi, bsel 0 is b = zeta; difference across eta is in wpe/wme
+      T de_a = wpe[3 + col] + cf.wme[3 + col];
+      T de_f = wpe[col] + cf.wme[col];
+      // a = xi (= s, sigma -1, a' = eta): bsel 1 is b = eta, bsel 0 is b = zeta
+      T px_a = wpx[3 + col] + cf.wmx[3 + col];
+      T px_f = wpx[col] + cf.wmx[col];
+      T dx_a = px_a - shfl_up(px_a, 1);
+      T dx_f = px_f - shfl_up(px_f, 1);
+      Gh[2][col] = de_a - dx_a;
+      Gh[0][col] = -de_f;
+      Gh[1][col] = dx_f;
+    }
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      wpe[e] = cf.wpe[e];
+      wpx[e] = cf.wpx[e];
+    }
+    if (O.cactive[2] && out_ok) {
+      T* o = O.cactive[2] + 3 * cl;
+      o[0] = Gh[2][0]; o[1] = Gh[2][1]; o[2] = Gh[2][2];
+    }
+    if (!full) continue;
+    // zeta line stencil: cells m-1, m (in P1), m+1 (front), m+2 (looked ahead)
+    {
+      T c2[3][8];
+      const int64_t b2 = nbase + (m + 2) * N.s2;
+      taylor_from_z(zplane(N, b2), zplane(N, b2 + N.s2), c2);
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int e = bb * 3 + col;
+          LineS<T> s2 = line_from_taylor(c2, q1, q2, 2, bb, lam1, lam2);
+          T v = T(0.5) * (P1[e] + (T(2) * cf.ln[e].u - cf.ln[e].vm) + s2.vm);
+          if (bb == 1) Gh[0][col] += v;   // row xi: + line[b = eta]
+          else Gh[1][col] -= v;           // row eta: - line[b = xi]
+          P1[e] = (cf.ln[e].vp - T(2) * cf.ln[e].u) - vp_prev[e];
+          vp_prev[e] = cf.ln[e].vp;
+        }
+      }
+    }
+    T Gf[3][3], Ff[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        Gf[r][cc] = T(0.5) * (Lp[r][cc] + cf.R[r][cc]);
+        Lp[r][cc] = cf.L[r][cc];
+      }
+    inv3(Gf, Ff);
+    T Jf = det3(Ff);
+    if (out_ok) {
+      store10(O.face_fwd[2] + 10 * cl, Ff, Jf);
+      store10(O.face_inv[2] + 10 * cl, Gf, Jf);
+      store9(O.face_cons[2] + 9 * cl, Gh);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+template <class T>
+inline bool tiled3d_supported(const Dims& D, const MetricOut<T>&) { return D.dim == 3; }
+template <class T>
+inline bool tiled2d_supported(const Dims&, const MetricOut<T>&) { return false; }
+template <class T>
+inline int launch_metrics2d_tiled(const Dims&, const T*, const T*, const MetricOut<T>&, int, int, cudaStream_t) {
+  return -1;
+}
+
+// mask: bit0 xi kernel (+cell), bit1 eta kernel, bit2 zeta kernel
+template <class T, int SCH>
+inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez, const MetricOut<T>& O, int what,
+                           int mask, cudaStream_t st) {
+  const int WY = 4;
+  // enough k-chunks to fill the machine a few times over, but long enough to amortise the prologue
+  int64_t tiles = ((D.nw[0] + WARP_OUT - 1) / WARP_OUT) * ((D.nw[1] + WY - 1) / WY);
+  int kchunk = (int)D.nw[2];
+  const int64_t want = 148LL * 16;
+  if (tiles < want) {
+    int64_t nchunks = (want + tiles - 1) / tiles;
+    kchunk = (int)((D.nw[2] + nchunks - 1) / nchunks);
+    if (kchunk < 16) kchunk = 16;
+    if (kchunk > D.nw[2]) kchunk = (int)D.nw[2];
+  }
+  dim3 block(32, WY);
+  dim3 grid((unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), (unsigned)((D.nw[1] + WY - 1) / WY),
+            (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
+  int n = 0;
+  const bool face = what & 2;
+  if ((mask & 1) && ((what & 1) || face)) {
+    k_face_xi<T, SCH><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
+    ++n;
+  }
+  if ((mask & 2) && face) {
+    k_face_eta<T, SCH><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+    ++n;
+  }
+  if ((mask & 4) && face) {
+    k_face_zeta<T, SCH><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+    ++n;
+  }
+  return n;
+}
+
+template <class T>
+inline int launch_metrics3d_tiled(const Dims& D, const T* ex, const T* ey, const T* ez, const MetricOut<T>& O,
+                                  int scheme, int what, int mask, cudaStream_t st) {
+  if (scheme == ENDPOINT) return launch3d_scheme<T, ENDPOINT>(D, ex, ey, ez, O, what, mask, st);
+  if (scheme == GRADIENT) return launch3d_scheme<T, GRADIENT>(D, ex, ey, ez, O, what, mask, st);
+  return launch3d_scheme<T, CURVATURE>(D, ex, ey, ez, O, what, mask, st);
+}
+
 }  // namespace cg

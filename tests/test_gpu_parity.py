@@ -36,6 +36,16 @@ def test_discrete_matches_oracle(cg, oracle, shape, nhalo, scheme, kernel):
     assert_metrics_close(got, ref, rtol=RTOL_F64, label=f"{shape} h={nhalo} {scheme} k{kernel}")
 
 
+@pytest.mark.parametrize("kernel", (17, 18, 20))
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_each_marching_kernel_alone(cg, oracle, scheme, kernel):
+    """Development masks: one marching kernel (xi+cell / eta / zeta) + gather for the other axes."""
+    nodes = mild_nodes((37, 9, 8), seed=21)   # > 29 cells along xi: two warp tiles
+    ref = oracle.discrete_eval(nodes, 2, scheme)
+    g = _make(cg, nodes, 2, scheme, kernel)
+    assert_metrics_close(grid_outputs(cg, g), ref, rtol=RTOL_F64, label=f"mask {kernel - 16} {scheme}")
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_halo_coords_included_discards_caller_halo(cg, oracle, kernel):
     """discrete_grid.jl:55-61, 556-566: the caller's halo nodes are stripped and re-created
@@ -170,7 +180,8 @@ def test_3d_128_sampled_oracle_and_kernel_crosscheck(cg, oracle):
     g0 = _make(cg, nodes, h, "curvature", 0)
     o0 = grid_outputs(cg, g0)
     dom = domain_indices(o1["nfull"], h)
-    assert_metrics_close(o1, o0, rtol=RTOL_F64, where=dom, label="tiled vs gather")
+    # two independently rounded evaluations, each within 1e-12 of the exact value
+    assert_metrics_close(o1, o0, rtol=4 * RTOL_F64, where=dom, label="tiled vs gather")
 
 
 def test_2d_1024_gradient_properties(cg, oracle):
