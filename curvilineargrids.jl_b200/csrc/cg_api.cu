@@ -170,27 +170,123 @@ int pad_nodes(cg_grid* g, cudaStream_t st) {
   return CG_OK;
 }
 
+
+template <class T>
+int bind_coord_outputs(cg_grid* g, cg::CoordOut<T>& C) {
+  const int N = g->dim;
+  memset(&C, 0, sizeof C);
+  size_t b;
+  for (int q = 0; q < N; ++q) {
+    Buf* nb = select(g, CG_ARR_NODE_COORD, q, &b);
+    int rc = ensure(g, *nb, b);
+    if (rc) return rc;
+    C.node[q] = (T*)nb->p;
+    Buf* cb = select(g, CG_ARR_CENTROID_COORD, q, &b);
+    rc = ensure(g, *cb, b);
+    if (rc) return rc;
+    C.centroid[q] = (T*)cb->p;
+    for (int a = 0; a < N; ++a) {
+      Buf* fb = select(g, CG_ARR_FACE_COORD, 3 * a + q, &b);
+      rc = ensure(g, *fb, b);
+      if (rc) return rc;
+      C.face[a][q] = (T*)fb->p;
+    }
+  }
+  return CG_OK;
+}
+
+template <class T>
+int bind_metric_outputs(cg_grid* g, int what, cg::MetricOut<T>& O) {
+  const int N = g->dim;
+  memset(&O, 0, sizeof O);
+  size_t b;
+  auto get = [&](int arr, int ax, T** dst) -> int {
+    Buf* p = select(g, arr, ax, &b);
+    int rc = ensure(g, *p, b);
+    if (rc) return rc;
+    *dst = (T*)p->p;
+    return CG_OK;
+  };
+  int rc = CG_OK;
+  if (g->profile == CG_PROFILE_FULL) {
+    if (what & CG_WHAT_CELL) {
+      if ((rc = get(CG_ARR_CELL_FORWARD, 0, &O.cell_fwd))) return rc;
+      if ((rc = get(CG_ARR_CELL_INVERSE, 0, &O.cell_inv))) return rc;
+    }
+    if (what & CG_WHAT_FACE)
+      for (int a = 0; a < N; ++a) {
+        if ((rc = get(CG_ARR_FACE_FORWARD, a, &O.face_fwd[a]))) return rc;
+        if ((rc = get(CG_ARR_FACE_INVERSE, a, &O.face_inv[a]))) return rc;
+        if ((rc = get(CG_ARR_FACE_CONSERVED, a, &O.face_cons[a]))) return rc;
+      }
+  } else {
+    if (what & CG_WHAT_CELL)
+      if ((rc = get(CG_ARR_COMPACT_J, 0, &O.cjac))) return rc;
+    if (what & CG_WHAT_FACE)
+      for (int a = 0; a < N; ++a)
+        if ((rc = get(CG_ARR_COMPACT_ACTIVE, a, &O.cactive[a]))) return rc;
+  }
+  return CG_OK;
+}
+
+int start_timer(cg_grid* g, cudaStream_t st) {
+  if (!g->ev0) {
+    CG_CUDA(cudaEventCreate(&g->ev0));
+    CG_CUDA(cudaEventCreate(&g->ev1));
+  }
+  CG_CUDA(cudaEventRecord(g->ev0, st));
+  return CG_OK;
+}
+
+// MappedGrid: 1-D operator tables (once per update) + the table-driven metric kernel
+template <class T>
+int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
+  const int N = g->dim;
+  cg::Dims D = g->dims();
+  int rc = cg::mapped_prepare<T>(g->mtab, g->terms, g->t, D, g->scheme, st);
+  if (rc == 1) return fail(CG_ERR_ARG, "mapping has too many terms (max %d)", cg::M_MAXT - 1);
+  if (rc == 2) return fail(CG_ERR_ARG, "mapping has too many term pairs (max %d)", cg::M_MAXP);
+  if (rc) return fail(CG_ERR_CUDA, "mapped_prepare: %s", cudaGetErrorString(cudaGetLastError()));
+  g_launches += g->mtab.launches;
+  g->mtab.launches = 0;
+  cg::MTerms TM = g->mtab.terms;
+  if (what & CG_WHAT_COORDS) {
+    cg::CoordOut<T> C;
+    if ((rc = bind_coord_outputs<T>(g, C))) return rc;
+    cg::k_mapped_coords<T><<<launch_blocks(g->nnodes(), 128), 128, 0, st>>>(D, TM, C);
+    g_launches++;
+    CG_CUDA(cudaGetLastError());
+    g->valid_coords = true;
+  }
+  if (!(what & (CG_WHAT_CELL | CG_WHAT_FACE))) return CG_OK;
+  cg::MetricOut<T> O;
+  if ((rc = bind_metric_outputs<T>(g, what, O))) return rc;
+  if ((rc = start_timer(g, st))) return rc;
+  const int64_t nc = g->ncells();
+  const T* tab = (const T*)g->mtab.tab;
+  const T* ftab = (const T*)g->mtab.ftab;
+  if (N == 1)
+    cg::k_mapped_metrics1d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, ftab, g->mtab.L, O, g->scheme, what);
+  else if (N == 2)
+    cg::k_mapped_metrics2d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
+                                                                      g->scheme, what);
+  else
+    cg::k_mapped_metrics3d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
+                                                                      g->scheme, what);
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  CG_CUDA(cudaEventRecord(g->ev1, st));
+  g->timed = true;
+  if (what & CG_WHAT_CELL) g->valid_cell = true;
+  if (what & CG_WHAT_FACE) g->valid_face = true;
+  return CG_OK;
+}
+
 template <class T>
 int eval_impl(cg_grid* g, int what, cudaStream_t st) {
   const int N = g->dim;
   if (g->kind == 0) return fail(CG_ERR_STATE, "cg_grid_eval: no nodes or mapping set");
-  if (g->kind == 2) {
-    int rc = cg::mapped_prepare<T>(g->mtab, g->terms, g->t, g->dims(), st);
-    if (rc) return fail(CG_ERR_CUDA, "mapped_prepare failed (%d)", rc);
-    g_launches += g->mtab.launches;
-    g->mtab.launches = 0;
-    // MappedGrid node coordinates feed the same padded-array layout (nodes evaluated analytically)
-    const size_t bytes = (size_t)g->next() * sizeof(T);
-    for (int q = 0; q < N; ++q) {
-      int r2 = ensure(g, g->ext[q], bytes);
-      if (r2) return r2;
-    }
-    cg::k_mapped_nodes<T><<<launch_blocks(g->next(), 256), 256, 0, st>>>(g->dims(), g->mtab.dev(), (T*)g->ext[0].p,
-                                                                        (T*)g->ext[1].p, (T*)g->ext[2].p);
-    g_launches++;
-    CG_CUDA(cudaGetLastError());
-    g->ext_valid = true;
-  }
+  if (g->kind == 2) return eval_mapped<T>(g, what, st);
   if (!g->ext_valid) return fail(CG_ERR_STATE, "cg_grid_eval: node data not available");
   cg::Dims D = g->dims();
   if (g->kind == 1)
@@ -199,24 +295,8 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
 
   if (what & CG_WHAT_COORDS) {
     cg::CoordOut<T> C;
-    memset(&C, 0, sizeof C);
-    size_t b;
-    for (int q = 0; q < N; ++q) {
-      Buf* nb = select(g, CG_ARR_NODE_COORD, q, &b);
-      int rc = ensure(g, *nb, b);
-      if (rc) return rc;
-      C.node[q] = (T*)nb->p;
-      Buf* cb = select(g, CG_ARR_CENTROID_COORD, q, &b);
-      rc = ensure(g, *cb, b);
-      if (rc) return rc;
-      C.centroid[q] = (T*)cb->p;
-      for (int a = 0; a < N; ++a) {
-        Buf* fb = select(g, CG_ARR_FACE_COORD, 3 * a + q, &b);
-        rc = ensure(g, *fb, b);
-        if (rc) return rc;
-        C.face[a][q] = (T*)fb->p;
-      }
-    }
+    int rcc = bind_coord_outputs<T>(g, C);
+    if (rcc) return rcc;
     cg::k_coords<T><<<launch_blocks(g->nnodes(), 256), 256, 0, st>>>(D, ex, ey, ez, C);
     g_launches++;
     CG_CUDA(cudaGetLastError());
@@ -225,54 +305,9 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
   if (!(what & (CG_WHAT_CELL | CG_WHAT_FACE))) return CG_OK;
 
   cg::MetricOut<T> O;
-  memset(&O, 0, sizeof O);
-  size_t b;
-  if (g->profile == CG_PROFILE_FULL) {
-    if (what & CG_WHAT_CELL) {
-      Buf* p = select(g, CG_ARR_CELL_FORWARD, 0, &b);
-      int rc = ensure(g, *p, b);
-      if (rc) return rc;
-      O.cell_fwd = (T*)p->p;
-      p = select(g, CG_ARR_CELL_INVERSE, 0, &b);
-      rc = ensure(g, *p, b);
-      if (rc) return rc;
-      O.cell_inv = (T*)p->p;
-    }
-    if (what & CG_WHAT_FACE)
-      for (int a = 0; a < N; ++a) {
-        Buf* p = select(g, CG_ARR_FACE_FORWARD, a, &b);
-        int rc = ensure(g, *p, b);
-        if (rc) return rc;
-        O.face_fwd[a] = (T*)p->p;
-        p = select(g, CG_ARR_FACE_INVERSE, a, &b);
-        rc = ensure(g, *p, b);
-        if (rc) return rc;
-        O.face_inv[a] = (T*)p->p;
-        p = select(g, CG_ARR_FACE_CONSERVED, a, &b);
-        rc = ensure(g, *p, b);
-        if (rc) return rc;
-        O.face_cons[a] = (T*)p->p;
-      }
-  } else {
-    if (what & CG_WHAT_CELL) {
-      Buf* p = select(g, CG_ARR_COMPACT_J, 0, &b);
-      int rc = ensure(g, *p, b);
-      if (rc) return rc;
-      O.cjac = (T*)p->p;
-    }
-    if (what & CG_WHAT_FACE)
-      for (int a = 0; a < N; ++a) {
-        Buf* p = select(g, CG_ARR_COMPACT_ACTIVE, a, &b);
-        int rc = ensure(g, *p, b);
-        if (rc) return rc;
-        O.cactive[a] = (T*)p->p;
-      }
-  }
-  if (!g->ev0) {
-    CG_CUDA(cudaEventCreate(&g->ev0));
-    CG_CUDA(cudaEventCreate(&g->ev1));
-  }
-  CG_CUDA(cudaEventRecord(g->ev0, st));
+  int rco = bind_metric_outputs<T>(g, what, O);
+  if (rco) return rco;
+  if ((rco = start_timer(g, st))) return rco;
   const int64_t nc = g->ncells();
   int nl = 0;
   if (N == 1) {

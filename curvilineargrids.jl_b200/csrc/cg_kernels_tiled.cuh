@@ -20,6 +20,9 @@
 namespace cg {
 
 #define CG_D __device__ __forceinline__
+#ifndef CG_MINB
+#define CG_MINB 2
+#endif
 constexpr int WARP_OUT = 29;  // output cells per warp along xi
 constexpr unsigned FULLMASK = 0xffffffffu;
 
@@ -196,7 +199,7 @@ struct March {
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
 // ===========================================================================
 template <class T, int SCH>
-__global__ void __launch_bounds__(128) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+__global__ void __launch_bounds__(128, CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
                                                  int what, int kchunk) {
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
@@ -224,10 +227,11 @@ __global__ void __launch_bounds__(128) k_face_xi(Dims D, const T* ex, const T* e
 #pragma unroll
     for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + shfl_dn(wm[e], 1);
   }
+  PF<T> z0 = zplane(N, nbase + k0 * N.s2), z1 = zplane(N, nbase + (k0 + 1) * N.s2);
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t b = nbase + m * N.s2;
     const int64_t cl = i + j * cs1 + m * cs2;
-    PF<T> z0 = zplane(N, b), z1 = zplane(N, b + N.s2);
+    PF<T> z2 = zplane(N, b + 2 * N.s2);  // looked-ahead plane; z0, z1 are carried
     T c[3][8];
     taylor_from_z(z0, z1, c);
     T F[3][3], G[3][3];
@@ -255,15 +259,21 @@ __global__ void __launch_bounds__(128) k_face_xi(Dims D, const T* ex, const T* e
         if (O.cjac) O.cjac[cl] = J;
       }
     }
-    if (!do_face) continue;
+    if (!do_face) {
+      z0 = z1;
+      z1 = z2;
+      continue;
+    }
     // ---- zeta-direction edge scalars: top face (m + 1/2), looked ahead one plane ----
     T psi_top[6];
     {
       T wp[6], wm[6];
-      eface6<T, SCH>(z0, z1, zplane(N, b + 2 * N.s2), wp, wm);
+      eface6<T, SCH>(z0, z1, z2, wp, wm);
 #pragma unroll
       for (int e = 0; e < 6; ++e) psi_top[e] = wp[e] + shfl_dn(wm[e], 1);
     }
+    z0 = z1;
+    z1 = z2;
     // ---- eta-direction edge scalars on both eta faces of the cell ----
     T dpsi_eta[6];
     {
@@ -301,14 +311,13 @@ __global__ void __launch_bounds__(128) k_face_xi(Dims D, const T* ex, const T* e
       }
     }
     // ---- reconstructed inverse Jacobian on the xi face ----
-    T Fp[3][3], L[3][3], R[3][3], Gf[3][3], Ff[3][3];
+    T Fa[3], Fb[3], L[3][3], R[3][3], Gf[3][3], Ff[3][3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      Fp[q][0] = T(0);
-      Fp[q][1] = c[q][3];
-      Fp[q][2] = c[q][5];
+      Fa[q] = c[q][3];
+      Fb[q] = c[q][5];
     }
-    ginv_states3(G, Fp, lam1, lam2, L, R);
+    ginv_states3_ax<0>(G, Fa, Fb, lam1, lam2, L, R);
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(128) k_face_xi(Dims D, const T* ex, const T* e
 //   row xi         : +dPsi^{zeta->eta}[b=eta] across zeta - line_eta[b=zeta]
 // ===========================================================================
 template <class T, int SCH>
-__global__ void __launch_bounds__(128) k_face_eta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+__global__ void __launch_bounds__(128, CG_MINB) k_face_eta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
                                                   int kchunk) {
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
@@ -432,18 +441,17 @@ __global__ void __launch_bounds__(128) k_face_eta(Dims D, const T* ex, const T* 
         const int64_t bc = b + cell * N.s1;
         T c[3][8];
         taylor_from_z(zplane(N, bc), zplane(N, bc + N.s2), c);
-        T F[3][3], G[3][3], Fp[3][3];
+        T F[3][3], G[3][3], Fa[3], Fb[3];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
 #pragma unroll
           for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-          Fp[q][0] = c[q][3];
-          Fp[q][1] = T(0);
-          Fp[q][2] = c[q][6];
+          Fa[q] = c[q][6];  // column zeta of dF/d(eta)
+          Fb[q] = c[q][3];  // column xi
         }
         inv3(F, G);
-        if (cell == 0) ginv_states3(G, Fp, lam1, lam2, L, R);
-        else ginv_states3(G, Fp, lam1, lam2, R, R1);  // R <- L of cell j+1 (unused), R1 <- R of cell j+1
+        if (cell == 0) ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, L, R);
+        else ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, R, R1);  // R <- L of cell j+1 (unused), R1 <- R of cell j+1
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -506,21 +514,20 @@ CG_D void cellz_compute(const NodeP<T>& N, int64_t b, bool full, T lam1, T lam2,
     o.ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
     o.ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
   }
-  T F[3][3], G[3][3], Fp[3][3];
+  T F[3][3], G[3][3], Fa[3], Fb[3];
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-    Fp[q][0] = c[q][5];
-    Fp[q][1] = c[q][6];
-    Fp[q][2] = T(0);
+    Fa[q] = c[q][5];  // column xi of dF/d(zeta)
+    Fb[q] = c[q][6];  // column eta
   }
   inv3(F, G);
-  ginv_states3(G, Fp, lam1, lam2, o.L, o.R);
+  ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, o.L, o.R);
 }
 
 template <class T, int SCH>
-__global__ void __launch_bounds__(128) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+__global__ void __launch_bounds__(128, CG_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
                                                    int kchunk) {
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];

@@ -114,6 +114,35 @@ CG_HD void ginv_states3(const T (&G)[3][3], const T (&Fp)[3][3], T lam1, T lam2,
       R[r][c] = s + d;
     }
 }
+// same, for a derivative axis AX whose column of F' is identically zero (d/d(xi_AX) of
+// dq/d(xi_AX) vanishes inside a multilinear cell): Fa, Fb are the columns (AX+1)%3, (AX+2)%3 of F'.
+template <int AX, class T>
+CG_HD void ginv_states3_ax(const T (&G)[3][3], const T (&Fa)[3], const T (&Fb)[3], T lam1, T lam2, T (&L)[3][3],
+                           T (&R)[3][3]) {
+  constexpr int A = (AX + 1) % 3, B = (AX + 2) % 3;
+  T Pa[3], Pb[3];  // columns A and B of G*F' (column AX is zero)
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    Pa[r] = G[r][0] * Fa[0] + G[r][1] * Fa[1] + G[r][2] * Fa[2];
+    Pb[r] = G[r][0] * Fb[0] + G[r][1] * Fb[1] + G[r][2] * Fb[2];
+  }
+  T G1[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) G1[r][c] = Pa[r] * G[A][c] + Pb[r] * G[B][c];  // = -G'
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T g2 = Pa[r] * G1[A][c] + Pb[r] * G1[B][c];  // = G''/2
+      T s = G[r][c] + (T(2) * lam2) * g2;
+      T d = lam1 * G1[r][c];
+      L[r][c] = s - d;
+      R[r][c] = s + d;
+    }
+}
+
 template <class T>
 CG_HD void ginv_states2(const T (&G)[2][2], const T (&Fp)[2][2], T lam1, T lam2, T (&L)[2][2], T (&R)[2][2]) {
   T GFp[2][2], G1[2][2], G2[2][2];
