@@ -1,0 +1,52 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol the header
+declares, and reports errors through status codes (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import curvigrid_b200 as cg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "curvigrid_cuda.h")).read()
+    declared = set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"cg_status", "cg_scheme"}
+    lib = cg._lib.lib()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(cg._lib.EXPORTS), declared ^ set(cg._lib.EXPORTS)
+    assert lib.cg_version() >= 100
+
+
+def test_null_and_bad_arguments_return_status_codes():
+    L = cg._lib
+    lib = L.lib()
+    assert lib.cg_grid_destroy(None) == L.CG_OK
+    assert lib.cg_grid_eval(None, 3, None) == L.CG_ERR_ARG
+    assert b"NULL" in lib.cg_last_error()
+    h = ctypes.c_void_p()
+    rc = lib.cg_grid_create(0, 7, 0, L.i64x3((4, 4, 4)), 2, 2, 0, None, None, None, ctypes.byref(h))
+    assert rc == L.CG_ERR_ARG and h.value is None
+    rc = lib.cg_grid_create(0, 2, 0, L.i64x3((4, 4)), -1, 2, 0, None, None, None, ctypes.byref(h))
+    assert rc == L.CG_ERR_ARG
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        cg.DiscreteGrid(*cg.workloads.wavy_nodes_2d(5, 5), 2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "curvilineargrids.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower() or f == "cg_mapped.cuh" or "oracle" in src.lower() and all(
+                    "import" not in ln and "#include" not in ln for ln in src.splitlines() if "oracle" in ln.lower()), f
