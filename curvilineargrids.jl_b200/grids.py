@@ -71,7 +71,8 @@ class _UnifiedGrid:
         self.dim = dim
         self.celldims = tuple(int(c) for c in celldims)
         self.nhalo = int(nhalo)
-        self.device = int(device)
+        # default: the current torch device (one process per GPU under torchrun)
+        self.device = int(torch.cuda.current_device() if device is None else device)
         self.T = np.dtype(T)
         if self.T not in (np.dtype(np.float64), np.dtype(np.float32)):
             raise ValueError("T must be float64 or float32")
@@ -243,7 +244,7 @@ class DiscreteGrid(_UnifiedGrid):
     memory order.
     """
 
-    def __init__(self, *args, device=0, T=None, compute_metrics=True, halo_coords_included=False,
+    def __init__(self, *args, device=None, T=None, compute_metrics=True, halo_coords_included=False,
                  coordinate_system="CurvilinearCS", basis="CartesianBasis", interpolation="linear",
                  cache_mode="eager", conserved_metric_scheme=CurvatureCorrectedReconstruction, profile="full",
                  window=None, global_celldims=None, node_origin=None):
@@ -327,7 +328,7 @@ class MappedGrid(_UnifiedGrid):
     (DESIGN.md §2).
     """
 
-    def __init__(self, mapping, params, celldims, nhalo, *, device=0, T=np.float64, compute_metrics=True,
+    def __init__(self, mapping, params, celldims, nhalo, *, device=None, T=np.float64, compute_metrics=True,
                  coordinate_system="CurvilinearCS", basis="CartesianBasis", cache_mode="eager",
                  conserved_metric_scheme=CurvatureCorrectedReconstruction, profile="full",
                  global_cell_indices=None, t=0.0):
