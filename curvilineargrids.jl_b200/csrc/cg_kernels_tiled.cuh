@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cg_kernels_ref.cuh"
 
 namespace cg {
@@ -37,6 +39,13 @@ struct NodeP {
 };
 
 template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
+// L1 prefetch of the node at linear index b for the three coordinates (the marching kernels are
+// load-latency bound at 8 warps/SM: the planes the NEXT iteration touches first are fetched now)
+template <class T>
+CG_D void pf3(const NodeP<T>& N, int64_t b) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(N.q[q] + b));
+}
 
 // zeta-plane forms (fixed k), transverse (xi, eta)
 template <class T>
@@ -198,9 +207,11 @@ struct March {
 // ===========================================================================
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
 // ===========================================================================
-template <class T, int SCH>
-__global__ void __launch_bounds__(128, CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
-                                                 int what, int kchunk) {
+// PART: bit0 = conserved metrics, bit1 = reconstructed inverse Jacobian (+ cell metrics); splitting the
+// two halves into separate launches halves the live register state of each (more warps per SM).
+template <class T, int SCH, int PART>
+__global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
+                                                                   MetricOut<T> O, int what, int kchunk) {
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
@@ -214,13 +225,15 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_xi(Dims D, const T* ex, c
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = D.se[1]; N.s2 = D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool do_cell = what & 1, do_face = what & 2;
   const bool full = O.face_cons[0] != nullptr;
+  const bool do_cell = (what & 1) && (PART & 2);
+  const bool do_cons = (what & 2) && (PART & 1);
+  const bool do_gf = (what & 2) && (PART & 2) && full;
   const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
 
   T psi_bot[6];
-  if (do_face) {
+  if (do_cons) {
     T wp[6], wm[6];
     const int64_t b = nbase + (k0 - 1) * N.s2;
     eface6<T, SCH>(zplane(N, b), zplane(N, b + N.s2), zplane(N, b + 2 * N.s2), wp, wm);
@@ -231,35 +244,65 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_xi(Dims D, const T* ex, c
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t b = nbase + m * N.s2;
     const int64_t cl = i + j * cs1 + m * cs2;
+    if (m + 1 < k1) {  // next iteration's new node rows: plane m+3 (rows j, j+1), plane m+2 (rows j-1, j+2)
+      pf3(N, b + 3 * N.s2);
+      pf3(N, b + 3 * N.s2 + N.s1);
+      if (do_cons) {
+        pf3(N, b + 2 * N.s2 - N.s1);
+        pf3(N, b + 2 * N.s2 + 2 * N.s1);
+      }
+    }
     PF<T> z2 = zplane(N, b + 2 * N.s2);  // looked-ahead plane; z0, z1 are carried
     T c[3][8];
     taylor_from_z(z0, z1, c);
-    T F[3][3], G[3][3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q)
-#pragma unroll
-      for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-    inv3(F, G);
-    if (do_cell) {
-      T dl[3] = {clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]),
-                 clamp_delta<T>(D.w0[2] + m, D.nhalo, D.gn[2])};
-      T Ff[3][3];
+    if (do_cell || do_gf) {
+      T F[3][3], G[3][3];
 #pragma unroll
       for (int q = 0; q < 3; ++q)
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const int e = (d + 1) % 3, g = (d + 2) % 3;
-          Ff[q][d] = c[q][1 << d] + c[q][(1 << d) | (1 << e)] * dl[e] + c[q][(1 << d) | (1 << g)] * dl[g] +
-                     c[q][7] * dl[e] * dl[g];
+        for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+      inv3(F, G);
+      if (do_cell) {
+        T dl[3] = {clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]),
+                   clamp_delta<T>(D.w0[2] + m, D.nhalo, D.gn[2])};
+        T Ff[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const int e = (d + 1) % 3, g = (d + 2) % 3;
+            Ff[q][d] = c[q][1 << d] + c[q][(1 << d) | (1 << e)] * dl[e] + c[q][(1 << d) | (1 << g)] * dl[g] +
+                       c[q][7] * dl[e] * dl[g];
+          }
+        T J = det3(Ff);
+        if (out_ok) {
+          if (O.cell_fwd) store10(O.cell_fwd + 10 * cl, Ff, J);
+          if (O.cell_inv) store10(O.cell_inv + 10 * cl, G, J);
+          if (O.cjac) O.cjac[cl] = J;
         }
-      T J = det3(Ff);
-      if (out_ok) {
-        if (O.cell_fwd) store10(O.cell_fwd + 10 * cl, Ff, J);
-        if (O.cell_inv) store10(O.cell_inv + 10 * cl, G, J);
-        if (O.cjac) O.cjac[cl] = J;
+      }
+      if (do_gf) {
+        // ---- reconstructed inverse Jacobian on the xi face ----
+        T Fa[3], Fb[3], L[3][3], R[3][3], Gf[3][3], Ff[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          Fa[q] = c[q][3];
+          Fb[q] = c[q][5];
+        }
+        ginv_states3_ax<0>(G, Fa, Fb, lam1, lam2, L, R);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
+        inv3(Gf, Ff);
+        T Jf = det3(Ff);
+        if (out_ok) {
+          store10(O.face_fwd[0] + 10 * cl, Ff, Jf);
+          store10(O.face_inv[0] + 10 * cl, Gf, Jf);
+        }
       }
     }
-    if (!do_face) {
+    if (!do_cons) {
       z0 = z1;
       z1 = z2;
       continue;
@@ -310,25 +353,7 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_xi(Dims D, const T* ex, c
         else Gh[2][col] -= T(0.5) * v;
       }
     }
-    // ---- reconstructed inverse Jacobian on the xi face ----
-    T Fa[3], Fb[3], L[3][3], R[3][3], Gf[3][3], Ff[3][3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      Fa[q] = c[q][3];
-      Fb[q] = c[q][5];
-    }
-    ginv_states3_ax<0>(G, Fa, Fb, lam1, lam2, L, R);
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
-    inv3(Gf, Ff);
-    T Jf = det3(Ff);
-    if (out_ok) {
-      store10(O.face_fwd[0] + 10 * cl, Ff, Jf);
-      store10(O.face_inv[0] + 10 * cl, Gf, Jf);
-      store9(O.face_cons[0] + 9 * cl, Gh);
-    }
+    if (out_ok) store9(O.face_cons[0] + 9 * cl, Gh);
   }
 }
 
@@ -338,9 +363,9 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_xi(Dims D, const T* ex, c
 //   row zeta       : +line_eta[b=xi]                     - dPsi^{xi->eta}[b=eta] across xi
 //   row xi         : +dPsi^{zeta->eta}[b=eta] across zeta - line_eta[b=zeta]
 // ===========================================================================
-template <class T, int SCH>
-__global__ void __launch_bounds__(128, CG_MINB) k_face_eta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
-                                                  int kchunk) {
+template <class T, int SCH, int PART>
+__global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_eta(Dims D, const T* ex, const T* ey, const T* ez,
+                                                                    MetricOut<T> O, int kchunk) {
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
@@ -355,6 +380,7 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_eta(Dims D, const T* ex, 
   N.s1 = D.se[1]; N.s2 = D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
   const bool full = O.face_cons[1] != nullptr;
+  const bool do_cons = PART & 1, do_gf = (PART & 2) && full;
   const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
 
@@ -369,10 +395,57 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_eta(Dims D, const T* ex, 
     for (int e = 0; e < 6; ++e) psi[e] = wp[e] + wn[e];
   };
   T psi_bot[6];
-  psi_zeta(nbase + (k0 - 1) * N.s2, psi_bot);
+  if (do_cons) psi_zeta(nbase + (k0 - 1) * N.s2, psi_bot);
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t b = nbase + m * N.s2;
     const int64_t cl = i + j * cs1 + m * cs2;
+    if (do_gf) {
+      // ---- reconstructed inverse Jacobian on the eta face: cells j and j+1 ----
+      if (m + 1 < k1) {
+        pf3(N, b + 2 * N.s2);
+        pf3(N, b + 2 * N.s2 + N.s1);
+        pf3(N, b + 2 * N.s2 + 2 * N.s1);
+      }
+      T Gf[3][3], Ff[3][3];
+      {
+        T L[3][3], R[3][3], R1[3][3];
+#pragma unroll
+        for (int cell = 0; cell < 2; ++cell) {
+          const int64_t bc = b + cell * N.s1;
+          T c[3][8];
+          taylor_from_z(zplane(N, bc), zplane(N, bc + N.s2), c);
+          T F[3][3], G[3][3], Fa[3], Fb[3];
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+            Fa[q] = c[q][6];  // column zeta of dF/d(eta)
+            Fb[q] = c[q][3];  // column xi
+          }
+          inv3(F, G);
+          if (cell == 0) ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, L, R);
+          else ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, R, R1);  // R <- L of cell j+1 (unused), R1 <- R of cell j+1
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + R1[r][cc]);
+      }
+      inv3(Gf, Ff);
+      T Jf = det3(Ff);
+      if (out_ok) {
+        store10(O.face_fwd[1] + 10 * cl, Ff, Jf);
+        store10(O.face_inv[1] + 10 * cl, Gf, Jf);
+      }
+    }
+    if (!do_cons) continue;
+    if (m + 1 < k1) {  // next iteration: plane m+3 rows j..j+2, plane m+2 rows j-1 and j+3
+      pf3(N, b + 3 * N.s2);
+      pf3(N, b + 3 * N.s2 + N.s1);
+      pf3(N, b + 3 * N.s2 + 2 * N.s1);
+      pf3(N, b + 2 * N.s2 - N.s1);
+      pf3(N, b + 2 * N.s2 + 3 * N.s1);
+    }
     T psi_top[6];
     psi_zeta(b, psi_top);
     // Psi^{xi->eta} on the zeta-edge (i+1/2, j+1/2): xi faces (i+1/2) of rows j and j+1, reconstructed along eta
@@ -432,39 +505,147 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_eta(Dims D, const T* ex, 
         Gh[0][col] -= T(0.5) * accz;
       }
     }
-    // ---- reconstructed inverse Jacobian on the eta face: cells j and j+1 ----
-    T Gf[3][3], Ff[3][3];
+    if (out_ok) store9(O.face_cons[1] + 9 * cl, Gh);
+  }
+}
+
+// ===========================================================================
+// Kernel B2: eta-face metrics with the eta-neighbours shared through shared memory.
+// A block is RY consecutive j-rows (one warp each) marching along k in lock-step:
+// row 0 and rows RY-2, RY-1 are the -1 / +1,+2 neighbours of the RY-3 output rows.
+// Every thread evaluates only ITS cell (W+- of its zeta and xi faces, line scalars,
+// L/R states), publishes the 39 values its eta-neighbours need, and after one
+// barrier assembles its face from rows r-1, r+1, r+2.  Roughly halves the FP64 work
+// of kernel B (which recomputes the neighbour rows from the nodes).
+// shared layout: [slot][row][lane] doubles — lanes contiguous, conflict-free.
+// ===========================================================================
+constexpr int B2_SLOTS = 39;
+template <class T, int SCH, int RY, int MB>
+__global__ void __launch_bounds__(32 * RY, MB) k_face_eta_sh(Dims D, const T* ex, const T* ey, const T* ez,
+                                                          MetricOut<T> O, int kchunk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  const int lane = threadIdx.x, r = threadIdx.y;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y * (RY - 3) + r - 1;   // full row of this warp (may be -1 or > nw1-1)
+  const int64_t jc = j > nw1 + 1 ? nw1 + 1 : j;
+  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
+  const int64_t ic = i > nw0 ? nw0 : i;
+  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0 && r >= 1 && r <= RY - 3 && j < nw1;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  NodeP<T> N;
+  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
+  N.s1 = D.se[1]; N.s2 = D.se[2];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const bool full = O.face_cons[1] != nullptr;
+  const int64_t nbase = (ic + 1) + (jc + 1) * N.s1 + N.s2;
+  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+  auto S = [&](int slot, int row) -> T& { return sm[(slot * RY + row) * 32 + lane]; };
+  const int rn = r + 1 < RY ? r + 1 : r, rn2 = r + 2 < RY ? r + 2 : r, rp = r > 0 ? r - 1 : r;
+
+  // zeta-face half states of this row on the face (m - 1/2), for the running psi_bot
+  T psi_bot[6];
+  {
+    T wp[6], wm[6];
+    const int64_t b = nbase + (k0 - 1) * N.s2;
+    eface6<T, SCH>(swap_uv(zplane(N, b)), swap_uv(zplane(N, b + N.s2)), swap_uv(zplane(N, b + 2 * N.s2)), wp, wm);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) S(e, r) = wm[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + S(e, rn);
+    __syncthreads();
+  }
+  PF<T> z0 = zplane(N, nbase + k0 * N.s2), z1 = zplane(N, nbase + (k0 + 1) * N.s2);
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t b = nbase + m * N.s2;
+    const int64_t cl = i + j * cs1 + m * cs2;
+    PF<T> z2 = zplane(N, b + 2 * N.s2);
+    T wpz[6], wpx[6];
     {
-      T L[3][3], R[3][3], R1[3][3];
+      T wm[6];
+      eface6<T, SCH>(swap_uv(z0), swap_uv(z1), swap_uv(z2), wpz, wm);
 #pragma unroll
-      for (int cell = 0; cell < 2; ++cell) {
-        const int64_t bc = b + cell * N.s1;
-        T c[3][8];
-        taylor_from_z(zplane(N, bc), zplane(N, bc + N.s2), c);
-        T F[3][3], G[3][3], Fa[3], Fb[3];
+      for (int e = 0; e < 6; ++e) S(e, r) = wm[e];
+      eface6<T, SCH>(xplane(N, b), xplane(N, b + 1), xplane(N, b + 2), wpx, wm);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+      for (int e = 0; e < 6; ++e) S(6 + e, r) = wm[e];
+    }
+    T L[3][3];
+    LineS<T> ln[6];
+    if (full) {
+      T c[3][8];
+      taylor_from_z(z0, z1, c);
 #pragma unroll
-          for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-          Fa[q] = c[q][6];  // column zeta of dF/d(eta)
-          Fb[q] = c[q][3];  // column xi
-        }
-        inv3(F, G);
-        if (cell == 0) ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, L, R);
-        else ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, R, R1);  // R <- L of cell j+1 (unused), R1 <- R of cell j+1
+      for (int col = 0; col < 3; ++col) {
+        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+        ln[col] = line_from_taylor(c, q1, q2, 1, 0, lam1, lam2);      // b = xi
+        ln[3 + col] = line_from_taylor(c, q1, q2, 1, 2, lam1, lam2);  // b = zeta
       }
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int e = 0; e < 6; ++e) {
+        S(12 + e, r) = ln[e].vp;
+        S(18 + e, r) = T(2) * ln[e].u - ln[e].vm;
+        S(24 + e, r) = ln[e].vm;
+      }
+      T F[3][3], G[3][3], Fa[3], Fb[3], R[3][3];
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + R1[r][cc]);
+      for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+        Fa[q] = c[q][6];
+        Fb[q] = c[q][3];
+      }
+      inv3(F, G);
+      ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, L, R);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) S(30 + 3 * a + bb, r) = R[a][bb];
     }
-    inv3(Gf, Ff);
-    T Jf = det3(Ff);
-    if (out_ok) {
-      store10(O.face_fwd[1] + 10 * cl, Ff, Jf);
-      store10(O.face_inv[1] + 10 * cl, Gf, Jf);
-      store9(O.face_cons[1] + 9 * cl, Gh);
+    z0 = z1;
+    z1 = z2;
+    __syncthreads();
+    T Gh[3][3];
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      T pt_a = wpz[3 + col] + S(3 + col, rn), pt_f = wpz[col] + S(col, rn);          // Psi^{zeta->eta}, top
+      T px_a = wpx[3 + col] + S(9 + col, rn), px_f = wpx[col] + S(6 + col, rn);      // Psi^{xi->eta}
+      T dxa = px_a - shfl_up(px_a, 1);
+      T dxf = px_f - shfl_up(px_f, 1);
+      Gh[1][col] = dxa - (pt_a - psi_bot[3 + col]);
+      Gh[2][col] = -dxf;
+      Gh[0][col] = pt_f - psi_bot[col];
+      psi_bot[3 + col] = pt_a;
+      psi_bot[col] = pt_f;
     }
+    if (O.cactive[1] && out_ok) {
+      T* o = O.cactive[1] + 3 * cl;
+      o[0] = Gh[1][0]; o[1] = Gh[1][1]; o[2] = Gh[1][2];
+    }
+    if (full) {
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        T vx = T(0.5) * ((ln[col].vp - T(2) * ln[col].u) - S(12 + col, rp) + S(18 + col, rn) + S(24 + col, rn2));
+        T vz = T(0.5) * ((ln[3 + col].vp - T(2) * ln[3 + col].u) - S(15 + col, rp) + S(21 + col, rn) + S(27 + col, rn2));
+        Gh[2][col] += vx;  // row zeta: + line[b = xi]
+        Gh[0][col] -= vz;  // row xi:   - line[b = zeta]
+      }
+      T Gf[3][3], Ff[3][3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) Gf[a][bb] = T(0.5) * (L[a][bb] + S(30 + 3 * a + bb, rn));
+      inv3(Gf, Ff);
+      T Jf = det3(Ff);
+      if (out_ok) {
+        store10(O.face_fwd[1] + 10 * cl, Ff, Jf);
+        store10(O.face_inv[1] + 10 * cl, Gf, Jf);
+        store9(O.face_cons[1] + 9 * cl, Gh);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -485,7 +666,7 @@ struct CellZ {
   T L[3][3], R[3][3];
 };
 
-template <class T, int SCH>
+template <class T, int SCH, bool GF>
 CG_D void cellz_compute(const NodeP<T>& N, int64_t b, bool full, T lam1, T lam2, CellZ<T>& o) {
   // b = node (ic, j, p) of the cell's low corner
   {
@@ -514,21 +695,84 @@ CG_D void cellz_compute(const NodeP<T>& N, int64_t b, bool full, T lam1, T lam2,
     o.ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
     o.ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
   }
-  T F[3][3], G[3][3], Fa[3], Fb[3];
+  if (GF) {
+    T F[3][3], G[3][3], Fa[3], Fb[3];
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < 3; ++q) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-    Fa[q] = c[q][5];  // column xi of dF/d(zeta)
-    Fb[q] = c[q][6];  // column eta
+      for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+      Fa[q] = c[q][5];  // column xi of dF/d(zeta)
+      Fb[q] = c[q][6];  // column eta
+    }
+    inv3(F, G);
+    ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, o.L, o.R);
   }
-  inv3(F, G);
-  ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, o.L, o.R);
 }
 
+// reconstructed inverse Jacobian on the zeta faces only (PART = 2 of the zeta kernel): marches along k,
+// carrying the zeta-plane forms and the L state of the cell below the face
 template <class T, int SCH>
-__global__ void __launch_bounds__(128, CG_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
-                                                   int kchunk) {
+__global__ void __launch_bounds__(128, 3) k_gface_zeta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+                                                       int kchunk) {
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
+  if (j >= nw1) return;
+  const bool out_ok = i < nw0;
+  const int64_t ic = i >= nw0 ? nw0 - 1 : i;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  NodeP<T> N;
+  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
+  N.s1 = D.se[1]; N.s2 = D.se[2];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
+  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+  auto states = [&](const PF<T>& lo, const PF<T>& hi, T (&L)[3][3], T (&R)[3][3]) {
+    T c[3][8];
+    taylor_from_z(lo, hi, c);
+    T F[3][3], G[3][3], Fa[3], Fb[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+      Fa[q] = c[q][5];
+      Fb[q] = c[q][6];
+    }
+    inv3(F, G);
+    ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, L, R);
+  };
+  PF<T> z0 = zplane(N, nbase + k0 * N.s2), z1 = zplane(N, nbase + (k0 + 1) * N.s2);
+  T Lp[3][3], Rtmp[3][3];
+  states(z0, z1, Lp, Rtmp);
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t cl = i + j * cs1 + m * cs2;
+    if (m + 1 < k1) pf3(N, nbase + (m + 3) * N.s2), pf3(N, nbase + (m + 3) * N.s2 + N.s1);
+    PF<T> z2 = zplane(N, nbase + (m + 2) * N.s2);
+    T Ln[3][3], Rn[3][3], Gf[3][3], Ff[3][3];
+    states(z1, z2, Ln, Rn);  // cell m+1
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        Gf[r][cc] = T(0.5) * (Lp[r][cc] + Rn[r][cc]);
+        Lp[r][cc] = Ln[r][cc];
+      }
+    z1 = z2;
+    inv3(Gf, Ff);
+    T Jf = det3(Ff);
+    if (out_ok) {
+      store10(O.face_fwd[2] + 10 * cl, Ff, Jf);
+      store10(O.face_inv[2] + 10 * cl, Gf, Jf);
+    }
+  }
+}
+
+template <class T, int SCH, int PART>
+__global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
+                                                                     MetricOut<T> O, int kchunk) {
+  constexpr bool GF = (PART & 2) != 0;
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
@@ -551,12 +795,12 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_zeta(Dims D, const T* ex,
   {
     CellZ<T> cm;  // cell k0 - 1
     if (full) {
-      cellz_compute<T, SCH>(N, nbase + (k0 - 1) * N.s2, true, lam1, lam2, cm);
+      cellz_compute<T, SCH, GF>(N, nbase + (k0 - 1) * N.s2, true, lam1, lam2, cm);
 #pragma unroll
       for (int e = 0; e < 6; ++e) vp_prev[e] = cm.ln[e].vp;
     }
     CellZ<T> c0;  // cell k0
-    cellz_compute<T, SCH>(N, nbase + k0 * N.s2, full, lam1, lam2, c0);
+    cellz_compute<T, SCH, GF>(N, nbase + k0 * N.s2, full, lam1, lam2, c0);
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
       wpe[e] = c0.wpe[e];
@@ -566,7 +810,7 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_zeta(Dims D, const T* ex,
         vp_prev[e] = c0.ln[e].vp;
       }
     }
-    if (full) {
+    if (full && GF) {
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
@@ -575,8 +819,15 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_zeta(Dims D, const T* ex,
   }
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl = i + j * cs1 + m * cs2;
+    if (m + 1 < k1) {  // next iteration: plane m+4 rows j, j+1; plane m+3 rows j-1, j+2
+      const int64_t bp = nbase + (m + 3) * N.s2;
+      pf3(N, bp + N.s2);
+      pf3(N, bp + N.s2 + N.s1);
+      pf3(N, bp - N.s1);
+      pf3(N, bp + 2 * N.s1);
+    }
     CellZ<T> cf;  // front cell m + 1
-    cellz_compute<T, SCH>(N, nbase + (m + 1) * N.s2, full, lam1, lam2, cf);
+    cellz_compute<T, SCH, GF>(N, nbase + (m + 1) * N.s2, full, lam1, lam2, cf);
     T Gh[3][3];  // rows 0 xi, 1 eta, 2 zeta
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
@@ -622,21 +873,23 @@ __global__ void __launch_bounds__(128, CG_MINB) k_face_zeta(Dims D, const T* ex,
         }
       }
     }
-    T Gf[3][3], Ff[3][3];
+    if (GF) {
+      T Gf[3][3], Ff[3][3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+      for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        Gf[r][cc] = T(0.5) * (Lp[r][cc] + cf.R[r][cc]);
-        Lp[r][cc] = cf.L[r][cc];
+        for (int cc = 0; cc < 3; ++cc) {
+          Gf[r][cc] = T(0.5) * (Lp[r][cc] + cf.R[r][cc]);
+          Lp[r][cc] = cf.L[r][cc];
+        }
+      inv3(Gf, Ff);
+      T Jf = det3(Ff);
+      if (out_ok) {
+        store10(O.face_fwd[2] + 10 * cl, Ff, Jf);
+        store10(O.face_inv[2] + 10 * cl, Gf, Jf);
       }
-    inv3(Gf, Ff);
-    T Jf = det3(Ff);
-    if (out_ok) {
-      store10(O.face_fwd[2] + 10 * cl, Ff, Jf);
-      store10(O.face_inv[2] + 10 * cl, Gf, Jf);
-      store9(O.face_cons[2] + 9 * cl, Gh);
     }
+    if (out_ok) store9(O.face_cons[2] + 9 * cl, Gh);
   }
 }
 
@@ -650,6 +903,25 @@ inline bool tiled2d_supported(const Dims&, const MetricOut<T>&) { return false; 
 template <class T>
 inline int launch_metrics2d_tiled(const Dims&, const T*, const T*, const MetricOut<T>&, int, int, cudaStream_t) {
   return -1;
+}
+
+// development switch (env CG_ETA_VARIANT): 1 = shared-memory eta kernel (default), 0 = warp-autonomous
+inline int eta_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_ETA_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+inline int split_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_SPLIT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 // mask: bit0 xi kernel (+cell), bit1 eta kernel, bit2 zeta kernel
@@ -672,17 +944,50 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
             (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
   int n = 0;
   const bool face = what & 2;
+  const bool full = O.face_cons[0] != nullptr;
+  const bool split = split_variant() != 0 && full && face;  // conserved and G-face halves as separate launches
   if ((mask & 1) && ((what & 1) || face)) {
-    k_face_xi<T, SCH><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
-    ++n;
+    if (split) {
+      k_face_xi<T, SCH, 2><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
+      k_face_xi<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
+      n += 2;
+    } else {
+      k_face_xi<T, SCH, 3><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
+      ++n;
+    }
   }
   if ((mask & 2) && face) {
-    k_face_eta<T, SCH><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-    ++n;
+    const int ev = eta_variant();
+    if (ev >= 1) {
+      auto go = [&](auto kern, int RY) {
+        const size_t shm = (size_t)B2_SLOTS * RY * 32 * sizeof(T);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        dim3 b2(32, RY);
+        dim3 g2(grid.x, (unsigned)((D.nw[1] + (RY - 3) - 1) / (RY - 3)), grid.z);
+        kern<<<g2, b2, shm, st>>>(D, ex, ey, ez, O, kchunk);
+      };
+      if (ev == 1) go(k_face_eta_sh<T, SCH, 16, 1>, 16);
+      else go(k_face_eta_sh<T, SCH, 8, 1>, 8);
+      ++n;
+    } else if (split) {
+      k_face_eta<T, SCH, 2><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      k_face_eta<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      n += 2;
+    } else {
+      k_face_eta<T, SCH, 3><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      ++n;
+    }
   }
   if ((mask & 4) && face) {
-    k_face_zeta<T, SCH><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-    ++n;
+    if (split) {
+      dim3 g3((unsigned)((D.nw[0] + 31) / 32), grid.y, grid.z);
+      k_gface_zeta<T, SCH><<<g3, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      k_face_zeta<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      n += 2;
+    } else {
+      k_face_zeta<T, SCH, 3><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      ++n;
+    }
   }
   return n;
 }
