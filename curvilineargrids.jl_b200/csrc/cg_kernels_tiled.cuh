@@ -898,11 +898,169 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, co
 // ---------------------------------------------------------------------------
 template <class T>
 inline bool tiled3d_supported(const Dims& D, const MetricOut<T>&) { return D.dim == 3; }
+// ===========================================================================
+// 2-D: one thread per PAIR of xi-adjacent cells (2p, 2p+1) of a row.  The pair's 80 B of every
+// `Metric` array and 64 B of every `ConservedMetric` array are contiguous and 16-B aligned, so all
+// stores are 16-B vector stores, and the 4x3 node patch is loaded once for both cells.
+// Replaces metrics.jl:1822-1848 (cell) and :1906-1960 (faces) for DiscreteGrid.
+// ===========================================================================
 template <class T>
-inline bool tiled2d_supported(const Dims&, const MetricOut<T>&) { return false; }
+CG_D void face2d(const Cell2<T>& c0, const Cell2<T>& c1, const T (&G0)[2][2], const T (&G1)[2][2], int f, T lam1,
+                 T lam2, bool want_g, T (&Gh)[2][2], T (&Gf)[2][2], T (&Ff)[2][2], T& J) {
+  T H0[2][2] = {{c0.F[1][1], -c0.F[0][1]}, {-c0.F[1][0], c0.F[0][0]}};
+  T H1[2][2] = {{c1.F[1][1], -c1.F[0][1]}, {-c1.F[1][0], c1.F[0][0]}};
+  T Hp0[2][2] = {{0, 0}, {0, 0}}, Hp1[2][2] = {{0, 0}, {0, 0}};
+  if (f == 0) {
+    Hp0[0][0] = c0.tw[1]; Hp0[0][1] = -c0.tw[0];
+    Hp1[0][0] = c1.tw[1]; Hp1[0][1] = -c1.tw[0];
+  } else {
+    Hp0[1][0] = -c0.tw[1]; Hp0[1][1] = c0.tw[0];
+    Hp1[1][0] = -c1.tw[1]; Hp1[1][1] = c1.tw[0];
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc)
+      Gh[r][cc] = T(0.5) * ((H0[r][cc] + lam1 * Hp0[r][cc]) + (H1[r][cc] - lam1 * Hp1[r][cc]));
+  if (!want_g) return;
+  const int o_ax = 1 - f;
+  T Fp0[2][2] = {{0, 0}, {0, 0}}, Fp1[2][2] = {{0, 0}, {0, 0}};
+  Fp0[0][o_ax] = c0.tw[0]; Fp0[1][o_ax] = c0.tw[1];
+  Fp1[0][o_ax] = c1.tw[0]; Fp1[1][o_ax] = c1.tw[1];
+  T L0[2][2], R0[2][2], L1[2][2], R1[2][2];
+  ginv_states2(G0, Fp0, lam1, lam2, L0, R0);
+  ginv_states2(G1, Fp1, lam1, lam2, L1, R1);
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) Gf[r][cc] = T(0.5) * (L0[r][cc] + R1[r][cc]);
+  inv2(Gf, Ff);
+  J = Ff[0][0] * Ff[1][1] - Ff[0][1] * Ff[1][0];
+}
+
+// store the Metric elements of the pair (10 values, 80 B, 16-B aligned for FP64)
 template <class T>
-inline int launch_metrics2d_tiled(const Dims&, const T*, const T*, const MetricOut<T>&, int, int, cudaStream_t) {
-  return -1;
+CG_D void store_pair5(T* o, const T (&A)[2][2], T JA, const T (&B)[2][2], T JB, bool second) {
+  if (sizeof(T) == 8 && second) {
+    double2* p = reinterpret_cast<double2*>(o);
+    p[0] = make_double2(A[0][0], A[1][0]);
+    p[1] = make_double2(A[0][1], A[1][1]);
+    p[2] = make_double2(JA, B[0][0]);
+    p[3] = make_double2(B[1][0], B[0][1]);
+    p[4] = make_double2(B[1][1], JB);
+  } else {
+    o[0] = A[0][0]; o[1] = A[1][0]; o[2] = A[0][1]; o[3] = A[1][1]; o[4] = JA;
+    if (second) { o[5] = B[0][0]; o[6] = B[1][0]; o[7] = B[0][1]; o[8] = B[1][1]; o[9] = JB; }
+  }
+}
+template <class T>
+CG_D void store_pair4(T* o, const T (&A)[2][2], const T (&B)[2][2], bool second) {
+  if (sizeof(T) == 8) {
+    double2* p = reinterpret_cast<double2*>(o);
+    p[0] = make_double2(A[0][0], A[1][0]);
+    p[1] = make_double2(A[0][1], A[1][1]);
+    if (second) {
+      p[2] = make_double2(B[0][0], B[1][0]);
+      p[3] = make_double2(B[0][1], B[1][1]);
+    }
+  } else {
+    o[0] = A[0][0]; o[1] = A[1][0]; o[2] = A[0][1]; o[3] = A[1][1];
+    if (second) { o[4] = B[0][0]; o[5] = B[1][0]; o[6] = B[0][1]; o[7] = B[1][1]; }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(128) k_metrics2d_pair(Dims D, const T* ex, const T* ey, MetricOut<T> O, int scheme,
+                                                        int what) {
+  const T lam1 = lam1_of<T>(scheme), lam2 = lam2_of<T>(scheme);
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1];
+  const int64_t npair = (nw0 + 1) / 2;
+  const int64_t s1 = D.se[1];
+  const int64_t ntot = npair * nw1;
+  for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
+       lin += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = lin % npair, j = lin / npair;
+    const int64_t i = 2 * p;
+    const bool second = i + 1 < nw0;
+    const int64_t b = (i + 1) + (j + 1) * s1;
+    const int64_t cl = i + j * nw0;
+    Cell2<T> c00 = cell2_load(ex, ey, b, s1), c10 = cell2_load(ex, ey, b + 1, s1);
+    T G00[2][2], G10[2][2];
+    inv2(c00.F, G00);
+    inv2(c10.F, G10);
+    if (what & 1) {
+      T dl1 = clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]);
+      T dlA = clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), dlB = clamp_delta<T>(D.w0[0] + i + 1, D.nhalo, D.gn[0]);
+      T FA[2][2], FB[2][2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        FA[q][0] = c00.F[q][0] + c00.tw[q] * dl1;
+        FA[q][1] = c00.F[q][1] + c00.tw[q] * dlA;
+        FB[q][0] = c10.F[q][0] + c10.tw[q] * dl1;
+        FB[q][1] = c10.F[q][1] + c10.tw[q] * dlB;
+      }
+      T JA = FA[0][0] * FA[1][1] - FA[0][1] * FA[1][0], JB = FB[0][0] * FB[1][1] - FB[0][1] * FB[1][0];
+      if (O.cell_fwd) store_pair5(O.cell_fwd + 5 * cl, FA, JA, FB, JB, second);
+      if (O.cell_inv) store_pair5(O.cell_inv + 5 * cl, G00, JA, G10, JB, second);
+      if (O.cjac) {
+        O.cjac[cl] = JA;
+        if (second) O.cjac[cl + 1] = JB;
+      }
+    }
+    if (!(what & 2)) continue;
+    const bool want_g = O.face_fwd[0] != nullptr;
+    T GhA[2][2], GhB[2][2], GfA[2][2], GfB[2][2], FfA[2][2], FfB[2][2], JA = 0, JB = 0;
+    {  // xi faces: (c00,c10) and (c10,c20)
+      Cell2<T> c20 = cell2_load(ex, ey, b + 2, s1);
+      T G20[2][2];
+      inv2(c20.F, G20);
+      face2d(c00, c10, G00, G10, 0, lam1, lam2, want_g, GhA, GfA, FfA, JA);
+      face2d(c10, c20, G10, G20, 0, lam1, lam2, want_g, GhB, GfB, FfB, JB);
+      if (O.face_cons[0]) store_pair4(O.face_cons[0] + 4 * cl, GhA, GhB, second);
+      if (O.cactive[0]) {
+        T* o = O.cactive[0] + 2 * cl;
+        o[0] = GhA[0][0]; o[1] = GhA[0][1];
+        if (second) { o[2] = GhB[0][0]; o[3] = GhB[0][1]; }
+      }
+      if (want_g) {
+        store_pair5(O.face_fwd[0] + 5 * cl, FfA, JA, FfB, JB, second);
+        store_pair5(O.face_inv[0] + 5 * cl, GfA, JA, GfB, JB, second);
+      }
+    }
+    {  // eta faces: (c00,c01) and (c10,c11)
+      Cell2<T> c01 = cell2_load(ex, ey, b + s1, s1), c11 = cell2_load(ex, ey, b + s1 + 1, s1);
+      T G01[2][2], G11[2][2];
+      inv2(c01.F, G01);
+      inv2(c11.F, G11);
+      face2d(c00, c01, G00, G01, 1, lam1, lam2, want_g, GhA, GfA, FfA, JA);
+      face2d(c10, c11, G10, G11, 1, lam1, lam2, want_g, GhB, GfB, FfB, JB);
+      if (O.face_cons[1]) store_pair4(O.face_cons[1] + 4 * cl, GhA, GhB, second);
+      if (O.cactive[1]) {
+        T* o = O.cactive[1] + 2 * cl;
+        o[0] = GhA[1][0]; o[1] = GhA[1][1];
+        if (second) { o[2] = GhB[1][0]; o[3] = GhB[1][1]; }
+      }
+      if (want_g) {
+        store_pair5(O.face_fwd[1] + 5 * cl, FfA, JA, FfB, JB, second);
+        store_pair5(O.face_inv[1] + 5 * cl, GfA, JA, GfB, JB, second);
+      }
+    }
+  }
+}
+
+template <class T>
+inline bool tiled2d_supported(const Dims& D, const MetricOut<T>&) {
+  // pair stores need every row to start 16-B aligned: an even number of cells per row
+  return D.dim == 2 && (D.nw[0] % 2 == 0 || sizeof(T) == 4);
+}
+template <class T>
+inline int launch_metrics2d_tiled(const Dims& D, const T* ex, const T* ey, const MetricOut<T>& O, int scheme, int what,
+                                  cudaStream_t st) {
+  const int64_t n = ((D.nw[0] + 1) / 2) * D.nw[1];
+  int64_t blocks = (n + 127) / 128;
+  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  k_metrics2d_pair<T><<<(unsigned)blocks, 128, 0, st>>>(D, ex, ey, O, scheme, what);
+  return 1;
 }
 
 // development switch (env CG_ETA_VARIANT): 1 = shared-memory eta kernel (default), 0 = warp-autonomous
