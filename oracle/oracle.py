@@ -165,3 +165,21 @@ def gcl_max(face_cons, nfull, nhalo):
     out = np.zeros(3)
     lib().cgo_gcl_max(ctypes.c_int(dim), _dp(cons), _ip(nf), ctypes.c_int(nhalo), _dp(out))
     return out[:dim]
+
+
+def legacy_meg6_3d(nodes, nhalo=5, halo_coords_included=False, symmetric=False):
+    """Legacy CurvilinearGrid3D(x,y,z,:meg6[_symmetric]) update! (oracle/legacy_meg6.hpp).
+    Returns dict: cell [28, ncell] (J, fwd 9, inv 9, hat 9), edge [3, 19, ncell] (J, inv 9, hat 9),
+    centroid [3, ncell], nfull (cell.full dims); arrays are Fortran-ordered over cells."""
+    nodes = [np.asarray(a, dtype=np.float64) for a in nodes]
+    flat = [np.ascontiguousarray(a.ravel(order="F")) for a in nodes]
+    nn = np.array(nodes[0].shape, dtype=np.int64)
+    nfull = tuple(int(s - 1 + (0 if halo_coords_included else 2 * nhalo)) for s in nodes[0].shape)
+    nc = int(np.prod(nfull))
+    cell = np.zeros((28, nc))
+    edge = np.zeros((3, 19, nc))
+    cent = np.zeros((3, nc))
+    lib().cgo_legacy_meg6_3d(_dp(flat[0]), _dp(flat[1]), _dp(flat[2]), _ip(nn), ctypes.c_int(nhalo),
+                             ctypes.c_int(int(halo_coords_included)), ctypes.c_int(int(symmetric)), _dp(cell),
+                             _dp(edge), _dp(cent))
+    return {"cell": cell, "edge": edge, "centroid": cent, "nfull": nfull}

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <vector>
 
+#include "legacy_meg6.hpp"
 #include "metric_oracle.hpp"
 
 using namespace cgo;
@@ -192,6 +193,15 @@ int cgo_gcl_max(int dim, const double* cons, const int64_t* nfull, int nhalo, do
           if (std::fabs(acc) > out[c]) out[c] = std::fabs(acc);
         }
       }
+  return 0;
+}
+
+// Legacy CurvilinearGrid3D(x, y, z, :meg6 | :meg6_symmetric) metric update (legacy_meg6.hpp).
+// x,y,z: node arrays, nnode = their extents (interior nodes, or node.full when halo_coords_included).
+// cell = [28][ncell.full], edge = [3][19][ncell.full], cent = [3][ncell.full] (may be NULL).
+int cgo_legacy_meg6_3d(const double* x, const double* y, const double* z, const int64_t* nnode, int nhalo,
+                       int halo_coords_included, int symmetric, double* cell, double* edge, double* cent) {
+  cgl::legacy_meg6_3d(x, y, z, nnode, nhalo, halo_coords_included != 0, symmetric != 0, cell, edge, cent);
   return 0;
 }
 
