@@ -1,11 +1,17 @@
 #!/bin/bash
-# Build libcurvigrid_cuda.so (sm_100a) in-tree and the oracle.
+# Build libcurvigrid_cuda.so (sm_100a) in-tree.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 SRC="$HERE/curvilineargrids.jl_b200/csrc"
 OUT="$HERE/curvilineargrids.jl_b200/libcurvigrid_cuda.so"
+OBJ="$HERE/build/obj"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo \
-  -Xcompiler -fPIC -shared ${CG_NVCC_EXTRA} \
-  -o "$OUT" "$SRC/cg_api.cu"
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+mkdir -p "$OBJ"
+# unified-grid kernels + C ABI
+"$NVCC" $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC ${CG_NVCC_EXTRA} -c "$SRC/cg_api.cu" -o "$OBJ/cg_api.o" &
+# legacy MEG6 pipeline: discontinuous thresholds -> no FMA contraction
+"$NVCC" $ARCH -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -c "$SRC/cg_legacy.cu" -o "$OBJ/cg_legacy.o" &
+wait
+"$NVCC" $ARCH -shared -o "$OUT" "$OBJ/cg_api.o" "$OBJ/cg_legacy.o"
 echo "built $OUT"

@@ -25,7 +25,7 @@ EXPORTS = [
     "cg_grid_set_nodes", "cg_grid_node_buffer", "cg_grid_nodes_changed", "cg_grid_required_node_range",
     "cg_grid_set_mapping_terms", "cg_grid_update", "cg_grid_eval", "cg_grid_valid", "cg_grid_invalidate",
     "cg_grid_get_ptr", "cg_grid_bind_output", "cg_grid_copy_out", "cg_grid_gcl_max", "cg_grid_sync",
-    "cg_grid_last_eval_ms", "cg_discrete_metrics_host",
+    "cg_grid_last_eval_ms", "cg_discrete_metrics_host", "cg_legacy_meg6_update_3d", "cg_legacy_last_error",
 ]
 
 _lib = None
@@ -51,6 +51,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         L.cg_last_error.restype = ctypes.c_char_p
         L.cg_launch_count.restype = ctypes.c_uint64
+        L.cg_legacy_last_error.restype = ctypes.c_char_p
         _lib = L
     return _lib
 

@@ -1,0 +1,394 @@
+// Legacy MEG6 metric pipeline on the device: CurvilinearGrid3D(x, y, z, :meg6 | :meg6_symmetric)
+// `update!(mesh, force, include_halo_region)`.
+//
+// Replaces (paths under /root/reference/src):
+//   grids/curvilinear_mapped_grids/3d.jl:472-598            update!, _centroid_coordinates_kernel!
+//   metric_schemes/MetricDiscretizationSchemes.jl:20-89     update_metrics!, update_edge_metrics!
+//   metric_schemes/forward_metrics.jl:89-167                forward_metrics!, jacobian_3d_kernel!
+//   metric_schemes/conservative_metrics.jl:13-175, 259-427  (symmetric_)conservative_metric(s)!
+//   discretization_schemes/DiscretizationSchemes.jl:90-159  compute_{first,second}_derivatives!
+//   discretization_schemes/derivative_kernels.jl:84-314     the KernelAbstractions GPU kernels
+//   discretization_schemes/derivative_stencils.jl:1-193     stencils (Kahan, tol_diff, eps clips)
+//   discretization_schemes/meg/*.jl                         MEG derivative + edge interpolation
+//
+// Design: the reference runs ~350 full-array KA launches per update, each with separate
+// inner / lo-edge / hi-edge kernels.  Here every pass is ONE launch that selects the central or
+// one-sided stencil from the cell's position in the domain, products/differences/divisions are
+// folded into the neighbouring pass, and all temporaries live in four scratch arrays.  The
+// thresholds (tol_diff, eps clips) are discontinuous, so this translation unit is compiled with
+// -fmad=false and keeps the reference's operation order (Kahan sums included).
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/curvigrid_cuda.h"
+
+namespace {
+
+struct LBox {
+  int lo[3], hi[3];
+};
+struct LShape {
+  int n[3];
+  long long st[3];
+};
+
+__device__ __forceinline__ double kahan3(double a, double b, double c) {
+  double s = 0.0, comp = 0.0, y, t;
+  y = a - comp; t = s + y; comp = (t - s) - y; s = t;
+  y = b - comp; t = s + y; comp = (t - s) - y; s = t;
+  y = c - comp; t = s + y; comp = (t - s) - y; s = t;
+  return s + comp;
+}
+__device__ __forceinline__ double kahan6(const double* v) {
+  double s = 0.0, comp = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double y = v[i] - comp;
+    double t = s + y;
+    comp = (t - s) - y;
+    s = t;
+  }
+  return s + comp;
+}
+__device__ __forceinline__ bool isapprox(double a, double b, double rtol, double atol) {
+  if (a == b) return true;
+  if (!isfinite(a) || !isfinite(b)) return false;
+  return fabs(a - b) <= fmax(atol, rtol * fmax(fabs(a), fabs(b)));
+}
+__device__ __forceinline__ double tol_diff(double a, double b) {
+  double d = a - b;
+  return isapprox(a, b, 1.4901161193847656e-08 /* sqrt(eps) */, 10 * DBL_EPSILON) ? d * 0.0 : d;
+}
+__device__ __forceinline__ double clip(double v, double e) { return fabs(v) >= e ? v : v * 0.0; }
+__device__ __forceinline__ double central6(double m3, double m2, double m1, double p1, double p2, double p3) {
+  double d = kahan3((3.0 / 4.0) * tol_diff(p1, m1), (-3.0 / 20.0) * tol_diff(p2, m2), (1.0 / 60.0) * tol_diff(p3, m3));
+  return clip(d, DBL_EPSILON);
+}
+// component `which` (0,1,2) of mixed_derivatives_loedge on the window p[0..5]
+__device__ __forceinline__ double mixed_lo(const double* p, int which) {
+  double v[6];
+  if (which == 0) {
+    v[0] = (-137.0 / 60.0) * p[0]; v[1] = 5 * p[1]; v[2] = -5 * p[2]; v[3] = (10.0 / 3.0) * p[3];
+    v[4] = -(5.0 / 4.0) * p[4]; v[5] = (1.0 / 5.0) * p[5];
+  } else if (which == 1) {
+    v[0] = (-1.0 / 5.0) * p[0]; v[1] = -(13.0 / 12.0) * p[1]; v[2] = 2 * p[2]; v[3] = -p[3];
+    v[4] = (1.0 / 3.0) * p[4]; v[5] = -(1.0 / 20.0) * p[5];
+  } else {
+    v[0] = (1.0 / 20.0) * p[0]; v[1] = -(1.0 / 2.0) * p[1]; v[2] = -(1.0 / 3.0) * p[2]; v[3] = p[3];
+    v[4] = -(1.0 / 4.0) * p[4]; v[5] = (1.0 / 30.0) * p[5];
+  }
+  return clip(kahan6(v), 50 * DBL_EPSILON);
+}
+// derivative at p[3 + which] (which = 0,1,2) of mixed_derivatives_hiedge on the window p[0..5]
+__device__ __forceinline__ double mixed_hi(const double* p, int which) {
+  double v[6];
+  if (which == 2) {
+    v[0] = (-1.0 / 5.0) * p[0]; v[1] = (5.0 / 4.0) * p[1]; v[2] = -(10.0 / 3.0) * p[2]; v[3] = 5 * p[3];
+    v[4] = -5 * p[4]; v[5] = (137.0 / 60.0) * p[5];
+  } else if (which == 1) {
+    v[0] = (1.0 / 20.0) * p[0]; v[1] = -(1.0 / 3.0) * p[1]; v[2] = p[2]; v[3] = -2 * p[3];
+    v[4] = (13.0 / 12.0) * p[4]; v[5] = (1.0 / 5.0) * p[5];
+  } else {
+    v[0] = (-1.0 / 30.0) * p[0]; v[1] = (1.0 / 4.0) * p[1]; v[2] = -p[2]; v[3] = (1.0 / 3.0) * p[3];
+    v[4] = (1.0 / 2.0) * p[4]; v[5] = -(1.0 / 20.0) * p[5];
+  }
+  return clip(kahan6(v), 50 * DBL_EPSILON);
+}
+__device__ __forceinline__ double phiL(double f, double d, double dd) { return f + ((1.0 / 2.0) * d + (1.0 / 12.0) * dd); }
+__device__ __forceinline__ double phiR(double f, double d, double dd) { return f - ((1.0 / 2.0) * d + (1.0 / 12.0) * dd); }
+
+// iterate a box: linear thread id -> (i,j,k), I = linear array index, pos/len along `axis`
+#define LEGACY_FOR_BOX(B)                                                                                   \
+  const long long e0_ = (B).hi[0] - (B).lo[0], e1_ = (B).hi[1] - (B).lo[1], e2_ = (B).hi[2] - (B).lo[2];    \
+  const long long ntot_ = e0_ * e1_ * e2_;                                                                  \
+  for (long long lin_ = blockIdx.x * (long long)blockDim.x + threadIdx.x; lin_ < ntot_;                     \
+       lin_ += (long long)gridDim.x * blockDim.x)
+
+#define LEGACY_INDEX(B, S)                                                        \
+  int c_[3];                                                                      \
+  c_[0] = (B).lo[0] + (int)(lin_ % e0_);                                          \
+  c_[1] = (B).lo[1] + (int)((lin_ / e0_) % e1_);                                  \
+  c_[2] = (B).lo[2] + (int)(lin_ / (e0_ * e1_));                                  \
+  const long long I = c_[0] * (S).st[0] + c_[1] * (S).st[1] + c_[2] * (S).st[2];
+
+// first derivative along `axis` over `dom` (inner central-6, first/last three cells one-sided);
+// MODE 0: src = phi.  MODE 1: src = a*b (product folded in).  MODE 2: src = a*b - c*d (symmetric scheme).
+template <int MODE>
+__device__ __forceinline__ double src_val(const double* a, const double* b, const double* c, const double* d, long long I) {
+  if (MODE == 0) return a[I];
+  if (MODE == 1) return a[I] * b[I];
+  return a[I] * b[I] - c[I] * d[I];
+}
+
+// materialise the (possibly product) source field over the WHOLE array (conservative_metrics.jl:39-41)
+template <int MODE>
+__global__ void k_legacy_source(LShape S, const double* a, const double* b, const double* c, const double* d, double* out) {
+  const long long n = (long long)S.n[0] * S.n[1] * S.n[2];
+  for (long long I = blockIdx.x * (long long)blockDim.x + threadIdx.x; I < n; I += (long long)gridDim.x * blockDim.x)
+    out[I] = src_val<MODE>(a, b, c, d, I);
+}
+
+__global__ void k_legacy_first(LShape S, LBox dom, int axis, const double* __restrict__ phi, double* __restrict__ d1) {
+  const long long s = S.st[axis];
+  const int lo = dom.lo[axis], n = dom.hi[axis] - dom.lo[axis];
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const int pos = c_[axis] - lo;
+    double r;
+    if (pos < 3) {
+      double p[6];
+      const long long b = I - pos * s;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) p[m] = phi[b + m * s];
+      r = mixed_lo(p, pos);
+    } else if (pos >= n - 3) {
+      double p[6];
+      const long long b = I + (n - 1 - pos) * s - 5 * s;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) p[m] = phi[b + m * s];
+      r = mixed_hi(p, pos - (n - 3));
+    } else {
+      r = central6(phi[I - 3 * s], phi[I - 2 * s], phi[I - s], phi[I + s], phi[I + 2 * s], phi[I + 3 * s]);
+    }
+    d1[I] = r;
+  }
+}
+
+__global__ void k_legacy_second(LShape S, LBox dom, int axis, const double* __restrict__ phi,
+                                const double* __restrict__ d1, double* __restrict__ d2) {
+  const long long s = S.st[axis];
+  const int lo = dom.lo[axis], n = dom.hi[axis] - dom.lo[axis];
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const int pos = c_[axis] - lo;
+    double r;
+    if (pos < 3) {
+      double p[6];
+      const long long b = I - pos * s;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) p[m] = d1[b + m * s];
+      r = mixed_lo(p, pos);
+    } else if (pos >= n - 3) {
+      double p[6];
+      const long long b = I + (n - 1 - pos) * s - 5 * s;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) p[m] = d1[b + m * s];
+      r = mixed_hi(p, pos - (n - 3));
+    } else {
+      double dd = -tol_diff(d1[I + s], d1[I - s]) / 2;
+      r = kahan3(2 * (phi[I + s] + phi[I - s]), -4 * phi[I], dd);
+    }
+    d2[I] = r;
+  }
+}
+
+// MEG cell-centre derivative (cell_center_derivs.jl:80-122).
+// POST 0: out = clip(v).  POST 1: out = clip(scale*(prev - v)) with prev = out's current content
+// (the second outer derivative of a conservative metric: hat = scale*(outer1 - outer2), then the eps clip).
+template <int POST>
+__global__ void k_legacy_meg(LShape S, LBox dom, int axis, const double* __restrict__ phi, const double* __restrict__ d1,
+                             const double* __restrict__ d2, double* __restrict__ out, double scale) {
+  const long long s = S.st[axis];
+  const int lo = dom.lo[axis], n = dom.hi[axis] - dom.lo[axis];
+  const double e = 50 * DBL_EPSILON;
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const int pos = c_[axis] - lo;
+    const double L0 = phiL(phi[I], d1[I], d2[I]), R0 = phiR(phi[I], d1[I], d2[I]);
+    double hi, lw;
+    if (pos == n - 1) hi = L0;
+    else hi = (L0 + phiR(phi[I + s], d1[I + s], d2[I + s])) / 2;
+    if (pos == 0) lw = R0;
+    else lw = (phiL(phi[I - s], d1[I - s], d2[I - s]) + R0) / 2;
+    double v = clip(hi - lw, e);
+    if (POST == 0) out[I] = v;
+    else {
+      double h = scale * (out[I] - v);
+      out[I] = clip(h, e);
+    }
+  }
+}
+
+// interpolate_to_edge! (interp_to_edges.jl:15-79): edge[I] holds the I+1/2 value
+__global__ void k_legacy_interp(LShape S, LBox dom, int axis, int whole, const double* __restrict__ phi,
+                                const double* __restrict__ d1, const double* __restrict__ d2, double* __restrict__ edge) {
+  const long long s = S.st[axis];
+  const int lo = dom.lo[axis], n = dom.hi[axis] - dom.lo[axis];
+  // whole-array domain: inner = [lo+1, hi-1), lo index lo+1 writes edge[lo], hi index hi-2 writes edge[hi-2];
+  // otherwise inner = dom, lo index lo writes edge[lo-1], hi index hi-1 writes edge[hi-1]
+  const int first = whole ? 1 : 0, last = whole ? n - 2 : n - 1;
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const int pos = c_[axis] - lo;
+    if (pos < first || pos > last) continue;
+    const double L0 = phiL(phi[I], d1[I], d2[I]);
+    if (pos == last) edge[I] = L0;
+    else edge[I] = (L0 + phiR(phi[I + s], d1[I + s], d2[I + s])) / 2;
+    if (pos == first) edge[I - s] = phiR(phi[I], d1[I], d2[I]);
+  }
+}
+
+__global__ void k_legacy_centroid(LShape S, LBox dom, const double* __restrict__ xn, const double* __restrict__ yn,
+                                  const double* __restrict__ zn, int off, int nn0, int nn1, double* cx, double* cy,
+                                  double* cz) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const long long sn1 = nn0, sn2 = (long long)nn0 * nn1;
+    const long long b = (c_[0] - off) + sn1 * (c_[1] - off) + sn2 * (c_[2] - off);
+    const double* A[3] = {xn, yn, zn};
+    double* C[3] = {cx, cy, cz};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double* a = A[q] + b;
+      // same summation order as 3d.jl:565-575
+      C[q][I] = 0.125 * (a[0] + a[1] + a[1 + sn1] + a[sn1] + a[sn2] + a[1 + sn2] + a[1 + sn1 + sn2] + a[sn1 + sn2]);
+    }
+  }
+}
+
+// jacobian_3d_kernel! (forward_metrics.jl:155-167): StaticArrays det = x0 . (x1 x x2) over the columns
+__global__ void k_legacy_det(LShape S, LBox dom, const double* __restrict__ fwd, long long nc, double* __restrict__ J) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const double a0 = fwd[0 * nc + I], b0 = fwd[1 * nc + I], c0 = fwd[2 * nc + I];   // x_xi, x_eta, x_zeta
+    const double a1 = fwd[3 * nc + I], b1 = fwd[4 * nc + I], c1 = fwd[5 * nc + I];   // y_*
+    const double a2 = fwd[6 * nc + I], b2 = fwd[7 * nc + I], c2 = fwd[8 * nc + I];   // z_*
+    J[I] = a0 * (b1 * c2 - b2 * c1) + a1 * (b2 * c0 - b0 * c2) + a2 * (b0 * c1 - b1 * c0);
+  }
+}
+
+__global__ void k_legacy_div9(LShape S, LBox dom, const double* __restrict__ hat, const double* __restrict__ J,
+                              long long nc, double* __restrict__ inv) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const double j = J[I];
+#pragma unroll
+    for (int m = 0; m < 9; ++m) inv[m * nc + I] = hat[m * nc + I] / j;
+  }
+}
+
+int blocks_for(long long n) {
+  long long b = (n + 255) / 256;
+  const long long cap = 148LL * 32;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+long long box_count(const LBox& b) {
+  return (long long)(b.hi[0] - b.lo[0]) * (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+}
+
+thread_local char g_legacy_err[256];
+
+}  // namespace
+
+extern "C" const char* cg_legacy_last_error(void) { return g_legacy_err; }
+
+// see include/curvigrid_cuda.h
+extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const double* y, const double* z,
+                                        const int64_t* nnode, int nhalo, int halo_coords_included, int symmetric,
+                                        double* cell, double* edge, double* centroid, double* scratch,
+                                        size_t scratch_bytes, void* stream, uint64_t* launches) {
+  g_legacy_err[0] = 0;
+  if (!x || !y || !z || !nnode || !cell || !edge || !scratch) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_meg6_update_3d: NULL argument");
+    return CG_ERR_ARG;
+  }
+  if (nhalo < 5) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "MEG6 needs nhalo >= 5 (DiscretizationSchemes.jl:53-60)");
+    return CG_ERR_ARG;
+  }
+  LShape S;
+  LBox full, dom;
+  for (int d = 0; d < 3; ++d) {
+    const int64_t nf = (halo_coords_included ? nnode[d] : nnode[d] + 2 * nhalo) - 1;
+    if (nf - 2 * nhalo < 6) {
+      snprintf(g_legacy_err, sizeof g_legacy_err, "MEG6 one-sided edge stencils need >= 6 interior cells per axis");
+      return CG_ERR_ARG;
+    }
+    S.n[d] = (int)nf;
+    full.lo[d] = 0;
+    full.hi[d] = (int)nf;
+    dom.lo[d] = nhalo;
+    dom.hi[d] = (int)nf - nhalo;
+  }
+  S.st[0] = 1;
+  S.st[1] = S.n[0];
+  S.st[2] = (long long)S.n[0] * S.n[1];
+  const long long nc = (long long)S.n[0] * S.n[1] * S.n[2];
+  if (scratch_bytes < (size_t)(7 * nc) * sizeof(double)) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "scratch too small: need %lld bytes", (long long)(7 * nc * 8));
+    return CG_ERR_ARG;
+  }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cudaSetDevice: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const LBox md = halo_coords_included ? full : dom;
+  const int whole = halo_coords_included ? 1 : 0;
+  uint64_t nl = 0;
+  double *cx = scratch, *cy = scratch + nc, *cz = scratch + 2 * nc;
+  double *d1 = scratch + 3 * nc, *d2 = scratch + 4 * nc, *src = scratch + 5 * nc, *tmp = scratch + 6 * nc;
+  cudaMemsetAsync(cell, 0, (size_t)28 * nc * sizeof(double), st);
+  cudaMemsetAsync(edge, 0, (size_t)57 * nc * sizeof(double), st);
+  cudaMemsetAsync(scratch, 0, (size_t)7 * nc * sizeof(double), st);
+  const int bl = blocks_for(box_count(md)), bw = blocks_for(nc);
+  k_legacy_centroid<<<bl, 256, 0, st>>>(S, md, x, y, z, halo_coords_included ? 0 : nhalo, (int)nnode[0], (int)nnode[1],
+                                         cx, cy, cz);
+  ++nl;
+  if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)3 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  double* C[3] = {cx, cy, cz};
+  double* J = cell;
+  double* fwd = cell + nc;       // [q*3+axis]
+  double* inv = cell + 10 * nc;  // [row*3+col]
+  double* hat = cell + 19 * nc;
+  auto ccd = [&](const double* phi, int axis, double* out, int post, double scale) {
+    k_legacy_first<<<bl, 256, 0, st>>>(S, md, axis, phi, d1);
+    k_legacy_second<<<bl, 256, 0, st>>>(S, md, axis, phi, d1, d2);
+    if (post == 0) k_legacy_meg<0><<<bl, 256, 0, st>>>(S, md, axis, phi, d1, d2, out, scale);
+    else k_legacy_meg<1><<<bl, 256, 0, st>>>(S, md, axis, phi, d1, d2, out, scale);
+    nl += 3;
+  };
+  for (int q = 0; q < 3; ++q)
+    for (int ax = 0; ax < 3; ++ax) ccd(C[q], ax, fwd + (long long)(q * 3 + ax) * nc, 0, 1.0);
+  k_legacy_det<<<bl, 256, 0, st>>>(S, md, fwd, nc, J);
+  ++nl;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const int q1 = (c + 1) % 3, q2 = (c + 2) % 3, s = (r + 1) % 3, u = (r + 2) % 3;
+      double* h = hat + (long long)(r * 3 + c) * nc;
+      const double *a_s = fwd + (long long)(q1 * 3 + s) * nc, *a_u = fwd + (long long)(q1 * 3 + u) * nc;
+      const double *b_s = fwd + (long long)(q2 * 3 + s) * nc, *b_u = fwd + (long long)(q2 * 3 + u) * nc;
+      // outer1 = (inner1)_u -> h ; then h = clip(scale*(h - (inner2)_s))
+      if (symmetric) k_legacy_source<2><<<bw, 256, 0, st>>>(S, a_s, C[q2], b_s, C[q1], src);
+      else k_legacy_source<1><<<bw, 256, 0, st>>>(S, a_s, C[q2], nullptr, nullptr, src);
+      ccd(src, u, h, 0, 1.0);
+      if (symmetric) k_legacy_source<2><<<bw, 256, 0, st>>>(S, a_u, C[q2], b_u, C[q1], src);
+      else k_legacy_source<1><<<bw, 256, 0, st>>>(S, a_u, C[q2], nullptr, nullptr, src);
+      ccd(src, s, h, 1, symmetric ? (1.0 / 2.0) : 1.0);
+      nl += 2;
+    }
+  k_legacy_div9<<<bl, 256, 0, st>>>(S, md, hat, J, nc, inv);
+  ++nl;
+  for (int ax = 0; ax < 3; ++ax) {
+    double* E = edge + (long long)ax * 19 * nc;
+    for (int m = 0; m < 19; ++m) {
+      const double* phi = m == 0 ? J : cell + (long long)(9 + m) * nc;  // J, inv 0..8, hat 0..8
+      k_legacy_first<<<bl, 256, 0, st>>>(S, md, ax, phi, d1);
+      k_legacy_second<<<bl, 256, 0, st>>>(S, md, ax, phi, d1, d2);
+      k_legacy_interp<<<bl, 256, 0, st>>>(S, md, ax, whole, phi, d1, d2, E + (long long)m * nc);
+      nl += 3;
+    }
+  }
+  (void)tmp;
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "legacy kernels: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  if (launches) *launches = nl;
+  return CG_OK;
+}

@@ -1,0 +1,123 @@
+"""Host-side mirror of the reference's LEGACY curvilinear grid for the metric path.
+
+    CurvilinearGrid3D(x, y, z, :meg6 | :meg6_symmetric; halo_coords_included)   3d.jl:51-115
+    update!(mesh, force, include_halo_region)                                   3d.jl:472-493
+    mesh.cell_center_metrics / mesh.edge_metrics (SoA, metric_soa.jl:2-170)
+    mesh.centroid_coordinates
+
+(paths under /root/reference/src/grids/curvilinear_mapped_grids/ and src/grids/).  The device
+pipeline is cg_legacy_meg6_update_3d in libcurvigrid_cuda.so (csrc/cg_legacy.cu).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib as L
+
+_SCHEMES = {"meg6": False, "meg6_symmetric": True}
+_AX = ("ξ", "η", "ζ")
+_X = ("x₁", "x₂", "x₃")
+
+
+class CurvilinearGrid3D:
+    nhalo = 5  # MEG6 (DiscretizationSchemes.jl:53-60)
+
+    def __init__(self, x, y, z, discretization_scheme="meg6", *, device=None, halo_coords_included=False,
+                 is_static=False, init_metrics=True):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("curvigrid: a CUDA device is required (no CPU fallback)")
+        key = str(discretization_scheme).lower().lstrip(":")
+        if key not in _SCHEMES:
+            # GridTypes.jl:595-626 knows :meg2/:meg4 too; their one-sided edge kernels only exist for
+            # SixthOrder in the reference (derivative_kernels.jl:184-292), so only MEG6 is buildable
+            raise ValueError(f"Unknown or unsupported discretization scheme {discretization_scheme!r}; "
+                             "use :meg6 or :meg6_symmetric")
+        self.symmetric = _SCHEMES[key]
+        self.discretization_scheme_name = key
+        self.device = int(torch.cuda.current_device() if device is None else device)
+        self.halo_coords_included = bool(halo_coords_included)
+        self.is_static = bool(is_static)
+        shp = tuple(np.shape(x))
+        if tuple(np.shape(y)) != shp or tuple(np.shape(z)) != shp:
+            raise ValueError("Size mismatch for the given x, y, z coordinate arrays, they must all be the same")
+        self.nnodes = shp
+        h = self.nhalo
+        self.celldims_full = tuple(s - 1 + (0 if halo_coords_included else 2 * h) for s in shp)
+        dev = f"cuda:{self.device}"
+        self._nodes = [torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(2, 1, 0))).to(dev)
+                       for a in (x, y, z)]
+        nc = int(np.prod(self.celldims_full))
+        self._cell = torch.zeros((28, nc), dtype=torch.float64, device=dev)
+        self._edge = torch.zeros((3, 19, nc), dtype=torch.float64, device=dev)
+        self._cent = torch.zeros((3, nc), dtype=torch.float64, device=dev)
+        self._scratch = torch.empty((7, nc), dtype=torch.float64, device=dev)
+        self.launches = 0
+        if init_metrics:
+            update(self, True, self.halo_coords_included)
+
+    # --- SoA views in the reference's naming (arrays shaped [nk, nj, ni]) ------------------------
+    def _v(self, t):
+        return t.view(tuple(reversed(self.celldims_full)))
+
+    @property
+    def centroid_coordinates(self):
+        return {"x": self._v(self._cent[0]), "y": self._v(self._cent[1]), "z": self._v(self._cent[2])}
+
+    @property
+    def cell_center_metrics(self):
+        c = self._cell
+        out = {"J": self._v(c[0])}
+        for q in range(3):
+            out[_X[q]] = {_AX[a]: self._v(c[1 + 3 * q + a]) for a in range(3)}
+        for r in range(3):
+            out[_AX[r]] = {_X[k]: self._v(c[10 + 3 * r + k]) for k in range(3)}
+            out[_AX[r] + "̂"] = {_X[k]: self._v(c[19 + 3 * r + k]) for k in range(3)}
+        return out
+
+    @property
+    def edge_metrics(self):
+        names = ("i₊½", "j₊½", "k₊½")
+        out = {}
+        for ax in range(3):
+            e = self._edge[ax]
+            d = {"J": self._v(e[0])}
+            for r in range(3):
+                d[_AX[r]] = {_X[k]: self._v(e[1 + 3 * r + k]) for k in range(3)}
+                d[_AX[r] + "̂"] = {_X[k]: self._v(e[10 + 3 * r + k]) for k in range(3)}
+            out[names[ax]] = d
+        return out
+
+
+def update(mesh, force=False, include_halo_region=False):
+    """update!(mesh::AbstractCurvilinearGrid3D, force, include_halo_region) — 3d.jl:472-493."""
+    import torch
+    if mesh.is_static and not force:
+        import warnings
+        warnings.warn("Attempting to update grid metrics when grid.is_static = true!")
+        return None
+    if bool(include_halo_region) != mesh.halo_coords_included:
+        # the reference evaluates on cell.full only when the node arrays carry real halo coordinates
+        raise ValueError("include_halo_region must match halo_coords_included")
+    nn = (ctypes.c_int64 * 3)(*mesh.nnodes)
+    nl = ctypes.c_uint64()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream(mesh.device).cuda_stream)
+    rc = L.lib().cg_legacy_meg6_update_3d(
+        mesh.device, p(mesh._nodes[0]), p(mesh._nodes[1]), p(mesh._nodes[2]), nn, mesh.nhalo,
+        int(mesh.halo_coords_included), int(mesh.symmetric), p(mesh._cell), p(mesh._edge), p(mesh._cent),
+        p(mesh._scratch), ctypes.c_size_t(mesh._scratch.numel() * 8), st, ctypes.byref(nl))
+    if rc != L.CG_OK:
+        msg = L.lib().cg_legacy_last_error().decode()
+        raise (L.CurvigridArgumentError if rc == L.CG_ERR_ARG else L.CurvigridError)(rc, msg)
+    mesh.launches = int(nl.value)
+    return None
+
+
+def set_node_coordinates(mesh, x, y, z):
+    """Mutate mesh.node_coordinates in place (the moving-mesh use of the legacy path), then call update."""
+    import torch
+    for t, a in zip(mesh._nodes, (x, y, z)):
+        t.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(2, 1, 0))))

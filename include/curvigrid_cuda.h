@@ -162,6 +162,25 @@ int cg_discrete_metrics_host(int device, int dim, int dtype, const void* x, cons
                              const int64_t* ncell, int nhalo, int halo_coords_included, int scheme,
                              void* cell_fwd, void* cell_inv, void* face_fwd, void* face_inv, void* face_cons);
 
+/*
+ * Legacy path: CurvilinearGrid3D(x, y, z, :meg6 | :meg6_symmetric) `update!(mesh, force, include_halo_region)`
+ * (src/grids/curvilinear_mapped_grids/3d.jl:472-493 -> src/metric_schemes/MetricDiscretizationSchemes.jl:20-89):
+ * centroids, MEG6 forward metrics, Thomas-Lombard (or Nonomura symmetric) conservative metrics and the 57 edge
+ * interpolations, FP64.  x,y,z: DEVICE node arrays of extents nnode[3] (interior nodes, or node.full when
+ * halo_coords_included).  With ncell = prod(cell.full dims), cell.full = node.full - 1:
+ *   cell     [28][ncell]   0 J | 1..9 d x_q/d xi_a at [1+3q+a] | 10..18 inverse [10+3row+col] | 19..27 hatted
+ *   edge     [3][19][ncell] per axis: 0 J | 1..9 inverse | 10..18 hatted; storage index I = face I+1/2
+ *   centroid [3][ncell]    (may be NULL)
+ *   scratch  >= 7*ncell doubles of device memory
+ * (the SoA of metric_soa.jl:2-170 without the never-written `.t` arrays).  Values are defined on the metric
+ * domain (cell.domain, or cell.full when halo_coords_included), zero elsewhere.
+ */
+int cg_legacy_meg6_update_3d(int device, const double* x, const double* y, const double* z, const int64_t* nnode,
+                             int nhalo, int halo_coords_included, int symmetric, double* cell, double* edge,
+                             double* centroid, double* scratch, size_t scratch_bytes, void* stream,
+                             uint64_t* launches);
+const char* cg_legacy_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

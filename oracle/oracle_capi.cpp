@@ -205,4 +205,11 @@ int cgo_legacy_meg6_3d(const double* x, const double* y, const double* z, const 
   return 0;
 }
 
+// stencil probes for the pins (derivative_stencils.jl:34-45, 97-175, 180-193)
+double cgo_legacy_central6(const double* v) { return cgl::central6(v[0], v[1], v[2], v[3], v[4], v[5]); }
+void cgo_legacy_mixed(const double* v, double* lo3, double* hi3) {
+  cgl::mixed_lo(v, lo3);
+  cgl::mixed_hi(v, hi3);
+}
+
 }  // extern "C"

@@ -1,0 +1,78 @@
+"""Legacy MEG6 pipeline (CurvilinearGrid3D :meg6 / :meg6_symmetric) on the GPU against the
+array-pass oracle.  Both sides keep the reference's operation order and are built without FMA
+contraction, so agreement is expected to the last bit almost everywhere; the gate is 1e-13 relative
+(per array, against the array's max) plus the reference's own known answers."""
+import numpy as np
+import pytest
+
+from util import mild_nodes
+
+pytestmark = pytest.mark.gpu
+
+
+def _dom(nfull, h=5):
+    idx = np.meshgrid(*[np.arange(h, n - h) for n in nfull], indexing="ij")
+    return (idx[0] + nfull[0] * (idx[1] + nfull[1] * idx[2])).ravel()
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+@pytest.mark.parametrize("halo_included", [False, True])
+def test_legacy_matches_oracle(cg, oracle, symmetric, halo_included):
+    shape = (13, 12, 14) if not halo_included else (19, 18, 20)
+    nodes = mild_nodes(shape, seed=41)
+    ref = oracle.legacy_meg6_3d(nodes, 5, halo_coords_included=halo_included, symmetric=symmetric)
+    mesh = cg.legacy.CurvilinearGrid3D(*nodes, "meg6_symmetric" if symmetric else "meg6",
+                                       halo_coords_included=halo_included)
+    assert mesh.celldims_full == ref["nfull"]
+    cell, edge, cent = mesh._cell.cpu().numpy(), mesh._edge.cpu().numpy(), mesh._cent.cpu().numpy()
+    sel = slice(None) if halo_included else _dom(ref["nfull"])
+    assert np.array_equal(cent, ref["centroid"])
+    for name, got, want in (("cell", cell, ref["cell"]), ("edge", edge, ref["edge"])):
+        g, w = got[..., sel], want[..., sel]
+        if halo_included and name == "edge":
+            continue  # last planes are not written by interpolate_to_edge!; compared below on the valid range
+        scale = np.abs(w).max(axis=-1, keepdims=True)
+        scale[scale == 0] = 1.0
+        err = (np.abs(g - w) / scale).max()
+        assert err <= 1e-13, (name, err)
+        assert (g == w).mean() > 0.99, (name, (g == w).mean())
+    # edges: everything the reference writes (incl. the lo-1 face plane) matches
+    w, g = ref["edge"], edge
+    scale = np.abs(w).max(axis=-1, keepdims=True)
+    scale[scale == 0] = 1.0
+    assert (np.abs(g - w) / scale).max() <= 1e-13
+
+
+def test_legacy_rectilinear_known_answers(cg):
+    """test_3d.jl:137-147 / rectilinear_compare_to_standard.jl: forward = (dx,dy,dz), J, hatted = J/dx..."""
+    wl = cg.workloads
+    x, y, z, dx, dy, dz = wl.rectilinear_nodes_3d(0.0, 2.0, 1.0, 3.0, -1.0, 2.0, 8, 9, 10)
+    mesh = cg.legacy.CurvilinearGrid3D(x, y, z, "meg6")
+    m = mesh.cell_center_metrics
+    h = 5
+    sl = (slice(h, -h),) * 3
+    J = dx * dy * dz
+    assert abs(m["J"][sl].cpu().numpy() - J).max() < 1e-14
+    assert abs(m["x₁"]["ξ"][sl].cpu().numpy() - dx).max() < 1e-14
+    assert abs(m["x₂"]["η"][sl].cpu().numpy() - dy).max() < 1e-14
+    assert abs(m["x₃"]["ζ"][sl].cpu().numpy() - dz).max() < 1e-14
+    assert abs(m["x₁"]["η"][sl].cpu().numpy()).max() == 0.0
+    assert abs(m["ξ"]["x₁"][sl].cpu().numpy() - 1 / dx).max() < 1e-12
+    assert abs(m["ξ̂"]["x₁"][sl].cpu().numpy() - J / dx).max() < 1e-14
+    e = mesh.edge_metrics["i₊½"]
+    assert abs(e["ξ̂"]["x₁"][sl].cpu().numpy() - J / dx).max() < 1e-14
+    assert abs(e["J"][sl].cpu().numpy() - J).max() < 1e-14
+
+
+def test_legacy_errors_and_static(cg):
+    nodes = mild_nodes((12, 12, 12), seed=1)
+    with pytest.raises(ValueError):
+        cg.legacy.CurvilinearGrid3D(*nodes, "meg9")
+    with pytest.raises(ValueError):
+        cg.legacy.CurvilinearGrid3D(nodes[0], nodes[1][:-1], nodes[2], "meg6")
+    with pytest.raises(cg.CurvigridArgumentError):
+        cg.legacy.CurvilinearGrid3D(*mild_nodes((5, 12, 12), seed=1), "meg6")   # < 6 interior cells
+    mesh = cg.legacy.CurvilinearGrid3D(*nodes, "meg6", is_static=True)
+    with pytest.warns(UserWarning):
+        cg.legacy.update(mesh, False, False)
+    assert mesh.launches > 0

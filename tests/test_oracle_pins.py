@@ -160,3 +160,84 @@ def test_golden_vectors_unchanged(oracle):
             r = oracle.mapped_eval(z["terms"], float(z["t"]), tuple(int(c) for c in z["celldims"]), int(z["nhalo"]), sch)
             for k in ("cell_fwd", "cell_inv", "face_fwd", "face_inv", "face_cons"):
                 assert np.allclose(r[k], z[f"{sch}_{k}"], rtol=1e-13, atol=1e-13), (name, sch, k)
+
+
+# ---------------------------------------------------------------------------
+# legacy MEG6 pipeline
+# ---------------------------------------------------------------------------
+def test_legacy_stencil_floating_point_error(oracle):
+    """test_discretizations.jl:193-221: Kahan sum + tol_diff zero the derivative of 1e4 + O(100 eps) noise."""
+    import ctypes
+    lib = oracle.lib()
+    lib.cgo_legacy_central6.restype = ctypes.c_double
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        v = 1e4 * np.ones(6) + 100 * EPS * rng.random(6)
+        naive = -1 / 60 * v[0] + 3 / 20 * v[1] - 3 / 4 * v[2] + 3 / 4 * v[3] - 3 / 20 * v[4] + 1 / 60 * v[5]
+        d = lib.cgo_legacy_central6(v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        assert d == 0.0
+    assert abs(naive) >= 0.0
+
+
+def test_legacy_stencils_exact_on_polynomials(oracle):
+    """test_discretizations.jl:41-146 (derivatives of linear fields) + order of the 6-point one-sided stencils:
+    exact for polynomials up to degree 5."""
+    import ctypes
+    lib = oracle.lib()
+    lib.cgo_legacy_central6.restype = ctypes.c_double
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    xs = np.arange(6, dtype=np.float64)
+    for deg in range(1, 6):
+        f = 0.3 * xs ** deg + 1.7 * xs + 2.0
+        df = 0.3 * deg * xs ** (deg - 1) + 1.7
+        lo, hi = np.zeros(3), np.zeros(3)
+        lib.cgo_legacy_mixed(dp(f), dp(lo), dp(hi))
+        assert np.allclose(lo, df[:3], rtol=1e-11, atol=1e-11), (deg, lo, df[:3])
+        assert np.allclose(hi, df[3:], rtol=1e-11, atol=1e-11), (deg, hi, df[3:])
+    xs7 = np.arange(-3, 4, dtype=np.float64)
+    for deg in range(1, 7):
+        f = 0.2 * xs7 ** deg + 0.9 * xs7
+        w = np.ascontiguousarray(np.delete(f, 3))
+        d = lib.cgo_legacy_central6(dp(w))
+        assert abs(d - (0.9 if deg > 1 else 1.1)) < 1e-11
+
+
+def test_legacy_rectilinear_and_2d_style_known_answers(oracle):
+    """test_3d.jl:137-147 and test_discretizations.jl:148-191 (x=i, y=2j -> x_xi=1, y_eta=2, xi_x=1, eta_y=1/2),
+    here on the 3-D pipeline with z = 3k."""
+    n = (17, 18, 19)
+    i, j, k = np.meshgrid(*[np.arange(1, m + 1, dtype=np.float64) for m in n], indexing="ij")
+    r = oracle.legacy_meg6_3d([i, 2 * j, 3 * k], 5, halo_coords_included=True)
+    nf = r["nfull"]
+    c = r["cell"]
+    idx = np.meshgrid(*[np.arange(5, m - 5) for m in nf], indexing="ij")
+    dom = (idx[0] + nf[0] * (idx[1] + nf[1] * idx[2])).ravel()
+    assert np.allclose(c[1][dom], 1.0) and np.allclose(c[5][dom], 2.0) and np.allclose(c[9][dom], 3.0)
+    assert np.allclose(c[10][dom], 1.0) and np.allclose(c[14][dom], 0.5) and np.allclose(c[18][dom], 1 / 3)
+    assert np.allclose(c[0][dom], 6.0)
+    assert np.abs(c[[2, 3, 4, 6, 7, 8]][:, dom]).max() == 0.0
+    # halo-included: metrics are evaluated on cell.full with one-sided stencils at the array edges
+    assert np.allclose(c[1], 1.0) and np.allclose(c[0], 6.0)
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_legacy_wavy_gcl_small(oracle, symmetric):
+    """The legacy conservative metrics are GCL-consistent to ~1e-14 on the wavy mesh
+    (test_2d_axisymmetric.jl / test_3d_spherical.jl assert eps-level GCL for :meg6_symmetric)."""
+    x, y, z = wl.wavy_nodes_3d(16, 16, 16)
+    r = oracle.legacy_meg6_3d([x, y, z], 5, symmetric=symmetric)
+    nf = r["nfull"]
+    E = r["edge"].reshape(3, 19, nf[2], nf[1], nf[0])
+    h = 5
+    worst = 0.0
+    for c in range(3):
+        tot = 0.0
+        for ax in range(3):
+            A = E[ax, 10 + 3 * ax + c]
+            hi = [slice(h, nf[2] - h), slice(h, nf[1] - h), slice(h, nf[0] - h)]
+            lo = list(hi)
+            d = 2 - ax
+            lo[d] = slice(h - 1, (nf[2], nf[1], nf[0])[d] - h - 1)
+            tot = tot + A[tuple(hi)] - A[tuple(lo)]
+        worst = max(worst, np.abs(tot).max())
+    assert worst < 5e-14
