@@ -25,6 +25,9 @@ namespace cg {
 #ifndef CG_MINB
 #define CG_MINB 2
 #endif
+#ifndef CG_ZETA_MINB
+#define CG_ZETA_MINB 2
+#endif
 constexpr int WARP_OUT = 29;  // output cells per warp along xi
 constexpr unsigned FULLMASK = 0xffffffffu;
 
@@ -32,24 +35,30 @@ template <class T>
 struct PF {
   Form4<T> q[3];
 };
+#ifndef CG_IX
+#define CG_IX uint32_t
+#endif
+// node index type of the marching kernels: 32-bit (launchers fall back to the gather kernels when the padded
+// node array has >= 2^31 elements); one IMAD.WIDE per address instead of 64-bit add chains
+using Ix = CG_IX;
 template <class T>
 struct NodeP {
   const T* q[3];
-  int64_t s1, s2;
+  Ix s1, s2;
 };
 
 template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
 // L1 prefetch of the node at linear index b for the three coordinates (the marching kernels are
 // load-latency bound at 8 warps/SM: the planes the NEXT iteration touches first are fetched now)
 template <class T>
-CG_D void pf3(const NodeP<T>& N, int64_t b) {
+CG_D void pf3(const NodeP<T>& N, Ix b) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(N.q[q] + b));
 }
 
 // zeta-plane forms (fixed k), transverse (xi, eta)
 template <class T>
-CG_D PF<T> zplane(const NodeP<T>& N, int64_t b) {
+CG_D PF<T> zplane(const NodeP<T>& N, Ix b) {
   PF<T> f;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -60,7 +69,7 @@ CG_D PF<T> zplane(const NodeP<T>& N, int64_t b) {
 }
 // eta-plane forms (fixed j), transverse (xi, zeta)
 template <class T>
-CG_D PF<T> eplane(const NodeP<T>& N, int64_t b) {
+CG_D PF<T> eplane(const NodeP<T>& N, Ix b) {
   PF<T> f;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -71,7 +80,7 @@ CG_D PF<T> eplane(const NodeP<T>& N, int64_t b) {
 }
 // xi-plane forms (fixed i), transverse (eta, zeta)
 template <class T>
-CG_D PF<T> xplane(const NodeP<T>& N, int64_t b) {
+CG_D PF<T> xplane(const NodeP<T>& N, Ix b) {
   PF<T> f;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -223,26 +232,26 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = D.se[1]; N.s2 = D.se[2];
+  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
   const bool full = O.face_cons[0] != nullptr;
   const bool do_cell = (what & 1) && (PART & 2);
   const bool do_cons = (what & 2) && (PART & 1);
   const bool do_gf = (what & 2) && (PART & 2) && full;
-  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
+  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
 
   T psi_bot[6];
   if (do_cons) {
     T wp[6], wm[6];
-    const int64_t b = nbase + (k0 - 1) * N.s2;
+    const Ix b = nbase + (Ix)(k0 - 1) * N.s2;
     eface6<T, SCH>(zplane(N, b), zplane(N, b + N.s2), zplane(N, b + 2 * N.s2), wp, wm);
 #pragma unroll
     for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + shfl_dn(wm[e], 1);
   }
-  PF<T> z0 = zplane(N, nbase + k0 * N.s2), z1 = zplane(N, nbase + (k0 + 1) * N.s2);
+  PF<T> z0 = zplane(N, nbase + (Ix)k0 * N.s2), z1 = zplane(N, nbase + (Ix)(k0 + 1) * N.s2);
   for (int64_t m = k0; m < k1; ++m) {
-    const int64_t b = nbase + m * N.s2;
+    const Ix b = nbase + (Ix)m * N.s2;
     const int64_t cl = i + j * cs1 + m * cs2;
     if (m + 1 < k1) {  // next iteration's new node rows: plane m+3 (rows j, j+1), plane m+2 (rows j-1, j+2)
       pf3(N, b + 3 * N.s2);
@@ -377,27 +386,27 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_eta(Dims D, con
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = D.se[1]; N.s2 = D.se[2];
+  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
   const bool full = O.face_cons[1] != nullptr;
   const bool do_cons = PART & 1, do_gf = (PART & 2) && full;
-  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
+  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
 
   // Psi^{zeta->eta} on the xi-edge (j+1/2, m-1/2): zeta faces of cells j and j+1, reconstructed along eta
-  auto psi_zeta = [&](int64_t b, T (&psi)[6]) {
+  auto psi_zeta = [&](Ix b, T (&psi)[6]) {
     // b = node (ic, j, plane below the face's lower cell)
     T wp[6], wm[6], wq[6], wn[6];
     eface6<T, SCH>(swap_uv(zplane(N, b)), swap_uv(zplane(N, b + N.s2)), swap_uv(zplane(N, b + 2 * N.s2)), wp, wm);
-    const int64_t bn = b + N.s1;
+    const Ix bn = b + N.s1;
     eface6<T, SCH>(swap_uv(zplane(N, bn)), swap_uv(zplane(N, bn + N.s2)), swap_uv(zplane(N, bn + 2 * N.s2)), wq, wn);
 #pragma unroll
     for (int e = 0; e < 6; ++e) psi[e] = wp[e] + wn[e];
   };
   T psi_bot[6];
-  if (do_cons) psi_zeta(nbase + (k0 - 1) * N.s2, psi_bot);
+  if (do_cons) psi_zeta(nbase + (Ix)(k0 - 1) * N.s2, psi_bot);
   for (int64_t m = k0; m < k1; ++m) {
-    const int64_t b = nbase + m * N.s2;
+    const Ix b = nbase + (Ix)m * N.s2;
     const int64_t cl = i + j * cs1 + m * cs2;
     if (do_gf) {
       // ---- reconstructed inverse Jacobian on the eta face: cells j and j+1 ----
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_eta(Dims D, con
         T L[3][3], R[3][3], R1[3][3];
 #pragma unroll
         for (int cell = 0; cell < 2; ++cell) {
-          const int64_t bc = b + cell * N.s1;
+          const Ix bc = b + (Ix)cell * N.s1;
           T c[3][8];
           taylor_from_z(zplane(N, bc), zplane(N, bc + N.s2), c);
           T F[3][3], G[3][3], Fa[3], Fb[3];
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_eta(Dims D, con
     {
       T wp[6], wm[6], wq[6], wn[6];
       eface6<T, SCH>(xplane(N, b), xplane(N, b + 1), xplane(N, b + 2), wp, wm);
-      const int64_t bn = b + N.s1;
+      const Ix bn = b + N.s1;
       eface6<T, SCH>(xplane(N, bn), xplane(N, bn + 1), xplane(N, bn + 2), wq, wn);
 #pragma unroll
       for (int e = 0; e < 6; ++e) psi_x[e] = wp[e] + wn[e];
@@ -536,10 +545,10 @@ __global__ void __launch_bounds__(32 * RY, MB) k_face_eta_sh(Dims D, const T* ex
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = D.se[1]; N.s2 = D.se[2];
+  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
   const bool full = O.face_cons[1] != nullptr;
-  const int64_t nbase = (ic + 1) + (jc + 1) * N.s1 + N.s2;
+  const Ix nbase = (Ix)(ic + 1) + (Ix)(jc + 1) * N.s1 + N.s2;
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
   auto S = [&](int slot, int row) -> T& { return sm[(slot * RY + row) * 32 + lane]; };
   const int rn = r + 1 < RY ? r + 1 : r, rn2 = r + 2 < RY ? r + 2 : r, rp = r > 0 ? r - 1 : r;
@@ -548,7 +557,7 @@ __global__ void __launch_bounds__(32 * RY, MB) k_face_eta_sh(Dims D, const T* ex
   T psi_bot[6];
   {
     T wp[6], wm[6];
-    const int64_t b = nbase + (k0 - 1) * N.s2;
+    const Ix b = nbase + (Ix)(k0 - 1) * N.s2;
     eface6<T, SCH>(swap_uv(zplane(N, b)), swap_uv(zplane(N, b + N.s2)), swap_uv(zplane(N, b + 2 * N.s2)), wp, wm);
 #pragma unroll
     for (int e = 0; e < 6; ++e) S(e, r) = wm[e];
@@ -557,9 +566,9 @@ __global__ void __launch_bounds__(32 * RY, MB) k_face_eta_sh(Dims D, const T* ex
     for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + S(e, rn);
     __syncthreads();
   }
-  PF<T> z0 = zplane(N, nbase + k0 * N.s2), z1 = zplane(N, nbase + (k0 + 1) * N.s2);
+  PF<T> z0 = zplane(N, nbase + (Ix)k0 * N.s2), z1 = zplane(N, nbase + (Ix)(k0 + 1) * N.s2);
   for (int64_t m = k0; m < k1; ++m) {
-    const int64_t b = nbase + m * N.s2;
+    const Ix b = nbase + (Ix)m * N.s2;
     const int64_t cl = i + j * cs1 + m * cs2;
     PF<T> z2 = zplane(N, b + 2 * N.s2);
     T wpz[6], wpx[6];
@@ -667,7 +676,7 @@ struct CellZ {
 };
 
 template <class T, int SCH, bool GF>
-CG_D void cellz_compute(const NodeP<T>& N, int64_t b, bool full, T lam1, T lam2, CellZ<T>& o) {
+CG_D void cellz_compute(const NodeP<T>& N, Ix b, bool full, T lam1, T lam2, CellZ<T>& o) {
   // b = node (ic, j, p) of the cell's low corner
   {
     // eta faces j-1/2 and j+1/2: eta-planes j-1 .. j+2, forms (xi,zeta) -> need (u,v) = (zeta, xi)
@@ -725,9 +734,9 @@ __global__ void __launch_bounds__(128, 3) k_gface_zeta(Dims D, const T* ex, cons
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = D.se[1]; N.s2 = D.se[2];
+  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
+  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
   auto states = [&](const PF<T>& lo, const PF<T>& hi, T (&L)[3][3], T (&R)[3][3]) {
     T c[3][8];
@@ -743,13 +752,13 @@ __global__ void __launch_bounds__(128, 3) k_gface_zeta(Dims D, const T* ex, cons
     inv3(F, G);
     ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, L, R);
   };
-  PF<T> z0 = zplane(N, nbase + k0 * N.s2), z1 = zplane(N, nbase + (k0 + 1) * N.s2);
+  PF<T> z0 = zplane(N, nbase + (Ix)k0 * N.s2), z1 = zplane(N, nbase + (Ix)(k0 + 1) * N.s2);
   T Lp[3][3], Rtmp[3][3];
   states(z0, z1, Lp, Rtmp);
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl = i + j * cs1 + m * cs2;
-    if (m + 1 < k1) pf3(N, nbase + (m + 3) * N.s2), pf3(N, nbase + (m + 3) * N.s2 + N.s1);
-    PF<T> z2 = zplane(N, nbase + (m + 2) * N.s2);
+    if (m + 1 < k1) pf3(N, nbase + (Ix)(m + 3) * N.s2), pf3(N, nbase + (Ix)(m + 3) * N.s2 + N.s1);
+    PF<T> z2 = zplane(N, nbase + (Ix)(m + 2) * N.s2);
     T Ln[3][3], Rn[3][3], Gf[3][3], Ff[3][3];
     states(z1, z2, Ln, Rn);  // cell m+1
 #pragma unroll
@@ -769,10 +778,23 @@ __global__ void __launch_bounds__(128, 3) k_gface_zeta(Dims D, const T* ex, cons
   }
 }
 
+// per-thread state carried from plane to plane, parked in shared memory (slot-major: conflict-free) so it
+// does not occupy registers across the whole loop body
+template <class T, int NSLOT>
+struct Parked {
+  T* base;
+  __device__ __forceinline__ T& operator[](int slot) const { return base[slot * 128]; }
+};
+
 template <class T, int SCH, int PART>
-__global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
-                                                                     MetricOut<T> O, int kchunk) {
+__global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
+                                                                MetricOut<T> O, int kchunk) {
   constexpr bool GF = (PART & 2) != 0;
+  __shared__ T park_mem[33 * 128];
+  const int tid_ = threadIdx.y * 32 + threadIdx.x;
+  Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * 128 + tid_}, P1{park_mem + 12 * 128 + tid_},
+      vp_prev{park_mem + 18 * 128 + tid_};
+  Parked<T, 9> Lpk{park_mem + 24 * 128 + tid_};
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
@@ -784,23 +806,22 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, co
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = D.se[1]; N.s2 = D.se[2];
+  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
   const bool full = O.face_cons[2] != nullptr;
-  const int64_t nbase = (ic + 1) + (j + 1) * N.s1 + N.s2;
+  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
 
-  // carried state: W+ of the cell below the face, line partial sums, L state
-  T wpe[6], wpx[6], P1[6], vp_prev[6], Lp[3][3];
+  // carried state: W+ of the cell below the face, line partial sums, L state (parked in shared memory)
   {
     CellZ<T> cm;  // cell k0 - 1
     if (full) {
-      cellz_compute<T, SCH, GF>(N, nbase + (k0 - 1) * N.s2, true, lam1, lam2, cm);
+      cellz_compute<T, SCH, GF>(N, nbase + (Ix)(k0 - 1) * N.s2, true, lam1, lam2, cm);
 #pragma unroll
       for (int e = 0; e < 6; ++e) vp_prev[e] = cm.ln[e].vp;
     }
     CellZ<T> c0;  // cell k0
-    cellz_compute<T, SCH, GF>(N, nbase + k0 * N.s2, full, lam1, lam2, c0);
+    cellz_compute<T, SCH, GF>(N, nbase + (Ix)k0 * N.s2, full, lam1, lam2, c0);
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
       wpe[e] = c0.wpe[e];
@@ -814,20 +835,20 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, co
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) Lp[r][cc] = c0.L[r][cc];
+        for (int cc = 0; cc < 3; ++cc) Lpk[3 * r + cc] = c0.L[r][cc];
     }
   }
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl = i + j * cs1 + m * cs2;
     if (m + 1 < k1) {  // next iteration: plane m+4 rows j, j+1; plane m+3 rows j-1, j+2
-      const int64_t bp = nbase + (m + 3) * N.s2;
+      const Ix bp = nbase + (Ix)(m + 3) * N.s2;
       pf3(N, bp + N.s2);
       pf3(N, bp + N.s2 + N.s1);
       pf3(N, bp - N.s1);
       pf3(N, bp + 2 * N.s1);
     }
     CellZ<T> cf;  // front cell m + 1
-    cellz_compute<T, SCH, GF>(N, nbase + (m + 1) * N.s2, full, lam1, lam2, cf);
+    cellz_compute<T, SCH, GF>(N, nbase + (Ix)(m + 1) * N.s2, full, lam1, lam2, cf);
     T Gh[3][3];  // rows 0 xi, 1 eta, 2 zeta
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
@@ -856,7 +877,7 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, co
     // zeta line stencil: cells m-1, m (in P1), m+1 (front), m+2 (looked ahead)
     {
       T c2[3][8];
-      const int64_t b2 = nbase + (m + 2) * N.s2;
+      const Ix b2 = nbase + (Ix)(m + 2) * N.s2;
       taylor_from_z(zplane(N, b2), zplane(N, b2 + N.s2), c2);
 #pragma unroll
       for (int col = 0; col < 3; ++col) {
@@ -879,8 +900,8 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, co
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          Gf[r][cc] = T(0.5) * (Lp[r][cc] + cf.R[r][cc]);
-          Lp[r][cc] = cf.L[r][cc];
+          Gf[r][cc] = T(0.5) * (Lpk[3 * r + cc] + cf.R[r][cc]);
+          Lpk[3 * r + cc] = cf.L[r][cc];
         }
       inv3(Gf, Ff);
       T Jf = det3(Ff);
@@ -897,7 +918,9 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_zeta(Dims D, co
 // launchers
 // ---------------------------------------------------------------------------
 template <class T>
-inline bool tiled3d_supported(const Dims& D, const MetricOut<T>&) { return D.dim == 3; }
+inline bool tiled3d_supported(const Dims& D, const MetricOut<T>&) {
+  return D.dim == 3 && (sizeof(Ix) == 8 || D.ne[0] * D.ne[1] * D.ne[2] < (int64_t(1) << 31));
+}
 // ===========================================================================
 // 2-D: one thread per PAIR of xi-adjacent cells (2p, 2p+1) of a row.  The pair's 80 B of every
 // `Metric` array and 64 B of every `ConservedMetric` array are contiguous and 16-B aligned, so all
