@@ -41,24 +41,25 @@ struct PF {
 // node index type of the marching kernels: 32-bit (launchers fall back to the gather kernels when the padded
 // node array has >= 2^31 elements); one IMAD.WIDE per address instead of 64-bit add chains
 using Ix = CG_IX;
-template <class T>
+template <class T, class IX = Ix>
 struct NodeP {
+  using ix = IX;
   const T* q[3];
-  Ix s1, s2;
+  IX s1, s2;
 };
 
 template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
 // L1 prefetch of the node at linear index b for the three coordinates (the marching kernels are
 // load-latency bound at 8 warps/SM: the planes the NEXT iteration touches first are fetched now)
-template <class T>
-CG_D void pf3(const NodeP<T>& N, Ix b) {
+template <class T, class IX>
+CG_D void pf3(const NodeP<T, IX>& N, IX b) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(N.q[q] + b));
 }
 
 // zeta-plane forms (fixed k), transverse (xi, eta)
-template <class T>
-CG_D PF<T> zplane(const NodeP<T>& N, Ix b) {
+template <class T, class IX>
+CG_D PF<T> zplane(const NodeP<T, IX>& N, IX b) {
   PF<T> f;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -68,8 +69,8 @@ CG_D PF<T> zplane(const NodeP<T>& N, Ix b) {
   return f;
 }
 // eta-plane forms (fixed j), transverse (xi, zeta)
-template <class T>
-CG_D PF<T> eplane(const NodeP<T>& N, Ix b) {
+template <class T, class IX>
+CG_D PF<T> eplane(const NodeP<T, IX>& N, IX b) {
   PF<T> f;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -79,8 +80,8 @@ CG_D PF<T> eplane(const NodeP<T>& N, Ix b) {
   return f;
 }
 // xi-plane forms (fixed i), transverse (eta, zeta)
-template <class T>
-CG_D PF<T> xplane(const NodeP<T>& N, Ix b) {
+template <class T, class IX>
+CG_D PF<T> xplane(const NodeP<T, IX>& N, IX b) {
   PF<T> f;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -384,7 +385,8 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_eta(Dims D, con
   const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
-  NodeP<T> N;
+  using Ix = int64_t;  // this kernel is faster with 64-bit row pointers + immediate column offsets (measured)
+  NodeP<T, Ix> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
