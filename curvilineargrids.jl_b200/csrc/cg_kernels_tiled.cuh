@@ -170,6 +170,60 @@ CG_D void eface6(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, T (&wp)[6], 
   }
 }
 
+// W+-( E on the a-face between rows 1|2 ) - W+-( E on the a-face between rows 0|1 ) for four consecutive
+// a-planes P0..P3: the second a-derivative of the middle cell cancels, so the difference needs two face
+// products and two cell products instead of two and four (same index convention as eface6).
+template <class T, int SCH>
+CG_D void eface6_diff(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, const PF<T>& P3, T (&wp)[6], T (&wm)[6]) {
+  if (SCH == ENDPOINT) {
+    // E = 1/2 (P_c + P_{c+a}) with cell-centre values: difference = 1/2 (P_{c+a} - P_{c-a}); W+ = W- = E/2
+    T q0a[3], q0b[3], qfa[3], qfb[3], qta[3], qtb[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      q0a[q] = T(0.5) * (P0.q[q].c0 + P1.q[q].c0);
+      q0b[q] = T(0.5) * (P2.q[q].c0 + P3.q[q].c0);
+      qfa[q] = T(0.5) * (P0.q[q].cu + P1.q[q].cu);
+      qfb[q] = T(0.5) * (P2.q[q].cu + P3.q[q].cu);
+      qta[q] = T(0.5) * (P0.q[q].cv + P1.q[q].cv);
+      qtb[q] = T(0.5) * (P2.q[q].cv + P3.q[q].cv);
+    }
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+      wp[col] = wm[col] = T(0.25) * (qfb[q1] * q0b[q2] - qfa[q1] * q0a[q2]);
+      wp[3 + col] = wm[3 + col] = T(0.25) * (qtb[q1] * q0b[q2] - qta[q1] * q0a[q2]);
+    }
+    return;
+  }
+  const T lam1 = T(0.5), lam2 = SCH == CURVATURE ? T(1.0 / 12.0) : T(0);
+  const T k2 = T(0.125) - lam2;
+  Form4<T> dL[3], dH[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    dL[q] = form_dif(P1.q[q], P0.q[q]);
+    dH[q] = form_dif(P3.q[q], P2.q[q]);
+  }
+#pragma unroll
+  for (int col = 0; col < 3; ++col) {
+    const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+    const Form4<T>&A1 = P1.q[q1], &B1 = P1.q[q2], &A2 = P2.q[q1], &B2 = P2.q[q2];
+    const Form4<T>&al = dL[q1], &bl = dL[q2], &ah = dH[q1], &bh = dH[q2];
+    T e0 = (A2.cu * B2.c0 - A1.cu * B1.c0) - k2 * (ah.cu * bh.c0 - al.cu * bl.c0);
+    T e1 = (A2.cu * B2.cu - A1.cu * B1.cu) - k2 * (ah.cu * bh.cu - al.cu * bl.cu);
+    T h0 = T(0.5) * e0, h1 = (T(0.5) * lam1) * e1;
+    wp[col] = h0 + h1;
+    wm[col] = h0 - h1;
+    e0 = (A2.cv * B2.c0 - A1.cv * B1.c0) - k2 * (ah.cv * bh.c0 - al.cv * bl.c0);
+    e1 = ((A2.cv * B2.cu + A2.cuv * B2.c0) - (A1.cv * B1.cu + A1.cuv * B1.c0)) -
+         k2 * ((ah.cv * bh.cu + ah.cuv * bh.c0) - (al.cv * bl.cu + al.cuv * bl.c0));
+    T e2 = (A2.cuv * B2.cu - A1.cuv * B1.cu) - k2 * (ah.cuv * bh.cu - al.cuv * bl.cu);
+    h0 = T(0.5) * e0 + lam2 * e2;
+    h1 = (T(0.5) * lam1) * e1;
+    wp[3 + col] = h0 + h1;
+    wm[3 + col] = h0 - h1;
+  }
+}
+
 template <class T> CG_D T shfl_dn(T v, int d) { return __shfl_down_sync(FULLMASK, v, d); }
 template <class T> CG_D T shfl_up(T v, int d) { return __shfl_up_sync(FULLMASK, v, d); }
 
@@ -331,11 +385,10 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
     T dpsi_eta[6];
     {
       PF<T> e0 = eplane(N, b - N.s1), e1 = eplane(N, b), e2 = eplane(N, b + N.s1), e3 = eplane(N, b + 2 * N.s1);
-      T wp[6], wm[6], wq[6], wn[6];
-      eface6<T, SCH>(e1, e2, e3, wp, wm);  // face j + 1/2
-      eface6<T, SCH>(e0, e1, e2, wq, wn);  // face j - 1/2
+      T wp[6], wm[6];
+      eface6_diff<T, SCH>(e0, e1, e2, e3, wp, wm);  // (face j + 1/2) - (face j - 1/2)
 #pragma unroll
-      for (int e = 0; e < 6; ++e) dpsi_eta[e] = (wp[e] - wq[e]) + shfl_dn(wm[e] - wn[e], 1);
+      for (int e = 0; e < 6; ++e) dpsi_eta[e] = wp[e] + shfl_dn(wm[e], 1);
     }
     T Gh[3][3];
 #pragma unroll
@@ -684,14 +737,7 @@ CG_D void cellz_compute(const NodeP<T>& N, Ix b, bool full, T lam1, T lam2, Cell
     // eta faces j-1/2 and j+1/2: eta-planes j-1 .. j+2, forms (xi,zeta) -> need (u,v) = (zeta, xi)
     PF<T> e0 = swap_uv(eplane(N, b - N.s1)), e1 = swap_uv(eplane(N, b)), e2 = swap_uv(eplane(N, b + N.s1)),
           e3 = swap_uv(eplane(N, b + 2 * N.s1));
-    T wp[6], wm[6], wq[6], wn[6];
-    eface6<T, SCH>(e1, e2, e3, wp, wm);
-    eface6<T, SCH>(e0, e1, e2, wq, wn);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) {
-      o.wpe[e] = wp[e] - wq[e];
-      o.wme[e] = wm[e] - wn[e];
-    }
+    eface6_diff<T, SCH>(e0, e1, e2, e3, o.wpe, o.wme);
   }
   {
     // xi face i+1/2: xi-planes i, i+1, i+2, forms (eta,zeta) -> need (u,v) = (zeta, eta)
@@ -788,17 +834,24 @@ struct Parked {
   __device__ __forceinline__ T& operator[](int slot) const { return base[slot * 128]; }
 };
 
-template <class T, int SCH, int PART>
+// SWAP = false: zeta faces, marching along k.  SWAP = true: ETA faces with the same code, marching along j:
+// the strides of eta and zeta are exchanged, i.e. the kernel works in the left-handed labelling
+// (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
+// Jacobian columns eta <-> zeta are exchanged; the stores undo both.
+template <class T, int SCH, int PART, bool SWAP>
 __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
   constexpr bool GF = (PART & 2) != 0;
+  constexpr int AX = SWAP ? 1 : 2;  // face axis written
   __shared__ T park_mem[33 * 128];
   const int tid_ = threadIdx.y * 32 + threadIdx.x;
   Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * 128 + tid_}, P1{park_mem + 12 * 128 + tid_},
       vp_prev{park_mem + 18 * 128 + tid_};
   Parked<T, 9> Lpk{park_mem + 24 * 128 + tid_};
   const int lane = threadIdx.x;
-  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t nw0 = D.nw[0];
+  const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
+  const int64_t nw2 = SWAP ? D.nw[1] : D.nw[2];  // extent of the marching axis
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;
   const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
@@ -808,11 +861,12 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
+  N.s1 = (Ix)D.se[SWAP ? 2 : 1]; N.s2 = (Ix)D.se[SWAP ? 1 : 2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = O.face_cons[2] != nullptr;
+  const bool full = O.face_cons[AX] != nullptr;
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
-  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+  // cell strides of the row axis and the marching axis in the output arrays
+  const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
 
   // carried state: W+ of the cell below the face, line partial sums, L state (parked in shared memory)
   {
@@ -871,9 +925,10 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
       wpe[e] = cf.wpe[e];
       wpx[e] = cf.wpx[e];
     }
-    if (O.cactive[2] && out_ok) {
-      T* o = O.cactive[2] + 3 * cl;
-      o[0] = Gh[2][0]; o[1] = Gh[2][1]; o[2] = Gh[2][2];
+    if (O.cactive[AX] && out_ok) {
+      T* o = O.cactive[AX] + 3 * cl;
+      const T sg = SWAP ? T(-1) : T(1);
+      o[0] = sg * Gh[2][0]; o[1] = sg * Gh[2][1]; o[2] = sg * Gh[2][2];
     }
     if (!full) continue;
     // zeta line stencil: cells m-1, m (in P1), m+1 (front), m+2 (looked ahead)
@@ -906,13 +961,27 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
           Lpk[3 * r + cc] = cf.L[r][cc];
         }
       inv3(Gf, Ff);
+      if (SWAP) {  // back to the true labelling: columns eta <-> zeta of F, rows eta <-> zeta of G
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          T t1 = Ff[q][1]; Ff[q][1] = Ff[q][2]; Ff[q][2] = t1;
+          T t2 = Gf[1][q]; Gf[1][q] = Gf[2][q]; Gf[2][q] = t2;
+        }
+      }
       T Jf = det3(Ff);
       if (out_ok) {
-        store10(O.face_fwd[2] + 10 * cl, Ff, Jf);
-        store10(O.face_inv[2] + 10 * cl, Gf, Jf);
+        store10(O.face_fwd[AX] + 10 * cl, Ff, Jf);
+        store10(O.face_inv[AX] + 10 * cl, Gf, Jf);
       }
     }
-    if (out_ok) store9(O.face_cons[2] + 9 * cl, Gh);
+    if (SWAP) {
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        T r0 = -Gh[0][col], r1 = -Gh[2][col], r2 = -Gh[1][col];
+        Gh[0][col] = r0; Gh[1][col] = r1; Gh[2][col] = r2;
+      }
+    }
+    if (out_ok) store9(O.face_cons[AX] + 9 * cl, Gh);
   }
 }
 
@@ -1088,14 +1157,45 @@ inline int launch_metrics2d_tiled(const Dims& D, const T* ex, const T* ey, const
   return 1;
 }
 
-// development switch (env CG_ETA_VARIANT): 1 = shared-memory eta kernel (default), 0 = warp-autonomous
+// development switch (env CG_ETA_VARIANT): 5 = zeta kernel marching along j (default), 0 = warp-autonomous
+// k-marching eta kernel, 1/2 = shared-memory eta kernel
 inline int eta_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CG_ETA_VARIANT");
+    v = e ? atoi(e) : 5;
+  }
+  return v;
+}
+
+inline int concurrent_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CG_CONCURRENT");
     v = e ? atoi(e) : 0;
   }
   return v;
+}
+struct Fork {
+  cudaStream_t s[2];
+  cudaEvent_t start, done[2];
+};
+// helper streams / events, one set per device, created on first use
+inline Fork* fork_streams() {
+  static Fork forks[16];
+  static bool made[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!made[dev]) {
+    Fork& f = forks[dev];
+    if (cudaStreamCreateWithFlags(&f.s[0], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&f.s[1], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    cudaEventCreateWithFlags(&f.start, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&f.done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&f.done[1], cudaEventDisableTiming);
+    made[dev] = true;
+  }
+  return &forks[dev];
 }
 
 inline int split_variant() {
@@ -1128,6 +1228,20 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   int n = 0;
   const bool face = what & 2;
   const bool full = O.face_cons[0] != nullptr;
+  // The three face kernels write disjoint arrays and are bound by different things (xi/zeta: load + shuffle
+  // latency, eta: FP64 issue).  Run them concurrently on two helper streams (fork/join on `st`) so that blocks
+  // of different kernels share an SM and fill each other's stalls and the tail of each grid.
+  cudaStream_t s_eta = st, s_zeta = st;
+  Fork* fk = concurrent_variant() ? fork_streams() : nullptr;
+  if (fk && face && (mask & 7) == 7) {
+    cudaEventRecord(fk->start, st);
+    cudaStreamWaitEvent(fk->s[0], fk->start, 0);
+    cudaStreamWaitEvent(fk->s[1], fk->start, 0);
+    s_eta = fk->s[0];
+    s_zeta = fk->s[1];
+  } else {
+    fk = nullptr;
+  }
   const bool split = split_variant() != 0 && full && face;  // conserved and G-face halves as separate launches
   if ((mask & 1) && ((what & 1) || face)) {
     if (split) {
@@ -1141,7 +1255,20 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   }
   if ((mask & 2) && face) {
     const int ev = eta_variant();
-    if (ev >= 1) {
+    if (ev == 5) {
+      // eta faces with the zeta kernel's code, marching along j: rows = k planes
+      int64_t t2 = ((D.nw[0] + WARP_OUT - 1) / WARP_OUT) * ((D.nw[2] + WY - 1) / WY);
+      int jchunk = (int)D.nw[1];
+      if (t2 < want) {
+        int64_t nch = (want + t2 - 1) / t2;
+        jchunk = (int)((D.nw[1] + nch - 1) / nch);
+        if (jchunk < 16) jchunk = 16;
+        if (jchunk > D.nw[1]) jchunk = (int)D.nw[1];
+      }
+      dim3 g5(grid.x, (unsigned)((D.nw[2] + WY - 1) / WY), (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
+      k_face_zeta<T, SCH, 3, true><<<g5, block, 0, s_eta>>>(D, ex, ey, ez, O, jchunk);
+      ++n;
+    } else if (ev >= 1) {
       auto go = [&](auto kern, int RY) {
         const size_t shm = (size_t)B2_SLOTS * RY * 32 * sizeof(T);
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
@@ -1157,7 +1284,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
       k_face_eta<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
       n += 2;
     } else {
-      k_face_eta<T, SCH, 3><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      k_face_eta<T, SCH, 3><<<grid, block, 0, s_eta>>>(D, ex, ey, ez, O, kchunk);
       ++n;
     }
   }
@@ -1165,12 +1292,18 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     if (split) {
       dim3 g3((unsigned)((D.nw[0] + 31) / 32), grid.y, grid.z);
       k_gface_zeta<T, SCH><<<g3, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-      k_face_zeta<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      k_face_zeta<T, SCH, 1, false><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
       n += 2;
     } else {
-      k_face_zeta<T, SCH, 3><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      k_face_zeta<T, SCH, 3, false><<<grid, block, 0, s_zeta>>>(D, ex, ey, ez, O, kchunk);
       ++n;
     }
+  }
+  if (fk) {
+    cudaEventRecord(fk->done[0], fk->s[0]);
+    cudaEventRecord(fk->done[1], fk->s[1]);
+    cudaStreamWaitEvent(st, fk->done[0], 0);
+    cudaStreamWaitEvent(st, fk->done[1], 0);
   }
   return n;
 }
