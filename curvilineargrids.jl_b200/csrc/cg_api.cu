@@ -162,8 +162,10 @@ int pad_nodes(cg_grid* g, cudaStream_t st) {
     S.st[d] = s;
     s *= g->src_count[d];
   }
-  cg::k_pad_nodes<T><<<launch_blocks(g->next(), 256), 256, 0, st>>>(D, S, (T*)g->ext[0].p, (T*)g->ext[1].p,
-                                                                    (T*)g->ext[2].p);
+  {
+    dim3 pgrid((unsigned)((D.ne[0] + 255) / 256), (unsigned)D.ne[1], (unsigned)D.ne[2]);
+    cg::k_pad_nodes<T><<<pgrid, 256, 0, st>>>(D, S, (T*)g->ext[0].p, (T*)g->ext[1].p, (T*)g->ext[2].p);
+  }
   g_launches++;
   CG_CUDA(cudaGetLastError());
   g->ext_valid = true;

@@ -41,23 +41,26 @@ struct NodeSrc {
 // ---------------------------------------------------------------------------
 template <class T>
 __global__ void k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, T* ey, T* ez) {
-  const int64_t ntot = D.ne[0] * D.ne[1] * D.ne[2];
+  // grid: x over i (grid-stride), y = ext row j, z = ext plane k  (no 64-bit div/mod per element)
   T* out[3] = {ex, ey, ez};
-  for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
-       lin += (int64_t)gridDim.x * blockDim.x) {
-    int64_t e[3], r = lin;
-    e[0] = r % D.ne[0];
-    r /= D.ne[0];
-    e[1] = r % D.ne[1];
-    e[2] = r / D.ne[1];
-    int64_t base = 0, off[3] = {0, 0, 0}, nbd[3] = {0, 0, 0};
-    for (int d = 0; d < D.dim; ++d) {
-      int64_t m = D.w0[d] + e[d] - 1 - D.nhalo;
-      int64_t c = m < 0 ? 0 : (m > D.gn[d] ? D.gn[d] : m);
-      off[d] = m - c;
-      nbd[d] = off[d] > 0 ? -S.st[d] : S.st[d];
-      base += (c - S.s0[d]) * S.st[d];
-    }
+  int64_t e[3];
+  e[1] = blockIdx.y;
+  e[2] = blockIdx.z;
+  int64_t base_jk = 0, off[3] = {0, 0, 0}, nbd[3] = {0, 0, 0};
+  for (int d = 1; d < D.dim; ++d) {
+    int64_t m = D.w0[d] + e[d] - 1 - D.nhalo;
+    int64_t c = m < 0 ? 0 : (m > D.gn[d] ? D.gn[d] : m);
+    off[d] = m - c;
+    nbd[d] = off[d] > 0 ? -S.st[d] : S.st[d];
+    base_jk += (c - S.s0[d]) * S.st[d];
+  }
+  const int64_t row = (e[1] + D.ne[1] * e[2]) * D.ne[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < D.ne[0]; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t m = D.w0[0] + i - 1 - D.nhalo;
+    int64_t c = m < 0 ? 0 : (m > D.gn[0] ? D.gn[0] : m);
+    off[0] = m - c;
+    nbd[0] = off[0] > 0 ? -S.st[0] : S.st[0];
+    const int64_t base = base_jk + (c - S.s0[0]) * S.st[0];
     for (int q = 0; q < D.dim; ++q) {
       const T* A = S.p[q];
       T v0 = A[base];
@@ -69,7 +72,7 @@ __global__ void k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, T* ey, T* ez) {
           v += T(off[d]) * g;
         }
       }
-      out[q][lin] = v;
+      out[q][row + i] = v;
     }
   }
 }

@@ -28,7 +28,8 @@ namespace cg {
 #ifndef CG_ZETA_MINB
 #define CG_ZETA_MINB 2
 #endif
-constexpr int WARP_OUT = 29;  // output cells per warp along xi
+constexpr int WARP_OUT = 29;  // output cells per warp along xi (kernels that need lanes -1, +1, +2)
+constexpr int ZETA_OUT = 31;  // the zeta / eta(SWAP) kernel only needs lane -1
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 template <class T>
@@ -854,9 +855,9 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
   const int64_t nw2 = SWAP ? D.nw[1] : D.nw[2];  // extent of the marching axis
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;
-  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
+  const int64_t i = (int64_t)blockIdx.x * ZETA_OUT + lane - 1;
   const int64_t ic = i > nw0 ? nw0 : i;  // this kernel reads node columns ic .. ic+2
-  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
+  const bool out_ok = lane >= 1 && lane <= ZETA_OUT && i < nw0;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
@@ -1265,7 +1266,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
         if (jchunk < 16) jchunk = 16;
         if (jchunk > D.nw[1]) jchunk = (int)D.nw[1];
       }
-      dim3 g5(grid.x, (unsigned)((D.nw[2] + WY - 1) / WY), (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
+      dim3 g5((unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT), (unsigned)((D.nw[2] + WY - 1) / WY),
+              (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
       k_face_zeta<T, SCH, 3, true><<<g5, block, 0, s_eta>>>(D, ex, ey, ez, O, jchunk);
       ++n;
     } else if (ev >= 1) {
@@ -1292,10 +1294,10 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     if (split) {
       dim3 g3((unsigned)((D.nw[0] + 31) / 32), grid.y, grid.z);
       k_gface_zeta<T, SCH><<<g3, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-      k_face_zeta<T, SCH, 1, false><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
+      k_face_zeta<T, SCH, 1, false><<<dim3((unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT), grid.y, grid.z), block, 0, st>>>(D, ex, ey, ez, O, kchunk);
       n += 2;
     } else {
-      k_face_zeta<T, SCH, 3, false><<<grid, block, 0, s_zeta>>>(D, ex, ey, ez, O, kchunk);
+      k_face_zeta<T, SCH, 3, false><<<dim3((unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT), grid.y, grid.z), block, 0, s_zeta>>>(D, ex, ey, ez, O, kchunk);
       ++n;
     }
   }
