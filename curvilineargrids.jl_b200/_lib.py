@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcurvigrid_cuda.so")
+# CG_LIB_PATH: development override (kernel variants under build/variants/)
+LIB_PATH = os.environ.get("CG_LIB_PATH") or os.path.join(_HERE, "libcurvigrid_cuda.so")
 
 CG_OK, CG_ERR_ARG, CG_ERR_OOM, CG_ERR_CUDA, CG_ERR_STATE, CG_ERR_NCCL = range(6)
 CG_F64, CG_F32 = 0, 1

@@ -163,8 +163,11 @@ int pad_nodes(cg_grid* g, cudaStream_t st) {
     s *= g->src_count[d];
   }
   {
-    dim3 pgrid((unsigned)((D.ne[0] + 255) / 256), (unsigned)D.ne[1], (unsigned)D.ne[2]);
-    cg::k_pad_nodes<T><<<pgrid, 256, 0, st>>>(D, S, (T*)g->ext[0].p, (T*)g->ext[1].p, (T*)g->ext[2].p);
+    const unsigned rows = (unsigned)(D.ne[1] * D.ne[2]);
+    T *e0 = (T*)g->ext[0].p, *e1 = (T*)g->ext[1].p, *e2 = (T*)g->ext[2].p;
+    if (D.dim == 3) cg::k_pad_nodes<T, 3><<<rows, 256, 0, st>>>(D, S, e0, e1, e2);
+    else if (D.dim == 2) cg::k_pad_nodes<T, 2><<<rows, 256, 0, st>>>(D, S, e0, e1, e2);
+    else cg::k_pad_nodes<T, 1><<<rows, 256, 0, st>>>(D, S, e0, e1, e2);
   }
   g_launches++;
   CG_CUDA(cudaGetLastError());
@@ -599,6 +602,8 @@ int cg_grid_bind_output(cg_grid* g, int array, int axis, void* devptr, size_t nb
   Buf* b = select(g, array, axis, &bytes);
   if (!b) return fail(CG_ERR_ARG, "unknown array %d / axis %d", array, axis);
   if (nbytes < bytes) return fail(CG_ERR_ARG, "buffer too small: %zu < %zu bytes", nbytes, bytes);
+  if (reinterpret_cast<uintptr_t>(devptr) & 15)  // 16-B vector stores and TMA bulk stores
+    return fail(CG_ERR_ARG, "bound output buffers must be 16-byte aligned");
   release(*b);
   b->p = devptr;
   b->bytes = nbytes;

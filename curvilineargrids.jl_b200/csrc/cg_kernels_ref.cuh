@@ -39,38 +39,52 @@ struct NodeSrc {
 // value = A[c] + sum_d (m_d - c_d) * one-sided difference in the boundary cell,
 // c = clamp(m) (no cross terms).
 // ---------------------------------------------------------------------------
-template <class T>
-__global__ void k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, T* ey, T* ez) {
-  // grid: x over i (grid-stride), y = ext row j, z = ext plane k  (no 64-bit div/mod per element)
-  T* out[3] = {ex, ey, ez};
-  int64_t e[3];
-  e[1] = blockIdx.y;
-  e[2] = blockIdx.z;
-  int64_t base_jk = 0, off[3] = {0, 0, 0}, nbd[3] = {0, 0, 0};
-  for (int d = 1; d < D.dim; ++d) {
-    int64_t m = D.w0[d] + e[d] - 1 - D.nhalo;
-    int64_t c = m < 0 ? 0 : (m > D.gn[d] ? D.gn[d] : m);
-    off[d] = m - c;
-    nbd[d] = off[d] > 0 ? -S.st[d] : S.st[d];
-    base_jk += (c - S.s0[d]) * S.st[d];
+template <class T, int DIM>
+__global__ void __launch_bounds__(256) k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, T* ey, T* ez) {
+  // one block per ext row (j, k); threads stride over i.  DIM is a template parameter so that every
+  // per-axis quantity lives in a register (a runtime dimension count put them in local memory).
+  const int64_t e1 = DIM > 1 ? (int64_t)(blockIdx.x % (unsigned)D.ne[1]) : 0;
+  const int64_t e2 = DIM > 2 ? (int64_t)(blockIdx.x / (unsigned)D.ne[1]) : 0;
+  int64_t base_jk = 0, off1 = 0, off2 = 0, nb1 = 0, nb2 = 0;
+  if (DIM > 1) {
+    const int64_t m = D.w0[1] + e1 - 1 - D.nhalo;
+    const int64_t c = m < 0 ? 0 : (m > D.gn[1] ? D.gn[1] : m);
+    off1 = m - c;
+    nb1 = off1 > 0 ? -S.st[1] : S.st[1];
+    base_jk += (c - S.s0[1]) * S.st[1];
   }
-  const int64_t row = (e[1] + D.ne[1] * e[2]) * D.ne[0];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < D.ne[0]; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t m = D.w0[0] + i - 1 - D.nhalo;
-    int64_t c = m < 0 ? 0 : (m > D.gn[0] ? D.gn[0] : m);
-    off[0] = m - c;
-    nbd[0] = off[0] > 0 ? -S.st[0] : S.st[0];
+  if (DIM > 2) {
+    const int64_t m = D.w0[2] + e2 - 1 - D.nhalo;
+    const int64_t c = m < 0 ? 0 : (m > D.gn[2] ? D.gn[2] : m);
+    off2 = m - c;
+    nb2 = off2 > 0 ? -S.st[2] : S.st[2];
+    base_jk += (c - S.s0[2]) * S.st[2];
+  }
+  const int64_t row = (e1 + D.ne[1] * e2) * D.ne[0];
+  const T* src[3] = {S.p[0], S.p[1], S.p[2]};
+  T* out[3] = {ex, ey, ez};
+  for (int64_t i = threadIdx.x; i < D.ne[0]; i += blockDim.x) {
+    const int64_t m = D.w0[0] + i - 1 - D.nhalo;
+    const int64_t c = m < 0 ? 0 : (m > D.gn[0] ? D.gn[0] : m);
+    const int64_t off0 = m - c;
+    const int64_t nb0 = off0 > 0 ? -S.st[0] : S.st[0];
     const int64_t base = base_jk + (c - S.s0[0]) * S.st[0];
-    for (int q = 0; q < D.dim; ++q) {
-      const T* A = S.p[q];
-      T v0 = A[base];
+#pragma unroll
+    for (int q = 0; q < DIM; ++q) {
+      const T* A = src[q];
+      const T v0 = A[base];
       T v = v0;
-      for (int d = 0; d < D.dim; ++d) {
-        if (off[d] != 0) {
-          T nb = A[base + nbd[d]];
-          T g = off[d] > 0 ? (v0 - nb) : (nb - v0);
-          v += T(off[d]) * g;
-        }
+      if (off0 != 0) {
+        const T nb = A[base + nb0];
+        v += T(off0) * (off0 > 0 ? (v0 - nb) : (nb - v0));
+      }
+      if (DIM > 1 && off1 != 0) {
+        const T nb = A[base + nb1];
+        v += T(off1) * (off1 > 0 ? (v0 - nb) : (nb - v0));
+      }
+      if (DIM > 2 && off2 != 0) {
+        const T nb = A[base + nb2];
+        v += T(off2) * (off2 > 0 ? (v0 - nb) : (nb - v0));
       }
       out[q][row + i] = v;
     }

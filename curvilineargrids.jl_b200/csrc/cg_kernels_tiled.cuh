@@ -28,6 +28,11 @@ namespace cg {
 #ifndef CG_ZETA_MINB
 #define CG_ZETA_MINB 2
 #endif
+#ifndef CG_WY
+#define CG_WY 4
+#endif
+constexpr int WY = CG_WY;       // warps (rows) per block of the marching kernels
+constexpr int NT = 32 * WY;     // threads per block
 constexpr int WARP_OUT = 29;  // output cells per warp along xi (kernels that need lanes -1, +1, +2)
 constexpr int ZETA_OUT = 31;  // the zeta / eta(SWAP) kernel only needs lane -1
 constexpr unsigned FULLMASK = 0xffffffffu;
@@ -50,8 +55,8 @@ struct NodeP {
 };
 
 template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
-// L1 prefetch of the node at linear index b for the three coordinates (the marching kernels are
-// load-latency bound at 8 warps/SM: the planes the NEXT iteration touches first are fetched now)
+// L1 prefetch of the node at linear index b for the three coordinates (the marching kernels run at
+// 8 warps/SM: the node rows the NEXT iteration touches first are fetched now)
 template <class T, class IX>
 CG_D void pf3(const NodeP<T, IX>& N, IX b) {
 #pragma unroll
@@ -238,10 +243,64 @@ CG_D LineS<T> line_from_taylor(const T (&c)[3][8], int q1, int q2, int f, int b,
   return line_scalars(p0, p1, p2, lam1, lam2);
 }
 
+// ---------------------------------------------------------------------------
+// Output staging.  The metric arrays are AoS (80-B / 72-B elements, layout of the Julia arrays): a lane
+// storing its own element touches one 128-B line per lane and instruction, which saturates the L1TEX
+// wavefront queue (measured: round 1, profiles/).  The cells a warp writes in one step are consecutive
+// along xi, i.e. ONE contiguous chunk per array.  Every lane puts its element into the warp's staging
+// buffer in shared memory and lane 0 hands the chunk to the TMA unit (cp.async.bulk shared -> global):
+// no global-store instructions, full-sector writes.  Chunks whose ends are not 16-B aligned (72-B
+// elements, FP32) keep the same 16-B phase in shared memory; the <= 3 head / tail values go out as
+// plain stores.
+// ---------------------------------------------------------------------------
+CG_D void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+CG_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory (the staging buffers may be rewritten)
+CG_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CG_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <class T, int E> constexpr int stage_len = 32 * E + 16 / (int)sizeof(T);  // values per array
+
+// staging slot of one array for one warp step: where the chunk goes in global memory and in shared memory
+template <class T, int E>
+struct Stage {
+  T* g;   // global address of the chunk's first value
+  T* s;   // shared address of the chunk's first value (same 16-B phase as g)
+  CG_D Stage(T* arr, int64_t cl0, T* sbuf) {
+    g = arr + (int64_t)E * cl0;
+    constexpr int A = 16 / (int)sizeof(T);
+    if constexpr ((E * sizeof(T)) % 16 == 0) s = sbuf;  // array bases are 16-B aligned (cudaMalloc / checked on bind)
+    else s = sbuf + (int)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) & (A - 1));
+  }
+  CG_D T* slot(int rel) const { return s + rel * E; }
+  // all lanes of the warp call this after the valid lanes have written their slots
+  CG_D void flush(int nvalid, int lane) const {
+    constexpr int A = 16 / (int)sizeof(T);
+    if constexpr ((E * sizeof(T)) % 16 == 0) {  // whole elements are 16-B multiples: no head / tail
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_store(g, s, (uint32_t)(nvalid * E * sizeof(T)));
+      return;
+    }
+    const int nvals = nvalid * E;
+    const int head = (int)((A - (reinterpret_cast<uintptr_t>(g) / sizeof(T))) & (A - 1));
+    const int tail = (nvals - head) & (A - 1);
+    const int body = nvals - head - tail;
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0 && body > 0) bulk_store(g + head, s + head, (uint32_t)(body * sizeof(T)));
+    if (lane < head) g[lane] = s[lane];
+    if (lane < tail) g[head + body + lane] = s[head + body + lane];
+  }
+};
+
 template <class T>
-CG_D void store10(T* o, const T (&M)[3][3], T J) {
-  // element = 80 B (FP64) and 16-B aligned: five 16-B stores
-  if (sizeof(T) == 8) {
+CG_D void put10(T* o, const T (&M)[3][3], T J) {  // o: staging slot (16-B aligned for FP64)
+  if constexpr (sizeof(T) == 8) {
     double2* p = reinterpret_cast<double2*>(o);
     p[0] = make_double2(M[0][0], M[1][0]);
     p[1] = make_double2(M[2][0], M[0][1]);
@@ -256,7 +315,7 @@ CG_D void store10(T* o, const T (&M)[3][3], T J) {
   }
 }
 template <class T>
-CG_D void store9(T* o, const T (&M)[3][3]) {
+CG_D void put9(T* o, const T (&M)[3][3]) {
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -272,18 +331,22 @@ struct March {
 // ===========================================================================
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
 // ===========================================================================
-// PART: bit0 = conserved metrics, bit1 = reconstructed inverse Jacobian (+ cell metrics); splitting the
-// two halves into separate launches halves the live register state of each (more warps per SM).
-template <class T, int SCH, int PART>
-__global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
-                                                                   MetricOut<T> O, int what, int kchunk) {
+// dynamic shared memory: per warp, staging buffers of the five AoS arrays this kernel writes
+template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9>;
+template <class T, int SCH>
+__global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
+                                                          MetricOut<T> O, int what, int kchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;  // whole warp
-  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
+  const int64_t i0 = (int64_t)blockIdx.x * WARP_OUT;  // first output cell of the warp (lane 1)
+  const int64_t i = i0 + lane - 1;
   const int64_t ic = i > nw0 + 1 ? nw0 + 1 : i;
   const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
+  const int nvalid = (int)(nw0 - i0 < WARP_OUT ? nw0 - i0 : WARP_OUT);
+  const int rel = lane - 1;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
@@ -291,11 +354,14 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
   N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
   const bool full = O.face_cons[0] != nullptr;
-  const bool do_cell = (what & 1) && (PART & 2);
-  const bool do_cons = (what & 2) && (PART & 1);
-  const bool do_gf = (what & 2) && (PART & 2) && full;
+  const bool do_cell = what & 1;
+  const bool do_cons = what & 2;
+  const bool do_gf = (what & 2) && full;
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+  T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_stage_vals<T>;
+  T* const sg_cf = sg, * const sg_ci = sg + stage_len<T, 10>, * const sg_ff = sg + 2 * stage_len<T, 10>,
+         * const sg_fi = sg + 3 * stage_len<T, 10>, * const sg_fc = sg + 4 * stage_len<T, 10>;
 
   T psi_bot[6];
   if (do_cons) {
@@ -308,7 +374,11 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
   PF<T> z0 = zplane(N, nbase + (Ix)k0 * N.s2), z1 = zplane(N, nbase + (Ix)(k0 + 1) * N.s2);
   for (int64_t m = k0; m < k1; ++m) {
     const Ix b = nbase + (Ix)m * N.s2;
-    const int64_t cl = i + j * cs1 + m * cs2;
+    const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this plane
+    const int64_t cl = cl0 + rel;
+    // the TMA unit has finished reading last step's staging buffers
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
     if (m + 1 < k1) {  // next iteration's new node rows: plane m+3 (rows j, j+1), plane m+2 (rows j-1, j+2)
       pf3(N, b + 3 * N.s2);
       pf3(N, b + 3 * N.s2 + N.s1);
@@ -340,11 +410,17 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
                        c[q][7] * dl[e] * dl[g];
           }
         T J = det3(Ff);
-        if (out_ok) {
-          if (O.cell_fwd) store10(O.cell_fwd + 10 * cl, Ff, J);
-          if (O.cell_inv) store10(O.cell_inv + 10 * cl, G, J);
-          if (O.cjac) O.cjac[cl] = J;
+        if (O.cell_fwd) {
+          Stage<T, 10> S(O.cell_fwd, cl0, sg_cf);
+          if (out_ok) put10(S.slot(rel), Ff, J);
+          S.flush(nvalid, lane);
         }
+        if (O.cell_inv) {
+          Stage<T, 10> S(O.cell_inv, cl0, sg_ci);
+          if (out_ok) put10(S.slot(rel), G, J);
+          S.flush(nvalid, lane);
+        }
+        if (O.cjac && out_ok) O.cjac[cl] = J;
       }
       if (do_gf) {
         // ---- reconstructed inverse Jacobian on the xi face ----
@@ -361,13 +437,17 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
           for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
         inv3(Gf, Ff);
         T Jf = det3(Ff);
+        Stage<T, 10> Sf(O.face_fwd[0], cl0, sg_ff), Si(O.face_inv[0], cl0, sg_fi);
         if (out_ok) {
-          store10(O.face_fwd[0] + 10 * cl, Ff, Jf);
-          store10(O.face_inv[0] + 10 * cl, Gf, Jf);
+          put10(Sf.slot(rel), Ff, Jf);
+          put10(Si.slot(rel), Gf, Jf);
         }
+        Sf.flush(nvalid, lane);
+        Si.flush(nvalid, lane);
       }
     }
     if (!do_cons) {
+      if (lane == 0) bulk_commit();
       z0 = z1;
       z1 = z2;
       continue;
@@ -404,7 +484,10 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
       T* o = O.cactive[0] + 3 * cl;
       o[0] = Gh[0][0]; o[1] = Gh[0][1]; o[2] = Gh[0][2];
     }
-    if (!full) continue;
+    if (!full) {
+      if (lane == 0) bulk_commit();
+      continue;
+    }
     // ---- xi line stencils (neighbours by shuffle): rows eta (+, b = zeta) and zeta (-, b = eta) ----
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
@@ -417,301 +500,14 @@ __global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_xi(Dims D, cons
         else Gh[2][col] -= T(0.5) * v;
       }
     }
-    if (out_ok) store9(O.face_cons[0] + 9 * cl, Gh);
-  }
-}
-
-// ===========================================================================
-// Kernel B: eta-face metrics.  f = eta, s = zeta, t = xi.
-//   active row eta : +dPsi^{xi->eta}[b=zeta] across xi  - dPsi^{zeta->eta}[b=xi] across zeta
-//   row zeta       : +line_eta[b=xi]                     - dPsi^{xi->eta}[b=eta] across xi
-//   row xi         : +dPsi^{zeta->eta}[b=eta] across zeta - line_eta[b=zeta]
-// ===========================================================================
-template <class T, int SCH, int PART>
-__global__ void __launch_bounds__(128, PART == 2 ? 3 : 2) k_face_eta(Dims D, const T* ex, const T* ey, const T* ez,
-                                                                    MetricOut<T> O, int kchunk) {
-  const int lane = threadIdx.x;
-  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
-  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= nw1) return;
-  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
-  const int64_t ic = i > nw0 ? nw0 : i;  // this kernel reads node columns ic .. ic+2
-  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
-  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
-  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
-  using Ix = int64_t;  // this kernel is faster with 64-bit row pointers + immediate column offsets (measured)
-  NodeP<T, Ix> N;
-  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
-  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = O.face_cons[1] != nullptr;
-  const bool do_cons = PART & 1, do_gf = (PART & 2) && full;
-  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
-  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
-
-  // Psi^{zeta->eta} on the xi-edge (j+1/2, m-1/2): zeta faces of cells j and j+1, reconstructed along eta
-  auto psi_zeta = [&](Ix b, T (&psi)[6]) {
-    // b = node (ic, j, plane below the face's lower cell)
-    T wp[6], wm[6], wq[6], wn[6];
-    eface6<T, SCH>(swap_uv(zplane(N, b)), swap_uv(zplane(N, b + N.s2)), swap_uv(zplane(N, b + 2 * N.s2)), wp, wm);
-    const Ix bn = b + N.s1;
-    eface6<T, SCH>(swap_uv(zplane(N, bn)), swap_uv(zplane(N, bn + N.s2)), swap_uv(zplane(N, bn + 2 * N.s2)), wq, wn);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) psi[e] = wp[e] + wn[e];
-  };
-  T psi_bot[6];
-  if (do_cons) psi_zeta(nbase + (Ix)(k0 - 1) * N.s2, psi_bot);
-  for (int64_t m = k0; m < k1; ++m) {
-    const Ix b = nbase + (Ix)m * N.s2;
-    const int64_t cl = i + j * cs1 + m * cs2;
-    if (do_gf) {
-      // ---- reconstructed inverse Jacobian on the eta face: cells j and j+1 ----
-      if (m + 1 < k1) {
-        pf3(N, b + 2 * N.s2);
-        pf3(N, b + 2 * N.s2 + N.s1);
-        pf3(N, b + 2 * N.s2 + 2 * N.s1);
-      }
-      T Gf[3][3], Ff[3][3];
-      {
-        T L[3][3], R[3][3], R1[3][3];
-#pragma unroll
-        for (int cell = 0; cell < 2; ++cell) {
-          const Ix bc = b + (Ix)cell * N.s1;
-          T c[3][8];
-          taylor_from_z(zplane(N, bc), zplane(N, bc + N.s2), c);
-          T F[3][3], G[3][3], Fa[3], Fb[3];
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-            Fa[q] = c[q][6];  // column zeta of dF/d(eta)
-            Fb[q] = c[q][3];  // column xi
-          }
-          inv3(F, G);
-          if (cell == 0) ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, L, R);
-          else ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, R, R1);  // R <- L of cell j+1 (unused), R1 <- R of cell j+1
-        }
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + R1[r][cc]);
-      }
-      inv3(Gf, Ff);
-      T Jf = det3(Ff);
-      if (out_ok) {
-        store10(O.face_fwd[1] + 10 * cl, Ff, Jf);
-        store10(O.face_inv[1] + 10 * cl, Gf, Jf);
-      }
-    }
-    if (!do_cons) continue;
-    if (m + 1 < k1) {  // next iteration: plane m+3 rows j..j+2, plane m+2 rows j-1 and j+3
-      pf3(N, b + 3 * N.s2);
-      pf3(N, b + 3 * N.s2 + N.s1);
-      pf3(N, b + 3 * N.s2 + 2 * N.s1);
-      pf3(N, b + 2 * N.s2 - N.s1);
-      pf3(N, b + 2 * N.s2 + 3 * N.s1);
-    }
-    T psi_top[6];
-    psi_zeta(b, psi_top);
-    // Psi^{xi->eta} on the zeta-edge (i+1/2, j+1/2): xi faces (i+1/2) of rows j and j+1, reconstructed along eta
-    T psi_x[6];
     {
-      T wp[6], wm[6], wq[6], wn[6];
-      eface6<T, SCH>(xplane(N, b), xplane(N, b + 1), xplane(N, b + 2), wp, wm);
-      const Ix bn = b + N.s1;
-      eface6<T, SCH>(xplane(N, bn), xplane(N, bn + 1), xplane(N, bn + 2), wq, wn);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) psi_x[e] = wp[e] + wn[e];
+      Stage<T, 9> S(O.face_cons[0], cl0, sg_fc);
+      if (out_ok) put9(S.slot(rel), Gh);
+      S.flush(nvalid, lane);
     }
-    T Gh[3][3];  // rows: 0 xi, 1 eta, 2 zeta
-#pragma unroll
-    for (int col = 0; col < 3; ++col) {
-      // a = xi (= t, sigma +1, a' = zeta): bsel 1 is b = zeta, bsel 0 is b = eta
-      T dxa = psi_x[3 + col] - shfl_up(psi_x[3 + col], 1);
-      T dxf = psi_x[col] - shfl_up(psi_x[col], 1);
-      // a = zeta (= s, sigma -1, a' = xi): bsel 1 is b = xi, bsel 0 is b = eta
-      Gh[1][col] = dxa - (psi_top[3 + col] - psi_bot[3 + col]);
-      Gh[2][col] = -dxf;
-      Gh[0][col] = psi_top[col] - psi_bot[col];
-    }
-#pragma unroll
-    for (int e = 0; e < 6; ++e) psi_bot[e] = psi_top[e];
-    if (O.cactive[1] && out_ok) {
-      T* o = O.cactive[1] + 3 * cl;
-      o[0] = Gh[1][0]; o[1] = Gh[1][1]; o[2] = Gh[1][2];
-    }
-    if (!full) continue;
-    // ---- eta line stencils: cells j-1 .. j+2 recomputed from the eta-planes j-1 .. j+3 ----
-    {
-      PF<T> r0 = eplane(N, b - N.s1), r1 = eplane(N, b), r2 = eplane(N, b + N.s1), r3 = eplane(N, b + 2 * N.s1),
-            r4 = eplane(N, b + 3 * N.s1);
-      const PF<T>* rows[5] = {&r0, &r1, &r2, &r3, &r4};
-      // eta-plane forms are (u,v) = (xi,zeta): q_xi = cu, q_zeta = cv, eta-derivative = difference of rows
-#pragma unroll
-      for (int col = 0; col < 3; ++col) {
-        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-        T accx = T(0), accz = T(0);  // b = xi (row zeta, +) and b = zeta (row xi, -)
-#pragma unroll
-        for (int cell = 0; cell < 4; ++cell) {
-          const Form4<T>&Alo = rows[cell]->q[q1], &Ahi = rows[cell + 1]->q[q1];
-          const Form4<T>&Blo = rows[cell]->q[q2], &Bhi = rows[cell + 1]->q[q2];
-          T q20 = T(0.5) * (Blo.c0 + Bhi.c0), q2f = Bhi.c0 - Blo.c0;
-#pragma unroll
-          for (int bb = 0; bb < 2; ++bb) {
-            T q1b = bb == 0 ? T(0.5) * (Alo.cu + Ahi.cu) : T(0.5) * (Alo.cv + Ahi.cv);
-            T q1bf = bb == 0 ? (Ahi.cu - Alo.cu) : (Ahi.cv - Alo.cv);
-            LineS<T> s = line_scalars(q1b * q20, q1b * q2f + q1bf * q20, q1bf * q2f, lam1, lam2);
-            T v = cell == 0 ? -s.vp : (cell == 1 ? (s.vp - T(2) * s.u) : (cell == 2 ? (T(2) * s.u - s.vm) : s.vm));
-            if (bb == 0) accx += v;
-            else accz += v;
-          }
-        }
-        Gh[2][col] += T(0.5) * accx;
-        Gh[0][col] -= T(0.5) * accz;
-      }
-    }
-    if (out_ok) store9(O.face_cons[1] + 9 * cl, Gh);
+    if (lane == 0) bulk_commit();
   }
-}
-
-// ===========================================================================
-// Kernel B2: eta-face metrics with the eta-neighbours shared through shared memory.
-// A block is RY consecutive j-rows (one warp each) marching along k in lock-step:
-// row 0 and rows RY-2, RY-1 are the -1 / +1,+2 neighbours of the RY-3 output rows.
-// Every thread evaluates only ITS cell (W+- of its zeta and xi faces, line scalars,
-// L/R states), publishes the 39 values its eta-neighbours need, and after one
-// barrier assembles its face from rows r-1, r+1, r+2.  Roughly halves the FP64 work
-// of kernel B (which recomputes the neighbour rows from the nodes).
-// shared layout: [slot][row][lane] doubles — lanes contiguous, conflict-free.
-// ===========================================================================
-constexpr int B2_SLOTS = 39;
-template <class T, int SCH, int RY, int MB>
-__global__ void __launch_bounds__(32 * RY, MB) k_face_eta_sh(Dims D, const T* ex, const T* ey, const T* ez,
-                                                          MetricOut<T> O, int kchunk) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sm = reinterpret_cast<T*>(smem_raw);
-  const int lane = threadIdx.x, r = threadIdx.y;
-  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
-  const int64_t j = (int64_t)blockIdx.y * (RY - 3) + r - 1;   // full row of this warp (may be -1 or > nw1-1)
-  const int64_t jc = j > nw1 + 1 ? nw1 + 1 : j;
-  const int64_t i = (int64_t)blockIdx.x * WARP_OUT + lane - 1;
-  const int64_t ic = i > nw0 ? nw0 : i;
-  const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0 && r >= 1 && r <= RY - 3 && j < nw1;
-  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
-  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
-  NodeP<T> N;
-  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
-  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = O.face_cons[1] != nullptr;
-  const Ix nbase = (Ix)(ic + 1) + (Ix)(jc + 1) * N.s1 + N.s2;
-  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
-  auto S = [&](int slot, int row) -> T& { return sm[(slot * RY + row) * 32 + lane]; };
-  const int rn = r + 1 < RY ? r + 1 : r, rn2 = r + 2 < RY ? r + 2 : r, rp = r > 0 ? r - 1 : r;
-
-  // zeta-face half states of this row on the face (m - 1/2), for the running psi_bot
-  T psi_bot[6];
-  {
-    T wp[6], wm[6];
-    const Ix b = nbase + (Ix)(k0 - 1) * N.s2;
-    eface6<T, SCH>(swap_uv(zplane(N, b)), swap_uv(zplane(N, b + N.s2)), swap_uv(zplane(N, b + 2 * N.s2)), wp, wm);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) S(e, r) = wm[e];
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + S(e, rn);
-    __syncthreads();
-  }
-  PF<T> z0 = zplane(N, nbase + (Ix)k0 * N.s2), z1 = zplane(N, nbase + (Ix)(k0 + 1) * N.s2);
-  for (int64_t m = k0; m < k1; ++m) {
-    const Ix b = nbase + (Ix)m * N.s2;
-    const int64_t cl = i + j * cs1 + m * cs2;
-    PF<T> z2 = zplane(N, b + 2 * N.s2);
-    T wpz[6], wpx[6];
-    {
-      T wm[6];
-      eface6<T, SCH>(swap_uv(z0), swap_uv(z1), swap_uv(z2), wpz, wm);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) S(e, r) = wm[e];
-      eface6<T, SCH>(xplane(N, b), xplane(N, b + 1), xplane(N, b + 2), wpx, wm);
-#pragma unroll
-      for (int e = 0; e < 6; ++e) S(6 + e, r) = wm[e];
-    }
-    T L[3][3];
-    LineS<T> ln[6];
-    if (full) {
-      T c[3][8];
-      taylor_from_z(z0, z1, c);
-#pragma unroll
-      for (int col = 0; col < 3; ++col) {
-        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-        ln[col] = line_from_taylor(c, q1, q2, 1, 0, lam1, lam2);      // b = xi
-        ln[3 + col] = line_from_taylor(c, q1, q2, 1, 2, lam1, lam2);  // b = zeta
-      }
-#pragma unroll
-      for (int e = 0; e < 6; ++e) {
-        S(12 + e, r) = ln[e].vp;
-        S(18 + e, r) = T(2) * ln[e].u - ln[e].vm;
-        S(24 + e, r) = ln[e].vm;
-      }
-      T F[3][3], G[3][3], Fa[3], Fb[3], R[3][3];
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-        Fa[q] = c[q][6];
-        Fb[q] = c[q][3];
-      }
-      inv3(F, G);
-      ginv_states3_ax<1>(G, Fa, Fb, lam1, lam2, L, R);
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 3; ++bb) S(30 + 3 * a + bb, r) = R[a][bb];
-    }
-    z0 = z1;
-    z1 = z2;
-    __syncthreads();
-    T Gh[3][3];
-#pragma unroll
-    for (int col = 0; col < 3; ++col) {
-      T pt_a = wpz[3 + col] + S(3 + col, rn), pt_f = wpz[col] + S(col, rn);          // Psi^{zeta->eta}, top
-      T px_a = wpx[3 + col] + S(9 + col, rn), px_f = wpx[col] + S(6 + col, rn);      // Psi^{xi->eta}
-      T dxa = px_a - shfl_up(px_a, 1);
-      T dxf = px_f - shfl_up(px_f, 1);
-      Gh[1][col] = dxa - (pt_a - psi_bot[3 + col]);
-      Gh[2][col] = -dxf;
-      Gh[0][col] = pt_f - psi_bot[col];
-      psi_bot[3 + col] = pt_a;
-      psi_bot[col] = pt_f;
-    }
-    if (O.cactive[1] && out_ok) {
-      T* o = O.cactive[1] + 3 * cl;
-      o[0] = Gh[1][0]; o[1] = Gh[1][1]; o[2] = Gh[1][2];
-    }
-    if (full) {
-#pragma unroll
-      for (int col = 0; col < 3; ++col) {
-        T vx = T(0.5) * ((ln[col].vp - T(2) * ln[col].u) - S(12 + col, rp) + S(18 + col, rn) + S(24 + col, rn2));
-        T vz = T(0.5) * ((ln[3 + col].vp - T(2) * ln[3 + col].u) - S(15 + col, rp) + S(21 + col, rn) + S(27 + col, rn2));
-        Gh[2][col] += vx;  // row zeta: + line[b = xi]
-        Gh[0][col] -= vz;  // row xi:   - line[b = zeta]
-      }
-      T Gf[3][3], Ff[3][3];
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int bb = 0; bb < 3; ++bb) Gf[a][bb] = T(0.5) * (L[a][bb] + S(30 + 3 * a + bb, rn));
-      inv3(Gf, Ff);
-      T Jf = det3(Ff);
-      if (out_ok) {
-        store10(O.face_fwd[1] + 10 * cl, Ff, Jf);
-        store10(O.face_inv[1] + 10 * cl, Gf, Jf);
-        store9(O.face_cons[1] + 9 * cl, Gh);
-      }
-    }
-    __syncthreads();
-  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
 }
 
 // ===========================================================================
@@ -767,97 +563,44 @@ CG_D void cellz_compute(const NodeP<T>& N, Ix b, bool full, T lam1, T lam2, Cell
   }
 }
 
-// reconstructed inverse Jacobian on the zeta faces only (PART = 2 of the zeta kernel): marches along k,
-// carrying the zeta-plane forms and the L state of the cell below the face
-template <class T, int SCH>
-__global__ void __launch_bounds__(128, 3) k_gface_zeta(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
-                                                       int kchunk) {
-  const int lane = threadIdx.x;
-  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
-  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
-  if (j >= nw1) return;
-  const bool out_ok = i < nw0;
-  const int64_t ic = i >= nw0 ? nw0 - 1 : i;
-  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
-  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
-  NodeP<T> N;
-  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
-  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
-  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
-  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
-  auto states = [&](const PF<T>& lo, const PF<T>& hi, T (&L)[3][3], T (&R)[3][3]) {
-    T c[3][8];
-    taylor_from_z(lo, hi, c);
-    T F[3][3], G[3][3], Fa[3], Fb[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-      Fa[q] = c[q][5];
-      Fb[q] = c[q][6];
-    }
-    inv3(F, G);
-    ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, L, R);
-  };
-  PF<T> z0 = zplane(N, nbase + (Ix)k0 * N.s2), z1 = zplane(N, nbase + (Ix)(k0 + 1) * N.s2);
-  T Lp[3][3], Rtmp[3][3];
-  states(z0, z1, Lp, Rtmp);
-  for (int64_t m = k0; m < k1; ++m) {
-    const int64_t cl = i + j * cs1 + m * cs2;
-    if (m + 1 < k1) pf3(N, nbase + (Ix)(m + 3) * N.s2), pf3(N, nbase + (Ix)(m + 3) * N.s2 + N.s1);
-    PF<T> z2 = zplane(N, nbase + (Ix)(m + 2) * N.s2);
-    T Ln[3][3], Rn[3][3], Gf[3][3], Ff[3][3];
-    states(z1, z2, Ln, Rn);  // cell m+1
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        Gf[r][cc] = T(0.5) * (Lp[r][cc] + Rn[r][cc]);
-        Lp[r][cc] = Ln[r][cc];
-      }
-    z1 = z2;
-    inv3(Gf, Ff);
-    T Jf = det3(Ff);
-    if (out_ok) {
-      store10(O.face_fwd[2] + 10 * cl, Ff, Jf);
-      store10(O.face_inv[2] + 10 * cl, Gf, Jf);
-    }
-  }
-}
-
 // per-thread state carried from plane to plane, parked in shared memory (slot-major: conflict-free) so it
 // does not occupy registers across the whole loop body
 template <class T, int NSLOT>
 struct Parked {
   T* base;
-  __device__ __forceinline__ T& operator[](int slot) const { return base[slot * 128]; }
+  __device__ __forceinline__ T& operator[](int slot) const { return base[slot * NT]; }
 };
 
 // SWAP = false: zeta faces, marching along k.  SWAP = true: ETA faces with the same code, marching along j:
 // the strides of eta and zeta are exchanged, i.e. the kernel works in the left-handed labelling
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
-template <class T, int SCH, int PART, bool SWAP>
-__global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
+template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9>;
+template <class T, int SCH, bool SWAP>
+__global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
-  constexpr bool GF = (PART & 2) != 0;
+  constexpr bool GF = true;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
-  __shared__ T park_mem[33 * 128];
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  __shared__ T park_mem[33 * NT];
   const int tid_ = threadIdx.y * 32 + threadIdx.x;
-  Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * 128 + tid_}, P1{park_mem + 12 * 128 + tid_},
-      vp_prev{park_mem + 18 * 128 + tid_};
-  Parked<T, 9> Lpk{park_mem + 24 * 128 + tid_};
+  Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * NT + tid_}, P1{park_mem + 12 * NT + tid_},
+      vp_prev{park_mem + 18 * NT + tid_};
+  Parked<T, 9> Lpk{park_mem + 24 * NT + tid_};
+  T* const stg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_stage_vals<T>;
+  T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
   const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
   const int64_t nw2 = SWAP ? D.nw[1] : D.nw[2];  // extent of the marching axis
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;
-  const int64_t i = (int64_t)blockIdx.x * ZETA_OUT + lane - 1;
+  const int64_t i0 = (int64_t)blockIdx.x * ZETA_OUT;  // first output cell of the warp (lane 1)
+  const int64_t i = i0 + lane - 1;
   const int64_t ic = i > nw0 ? nw0 : i;  // this kernel reads node columns ic .. ic+2
   const bool out_ok = lane >= 1 && lane <= ZETA_OUT && i < nw0;
+  const int nvalid = (int)(nw0 - i0 < ZETA_OUT ? nw0 - i0 : ZETA_OUT);
+  const int rel = lane - 1;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
@@ -896,7 +639,10 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
     }
   }
   for (int64_t m = k0; m < k1; ++m) {
-    const int64_t cl = i + j * cs1 + m * cs2;
+    const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this step
+    const int64_t cl = cl0 + rel;
+    if (lane == 0) bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers
+    __syncwarp();
     if (m + 1 < k1) {  // next iteration: plane m+4 rows j, j+1; plane m+3 rows j-1, j+2
       const Ix bp = nbase + (Ix)(m + 3) * N.s2;
       pf3(N, bp + N.s2);
@@ -970,10 +716,13 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
         }
       }
       T Jf = det3(Ff);
+      Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
       if (out_ok) {
-        store10(O.face_fwd[AX] + 10 * cl, Ff, Jf);
-        store10(O.face_inv[AX] + 10 * cl, Gf, Jf);
+        put10(Sf.slot(rel), Ff, Jf);
+        put10(Si.slot(rel), Gf, Jf);
       }
+      Sf.flush(nvalid, lane);
+      Si.flush(nvalid, lane);
     }
     if (SWAP) {
 #pragma unroll
@@ -982,8 +731,14 @@ __global__ void __launch_bounds__(128, CG_ZETA_MINB) k_face_zeta(Dims D, const T
         Gh[0][col] = r0; Gh[1][col] = r1; Gh[2][col] = r2;
       }
     }
-    if (out_ok) store9(O.face_cons[AX] + 9 * cl, Gh);
+    {
+      Stage<T, 9> S(O.face_cons[AX], cl0, sg_fc);
+      if (out_ok) put9(S.slot(rel), Gh);
+      S.flush(nvalid, lane);
+    }
+    if (lane == 0) bulk_commit();
   }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
 }
 
 // ---------------------------------------------------------------------------
@@ -1158,154 +913,52 @@ inline int launch_metrics2d_tiled(const Dims& D, const T* ex, const T* ey, const
   return 1;
 }
 
-// development switch (env CG_ETA_VARIANT): 5 = zeta kernel marching along j (default), 0 = warp-autonomous
-// k-marching eta kernel, 1/2 = shared-memory eta kernel
-inline int eta_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CG_ETA_VARIANT");
-    v = e ? atoi(e) : 5;
-  }
-  return v;
-}
-
-inline int concurrent_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CG_CONCURRENT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-struct Fork {
-  cudaStream_t s[2];
-  cudaEvent_t start, done[2];
-};
-// helper streams / events, one set per device, created on first use
-inline Fork* fork_streams() {
-  static Fork forks[16];
-  static bool made[16] = {false};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (!made[dev]) {
-    Fork& f = forks[dev];
-    if (cudaStreamCreateWithFlags(&f.s[0], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&f.s[1], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&f.start, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&f.done[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&f.done[1], cudaEventDisableTiming);
-    made[dev] = true;
-  }
-  return &forks[dev];
-}
-
-inline int split_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CG_SPLIT");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
 // mask: bit0 xi kernel (+cell), bit1 eta kernel, bit2 zeta kernel
 template <class T, int SCH>
 inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez, const MetricOut<T>& O, int what,
                            int mask, cudaStream_t st) {
-  const int WY = 4;
-  // enough k-chunks to fill the machine a few times over, but long enough to amortise the prologue
-  int64_t tiles = ((D.nw[0] + WARP_OUT - 1) / WARP_OUT) * ((D.nw[1] + WY - 1) / WY);
-  int kchunk = (int)D.nw[2];
-  const int64_t want = 148LL * 16;
-  if (tiles < want) {
-    int64_t nchunks = (want + tiles - 1) / tiles;
-    kchunk = (int)((D.nw[2] + nchunks - 1) / nchunks);
-    if (kchunk < 16) kchunk = 16;
-    if (kchunk > D.nw[2]) kchunk = (int)D.nw[2];
-  }
+  const int64_t want = 148LL * 16;  // enough chunks to fill the machine a few times over
+  // chunk length along the marching axis: long enough to amortise the prologue
+  auto chunk_of = [&](int64_t tiles, int64_t extent) {
+    int c = (int)extent;
+    if (tiles < want) {
+      int64_t nchunks = (want + tiles - 1) / tiles;
+      c = (int)((extent + nchunks - 1) / nchunks);
+      if (c < 16) c = 16;
+      if (c > extent) c = (int)extent;
+    }
+    return c;
+  };
   dim3 block(32, WY);
-  dim3 grid((unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), (unsigned)((D.nw[1] + WY - 1) / WY),
-            (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
   int n = 0;
   const bool face = what & 2;
-  const bool full = O.face_cons[0] != nullptr;
-  // The three face kernels write disjoint arrays and are bound by different things (xi/zeta: load + shuffle
-  // latency, eta: FP64 issue).  Run them concurrently on two helper streams (fork/join on `st`) so that blocks
-  // of different kernels share an SM and fill each other's stalls and the tail of each grid.
-  cudaStream_t s_eta = st, s_zeta = st;
-  Fork* fk = concurrent_variant() ? fork_streams() : nullptr;
-  if (fk && face && (mask & 7) == 7) {
-    cudaEventRecord(fk->start, st);
-    cudaStreamWaitEvent(fk->s[0], fk->start, 0);
-    cudaStreamWaitEvent(fk->s[1], fk->start, 0);
-    s_eta = fk->s[0];
-    s_zeta = fk->s[1];
-  } else {
-    fk = nullptr;
-  }
-  const bool split = split_variant() != 0 && full && face;  // conserved and G-face halves as separate launches
+  // opt in to > 48 KB of shared memory (per device, cheap: set on every launch)
+  const int xi_smem = WY * xi_stage_vals<T> * (int)sizeof(T), zeta_smem = WY * zeta_stage_vals<T> * (int)sizeof(T);
+  cudaFuncSetAttribute(k_face_xi<T, SCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, xi_smem);
+  cudaFuncSetAttribute(k_face_zeta<T, SCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
+  cudaFuncSetAttribute(k_face_zeta<T, SCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
   if ((mask & 1) && ((what & 1) || face)) {
-    if (split) {
-      k_face_xi<T, SCH, 2><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
-      k_face_xi<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
-      n += 2;
-    } else {
-      k_face_xi<T, SCH, 3><<<grid, block, 0, st>>>(D, ex, ey, ez, O, what, kchunk);
-      ++n;
-    }
+    const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+    const int kchunk = chunk_of((int64_t)gx * gy, D.nw[2]);
+    k_face_xi<T, SCH><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), block, xi_smem, st>>>(
+        D, ex, ey, ez, O, what, kchunk);
+    ++n;
   }
+  const unsigned gxz = (unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT);
   if ((mask & 2) && face) {
-    const int ev = eta_variant();
-    if (ev == 5) {
-      // eta faces with the zeta kernel's code, marching along j: rows = k planes
-      int64_t t2 = ((D.nw[0] + WARP_OUT - 1) / WARP_OUT) * ((D.nw[2] + WY - 1) / WY);
-      int jchunk = (int)D.nw[1];
-      if (t2 < want) {
-        int64_t nch = (want + t2 - 1) / t2;
-        jchunk = (int)((D.nw[1] + nch - 1) / nch);
-        if (jchunk < 16) jchunk = 16;
-        if (jchunk > D.nw[1]) jchunk = (int)D.nw[1];
-      }
-      dim3 g5((unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT), (unsigned)((D.nw[2] + WY - 1) / WY),
-              (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
-      k_face_zeta<T, SCH, 3, true><<<g5, block, 0, s_eta>>>(D, ex, ey, ez, O, jchunk);
-      ++n;
-    } else if (ev >= 1) {
-      auto go = [&](auto kern, int RY) {
-        const size_t shm = (size_t)B2_SLOTS * RY * 32 * sizeof(T);
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
-        dim3 b2(32, RY);
-        dim3 g2(grid.x, (unsigned)((D.nw[1] + (RY - 3) - 1) / (RY - 3)), grid.z);
-        kern<<<g2, b2, shm, st>>>(D, ex, ey, ez, O, kchunk);
-      };
-      if (ev == 1) go(k_face_eta_sh<T, SCH, 16, 1>, 16);
-      else go(k_face_eta_sh<T, SCH, 8, 1>, 8);
-      ++n;
-    } else if (split) {
-      k_face_eta<T, SCH, 2><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-      k_face_eta<T, SCH, 1><<<grid, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-      n += 2;
-    } else {
-      k_face_eta<T, SCH, 3><<<grid, block, 0, s_eta>>>(D, ex, ey, ez, O, kchunk);
-      ++n;
-    }
+    // eta faces with the zeta kernel's code, marching along j: rows = k planes
+    const unsigned gy = (unsigned)((D.nw[2] + WY - 1) / WY);
+    const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
+    k_face_zeta<T, SCH, true><<<dim3(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk)), block, zeta_smem, st>>>(
+        D, ex, ey, ez, O, jchunk);
+    ++n;
   }
   if ((mask & 4) && face) {
-    if (split) {
-      dim3 g3((unsigned)((D.nw[0] + 31) / 32), grid.y, grid.z);
-      k_gface_zeta<T, SCH><<<g3, block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-      k_face_zeta<T, SCH, 1, false><<<dim3((unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT), grid.y, grid.z), block, 0, st>>>(D, ex, ey, ez, O, kchunk);
-      n += 2;
-    } else {
-      k_face_zeta<T, SCH, 3, false><<<dim3((unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT), grid.y, grid.z), block, 0, s_zeta>>>(D, ex, ey, ez, O, kchunk);
-      ++n;
-    }
-  }
-  if (fk) {
-    cudaEventRecord(fk->done[0], fk->s[0]);
-    cudaEventRecord(fk->done[1], fk->s[1]);
-    cudaStreamWaitEvent(st, fk->done[0], 0);
-    cudaStreamWaitEvent(st, fk->done[1], 0);
+    const unsigned gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+    const int kchunk = chunk_of((int64_t)gxz * gy, D.nw[2]);
+    k_face_zeta<T, SCH, false><<<dim3(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), block, zeta_smem, st>>>(
+        D, ex, ey, ez, O, kchunk);
+    ++n;
   }
   return n;
 }

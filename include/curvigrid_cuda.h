@@ -141,7 +141,8 @@ int cg_grid_invalidate(cg_grid* g, int what);
 
 /* device pointer + size of an output array (allocated on first use) */
 int cg_grid_get_ptr(cg_grid* g, int array, int axis, void** devptr, size_t* nbytes);
-/* use caller-owned device storage (CUDA.jl / torch) for an output array */
+/* use caller-owned device storage (CUDA.jl / torch) for an output array; devptr must be 16-byte aligned
+ * (CUDA allocations are): the kernels write with 16-B vector stores and TMA bulk copies */
 int cg_grid_bind_output(cg_grid* g, int array, int axis, void* devptr, size_t nbytes);
 /* synchronous device->host copy of an output array */
 int cg_grid_copy_out(cg_grid* g, int array, int axis, void* host_dst, size_t nbytes);
