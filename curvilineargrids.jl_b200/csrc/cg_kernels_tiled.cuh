@@ -277,12 +277,11 @@ struct Stage {
     else s = sbuf + (int)((reinterpret_cast<uintptr_t>(g) / sizeof(T)) & (A - 1));
   }
   CG_D T* slot(int rel) const { return s + rel * E; }
-  // all lanes of the warp call this after the valid lanes have written their slots
-  CG_D void flush(int nvalid, int lane) const {
+  // hand the chunk to the TMA unit.  All lanes of the warp call this AFTER the valid lanes have written
+  // their slots, executed fence_async_smem() and passed a __syncwarp().
+  CG_D void issue(int nvalid, int lane) const {
     constexpr int A = 16 / (int)sizeof(T);
     if constexpr ((E * sizeof(T)) % 16 == 0) {  // whole elements are 16-B multiples: no head / tail
-      fence_async_smem();
-      __syncwarp();
       if (lane == 0) bulk_store(g, s, (uint32_t)(nvalid * E * sizeof(T)));
       return;
     }
@@ -290,11 +289,14 @@ struct Stage {
     const int head = (int)((A - (reinterpret_cast<uintptr_t>(g) / sizeof(T))) & (A - 1));
     const int tail = (nvals - head) & (A - 1);
     const int body = nvals - head - tail;
-    fence_async_smem();
-    __syncwarp();
     if (lane == 0 && body > 0) bulk_store(g + head, s + head, (uint32_t)(body * sizeof(T)));
     if (lane < head) g[lane] = s[lane];
     if (lane < tail) g[head + body + lane] = s[head + body + lane];
+  }
+  CG_D void flush(int nvalid, int lane) const {
+    fence_async_smem();
+    __syncwarp();
+    issue(nvalid, lane);
   }
 };
 
@@ -333,9 +335,11 @@ struct March {
 // ===========================================================================
 // dynamic shared memory: per warp, staging buffers of the five AoS arrays this kernel writes
 template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9>;
-template <class T, int SCH>
+// ALL = true: FULL profile with cell + face outputs (the hot configuration) — every output switch is a
+// compile-time constant, so the loop body is one straight-line block the scheduler can interleave freely.
+template <class T, int SCH, bool ALL>
 __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
-                                                          MetricOut<T> O, int what, int kchunk) {
+                                                         MetricOut<T> O, int what, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
@@ -353,10 +357,11 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = O.face_cons[0] != nullptr;
-  const bool do_cell = what & 1;
-  const bool do_cons = what & 2;
-  const bool do_gf = (what & 2) && full;
+  const bool full = ALL || O.face_cons[0] != nullptr;
+  const bool do_cell = ALL || (what & 1);
+  const bool do_cons = ALL || (what & 2);
+  const bool do_gf = ALL || ((what & 2) && full);
+  const bool st_cf = ALL || (do_cell && O.cell_fwd), st_ci = ALL || (do_cell && O.cell_inv);
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
   T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_stage_vals<T>;
@@ -388,6 +393,9 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
       }
     }
     PF<T> z2 = zplane(N, b + 2 * N.s2);  // looked-ahead plane; z0, z1 are carried
+    Stage<T, 10> Scf(O.cell_fwd, cl0, sg_cf), Sci(O.cell_inv, cl0, sg_ci), Sff(O.face_fwd[0], cl0, sg_ff),
+        Sfi(O.face_inv[0], cl0, sg_fi);
+    Stage<T, 9> Sfc(O.face_cons[0], cl0, sg_fc);
     T c[3][8];
     taylor_from_z(z0, z1, c);
     if (do_cell || do_gf) {
@@ -410,17 +418,9 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
                        c[q][7] * dl[e] * dl[g];
           }
         T J = det3(Ff);
-        if (O.cell_fwd) {
-          Stage<T, 10> S(O.cell_fwd, cl0, sg_cf);
-          if (out_ok) put10(S.slot(rel), Ff, J);
-          S.flush(nvalid, lane);
-        }
-        if (O.cell_inv) {
-          Stage<T, 10> S(O.cell_inv, cl0, sg_ci);
-          if (out_ok) put10(S.slot(rel), G, J);
-          S.flush(nvalid, lane);
-        }
-        if (O.cjac && out_ok) O.cjac[cl] = J;
+        if (st_cf && out_ok) put10(Scf.slot(rel), Ff, J);
+        if (st_ci && out_ok) put10(Sci.slot(rel), G, J);
+        if (!ALL && O.cjac && out_ok) O.cjac[cl] = J;
       }
       if (do_gf) {
         // ---- reconstructed inverse Jacobian on the xi face ----
@@ -437,74 +437,71 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
           for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
         inv3(Gf, Ff);
         T Jf = det3(Ff);
-        Stage<T, 10> Sf(O.face_fwd[0], cl0, sg_ff), Si(O.face_inv[0], cl0, sg_fi);
         if (out_ok) {
-          put10(Sf.slot(rel), Ff, Jf);
-          put10(Si.slot(rel), Gf, Jf);
+          put10(Sff.slot(rel), Ff, Jf);
+          put10(Sfi.slot(rel), Gf, Jf);
         }
-        Sf.flush(nvalid, lane);
-        Si.flush(nvalid, lane);
       }
     }
-    if (!do_cons) {
-      if (lane == 0) bulk_commit();
-      z0 = z1;
-      z1 = z2;
-      continue;
-    }
-    // ---- zeta-direction edge scalars: top face (m + 1/2), looked ahead one plane ----
-    T psi_top[6];
-    {
-      T wp[6], wm[6];
-      eface6<T, SCH>(z0, z1, z2, wp, wm);
+    if (do_cons) {
+      // ---- zeta-direction edge scalars: top face (m + 1/2), looked ahead one plane ----
+      T psi_top[6];
+      {
+        T wp[6], wm[6];
+        eface6<T, SCH>(z0, z1, z2, wp, wm);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) psi_top[e] = wp[e] + shfl_dn(wm[e], 1);
+        for (int e = 0; e < 6; ++e) psi_top[e] = wp[e] + shfl_dn(wm[e], 1);
+      }
+      // ---- eta-direction edge scalars on both eta faces of the cell ----
+      T dpsi_eta[6];
+      {
+        PF<T> e0 = eplane(N, b - N.s1), e1 = eplane(N, b), e2 = eplane(N, b + N.s1), e3 = eplane(N, b + 2 * N.s1);
+        T wp[6], wm[6];
+        eface6_diff<T, SCH>(e0, e1, e2, e3, wp, wm);  // (face j + 1/2) - (face j - 1/2)
+#pragma unroll
+        for (int e = 0; e < 6; ++e) dpsi_eta[e] = wp[e] + shfl_dn(wm[e], 1);
+      }
+      T Gh[3][3];
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        Gh[0][col] = (psi_top[3 + col] - psi_bot[3 + col]) - dpsi_eta[3 + col];
+        Gh[1][col] = -(psi_top[col] - psi_bot[col]);
+        Gh[2][col] = dpsi_eta[col];
+      }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) psi_bot[e] = psi_top[e];
+      if (!ALL && O.cactive[0] && out_ok) {
+        T* o = O.cactive[0] + 3 * cl;
+        o[0] = Gh[0][0]; o[1] = Gh[0][1]; o[2] = Gh[0][2];
+      }
+      if (full) {
+        // ---- xi line stencils (neighbours by shuffle): rows eta (+, b = zeta) and zeta (-, b = eta) ----
+#pragma unroll
+        for (int col = 0; col < 3; ++col) {
+          const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+#pragma unroll
+          for (int bb = 1; bb <= 2; ++bb) {
+            LineS<T> s = line_from_taylor(c, q1, q2, 0, bb, lam1, lam2);
+            T v = (s.vp - T(2) * s.u) - shfl_up(s.vp, 1) + shfl_dn(T(2) * s.u - s.vm, 1) + shfl_dn(s.vm, 2);
+            if (bb == 2) Gh[1][col] += T(0.5) * v;
+            else Gh[2][col] -= T(0.5) * v;
+          }
+        }
+        if (out_ok) put9(Sfc.slot(rel), Gh);
+      }
     }
     z0 = z1;
     z1 = z2;
-    // ---- eta-direction edge scalars on both eta faces of the cell ----
-    T dpsi_eta[6];
-    {
-      PF<T> e0 = eplane(N, b - N.s1), e1 = eplane(N, b), e2 = eplane(N, b + N.s1), e3 = eplane(N, b + 2 * N.s1);
-      T wp[6], wm[6];
-      eface6_diff<T, SCH>(e0, e1, e2, e3, wp, wm);  // (face j + 1/2) - (face j - 1/2)
-#pragma unroll
-      for (int e = 0; e < 6; ++e) dpsi_eta[e] = wp[e] + shfl_dn(wm[e], 1);
+    // ---- one flush point: staged arrays -> TMA ----
+    fence_async_smem();
+    __syncwarp();
+    if (st_cf) Scf.issue(nvalid, lane);
+    if (st_ci) Sci.issue(nvalid, lane);
+    if (do_gf) {
+      Sff.issue(nvalid, lane);
+      Sfi.issue(nvalid, lane);
     }
-    T Gh[3][3];
-#pragma unroll
-    for (int col = 0; col < 3; ++col) {
-      Gh[0][col] = (psi_top[3 + col] - psi_bot[3 + col]) - dpsi_eta[3 + col];
-      Gh[1][col] = -(psi_top[col] - psi_bot[col]);
-      Gh[2][col] = dpsi_eta[col];
-    }
-#pragma unroll
-    for (int e = 0; e < 6; ++e) psi_bot[e] = psi_top[e];
-    if (O.cactive[0] && out_ok) {
-      T* o = O.cactive[0] + 3 * cl;
-      o[0] = Gh[0][0]; o[1] = Gh[0][1]; o[2] = Gh[0][2];
-    }
-    if (!full) {
-      if (lane == 0) bulk_commit();
-      continue;
-    }
-    // ---- xi line stencils (neighbours by shuffle): rows eta (+, b = zeta) and zeta (-, b = eta) ----
-#pragma unroll
-    for (int col = 0; col < 3; ++col) {
-      const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-#pragma unroll
-      for (int bb = 1; bb <= 2; ++bb) {
-        LineS<T> s = line_from_taylor(c, q1, q2, 0, bb, lam1, lam2);
-        T v = (s.vp - T(2) * s.u) - shfl_up(s.vp, 1) + shfl_dn(T(2) * s.u - s.vm, 1) + shfl_dn(s.vm, 2);
-        if (bb == 2) Gh[1][col] += T(0.5) * v;
-        else Gh[2][col] -= T(0.5) * v;
-      }
-    }
-    {
-      Stage<T, 9> S(O.face_cons[0], cl0, sg_fc);
-      if (out_ok) put9(S.slot(rel), Gh);
-      S.flush(nvalid, lane);
-    }
+    if (do_cons && full) Sfc.issue(nvalid, lane);
     if (lane == 0) bulk_commit();
   }
   if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
@@ -576,10 +573,13 @@ struct Parked {
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
 template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9>;
-template <class T, int SCH, bool SWAP>
+#ifndef CG_GF
+#define CG_GF true
+#endif
+template <class T, int SCH, bool SWAP, bool ALL>
 __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
-  constexpr bool GF = true;
+  constexpr bool GF = CG_GF;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   __shared__ T park_mem[33 * NT];
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[SWAP ? 2 : 1]; N.s2 = (Ix)D.se[SWAP ? 1 : 2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = O.face_cons[AX] != nullptr;
+  const bool full = ALL || O.face_cons[AX] != nullptr;
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
   // cell strides of the row axis and the marching axis in the output arrays
   const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
@@ -672,12 +672,14 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
       wpe[e] = cf.wpe[e];
       wpx[e] = cf.wpx[e];
     }
-    if (O.cactive[AX] && out_ok) {
+    if (!ALL && O.cactive[AX] && out_ok) {
       T* o = O.cactive[AX] + 3 * cl;
-      const T sg = SWAP ? T(-1) : T(1);
-      o[0] = sg * Gh[2][0]; o[1] = sg * Gh[2][1]; o[2] = sg * Gh[2][2];
+      const T sgn = SWAP ? T(-1) : T(1);
+      o[0] = sgn * Gh[2][0]; o[1] = sgn * Gh[2][1]; o[2] = sgn * Gh[2][2];
     }
     if (!full) continue;
+    Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
+    Stage<T, 9> Sc(O.face_cons[AX], cl0, sg_fc);
     // zeta line stencil: cells m-1, m (in P1), m+1 (front), m+2 (looked ahead)
     {
       T c2[3][8];
@@ -716,13 +718,10 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
         }
       }
       T Jf = det3(Ff);
-      Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
       if (out_ok) {
         put10(Sf.slot(rel), Ff, Jf);
         put10(Si.slot(rel), Gf, Jf);
       }
-      Sf.flush(nvalid, lane);
-      Si.flush(nvalid, lane);
     }
     if (SWAP) {
 #pragma unroll
@@ -731,11 +730,15 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
         Gh[0][col] = r0; Gh[1][col] = r1; Gh[2][col] = r2;
       }
     }
-    {
-      Stage<T, 9> S(O.face_cons[AX], cl0, sg_fc);
-      if (out_ok) put9(S.slot(rel), Gh);
-      S.flush(nvalid, lane);
+    if (out_ok) put9(Sc.slot(rel), Gh);
+    // ---- one flush point: staged arrays -> TMA ----
+    fence_async_smem();
+    __syncwarp();
+    if (GF) {
+      Sf.issue(nvalid, lane);
+      Si.issue(nvalid, lane);
     }
+    Sc.issue(nvalid, lane);
     if (lane == 0) bulk_commit();
   }
   if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
@@ -934,14 +937,20 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   const bool face = what & 2;
   // opt in to > 48 KB of shared memory (per device, cheap: set on every launch)
   const int xi_smem = WY * xi_stage_vals<T> * (int)sizeof(T), zeta_smem = WY * zeta_stage_vals<T> * (int)sizeof(T);
-  cudaFuncSetAttribute(k_face_xi<T, SCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, xi_smem);
-  cudaFuncSetAttribute(k_face_zeta<T, SCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
-  cudaFuncSetAttribute(k_face_zeta<T, SCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
+  cudaFuncSetAttribute(k_face_xi<T, SCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xi_smem);
+  cudaFuncSetAttribute(k_face_xi<T, SCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xi_smem);
+  cudaFuncSetAttribute(k_face_zeta<T, SCH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
+  cudaFuncSetAttribute(k_face_zeta<T, SCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
+  cudaFuncSetAttribute(k_face_zeta<T, SCH, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
+  cudaFuncSetAttribute(k_face_zeta<T, SCH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
   if ((mask & 1) && ((what & 1) || face)) {
     const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
     const int kchunk = chunk_of((int64_t)gx * gy, D.nw[2]);
-    k_face_xi<T, SCH><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), block, xi_smem, st>>>(
-        D, ex, ey, ez, O, what, kchunk);
+    const dim3 grid(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
+    const bool all = (what & 3) == 3 && O.cell_fwd && O.cell_inv && O.face_fwd[0] && O.face_inv[0] && O.face_cons[0] &&
+                     !O.cjac && !O.cactive[0];
+    if (all) k_face_xi<T, SCH, true><<<grid, block, xi_smem, st>>>(D, ex, ey, ez, O, what, kchunk);
+    else k_face_xi<T, SCH, false><<<grid, block, xi_smem, st>>>(D, ex, ey, ez, O, what, kchunk);
     ++n;
   }
   const unsigned gxz = (unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT);
@@ -949,15 +958,19 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     // eta faces with the zeta kernel's code, marching along j: rows = k planes
     const unsigned gy = (unsigned)((D.nw[2] + WY - 1) / WY);
     const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
-    k_face_zeta<T, SCH, true><<<dim3(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk)), block, zeta_smem, st>>>(
-        D, ex, ey, ez, O, jchunk);
+    const dim3 grid(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
+    if (O.face_cons[1] && O.face_fwd[1] && O.face_inv[1] && !O.cactive[1])
+      k_face_zeta<T, SCH, true, true><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, jchunk);
+    else k_face_zeta<T, SCH, true, false><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, jchunk);
     ++n;
   }
   if ((mask & 4) && face) {
     const unsigned gy = (unsigned)((D.nw[1] + WY - 1) / WY);
     const int kchunk = chunk_of((int64_t)gxz * gy, D.nw[2]);
-    k_face_zeta<T, SCH, false><<<dim3(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), block, zeta_smem, st>>>(
-        D, ex, ey, ez, O, kchunk);
+    const dim3 grid(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
+    if (O.face_cons[2] && O.face_fwd[2] && O.face_inv[2] && !O.cactive[2])
+      k_face_zeta<T, SCH, false, true><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, kchunk);
+    else k_face_zeta<T, SCH, false, false><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, kchunk);
     ++n;
   }
   return n;
