@@ -63,6 +63,14 @@ CG_D void pf3(const NodeP<T, IX>& N, IX b) {
   for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(N.q[q] + b));
 }
 
+// RAW bilinear form of 4 face nodes n[bu][bv] (no normalisation: pure sums and differences)
+//   c0 = 4 * (true c0), cu = 2 * (true cu), cv = 2 * (true cv), cuv = true cuv
+// Every consumer below is bilinear in form coefficients, so the powers of two fold into its constants.
+template <class T>
+CG_D Form4<T> raw_form(T n00, T n10, T n01, T n11) {
+  T s0 = n10 + n00, d0 = n10 - n00, s1 = n11 + n01, d1 = n11 - n01;
+  return {s0 + s1, d0 + d1, s1 - s0, d1 - d0};
+}
 // zeta-plane forms (fixed k), transverse (xi, eta)
 template <class T, class IX>
 CG_D PF<T> zplane(const NodeP<T, IX>& N, IX b) {
@@ -70,32 +78,93 @@ CG_D PF<T> zplane(const NodeP<T, IX>& N, IX b) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     const T* A = N.q[q] + b;
-    f.q[q] = face_form(ldn(A), ldn(A + 1), ldn(A + N.s1), ldn(A + N.s1 + 1));
+    f.q[q] = raw_form(ldn(A), ldn(A + 1), ldn(A + N.s1), ldn(A + N.s1 + 1));
   }
   return f;
 }
-// eta-plane forms (fixed j), transverse (xi, zeta)
+// sum / difference of a node column across two consecutive zeta planes, per coordinate
+template <class T>
+struct ZPair {
+  T s[3], d[3];
+};
 template <class T, class IX>
-CG_D PF<T> eplane(const NodeP<T, IX>& N, IX b) {
-  PF<T> f;
+CG_D ZPair<T> zpair(const NodeP<T, IX>& N, IX b) {
+  ZPair<T> p;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
-    const T* A = N.q[q] + b;
-    f.q[q] = face_form(ldn(A), ldn(A + 1), ldn(A + N.s2), ldn(A + N.s2 + 1));
+    const T lo = ldn(N.q[q] + b), hi = ldn(N.q[q] + b + N.s2);
+    p.s[q] = hi + lo;
+    p.d[q] = hi - lo;
   }
-  return f;
+  return p;
 }
-// xi-plane forms (fixed i), transverse (eta, zeta)
-template <class T, class IX>
-CG_D PF<T> xplane(const NodeP<T, IX>& N, IX b) {
+// raw form of the plane through two node columns a, b (u = from a to b, v = zeta): an eta-plane from two
+// xi-adjacent columns, a xi-plane from two eta-adjacent columns; 4 additions per coordinate
+template <class T>
+CG_D PF<T> pair_form(const ZPair<T>& a, const ZPair<T>& b) {
   PF<T> f;
 #pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const T* A = N.q[q] + b;
-    f.q[q] = face_form(ldn(A), ldn(A + N.s1), ldn(A + N.s2), ldn(A + N.s1 + N.s2));
-  }
+  for (int q = 0; q < 3; ++q) f.q[q] = {a.s[q] + b.s[q], b.s[q] - a.s[q], a.d[q] + b.d[q], b.d[q] - a.d[q]};
   return f;
 }
+// ---------------------------------------------------------------------------
+// Per-warp ring of node planes in shared memory.  The marching kernels run at 8 warps/SM, too few to hide a
+// global-load miss, and prefetch.global.L1 does not shorten it (measured).  Each lane therefore copies the
+// node column it owns (plus one spare column, by lane 0) of the plane that is first needed in the NEXT step
+// with cp.async, asynchronously, while the current step computes; all node reads of a step are LDS.
+// Layout [slot][row][coordinate][column]: lanes read consecutive columns (conflict-free).
+// ---------------------------------------------------------------------------
+constexpr int RING_COLS = 34;  // 32 lanes + the spare column 32 (+1 keeps rows 16-B aligned)
+constexpr int RING_SLOTS = 4;
+template <int ROWS> constexpr int ring_vals = RING_SLOTS * ROWS * 3 * RING_COLS;
+template <class T> CG_D void cp_async_val(T* sdst, const T* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst);
+  if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+CG_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+CG_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <class T, int ROWS>
+struct Ring {
+  T* base;
+  CG_D T* row(int plane, int r, int q) const { return base + (((plane & (RING_SLOTS - 1)) * ROWS + r) * 3 + q) * RING_COLS; }
+  // copy ring rows [r0, r1) of one plane: g0 = index of (this lane's column, ring row 0, that plane),
+  // gx = the same for the spare column (used by lane 0 only)
+  template <class IX>
+  CG_D void fetch(const NodeP<T, IX>& N, int plane, IX g0, IX gx, int lane, int r0 = 0, int r1 = ROWS) const {
+#pragma unroll
+    for (int r = r0; r < r1; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        T* dst = row(plane, r, q);
+        cp_async_val(dst + lane, N.q[q] + g0 + (IX)r * N.s1);
+        if (lane == 0) cp_async_val(dst + 32, N.q[q] + gx + (IX)r * N.s1);
+      }
+  }
+  // raw form of the zeta-plane `plane`, rows r, r+1, columns lane, lane+1
+  CG_D PF<T> zplane(int plane, int r, int lane) const {
+    PF<T> f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const T* a = row(plane, r, q) + lane;
+      const T* b = row(plane, r + 1, q) + lane;
+      f.q[q] = raw_form(a[0], a[1], b[0], b[1]);
+    }
+    return f;
+  }
+  // zeta-pair (planes plane, plane+1) of the node column (row r, column c)
+  CG_D ZPair<T> zpair(int plane, int r, int c) const {
+    ZPair<T> p;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const T lo = row(plane, r, q)[c], hi = row(plane + 1, r, q)[c];
+      p.s[q] = hi + lo;
+      p.d[q] = hi - lo;
+    }
+    return p;
+  }
+};
+
 template <class T>
 CG_D PF<T> swap_uv(const PF<T>& p) {
   PF<T> o;
@@ -104,45 +173,61 @@ CG_D PF<T> swap_uv(const PF<T>& p) {
   return o;
 }
 
-// cell Taylor coefficients from the two zeta-planes of the cell (bitmask: 1 xi, 2 eta, 4 zeta)
+// cell Taylor coefficients (true values) from the two RAW zeta-planes of the cell (bitmask: 1 xi, 2 eta, 4 zeta)
 template <class T>
 CG_D void taylor_from_z(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
-    c[q][0] = T(0.5) * (lo.q[q].c0 + hi.q[q].c0);
-    c[q][1] = T(0.5) * (lo.q[q].cu + hi.q[q].cu);
-    c[q][2] = T(0.5) * (lo.q[q].cv + hi.q[q].cv);
+    c[q][0] = T(0.125) * (lo.q[q].c0 + hi.q[q].c0);
+    c[q][1] = T(0.25) * (lo.q[q].cu + hi.q[q].cu);
+    c[q][2] = T(0.25) * (lo.q[q].cv + hi.q[q].cv);
     c[q][3] = T(0.5) * (lo.q[q].cuv + hi.q[q].cuv);
-    c[q][4] = hi.q[q].c0 - lo.q[q].c0;
-    c[q][5] = hi.q[q].cu - lo.q[q].cu;
-    c[q][6] = hi.q[q].cv - lo.q[q].cv;
+    c[q][4] = T(0.25) * (hi.q[q].c0 - lo.q[q].c0);
+    c[q][5] = T(0.5) * (hi.q[q].cu - lo.q[q].cu);
+    c[q][6] = T(0.5) * (hi.q[q].cv - lo.q[q].cv);
+    c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
+  }
+}
+// the same from the two RAW eta-planes (u = xi, v = zeta) of the cell
+template <class T>
+CG_D void taylor_from_e(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    c[q][0] = T(0.125) * (lo.q[q].c0 + hi.q[q].c0);
+    c[q][1] = T(0.25) * (lo.q[q].cu + hi.q[q].cu);
+    c[q][2] = T(0.25) * (hi.q[q].c0 - lo.q[q].c0);
+    c[q][3] = T(0.5) * (hi.q[q].cu - lo.q[q].cu);
+    c[q][4] = T(0.25) * (lo.q[q].cv + hi.q[q].cv);
+    c[q][5] = T(0.5) * (lo.q[q].cuv + hi.q[q].cuv);
+    c[q][6] = T(0.5) * (hi.q[q].cv - lo.q[q].cv);
     c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
   }
 }
 
 // Half states W+-_f of the six E^a polynomials on the a-face between cells c and
-// c+a.  P0/P1/P2: forms on the low face of c, the shared face, the high face of
-// c+a, Form4 ordered (u = f, v = t).  Index = bsel*3 + col, bsel 0: b = f, 1: b = t;
+// c+a.  P0/P1/P2: RAW forms on the low face of c, the shared face, the high face of
+// c+a, Form4 ordered (u = f, v = t).  Raw products carry 8 (cu c0, cv c0), 4 (cu cu, cv cu, cuv c0) or
+// 2 (cuv cu) times the true value; the factors are folded into the reconstruction weights.  Index = bsel*3 + col, bsel 0: b = f, 1: b = t;
 // col selects (q1,q2) = (col+1, col+2) mod 3.       
 template <class T, int SCH>
 CG_D void eface6(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, T (&wp)[6], T (&wm)[6]) {
   if (SCH == ENDPOINT) {
     // E = 1/2 (P_c + P_{c+a}) with cell-centre values; W+ = W- = E/2
-    T q0c[3], q0n[3], qfc[3], qfn[3], qtc[3], qtn[3];
+    T q0c[3], q0n[3], qfc[3], qfn[3], qtc[3], qtn[3];  // raw sums: 8 x and 4 x the cell-centre values
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      q0c[q] = T(0.5) * (P0.q[q].c0 + P1.q[q].c0);
-      q0n[q] = T(0.5) * (P1.q[q].c0 + P2.q[q].c0);
-      qfc[q] = T(0.5) * (P0.q[q].cu + P1.q[q].cu);
-      qfn[q] = T(0.5) * (P1.q[q].cu + P2.q[q].cu);
-      qtc[q] = T(0.5) * (P0.q[q].cv + P1.q[q].cv);
-      qtn[q] = T(0.5) * (P1.q[q].cv + P2.q[q].cv);
+      q0c[q] = P0.q[q].c0 + P1.q[q].c0;
+      q0n[q] = P1.q[q].c0 + P2.q[q].c0;
+      qfc[q] = P0.q[q].cu + P1.q[q].cu;
+      qfn[q] = P1.q[q].cu + P2.q[q].cu;
+      qtc[q] = P0.q[q].cv + P1.q[q].cv;
+      qtn[q] = P1.q[q].cv + P2.q[q].cv;
     }
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
       const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-      wp[col] = wm[col] = T(0.25) * (qfc[q1] * q0c[q2] + qfn[q1] * q0n[q2]);
-      wp[3 + col] = wm[3 + col] = T(0.25) * (qtc[q1] * q0c[q2] + qtn[q1] * q0n[q2]);
+      wp[col] = wm[col] = T(0.25 / 32) * (qfc[q1] * q0c[q2] + qfn[q1] * q0n[q2]);
+      wp[3 + col] = wm[3 + col] = T(0.25 / 32) * (qtc[q1] * q0c[q2] + qtn[q1] * q0n[q2]);
     }
     return;
   }
@@ -162,15 +247,15 @@ CG_D void eface6(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, T (&wp)[6], 
     // b = f
     T e0 = A1.cu * B1.c0 - k2 * (a0.cu * b0.c0 + a1.cu * b1.c0);
     T e1 = A1.cu * B1.cu - k2 * (a0.cu * b0.cu + a1.cu * b1.cu);
-    T h0 = T(0.5) * e0, h1 = (T(0.5) * lam1) * e1;
+    T h0 = T(0.0625) * e0, h1 = (T(0.125) * lam1) * e1;  // raw e0 = 8 x, raw e1 = 4 x
     wp[col] = h0 + h1;
     wm[col] = h0 - h1;
     // b = t
     e0 = A1.cv * B1.c0 - k2 * (a0.cv * b0.c0 + a1.cv * b1.c0);
     e1 = A1.cv * B1.cu + A1.cuv * B1.c0 - k2 * (a0.cv * b0.cu + a0.cuv * b0.c0 + a1.cv * b1.cu + a1.cuv * b1.c0);
     T e2 = A1.cuv * B1.cu - k2 * (a0.cuv * b0.cu + a1.cuv * b1.cu);
-    h0 = T(0.5) * e0 + lam2 * e2;
-    h1 = (T(0.5) * lam1) * e1;
+    h0 = T(0.0625) * e0 + (T(0.5) * lam2) * e2;  // raw e0 = 8 x, e1 = 4 x, e2 = 2 x
+    h1 = (T(0.125) * lam1) * e1;
     wp[3 + col] = h0 + h1;
     wm[3 + col] = h0 - h1;
   }
@@ -183,21 +268,21 @@ template <class T, int SCH>
 CG_D void eface6_diff(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, const PF<T>& P3, T (&wp)[6], T (&wm)[6]) {
   if (SCH == ENDPOINT) {
     // E = 1/2 (P_c + P_{c+a}) with cell-centre values: difference = 1/2 (P_{c+a} - P_{c-a}); W+ = W- = E/2
-    T q0a[3], q0b[3], qfa[3], qfb[3], qta[3], qtb[3];
+    T q0a[3], q0b[3], qfa[3], qfb[3], qta[3], qtb[3];  // raw sums: 8 x and 4 x the cell-centre values
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      q0a[q] = T(0.5) * (P0.q[q].c0 + P1.q[q].c0);
-      q0b[q] = T(0.5) * (P2.q[q].c0 + P3.q[q].c0);
-      qfa[q] = T(0.5) * (P0.q[q].cu + P1.q[q].cu);
-      qfb[q] = T(0.5) * (P2.q[q].cu + P3.q[q].cu);
-      qta[q] = T(0.5) * (P0.q[q].cv + P1.q[q].cv);
-      qtb[q] = T(0.5) * (P2.q[q].cv + P3.q[q].cv);
+      q0a[q] = P0.q[q].c0 + P1.q[q].c0;
+      q0b[q] = P2.q[q].c0 + P3.q[q].c0;
+      qfa[q] = P0.q[q].cu + P1.q[q].cu;
+      qfb[q] = P2.q[q].cu + P3.q[q].cu;
+      qta[q] = P0.q[q].cv + P1.q[q].cv;
+      qtb[q] = P2.q[q].cv + P3.q[q].cv;
     }
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
       const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-      wp[col] = wm[col] = T(0.25) * (qfb[q1] * q0b[q2] - qfa[q1] * q0a[q2]);
-      wp[3 + col] = wm[3 + col] = T(0.25) * (qtb[q1] * q0b[q2] - qta[q1] * q0a[q2]);
+      wp[col] = wm[col] = T(0.25 / 32) * (qfb[q1] * q0b[q2] - qfa[q1] * q0a[q2]);
+      wp[3 + col] = wm[3 + col] = T(0.25 / 32) * (qtb[q1] * q0b[q2] - qta[q1] * q0a[q2]);
     }
     return;
   }
@@ -216,15 +301,15 @@ CG_D void eface6_diff(const PF<T>& P0, const PF<T>& P1, const PF<T>& P2, const P
     const Form4<T>&al = dL[q1], &bl = dL[q2], &ah = dH[q1], &bh = dH[q2];
     T e0 = (A2.cu * B2.c0 - A1.cu * B1.c0) - k2 * (ah.cu * bh.c0 - al.cu * bl.c0);
     T e1 = (A2.cu * B2.cu - A1.cu * B1.cu) - k2 * (ah.cu * bh.cu - al.cu * bl.cu);
-    T h0 = T(0.5) * e0, h1 = (T(0.5) * lam1) * e1;
+    T h0 = T(0.0625) * e0, h1 = (T(0.125) * lam1) * e1;  // raw e0 = 8 x, raw e1 = 4 x
     wp[col] = h0 + h1;
     wm[col] = h0 - h1;
     e0 = (A2.cv * B2.c0 - A1.cv * B1.c0) - k2 * (ah.cv * bh.c0 - al.cv * bl.c0);
     e1 = ((A2.cv * B2.cu + A2.cuv * B2.c0) - (A1.cv * B1.cu + A1.cuv * B1.c0)) -
          k2 * ((ah.cv * bh.cu + ah.cuv * bh.c0) - (al.cv * bl.cu + al.cuv * bl.c0));
     T e2 = (A2.cuv * B2.cu - A1.cuv * B1.cu) - k2 * (ah.cuv * bh.cu - al.cuv * bl.cu);
-    h0 = T(0.5) * e0 + lam2 * e2;
-    h1 = (T(0.5) * lam1) * e1;
+    h0 = T(0.0625) * e0 + (T(0.5) * lam2) * e2;  // raw e0 = 8 x, e1 = 4 x, e2 = 2 x
+    h1 = (T(0.125) * lam1) * e1;
     wp[3 + col] = h0 + h1;
     wm[3 + col] = h0 - h1;
   }
@@ -334,7 +419,7 @@ struct March {
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
 // ===========================================================================
 // dynamic shared memory: per warp, staging buffers of the five AoS arrays this kernel writes
-template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9>;
+template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4>;
 // ALL = true: FULL profile with cell + face outputs (the hot configuration) — every output switch is a
 // compile-time constant, so the loop body is one straight-line block the scheduler can interleave freely.
 template <class T, int SCH, bool ALL>
@@ -367,6 +452,13 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
   T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_stage_vals<T>;
   T* const sg_cf = sg, * const sg_ci = sg + stage_len<T, 10>, * const sg_ff = sg + 2 * stage_len<T, 10>,
          * const sg_fi = sg + 3 * stage_len<T, 10>, * const sg_fc = sg + 4 * stage_len<T, 10>;
+  // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2)
+  const Ring<T, 4> R{sg + 4 * stage_len<T, 10> + stage_len<T, 9>};
+  auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
+  const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32) + (Ix)j * N.s1 + N.s2;  // plane 0, row j-1
+#pragma unroll
+  for (int pp = 0; pp < 3; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
+  cp_async_commit();
 
   T psi_bot[6];
   if (do_cons) {
@@ -381,18 +473,16 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
     const Ix b = nbase + (Ix)m * N.s2;
     const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this plane
     const int64_t cl = cl0 + rel;
-    // the TMA unit has finished reading last step's staging buffers
+    // the TMA unit has finished reading last step's staging buffers; the node planes m .. m+2 have landed
     if (lane == 0) bulk_wait_read();
+    cp_async_wait_all();
     __syncwarp();
-    if (m + 1 < k1) {  // next iteration's new node rows: plane m+3 (rows j, j+1), plane m+2 (rows j-1, j+2)
-      pf3(N, b + 3 * N.s2);
-      pf3(N, b + 3 * N.s2 + N.s1);
-      if (do_cons) {
-        pf3(N, b + 2 * N.s2 - N.s1);
-        pf3(N, b + 2 * N.s2 + 2 * N.s1);
-      }
+    if (m + 1 < k1) {  // plane m+3 (first needed in the next step) into the slot plane m-1 has left
+      R.fetch(N, (int)(m + 3), rg0 + (Ix)(m + 3) * N.s2, rgx + (Ix)(m + 3) * N.s2, lane);
+      cp_async_commit();
     }
-    PF<T> z2 = zplane(N, b + 2 * N.s2);  // looked-ahead plane; z0, z1 are carried
+    const int pm = (int)m;
+    PF<T> z2 = R.zplane(pm + 2, 1, lane);  // looked-ahead plane; z0, z1 are carried
     Stage<T, 10> Scf(O.cell_fwd, cl0, sg_cf), Sci(O.cell_inv, cl0, sg_ci), Sff(O.face_fwd[0], cl0, sg_ff),
         Sfi(O.face_inv[0], cl0, sg_fi);
     Stage<T, 9> Sfc(O.face_cons[0], cl0, sg_fc);
@@ -435,8 +525,7 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
-        inv3(Gf, Ff);
-        T Jf = det3(Ff);
+        T Jf = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
         if (out_ok) {
           put10(Sff.slot(rel), Ff, Jf);
           put10(Sfi.slot(rel), Gf, Jf);
@@ -455,7 +544,11 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
       // ---- eta-direction edge scalars on both eta faces of the cell ----
       T dpsi_eta[6];
       {
-        PF<T> e0 = eplane(N, b - N.s1), e1 = eplane(N, b), e2 = eplane(N, b + N.s1), e3 = eplane(N, b + 2 * N.s1);
+        // eta-planes j-1 .. j+2 (u = xi, v = zeta) from the zeta-pairs of the node columns i, i+1
+        PF<T> e0 = pair_form(R.zpair(pm, 0, lane), R.zpair(pm, 0, lane + 1)),
+              e1 = pair_form(R.zpair(pm, 1, lane), R.zpair(pm, 1, lane + 1)),
+              e2 = pair_form(R.zpair(pm, 2, lane), R.zpair(pm, 2, lane + 1)),
+              e3 = pair_form(R.zpair(pm, 3, lane), R.zpair(pm, 3, lane + 1));
         T wp[6], wm[6];
         eface6_diff<T, SCH>(e0, e1, e2, e3, wp, wm);  // (face j + 1/2) - (face j - 1/2)
 #pragma unroll
@@ -520,33 +613,44 @@ struct CellZ {
   T wme[6];
   T wpx[6];  // W+_zeta [E^xi(i+1/2)]
   T wmx[6];
-  LineS<T> ln[6];  // index = bb*3 + col; bb 0: b = xi, 1: b = eta
   T L[3][3], R[3][3];
 };
 
-template <class T, int SCH, bool GF>
-CG_D void cellz_compute(const NodeP<T>& N, Ix b, bool full, T lam1, T lam2, CellZ<T>& o) {
-  // b = node (ic, j, p) of the cell's low corner
-  {
-    // eta faces j-1/2 and j+1/2: eta-planes j-1 .. j+2, forms (xi,zeta) -> need (u,v) = (zeta, xi)
-    PF<T> e0 = swap_uv(eplane(N, b - N.s1)), e1 = swap_uv(eplane(N, b)), e2 = swap_uv(eplane(N, b + N.s1)),
-          e3 = swap_uv(eplane(N, b + 2 * N.s1));
-    eface6_diff<T, SCH>(e0, e1, e2, e3, o.wpe, o.wme);
-  }
-  {
-    // xi face i+1/2: xi-planes i, i+1, i+2, forms (eta,zeta) -> need (u,v) = (zeta, eta)
-    eface6<T, SCH>(swap_uv(xplane(N, b)), swap_uv(xplane(N, b + 1)), swap_uv(xplane(N, b + 2)), o.wpx, o.wmx);
-  }
-  if (!full) return;
+// the six zeta-line scalars of the cell whose low corner node is b (index = bb*3 + col; bb 0: b = xi, 1: b = eta)
+template <class T>
+CG_D void zlines(const NodeP<T>& N, Ix b, T lam1, T lam2, LineS<T> (&ln)[6]) {
   T c[3][8];
   taylor_from_z(zplane(N, b), zplane(N, b + N.s2), c);
 #pragma unroll
   for (int col = 0; col < 3; ++col) {
     const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-    o.ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
-    o.ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
+    ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
+    ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
   }
+}
+
+template <class T, int SCH, bool GF>
+CG_D void cellz_compute(const NodeP<T>& N, Ix b, bool full, T lam1, T lam2, CellZ<T>& o) {
+  // b = node (ic, j, p) of the cell's low corner.  All plane forms come from the zeta-pairs (sum, difference
+  // across planes p, p+1) of the node columns rows j-1 .. j+2 x cols i, i+1 and rows j, j+1 x col i+2.
+  const ZPair<T> p00 = zpair(N, b), p01 = zpair(N, b + 1), p10 = zpair(N, b + N.s1), p11 = zpair(N, b + N.s1 + 1);
+  const PF<T> E1 = pair_form(p00, p01), E2 = pair_form(p10, p11);  // eta-planes j, j+1 (u = xi, v = zeta)
+  {
+    // eta faces j-1/2 and j+1/2: eta-planes j-1 .. j+2 -> need (u,v) = (zeta, xi)
+    const PF<T> E0 = pair_form(zpair(N, b - N.s1), zpair(N, b - N.s1 + 1)),
+                E3 = pair_form(zpair(N, b + 2 * N.s1), zpair(N, b + 2 * N.s1 + 1));
+    eface6_diff<T, SCH>(swap_uv(E0), swap_uv(E1), swap_uv(E2), swap_uv(E3), o.wpe, o.wme);
+  }
+  {
+    // xi face i+1/2: xi-planes i, i+1, i+2, forms (eta,zeta) -> need (u,v) = (zeta, eta)
+    const PF<T> X0 = pair_form(p00, p10), X1 = pair_form(p01, p11),
+                X2 = pair_form(zpair(N, b + 2), zpair(N, b + N.s1 + 2));
+    eface6<T, SCH>(swap_uv(X0), swap_uv(X1), swap_uv(X2), o.wpx, o.wmx);
+  }
+  if (!full) return;
   if (GF) {
+    T c[3][8];
+    taylor_from_e(E1, E2, c);
     T F[3][3], G[3][3], Fa[3], Fb[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -582,11 +686,13 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   constexpr bool GF = CG_GF;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
-  __shared__ T park_mem[33 * NT];
+  __shared__ T park_mem[45 * NT];
   const int tid_ = threadIdx.y * 32 + threadIdx.x;
+  // line stencil state: P1 = (V+ - 2U)_m - V+_{m-1}, Pn = the same one cell ahead,
+  // Qn = (2U - V-)_{m+1}, X1 = V+_{m+1}
   Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * NT + tid_}, P1{park_mem + 12 * NT + tid_},
-      vp_prev{park_mem + 18 * NT + tid_};
-  Parked<T, 9> Lpk{park_mem + 24 * NT + tid_};
+      Pn{park_mem + 18 * NT + tid_}, Qn{park_mem + 24 * NT + tid_}, X1{park_mem + 30 * NT + tid_};
+  Parked<T, 9> Lpk{park_mem + 36 * NT + tid_};
   T* const stg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_stage_vals<T>;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
   const int lane = threadIdx.x;
@@ -614,11 +720,18 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
 
   // carried state: W+ of the cell below the face, line partial sums, L state (parked in shared memory)
   {
-    CellZ<T> cm;  // cell k0 - 1
     if (full) {
-      cellz_compute<T, SCH, GF>(N, nbase + (Ix)(k0 - 1) * N.s2, true, lam1, lam2, cm);
+      LineS<T> lm[6], l0[6], l1[6];  // cells k0 - 1, k0, k0 + 1
+      zlines(N, nbase + (Ix)(k0 - 1) * N.s2, lam1, lam2, lm);
+      zlines(N, nbase + (Ix)k0 * N.s2, lam1, lam2, l0);
+      zlines(N, nbase + (Ix)(k0 + 1) * N.s2, lam1, lam2, l1);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) vp_prev[e] = cm.ln[e].vp;
+      for (int e = 0; e < 6; ++e) {
+        P1[e] = (l0[e].vp - T(2) * l0[e].u) - lm[e].vp;
+        Pn[e] = (l1[e].vp - T(2) * l1[e].u) - l0[e].vp;
+        Qn[e] = T(2) * l1[e].u - l1[e].vm;
+        X1[e] = l1[e].vp;
+      }
     }
     CellZ<T> c0;  // cell k0
     cellz_compute<T, SCH, GF>(N, nbase + (Ix)k0 * N.s2, full, lam1, lam2, c0);
@@ -626,10 +739,6 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
     for (int e = 0; e < 6; ++e) {
       wpe[e] = c0.wpe[e];
       wpx[e] = c0.wpx[e];
-      if (full) {
-        P1[e] = (c0.ln[e].vp - T(2) * c0.ln[e].u) - vp_prev[e];
-        vp_prev[e] = c0.ln[e].vp;
-      }
     }
     if (full && GF) {
 #pragma unroll
@@ -680,24 +789,20 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
     if (!full) continue;
     Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
     Stage<T, 9> Sc(O.face_cons[AX], cl0, sg_fc);
-    // zeta line stencil: cells m-1, m (in P1), m+1 (front), m+2 (looked ahead)
+    // zeta line stencil: cells m-1, m (in P1), m+1 (in Qn), m+2 (looked ahead: its scalars are computed
+    // once, here, and carried as Pn / Qn / X1 until the face two steps on has used them)
     {
-      T c2[3][8];
-      const Ix b2 = nbase + (Ix)(m + 2) * N.s2;
-      taylor_from_z(zplane(N, b2), zplane(N, b2 + N.s2), c2);
+      LineS<T> s2[6];
+      zlines(N, nbase + (Ix)(m + 2) * N.s2, lam1, lam2, s2);
 #pragma unroll
-      for (int col = 0; col < 3; ++col) {
-        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-#pragma unroll
-        for (int bb = 0; bb < 2; ++bb) {
-          const int e = bb * 3 + col;
-          LineS<T> s2 = line_from_taylor(c2, q1, q2, 2, bb, lam1, lam2);
-          T v = T(0.5) * (P1[e] + (T(2) * cf.ln[e].u - cf.ln[e].vm) + s2.vm);
-          if (bb == 1) Gh[0][col] += v;   // row xi: + line[b = eta]
-          else Gh[1][col] -= v;           // row eta: - line[b = xi]
-          P1[e] = (cf.ln[e].vp - T(2) * cf.ln[e].u) - vp_prev[e];
-          vp_prev[e] = cf.ln[e].vp;
-        }
+      for (int e = 0; e < 6; ++e) {
+        T v = T(0.5) * (P1[e] + Qn[e] + s2[e].vm);
+        if (e >= 3) Gh[0][e - 3] += v;  // row xi: + line[b = eta]
+        else Gh[1][e] -= v;             // row eta: - line[b = xi]
+        P1[e] = Pn[e];
+        Pn[e] = (s2[e].vp - T(2) * s2[e].u) - X1[e];
+        X1[e] = s2[e].vp;
+        Qn[e] = T(2) * s2[e].u - s2[e].vm;
       }
     }
     if (GF) {
@@ -709,15 +814,15 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
           Gf[r][cc] = T(0.5) * (Lpk[3 * r + cc] + cf.R[r][cc]);
           Lpk[3 * r + cc] = cf.L[r][cc];
         }
-      inv3(Gf, Ff);
-      if (SWAP) {  // back to the true labelling: columns eta <-> zeta of F, rows eta <-> zeta of G
+      T Jf = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
+      if (SWAP) {  // back to the true labelling: columns eta <-> zeta of F, rows eta <-> zeta of G (det changes sign)
+        Jf = -Jf;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           T t1 = Ff[q][1]; Ff[q][1] = Ff[q][2]; Ff[q][2] = t1;
           T t2 = Gf[1][q]; Gf[1][q] = Gf[2][q]; Gf[2][q] = t2;
         }
       }
-      T Jf = det3(Ff);
       if (out_ok) {
         put10(Sf.slot(rel), Ff, Jf);
         put10(Si.slot(rel), Gf, Jf);
