@@ -114,9 +114,8 @@ CG_D PF<T> pair_form(const ZPair<T>& a, const ZPair<T>& b) {
 // with cp.async, asynchronously, while the current step computes; all node reads of a step are LDS.
 // Layout [slot][row][coordinate][column]: lanes read consecutive columns (conflict-free).
 // ---------------------------------------------------------------------------
-constexpr int RING_COLS = 34;  // 32 lanes + the spare column 32 (+1 keeps rows 16-B aligned)
-constexpr int RING_SLOTS = 4;
-template <int ROWS> constexpr int ring_vals = RING_SLOTS * ROWS * 3 * RING_COLS;
+constexpr int RING_COLS = 34;  // 32 lanes + the spare columns 32, 33
+template <int ROWS, int SLOTS> constexpr int ring_vals = SLOTS * ROWS * 3 * RING_COLS;
 template <class T> CG_D void cp_async_val(T* sdst, const T* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst);
   if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -124,21 +123,24 @@ template <class T> CG_D void cp_async_val(T* sdst, const T* gsrc) {
 }
 CG_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 CG_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-template <class T, int ROWS>
+template <class T, int ROWS, int SLOTS>
 struct Ring {
   T* base;
-  CG_D T* row(int plane, int r, int q) const { return base + (((plane & (RING_SLOTS - 1)) * ROWS + r) * 3 + q) * RING_COLS; }
-  // copy ring rows [r0, r1) of one plane: g0 = index of (this lane's column, ring row 0, that plane),
-  // gx = the same for the spare column (used by lane 0 only)
-  template <class IX>
-  CG_D void fetch(const NodeP<T, IX>& N, int plane, IX g0, IX gx, int lane, int r0 = 0, int r1 = ROWS) const {
+  CG_D T* row(int plane, int r, int q) const {
+    const int slot = SLOTS == 4 ? (plane & 3) : plane % SLOTS;
+    return base + ((slot * ROWS + r) * 3 + q) * RING_COLS;
+  }
+  // copy all ring rows of one plane: g0 = index of (this lane's column, ring row 0, that plane); lanes
+  // 0 .. NX-1 also copy the spare columns 32 .. 32+NX-1 from gx (same row and plane)
+  template <int NX, class IX>
+  CG_D void fetch(const NodeP<T, IX>& N, int plane, IX g0, IX gx, int lane) const {
 #pragma unroll
-    for (int r = r0; r < r1; ++r)
+    for (int r = 0; r < ROWS; ++r)
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         T* dst = row(plane, r, q);
         cp_async_val(dst + lane, N.q[q] + g0 + (IX)r * N.s1);
-        if (lane == 0) cp_async_val(dst + 32, N.q[q] + gx + (IX)r * N.s1);
+        if (lane < NX) cp_async_val(dst + 32 + lane, N.q[q] + gx + (IX)r * N.s1);
       }
   }
   // raw form of the zeta-plane `plane`, rows r, r+1, columns lane, lane+1
@@ -419,7 +421,7 @@ struct March {
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
 // ===========================================================================
 // dynamic shared memory: per warp, staging buffers of the five AoS arrays this kernel writes
-template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4>;
+template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4, 4>;
 // ALL = true: FULL profile with cell + face outputs (the hot configuration) — every output switch is a
 // compile-time constant, so the loop body is one straight-line block the scheduler can interleave freely.
 template <class T, int SCH, bool ALL>
@@ -453,11 +455,11 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
   T* const sg_cf = sg, * const sg_ci = sg + stage_len<T, 10>, * const sg_ff = sg + 2 * stage_len<T, 10>,
          * const sg_fi = sg + 3 * stage_len<T, 10>, * const sg_fc = sg + 4 * stage_len<T, 10>;
   // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2)
-  const Ring<T, 4> R{sg + 4 * stage_len<T, 10> + stage_len<T, 9>};
+  const Ring<T, 4, 4> R{sg + 4 * stage_len<T, 10> + stage_len<T, 9>};
   auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
   const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32) + (Ix)j * N.s1 + N.s2;  // plane 0, row j-1
 #pragma unroll
-  for (int pp = 0; pp < 3; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
+  for (int pp = 0; pp < 3; ++pp) R.template fetch<1>(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
   cp_async_commit();
 
   T psi_bot[6];
@@ -478,7 +480,7 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
     cp_async_wait_all();
     __syncwarp();
     if (m + 1 < k1) {  // plane m+3 (first needed in the next step) into the slot plane m-1 has left
-      R.fetch(N, (int)(m + 3), rg0 + (Ix)(m + 3) * N.s2, rgx + (Ix)(m + 3) * N.s2, lane);
+      R.template fetch<1>(N, (int)(m + 3), rg0 + (Ix)(m + 3) * N.s2, rgx + (Ix)(m + 3) * N.s2, lane);
       cp_async_commit();
     }
     const int pm = (int)m;
@@ -616,11 +618,28 @@ struct CellZ {
   T L[3][3], R[3][3];
 };
 
-// the six zeta-line scalars of the cell whose low corner node is b (index = bb*3 + col; bb 0: b = xi, 1: b = eta)
+// node sources of the zeta kernel: global memory (prologue) or the warp's ring (marching loop).
+// zp(r, c): zeta-pair across planes p, p+1 of the column (row j + r, col i + c); zpl(d): raw zeta-plane p + d
 template <class T>
-CG_D void zlines(const NodeP<T>& N, Ix b, T lam1, T lam2, LineS<T> (&ln)[6]) {
+struct GlobalSrc {
+  const NodeP<T>& N;
+  Ix b;  // node (ic, j, p)
+  CG_D ZPair<T> zp(int r, int c) const { return zpair(N, b + (Ix)r * N.s1 + (Ix)c); }
+  CG_D PF<T> zpl(int d) const { return zplane(N, b + (Ix)d * N.s2); }
+};
+template <class T, class RING>
+struct RingSrc {
+  const RING& R;
+  int p, lane;
+  CG_D ZPair<T> zp(int r, int c) const { return R.zpair(p, r + 1, lane + c); }
+  CG_D PF<T> zpl(int d) const { return R.zplane(p + d, 1, lane); }
+};
+
+// the six zeta-line scalars of the cell at plane offset d of the source (index = bb*3 + col; bb 0: b = xi, 1: b = eta)
+template <class T, class SRC>
+CG_D void zlines(const SRC& S, int d, T lam1, T lam2, LineS<T> (&ln)[6]) {
   T c[3][8];
-  taylor_from_z(zplane(N, b), zplane(N, b + N.s2), c);
+  taylor_from_z(S.zpl(d), S.zpl(d + 1), c);
 #pragma unroll
   for (int col = 0; col < 3; ++col) {
     const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
@@ -629,22 +648,20 @@ CG_D void zlines(const NodeP<T>& N, Ix b, T lam1, T lam2, LineS<T> (&ln)[6]) {
   }
 }
 
-template <class T, int SCH, bool GF>
-CG_D void cellz_compute(const NodeP<T>& N, Ix b, bool full, T lam1, T lam2, CellZ<T>& o) {
-  // b = node (ic, j, p) of the cell's low corner.  All plane forms come from the zeta-pairs (sum, difference
-  // across planes p, p+1) of the node columns rows j-1 .. j+2 x cols i, i+1 and rows j, j+1 x col i+2.
-  const ZPair<T> p00 = zpair(N, b), p01 = zpair(N, b + 1), p10 = zpair(N, b + N.s1), p11 = zpair(N, b + N.s1 + 1);
+template <class T, int SCH, bool GF, class SRC>
+CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
+  // All plane forms of the cell at the source's plane p come from the zeta-pairs (sum, difference across
+  // planes p, p+1) of the node columns rows j-1 .. j+2 x cols i, i+1 and rows j, j+1 x col i+2.
+  const ZPair<T> p00 = S.zp(0, 0), p01 = S.zp(0, 1), p10 = S.zp(1, 0), p11 = S.zp(1, 1);
   const PF<T> E1 = pair_form(p00, p01), E2 = pair_form(p10, p11);  // eta-planes j, j+1 (u = xi, v = zeta)
   {
     // eta faces j-1/2 and j+1/2: eta-planes j-1 .. j+2 -> need (u,v) = (zeta, xi)
-    const PF<T> E0 = pair_form(zpair(N, b - N.s1), zpair(N, b - N.s1 + 1)),
-                E3 = pair_form(zpair(N, b + 2 * N.s1), zpair(N, b + 2 * N.s1 + 1));
+    const PF<T> E0 = pair_form(S.zp(-1, 0), S.zp(-1, 1)), E3 = pair_form(S.zp(2, 0), S.zp(2, 1));
     eface6_diff<T, SCH>(swap_uv(E0), swap_uv(E1), swap_uv(E2), swap_uv(E3), o.wpe, o.wme);
   }
   {
     // xi face i+1/2: xi-planes i, i+1, i+2, forms (eta,zeta) -> need (u,v) = (zeta, eta)
-    const PF<T> X0 = pair_form(p00, p10), X1 = pair_form(p01, p11),
-                X2 = pair_form(zpair(N, b + 2), zpair(N, b + N.s1 + 2));
+    const PF<T> X0 = pair_form(p00, p10), X1 = pair_form(p01, p11), X2 = pair_form(S.zp(0, 2), S.zp(1, 2));
     eface6<T, SCH>(swap_uv(X0), swap_uv(X1), swap_uv(X2), o.wpx, o.wmx);
   }
   if (!full) return;
@@ -676,7 +693,7 @@ struct Parked {
 // the strides of eta and zeta are exchanged, i.e. the kernel works in the left-handed labelling
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
-template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9>;
+template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4, 3>;
 #ifndef CG_GF
 #define CG_GF true
 #endif
@@ -686,15 +703,17 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   constexpr bool GF = CG_GF;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
-  __shared__ T park_mem[45 * NT];
+  __shared__ T park_mem[39 * NT];
   const int tid_ = threadIdx.y * 32 + threadIdx.x;
-  // line stencil state: P1 = (V+ - 2U)_m - V+_{m-1}, Pn = the same one cell ahead,
-  // Qn = (2U - V-)_{m+1}, X1 = V+_{m+1}
-  Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * NT + tid_}, P1{park_mem + 12 * NT + tid_},
-      Pn{park_mem + 18 * NT + tid_}, Qn{park_mem + 24 * NT + tid_}, X1{park_mem + 30 * NT + tid_};
-  Parked<T, 9> Lpk{park_mem + 36 * NT + tid_};
+  // line stencil pipeline: partial sums of the faces m, m+1, m+2 --
+  //   F0 = (V+ - 2U)_m - V+_{m-1} + (2U - V-)_{m+1},  F1 = (V+ - 2U)_{m+1} - V+_m,  F2 = -V+_{m+1}
+  Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * NT + tid_}, F0{park_mem + 12 * NT + tid_},
+      F1{park_mem + 18 * NT + tid_}, F2{park_mem + 24 * NT + tid_};
+  Parked<T, 9> Lpk{park_mem + 30 * NT + tid_};
   T* const stg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_stage_vals<T>;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
+  using RingT = Ring<T, 4, 3>;
+  const RingT R{stg + 2 * stage_len<T, 10> + stage_len<T, 9>};
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
   const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
@@ -718,23 +737,31 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   // cell strides of the row axis and the marching axis in the output arrays
   const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
 
+  // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2);
+  // planes k0+1 .. k0+3 are primed here, plane m+4 follows in step m
+  auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
+  const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32 + (lane & 1)) + (Ix)j * N.s1 + N.s2;
+#pragma unroll
+  for (int pp = 1; pp <= 3; ++pp)
+    R.template fetch<2>(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
+  cp_async_commit();
   // carried state: W+ of the cell below the face, line partial sums, L state (parked in shared memory)
   {
+    const GlobalSrc<T> S0{N, nbase + (Ix)k0 * N.s2};
     if (full) {
       LineS<T> lm[6], l0[6], l1[6];  // cells k0 - 1, k0, k0 + 1
-      zlines(N, nbase + (Ix)(k0 - 1) * N.s2, lam1, lam2, lm);
-      zlines(N, nbase + (Ix)k0 * N.s2, lam1, lam2, l0);
-      zlines(N, nbase + (Ix)(k0 + 1) * N.s2, lam1, lam2, l1);
+      zlines(S0, -1, lam1, lam2, lm);
+      zlines(S0, 0, lam1, lam2, l0);
+      zlines(S0, 1, lam1, lam2, l1);
 #pragma unroll
       for (int e = 0; e < 6; ++e) {
-        P1[e] = (l0[e].vp - T(2) * l0[e].u) - lm[e].vp;
-        Pn[e] = (l1[e].vp - T(2) * l1[e].u) - l0[e].vp;
-        Qn[e] = T(2) * l1[e].u - l1[e].vm;
-        X1[e] = l1[e].vp;
+        F0[e] = ((l0[e].vp - T(2) * l0[e].u) - lm[e].vp) + (T(2) * l1[e].u - l1[e].vm);
+        F1[e] = (l1[e].vp - T(2) * l1[e].u) - l0[e].vp;
+        F2[e] = -l1[e].vp;
       }
     }
     CellZ<T> c0;  // cell k0
-    cellz_compute<T, SCH, GF>(N, nbase + (Ix)k0 * N.s2, full, lam1, lam2, c0);
+    cellz_compute<T, SCH, GF>(S0, full, lam1, lam2, c0);
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
       wpe[e] = c0.wpe[e];
@@ -750,17 +777,18 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this step
     const int64_t cl = cl0 + rel;
-    if (lane == 0) bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers
+    // the TMA unit has finished reading last step's staging buffers; node planes m+1 .. m+3 have landed
+    if (lane == 0) bulk_wait_read();
+    cp_async_wait_all();
     __syncwarp();
-    if (m + 1 < k1) {  // next iteration: plane m+4 rows j, j+1; plane m+3 rows j-1, j+2
-      const Ix bp = nbase + (Ix)(m + 3) * N.s2;
-      pf3(N, bp + N.s2);
-      pf3(N, bp + N.s2 + N.s1);
-      pf3(N, bp - N.s1);
-      pf3(N, bp + 2 * N.s1);
-    }
+    const RingSrc<T, RingT> S{R, (int)(m + 1), lane};
     CellZ<T> cf;  // front cell m + 1
-    cellz_compute<T, SCH, GF>(N, nbase + (Ix)(m + 1) * N.s2, full, lam1, lam2, cf);
+    cellz_compute<T, SCH, GF>(S, full, lam1, lam2, cf);
+    if (m + 1 < k1) {  // plane m+4 into the slot of plane m+1, which every lane has finished reading
+      __syncwarp();
+      R.template fetch<2>(N, (int)(m + 4), rg0 + (Ix)(m + 4) * N.s2, rgx + (Ix)(m + 4) * N.s2, lane);
+      cp_async_commit();
+    }
     T Gh[3][3];  // rows 0 xi, 1 eta, 2 zeta
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
@@ -789,20 +817,19 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
     if (!full) continue;
     Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
     Stage<T, 9> Sc(O.face_cons[AX], cl0, sg_fc);
-    // zeta line stencil: cells m-1, m (in P1), m+1 (in Qn), m+2 (looked ahead: its scalars are computed
-    // once, here, and carried as Pn / Qn / X1 until the face two steps on has used them)
+    // zeta line stencil: the scalars of the looked-ahead cell m+2 are computed once, here, and distributed
+    // to the partial sums of the three faces they belong to
     {
       LineS<T> s2[6];
-      zlines(N, nbase + (Ix)(m + 2) * N.s2, lam1, lam2, s2);
+      zlines(S, 1, lam1, lam2, s2);
 #pragma unroll
       for (int e = 0; e < 6; ++e) {
-        T v = T(0.5) * (P1[e] + Qn[e] + s2[e].vm);
+        T v = T(0.5) * (F0[e] + s2[e].vm);
         if (e >= 3) Gh[0][e - 3] += v;  // row xi: + line[b = eta]
         else Gh[1][e] -= v;             // row eta: - line[b = xi]
-        P1[e] = Pn[e];
-        Pn[e] = (s2[e].vp - T(2) * s2[e].u) - X1[e];
-        X1[e] = s2[e].vp;
-        Qn[e] = T(2) * s2[e].u - s2[e].vm;
+        F0[e] = F1[e] + (T(2) * s2[e].u - s2[e].vm);
+        F1[e] = F2[e] + (s2[e].vp - T(2) * s2[e].u);
+        F2[e] = -s2[e].vp;
       }
     }
     if (GF) {
