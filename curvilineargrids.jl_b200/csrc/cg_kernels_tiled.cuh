@@ -190,6 +190,21 @@ CG_D void taylor_from_z(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
     c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
   }
 }
+// the same with the lower plane given as 2 x raw
+template <class T>
+CG_D void taylor_from_z2(const PF<T>& lo2, const PF<T>& hi, T (&c)[3][8]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    c[q][0] = T(0.0625) * lo2.q[q].c0 + T(0.125) * hi.q[q].c0;
+    c[q][1] = T(0.125) * lo2.q[q].cu + T(0.25) * hi.q[q].cu;
+    c[q][2] = T(0.125) * lo2.q[q].cv + T(0.25) * hi.q[q].cv;
+    c[q][3] = T(0.25) * lo2.q[q].cuv + T(0.5) * hi.q[q].cuv;
+    c[q][4] = T(0.25) * hi.q[q].c0 - T(0.125) * lo2.q[q].c0;
+    c[q][5] = T(0.5) * hi.q[q].cu - T(0.25) * lo2.q[q].cu;
+    c[q][6] = T(0.5) * hi.q[q].cv - T(0.25) * lo2.q[q].cv;
+    c[q][7] = hi.q[q].cuv - T(0.5) * lo2.q[q].cuv;
+  }
+}
 // the same from the two RAW eta-planes (u = xi, v = zeta) of the cell
 template <class T>
 CG_D void taylor_from_e(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
@@ -462,6 +477,8 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
   for (int pp = 0; pp < 3; ++pp) R.template fetch<1>(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
   cp_async_commit();
 
+  const T dl0 = clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), dl1 = clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]);
+
   T psi_bot[6];
   if (do_cons) {
     T wp[6], wm[6];
@@ -496,20 +513,28 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
       for (int q = 0; q < 3; ++q)
 #pragma unroll
         for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
-      inv3(F, G);
+      const T detF = inv3(F, G);
       if (do_cell) {
-        T dl[3] = {clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]),
-                   clamp_delta<T>(D.w0[2] + m, D.nhalo, D.gn[2])};
-        T Ff[3][3];
+        // cell.forward is evaluated at the clamped point (discrete_grid.jl:113-142): only halo cells differ
+        // from the centre value, so the correction is skipped by warps that hold interior cells only
+        T Ff[3][3], J = detF;
 #pragma unroll
         for (int q = 0; q < 3; ++q)
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const int e = (d + 1) % 3, g = (d + 2) % 3;
-            Ff[q][d] = c[q][1 << d] + c[q][(1 << d) | (1 << e)] * dl[e] + c[q][(1 << d) | (1 << g)] * dl[g] +
-                       c[q][7] * dl[e] * dl[g];
-          }
-        T J = det3(Ff);
+          for (int d = 0; d < 3; ++d) Ff[q][d] = F[q][d];
+        const T dl2 = clamp_delta<T>(D.w0[2] + m, D.nhalo, D.gn[2]);
+        if (__any_sync(FULLMASK, dl0 != T(0)) || dl1 != T(0) || dl2 != T(0)) {
+          const T dl[3] = {dl0, dl1, dl2};
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const int e = (d + 1) % 3, g = (d + 2) % 3;
+              Ff[q][d] = c[q][1 << d] + c[q][(1 << d) | (1 << e)] * dl[e] + c[q][(1 << d) | (1 << g)] * dl[g] +
+                         c[q][7] * dl[e] * dl[g];
+            }
+          J = det3(Ff);
+        }
         if (st_cf && out_ok) put10(Scf.slot(rel), Ff, J);
         if (st_ci && out_ok) put10(Sci.slot(rel), G, J);
         if (!ALL && O.cjac && out_ok) O.cjac[cl] = J;
@@ -616,6 +641,7 @@ struct CellZ {
   T wpx[6];  // W+_zeta [E^xi(i+1/2)]
   T wmx[6];
   T L[3][3], R[3][3];
+  PF<T> ztop2;  // 2 x the raw form of the cell's upper zeta-plane (= lower plane of the looked-ahead cell)
 };
 
 // node sources of the zeta kernel: global memory (prologue) or the warp's ring (marching loop).
@@ -648,6 +674,19 @@ CG_D void zlines(const SRC& S, int d, T lam1, T lam2, LineS<T> (&ln)[6]) {
   }
 }
 
+// ... of the cell above the source's cell, whose lower plane is given as 2 x raw
+template <class T, class SRC>
+CG_D void zlines_above(const SRC& S, const PF<T>& lo2, T lam1, T lam2, LineS<T> (&ln)[6]) {
+  T c[3][8];
+  taylor_from_z2(lo2, S.zpl(2), c);
+#pragma unroll
+  for (int col = 0; col < 3; ++col) {
+    const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+    ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
+    ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
+  }
+}
+
 template <class T, int SCH, bool GF, class SRC>
 CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
   // All plane forms of the cell at the source's plane p come from the zeta-pairs (sum, difference across
@@ -665,6 +704,11 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
     eface6<T, SCH>(swap_uv(X0), swap_uv(X1), swap_uv(X2), o.wpx, o.wmx);
   }
   if (!full) return;
+  // upper zeta-plane of the cell from the same pair forms (the plane's nodes are the `hi` halves of the pairs)
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    o.ztop2.q[q] = {(E1.q[q].c0 + E2.q[q].c0) + (E1.q[q].cv + E2.q[q].cv), (E1.q[q].cu + E2.q[q].cu) + (E1.q[q].cuv + E2.q[q].cuv),
+                    (E2.q[q].c0 - E1.q[q].c0) + (E2.q[q].cv - E1.q[q].cv), (E2.q[q].cu - E1.q[q].cu) + (E2.q[q].cuv - E1.q[q].cuv)};
   if (GF) {
     T c[3][8];
     taylor_from_e(E1, E2, c);
@@ -821,7 +865,7 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
     // to the partial sums of the three faces they belong to
     {
       LineS<T> s2[6];
-      zlines(S, 1, lam1, lam2, s2);
+      zlines_above(S, cf.ztop2, lam1, lam2, s2);
 #pragma unroll
       for (int e = 0; e < 6; ++e) {
         T v = T(0.5) * (F0[e] + s2[e].vm);
