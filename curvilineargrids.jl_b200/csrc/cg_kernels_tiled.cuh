@@ -725,35 +725,23 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
   }
 }
 
-// per-thread state carried from plane to plane, parked in shared memory (slot-major: conflict-free) so it
-// does not occupy registers across the whole loop body
-template <class T, int NSLOT>
-struct Parked {
-  T* base;
-  __device__ __forceinline__ T& operator[](int slot) const { return base[slot * NT]; }
-};
-
 // SWAP = false: zeta faces, marching along k.  SWAP = true: ETA faces with the same code, marching along j:
 // the strides of eta and zeta are exchanged, i.e. the kernel works in the left-handed labelling
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
 template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4, 3>;
-#ifndef CG_GF
-#define CG_GF true
-#endif
 template <class T, int SCH, bool SWAP, bool ALL>
 __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
-  constexpr bool GF = CG_GF;
+  constexpr bool GF = true;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
-  __shared__ T park_mem[39 * NT];
-  const int tid_ = threadIdx.y * 32 + threadIdx.x;
-  // line stencil pipeline: partial sums of the faces m, m+1, m+2 --
-  //   F0 = (V+ - 2U)_m - V+_{m-1} + (2U - V-)_{m+1},  F1 = (V+ - 2U)_{m+1} - V+_m,  F2 = -V+_{m+1}
-  Parked<T, 6> wpe{park_mem + tid_}, wpx{park_mem + 6 * NT + tid_}, F0{park_mem + 12 * NT + tid_},
-      F1{park_mem + 18 * NT + tid_}, F2{park_mem + 24 * NT + tid_};
-  Parked<T, 9> Lpk{park_mem + 30 * NT + tid_};
+  // state carried from step to step (registers):
+  //   wpe, wpx : W+ of the cell below the face (eta-difference / xi-face polynomials)
+  //   F0..F2   : line stencil pipeline, partial sums of the faces m, m+1, m+2 --
+  //              F0 = (V+ - 2U)_m - V+_{m-1} + (2U - V-)_{m+1},  F1 = (V+ - 2U)_{m+1} - V+_m,  F2 = -V+_{m+1}
+  //   Lpk      : L state of the reconstructed inverse Jacobian of the cell below the face
+  T wpe[6], wpx[6], F0[6], F1[6], F2[6], Lpk[9];
   T* const stg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_stage_vals<T>;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
   using RingT = Ring<T, 4, 3>;
@@ -789,7 +777,7 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   for (int pp = 1; pp <= 3; ++pp)
     R.template fetch<2>(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
   cp_async_commit();
-  // carried state: W+ of the cell below the face, line partial sums, L state (parked in shared memory)
+  // carried state of the first step
   {
     const GlobalSrc<T> S0{N, nbase + (Ix)k0 * N.s2};
     if (full) {
