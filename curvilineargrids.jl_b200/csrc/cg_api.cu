@@ -275,6 +275,9 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
   else if (N == 2)
     cg::k_mapped_metrics2d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
                                                                       g->scheme, what);
+  else if ((what & 3) == 3 && O.cell_fwd && O.cell_inv && O.face_cons[0] && O.face_fwd[0] && O.face_inv[0] && !O.cjac &&
+           !O.cactive[0])
+    cg::launch_mapped_metrics3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
   else
     cg::k_mapped_metrics3d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
                                                                       g->scheme, what);

@@ -190,21 +190,6 @@ CG_D void taylor_from_z(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
     c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
   }
 }
-// the same with the lower plane given as 2 x raw
-template <class T>
-CG_D void taylor_from_z2(const PF<T>& lo2, const PF<T>& hi, T (&c)[3][8]) {
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    c[q][0] = T(0.0625) * lo2.q[q].c0 + T(0.125) * hi.q[q].c0;
-    c[q][1] = T(0.125) * lo2.q[q].cu + T(0.25) * hi.q[q].cu;
-    c[q][2] = T(0.125) * lo2.q[q].cv + T(0.25) * hi.q[q].cv;
-    c[q][3] = T(0.25) * lo2.q[q].cuv + T(0.5) * hi.q[q].cuv;
-    c[q][4] = T(0.25) * hi.q[q].c0 - T(0.125) * lo2.q[q].c0;
-    c[q][5] = T(0.5) * hi.q[q].cu - T(0.25) * lo2.q[q].cu;
-    c[q][6] = T(0.5) * hi.q[q].cv - T(0.25) * lo2.q[q].cv;
-    c[q][7] = hi.q[q].cuv - T(0.5) * lo2.q[q].cuv;
-  }
-}
 // the same from the two RAW eta-planes (u = xi, v = zeta) of the cell
 template <class T>
 CG_D void taylor_from_e(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
@@ -571,11 +556,18 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
       // ---- eta-direction edge scalars on both eta faces of the cell ----
       T dpsi_eta[6];
       {
-        // eta-planes j-1 .. j+2 (u = xi, v = zeta) from the zeta-pairs of the node columns i, i+1
+        // eta-planes j-1 .. j+2 (u = xi, v = zeta): the outer two from the zeta-pairs of the node columns
+        // i, i+1; the cell's own two eta-faces from the carried zeta-planes (same 8 nodes, no reloads)
         PF<T> e0 = pair_form(R.zpair(pm, 0, lane), R.zpair(pm, 0, lane + 1)),
-              e1 = pair_form(R.zpair(pm, 1, lane), R.zpair(pm, 1, lane + 1)),
-              e2 = pair_form(R.zpair(pm, 2, lane), R.zpair(pm, 2, lane + 1)),
-              e3 = pair_form(R.zpair(pm, 3, lane), R.zpair(pm, 3, lane + 1));
+              e3 = pair_form(R.zpair(pm, 3, lane), R.zpair(pm, 3, lane + 1)), e1, e2;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const Form4<T>&lo = z0.q[q], &hi = z1.q[q];
+          const T s0 = lo.c0 + hi.c0, su = lo.cu + hi.cu, sv = lo.cv + hi.cv, suv = lo.cuv + hi.cuv;
+          const T d0 = hi.c0 - lo.c0, du = hi.cu - lo.cu, dv = hi.cv - lo.cv, duv = hi.cuv - lo.cuv;
+          e1.q[q] = {T(0.5) * (s0 - sv), T(0.5) * (su - suv), T(0.5) * (d0 - dv), T(0.5) * (du - duv)};
+          e2.q[q] = {T(0.5) * (s0 + sv), T(0.5) * (su + suv), T(0.5) * (d0 + dv), T(0.5) * (du + duv)};
+        }
         T wp[6], wm[6];
         eface6_diff<T, SCH>(e0, e1, e2, e3, wp, wm);  // (face j + 1/2) - (face j - 1/2)
 #pragma unroll
@@ -641,7 +633,7 @@ struct CellZ {
   T wpx[6];  // W+_zeta [E^xi(i+1/2)]
   T wmx[6];
   T L[3][3], R[3][3];
-  PF<T> ztop2;  // 2 x the raw form of the cell's upper zeta-plane (= lower plane of the looked-ahead cell)
+  LineS<T> ln[6];  // zeta-line scalars of the cell (index = bb*3 + col; bb 0: b = xi, 1: b = eta)
 };
 
 // node sources of the zeta kernel: global memory (prologue) or the warp's ring (marching loop).
@@ -674,19 +666,6 @@ CG_D void zlines(const SRC& S, int d, T lam1, T lam2, LineS<T> (&ln)[6]) {
   }
 }
 
-// ... of the cell above the source's cell, whose lower plane is given as 2 x raw
-template <class T, class SRC>
-CG_D void zlines_above(const SRC& S, const PF<T>& lo2, T lam1, T lam2, LineS<T> (&ln)[6]) {
-  T c[3][8];
-  taylor_from_z2(lo2, S.zpl(2), c);
-#pragma unroll
-  for (int col = 0; col < 3; ++col) {
-    const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-    ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
-    ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
-  }
-}
-
 template <class T, int SCH, bool GF, class SRC>
 CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
   // All plane forms of the cell at the source's plane p come from the zeta-pairs (sum, difference across
@@ -704,14 +683,15 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
     eface6<T, SCH>(swap_uv(X0), swap_uv(X1), swap_uv(X2), o.wpx, o.wmx);
   }
   if (!full) return;
-  // upper zeta-plane of the cell from the same pair forms (the plane's nodes are the `hi` halves of the pairs)
+  T c[3][8];
+  taylor_from_e(E1, E2, c);  // one Taylor expansion of the cell serves the line scalars and the L / R states
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
-    o.ztop2.q[q] = {(E1.q[q].c0 + E2.q[q].c0) + (E1.q[q].cv + E2.q[q].cv), (E1.q[q].cu + E2.q[q].cu) + (E1.q[q].cuv + E2.q[q].cuv),
-                    (E2.q[q].c0 - E1.q[q].c0) + (E2.q[q].cv - E1.q[q].cv), (E2.q[q].cu - E1.q[q].cu) + (E2.q[q].cuv - E1.q[q].cuv)};
+  for (int col = 0; col < 3; ++col) {
+    const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+    o.ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
+    o.ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
+  }
   if (GF) {
-    T c[3][8];
-    taylor_from_e(E1, E2, c);
     T F[3][3], G[3][3], Fa[3], Fb[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -738,10 +718,12 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   // state carried from step to step (registers):
   //   wpe, wpx : W+ of the cell below the face (eta-difference / xi-face polynomials)
-  //   F0..F2   : line stencil pipeline, partial sums of the faces m, m+1, m+2 --
-  //              F0 = (V+ - 2U)_m - V+_{m-1} + (2U - V-)_{m+1},  F1 = (V+ - 2U)_{m+1} - V+_m,  F2 = -V+_{m+1}
+  //   F0..F2   : line stencil pipeline.  The front cell m+1 contributes V- to the face m-1, (2U - V-) to m,
+  //              (V+ - 2U) to m+1 and -V+ to m+2, so the conserved metrics of the face m-1 are completed (and
+  //              stored) in step m; F0, F1, F2 are the partial sums of the faces m-1, m, m+1 at step entry
+  //   GhP      : conserved metrics of the face m-1 without the V- term (kernel labelling)
   //   Lpk      : L state of the reconstructed inverse Jacobian of the cell below the face
-  T wpe[6], wpx[6], F0[6], F1[6], F2[6], Lpk[9];
+  T wpe[6], wpx[6], F0[6], F1[6], F2[6], GhP[3][3], Lpk[9];
   T* const stg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_stage_vals<T>;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
   using RingT = Ring<T, 4, 3>;
@@ -781,16 +763,10 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   {
     const GlobalSrc<T> S0{N, nbase + (Ix)k0 * N.s2};
     if (full) {
-      LineS<T> lm[6], l0[6], l1[6];  // cells k0 - 1, k0, k0 + 1
+      LineS<T> lm[6];  // cell k0 - 1
       zlines(S0, -1, lam1, lam2, lm);
-      zlines(S0, 0, lam1, lam2, l0);
-      zlines(S0, 1, lam1, lam2, l1);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) {
-        F0[e] = ((l0[e].vp - T(2) * l0[e].u) - lm[e].vp) + (T(2) * l1[e].u - l1[e].vm);
-        F1[e] = (l1[e].vp - T(2) * l1[e].u) - l0[e].vp;
-        F2[e] = -l1[e].vp;
-      }
+      for (int e = 0; e < 6; ++e) F2[e] = -lm[e].vp;
     }
     CellZ<T> c0;  // cell k0
     cellz_compute<T, SCH, GF>(S0, full, lam1, lam2, c0);
@@ -799,13 +775,46 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
       wpe[e] = c0.wpe[e];
       wpx[e] = c0.wpx[e];
     }
-    if (full && GF) {
+    if (full) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {  // the face k0-1 belongs to the previous chunk: F0 is not needed
+        F0[e] = T(0);
+        F1[e] = F2[e] + (c0.ln[e].vp - T(2) * c0.ln[e].u);
+        F2[e] = -c0.ln[e].vp;
+      }
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) Lpk[3 * r + cc] = c0.L[r][cc];
+        for (int cc = 0; cc < 3; ++cc) {
+          GhP[r][cc] = T(0);
+          if (GF) Lpk[3 * r + cc] = c0.L[r][cc];
+        }
     }
   }
+  // completes the conserved metrics of the face below (GhP + V- term), stages and hands them to the TMA unit
+  auto finish_cons = [&](const T (&vm)[6], int64_t cl0_prev) {
+    T Go[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Go[r][cc] = GhP[r][cc];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const T v = T(0.5) * (F0[e] + vm[e]);
+      if (e >= 3) Go[0][e - 3] += v;  // row xi: + line[b = eta]
+      else Go[1][e] -= v;             // row eta: - line[b = xi]
+    }
+    if (SWAP) {
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        T r0 = -Go[0][col], r1 = -Go[2][col], r2 = -Go[1][col];
+        Go[0][col] = r0; Go[1][col] = r1; Go[2][col] = r2;
+      }
+    }
+    Stage<T, 9> Sc(O.face_cons[AX], cl0_prev, sg_fc);
+    if (out_ok) put9(Sc.slot(rel), Go);
+    return Sc;
+  };
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this step
     const int64_t cl = cl0 + rel;
@@ -848,22 +857,21 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
     }
     if (!full) continue;
     Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
-    Stage<T, 9> Sc(O.face_cons[AX], cl0, sg_fc);
-    // zeta line stencil: the scalars of the looked-ahead cell m+2 are computed once, here, and distributed
-    // to the partial sums of the three faces they belong to
-    {
-      LineS<T> s2[6];
-      zlines_above(S, cf.ztop2, lam1, lam2, s2);
+    // zeta line stencil: the front cell's V- completes the face m-1 (stored now, one step late)
+    T vm[6];
 #pragma unroll
-      for (int e = 0; e < 6; ++e) {
-        T v = T(0.5) * (F0[e] + s2[e].vm);
-        if (e >= 3) Gh[0][e - 3] += v;  // row xi: + line[b = eta]
-        else Gh[1][e] -= v;             // row eta: - line[b = xi]
-        F0[e] = F1[e] + (T(2) * s2[e].u - s2[e].vm);
-        F1[e] = F2[e] + (s2[e].vp - T(2) * s2[e].u);
-        F2[e] = -s2[e].vp;
-      }
+    for (int e = 0; e < 6; ++e) vm[e] = cf.ln[e].vm;
+    const Stage<T, 9> Sc = finish_cons(vm, cl0 - cs2);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      F0[e] = F1[e] + (T(2) * cf.ln[e].u - cf.ln[e].vm);
+      F1[e] = F2[e] + (cf.ln[e].vp - T(2) * cf.ln[e].u);
+      F2[e] = -cf.ln[e].vp;
     }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) GhP[r][cc] = Gh[r][cc];
     if (GF) {
       T Gf[3][3], Ff[3][3];
 #pragma unroll
@@ -887,14 +895,6 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
         put10(Si.slot(rel), Gf, Jf);
       }
     }
-    if (SWAP) {
-#pragma unroll
-      for (int col = 0; col < 3; ++col) {
-        T r0 = -Gh[0][col], r1 = -Gh[2][col], r2 = -Gh[1][col];
-        Gh[0][col] = r0; Gh[1][col] = r1; Gh[2][col] = r2;
-      }
-    }
-    if (out_ok) put9(Sc.slot(rel), Gh);
     // ---- one flush point: staged arrays -> TMA ----
     fence_async_smem();
     __syncwarp();
@@ -902,6 +902,22 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
       Sf.issue(nvalid, lane);
       Si.issue(nvalid, lane);
     }
+    if (m > k0) Sc.issue(nvalid, lane);
+    if (lane == 0) bulk_commit();
+  }
+  if (full) {
+    // the last face of the chunk needs V- of the cell k1 + 1
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
+    const GlobalSrc<T> S1{N, nbase + (Ix)(k1 + 1) * N.s2};
+    LineS<T> l2[6];
+    zlines(S1, 0, lam1, lam2, l2);
+    T vm[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) vm[e] = l2[e].vm;
+    const Stage<T, 9> Sc = finish_cons(vm, i0 + j * cs1 + (k1 - 1) * cs2);
+    fence_async_smem();
+    __syncwarp();
     Sc.issue(nvalid, lane);
     if (lane == 0) bulk_commit();
   }

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "cg_kernels_ref.cuh"
+#include "cg_kernels_tiled.cuh"
 
 namespace cg {
 
@@ -326,6 +327,135 @@ __global__ void __launch_bounds__(128) k_mapped_metrics3d(Dims D, MTerms TM, MPa
       store_metric3(O.face_inv[f] + 10 * lin, Gf, J);
     }
   }
+}
+
+// ---------------------------------------------------------------------------
+// FULL-profile fast path of the 3-D kernel: same arithmetic, but a warp owns 32 consecutive cells of a
+// j-row and walks along k, and every AoS output goes through the warp's staging buffers and the TMA
+// unit (cg_kernels_tiled.cuh, "Output staging") instead of 80-B-strided stores.
+// ---------------------------------------------------------------------------
+template <class T> constexpr int mapped_stage_vals = 8 * stage_len<T, 10> + 3 * stage_len<T, 9>;
+template <class T>
+__global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerms TM, MPairs PR, const T* __restrict__ tab,
+                                                                  const T* __restrict__ ftab, int64_t L, MetricOut<T> O,
+                                                                  int scheme, int kchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  const T lam1 = lam1_of<T>(scheme), lam2 = lam2_of<T>(scheme);
+  const int64_t L1 = L + 1;
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= nw1) return;  // whole warp
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int nvalid = (int)(nw0 - i0 < 32 ? nw0 - i0 : 32);
+  const bool out_ok = lane < nvalid;
+  const int64_t i = out_ok ? i0 + lane : nw0 - 1;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * mapped_stage_vals<T>;
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t ix[3] = {i, j, m};
+    const int64_t cl0 = i0 + nw0 * (j + nw1 * m);
+    if (lane == 0) bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers
+    __syncwarp();
+    Stage<T, 10> Scf(O.cell_fwd, cl0, sg), Sci(O.cell_inv, cl0, sg + stage_len<T, 10>);
+    T F[3][3], Fp[3][3], Fpp[3][3], G[3][3], Lc[3][3], Rc[3][3];
+    {
+      mapped_jac<T, 3>(TM, ftab, L1, ix, 0, F, Fp, Fpp);
+      T J = inv3(F, G);
+      if (out_ok) {
+        put10(Scf.slot(lane), F, J);
+        put10(Sci.slot(lane), G, J);
+      }
+    }
+    // ---- conserved metrics: sums over term pairs of triple products of 1-D table values ----
+    T Gh[3][3][3];  // [face][row][col]
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Gh[f][rr][cc] = T(0);
+    for (int p = 0; p < PR.n; ++p) {
+      T tv[3][OP_COUNT];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = tab[((int64_t)(p * 3 + d) * OP_COUNT + o) * L + ix[d]];
+      const T C = T(TM.t[PR.p[p].m1].coef * TM.t[PR.p[p].m2].coef);
+      const int col = PR.p[p].col;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const int s = (f + 1) % 3, t = (f + 2) % 3;
+        T act = C * tv[f][OP_E0] * (tv[s][OP_V1] * tv[t][OP_D0] - tv[s][OP_D0] * tv[t][OP_V1]);
+        T rs = C * tv[s][OP_V0] * (tv[f][OP_FD0] * tv[t][OP_V1] - tv[f][OP_E1] * tv[t][OP_D0]);
+        T rt = C * tv[t][OP_V0] * (tv[f][OP_E1] * tv[s][OP_D0] - tv[f][OP_FD0] * tv[s][OP_V1]);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+          if (cc == col) {
+            Gh[f][f][cc] += act;
+            Gh[f][s][cc] += rs;
+            Gh[f][t][cc] += rt;
+          }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      T* const sf = sg + (2 + 2 * f) * stage_len<T, 10>;
+      Stage<T, 10> Sff(O.face_fwd[f], cl0, sf), Sfi(O.face_inv[f], cl0, sf + stage_len<T, 10>);
+      Stage<T, 9> Sfc(O.face_cons[f], cl0, sg + 8 * stage_len<T, 10> + f * stage_len<T, 9>);
+      if (out_ok) put9(Sfc.slot(lane), Gh[f]);
+      // ---- reconstructed inverse Jacobian ----
+      T Gn[3][3], Ln[3][3], Rn[3][3], Gf[3][3], Ff[3][3];
+      mapped_jac<T, 3>(TM, ftab, L1, ix, f, F, Fp, Fpp);
+      mapped_states3(F, Fp, Fpp, lam1, lam2, G, Lc, Rc);
+      int64_t in[3] = {ix[0], ix[1], ix[2]};
+      in[f] += 1;
+      mapped_jac<T, 3>(TM, ftab, L1, in, f, F, Fp, Fpp);
+      mapped_states3(F, Fp, Fpp, lam1, lam2, Gn, Ln, Rn);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (Lc[a][b] + Rn[a][b]);
+      T J = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
+      if (out_ok) {
+        put10(Sff.slot(lane), Ff, J);
+        put10(Sfi.slot(lane), Gf, J);
+      }
+    }
+    // ---- one flush point: staged arrays -> TMA ----
+    fence_async_smem();
+    __syncwarp();
+    Scf.issue(nvalid, lane);
+    Sci.issue(nvalid, lane);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      T* const sf = sg + (2 + 2 * f) * stage_len<T, 10>;
+      Stage<T, 10>(O.face_fwd[f], cl0, sf).issue(nvalid, lane);
+      Stage<T, 10>(O.face_inv[f], cl0, sf + stage_len<T, 10>).issue(nvalid, lane);
+      Stage<T, 9>(O.face_cons[f], cl0, sg + 8 * stage_len<T, 10> + f * stage_len<T, 9>).issue(nvalid, lane);
+    }
+    if (lane == 0) bulk_commit();
+  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
+}
+
+template <class T>
+inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
+                                           int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
+  const unsigned gx = (unsigned)((D.nw[0] + 31) / 32), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+  const int64_t tiles = (int64_t)gx * gy, want = 148LL * 16;
+  int kchunk = (int)D.nw[2];
+  if (tiles < want) {
+    const int64_t nch = (want + tiles - 1) / tiles;
+    kchunk = (int)((D.nw[2] + nch - 1) / nch);
+    if (kchunk < 4) kchunk = 4;
+    if (kchunk > D.nw[2]) kchunk = (int)D.nw[2];
+  }
+  const int smem = WY * mapped_stage_vals<T> * (int)sizeof(T);
+  cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, WY), smem, st>>>(
+      D, TM, PR, tab, ftab, L, O, scheme, kchunk);
 }
 
 // =============================== 2-D ========================================
