@@ -28,6 +28,9 @@ namespace cg {
 #ifndef CG_ZETA_MINB
 #define CG_ZETA_MINB 2
 #endif
+#ifndef CG_COMPACT_MINB
+#define CG_COMPACT_MINB 3
+#endif
 #ifndef CG_WY
 #define CG_WY 4
 #endif
@@ -36,6 +39,12 @@ constexpr int NT = 32 * WY;     // threads per block
 constexpr int WARP_OUT = 29;  // output cells per warp along xi (kernels that need lanes -1, +1, +2)
 constexpr int ZETA_OUT = 31;  // the zeta / eta(SWAP) kernel only needs lane -1
 constexpr unsigned FULLMASK = 0xffffffffu;
+// MODE: the two hot configurations are compiled with every output switch as a compile-time constant, so the
+// loop body is straight-line code the scheduler can interleave freely and unused work disappears:
+//   MODE_FULL    : FULL profile, cell + face outputs (all nine AoS arrays)
+//   MODE_COMPACT : COMPACT profile, cell + face outputs (J of the cell, active conserved row per axis)
+//   MODE_GENERIC : anything else (cell-only / face-only refreshes), switches read at run time
+enum { MODE_GENERIC = 0, MODE_FULL = 1, MODE_COMPACT = 2 };
 
 template <class T>
 struct PF {
@@ -421,11 +430,11 @@ struct March {
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
 // ===========================================================================
 // dynamic shared memory: per warp, staging buffers of the five AoS arrays this kernel writes
-template <class T> constexpr int xi_stage_vals = 4 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4, 4>;
-// ALL = true: FULL profile with cell + face outputs (the hot configuration) — every output switch is a
-// compile-time constant, so the loop body is one straight-line block the scheduler can interleave freely.
-template <class T, int SCH, bool ALL>
-__global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
+// per-warp shared memory: [node ring | staging buffers]; the COMPACT configuration stages nothing
+template <class T, int MODE> constexpr int xi_warp_vals =
+    ring_vals<4, 4> + (MODE == MODE_COMPACT ? 0 : 4 * stage_len<T, 10> + stage_len<T, 9>);
+template <class T, int SCH, int MODE>
+__global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
                                                          MetricOut<T> O, int what, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
@@ -444,18 +453,21 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = ALL || O.face_cons[0] != nullptr;
-  const bool do_cell = ALL || (what & 1);
-  const bool do_cons = ALL || (what & 2);
-  const bool do_gf = ALL || ((what & 2) && full);
-  const bool st_cf = ALL || (do_cell && O.cell_fwd), st_ci = ALL || (do_cell && O.cell_inv);
+  constexpr bool ALL = MODE == MODE_FULL, CMP = MODE == MODE_COMPACT;
+  const bool full = ALL || (!CMP && O.face_cons[0] != nullptr);
+  const bool do_cell = ALL || CMP || (what & 1);
+  const bool do_cons = ALL || CMP || (what & 2);
+  const bool do_gf = ALL || (!CMP && (what & 2) && full);
+  const bool st_cf = ALL || (!CMP && do_cell && O.cell_fwd), st_ci = ALL || (!CMP && do_cell && O.cell_inv);
+  const bool st_cj = CMP || (!ALL && O.cjac), st_ca = CMP || (!ALL && O.cactive[0]);
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
-  T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_stage_vals<T>;
+  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_warp_vals<T, MODE>;
+  T* const sg = wsm + ring_vals<4, 4>;
   T* const sg_cf = sg, * const sg_ci = sg + stage_len<T, 10>, * const sg_ff = sg + 2 * stage_len<T, 10>,
          * const sg_fi = sg + 3 * stage_len<T, 10>, * const sg_fc = sg + 4 * stage_len<T, 10>;
   // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2)
-  const Ring<T, 4, 4> R{sg + 4 * stage_len<T, 10> + stage_len<T, 9>};
+  const Ring<T, 4, 4> R{wsm};
   auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
   const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32) + (Ix)j * N.s1 + N.s2;  // plane 0, row j-1
 #pragma unroll
@@ -522,7 +534,7 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
         }
         if (st_cf && out_ok) put10(Scf.slot(rel), Ff, J);
         if (st_ci && out_ok) put10(Sci.slot(rel), G, J);
-        if (!ALL && O.cjac && out_ok) O.cjac[cl] = J;
+        if (st_cj && out_ok) O.cjac[cl] = J;
       }
       if (do_gf) {
         // ---- reconstructed inverse Jacobian on the xi face ----
@@ -582,7 +594,7 @@ __global__ void __launch_bounds__(NT, CG_MINB) k_face_xi(Dims D, const T* ex, co
       }
 #pragma unroll
       for (int e = 0; e < 6; ++e) psi_bot[e] = psi_top[e];
-      if (!ALL && O.cactive[0] && out_ok) {
+      if (st_ca && out_ok) {
         T* o = O.cactive[0] + 3 * cl;
         o[0] = Gh[0][0]; o[1] = Gh[0][1]; o[2] = Gh[0][2];
       }
@@ -709,9 +721,10 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
 // the strides of eta and zeta are exchanged, i.e. the kernel works in the left-handed labelling
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
-template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9> + ring_vals<4, 3>;
-template <class T, int SCH, bool SWAP, bool ALL>
-__global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
+template <class T, int MODE> constexpr int zeta_warp_vals =
+    ring_vals<4, 3> + (MODE == MODE_COMPACT ? 0 : 2 * stage_len<T, 10> + stage_len<T, 9>);
+template <class T, int SCH, bool SWAP, int MODE>
+__global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
   constexpr bool GF = true;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
@@ -724,10 +737,11 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   //   GhP      : conserved metrics of the face m-1 without the V- term (kernel labelling)
   //   Lpk      : L state of the reconstructed inverse Jacobian of the cell below the face
   T wpe[6], wpx[6], F0[6], F1[6], F2[6], GhP[3][3], Lpk[9];
-  T* const stg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_stage_vals<T>;
+  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_warp_vals<T, MODE>;
+  T* const stg = wsm + ring_vals<4, 3>;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
   using RingT = Ring<T, 4, 3>;
-  const RingT R{stg + 2 * stage_len<T, 10> + stage_len<T, 9>};
+  const RingT R{wsm};
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
   const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
@@ -746,7 +760,8 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[SWAP ? 2 : 1]; N.s2 = (Ix)D.se[SWAP ? 1 : 2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  const bool full = ALL || O.face_cons[AX] != nullptr;
+  constexpr bool ALL = MODE == MODE_FULL, CMP = MODE == MODE_COMPACT;
+  const bool full = ALL || (!CMP && O.face_cons[AX] != nullptr);
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;
   // cell strides of the row axis and the marching axis in the output arrays
   const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
@@ -850,7 +865,7 @@ __global__ void __launch_bounds__(NT, CG_ZETA_MINB) k_face_zeta(Dims D, const T*
       wpe[e] = cf.wpe[e];
       wpx[e] = cf.wpx[e];
     }
-    if (!ALL && O.cactive[AX] && out_ok) {
+    if ((CMP || (!ALL && O.cactive[AX])) && out_ok) {
       T* o = O.cactive[AX] + 3 * cl;
       const T sgn = SWAP ? T(-1) : T(1);
       o[0] = sgn * Gh[2][0]; o[1] = sgn * Gh[2][1]; o[2] = sgn * Gh[2][2];
@@ -1116,21 +1131,31 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   int n = 0;
   const bool face = what & 2;
   // opt in to > 48 KB of shared memory (per device, cheap: set on every launch)
-  const int xi_smem = WY * xi_stage_vals<T> * (int)sizeof(T), zeta_smem = WY * zeta_stage_vals<T> * (int)sizeof(T);
-  cudaFuncSetAttribute(k_face_xi<T, SCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, xi_smem);
-  cudaFuncSetAttribute(k_face_xi<T, SCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, xi_smem);
-  cudaFuncSetAttribute(k_face_zeta<T, SCH, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
-  cudaFuncSetAttribute(k_face_zeta<T, SCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
-  cudaFuncSetAttribute(k_face_zeta<T, SCH, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
-  cudaFuncSetAttribute(k_face_zeta<T, SCH, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, zeta_smem);
+  // which compile-time configuration the outputs correspond to
+  const bool cellface = (what & 3) == 3;
+  const bool is_full = cellface && O.cell_fwd && O.cell_inv && !O.cjac && !O.cactive[0] && !O.cactive[1] && !O.cactive[2] &&
+                       O.face_fwd[0] && O.face_inv[0] && O.face_cons[0] && O.face_fwd[1] && O.face_inv[1] && O.face_cons[1] &&
+                       O.face_fwd[2] && O.face_inv[2] && O.face_cons[2];
+  const bool is_compact = cellface && O.cjac && O.cactive[0] && O.cactive[1] && O.cactive[2] && !O.cell_fwd && !O.cell_inv &&
+                          !O.face_cons[0] && !O.face_cons[1] && !O.face_cons[2];
+  const int mode = is_full ? MODE_FULL : (is_compact ? MODE_COMPACT : MODE_GENERIC);
+  auto launch_xi = [&](auto kern, int warp_vals, dim3 grid, int kchunk) {
+    const int smem = WY * warp_vals * (int)sizeof(T);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<grid, block, smem, st>>>(D, ex, ey, ez, O, what, kchunk);
+  };
+  auto launch_zeta = [&](auto kern, int warp_vals, dim3 grid, int chunk) {
+    const int smem = WY * warp_vals * (int)sizeof(T);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    kern<<<grid, block, smem, st>>>(D, ex, ey, ez, O, chunk);
+  };
   if ((mask & 1) && ((what & 1) || face)) {
     const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
     const int kchunk = chunk_of((int64_t)gx * gy, D.nw[2]);
     const dim3 grid(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
-    const bool all = (what & 3) == 3 && O.cell_fwd && O.cell_inv && O.face_fwd[0] && O.face_inv[0] && O.face_cons[0] &&
-                     !O.cjac && !O.cactive[0];
-    if (all) k_face_xi<T, SCH, true><<<grid, block, xi_smem, st>>>(D, ex, ey, ez, O, what, kchunk);
-    else k_face_xi<T, SCH, false><<<grid, block, xi_smem, st>>>(D, ex, ey, ez, O, what, kchunk);
+    if (mode == MODE_FULL) launch_xi(k_face_xi<T, SCH, MODE_FULL>, xi_warp_vals<T, MODE_FULL>, grid, kchunk);
+    else if (mode == MODE_COMPACT) launch_xi(k_face_xi<T, SCH, MODE_COMPACT>, xi_warp_vals<T, MODE_COMPACT>, grid, kchunk);
+    else launch_xi(k_face_xi<T, SCH, MODE_GENERIC>, xi_warp_vals<T, MODE_GENERIC>, grid, kchunk);
     ++n;
   }
   const unsigned gxz = (unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT);
@@ -1139,18 +1164,18 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     const unsigned gy = (unsigned)((D.nw[2] + WY - 1) / WY);
     const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
-    if (O.face_cons[1] && O.face_fwd[1] && O.face_inv[1] && !O.cactive[1])
-      k_face_zeta<T, SCH, true, true><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, jchunk);
-    else k_face_zeta<T, SCH, true, false><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, jchunk);
+    if (mode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, true, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, jchunk);
+    else if (mode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, true, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, jchunk);
+    else launch_zeta(k_face_zeta<T, SCH, true, MODE_GENERIC>, zeta_warp_vals<T, MODE_GENERIC>, grid, jchunk);
     ++n;
   }
   if ((mask & 4) && face) {
     const unsigned gy = (unsigned)((D.nw[1] + WY - 1) / WY);
     const int kchunk = chunk_of((int64_t)gxz * gy, D.nw[2]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
-    if (O.face_cons[2] && O.face_fwd[2] && O.face_inv[2] && !O.cactive[2])
-      k_face_zeta<T, SCH, false, true><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, kchunk);
-    else k_face_zeta<T, SCH, false, false><<<grid, block, zeta_smem, st>>>(D, ex, ey, ez, O, kchunk);
+    if (mode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, false, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, kchunk);
+    else if (mode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, false, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, kchunk);
+    else launch_zeta(k_face_zeta<T, SCH, false, MODE_GENERIC>, zeta_warp_vals<T, MODE_GENERIC>, grid, kchunk);
     ++n;
   }
   return n;
