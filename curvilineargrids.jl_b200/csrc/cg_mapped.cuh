@@ -330,15 +330,101 @@ __global__ void __launch_bounds__(128) k_mapped_metrics3d(Dims D, MTerms TM, MPa
 }
 
 // ---------------------------------------------------------------------------
-// FULL-profile fast path of the 3-D kernel: same arithmetic, but a warp owns 32 consecutive cells of a
-// j-row and walks along k, and every AoS output goes through the warp's staging buffers and the TMA
-// unit (cg_kernels_tiled.cuh, "Output staging") instead of 80-B-strided stores.
+// FULL-profile fast path of the 3-D kernel.  Same arithmetic as k_mapped_metrics3d, organised like the
+// DiscreteGrid marching kernels: a warp owns 31 consecutive cells of a j-row (lane 31 is the +xi neighbour)
+// and walks along k;
+//   * every AoS output goes through the warp's staging buffers and the TMA unit (cg_kernels_tiled.cuh);
+//   * the L / R states of the reconstructed inverse Jacobian are computed once per cell and axis where the
+//     neighbour is in reach: the +xi neighbour's R state comes by warp shuffle, the +zeta neighbour's state is
+//     the next step's own state (carried); only the +eta neighbour is recomputed;
+//   * one pass over the mapping terms per cell position accumulates F and the f-derivatives of every axis
+//     needed there; the terms are visited coordinate by coordinate (MCoordTerms), no run-time selects.
 // ---------------------------------------------------------------------------
+struct MCoordTerms {
+  int cnt[3];
+  int idx[3][M_MAXT];
+};
+inline MCoordTerms coord_terms(const MTerms& TM) {
+  MCoordTerms C;
+  for (int q = 0; q < 3; ++q) C.cnt[q] = 0;
+  for (int m = 0; m < TM.n; ++m) {
+    const int q = TM.t[m].coord;
+    if (q >= 0 && q < 3) C.idx[q][C.cnt[q]++] = m;
+  }
+  return C;
+}
+// F and, for every axis f with (AXES >> f) & 1, dF/d(xi_f) and d2F/d(xi_f)^2 at the centre of cell ix
+template <class T, int AXES>
+__device__ __forceinline__ void mapped_jac_multi(const MTerms& TM, const MCoordTerms& CT, const T* __restrict__ ftab,
+                                                 int64_t L1, const int64_t (&ix)[3], T (&F)[3][3], T (&Fp)[3][3][3],
+                                                 T (&Fpp)[3][3][3]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      F[q][d] = T(0);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) Fp[f][q][d] = Fpp[f][q][d] = T(0);
+    }
+    for (int mm = 0; mm < CT.cnt[q]; ++mm) {
+      const int m = CT.idx[q][mm];
+      T a[3][4];
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a[d][o] = __ldg(ftab + ((int64_t)(m * 3 + d) * 4 + o) * L1 + ix[d]);
+      const T c = T(TM.t[m].coef);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        // orders: o_ax = (ax == d) for F; + (ax == f) for dF/dxi_f; + 2 (ax == f) for the second derivative
+        const int e = (d + 1) % 3, g = (d + 2) % 3;
+        const T ce = c * a[e][0], cg_ = c * a[g][0];
+        F[q][d] += ce * a[g][0] * a[d][1];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          if (!((AXES >> f) & 1)) continue;
+          if (f == d) {
+            Fp[f][q][d] += ce * a[g][0] * a[d][2];
+            Fpp[f][q][d] += ce * a[g][0] * a[d][3];
+          } else if (f == e) {
+            Fp[f][q][d] += cg_ * a[e][1] * a[d][1];
+            Fpp[f][q][d] += cg_ * a[e][2] * a[d][1];
+          } else {
+            Fp[f][q][d] += ce * a[g][1] * a[d][1];
+            Fpp[f][q][d] += ce * a[g][2] * a[d][1];
+          }
+        }
+      }
+    }
+  }
+}
+// L / R states from G = inv(F) already known
+template <class T>
+__device__ __forceinline__ void mapped_states3_g(const T (&G)[3][3], const T (&Fp)[3][3], const T (&Fpp)[3][3], T lam1,
+                                                 T lam2, T (&Lo)[3][3], T (&Ro)[3][3]) {
+  T A1[3][3], G1[3][3], G2[3][3], A2[3][3], H[3][3];
+  mul3(G, Fp, A1);
+  mul3(A1, G, G1);
+  mul3(A1, G1, G2);
+  mul3(G, Fpp, A2);
+  mul3(A2, G, H);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T s = G[r][c] + lam2 * (T(2) * G2[r][c] - H[r][c]);
+      T d = lam1 * G1[r][c];
+      Lo[r][c] = s - d;
+      Ro[r][c] = s + d;
+    }
+}
+
+constexpr int MAPPED_OUT = 31;
 template <class T> constexpr int mapped_stage_vals = 8 * stage_len<T, 10> + 3 * stage_len<T, 9>;
 template <class T>
-__global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerms TM, MPairs PR, const T* __restrict__ tab,
-                                                                  const T* __restrict__ ftab, int64_t L, MetricOut<T> O,
-                                                                  int scheme, int kchunk) {
+__global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerms TM, MCoordTerms CT, MPairs PR,
+                                                                  const T* __restrict__ tab, const T* __restrict__ ftab,
+                                                                  int64_t L, MetricOut<T> O, int scheme, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const T lam1 = lam1_of<T>(scheme), lam2 = lam2_of<T>(scheme);
   const int64_t L1 = L + 1;
@@ -346,27 +432,46 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
   const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;  // whole warp
-  const int64_t i0 = (int64_t)blockIdx.x * 32;
-  const int nvalid = (int)(nw0 - i0 < 32 ? nw0 - i0 : 32);
+  const int64_t i0 = (int64_t)blockIdx.x * MAPPED_OUT;
+  const int nvalid = (int)(nw0 - i0 < MAPPED_OUT ? nw0 - i0 : MAPPED_OUT);
   const bool out_ok = lane < nvalid;
-  const int64_t i = out_ok ? i0 + lane : nw0 - 1;
+  // lane 31 (and lanes past the row end) evaluate the cell nw0, i.e. the +xi neighbour of the last cell: the
+  // factor tables hold nw + 1 entries per axis
+  const int64_t i = i0 + lane < nw0 ? i0 + lane : nw0;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * mapped_stage_vals<T>;
+
+  // carried along zeta: F, G = inv F, det F and the zeta-axis L state of the cell of the next step
+  T Fc[3][3], Gc[3][3], Jc, Lz[3][3], Fp0[3][3], Fpp0[3][3], Fp1[3][3], Fpp1[3][3];
+  auto cell_state = [&](int64_t m, T (&F)[3][3], T (&G)[3][3], T& J, T (&L2)[3][3], T (&R2)[3][3], T (&P0)[3][3],
+                        T (&PP0)[3][3], T (&P1)[3][3], T (&PP1)[3][3]) {
+    const int64_t ix[3] = {i, j, m};
+    T Fp[3][3][3], Fpp[3][3][3];
+    mapped_jac_multi<T, 7>(TM, CT, ftab, L1, ix, F, Fp, Fpp);
+    J = inv3(F, G);
+    mapped_states3_g(G, Fp[2], Fpp[2], lam1, lam2, L2, R2);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        P0[r][c] = Fp[0][r][c]; PP0[r][c] = Fpp[0][r][c];
+        P1[r][c] = Fp[1][r][c]; PP1[r][c] = Fpp[1][r][c];
+      }
+  };
+  {
+    T R2[3][3];
+    cell_state(k0, Fc, Gc, Jc, Lz, R2, Fp0, Fpp0, Fp1, Fpp1);
+  }
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t ix[3] = {i, j, m};
     const int64_t cl0 = i0 + nw0 * (j + nw1 * m);
     if (lane == 0) bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers
     __syncwarp();
     Stage<T, 10> Scf(O.cell_fwd, cl0, sg), Sci(O.cell_inv, cl0, sg + stage_len<T, 10>);
-    T F[3][3], Fp[3][3], Fpp[3][3], G[3][3], Lc[3][3], Rc[3][3];
-    {
-      mapped_jac<T, 3>(TM, ftab, L1, ix, 0, F, Fp, Fpp);
-      T J = inv3(F, G);
-      if (out_ok) {
-        put10(Scf.slot(lane), F, J);
-        put10(Sci.slot(lane), G, J);
-      }
+    if (out_ok) {
+      put10(Scf.slot(lane), Fc, Jc);
+      put10(Sci.slot(lane), Gc, Jc);
     }
     // ---- conserved metrics: sums over term pairs of triple products of 1-D table values ----
     T Gh[3][3][3];  // [face][row][col]
@@ -381,7 +486,7 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
 #pragma unroll
       for (int d = 0; d < 3; ++d)
 #pragma unroll
-        for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = tab[((int64_t)(p * 3 + d) * OP_COUNT + o) * L + ix[d]];
+        for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = __ldg(tab + ((int64_t)(p * 3 + d) * OP_COUNT + o) * L + (ix[d] < D.nw[d] ? ix[d] : D.nw[d] - 1));
       const T C = T(TM.t[PR.p[p].m1].coef * TM.t[PR.p[p].m2].coef);
       const int col = PR.p[p].col;
 #pragma unroll
@@ -399,24 +504,43 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
           }
       }
     }
+    // ---- reconstructed inverse Jacobian on the three faces ----
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
       T* const sf = sg + (2 + 2 * f) * stage_len<T, 10>;
       Stage<T, 10> Sff(O.face_fwd[f], cl0, sf), Sfi(O.face_inv[f], cl0, sf + stage_len<T, 10>);
       Stage<T, 9> Sfc(O.face_cons[f], cl0, sg + 8 * stage_len<T, 10> + f * stage_len<T, 9>);
       if (out_ok) put9(Sfc.slot(lane), Gh[f]);
-      // ---- reconstructed inverse Jacobian ----
-      T Gn[3][3], Ln[3][3], Rn[3][3], Gf[3][3], Ff[3][3];
-      mapped_jac<T, 3>(TM, ftab, L1, ix, f, F, Fp, Fpp);
-      mapped_states3(F, Fp, Fpp, lam1, lam2, G, Lc, Rc);
-      int64_t in[3] = {ix[0], ix[1], ix[2]};
-      in[f] += 1;
-      mapped_jac<T, 3>(TM, ftab, L1, in, f, F, Fp, Fpp);
-      mapped_states3(F, Fp, Fpp, lam1, lam2, Gn, Ln, Rn);
+      T Gf[3][3], Ff[3][3];
+      if (f == 0) {  // +xi neighbour: its R state by shuffle
+        T L0[3][3], R0[3][3];
+        mapped_states3_g(Gc, Fp0, Fpp0, lam1, lam2, L0, R0);
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-        for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (Lc[a][b] + Rn[a][b]);
+          for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (L0[a][b] + __shfl_down_sync(FULLMASK, R0[a][b], 1));
+      } else if (f == 1) {  // +eta neighbour: recomputed
+        T L1s[3][3], R1s[3][3], Fn[3][3], Gn[3][3], Ln[3][3], Rn[3][3], Fpn[3][3][3], Fppn[3][3][3];
+        mapped_states3_g(Gc, Fp1, Fpp1, lam1, lam2, L1s, R1s);
+        const int64_t in[3] = {i, j + 1, m};
+        mapped_jac_multi<T, 2>(TM, CT, ftab, L1, in, Fn, Fpn, Fppn);
+        inv3(Fn, Gn);
+        mapped_states3_g(Gn, Fpn[1], Fppn[1], lam1, lam2, Ln, Rn);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (L1s[a][b] + Rn[a][b]);
+      } else {  // +zeta neighbour: the cell of the next step; its F, G, L state are carried
+        T Ln[3][3], Rn[3][3];
+        cell_state(m + 1, Fc, Gc, Jc, Ln, Rn, Fp0, Fpp0, Fp1, Fpp1);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) {
+            Gf[a][b] = T(0.5) * (Lz[a][b] + Rn[a][b]);
+            Lz[a][b] = Ln[a][b];
+          }
+      }
       T J = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
       if (out_ok) {
         put10(Sff.slot(lane), Ff, J);
@@ -443,19 +567,19 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
 template <class T>
 inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
                                            int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
-  const unsigned gx = (unsigned)((D.nw[0] + 31) / 32), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+  const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
   const int64_t tiles = (int64_t)gx * gy, want = 148LL * 16;
   int kchunk = (int)D.nw[2];
   if (tiles < want) {
     const int64_t nch = (want + tiles - 1) / tiles;
     kchunk = (int)((D.nw[2] + nch - 1) / nch);
-    if (kchunk < 4) kchunk = 4;
+    if (kchunk < 8) kchunk = 8;
     if (kchunk > D.nw[2]) kchunk = (int)D.nw[2];
   }
   const int smem = WY * mapped_stage_vals<T> * (int)sizeof(T);
   cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, WY), smem, st>>>(
-      D, TM, PR, tab, ftab, L, O, scheme, kchunk);
+      D, TM, coord_terms(TM), PR, tab, ftab, L, O, scheme, kchunk);
 }
 
 // =============================== 2-D ========================================
