@@ -340,6 +340,13 @@ __global__ void __launch_bounds__(128) k_mapped_metrics3d(Dims D, MTerms TM, MPa
 //   * one pass over the mapping terms per cell position accumulates F and the f-derivatives of every axis
 //     needed there; the terms are visited coordinate by coordinate (MCoordTerms), no run-time selects.
 // ---------------------------------------------------------------------------
+#ifndef CG_MAPPED_UNROLL_P
+#define CG_MAPPED_UNROLL_P 2
+#endif
+#ifndef CG_MAPPED_UNROLL_T
+#define CG_MAPPED_UNROLL_T 2
+#endif
+constexpr int MAPPED_UNROLL_P = CG_MAPPED_UNROLL_P, MAPPED_UNROLL_T = CG_MAPPED_UNROLL_T;
 struct MCoordTerms {
   int cnt[3];
   int idx[3][M_MAXT];
@@ -366,6 +373,7 @@ __device__ __forceinline__ void mapped_jac_multi(const MTerms& TM, const MCoordT
 #pragma unroll
       for (int f = 0; f < 3; ++f) Fp[f][q][d] = Fpp[f][q][d] = T(0);
     }
+#pragma unroll(MAPPED_UNROLL_T)
     for (int mm = 0; mm < CT.cnt[q]; ++mm) {
       const int m = CT.idx[q][mm];
       T a[3][4];
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
       for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) Gh[f][rr][cc] = T(0);
+#pragma unroll(MAPPED_UNROLL_P)
     for (int p = 0; p < PR.n; ++p) {
       T tv[3][OP_COUNT];
 #pragma unroll
