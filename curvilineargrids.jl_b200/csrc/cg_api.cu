@@ -322,7 +322,7 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
     cg::k_metrics1d_ref<T><<<launch_blocks(nc, 256), 256, 0, st>>>(D, ex, O, g->scheme, what);
     nl = 1;
   } else if (N == 2) {
-    if (g->kernel_opt == 1 && cg::tiled2d_supported<T>(D, O))
+    if (g->kernel_opt == 1 && cg::tiled2d_supported<T>(D, O, what))
       nl = cg::launch_metrics2d_tiled<T>(D, ex, ey, O, g->scheme, what, st);
     else {
       cg::k_metrics2d_ref<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, ex, ey, O, g->scheme, what);

@@ -1096,14 +1096,129 @@ __global__ void __launch_bounds__(128) k_metrics2d_pair(Dims D, const T* ex, con
   }
 }
 
+// ===========================================================================
+// 2-D, FULL profile, cell + face: a warp owns 32 consecutive cells of a row and walks along eta; the
+// eight AoS arrays (40-B Metric / 32-B ConservedMetric elements) go through the warp's staging buffers
+// and the TMA unit like the 3-D kernels ("Output staging" above).  Same arithmetic as k_metrics2d_pair.
+// ===========================================================================
 template <class T>
-inline bool tiled2d_supported(const Dims& D, const MetricOut<T>&) {
+CG_D void put5(T* o, const T (&M)[2][2], T J) {
+  o[0] = M[0][0]; o[1] = M[1][0]; o[2] = M[0][1]; o[3] = M[1][1]; o[4] = J;
+}
+template <class T>
+CG_D void put4(T* o, const T (&M)[2][2]) {
+  if constexpr (sizeof(T) == 8) {
+    double2* p = reinterpret_cast<double2*>(o);
+    p[0] = make_double2(M[0][0], M[1][0]);
+    p[1] = make_double2(M[0][1], M[1][1]);
+  } else {
+    o[0] = M[0][0]; o[1] = M[1][0]; o[2] = M[0][1]; o[3] = M[1][1];
+  }
+}
+template <class T> constexpr int stage2d_vals = 6 * stage_len<T, 5> + 2 * stage_len<T, 4>;
+template <class T>
+__global__ void __launch_bounds__(NT) k_metrics2d_staged(Dims D, const T* __restrict__ ex, const T* __restrict__ ey,
+                                                         MetricOut<T> O, int scheme, int jchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  const T lam1 = lam1_of<T>(scheme), lam2 = lam2_of<T>(scheme);
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], s1 = D.se[1];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int nvalid = (int)(nw0 - i0 < 32 ? nw0 - i0 : 32);
+  const bool out_ok = lane < nvalid;
+  const int64_t i = out_ok ? i0 + lane : nw0 - 1;
+  const int64_t j0 = ((int64_t)blockIdx.y * blockDim.y + threadIdx.y) * jchunk;
+  const int64_t j1 = j0 + jchunk < nw1 ? j0 + jchunk : nw1;
+  T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * stage2d_vals<T>;
+  T* sb[8];
+#pragma unroll
+  for (int a = 0; a < 6; ++a) sb[a] = sg + a * stage_len<T, 5>;
+  sb[6] = sg + 6 * stage_len<T, 5>;
+  sb[7] = sb[6] + stage_len<T, 4>;
+  const T dl0 = clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]);
+  for (int64_t j = j0; j < j1; ++j) {
+    const int64_t b = (i + 1) + (j + 1) * s1;
+    const int64_t cl0 = i0 + j * nw0;
+    if (lane == 0) bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers
+    __syncwarp();
+    Stage<T, 5> Scf(O.cell_fwd, cl0, sb[0]), Sci(O.cell_inv, cl0, sb[1]), Sf0(O.face_fwd[0], cl0, sb[2]),
+        Si0(O.face_inv[0], cl0, sb[3]), Sf1(O.face_fwd[1], cl0, sb[4]), Si1(O.face_inv[1], cl0, sb[5]);
+    Stage<T, 4> Sc0(O.face_cons[0], cl0, sb[6]), Sc1(O.face_cons[1], cl0, sb[7]);
+    const Cell2<T> c00 = cell2_load(ex, ey, b, s1), c10 = cell2_load(ex, ey, b + 1, s1), c01 = cell2_load(ex, ey, b + s1, s1);
+    T G00[2][2], G10[2][2], G01[2][2];
+    inv2(c00.F, G00);
+    inv2(c10.F, G10);
+    inv2(c01.F, G01);
+    {
+      const T dl1 = clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]);
+      T FA[2][2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        FA[q][0] = c00.F[q][0] + c00.tw[q] * dl1;
+        FA[q][1] = c00.F[q][1] + c00.tw[q] * dl0;
+      }
+      const T JA = FA[0][0] * FA[1][1] - FA[0][1] * FA[1][0];
+      if (out_ok) {
+        put5(Scf.slot(lane), FA, JA);
+        put5(Sci.slot(lane), G00, JA);
+      }
+    }
+    {
+      T Gh[2][2], Gf[2][2], Ff[2][2], J = 0;
+      face2d(c00, c10, G00, G10, 0, lam1, lam2, true, Gh, Gf, Ff, J);
+      if (out_ok) {
+        put4(Sc0.slot(lane), Gh);
+        put5(Sf0.slot(lane), Ff, J);
+        put5(Si0.slot(lane), Gf, J);
+      }
+      face2d(c00, c01, G00, G01, 1, lam1, lam2, true, Gh, Gf, Ff, J);
+      if (out_ok) {
+        put4(Sc1.slot(lane), Gh);
+        put5(Sf1.slot(lane), Ff, J);
+        put5(Si1.slot(lane), Gf, J);
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    Scf.issue(nvalid, lane);
+    Sci.issue(nvalid, lane);
+    Sf0.issue(nvalid, lane);
+    Si0.issue(nvalid, lane);
+    Sf1.issue(nvalid, lane);
+    Si1.issue(nvalid, lane);
+    Sc0.issue(nvalid, lane);
+    Sc1.issue(nvalid, lane);
+    if (lane == 0) bulk_commit();
+  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
+}
+
+// the staged kernel covers the FULL cell+face configuration at any width
+template <class T>
+inline bool staged2d_applies(const MetricOut<T>& O, int what) {
+  static const bool use_staged = !(getenv("CG_2D_STAGED") && atoi(getenv("CG_2D_STAGED")) == 0);
+  return use_staged && (what & 3) == 3 && O.cell_fwd && O.cell_inv && O.face_fwd[0] && O.face_inv[0] && O.face_cons[0] &&
+         O.face_fwd[1] && O.face_inv[1] && O.face_cons[1] && !O.cjac && !O.cactive[0] && !O.cactive[1];
+}
+template <class T>
+inline bool tiled2d_supported(const Dims& D, const MetricOut<T>& O, int what) {
   // pair stores need every row to start 16-B aligned: an even number of cells per row
-  return D.dim == 2 && (D.nw[0] % 2 == 0 || sizeof(T) == 4);
+  return D.dim == 2 && (staged2d_applies(O, what) || D.nw[0] % 2 == 0 || sizeof(T) == 4);
 }
 template <class T>
 inline int launch_metrics2d_tiled(const Dims& D, const T* ex, const T* ey, const MetricOut<T>& O, int scheme, int what,
                                   cudaStream_t st) {
+  if (staged2d_applies(O, what)) {
+    const unsigned gx = (unsigned)((D.nw[0] + 31) / 32);
+    // rows per warp: enough warps to fill the machine a few times over, long enough to amortise the set-up
+    int jchunk = (int)((D.nw[1] * (int64_t)gx + 148LL * 64 - 1) / (148LL * 64));
+    if (jchunk < 4) jchunk = 4;
+    const int64_t nwarps_y = (D.nw[1] + jchunk - 1) / jchunk;
+    const int smem = WY * stage2d_vals<T> * (int)sizeof(T);
+    cudaFuncSetAttribute(k_metrics2d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_metrics2d_staged<T><<<dim3(gx, (unsigned)((nwarps_y + WY - 1) / WY)), dim3(32, WY), smem, st>>>(D, ex, ey, O, scheme, jchunk);
+    return 1;
+  }
   const int64_t n = ((D.nw[0] + 1) / 2) * D.nw[1];
   int64_t blocks = (n + 127) / 128;
   if (blocks > 148LL * 64) blocks = 148LL * 64;
