@@ -1260,14 +1260,16 @@ inline Fork* fork_streams() {
 template <class T, int SCH>
 inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez, const MetricOut<T>& O, int what,
                            int mask, cudaStream_t st) {
-  const int64_t want = 148LL * 16;  // enough chunks to fill the machine a few times over
+  // enough blocks for ~30 waves (fine-grained tail, measured best at 512^3) as long as a chunk stays >= 64 steps
+  // (the prologue of a chunk costs about three steps)
+  const int64_t want = 148LL * 64;
   // chunk length along the marching axis: long enough to amortise the prologue
   auto chunk_of = [&](int64_t tiles, int64_t extent) {
     int c = (int)extent;
     if (tiles < want) {
       int64_t nchunks = (want + tiles - 1) / tiles;
       c = (int)((extent + nchunks - 1) / nchunks);
-      if (c < 16) c = 16;
+      if (c < 64) c = 64;
       if (c > extent) c = (int)extent;
     }
     return c;
