@@ -722,7 +722,7 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
 template <class T, int MODE> constexpr int zeta_warp_vals =
-    ring_vals<4, 3> + (MODE == MODE_COMPACT ? 0 : 2 * stage_len<T, 10> + stage_len<T, 9>);
+    ring_vals<4, 4> + (MODE == MODE_COMPACT ? 0 : 2 * stage_len<T, 10> + stage_len<T, 9>);
 template <class T, int SCH, bool SWAP, int MODE>
 __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
@@ -738,9 +738,9 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   //   Lpk      : L state of the reconstructed inverse Jacobian of the cell below the face
   T wpe[6], wpx[6], F0[6], F1[6], F2[6], GhP[3][3], Lpk[9];
   T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_warp_vals<T, MODE>;
-  T* const stg = wsm + ring_vals<4, 3>;
+  T* const stg = wsm + ring_vals<4, 4>;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
-  using RingT = Ring<T, 4, 3>;
+  using RingT = Ring<T, 4, 4>;
   const RingT R{wsm};
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
@@ -767,7 +767,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
 
   // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2);
-  // planes k0+1 .. k0+3 are primed here, plane m+4 follows in step m
+  // planes k0+1 .. k0+3 are primed here, plane m+4 follows at the top of step m (4 slots: no barrier inside a step)
   auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
   const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32 + (lane & 1)) + (Ix)j * N.s1 + N.s2;
 #pragma unroll
@@ -837,14 +837,13 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
     if (lane == 0) bulk_wait_read();
     cp_async_wait_all();
     __syncwarp();
-    const RingSrc<T, RingT> S{R, (int)(m + 1), lane};
-    CellZ<T> cf;  // front cell m + 1
-    cellz_compute<T, SCH, GF>(S, full, lam1, lam2, cf);
-    if (m + 1 < k1) {  // plane m+4 into the slot of plane m+1, which every lane has finished reading
-      __syncwarp();
+    if (m + 1 < k1) {  // plane m+4 (first needed in the next step) into the slot plane m has left
       R.template fetch<2>(N, (int)(m + 4), rg0 + (Ix)(m + 4) * N.s2, rgx + (Ix)(m + 4) * N.s2, lane);
       cp_async_commit();
     }
+    const RingSrc<T, RingT> S{R, (int)(m + 1), lane};
+    CellZ<T> cf;  // front cell m + 1
+    cellz_compute<T, SCH, GF>(S, full, lam1, lam2, cf);
     T Gh[3][3];  // rows 0 xi, 1 eta, 2 zeta
 #pragma unroll
     for (int col = 0; col < 3; ++col) {
