@@ -17,6 +17,9 @@ between k-slabs when N > 1).
                       host nodes -> H2D -> (exchange) -> pad -> metrics -> GCL max
                       reduced on device -> D2H of the residuals, all inside the
                       timed region.
+  other workloads     --workload 2d4096 (BASELINE configs[1], GradientCorrected), m3d512 (configs[3]: MappedGrid,
+                      update!(grid, t) + both metric caches every step), sph1536 --profile compact (configs[4]:
+                      spherical-basis DiscreteGrid, 1536 x 1536 x 192 cells per GPU, k-slabs, weak scaling)
   --impl reference    the CPU oracle (restatement of the reference algorithm; the
                       Julia package cannot run here) on all host threads over a
                       bounded sample of the same workload.
@@ -72,6 +75,13 @@ def workload_spec(name, scheme):
         n = int(name[2:])
         return dict(kind="2d", n=n, nhalo=5, scheme=scheme or "gradient",
                     desc=f"2-D DiscreteGrid {n}^2 wavy (test_2d.jl:154-181), nhalo=5, cell+face")
+    if name.startswith("sph"):
+        # BASELINE config 5: spherical-basis DiscreteGrid ((r, theta, phi) node coordinates), k-slabs; per GPU
+        # sph<N> = N x N x N/8 cells (sph1536: 1536 x 1536 x 192), COMPACT profile unless --profile full is given
+        n = int(name[3:])
+        return dict(kind="3d", gen="sph", n=n, nslab=max(1, n // 8), nhalo=5, scheme=scheme or "curvature",
+                    desc=f"3-D spherical-basis DiscreteGrid {n}x{n}x{max(1, n // 8)} cells per GPU ((r,theta,phi) nodes of "
+                         f"test_mapped_discrete_face_geometry.jl:196-226), nhalo=5, cell+face")
     if name.startswith("m3d"):
         n = int(name[3:])
         return dict(kind="m3d", n=n, nhalo=5, scheme=scheme or "curvature",
@@ -95,6 +105,23 @@ def wavy_slab_3d(ni, nj, nk_total, k_lo, k_hi, L=4.0):
     y = -L / 2 + dy * (j + sp(k * dz) * sp(i * dx))
     z = -L / 2 + dz * (k + sp(i * dx) * sp(j * dy))
     return [np.ascontiguousarray(np.broadcast_to(a, shp)) for a in (x, y, z)]
+
+
+def sph_slab_3d(ni, nj, nk_total, k_lo, k_hi):
+    """Node planes [k_lo,k_hi) of the perturbed (r, theta, phi) mesh of workloads.spherical_rtp_3d_terms, memory order
+    [k,j,i]; ni, nj, nk_total are node counts."""
+    ci, cj, ck = ni - 1, nj - 1, nk_total - 1
+    r0, th0, ph0 = 1.2, 0.45, 0.25
+    dr, dth, dph = 0.4 / ci, 0.35 / cj, 0.45 / ck
+    i = np.arange(ni, dtype=np.float64)[None, None, :]
+    j = np.arange(nj, dtype=np.float64)[None, :, None]
+    k = np.arange(k_lo, k_hi, dtype=np.float64)[:, None, None]
+    s2i, s2j, s1k = np.sin(2 * np.pi * i / ci), np.sin(2 * np.pi * j / cj), np.sin(np.pi * k / ck)
+    shp = (k_hi - k_lo, nj, ni)
+    r = r0 + dr * i + 0.012 * s2j * s1k
+    th = th0 + dth * j + 0.008 * s2i
+    ph = ph0 + dph * k + 0.006 * s2i * s2j
+    return [np.ascontiguousarray(np.broadcast_to(a, shp)) for a in (r, th, ph)]
 
 
 def wavy_slab_2d(nx, ny_total, j_lo, j_hi, a0=0.1):
@@ -196,6 +223,10 @@ def cpu_oracle_rate(spec, nodes_host_global, seconds, nthreads=None):
 def global_nodes_for_cpu(spec, nranks):
     """Host node arrays of the whole workload as numpy [i,j,k]-indexed views (for the oracle)."""
     n = spec["n"]
+    if spec.get("gen") == "sph":
+        ns = spec["nslab"]
+        arrs = sph_slab_3d(n + 1, n + 1, ns * nranks + 1, 0, ns * nranks + 1)
+        return [a.transpose(2, 1, 0) for a in arrs]
     if spec["kind"] == "3d":
         arrs = wavy_slab_3d(n + 1, n + 1, n * nranks + 1, 0, n * nranks + 1)
         return [a.transpose(2, 1, 0) for a in arrs]
@@ -252,11 +283,13 @@ def run_ours(args, spec):
     dim = 3 if spec["kind"] == "3d" else 2
     T = np.float64 if args.dtype == "f64" else np.float32
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
-    ncell_slab = n * world  # weak scaling: the grid grows along the slab axis
+    nslab = spec.get("nslab", n)
+    ncell_slab = nslab * world  # weak scaling: the grid grows along the slab axis
     plan = cg.slabs.make_plan(rank, world, ncell_slab, h)
     lo, hi = plan.required
     if dim == 3:
-        host = wavy_slab_3d(n + 1, n + 1, ncell_slab + 1, lo, hi)
+        gen = sph_slab_3d if spec.get("gen") == "sph" else wavy_slab_3d
+        host = gen(n + 1, n + 1, ncell_slab + 1, lo, hi)
         inplane = (n, n)
     else:
         host = wavy_slab_2d(n + 1, ncell_slab + 1, lo, hi)
@@ -359,7 +392,7 @@ def run_ours(args, spec):
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "algorithmic_bytes": bpc * cells_local,
-                "kernel": ("k_face_xi + k_face_eta + k_face_zeta (one fused cell+face evaluation = 3 launches)"
+                "kernel": ("k_face_xi + k_face_zeta<SWAP> (eta) + k_face_zeta (one cell+face evaluation = 3 launches)"
                            if dim == 3 and args.kernel == 1 else ("metrics3d" if dim == 3 else "metrics2d")),
                 "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": bpc, "peak_source": f"MEASURED_PEAKS.json ({peak_src}, copy burst)"}
@@ -387,7 +420,7 @@ def run_ours(args, spec):
             "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": spec["desc"] + (f"; k-slabs over {world} GPUs, grid {n}x{n}x{n * world}" if world > 1 and dim == 3 else ""),
+            "config": {"workload": spec["desc"] + (f"; k-slabs over {world} GPUs, grid {n}x{n}x{nslab * world}" if world > 1 and dim == 3 else ""),
                        "scheme": spec["scheme"], "profile": args.profile, "cells_written": cells_total,
                        "kernel": "tiled" if args.kernel == 1 else "gather",
                        "l2": "inputs+outputs per step far exceed the 126 MB L2 (no flush needed)",
