@@ -43,8 +43,11 @@ constexpr unsigned FULLMASK = 0xffffffffu;
 // loop body is straight-line code the scheduler can interleave freely and unused work disappears:
 //   MODE_FULL    : FULL profile, cell + face outputs (all nine AoS arrays)
 //   MODE_COMPACT : COMPACT profile, cell + face outputs (J of the cell, active conserved row per axis)
-//   MODE_GENERIC : anything else (cell-only / face-only refreshes), switches read at run time
-enum { MODE_GENERIC = 0, MODE_FULL = 1, MODE_COMPACT = 2 };
+//   MODE_FACE    : FULL profile, face outputs only  (refresh_face_metrics!; xi kernel only — the eta / zeta kernels
+//                  never write cell arrays and use MODE_FULL)
+//   MODE_CELL    : FULL profile, cell outputs only  (refresh_cell_metrics!; xi kernel only)
+//   MODE_GENERIC : anything else, switches read at run time
+enum { MODE_GENERIC = 0, MODE_FULL = 1, MODE_COMPACT = 2, MODE_FACE = 3, MODE_CELL = 4 };
 
 template <class T>
 struct PF {
@@ -453,13 +456,14 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
   const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
-  constexpr bool ALL = MODE == MODE_FULL, CMP = MODE == MODE_COMPACT;
-  const bool full = ALL || (!CMP && O.face_cons[0] != nullptr);
-  const bool do_cell = ALL || CMP || (what & 1);
-  const bool do_cons = ALL || CMP || (what & 2);
-  const bool do_gf = ALL || (!CMP && (what & 2) && full);
-  const bool st_cf = ALL || (!CMP && do_cell && O.cell_fwd), st_ci = ALL || (!CMP && do_cell && O.cell_inv);
-  const bool st_cj = CMP || (!ALL && O.cjac), st_ca = CMP || (!ALL && O.cactive[0]);
+  constexpr bool ALL = MODE == MODE_FULL, CMP = MODE == MODE_COMPACT, FACE = MODE == MODE_FACE, CELL = MODE == MODE_CELL;
+  constexpr bool GEN = MODE == MODE_GENERIC;
+  const bool full = ALL || FACE || (GEN && O.face_cons[0] != nullptr);
+  const bool do_cell = ALL || CMP || CELL || (GEN && (what & 1));
+  const bool do_cons = ALL || CMP || FACE || (GEN && (what & 2));
+  const bool do_gf = ALL || FACE || (GEN && (what & 2) && full);
+  const bool st_cf = ALL || CELL || (GEN && do_cell && O.cell_fwd), st_ci = ALL || CELL || (GEN && do_cell && O.cell_inv);
+  const bool st_cj = CMP || (GEN && O.cjac), st_ca = CMP || (GEN && O.cactive[0]);
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
   T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_warp_vals<T, MODE>;
@@ -1285,6 +1289,13 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   const bool is_compact = cellface && O.cjac && O.cactive[0] && O.cactive[1] && O.cactive[2] && !O.cell_fwd && !O.cell_inv &&
                           !O.face_cons[0] && !O.face_cons[1] && !O.face_cons[2];
   const int mode = is_full ? MODE_FULL : (is_compact ? MODE_COMPACT : MODE_GENERIC);
+  // FULL-profile refreshes of one cache only (the reference's refresh_cell_metrics! / refresh_face_metrics!)
+  const bool no_compact = !O.cjac && !O.cactive[0] && !O.cactive[1] && !O.cactive[2];
+  const bool faces_full = no_compact && O.face_fwd[0] && O.face_inv[0] && O.face_cons[0] && O.face_fwd[1] && O.face_inv[1] &&
+                          O.face_cons[1] && O.face_fwd[2] && O.face_inv[2] && O.face_cons[2];
+  const bool is_face_only = (what & 3) == 2 && faces_full;
+  const bool is_cell_only = (what & 3) == 1 && no_compact && O.cell_fwd && O.cell_inv;
+  const int zmode = (is_full || is_face_only) ? MODE_FULL : mode;  // eta / zeta kernels
   auto launch_xi = [&](auto kern, int warp_vals, dim3 grid, int kchunk) {
     const int smem = WY * warp_vals * (int)sizeof(T);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1308,6 +1319,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     const dim3 grid(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
     if (mode == MODE_FULL) launch_xi(k_face_xi<T, SCH, MODE_FULL>, xi_warp_vals<T, MODE_FULL>, grid, kchunk);
     else if (mode == MODE_COMPACT) launch_xi(k_face_xi<T, SCH, MODE_COMPACT>, xi_warp_vals<T, MODE_COMPACT>, grid, kchunk);
+    else if (is_face_only) launch_xi(k_face_xi<T, SCH, MODE_FACE>, xi_warp_vals<T, MODE_FACE>, grid, kchunk);
+    else if (is_cell_only) launch_xi(k_face_xi<T, SCH, MODE_CELL>, xi_warp_vals<T, MODE_CELL>, grid, kchunk);
     else launch_xi(k_face_xi<T, SCH, MODE_GENERIC>, xi_warp_vals<T, MODE_GENERIC>, grid, kchunk);
     ++n;
   }
@@ -1318,8 +1331,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     const unsigned gy = (unsigned)((D.nw[2] + WY - 1) / WY);
     const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
-    if (mode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, true, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, jchunk);
-    else if (mode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, true, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, jchunk);
+    if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, true, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, jchunk);
+    else if (zmode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, true, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, jchunk);
     else launch_zeta(k_face_zeta<T, SCH, true, MODE_GENERIC>, zeta_warp_vals<T, MODE_GENERIC>, grid, jchunk);
     ++n;
   }
@@ -1328,8 +1341,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     const unsigned gy = (unsigned)((D.nw[1] + WY - 1) / WY);
     const int kchunk = chunk_of((int64_t)gxz * gy, D.nw[2]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
-    if (mode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, false, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, kchunk);
-    else if (mode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, false, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, kchunk);
+    if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, false, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, kchunk);
+    else if (zmode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, false, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, kchunk);
     else launch_zeta(k_face_zeta<T, SCH, false, MODE_GENERIC>, zeta_warp_vals<T, MODE_GENERIC>, grid, kchunk);
     ++n;
   }
