@@ -72,10 +72,13 @@ struct cg_grid {
     for (int d = 0; d < dim; ++d) n *= nw[d] + 1;
     return n;
   }
+  // padded ("ext") node array: nw + 4 nodes per active axis; the row pitch is a multiple of 16 bytes (the eta / zeta
+  // kernels fetch row segments with 16-byte cp.async) and 64 values of slack follow the last row
+  int64_t pitch0() const { return dim > 1 ? (nw[0] + 4 + 3) / 4 * 4 : nw[0] + 4; }
   int64_t next() const {
-    int64_t n = 1;
-    for (int d = 0; d < dim; ++d) n *= nw[d] + 4;
-    return n;
+    int64_t n = pitch0();
+    for (int d = 1; d < dim; ++d) n *= nw[d] + 4;
+    return n + 64;
   }
   cg::Dims dims() const {
     cg::Dims D;
@@ -86,7 +89,7 @@ struct cg_grid {
       D.nw[d] = nw[d];
       D.ne[d] = d < dim ? nw[d] + 4 : 1;
       D.se[d] = s;
-      s *= D.ne[d];
+      s *= d == 0 ? pitch0() : D.ne[d];
       D.w0[d] = w0[d] + goff[d];
       D.gn[d] = ncell[d];
     }

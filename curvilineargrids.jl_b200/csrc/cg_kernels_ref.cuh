@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, 
     nb2 = off2 > 0 ? -S.st[2] : S.st[2];
     base_jk += (c - S.s0[2]) * S.st[2];
   }
-  const int64_t row = (e1 + D.ne[1] * e2) * D.ne[0];
+  const int64_t row = e1 * D.se[1] + e2 * D.se[2];
   const T* src[3] = {S.p[0], S.p[1], S.p[2]};
   T* out[3] = {ex, ey, ez};
   for (int64_t i = threadIdx.x; i < D.ne[0]; i += blockDim.x) {

@@ -36,6 +36,17 @@ namespace cg {
 #endif
 constexpr int WY = CG_WY;       // warps (rows) per block of the marching kernels
 constexpr int NT = 32 * WY;     // threads per block
+#ifndef CG_ZWY
+#define CG_ZWY 1
+#endif
+// The eta / zeta kernels run ONE warp per block: row index, chunk and every staging / TMA address are then functions
+// of blockIdx alone, i.e. they live in uniform registers (UBLKCP straight from UR operands, no R2UR loops).
+constexpr int ZWY = CG_ZWY;
+#ifndef CG_Z_UNROLL
+#define CG_Z_UNROLL 1
+#endif
+constexpr int Z_UNROLL = CG_Z_UNROLL;  // unroll factor of the eta / zeta marching loop
+constexpr int ZNT = 32 * ZWY;
 constexpr int WARP_OUT = 29;  // output cells per warp along xi (kernels that need lanes -1, +1, +2)
 constexpr int ZETA_OUT = 31;  // the zeta / eta(SWAP) kernel only needs lane -1
 constexpr unsigned FULLMASK = 0xffffffffu;
@@ -167,6 +178,56 @@ struct Ring {
     return f;
   }
   // zeta-pair (planes plane, plane+1) of the node column (row r, column c)
+  CG_D ZPair<T> zpair(int plane, int r, int c) const {
+    ZPair<T> p;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const T lo = row(plane, r, q)[c], hi = row(plane + 1, r, q)[c];
+      p.s[q] = hi + lo;
+      p.d[q] = hi - lo;
+    }
+    return p;
+  }
+};
+
+// Ring of the eta / zeta kernels: same layout, but a plane row is fetched with 16-byte cp.async by the first NL
+// lanes.  The padded node arrays have a row pitch that is a multiple of 16 bytes (cg_api.cu: dims()), so the
+// row segment starting at the column i0 rounded DOWN to a 16-byte boundary is aligned; `ph` = i0 mod VEC is the
+// warp-uniform column phase every read adds.  Columns past the end of a row belong to lanes without output.
+template <class T, int ROWS, int SLOTS>
+struct RingV {
+  static constexpr int VEC = 16 / (int)sizeof(T);
+  static constexpr int NL = (34 + 2 * (VEC - 1)) / VEC;  // lanes that copy
+  static constexpr int COLS = VEC * NL;
+  static constexpr int VALS = SLOTS * ROWS * 3 * COLS;
+  T* base;  // already shifted by the phase
+  CG_D T* row(int plane, int r, int q) const {
+    const int slot = SLOTS == 4 ? (plane & 3) : plane % SLOTS;
+    return base + ((slot * ROWS + r) * 3 + q) * COLS;
+  }
+  // g0 = index of (aligned first column + VEC * lane, ring row 0, that plane); base_unshifted = base - ph
+  template <class IX>
+  CG_D void fetch(const NodeP<T, IX>& N, int plane, IX g0, int lane, int ph) const {
+    if (lane < NL) {
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const uint32_t d = (uint32_t)__cvta_generic_to_shared(row(plane, r, q) - ph + VEC * lane);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(N.q[q] + g0 + (IX)r * N.s1) : "memory");
+        }
+    }
+  }
+  CG_D PF<T> zplane(int plane, int r, int lane) const {
+    PF<T> f;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const T* a = row(plane, r, q) + lane;
+      const T* b = row(plane, r + 1, q) + lane;
+      f.q[q] = raw_form(a[0], a[1], b[0], b[1]);
+    }
+    return f;
+  }
   CG_D ZPair<T> zpair(int plane, int r, int c) const {
     ZPair<T> p;
 #pragma unroll
@@ -342,6 +403,39 @@ CG_D LineS<T> line_from_taylor(const T (&c)[3][8], int q1, int q2, int f, int b,
   return line_scalars(p0, p1, p2, lam1, lam2);
 }
 
+// RAW Taylor sums of the cell from its two RAW eta-planes: craw[q][S] = 2^(3 - |S|) * (true coefficient), pure
+// sums / differences.  Every consumer in the eta / zeta kernels is a product of two coefficients (line scalars) or
+// homogeneous in F (inverse Jacobian states), so the powers of two fold into compile-time weights.
+template <class T>
+CG_D void taylor_raw_e(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    c[q][0] = lo.q[q].c0 + hi.q[q].c0;
+    c[q][1] = lo.q[q].cu + hi.q[q].cu;
+    c[q][2] = hi.q[q].c0 - lo.q[q].c0;
+    c[q][3] = hi.q[q].cu - lo.q[q].cu;
+    c[q][4] = lo.q[q].cv + hi.q[q].cv;
+    c[q][5] = lo.q[q].cuv + hi.q[q].cuv;
+    c[q][6] = hi.q[q].cv - lo.q[q].cv;
+    c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
+  }
+}
+// line scalars from RAW Taylor sums: p0 carries 32 x, p1 16 x, p2 8 x the true value
+template <class T>
+CG_D LineS<T> line_from_taylor_raw(const T (&c)[3][8], int q1, int q2, int f, int b, T lam1, T lam2) {
+  const int mb = 1 << b, mf = 1 << f;
+  const T p0 = c[q1][mb] * c[q2][0];
+  const T p1 = c[q1][mb] * c[q2][mf] + c[q1][mb | mf] * c[q2][0];
+  const T p2 = c[q1][mb | mf] * c[q2][mf];
+  const T a = (T(2) * lam2 + lam1 * lam1) * T(0.125), bq = (T(2) * lam2 - lam1 * lam1) * T(0.125), l1 = lam1 * T(0.0625);
+  LineS<T> s;
+  const T base = T(0.5 / 32) * p0 + a * p2;
+  s.vp = base + l1 * p1;
+  s.vm = base - l1 * p1;
+  s.u = T(0.5 / 32) * p0 + bq * p2;
+  return s;
+}
+
 // ---------------------------------------------------------------------------
 // Output staging.  The metric arrays are AoS (80-B / 72-B elements, layout of the Julia arrays): a lane
 // storing its own element touches one 128-B line per lane and instruction, which saturates the L1TEX
@@ -442,7 +536,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
-  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int64_t j = WY == 1 ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;  // whole warp
   const int64_t i0 = (int64_t)blockIdx.x * WARP_OUT;  // first output cell of the warp (lane 1)
   const int64_t i = i0 + lane - 1;
@@ -466,7 +560,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   const bool st_cj = CMP || (GEN && O.cjac), st_ca = CMP || (GEN && O.cactive[0]);
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
-  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * xi_warp_vals<T, MODE>;
+  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + (WY == 1 ? 0 : threadIdx.y) * xi_warp_vals<T, MODE>;
   T* const sg = wsm + ring_vals<4, 4>;
   T* const sg_cf = sg, * const sg_ci = sg + stage_len<T, 10>, * const sg_ff = sg + 2 * stage_len<T, 10>,
          * const sg_fi = sg + 3 * stage_len<T, 10>, * const sg_fc = sg + 4 * stage_len<T, 10>;
@@ -700,14 +794,16 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
   }
   if (!full) return;
   T c[3][8];
-  taylor_from_e(E1, E2, c);  // one Taylor expansion of the cell serves the line scalars and the L / R states
+  taylor_raw_e(E1, E2, c);  // one (raw) Taylor expansion of the cell serves the line scalars and the L / R states
 #pragma unroll
   for (int col = 0; col < 3; ++col) {
     const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
-    o.ln[col] = line_from_taylor(c, q1, q2, 2, 0, lam1, lam2);
-    o.ln[3 + col] = line_from_taylor(c, q1, q2, 2, 1, lam1, lam2);
+    o.ln[col] = line_from_taylor_raw(c, q1, q2, 2, 0, lam1, lam2);
+    o.ln[3 + col] = line_from_taylor_raw(c, q1, q2, 2, 1, lam1, lam2);
   }
   if (GF) {
+    // raw F = 4 F, raw dF/d(zeta) = 2 dF/d(zeta): inv gives G / 4, and with (2 lam1, 4 lam2) the states come out as
+    // L / 4, R / 4 (G' ~ G F' G, G'' ~ G F' G F' G); the face average folds the 4 back in
     T F[3][3], G[3][3], Fa[3], Fb[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
@@ -717,7 +813,7 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
       Fb[q] = c[q][6];  // column eta
     }
     inv3(F, G);
-    ginv_states3_ax<2>(G, Fa, Fb, lam1, lam2, o.L, o.R);
+    ginv_states3_ax<2>(G, Fa, Fb, T(2) * lam1, T(4) * lam2, o.L, o.R);
   }
 }
 
@@ -726,9 +822,9 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
 template <class T, int MODE> constexpr int zeta_warp_vals =
-    ring_vals<4, 4> + (MODE == MODE_COMPACT ? 0 : 2 * stage_len<T, 10> + stage_len<T, 9>);
+    RingV<T, 4, 4>::VALS + (MODE == MODE_COMPACT ? 0 : 2 * stage_len<T, 10> + stage_len<T, 9>);
 template <class T, int SCH, bool SWAP, int MODE>
-__global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_ZETA_MINB) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
+__global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_ZETA_MINB) * 4 / ZWY) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
   constexpr bool GF = true;
   constexpr int AX = SWAP ? 1 : 2;  // face axis written
@@ -737,20 +833,19 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   //   wpe, wpx : W+ of the cell below the face (eta-difference / xi-face polynomials)
   //   F0..F2   : line stencil pipeline.  The front cell m+1 contributes V- to the face m-1, (2U - V-) to m,
   //              (V+ - 2U) to m+1 and -V+ to m+2, so the conserved metrics of the face m-1 are completed (and
-  //              stored) in step m; F0, F1, F2 are the partial sums of the faces m-1, m, m+1 at step entry
+  //              stored) in step m; F0, F1, -F2 are the partial sums of the faces m-1, m, m+1 at step entry
   //   GhP      : conserved metrics of the face m-1 without the V- term (kernel labelling)
   //   Lpk      : L state of the reconstructed inverse Jacobian of the cell below the face
   T wpe[6], wpx[6], F0[6], F1[6], F2[6], GhP[3][3], Lpk[9];
-  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * zeta_warp_vals<T, MODE>;
-  T* const stg = wsm + ring_vals<4, 4>;
+  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + (ZWY == 1 ? 0 : threadIdx.y) * zeta_warp_vals<T, MODE>;
+  using RingT = RingV<T, 4, 4>;
+  T* const stg = wsm + RingT::VALS;
   T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
-  using RingT = Ring<T, 4, 4>;
-  const RingT R{wsm};
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
   const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
   const int64_t nw2 = SWAP ? D.nw[1] : D.nw[2];  // extent of the marching axis
-  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int64_t j = ZWY == 1 ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;
   const int64_t i0 = (int64_t)blockIdx.x * ZETA_OUT;  // first output cell of the warp (lane 1)
   const int64_t i = i0 + lane - 1;
@@ -758,6 +853,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   const bool out_ok = lane >= 1 && lane <= ZETA_OUT && i < nw0;
   const int nvalid = (int)(nw0 - i0 < ZETA_OUT ? nw0 - i0 : ZETA_OUT);
   const int rel = lane - 1;
+  // staging slot of this lane: every lane writes (no branch); slot 31 is never sent (31 output cells per warp)
+  const int srel = lane == 0 ? 31 : lane - 1;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
@@ -770,13 +867,13 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   // cell strides of the row axis and the marching axis in the output arrays
   const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
 
-  // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2);
+  // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c (after the phase shift) = node column i0 - 1 + c;
   // planes k0+1 .. k0+3 are primed here, plane m+4 follows at the top of step m (4 slots: no barrier inside a step)
-  auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
-  const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32 + (lane & 1)) + (Ix)j * N.s1 + N.s2;
+  const int ph = (int)(i0 & (RingT::VEC - 1));
+  const RingT R{wsm + ph};
+  const Ix rg0 = (Ix)(i0 - ph + RingT::VEC * lane) + (Ix)j * N.s1 + N.s2;
 #pragma unroll
-  for (int pp = 1; pp <= 3; ++pp)
-    R.template fetch<2>(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
+  for (int pp = 1; pp <= 3; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, lane, ph);
   cp_async_commit();
   // carried state of the first step
   {
@@ -785,7 +882,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
       LineS<T> lm[6];  // cell k0 - 1
       zlines(S0, -1, lam1, lam2, lm);
 #pragma unroll
-      for (int e = 0; e < 6; ++e) F2[e] = -lm[e].vp;
+      for (int e = 0; e < 6; ++e) F2[e] = lm[e].vp;
     }
     CellZ<T> c0;  // cell k0
     cellz_compute<T, SCH, GF>(S0, full, lam1, lam2, c0);
@@ -798,8 +895,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
 #pragma unroll
       for (int e = 0; e < 6; ++e) {  // the face k0-1 belongs to the previous chunk: F0 is not needed
         F0[e] = T(0);
-        F1[e] = F2[e] + (c0.ln[e].vp - T(2) * c0.ln[e].u);
-        F2[e] = -c0.ln[e].vp;
+        F1[e] = (c0.ln[e].vp - T(2) * c0.ln[e].u) - F2[e];
+        F2[e] = c0.ln[e].vp;
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r)
@@ -831,18 +928,22 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
       }
     }
     Stage<T, 9> Sc(O.face_cons[AX], cl0_prev, sg_fc);
-    if (out_ok) put9(Sc.slot(rel), Go);
+    put9(Sc.slot(srel), Go);
     return Sc;
   };
+#pragma unroll(Z_UNROLL)
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this step
     const int64_t cl = cl0 + rel;
-    // the TMA unit has finished reading last step's staging buffers; node planes m+1 .. m+3 have landed
-    if (lane == 0) bulk_wait_read();
+    // the TMA unit has finished reading last step's staging buffers (lanes other than 0 own no bulk groups: their
+    // wait returns at once); node planes m+1 .. m+3 have landed
+#ifndef CG_Z_LATE_WAIT
+    bulk_wait_read();
+#endif
     cp_async_wait_all();
     __syncwarp();
     if (m + 1 < k1) {  // plane m+4 (first needed in the next step) into the slot plane m has left
-      R.template fetch<2>(N, (int)(m + 4), rg0 + (Ix)(m + 4) * N.s2, rgx + (Ix)(m + 4) * N.s2, lane);
+      R.fetch(N, (int)(m + 4), rg0 + (Ix)(m + 4) * N.s2, lane, ph);
       cp_async_commit();
     }
     const RingSrc<T, RingT> S{R, (int)(m + 1), lane};
@@ -875,6 +976,10 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
     }
     if (!full) continue;
     Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
+#ifdef CG_Z_LATE_WAIT
+    bulk_wait_read();
+    __syncwarp();
+#endif
     // zeta line stencil: the front cell's V- completes the face m-1 (stored now, one step late)
     T vm[6];
 #pragma unroll
@@ -883,8 +988,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
       F0[e] = F1[e] + (T(2) * cf.ln[e].u - cf.ln[e].vm);
-      F1[e] = F2[e] + (cf.ln[e].vp - T(2) * cf.ln[e].u);
-      F2[e] = -cf.ln[e].vp;
+      F1[e] = (cf.ln[e].vp - T(2) * cf.ln[e].u) - F2[e];
+      F2[e] = cf.ln[e].vp;
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -896,7 +1001,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
-          Gf[r][cc] = T(0.5) * (Lpk[3 * r + cc] + cf.R[r][cc]);
+          Gf[r][cc] = T(2) * (Lpk[3 * r + cc] + cf.R[r][cc]);  // states carry 1/4 (cellz_compute)
           Lpk[3 * r + cc] = cf.L[r][cc];
         }
       T Jf = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
@@ -908,10 +1013,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
           T t2 = Gf[1][q]; Gf[1][q] = Gf[2][q]; Gf[2][q] = t2;
         }
       }
-      if (out_ok) {
-        put10(Sf.slot(rel), Ff, Jf);
-        put10(Si.slot(rel), Gf, Jf);
-      }
+      put10(Sf.slot(srel), Ff, Jf);
+      put10(Si.slot(srel), Gf, Jf);
     }
     // ---- one flush point: staged arrays -> TMA ----
     fence_async_smem();
@@ -1303,9 +1406,9 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   };
   cudaStream_t zst = st;  // stream of the next eta / zeta launch
   auto launch_zeta = [&](auto kern, int warp_vals, dim3 grid, int chunk) {
-    const int smem = WY * warp_vals * (int)sizeof(T);
+    const int smem = ZWY * warp_vals * (int)sizeof(T);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    kern<<<grid, block, smem, zst>>>(D, ex, ey, ez, O, chunk);
+    kern<<<grid, dim3(32, ZWY), smem, zst>>>(D, ex, ey, ez, O, chunk);
   };
   Fork* fk = (face && (mask & 7) == 7) ? fork_streams() : nullptr;
   if (fk) {
@@ -1328,7 +1431,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   if ((mask & 2) && face) {
     if (fk) zst = fk->s[0];
     // eta faces with the zeta kernel's code, marching along j: rows = k planes
-    const unsigned gy = (unsigned)((D.nw[2] + WY - 1) / WY);
+    const unsigned gy = (unsigned)((D.nw[2] + ZWY - 1) / ZWY);
     const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
     if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, true, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, jchunk);
@@ -1338,7 +1441,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   }
   if ((mask & 4) && face) {
     if (fk) zst = fk->s[1];
-    const unsigned gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+    const unsigned gy = (unsigned)((D.nw[1] + ZWY - 1) / ZWY);
     const int kchunk = chunk_of((int64_t)gxz * gy, D.nw[2]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
     if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, false, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, kchunk);

@@ -47,11 +47,19 @@ template <class T> CG_HD Form4<T> form_dif(const Form4<T>& hi, const Form4<T>& l
 }
 
 // 3x3 helpers; M[r][c] row-major in registers
-// 1/x: on the device the correctly rounded reciprocal intrinsic (same bits as the IEEE division, far fewer
-// instructions than the generic a/b routine)
+// 1/x on the device: MUFU.RCP64H seed (rcp.approx, ~2^-20) + two Newton steps, straight-line code (no
+// special-case branch / slow-path call like the generic division or __drcp_rn; <= 1 ulp, x = 0 gives NaN)
 CG_HD double rcp(double x) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(CG_RCP_RN)
   return __drcp_rn(x);
+#elif defined(__CUDA_ARCH__)
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
 #else
   return 1.0 / x;
 #endif

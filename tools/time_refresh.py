@@ -11,7 +11,10 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 host = bench.wavy_slab_3d(n + 1, n + 1, n + 1, 0, n + 1)
 dev = [torch.from_numpy(a).cuda() for a in host]
 g = cg.DiscreteGrid(*dev, 5, cache_mode="lazy")
-for name, fn in (("cell", cg.refresh_cell_metrics), ("face", cg.refresh_face_metrics), ("cell+face", cg.refresh_metrics)):
+which = (("cell", cg.refresh_cell_metrics), ("face", cg.refresh_face_metrics), ("cell+face", cg.refresh_metrics))
+if len(sys.argv) > 2 and sys.argv[2] == "fused":
+    which = which[2:]
+for name, fn in which:
     ts = []
     for _ in range(4):
         fn(g)
