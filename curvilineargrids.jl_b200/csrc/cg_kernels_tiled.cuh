@@ -42,10 +42,31 @@ constexpr int NT = 32 * WY;     // threads per block
 // The eta / zeta kernels run ONE warp per block: row index, chunk and every staging / TMA address are then functions
 // of blockIdx alone, i.e. they live in uniform registers (UBLKCP straight from UR operands, no R2UR loops).
 constexpr int ZWY = CG_ZWY;
+#ifndef CG_XWY
+#define CG_XWY 4
+#endif
+constexpr int XWY = CG_XWY;  // warps per block of the xi kernel
+constexpr int XNT = 32 * XWY;
+#ifndef CG_JFAST
+#define CG_JFAST 0
+#endif
+// one-warp blocks: 1 = blockIdx.x counts rows (fastest), blockIdx.y the xi segments, so the blocks resident on one
+// SM are neighbouring rows and share node rows in L1
+constexpr int JFAST = CG_JFAST;
 #ifndef CG_Z_UNROLL
 #define CG_Z_UNROLL 1
 #endif
 constexpr int Z_UNROLL = CG_Z_UNROLL;  // unroll factor of the eta / zeta marching loop
+#ifndef CG_Z_SLOTS
+#define CG_Z_SLOTS 3
+#endif
+#ifndef CG_Z_DBUF
+#define CG_Z_DBUF 0
+#endif
+// eta / zeta kernels: node ring slots (3: the plane needed in the next step is fetched now; 4: one more step of
+// slack) and double-buffered output staging (the TMA unit may still read last step's chunks while this step stages)
+constexpr int Z_SLOTS = CG_Z_SLOTS;
+constexpr int Z_DBUF = CG_Z_DBUF;
 constexpr int ZNT = 32 * ZWY;
 constexpr int WARP_OUT = 29;  // output cells per warp along xi (kernels that need lanes -1, +1, +2)
 constexpr int ZETA_OUT = 31;  // the zeta / eta(SWAP) kernel only needs lane -1
@@ -447,13 +468,22 @@ CG_D LineS<T> line_from_taylor_raw(const T (&c)[3][8], int q1, int q2, int f, in
 // plain stores.
 // ---------------------------------------------------------------------------
 CG_D void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+#ifdef CG_NO_STORE  // experiment: time the kernels without their bulk stores
+  if (bytes != 0xffffffffu) return;
+#endif
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
                "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                : "memory");
 }
 CG_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING shared memory (the staging buffers may be rewritten)
-CG_D void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+CG_D void bulk_wait_read() {
+#ifndef CG_NO_WAIT  // experiment: results are wrong without the wait, only the timing is of interest
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#endif
+}
+// ... all but the most recent group (double-buffered staging: the group of two steps ago used this buffer)
+CG_D void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 CG_D void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <class T, int E> constexpr int stage_len = 32 * E + 16 / (int)sizeof(T);  // values per array
@@ -529,21 +559,24 @@ struct March {
 // dynamic shared memory: per warp, staging buffers of the five AoS arrays this kernel writes
 // per-warp shared memory: [node ring | staging buffers]; the COMPACT configuration stages nothing
 template <class T, int MODE> constexpr int xi_warp_vals =
-    ring_vals<4, 4> + (MODE == MODE_COMPACT ? 0 : 4 * stage_len<T, 10> + stage_len<T, 9>);
+    RingV<T, 4, 4>::VALS + (MODE == MODE_COMPACT ? 0 : 4 * stage_len<T, 10> + stage_len<T, 9>);
 template <class T, int SCH, int MODE>
-__global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
+__global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) * 4 / XWY) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
                                                          MetricOut<T> O, int what, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
-  const int64_t j = WY == 1 ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const unsigned bx = (XWY == 1 && JFAST) ? blockIdx.y : blockIdx.x, by = (XWY == 1 && JFAST) ? blockIdx.x : blockIdx.y;
+  const int64_t j = XWY == 1 ? (int64_t)by : (int64_t)by * blockDim.y + threadIdx.y;
   if (j >= nw1) return;  // whole warp
-  const int64_t i0 = (int64_t)blockIdx.x * WARP_OUT;  // first output cell of the warp (lane 1)
+  const int64_t i0 = (int64_t)bx * WARP_OUT;  // first output cell of the warp (lane 1)
   const int64_t i = i0 + lane - 1;
   const int64_t ic = i > nw0 + 1 ? nw0 + 1 : i;
   const bool out_ok = lane >= 1 && lane <= WARP_OUT && i < nw0;
   const int nvalid = (int)(nw0 - i0 < WARP_OUT ? nw0 - i0 : WARP_OUT);
   const int rel = lane - 1;
+  // staging slot of this lane: every lane writes (no branch); the slots 29 .. 31 are never sent
+  const int srel = lane == 0 ? 31 : lane - 1;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
@@ -560,16 +593,18 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
   const bool st_cj = CMP || (GEN && O.cjac), st_ca = CMP || (GEN && O.cactive[0]);
   const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
   const int64_t cs1 = nw0, cs2 = nw0 * nw1;
-  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + (WY == 1 ? 0 : threadIdx.y) * xi_warp_vals<T, MODE>;
-  T* const sg = wsm + ring_vals<4, 4>;
+  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + (XWY == 1 ? 0 : threadIdx.y) * xi_warp_vals<T, MODE>;
+  using RingT = RingV<T, 4, 4>;
+  T* const sg = wsm + RingT::VALS;
   T* const sg_cf = sg, * const sg_ci = sg + stage_len<T, 10>, * const sg_ff = sg + 2 * stage_len<T, 10>,
          * const sg_fi = sg + 3 * stage_len<T, 10>, * const sg_fc = sg + 4 * stage_len<T, 10>;
-  // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c = node column min(i0 - 1 + c, nw0 + 2)
-  const Ring<T, 4, 4> R{wsm};
-  auto ring_col = [&](int c) { const int64_t v = i0 - 1 + c; return (Ix)((v > nw0 + 2 ? nw0 + 2 : v) + 1); };
-  const Ix rg0 = ring_col(lane) + (Ix)j * N.s1 + N.s2, rgx = ring_col(32) + (Ix)j * N.s1 + N.s2;  // plane 0, row j-1
+  // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c (after the phase shift) = node column i0 - 1 + c,
+  // fetched in 16-byte pieces (RingV)
+  const int ph = (int)(i0 & (RingT::VEC - 1));
+  const RingT R{wsm + ph};
+  const Ix rg0 = (Ix)(i0 - ph + RingT::VEC * lane) + (Ix)j * N.s1 + N.s2;  // plane 0, row j-1
 #pragma unroll
-  for (int pp = 0; pp < 3; ++pp) R.template fetch<1>(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, rgx + (Ix)(k0 + pp) * N.s2, lane);
+  for (int pp = 0; pp < 3; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, lane, ph);
   cp_async_commit();
 
   const T dl0 = clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), dl1 = clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]);
@@ -588,11 +623,11 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
     const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this plane
     const int64_t cl = cl0 + rel;
     // the TMA unit has finished reading last step's staging buffers; the node planes m .. m+2 have landed
-    if (lane == 0) bulk_wait_read();
+    bulk_wait_read();  // lanes other than 0 own no bulk groups: their wait returns at once
     cp_async_wait_all();
     __syncwarp();
     if (m + 1 < k1) {  // plane m+3 (first needed in the next step) into the slot plane m-1 has left
-      R.template fetch<1>(N, (int)(m + 3), rg0 + (Ix)(m + 3) * N.s2, rgx + (Ix)(m + 3) * N.s2, lane);
+      R.fetch(N, (int)(m + 3), rg0 + (Ix)(m + 3) * N.s2, lane, ph);
       cp_async_commit();
     }
     const int pm = (int)m;
@@ -630,8 +665,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
             }
           J = det3(Ff);
         }
-        if (st_cf && out_ok) put10(Scf.slot(rel), Ff, J);
-        if (st_ci && out_ok) put10(Sci.slot(rel), G, J);
+        if (st_cf) put10(Scf.slot(srel), Ff, J);
+        if (st_ci) put10(Sci.slot(srel), G, J);
         if (st_cj && out_ok) O.cjac[cl] = J;
       }
       if (do_gf) {
@@ -648,10 +683,8 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
 #pragma unroll
           for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(0.5) * (L[r][cc] + shfl_dn(R[r][cc], 1));
         T Jf = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
-        if (out_ok) {
-          put10(Sff.slot(rel), Ff, Jf);
-          put10(Sfi.slot(rel), Gf, Jf);
-        }
+        put10(Sff.slot(srel), Ff, Jf);
+        put10(Sfi.slot(srel), Gf, Jf);
       }
     }
     if (do_cons) {
@@ -709,7 +742,7 @@ __global__ void __launch_bounds__(NT, MODE == MODE_COMPACT ? CG_COMPACT_MINB : C
             else Gh[2][col] -= T(0.5) * v;
           }
         }
-        if (out_ok) put9(Sfc.slot(rel), Gh);
+        put9(Sfc.slot(srel), Gh);
       }
     }
     z0 = z1;
@@ -821,8 +854,9 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
 // the strides of eta and zeta are exchanged, i.e. the kernel works in the left-handed labelling
 // (xi, eta' = zeta, zeta' = eta).  In that labelling every Thomas-Lombard entry changes sign and the rows /
 // Jacobian columns eta <-> zeta are exchanged; the stores undo both.
+template <class T> constexpr int zeta_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9>;
 template <class T, int MODE> constexpr int zeta_warp_vals =
-    RingV<T, 4, 4>::VALS + (MODE == MODE_COMPACT ? 0 : 2 * stage_len<T, 10> + stage_len<T, 9>);
+    RingV<T, 4, Z_SLOTS>::VALS + (MODE == MODE_COMPACT ? 0 : (1 + Z_DBUF) * zeta_stage_vals<T>);
 template <class T, int SCH, bool SWAP, int MODE>
 __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_ZETA_MINB) * 4 / ZWY) k_face_zeta(Dims D, const T* ex, const T* ey, const T* ez,
                                                                 MetricOut<T> O, int kchunk) {
@@ -838,16 +872,16 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   //   Lpk      : L state of the reconstructed inverse Jacobian of the cell below the face
   T wpe[6], wpx[6], F0[6], F1[6], F2[6], GhP[3][3], Lpk[9];
   T* const wsm = reinterpret_cast<T*>(cg_dyn_smem) + (ZWY == 1 ? 0 : threadIdx.y) * zeta_warp_vals<T, MODE>;
-  using RingT = RingV<T, 4, 4>;
+  using RingT = RingV<T, 4, Z_SLOTS>;
   T* const stg = wsm + RingT::VALS;
-  T* const sg_ff = stg, * const sg_fi = stg + stage_len<T, 10>, * const sg_fc = stg + 2 * stage_len<T, 10>;
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
   const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
   const int64_t nw2 = SWAP ? D.nw[1] : D.nw[2];  // extent of the marching axis
-  const int64_t j = ZWY == 1 ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const unsigned bx = (ZWY == 1 && JFAST) ? blockIdx.y : blockIdx.x, by = (ZWY == 1 && JFAST) ? blockIdx.x : blockIdx.y;
+  const int64_t j = ZWY == 1 ? (int64_t)by : (int64_t)by * blockDim.y + threadIdx.y;
   if (j >= nw1) return;
-  const int64_t i0 = (int64_t)blockIdx.x * ZETA_OUT;  // first output cell of the warp (lane 1)
+  const int64_t i0 = (int64_t)bx * ZETA_OUT;  // first output cell of the warp (lane 1)
   const int64_t i = i0 + lane - 1;
   const int64_t ic = i > nw0 ? nw0 : i;  // this kernel reads node columns ic .. ic+2
   const bool out_ok = lane >= 1 && lane <= ZETA_OUT && i < nw0;
@@ -868,12 +902,13 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   const int64_t cs1 = SWAP ? D.nw[0] * D.nw[1] : D.nw[0], cs2 = SWAP ? D.nw[0] : D.nw[0] * D.nw[1];
 
   // node ring: ring rows 0..3 = node rows j-1 .. j+2, ring column c (after the phase shift) = node column i0 - 1 + c;
-  // planes k0+1 .. k0+3 are primed here, plane m+4 follows at the top of step m (4 slots: no barrier inside a step)
+  // planes k0+1 .. k0+Z_SLOTS-1 are primed here, plane m+Z_SLOTS follows at the top of step m into the slot the plane m
+  // has left (no barrier inside a step)
   const int ph = (int)(i0 & (RingT::VEC - 1));
   const RingT R{wsm + ph};
   const Ix rg0 = (Ix)(i0 - ph + RingT::VEC * lane) + (Ix)j * N.s1 + N.s2;
 #pragma unroll
-  for (int pp = 1; pp <= 3; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, lane, ph);
+  for (int pp = 1; pp < Z_SLOTS; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, lane, ph);
   cp_async_commit();
   // carried state of the first step
   {
@@ -908,7 +943,7 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
     }
   }
   // completes the conserved metrics of the face below (GhP + V- term), stages and hands them to the TMA unit
-  auto finish_cons = [&](const T (&vm)[6], int64_t cl0_prev) {
+  auto finish_cons = [&](const T (&vm)[6], int64_t cl0_prev, T* sg_fc) {
     T Go[3][3];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -935,17 +970,18 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t cl0 = i0 + j * cs1 + m * cs2;  // first output cell of the warp in this step
     const int64_t cl = cl0 + rel;
-    // the TMA unit has finished reading last step's staging buffers (lanes other than 0 own no bulk groups: their
-    // wait returns at once); node planes m+1 .. m+3 have landed
-#ifndef CG_Z_LATE_WAIT
-    bulk_wait_read();
-#endif
+    // the TMA unit has finished reading the staging buffers this step writes (lanes other than 0 own no bulk groups:
+    // their wait returns at once); the node planes m+1, m+2 have landed
+    if (Z_DBUF) bulk_wait_read1();
+    else bulk_wait_read();
     cp_async_wait_all();
     __syncwarp();
-    if (m + 1 < k1) {  // plane m+4 (first needed in the next step) into the slot plane m has left
-      R.fetch(N, (int)(m + 4), rg0 + (Ix)(m + 4) * N.s2, lane, ph);
+    if (m + 1 < k1) {  // the next plane the ring lacks, into the slot the plane m has left
+      R.fetch(N, (int)(m + Z_SLOTS), rg0 + (Ix)(m + Z_SLOTS) * N.s2, lane, ph);
       cp_async_commit();
     }
+    T* const sgm = stg + (Z_DBUF ? (int)((m - k0) & 1) * zeta_stage_vals<T> : 0);
+    T* const sg_ff = sgm, * const sg_fi = sgm + stage_len<T, 10>, * const sg_fc = sgm + 2 * stage_len<T, 10>;
     const RingSrc<T, RingT> S{R, (int)(m + 1), lane};
     CellZ<T> cf;  // front cell m + 1
     cellz_compute<T, SCH, GF>(S, full, lam1, lam2, cf);
@@ -976,15 +1012,11 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
     }
     if (!full) continue;
     Stage<T, 10> Sf(O.face_fwd[AX], cl0, sg_ff), Si(O.face_inv[AX], cl0, sg_fi);
-#ifdef CG_Z_LATE_WAIT
-    bulk_wait_read();
-    __syncwarp();
-#endif
     // zeta line stencil: the front cell's V- completes the face m-1 (stored now, one step late)
     T vm[6];
 #pragma unroll
     for (int e = 0; e < 6; ++e) vm[e] = cf.ln[e].vm;
-    const Stage<T, 9> Sc = finish_cons(vm, cl0 - cs2);
+    const Stage<T, 9> Sc = finish_cons(vm, cl0 - cs2, sg_fc);
 #pragma unroll
     for (int e = 0; e < 6; ++e) {
       F0[e] = F1[e] + (T(2) * cf.ln[e].u - cf.ln[e].vm);
@@ -1036,7 +1068,7 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
     T vm[6];
 #pragma unroll
     for (int e = 0; e < 6; ++e) vm[e] = l2[e].vm;
-    const Stage<T, 9> Sc = finish_cons(vm, i0 + j * cs1 + (k1 - 1) * cs2);
+    const Stage<T, 9> Sc = finish_cons(vm, i0 + j * cs1 + (k1 - 1) * cs2, stg + 2 * stage_len<T, 10>);
     fence_async_smem();
     __syncwarp();
     Sc.issue(nvalid, lane);
@@ -1332,9 +1364,9 @@ inline int launch_metrics2d_tiled(const Dims& D, const T* ex, const T* ey, const
   return 1;
 }
 
-// The three face kernels write disjoint arrays.  They are launched on `st` and two helper streams (fork / join with
-// events) so that the last, partly filled wave of one kernel overlaps the first wave of the next: with 2 blocks
-// per SM and ~15 waves per kernel the tail is ~6 % of a kernel's time.  CG_CONCURRENT=0 serialises them.
+// The three face kernels write disjoint arrays.  On small grids they are launched on `st` and two helper streams
+// (fork / join with events) so that the last, partly filled wave of one kernel overlaps the first wave of the next.
+// CG_CONCURRENT=0 serialises them always.
 struct Fork {
   cudaStream_t s[2];
   cudaEvent_t start, done[2];
@@ -1380,7 +1412,6 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     }
     return c;
   };
-  dim3 block(32, WY);
   int n = 0;
   const bool face = what & 2;
   // opt in to > 48 KB of shared memory (per device, cheap: set on every launch)
@@ -1400,24 +1431,29 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   const bool is_cell_only = (what & 3) == 1 && no_compact && O.cell_fwd && O.cell_inv;
   const int zmode = (is_full || is_face_only) ? MODE_FULL : mode;  // eta / zeta kernels
   auto launch_xi = [&](auto kern, int warp_vals, dim3 grid, int kchunk) {
-    const int smem = WY * warp_vals * (int)sizeof(T);
+    const int smem = XWY * warp_vals * (int)sizeof(T);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    kern<<<grid, block, smem, st>>>(D, ex, ey, ez, O, what, kchunk);
+    if (XWY == 1 && JFAST) grid = dim3(grid.y, grid.x, grid.z);
+    kern<<<grid, dim3(32, XWY), smem, st>>>(D, ex, ey, ez, O, what, kchunk);
   };
   cudaStream_t zst = st;  // stream of the next eta / zeta launch
   auto launch_zeta = [&](auto kern, int warp_vals, dim3 grid, int chunk) {
     const int smem = ZWY * warp_vals * (int)sizeof(T);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ZWY == 1 && JFAST) grid = dim3(grid.y, grid.x, grid.z);
     kern<<<grid, dim3(32, ZWY), smem, zst>>>(D, ex, ey, ez, O, chunk);
   };
-  Fork* fk = (face && (mask & 7) == 7) ? fork_streams() : nullptr;
+  // small grids only: a large grid fills the GPU for many waves per kernel and the one-warp blocks of the eta / zeta
+  // kernels leave short tails; serial launches measured equal or better there (512^3: 28.6 vs 29.2 ms)
+  const bool small_grid = D.nw[0] * D.nw[1] * D.nw[2] < (int64_t)(1 << 24);
+  Fork* fk = (face && (mask & 7) == 7 && small_grid) ? fork_streams() : nullptr;
   if (fk) {
     cudaEventRecord(fk->start, st);
     cudaStreamWaitEvent(fk->s[0], fk->start, 0);
     cudaStreamWaitEvent(fk->s[1], fk->start, 0);
   }
   if ((mask & 1) && ((what & 1) || face)) {
-    const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+    const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + XWY - 1) / XWY);
     const int kchunk = chunk_of((int64_t)gx * gy, D.nw[2]);
     const dim3 grid(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
     if (mode == MODE_FULL) launch_xi(k_face_xi<T, SCH, MODE_FULL>, xi_warp_vals<T, MODE_FULL>, grid, kchunk);
