@@ -93,6 +93,8 @@ struct cg_grid {
       D.w0[d] = w0[d] + goff[d];
       D.gn[d] = ncell[d];
     }
+    D.r0 = 0;
+    D.r1 = nw[2];
     return D;
   }
 };
@@ -147,7 +149,7 @@ int launch_blocks(int64_t n, int threads) {
 }
 
 template <class T>
-int pad_nodes(cg_grid* g, cudaStream_t st) {
+int pad_nodes(cg_grid* g, cudaStream_t st, int64_t e_lo = 0, int64_t e_hi = -1) {
   const size_t bytes = (size_t)g->next() * sizeof(T);
   for (int q = 0; q < g->dim; ++q) {
     int rc = ensure(g, g->ext[q], bytes);
@@ -166,11 +168,13 @@ int pad_nodes(cg_grid* g, cudaStream_t st) {
     s *= g->src_count[d];
   }
   {
-    const unsigned rows = (unsigned)(D.ne[1] * D.ne[2]);
+    if (e_hi < 0) e_hi = D.ne[2];  // padded planes [e_lo, e_hi) of axis 2 (3-D only; the whole array by default)
+    const unsigned rows = (unsigned)(D.ne[1] * (e_hi - e_lo));
     T *e0 = (T*)g->ext[0].p, *e1 = (T*)g->ext[1].p, *e2 = (T*)g->ext[2].p;
-    if (D.dim == 3) cg::k_pad_nodes<T, 3><<<rows, 256, 0, st>>>(D, S, e0, e1, e2);
-    else if (D.dim == 2) cg::k_pad_nodes<T, 2><<<rows, 256, 0, st>>>(D, S, e0, e1, e2);
-    else cg::k_pad_nodes<T, 1><<<rows, 256, 0, st>>>(D, S, e0, e1, e2);
+    if (rows == 0) return CG_OK;
+    if (D.dim == 3) cg::k_pad_nodes<T, 3><<<rows, 256, 0, st>>>(D, S, e0, e1, e2, (int)e_lo);
+    else if (D.dim == 2) cg::k_pad_nodes<T, 2><<<rows, 256, 0, st>>>(D, S, e0, e1, e2, 0);
+    else cg::k_pad_nodes<T, 1><<<rows, 256, 0, st>>>(D, S, e0, e1, e2, 0);
   }
   g_launches++;
   CG_CUDA(cudaGetLastError());
@@ -294,7 +298,7 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
 }
 
 template <class T>
-int eval_impl(cg_grid* g, int what, cudaStream_t st) {
+int eval_impl(cg_grid* g, int what, cudaStream_t st, int64_t k_lo = 0, int64_t k_hi = -1, bool final = true) {
   const int N = g->dim;
   if (g->kind == 0) return fail(CG_ERR_STATE, "cg_grid_eval: no nodes or mapping set");
   if (g->kind == 2) return eval_mapped<T>(g, what, st);
@@ -303,6 +307,11 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
   if (g->kind == 1)
     for (int d = 0; d < 3; ++d) D.w0[d] = g->w0[d];
   const T *ex = (const T*)g->ext[0].p, *ey = (const T*)g->ext[1].p, *ez = (const T*)g->ext[2].p;
+  const bool ranged = k_hi >= 0;
+  if (ranged) {
+    D.r0 = k_lo;
+    D.r1 = k_hi;
+  }
 
   if (what & CG_WHAT_COORDS) {
     cg::CoordOut<T> C;
@@ -336,6 +345,7 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
     // (bit0 xi+cell, bit1 eta, bit2 zeta) and the gather kernel for the rest (development cross-checks)
     int mask = g->kernel_opt == 1 ? 7 : (g->kernel_opt >= 16 ? (g->kernel_opt - 16) & 7 : 0);
     if (!cg::tiled3d_supported<T>(D, O)) mask = 0;
+    if (ranged && mask != 7) return fail(CG_ERR_ARG, "cg_grid_eval_planes needs the marching kernels (CG_OPT_KERNEL = 1)");
     if (mask != 7) {
       const int rest = (~mask & 7) | ((mask & 1) ? 0 : 8);
       cg::k_metrics3d_ref<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, ex, ey, ez, O, g->scheme, what, rest);
@@ -352,8 +362,10 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st) {
   CG_CUDA(cudaGetLastError());
   CG_CUDA(cudaEventRecord(g->ev1, st));
   g->timed = true;
-  if (what & CG_WHAT_CELL) g->valid_cell = true;
-  if (what & CG_WHAT_FACE) g->valid_face = true;
+  if (final) {
+    if (what & CG_WHAT_CELL) g->valid_cell = true;
+    if (what & CG_WHAT_FACE) g->valid_face = true;
+  }
   return CG_OK;
 }
 
@@ -575,6 +587,26 @@ int cg_grid_eval(cg_grid* g, int what, void* stream) {
                             : eval_impl<float>(g, what, (cudaStream_t)stream);
 }
 
+int cg_grid_pad_planes(cg_grid* g, int64_t e_lo, int64_t e_hi, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (g->kind != 1 || g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_pad_planes: 3-D DiscreteGrid only");
+  if (e_lo < 0 || e_hi > g->nw[2] + 4 || e_lo > e_hi) return fail(CG_ERR_ARG, "bad padded plane range [%lld, %lld)", (long long)e_lo, (long long)e_hi);
+  CG_CUDA(cudaSetDevice(g->device));
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return g->dtype == CG_F64 ? pad_nodes<double>(g, (cudaStream_t)stream, e_lo, e_hi)
+                            : pad_nodes<float>(g, (cudaStream_t)stream, e_lo, e_hi);
+}
+
+int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int final, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (what <= 0 || what > 3) return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE)", what);
+  if (g->kind != 1 || g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_eval_planes: 3-D DiscreteGrid only");
+  if (k_lo < 0 || k_hi > g->nw[2] || k_lo > k_hi) return fail(CG_ERR_ARG, "bad cell plane range [%lld, %lld)", (long long)k_lo, (long long)k_hi);
+  CG_CUDA(cudaSetDevice(g->device));
+  return g->dtype == CG_F64 ? eval_impl<double>(g, what, (cudaStream_t)stream, k_lo, k_hi, final != 0)
+                            : eval_impl<float>(g, what, (cudaStream_t)stream, k_lo, k_hi, final != 0);
+}
+
 int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid) {
   if (!g) return fail(CG_ERR_ARG, "NULL grid");
   if (cell_valid) *cell_valid = g->valid_cell;
@@ -627,6 +659,65 @@ int cg_grid_copy_out(cg_grid* g, int array, int axis, void* host_dst, size_t nby
   CG_CUDA(cudaSetDevice(g->device));
   CG_CUDA(cudaMemcpy(host_dst, b->p, bytes, cudaMemcpyDeviceToHost));
   return CG_OK;
+}
+
+extern "C++" {
+namespace {
+template <class T>
+int face_flux_bundle_t(cg_grid* g, int axis, int csys, void* mv, void* area, void* normal, cudaStream_t st) {
+  const int N = g->dim;
+  const bool compact = g->profile == CG_PROFILE_COMPACT;
+  const void* cons = compact ? g->cactive[axis].p : g->face_cons[axis].p;
+  if (!cons) return fail(CG_ERR_STATE, "conserved face metrics of axis %d are not stored", axis);
+  const T* fq[3] = {nullptr, nullptr, nullptr};
+  if (csys != 0) {
+    if (!g->valid_coords) return fail(CG_ERR_STATE, "face coordinates are not valid; call cg_grid_eval(CG_WHAT_COORDS) first");
+    for (int c = 0; c < N; ++c) fq[c] = (const T*)g->facec[axis][c].p;
+  }
+  const int64_t n = g->ncells();
+  cg::k_face_flux_bundle<T><<<launch_blocks(n, 256), 256, 0, st>>>(N, axis, csys, compact, n, (const T*)cons, fq[0], fq[1],
+                                                                    fq[2], (T*)mv, (T*)area, (T*)normal);
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+template <class T>
+int cell_volumes_t(cg_grid* g, int csys, void* vol, cudaStream_t st) {
+  const int N = g->dim;
+  const bool compact = g->profile == CG_PROFILE_COMPACT;
+  const void* J = compact ? g->cjac.p : g->cell_fwd.p;
+  if (!J) return fail(CG_ERR_STATE, "cell metrics are not stored");
+  const T* cq[3] = {nullptr, nullptr, nullptr};
+  if (csys != 0) {
+    if (!g->valid_coords) return fail(CG_ERR_STATE, "centroid coordinates are not valid; call cg_grid_eval(CG_WHAT_COORDS) first");
+    for (int c = 0; c < N; ++c) cq[c] = (const T*)g->centroid[c].p;
+  }
+  const int64_t n = g->ncells();
+  cg::k_cell_volumes<T><<<launch_blocks(n, 256), 256, 0, st>>>(N, csys, compact, n, (const T*)J, cq[0], cq[1], cq[2], (T*)vol);
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int cg_grid_face_flux_geometry(cg_grid* g, int axis, int coordsys, void* metric_vector, void* area, void* normal,
+                               void* stream) {
+  if (!g || axis < 0 || axis >= g->dim) return fail(CG_ERR_ARG, "bad grid / face axis");
+  if (coordsys < 0 || coordsys > 4) return fail(CG_ERR_ARG, "bad coordinate system id %d", coordsys);
+  if (!g->valid_face) return fail(CG_ERR_STATE, "face metrics are not valid; call cg_grid_eval first");
+  CG_CUDA(cudaSetDevice(g->device));
+  return g->dtype == CG_F64 ? face_flux_bundle_t<double>(g, axis, coordsys, metric_vector, area, normal, (cudaStream_t)stream)
+                            : face_flux_bundle_t<float>(g, axis, coordsys, metric_vector, area, normal, (cudaStream_t)stream);
+}
+
+int cg_grid_cell_volumes(cg_grid* g, int coordsys, void* volume, void* stream) {
+  if (!g || !volume) return fail(CG_ERR_ARG, "bad argument");
+  if (coordsys < 0 || coordsys > 4) return fail(CG_ERR_ARG, "bad coordinate system id %d", coordsys);
+  if (!g->valid_cell) return fail(CG_ERR_STATE, "cell metrics are not valid; call cg_grid_eval first");
+  CG_CUDA(cudaSetDevice(g->device));
+  return g->dtype == CG_F64 ? cell_volumes_t<double>(g, coordsys, volume, (cudaStream_t)stream)
+                            : cell_volumes_t<float>(g, coordsys, volume, (cudaStream_t)stream);
 }
 
 int cg_grid_gcl_max(cg_grid* g, double* out, void* stream) {

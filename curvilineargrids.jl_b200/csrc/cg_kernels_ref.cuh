@@ -24,6 +24,7 @@ struct Dims {
   int64_t se[3];    // ext node strides
   int64_t w0[3];    // window origin in global full-cell indices
   int64_t gn[3];    // global interior cell counts
+  int64_t r0, r1;   // 3-D marching kernels: window cell planes [r0, r1) of axis 2 to evaluate (default 0, nw[2])
 };
 
 template <class T>
@@ -40,11 +41,11 @@ struct NodeSrc {
 // c = clamp(m) (no cross terms).
 // ---------------------------------------------------------------------------
 template <class T, int DIM>
-__global__ void __launch_bounds__(256) k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, T* ey, T* ez) {
+__global__ void __launch_bounds__(256) k_pad_nodes(Dims D, NodeSrc<T> S, T* ex, T* ey, T* ez, int e2_lo) {
   // one block per ext row (j, k); threads stride over i.  DIM is a template parameter so that every
   // per-axis quantity lives in a register (a runtime dimension count put them in local memory).
   const int64_t e1 = DIM > 1 ? (int64_t)(blockIdx.x % (unsigned)D.ne[1]) : 0;
-  const int64_t e2 = DIM > 2 ? (int64_t)(blockIdx.x / (unsigned)D.ne[1]) : 0;
+  const int64_t e2 = DIM > 2 ? (int64_t)(blockIdx.x / (unsigned)D.ne[1]) + e2_lo : 0;  // e2_lo: first padded plane
   int64_t base_jk = 0, off1 = 0, off2 = 0, nb1 = 0, nb2 = 0;
   if (DIM > 1) {
     const int64_t m = D.w0[1] + e1 - 1 - D.nhalo;
@@ -554,6 +555,94 @@ __global__ void k_gcl(Dims D, const T* c0, const T* c1, const T* c2, int compact
       v = w > v ? w : v;
     }
     if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out_bits + c, (unsigned long long)__double_as_longlong(v));
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Solver-facing bundles: face_flux_geometry (face_geometry.jl:393-416) and cellvolume
+// (generation.jl:615-726, 942-990) for every cell of the window, SoA.
+//   metric vector of the face I+1/2 on `axis` = component_scale(q_face) .* conserved[axis][I][axis, :]
+//   (conservation_face_metric_component_scale, face_geometry.jl:302-332), area = |mv|, normal = mv / area;
+//   the low face of cell I is the negative of the entry I - e_axis (face_geometry.jl:369-373, 410).
+//   volume = conservation_cell_metric_scale(q_centroid) * |det F_cell| (face_geometry.jl:277-300).
+// csys: 0 unit scale, 1 CylindricalCS, 2 AxisymmetricCS{:x}, 3 AxisymmetricCS{:y}, 4 SphericalCS + SphericalBasis
+// ---------------------------------------------------------------------------
+template <class T>
+CG_HD T cell_scale_of(int csys, int N, const T (&q)[3]) {
+  const T pi = T(3.14159265358979323846);
+  switch (csys) {
+    case 1: return T(2) * pi * fabs(q[0]);
+    case 2: return N == 2 ? T(2) * pi * fabs(q[1]) : T(1);
+    case 3: return N == 2 ? T(2) * pi * fabs(q[0]) : T(1);
+    case 4:
+      if (N == 1) return T(4) * pi * q[0] * q[0];
+      if (N == 2) return T(2) * pi * q[0] * q[0] * sin(q[1]);
+      return q[0] * q[0] * sin(q[1]);
+    default: return T(1);
+  }
+}
+template <class T>
+CG_HD void face_scale_of(int csys, int N, const T (&q)[3], T (&sc)[3]) {
+  if (csys == 4) {
+    const T pi = T(3.14159265358979323846);
+    const T r = fabs(q[0]);
+    if (N == 1) {
+      sc[0] = T(4) * pi * r * r;
+    } else if (N == 2) {
+      const T st = sin(q[1]);
+      sc[0] = T(2) * pi * r * r * st;
+      sc[1] = T(2) * pi * r * st;
+    } else {
+      const T st = sin(q[1]);
+      sc[0] = r * r * st;
+      sc[1] = r * st;
+      sc[2] = r;
+    }
+    return;
+  }
+  const T s = cell_scale_of(csys, N, q);
+  sc[0] = sc[1] = sc[2] = s;
+}
+// cons: FULL profile conserved array of `axis` ([cell][N*N], column-major) or the COMPACT active row ([cell][N]);
+// fq[c]: face coordinate c of `axis` (may be null when csys == 0); outputs [c][cell] / [cell], any may be null
+template <class T>
+__global__ void __launch_bounds__(256) k_face_flux_bundle(int N, int axis, int csys, int compact, int64_t ncell,
+                                                          const T* __restrict__ cons, const T* fq0, const T* fq1,
+                                                          const T* fq2, T* mv, T* area, T* normal) {
+  const T* FQ[3] = {fq0, fq1, fq2};
+  for (int64_t cl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cl < ncell; cl += (int64_t)gridDim.x * blockDim.x) {
+    T q[3] = {0, 0, 0}, sc[3] = {1, 1, 1}, v[3] = {0, 0, 0};
+    if (csys != 0)
+      for (int c = 0; c < N; ++c) q[c] = FQ[c][cl];
+    face_scale_of(csys, N, q, sc);
+    T a2 = 0;
+    for (int c = 0; c < N; ++c) {
+      const T row = compact ? cons[cl * N + c] : cons[cl * (N * N) + axis + N * c];
+      v[c] = sc[c] * row;
+      a2 += v[c] * v[c];
+    }
+    const T a = sqrt(a2);
+    const T ia = a > T(0) ? T(1) / a : T(0);
+    for (int c = 0; c < N; ++c) {
+      if (mv) mv[c * ncell + cl] = v[c];
+      if (normal) normal[c * ncell + cl] = v[c] * ia;
+    }
+    if (area) area[cl] = a;
+  }
+}
+// J: cell_metrics.forward ([cell][N*N+1], J last) or the COMPACT det F array ([cell])
+template <class T>
+__global__ void __launch_bounds__(256) k_cell_volumes(int N, int csys, int compact, int64_t ncell,
+                                                      const T* __restrict__ Jsrc, const T* cq0, const T* cq1,
+                                                      const T* cq2, T* vol) {
+  const T* CQ[3] = {cq0, cq1, cq2};
+  for (int64_t cl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cl < ncell; cl += (int64_t)gridDim.x * blockDim.x) {
+    T q[3] = {0, 0, 0};
+    if (csys != 0)
+      for (int c = 0; c < N; ++c) q[c] = CQ[c][cl];
+    const T J = compact ? Jsrc[cl] : Jsrc[cl * (N * N + 1) + N * N];
+    vol[cl] = cell_scale_of(csys, N, q) * fabs(J);
   }
 }
 

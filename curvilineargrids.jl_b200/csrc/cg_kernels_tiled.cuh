@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
                                                          MetricOut<T> O, int what, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
-  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1];
   const unsigned bx = (XWY == 1 && JFAST) ? blockIdx.y : blockIdx.x, by = (XWY == 1 && JFAST) ? blockIdx.x : blockIdx.y;
   const int64_t j = XWY == 1 ? (int64_t)by : (int64_t)by * blockDim.y + threadIdx.y;
   if (j >= nw1) return;  // whole warp
@@ -577,8 +577,8 @@ __global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   const int rel = lane - 1;
   // staging slot of this lane: every lane writes (no branch); the slots 29 .. 31 are never sent
   const int srel = lane == 0 ? 31 : lane - 1;
-  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
-  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  const int64_t k0 = D.r0 + (int64_t)blockIdx.z * kchunk;  // planes [D.r0, D.r1) of the window
+  const int64_t k1 = k0 + kchunk < D.r1 ? k0 + kchunk : D.r1;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
   N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
@@ -876,10 +876,11 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   T* const stg = wsm + RingT::VALS;
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0];
-  const int64_t nw1 = SWAP ? D.nw[2] : D.nw[1];  // extent of the "row" axis (threadIdx.y / blockIdx.y)
-  const int64_t nw2 = SWAP ? D.nw[1] : D.nw[2];  // extent of the marching axis
+  // "row" axis (blockIdx.y) and marching axis; the plane range [D.r0, D.r1) of axis 2 restricts whichever is zeta
+  const int64_t row0 = SWAP ? D.r0 : 0, nw1 = SWAP ? D.r1 : D.nw[1];
+  const int64_t mar0 = SWAP ? 0 : D.r0, nw2 = SWAP ? D.nw[1] : D.r1;
   const unsigned bx = (ZWY == 1 && JFAST) ? blockIdx.y : blockIdx.x, by = (ZWY == 1 && JFAST) ? blockIdx.x : blockIdx.y;
-  const int64_t j = ZWY == 1 ? (int64_t)by : (int64_t)by * blockDim.y + threadIdx.y;
+  const int64_t j = row0 + (ZWY == 1 ? (int64_t)by : (int64_t)by * blockDim.y + threadIdx.y);
   if (j >= nw1) return;
   const int64_t i0 = (int64_t)bx * ZETA_OUT;  // first output cell of the warp (lane 1)
   const int64_t i = i0 + lane - 1;
@@ -889,7 +890,7 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   const int rel = lane - 1;
   // staging slot of this lane: every lane writes (no branch); slot 31 is never sent (31 output cells per warp)
   const int srel = lane == 0 ? 31 : lane - 1;
-  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k0 = mar0 + (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
   NodeP<T> N;
   N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
@@ -1401,6 +1402,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   // enough blocks for ~30 waves (fine-grained tail, measured best at 512^3) as long as a chunk stays >= 64 steps
   // (the prologue of a chunk costs about three steps)
   const int64_t want = 148LL * 64;
+  const int64_t nplanes = D.r1 - D.r0;  // planes of axis 2 to evaluate (the whole window unless cg_grid_eval_planes)
+  if (nplanes <= 0) return 0;
   // chunk length along the marching axis: long enough to amortise the prologue
   auto chunk_of = [&](int64_t tiles, int64_t extent) {
     int c = (int)extent;
@@ -1445,7 +1448,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   };
   // small grids only: a large grid fills the GPU for many waves per kernel and the one-warp blocks of the eta / zeta
   // kernels leave short tails; serial launches measured equal or better there (512^3: 28.6 vs 29.2 ms)
-  const bool small_grid = D.nw[0] * D.nw[1] * D.nw[2] < (int64_t)(1 << 24);
+  const bool small_grid = D.nw[0] * D.nw[1] * nplanes < (int64_t)(1 << 24);
   Fork* fk = (face && (mask & 7) == 7 && small_grid) ? fork_streams() : nullptr;
   if (fk) {
     cudaEventRecord(fk->start, st);
@@ -1454,8 +1457,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   }
   if ((mask & 1) && ((what & 1) || face)) {
     const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + XWY - 1) / XWY);
-    const int kchunk = chunk_of((int64_t)gx * gy, D.nw[2]);
-    const dim3 grid(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
+    const int kchunk = chunk_of((int64_t)gx * gy, nplanes);
+    const dim3 grid(gx, gy, (unsigned)((nplanes + kchunk - 1) / kchunk));
     if (mode == MODE_FULL) launch_xi(k_face_xi<T, SCH, MODE_FULL>, xi_warp_vals<T, MODE_FULL>, grid, kchunk);
     else if (mode == MODE_COMPACT) launch_xi(k_face_xi<T, SCH, MODE_COMPACT>, xi_warp_vals<T, MODE_COMPACT>, grid, kchunk);
     else if (is_face_only) launch_xi(k_face_xi<T, SCH, MODE_FACE>, xi_warp_vals<T, MODE_FACE>, grid, kchunk);
@@ -1467,7 +1470,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   if ((mask & 2) && face) {
     if (fk) zst = fk->s[0];
     // eta faces with the zeta kernel's code, marching along j: rows = k planes
-    const unsigned gy = (unsigned)((D.nw[2] + ZWY - 1) / ZWY);
+    const unsigned gy = (unsigned)((nplanes + ZWY - 1) / ZWY);
     const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
     if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, true, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, jchunk);
@@ -1478,8 +1481,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   if ((mask & 4) && face) {
     if (fk) zst = fk->s[1];
     const unsigned gy = (unsigned)((D.nw[1] + ZWY - 1) / ZWY);
-    const int kchunk = chunk_of((int64_t)gxz * gy, D.nw[2]);
-    const dim3 grid(gxz, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
+    const int kchunk = chunk_of((int64_t)gxz * gy, nplanes);
+    const dim3 grid(gxz, gy, (unsigned)((nplanes + kchunk - 1) / kchunk));
     if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, false, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, kchunk);
     else if (zmode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, false, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, kchunk);
     else launch_zeta(k_face_zeta<T, SCH, false, MODE_GENERIC>, zeta_warp_vals<T, MODE_GENERIC>, grid, kchunk);

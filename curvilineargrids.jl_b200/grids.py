@@ -515,3 +515,59 @@ def cellvolume(grid, idx):
     q = [float(grid.centroid_coordinates[c][tidx]) for c in range(grid.dim)]
     J = float(cell_metrics(grid).forward[tidx][-1])
     return _cell_scale(grid.coordinate_system, grid.basis, q) * abs(J)
+
+
+# ---------------------------------------------------------------------------
+# solver-facing bundles on the device
+# ---------------------------------------------------------------------------
+def _coordsys_id(cs, basis):
+    if cs == "CylindricalCS" and basis == "CartesianBasis":
+        return L.CG_CS_CYLINDRICAL
+    if cs == "AxisymmetricCS{:x}" and basis == "CartesianBasis":
+        return L.CG_CS_AXISYMMETRIC_X
+    if cs == "AxisymmetricCS{:y}" and basis == "CartesianBasis":
+        return L.CG_CS_AXISYMMETRIC_Y
+    if cs == "SphericalCS" and basis == "SphericalBasis":
+        return L.CG_CS_SPHERICAL_BASIS
+    return L.CG_CS_UNIT
+
+
+def _refresh_coords_if_scaled(grid, csys):
+    if csys != L.CG_CS_UNIT:
+        grid._eval(L.CG_WHAT_COORDS)
+
+
+def face_flux_geometry_arrays(grid, axis):
+    """`face_flux_geometry(grid, I, hi side of axis)` (face_geometry.jl:393-416) for every cell of the window in one
+    launch.  Returns a FaceFluxGeometry of device tensors: mapped_coordinate = the face coordinates of `axis`,
+    metric_vector [N, *cells], area [*cells], normal [N, *cells]; the low face of cell I is minus the entry I - e_axis."""
+    torch = _torch()
+    if not 0 <= axis < grid.dim:
+        raise ValueError(f"Invalid face axis {axis} for a {grid.dim}-D grid")
+    face_metrics(grid)
+    csys = _coordsys_id(grid.coordinate_system, grid.basis)
+    _refresh_coords_if_scaled(grid, csys)
+    shape = grid._cell_shape()
+    dt, dev = grid.tdtype, f"cuda:{grid.device}"
+    mv = torch.empty((grid.dim,) + tuple(shape), dtype=dt, device=dev)
+    nrm = torch.empty_like(mv)
+    area = torch.empty(tuple(shape), dtype=dt, device=dev)
+    L.check(L.lib().cg_grid_face_flux_geometry(grid._h, axis, csys, ctypes.c_void_p(mv.data_ptr()),
+                                               ctypes.c_void_p(area.data_ptr()), ctypes.c_void_p(nrm.data_ptr()),
+                                               grid._stream()))
+    q = grid.face_coordinates[axis] if csys != L.CG_CS_UNIT or grid._coords_enabled else None
+    return FaceFluxGeometry(q, mv, area, nrm)
+
+
+def cellvolumes(grid, include_halo=False):
+    """cellvolumes(grid; include_halo) (generation.jl:942-990): scale(q_centroid) * |det F| per cell, device tensor."""
+    torch = _torch()
+    cell_metrics(grid)
+    csys = _coordsys_id(grid.coordinate_system, grid.basis)
+    _refresh_coords_if_scaled(grid, csys)
+    vol = torch.empty(tuple(grid._cell_shape()), dtype=grid.tdtype, device=f"cuda:{grid.device}")
+    L.check(L.lib().cg_grid_cell_volumes(grid._h, csys, ctypes.c_void_p(vol.data_ptr()), grid._stream()))
+    if include_halo or tuple(grid.window_cells) != tuple(grid.nfull):
+        return vol
+    h = grid.nhalo
+    return vol[tuple(slice(h, n - h) for n in vol.shape)]

@@ -81,12 +81,9 @@ def make_plan(rank, nranks, ncell_slab, nhalo):
     return SlabPlan(rank, nranks, nhalo, ncell_slab, parts[rank], req[rank], own[rank], sends, recvs)
 
 
-def exchange_node_planes(plan, buffers, dist=None, group=None):
-    """Fill the non-owned planes of each local node buffer from their owners.
-
-    buffers: list of torch tensors whose FIRST dimension is the slab axis and covers
-    plan.required (memory order, e.g. [nk_local, nj+1, ni+1]).  Returns the list of
-    pending work handles (already waited on when `dist` is None-safe)."""
+def post_exchange(plan, buffers, dist=None, group=None):
+    """Post the sends / receives of the node-plane exchange and return the pending requests WITHOUT waiting
+    (NCCL: the transfers run on NCCL's stream while the caller keeps launching interior work)."""
     if plan.nranks == 1:
         return []
     if dist is None:
@@ -100,10 +97,87 @@ def exchange_node_planes(plan, buffers, dist=None, group=None):
             ops.append(dist.P2POp(dist.irecv, buf[lo - base:hi - base], peer, group=group))
     if not ops:
         return []
-    reqs = dist.batch_isend_irecv(ops)
+    return dist.batch_isend_irecv(ops)
+
+
+def wait_exchange(reqs):
+    """NCCL: makes the current stream wait for the transfers (the host does not block); gloo: blocks."""
     for r in reqs:
         r.wait()
+
+
+def exchange_node_planes(plan, buffers, dist=None, group=None):
+    """Fill the non-owned planes of each local node buffer from their owners.
+
+    buffers: list of torch tensors whose FIRST dimension is the slab axis and covers
+    plan.required (memory order, e.g. [nk_local, nj+1, ni+1]).  Returns the (completed) requests."""
+    reqs = post_exchange(plan, buffers, dist, group)
+    wait_exchange(reqs)
     return reqs
+
+
+def overlap_schedule(plan):
+    """Which padded node planes and cell planes of a rank's slab can be done BEFORE the exchange has landed.
+
+    Padded plane e of the slab holds the global interior node plane m = k0 + e - 1 - nhalo, Line()-extrapolated
+    outside [0, ncell] from the planes c = clamp(m) and c -+ 1; the cell plane k of the slab reads
+    the padded planes k .. k+4 (cg_grid_eval_planes).  Returns a dict:
+      pad_early / pad_late   lists of padded plane ranges [e_lo, e_hi)
+      eval_early / eval_late lists of cell plane ranges   [k_lo, k_hi)   (window-local)
+    pad_early + eval_early depend on owned node planes only."""
+    k0, k1 = plan.cells
+    nw, h, n = k1 - k0, plan.nhalo, plan.ncell_slab
+    ne = nw + 4
+    recv = [(lo, hi) for _, lo, hi in plan.recvs]
+
+    def received(m):
+        return any(lo <= m < hi for lo, hi in recv)
+
+    dirty = []
+    for e in range(ne):
+        m = k0 + e - 1 - h
+        c = min(max(m, 0), n)
+        deps = [c] if m == c else [c, c + 1 if m < c else c - 1]
+        dirty.append(any(received(d) for d in deps))
+    a = 0
+    while a < ne and dirty[a]:
+        a += 1
+    b = ne
+    while b > a and dirty[b - 1]:
+        b -= 1
+    if any(dirty[a:b]):  # not a prefix + suffix (cannot happen with contiguous ownership): no early work
+        a, b = ne, ne
+    ke_lo = min(a, nw)
+    ke_hi = max(ke_lo, min(b - 4, nw))
+    return {"pad_early": [(a, b)] if b > a else [], "pad_late": [r for r in ((0, a), (b, ne)) if r[1] > r[0]],
+            "eval_early": [(ke_lo, ke_hi)] if ke_hi > ke_lo else [],
+            "eval_late": [r for r in ((0, ke_lo), (ke_hi, nw)) if r[1] > r[0]]}
+
+
+def step_overlapped(grid, plan, buffers, what=3, dist=None, group=None):
+    """One evaluation of a rank's slab with the node-plane exchange overlapped with interior work
+    (3-D DiscreteGrid, marching kernels): post the exchange, pad + evaluate everything that depends on owned
+    node planes only, wait for the exchange, pad + evaluate the 1 (low) / 3 (high) boundary planes."""
+    import ctypes
+
+    from . import _lib as L
+    lib, st = L.lib(), grid._stream()
+    i64 = ctypes.c_int64
+    plan_ = overlap_schedule(plan)
+    grid._bind_metric_outputs(what)
+    reqs = post_exchange(plan, buffers, dist, group)
+    for lo, hi in plan_["pad_early"]:
+        L.check(lib.cg_grid_pad_planes(grid._h, i64(lo), i64(hi), st))
+    for lo, hi in plan_["eval_early"]:
+        L.check(lib.cg_grid_eval_planes(grid._h, what, i64(lo), i64(hi), 0, st))
+    wait_exchange(reqs)
+    for lo, hi in plan_["pad_late"]:
+        L.check(lib.cg_grid_pad_planes(grid._h, i64(lo), i64(hi), st))
+    for lo, hi in plan_["eval_late"]:
+        L.check(lib.cg_grid_eval_planes(grid._h, what, i64(lo), i64(hi), 0, st))
+    # every plane is covered: an empty final range marks the caches valid
+    L.check(lib.cg_grid_eval_planes(grid._h, what, i64(0), i64(0), 1, st))
+    return plan_
 
 
 def slab_grid_kwargs(plan, inplane_celldims, nhalo):

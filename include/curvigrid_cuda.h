@@ -135,6 +135,18 @@ int cg_grid_update(cg_grid* g, double t, void* stream);
  */
 int cg_grid_eval(cg_grid* g, int what, void* stream);
 
+/*
+ * Overlap of the node-plane exchange with interior work (3-D DiscreteGrid k-slabs, marching kernels):
+ *   cg_grid_pad_planes  re-pads only the padded node planes [e_lo, e_hi) of the slab axis.  Padded plane e holds
+ *                       the window's node plane e - 1; the cell plane k reads the padded planes k .. k+4.
+ *   cg_grid_eval_planes fills the cell + face metrics of the window's cell planes [k_lo, k_hi) only; the caches are
+ *                       marked valid when `final` != 0 (the caller covers every plane before that).
+ * Typical step: post ncclSend/ncclRecv of the neighbour planes; pad + evaluate the planes that depend on owned nodes
+ * only; wait for the exchange; pad + evaluate the 1 (low) / 3 (high) boundary planes.
+ */
+int cg_grid_pad_planes(cg_grid* g, int64_t e_lo, int64_t e_hi, void* stream);
+int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int final, void* stream);
+
 /* valid flags of UnifiedMetricCache (unified_grids.jl:34-52); invalidate_* (metric_cache_api.jl:16-41) */
 int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid);
 int cg_grid_invalidate(cg_grid* g, int what);
@@ -152,6 +164,28 @@ int cg_grid_copy_out(cg_grid* g, int array, int axis, void* host_dst, size_t nby
  * column (../gcl.jl:20-117).  Synchronises the stream; out[0..dim).
  */
 int cg_grid_gcl_max(cg_grid* g, double* out, void* stream);
+
+/*
+ * Solver-facing bundles for every cell of the window, SoA, device pointers of the grid's dtype:
+ *   face_flux_geometry(grid, I, hi side of `axis`) (face_geometry.jl:393-416):
+ *     metric_vector [N][cell] = component_scale(q_face) .* conserved[axis][I][axis,:]
+ *                               (conservation_face_metric_component_scale, face_geometry.jl:302-332),
+ *     area [cell] = |metric_vector|, normal [N][cell]; the low face of cell I is minus the entry I - e_axis.
+ *   cellvolume(grid, I) = conservation_cell_metric_scale(q_centroid) * |det F| (face_geometry.jl:277-300,
+ *     generation.jl:615-726; the array form is _compute_unified_cell_volumes_kernel!, generation.jl:942-990).
+ * Work on either profile (COMPACT holds exactly what they read).  coordsys != CG_CS_UNIT needs valid coordinate
+ * storage (cg_grid_eval with CG_WHAT_COORDS).  Any output of cg_grid_face_flux_geometry may be NULL.
+ */
+enum cg_coordsys {
+  CG_CS_UNIT = 0,           /* CartesianCS / CurvilinearCS: scale 1 */
+  CG_CS_CYLINDRICAL = 1,    /* CylindricalCS + CartesianBasis: 2 pi |q1| */
+  CG_CS_AXISYMMETRIC_X = 2, /* AxisymmetricCS{:x}: 2 pi |q2| */
+  CG_CS_AXISYMMETRIC_Y = 3, /* AxisymmetricCS{:y}: 2 pi |q1| */
+  CG_CS_SPHERICAL_BASIS = 4 /* SphericalCS + SphericalBasis: (r^2 sin th, r sin th, r) per component */
+};
+int cg_grid_face_flux_geometry(cg_grid* g, int axis, int coordsys, void* metric_vector, void* area, void* normal,
+                               void* stream);
+int cg_grid_cell_volumes(cg_grid* g, int coordsys, void* volume, void* stream);
 
 int cg_grid_sync(cg_grid* g, void* stream);
 /* device time of the last cg_grid_eval on this handle in ms (CUDA events; synchronises) */

@@ -37,8 +37,12 @@ def main():
             t[: olo - lo] = float("nan")   # not mine: must arrive through the exchange
             t[ohi - lo:] = float("nan")
             local.append(t)
-        cg.slabs.exchange_node_planes(plan, local)
-        g = cg.DiscreteGrid(*local, h, profile=profile, **cg.slabs.slab_grid_kwargs(plan, (ni, nj), h))
+        # handle first (its node buffer aliases `local`), then ONE overlapped step: exchange posted, interior planes
+        # padded + evaluated while the neighbour planes travel, boundary planes after the wait
+        g = cg.DiscreteGrid(*local, h, profile=profile, cache_mode="lazy",
+                            **cg.slabs.slab_grid_kwargs(plan, (ni, nj), h))
+        sched = cg.slabs.step_overlapped(g, plan, local)
+        assert world == 1 or sched["eval_late"], sched
         whole = cg.DiscreteGrid(*nodes, h, profile=profile)
         k0, k1 = plan.cells
         plane = (ni + 2 * h) * (nj + 2 * h)

@@ -49,3 +49,48 @@ def test_slabs_reproduce_single_grid(cg, world, profile):
                 assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
         res = cg.gcl(g)
         assert max(res) < 1e-13
+
+
+@pytest.mark.parametrize("profile", ["full", "compact"])
+def test_plane_ranged_pad_and_eval_match_one_evaluation(cg, profile):
+    """cg_grid_pad_planes / cg_grid_eval_planes (the pieces slabs.step_overlapped launches around the exchange):
+    padding and evaluating a slab in the early / late pieces of its overlap schedule gives the arrays of one
+    cg_grid_eval (1e-13: chunk boundaries differ, see above)."""
+    h = 3
+    nodes = mild_nodes((35, 9, 30), seed=5)
+    ni, nj, nk = (s - 1 for s in nodes[0].shape)
+    world, rank = 3, 1
+    plan = cg.slabs.make_plan(rank, world, nk, h)
+    lo, hi = plan.required
+    local = [torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0)[lo:hi])).cuda() for a in nodes]
+    kw = cg.slabs.slab_grid_kwargs(plan, (ni, nj), h)
+    ref_g = cg.DiscreteGrid(*local, h, profile=profile, **kw)
+    g = cg.DiscreteGrid(*local, h, profile=profile, cache_mode="lazy", **kw)
+    sched = cg.slabs.overlap_schedule(plan)
+    assert sched["eval_early"] and len(sched["eval_late"]) == 2
+    lib, st = cg._lib.lib(), g._stream()
+    g._bind_metric_outputs(3)
+    i64 = ctypes.c_int64
+    for a, b in sched["pad_early"]:
+        cg._lib.check(lib.cg_grid_pad_planes(g._h, i64(a), i64(b), st))
+    for a, b in sched["eval_early"]:
+        cg._lib.check(lib.cg_grid_eval_planes(g._h, 3, i64(a), i64(b), 0, st))
+    assert cg.cell_metrics_valid(g) is False and cg.face_metrics_valid(g) is False
+    for a, b in sched["pad_late"]:
+        cg._lib.check(lib.cg_grid_pad_planes(g._h, i64(a), i64(b), st))
+    for a, b in sched["eval_late"]:
+        cg._lib.check(lib.cg_grid_eval_planes(g._h, 3, i64(a), i64(b), 0, st))
+    cg._lib.check(lib.cg_grid_eval_planes(g._h, 3, i64(0), i64(0), 1, st))
+    assert cg.cell_metrics_valid(g) and cg.face_metrics_valid(g)
+    if profile == "full":
+        assert_metrics_close(grid_outputs(cg, g), grid_outputs(cg, ref_g), rtol=1e-13, label="ranged")
+    else:
+        assert np.allclose(cg.cell_metrics(g).cpu().numpy(), cg.cell_metrics(ref_g).cpu().numpy(), rtol=1e-13, atol=0)
+        for ax in range(3):
+            a, b = cg.face_metrics(g)[ax].cpu().numpy(), cg.face_metrics(ref_g)[ax].cpu().numpy()
+            assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    # argument checks
+    with pytest.raises(cg.CurvigridArgumentError):
+        cg._lib.check(lib.cg_grid_eval_planes(g._h, 3, i64(2), i64(1), 0, st))
+    with pytest.raises(cg.CurvigridArgumentError):
+        cg._lib.check(lib.cg_grid_pad_planes(g._h, i64(0), i64(10 ** 6), st))

@@ -88,3 +88,41 @@ def test_slab_grid_kwargs():
     assert kw["global_celldims"] == (8, 6, 16)
     assert kw["window"][0] == (0, 0, plan.cells[0]) and kw["window"][1] == (18, 16, plan.cells[1] - plan.cells[0])
     assert kw["node_origin"] == (0, 0, plan.required[0])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("ncell,nhalo", [(40, 5), (13, 2), (9, 0), (64, 3)])
+def test_overlap_schedule_covers_slab_and_needs_owned_planes_only(world, ncell, nhalo):
+    """slabs.overlap_schedule: the early work touches owned node planes only, early + late cover every padded plane
+    and every cell plane exactly once (pure index algebra; the GPU side is tests/test_gpu_slabs.py)."""
+    for rank in range(world):
+        plan = slabs.make_plan(rank, world, ncell, nhalo)
+        k0, k1 = plan.cells
+        nw = k1 - k0
+        if nw <= 0:
+            continue
+        s = slabs.overlap_schedule(plan)
+        cover = np.zeros(nw, dtype=int)
+        for lo, hi in s["eval_early"] + s["eval_late"]:
+            cover[lo:hi] += 1
+        assert (cover == 1).all(), (rank, world, s)
+        pcover = np.zeros(nw + 4, dtype=int)
+        for lo, hi in s["pad_early"] + s["pad_late"]:
+            pcover[lo:hi] += 1
+        assert (pcover == 1).all(), (rank, world, s)
+        recv = set()
+        for _, lo, hi in plan.recvs:
+            recv.update(range(lo, hi))
+        early_pad = set()
+        for lo, hi in s["pad_early"]:
+            early_pad.update(range(lo, hi))
+        for e in early_pad:  # dependencies of a padded plane: clamp(m) and, when extrapolated, its inner neighbour
+            m = k0 + e - 1 - nhalo
+            c = min(max(m, 0), ncell)
+            deps = {c} if m == c else {c, c + 1 if m < c else c - 1}
+            assert not (deps & recv), (rank, world, e, deps)
+        for lo, hi in s["eval_early"]:  # a cell plane reads the padded planes k .. k+4
+            for k in range(lo, hi):
+                assert set(range(k, k + 5)) <= early_pad, (rank, world, k)
+        if world == 1:
+            assert not s["eval_late"] and not s["pad_late"]
