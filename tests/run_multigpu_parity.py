@@ -49,10 +49,10 @@ def main():
         if profile == "full":
             got, ref = grid_outputs(cg, g), grid_outputs(cg, whole)
             want = {k: ref[k][..., k0 * plane:k1 * plane, :] for k in ("cell_fwd", "cell_inv", "face_fwd", "face_inv", "face_cons")}
-            assert_metrics_close(got, want, rtol=1e-13, label=f"rank {rank}")
+            assert_metrics_close(got, want, rtol=5e-13, label=f"rank {rank}")  # chunk boundaries differ (1-ulp FMA contraction, amplified by the cancellation in the conserved metrics)
         else:
             a, b = cg.cell_metrics(g).cpu().numpy(), cg.cell_metrics(whole).cpu().numpy()[k0:k1]
-            assert np.allclose(a, b, rtol=1e-13, atol=0)
+            assert np.allclose(a, b, rtol=5e-13, atol=0)
         res = torch.tensor(cg.gcl(g), device="cuda", dtype=torch.float64)
         dist.all_reduce(res, op=dist.ReduceOp.MAX)   # GCL max over all slabs (SURVEY.md §8e reductions)
         assert float(res.max()) < 1e-13, res
