@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--h2d-chunks", type=int, default=16, help="pieces of the pipelined host->device update (e2e)")
     ap.add_argument("--workload", default="3d512",
                     help="3d<N> | 2d<N> DiscreteGrid, m3d<N> MappedGrid with update! every step (interior cells per axis)")
     ap.add_argument("--scheme", default=None)
@@ -331,10 +332,17 @@ def run_ours(args, spec):
         else:
             step_plain()
 
+    pipelined = world == 1 and dim == 3 and args.kernel == 1
+
     def step_e2e():
-        for d, hsrc in zip(dev_nodes, host_pinned):
-            d[olo - lo:ohi - lo].copy_(hsrc[olo - lo:ohi - lo], non_blocking=True)
-        step_resident()
+        if pipelined:
+            # cg_grid_update_from_host: node planes in pieces, the H2D copy of a piece overlaps the kernels of the
+            # piece before (pinned host arrays -> padded nodes -> metrics)
+            grid.update_from_host(*host_pinned, nchunks=args.h2d_chunks)
+        else:
+            for d, hsrc in zip(dev_nodes, host_pinned):
+                d[olo - lo:ohi - lo].copy_(hsrc[olo - lo:ohi - lo], non_blocking=True)
+            step_resident()
         res = cg.gcl(grid)  # device reduction + D2H of the residuals (synchronises)
         return res
 
@@ -415,8 +423,10 @@ def run_ours(args, spec):
         h2d = sum(int(t[olo - lo:ohi - lo].numel() * t.element_size()) for t in host_pinned)
         e2e = {"value": cells_total / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 8 * dim, "ms_per_step": ms,
-               "note": "pinned host nodes -> H2D -> pad -> metrics -> device GCL max -> D2H; metric arrays stay on "
-                       "the device like a KernelAbstractions GPU backend's storage"}
+               "note": ("pinned host nodes -> H2D in %d pieces overlapped with pad + metrics of the piece before "
+                        "(cg_grid_update_from_host)" % args.h2d_chunks if pipelined else
+                        "pinned host nodes -> H2D -> pad -> metrics") + " -> device GCL max -> D2H; metric arrays "
+                       "stay on the device like a KernelAbstractions GPU backend's storage"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -61,6 +61,8 @@ struct cg_grid {
   unsigned long long* gcl_bits = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  cudaStream_t copy_stream = nullptr;  // cg_grid_update_from_host: H2D pieces
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   std::vector<double> terms;
   cg::MappedTables mtab;
   double t = 0.0;
@@ -454,6 +456,9 @@ int cg_grid_destroy(cg_grid* g) {
   if (g->gcl_bits) cudaFree(g->gcl_bits);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
+  if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
+  for (int e = 0; e < 2; ++e)
+    if (g->copy_ev[e]) cudaEventDestroy(g->copy_ev[e]);
   delete g;
   return CG_OK;
 }
@@ -605,6 +610,69 @@ int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int fi
   CG_CUDA(cudaSetDevice(g->device));
   return g->dtype == CG_F64 ? eval_impl<double>(g, what, (cudaStream_t)stream, k_lo, k_hi, final != 0)
                             : eval_impl<float>(g, what, (cudaStream_t)stream, k_lo, k_hi, final != 0);
+}
+
+int cg_grid_update_from_host(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
+                             void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (g->kind != 1 || g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_update_from_host: 3-D DiscreteGrid only");
+  if (what <= 0 || what > 3) return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE)", what);
+  const void* in[3] = {x, y, z};
+  for (int q = 0; q < 3; ++q) {
+    if (!in[q]) return fail(CG_ERR_ARG, "coordinate array %d is NULL", q);
+    if (!g->src[q].p) return fail(CG_ERR_STATE, "no node buffer: call cg_grid_set_nodes once first");
+  }
+  CG_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g->copy_stream) {
+    CG_CUDA(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    CG_CUDA(cudaEventCreateWithFlags(&g->copy_ev[0], cudaEventDisableTiming));
+    CG_CUDA(cudaEventCreateWithFlags(&g->copy_ev[1], cudaEventDisableTiming));
+  }
+  const int64_t nk = g->src_count[2], plane = g->src_count[0] * g->src_count[1];
+  const int64_t o = g->src_origin[2], gn = g->ncell[2], h = g->nhalo, nw = g->nw[2], ne = nw + 4;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > nk) nchunks = (int)nk;
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  // the copies overwrite the node buffer the previous evaluation's padding read
+  CG_CUDA(cudaEventRecord(g->copy_ev[0], st));
+  CG_CUDA(cudaStreamWaitEvent(g->copy_stream, g->copy_ev[0], 0));
+  int64_t ext_done = 0, cell_done = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const int64_t p_lo = nk * c / nchunks, p_hi = nk * (c + 1) / nchunks;
+    for (int q = 0; q < 3; ++q)
+      CG_CUDA(cudaMemcpyAsync((char*)g->src[q].p + (size_t)(p_lo * plane) * g->esize(),
+                              (const char*)in[q] + (size_t)(p_lo * plane) * g->esize(),
+                              (size_t)((p_hi - p_lo) * plane) * g->esize(), cudaMemcpyHostToDevice, g->copy_stream));
+    CG_CUDA(cudaEventRecord(g->copy_ev[1], g->copy_stream));
+    CG_CUDA(cudaStreamWaitEvent(st, g->copy_ev[1], 0));
+    // padded planes whose source planes (clamp(m) and, when extrapolated, its inner neighbour) have all landed
+    auto landed = [&](int64_t m) { return m >= o && m < o + p_hi; };
+    int64_t e_hi = ext_done;
+    for (; e_hi < ne; ++e_hi) {
+      const int64_t m = g->w0[2] + e_hi - 1 - h;
+      const int64_t cc = m < 0 ? 0 : (m > gn ? gn : m);
+      if (!landed(cc)) break;
+      if (m != cc && !landed(m < cc ? cc + 1 : cc - 1)) break;
+    }
+    int rc = CG_OK;
+    if (e_hi > ext_done)
+      rc = g->dtype == CG_F64 ? pad_nodes<double>(g, st, ext_done, e_hi) : pad_nodes<float>(g, st, ext_done, e_hi);
+    if (rc) return rc;
+    ext_done = e_hi;
+    int64_t k_hi = ext_done - 4 < cell_done ? cell_done : (ext_done - 4 > nw ? nw : ext_done - 4);
+    if (c == nchunks - 1) {
+      if (ext_done != ne) return fail(CG_ERR_STATE, "node buffer does not cover the window");
+      k_hi = nw;
+    }
+    const bool last = c == nchunks - 1;
+    if (k_hi > cell_done || last)
+      rc = g->dtype == CG_F64 ? eval_impl<double>(g, what, st, cell_done, k_hi, last)
+                              : eval_impl<float>(g, what, st, cell_done, k_hi, last);
+    if (rc) return rc;
+    cell_done = k_hi;
+  }
+  return CG_OK;
 }
 
 int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid) {

@@ -314,6 +314,24 @@ class DiscreteGrid(_UnifiedGrid):
         if any(isinstance(k, np.ndarray) for k in keep):
             self.synchronize()  # pageable host memory must outlive the async copy
 
+    def update_from_host(self, *coords, what=3, nchunks=8):
+        """update!(grid, x, y, z) from HOST arrays + refresh of both caches, pipelined (cg_grid_update_from_host):
+        the H2D copy of a piece of node planes overlaps the metric kernels of the piece before.  `coords`: pinned
+        CPU torch tensors (or numpy arrays) in memory order [k, j, i] with the extents of the constructor's arrays."""
+        torch = _torch()
+        if self.dim != 3:
+            raise ValueError("update_from_host: 3-D DiscreteGrid only")
+        ptrs = []
+        for c in coords:
+            t = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c, dtype=self.T))
+            if t.is_cuda or not t.is_contiguous() or t.dtype != self.tdtype:
+                raise ValueError("update_from_host needs contiguous CPU arrays of the grid's dtype")
+            ptrs.append(t)
+        self._bind_metric_outputs(what)
+        L.check(L.lib().cg_grid_update_from_host(self._h, *[ctypes.c_void_p(t.data_ptr()) for t in ptrs], what,
+                                                 int(nchunks), self._stream()))
+        self._host_keepalive = ptrs  # the copies are asynchronous
+
     def set_nodes(self, *coords):
         """Moving sampled mesh: new node arrays (the reference re-creates the grid;
         legacy `update!(mesh, force, include_halo)` is the analogue, 3d.jl:472-493)."""

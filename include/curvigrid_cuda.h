@@ -147,6 +147,17 @@ int cg_grid_eval(cg_grid* g, int what, void* stream);
 int cg_grid_pad_planes(cg_grid* g, int64_t e_lo, int64_t e_hi, void* stream);
 int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int final, void* stream);
 
+/*
+ * update!(grid, x, y, z) of a 3-D DiscreteGrid from HOST coordinate arrays (discrete_grid.jl:605-647) followed by
+ * refresh_cell_metrics! / refresh_face_metrics!, pipelined: the node planes (same layout and extents as the arrays
+ * of the last cg_grid_set_nodes; pinned host memory for a truly asynchronous copy) go to the device in `nchunks`
+ * pieces along the slab axis on an internal copy stream; each piece that lands releases the padded planes and cell
+ * planes it completes on `stream` (cg_grid_pad_planes / cg_grid_eval_planes), so the host-to-device copy of piece
+ * c+1 overlaps the metric kernels of piece c.  Marks the caches valid.
+ */
+int cg_grid_update_from_host(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
+                             void* stream);
+
 /* valid flags of UnifiedMetricCache (unified_grids.jl:34-52); invalidate_* (metric_cache_api.jl:16-41) */
 int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid);
 int cg_grid_invalidate(cg_grid* g, int what);

@@ -94,3 +94,28 @@ def test_plane_ranged_pad_and_eval_match_one_evaluation(cg, profile):
         cg._lib.check(lib.cg_grid_eval_planes(g._h, 3, i64(2), i64(1), 0, st))
     with pytest.raises(cg.CurvigridArgumentError):
         cg._lib.check(lib.cg_grid_pad_planes(g._h, i64(0), i64(10 ** 6), st))
+
+
+@pytest.mark.parametrize("nchunks", [1, 3, 8, 1000])
+@pytest.mark.parametrize("profile", ["full", "compact"])
+def test_update_from_host_pipelined(cg, nchunks, profile):
+    """cg_grid_update_from_host: pipelined H2D + pad + evaluation in pieces gives the arrays of set_nodes + one
+    evaluation, for new node values (update!(grid, x, y, z), discrete_grid.jl:605-647)."""
+    h = 3
+    nodes0 = mild_nodes((20, 9, 26), seed=1)
+    nodes1 = mild_nodes((20, 9, 26), seed=2)
+    dev0 = [torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).cuda() for a in nodes0]
+    g = cg.DiscreteGrid(*dev0, h, profile=profile, cache_mode="lazy")
+    cg.refresh_metrics(g)
+    pinned = [torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).pin_memory() for a in nodes1]
+    g.update_from_host(*pinned, nchunks=nchunks)
+    assert cg.cell_metrics_valid(g) and cg.face_metrics_valid(g)
+    ref_g = cg.DiscreteGrid(*nodes1, h, profile=profile)
+    if profile == "full":
+        assert_metrics_close(grid_outputs(cg, g), grid_outputs(cg, ref_g), rtol=5e-13, label="pipelined")
+    else:
+        assert np.allclose(cg.cell_metrics(g).cpu().numpy(), cg.cell_metrics(ref_g).cpu().numpy(), rtol=5e-13, atol=0)
+        for ax in range(3):
+            a, b = cg.face_metrics(g)[ax].cpu().numpy(), cg.face_metrics(ref_g)[ax].cpu().numpy()
+            assert np.abs(a - b).max() <= 5e-13 * np.abs(b).max()
+    assert max(cg.gcl(g)) < 1e-12
