@@ -51,7 +51,9 @@ struct MPair {
 };
 struct MPairs {
   int n;
+  int cstart[4];  // 3-D: pairs of column c are p[cstart[c] .. cstart[c+1]) (the list is built column by column)
   MPair p[M_MAXP];
+  double coef[M_MAXP + 1];  // coef(m1) * coef(m2) at the current time (one entry of slack for the prefetch)
 };
 
 // n-th derivative of a factor (kind 0: 1, 1: a+b*s, 2: sin(a+b*s), 3: cos(a+b*s))
@@ -86,7 +88,8 @@ __host__ __device__ inline double cell_centre(const Dims& D, int d, int64_t idx)
 //   E  = 1/2 [ (h + l1 h' + l2 h'')(s_I) + (h - l1 h' + l2 h'')(s_I + 1) ]      face reconstruction
 //   D  = E(s_I) - E(s_I - 1)                                                       cell-centred difference
 //   FD = face reconstruction of the function u(s) = E[h](s) - E[h](s-1), with u', u''
-// tab[((p*3 + d)*OP_COUNT + op) * L + I]
+// tab[((p*3 + d)*L + I)*OP_COUNT + op]: the six operator values of one position are contiguous (48 B, 16-B
+// aligned), so a cell reads them with three 16-byte loads per axis
 // ---------------------------------------------------------------------------
 template <class T>
 __global__ void k_mapped_tables(Dims D, MTerms TM, MPairs PR, double lam1, double lam2, T* tab, int64_t L) {
@@ -121,26 +124,27 @@ __global__ void k_mapped_tables(Dims D, MTerms TM, MPairs PR, double lam1, doubl
         for (int n = 0; n < 3; ++n)
           En[pos][n] = 0.5 * ((hn[pos][n] + lam1 * hn[pos][n + 1] + lam2 * hn[pos][n + 2]) +
                               (hn[pos + 1][n] - lam1 * hn[pos + 1][n + 1] + lam2 * hn[pos + 1][n + 2]));
-      T* base = tab + ((int64_t)(p * 3 + d) * OP_COUNT) * L + I;
+      T* base = tab + ((int64_t)(p * 3 + d) * L + I) * OP_COUNT;
       if (v == 0) {
-        base[OP_V0 * L] = T(hn[1][0]);
-        base[OP_E0 * L] = T(En[1][0]);
-        base[OP_D0 * L] = T(En[1][0] - En[0][0]);
+        base[OP_V0] = T(hn[1][0]);
+        base[OP_E0] = T(En[1][0]);
+        base[OP_D0] = T(En[1][0] - En[0][0]);
         double u0[3], u1[3];  // u, u', u'' at s0 and s0+1
         for (int n = 0; n < 3; ++n) {
           u0[n] = En[1][n] - En[0][n];
           u1[n] = En[2][n] - En[1][n];
         }
-        base[OP_FD0 * L] = T(0.5 * ((u0[0] + lam1 * u0[1] + lam2 * u0[2]) + (u1[0] - lam1 * u1[1] + lam2 * u1[2])));
+        base[OP_FD0] = T(0.5 * ((u0[0] + lam1 * u0[1] + lam2 * u0[2]) + (u1[0] - lam1 * u1[1] + lam2 * u1[2])));
       } else {
-        base[OP_V1 * L] = T(hn[1][0]);
-        base[OP_E1 * L] = T(En[1][0]);
+        base[OP_V1] = T(hn[1][0]);
+        base[OP_E1] = T(En[1][0]);
       }
     }
   }
 }
 
-// factor derivative tables for the analytic Jacobian: ftab[((m*3 + d)*4 + order)*L1 + I], I in [0, nw_d]
+// factor derivative tables for the analytic Jacobian: ftab[((m*3 + d)*L1 + I)*4 + order], I in [0, nw_d]
+// (the four derivative orders of one position are contiguous: two 16-byte loads)
 template <class T>
 __global__ void k_mapped_factors(Dims D, MTerms TM, T* ftab, int64_t L1) {
   const int64_t ntot = (int64_t)TM.n * 3 * L1;
@@ -149,15 +153,15 @@ __global__ void k_mapped_factors(Dims D, MTerms TM, T* ftab, int64_t L1) {
     const int64_t I = lin % L1;
     const int d = (int)((lin / L1) % 3);
     const int m = (int)(lin / (3 * L1));
-    T* base = ftab + ((int64_t)(m * 3 + d) * 4) * L1 + I;
+    T* base = ftab + ((int64_t)(m * 3 + d) * L1 + I) * 4;
     if (d >= D.dim) {
-      for (int o = 0; o < 4; ++o) base[o * L1] = o == 0 ? T(1) : T(0);
+      for (int o = 0; o < 4; ++o) base[o] = o == 0 ? T(1) : T(0);
       continue;
     }
     if (I > D.nw[d]) continue;
     const MTerm& t = TM.t[m];
     const double s = cell_centre(D, d, I);
-    for (int o = 0; o < 4; ++o) base[o * L1] = T(fac_der(t.kind[d], t.a[d], t.b[d], s, o));
+    for (int o = 0; o < 4; ++o) base[o] = T(fac_der(t.kind[d], t.a[d], t.b[d], s, o));
   }
 }
 
@@ -175,7 +179,7 @@ __device__ __forceinline__ void mapped_jac(const MTerms& TM, const T* ftab, int6
 #pragma unroll
     for (int d = 0; d < 3; ++d)
 #pragma unroll
-      for (int o = 0; o < 4; ++o) a[d][o] = d < N ? ftab[((int64_t)(m * 3 + d) * 4 + o) * L1 + ix[d]] : (o == 0 ? T(1) : T(0));
+      for (int o = 0; o < 4; ++o) a[d][o] = d < N ? ftab[((int64_t)(m * 3 + d) * L1 + ix[d]) * 4 + o] : (o == 0 ? T(1) : T(0));
     const T c = T(TM.t[m].coef);
 #pragma unroll
     for (int d = 0; d < N; ++d) {
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(128) k_mapped_metrics3d(Dims D, MTerms TM, MPa
 #pragma unroll
       for (int d = 0; d < 3; ++d)
 #pragma unroll
-        for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = tab[((int64_t)(p * 3 + d) * OP_COUNT + o) * L + ix[d]];
+        for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = tab[((int64_t)(p * 3 + d) * L + ix[d]) * OP_COUNT + o];
       const T C = T(TM.t[PR.p[p].m1].coef * TM.t[PR.p[p].m2].coef);
       const int col = PR.p[p].col;
 #pragma unroll
@@ -347,9 +351,38 @@ __global__ void __launch_bounds__(128) k_mapped_metrics3d(Dims D, MTerms TM, MPa
 #define CG_MAPPED_UNROLL_T 2
 #endif
 constexpr int MAPPED_UNROLL_P = CG_MAPPED_UNROLL_P, MAPPED_UNROLL_T = CG_MAPPED_UNROLL_T;
+// vector loads of N consecutive table values: 16-byte pieces when N * sizeof(T) is a multiple of 16 (FP64 rows, FP32
+// factor rows), 8-byte pieces otherwise (FP32 operator rows: 24 B); the address is aligned to the piece
+template <class T, int N>
+__device__ __forceinline__ void ldg_vec(const T* __restrict__ p, T (&v)[N]) {
+  if constexpr (sizeof(T) == 8) {
+    static_assert(N % 2 == 0, "table rows are 16-byte multiples");
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      const double2 w = __ldg(reinterpret_cast<const double2*>(p) + k);
+      v[2 * k] = w.x; v[2 * k + 1] = w.y;
+    }
+  } else if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p) + k);
+      v[4 * k] = w.x; v[4 * k + 1] = w.y; v[4 * k + 2] = w.z; v[4 * k + 3] = w.w;
+    }
+  } else {
+    static_assert(N % 2 == 0, "table rows are 8-byte multiples");
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(p) + k);
+      v[2 * k] = w.x; v[2 * k + 1] = w.y;
+    }
+  }
+}
+
 struct MCoordTerms {
   int cnt[3];
   int idx[3][M_MAXT];
+  int flat[M_MAXT + 1];     // the same terms as one sequence ordered by coordinate (software pipelining of the loads)
+  double coef[M_MAXT + 1];  // their time-dependent coefficients in that order
 };
 inline MCoordTerms coord_terms(const MTerms& TM) {
   MCoordTerms C;
@@ -358,6 +391,14 @@ inline MCoordTerms coord_terms(const MTerms& TM) {
     const int q = TM.t[m].coord;
     if (q >= 0 && q < 3) C.idx[q][C.cnt[q]++] = m;
   }
+  int s = 0;
+  for (int q = 0; q < 3; ++q)
+    for (int mm = 0; mm < C.cnt[q]; ++mm) {
+      C.flat[s] = C.idx[q][mm];
+      C.coef[s++] = TM.t[C.idx[q][mm]].coef;
+    }
+  C.flat[s] = s > 0 ? C.flat[s - 1] : 0;  // sentinel: the prefetch of "one past the end" stays in range
+  C.coef[s] = 0.0;
   return C;
 }
 // F and, for every axis f with (AXES >> f) & 1, dF/d(xi_f) and d2F/d(xi_f)^2 at the centre of cell ix
@@ -365,6 +406,13 @@ template <class T, int AXES>
 __device__ __forceinline__ void mapped_jac_multi(const MTerms& TM, const MCoordTerms& CT, const T* __restrict__ ftab,
                                                  int64_t L1, const int64_t (&ix)[3], T (&F)[3][3], T (&Fp)[3][3][3],
                                                  T (&Fpp)[3][3][3]) {
+  // software pipeline over the flat term sequence: the table rows of the NEXT term are requested before the current
+  // term is accumulated (8 warps per SM cannot hide an L1 round trip per term otherwise)
+  T a[3][4], an[3][4];
+  T c = T(CT.coef[0]), cn;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) ldg_vec<T, 4>(ftab + ((int64_t)(CT.flat[0] * 3 + d) * L1 + ix[d]) * 4, a[d]);
+  int s = 0;
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
 #pragma unroll
@@ -375,13 +423,11 @@ __device__ __forceinline__ void mapped_jac_multi(const MTerms& TM, const MCoordT
     }
 #pragma unroll(MAPPED_UNROLL_T)
     for (int mm = 0; mm < CT.cnt[q]; ++mm) {
-      const int m = CT.idx[q][mm];
-      T a[3][4];
+      ++s;
+      const int mnext = CT.flat[s];  // sentinel past the end
+      cn = T(CT.coef[s]);
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
-#pragma unroll
-        for (int o = 0; o < 4; ++o) a[d][o] = __ldg(ftab + ((int64_t)(m * 3 + d) * 4 + o) * L1 + ix[d]);
-      const T c = T(TM.t[m].coef);
+      for (int d = 0; d < 3; ++d) ldg_vec<T, 4>(ftab + ((int64_t)(mnext * 3 + d) * L1 + ix[d]) * 4, an[d]);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
         // orders: o_ax = (ax == d) for F; + (ax == f) for dF/dxi_f; + 2 (ax == f) for the second derivative
@@ -403,6 +449,11 @@ __device__ __forceinline__ void mapped_jac_multi(const MTerms& TM, const MCoordT
           }
         }
       }
+      c = cn;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a[d][o] = an[d][o];
     }
   }
 }
@@ -428,9 +479,14 @@ __device__ __forceinline__ void mapped_states3_g(const T (&G)[3][3], const T (&F
 }
 
 constexpr int MAPPED_OUT = 31;
+#ifndef CG_MWY
+#define CG_MWY 1
+#endif
+// one warp per block: row, plane and every staging / TMA address are uniform (see ZWY in cg_kernels_tiled.cuh)
+constexpr int MWY = CG_MWY;
 template <class T> constexpr int mapped_stage_vals = 8 * stage_len<T, 10> + 3 * stage_len<T, 9>;
 template <class T>
-__global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerms TM, MCoordTerms CT, MPairs PR,
+__global__ void __launch_bounds__(32 * MWY, 8 / MWY) k_mapped_metrics3d_staged(Dims D, MTerms TM, MCoordTerms CT, MPairs PR,
                                                                   const T* __restrict__ tab, const T* __restrict__ ftab,
                                                                   int64_t L, MetricOut<T> O, int scheme, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
@@ -438,7 +494,7 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
   const int64_t L1 = L + 1;
   const int lane = threadIdx.x;
   const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
-  const int64_t j = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int64_t j = MWY == 1 ? (int64_t)blockIdx.y : (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nw1) return;  // whole warp
   const int64_t i0 = (int64_t)blockIdx.x * MAPPED_OUT;
   const int nvalid = (int)(nw0 - i0 < MAPPED_OUT ? nw0 - i0 : MAPPED_OUT);
@@ -448,7 +504,7 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
   const int64_t i = i0 + lane < nw0 ? i0 + lane : nw0;
   const int64_t k0 = (int64_t)blockIdx.z * kchunk;
   const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
-  T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + threadIdx.y * mapped_stage_vals<T>;
+  T* const sg = reinterpret_cast<T*>(cg_dyn_smem) + (MWY == 1 ? 0 : threadIdx.y) * mapped_stage_vals<T>;
 
   // carried along zeta: F, G = inv F, det F and the zeta-axis L state of the cell of the next step
   T Fc[3][3], Gc[3][3], Jc, Lz[3][3], Fp0[3][3], Fpp0[3][3], Fp1[3][3], Fpp1[3][3];
@@ -474,13 +530,11 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
   for (int64_t m = k0; m < k1; ++m) {
     const int64_t ix[3] = {i, j, m};
     const int64_t cl0 = i0 + nw0 * (j + nw1 * m);
-    if (lane == 0) bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers
+    bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers (lanes > 0 own no groups)
     __syncwarp();
     Stage<T, 10> Scf(O.cell_fwd, cl0, sg), Sci(O.cell_inv, cl0, sg + stage_len<T, 10>);
-    if (out_ok) {
-      put10(Scf.slot(lane), Fc, Jc);
-      put10(Sci.slot(lane), Gc, Jc);
-    }
+    put10(Scf.slot(lane), Fc, Jc);  // every lane stages (no branch); slots >= nvalid are never sent
+    put10(Sci.slot(lane), Gc, Jc);
     // ---- conserved metrics: sums over term pairs of triple products of 1-D table values ----
     T Gh[3][3][3];  // [face][row][col]
 #pragma unroll
@@ -489,28 +543,38 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
       for (int rr = 0; rr < 3; ++rr)
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) Gh[f][rr][cc] = T(0);
+    // the pair list is ordered by column: three loops with a compile-time column (no predicated accumulation),
+    // software-pipelined over the flat list: the rows of pair p + 1 are requested before pair p is accumulated
+    {
+      const int np = PR.n;
+      int64_t ixc[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) ixc[d] = ix[d] < D.nw[d] ? ix[d] : D.nw[d] - 1;
+      T tv[3][OP_COUNT], tn[3][OP_COUNT];
+      T C = T(PR.coef[0]), Cn;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) ldg_vec<T, OP_COUNT>(tab + ((int64_t)d * L + ixc[d]) * OP_COUNT, tv[d]);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
 #pragma unroll(MAPPED_UNROLL_P)
-    for (int p = 0; p < PR.n; ++p) {
-      T tv[3][OP_COUNT];
+        for (int p = PR.cstart[cc]; p < PR.cstart[cc + 1]; ++p) {
+          const int pn = p + 1 < np ? p + 1 : p;  // the last prefetch re-reads the last pair
+          Cn = T(PR.coef[p + 1]);
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
+          for (int d = 0; d < 3; ++d) ldg_vec<T, OP_COUNT>(tab + ((int64_t)(pn * 3 + d) * L + ixc[d]) * OP_COUNT, tn[d]);
 #pragma unroll
-        for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = __ldg(tab + ((int64_t)(p * 3 + d) * OP_COUNT + o) * L + (ix[d] < D.nw[d] ? ix[d] : D.nw[d] - 1));
-      const T C = T(TM.t[PR.p[p].m1].coef * TM.t[PR.p[p].m2].coef);
-      const int col = PR.p[p].col;
-#pragma unroll
-      for (int f = 0; f < 3; ++f) {
-        const int s = (f + 1) % 3, t = (f + 2) % 3;
-        T act = C * tv[f][OP_E0] * (tv[s][OP_V1] * tv[t][OP_D0] - tv[s][OP_D0] * tv[t][OP_V1]);
-        T rs = C * tv[s][OP_V0] * (tv[f][OP_FD0] * tv[t][OP_V1] - tv[f][OP_E1] * tv[t][OP_D0]);
-        T rt = C * tv[t][OP_V0] * (tv[f][OP_E1] * tv[s][OP_D0] - tv[f][OP_FD0] * tv[s][OP_V1]);
-#pragma unroll
-        for (int cc = 0; cc < 3; ++cc)
-          if (cc == col) {
-            Gh[f][f][cc] += act;
-            Gh[f][s][cc] += rs;
-            Gh[f][t][cc] += rt;
+          for (int f = 0; f < 3; ++f) {
+            const int s = (f + 1) % 3, t = (f + 2) % 3;
+            Gh[f][f][cc] += C * tv[f][OP_E0] * (tv[s][OP_V1] * tv[t][OP_D0] - tv[s][OP_D0] * tv[t][OP_V1]);
+            Gh[f][s][cc] += C * tv[s][OP_V0] * (tv[f][OP_FD0] * tv[t][OP_V1] - tv[f][OP_E1] * tv[t][OP_D0]);
+            Gh[f][t][cc] += C * tv[t][OP_V0] * (tv[f][OP_E1] * tv[s][OP_D0] - tv[f][OP_FD0] * tv[s][OP_V1]);
           }
+          C = Cn;
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int o = 0; o < OP_COUNT; ++o) tv[d][o] = tn[d][o];
+        }
       }
     }
     // ---- reconstructed inverse Jacobian on the three faces ----
@@ -519,7 +583,7 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
       T* const sf = sg + (2 + 2 * f) * stage_len<T, 10>;
       Stage<T, 10> Sff(O.face_fwd[f], cl0, sf), Sfi(O.face_inv[f], cl0, sf + stage_len<T, 10>);
       Stage<T, 9> Sfc(O.face_cons[f], cl0, sg + 8 * stage_len<T, 10> + f * stage_len<T, 9>);
-      if (out_ok) put9(Sfc.slot(lane), Gh[f]);
+      put9(Sfc.slot(lane), Gh[f]);
       T Gf[3][3], Ff[3][3];
       if (f == 0) {  // +xi neighbour: its R state by shuffle
         T L0[3][3], R0[3][3];
@@ -551,10 +615,8 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
           }
       }
       T J = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
-      if (out_ok) {
-        put10(Sff.slot(lane), Ff, J);
-        put10(Sfi.slot(lane), Gf, J);
-      }
+      put10(Sff.slot(lane), Ff, J);
+      put10(Sfi.slot(lane), Gf, J);
     }
     // ---- one flush point: staged arrays -> TMA ----
     fence_async_smem();
@@ -576,7 +638,7 @@ __global__ void __launch_bounds__(NT, 2) k_mapped_metrics3d_staged(Dims D, MTerm
 template <class T>
 inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
                                            int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
-  const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + WY - 1) / WY);
+  const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + MWY - 1) / MWY);
   const int64_t tiles = (int64_t)gx * gy, want = 148LL * 16;
   int kchunk = (int)D.nw[2];
   if (tiles < want) {
@@ -585,9 +647,9 @@ inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, cons
     if (kchunk < 8) kchunk = 8;
     if (kchunk > D.nw[2]) kchunk = (int)D.nw[2];
   }
-  const int smem = WY * mapped_stage_vals<T> * (int)sizeof(T);
+  const int smem = MWY * mapped_stage_vals<T> * (int)sizeof(T);
   cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, WY), smem, st>>>(
+  k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, MWY), smem, st>>>(
       D, TM, coord_terms(TM), PR, tab, ftab, L, O, scheme, kchunk);
 }
 
@@ -617,11 +679,11 @@ __global__ void k_mapped_metrics2d(Dims D, MTerms TM, MPairs PR, const T* __rest
       for (int p = 0; p < PR.n; ++p) {
         const int q = TM.t[PR.p[p].m1].coord;
         const T C = T(TM.t[PR.p[p].m1].coef);
-        const T* t0 = tab + ((int64_t)(p * 3 + 0) * OP_COUNT) * L + ix[0];
-        const T* t1 = tab + ((int64_t)(p * 3 + 1) * OP_COUNT) * L + ix[1];
+        const T* t0 = tab + ((int64_t)(p * 3 + 0) * L + ix[0]) * OP_COUNT;
+        const T* t1 = tab + ((int64_t)(p * 3 + 1) * L + ix[1]) * OP_COUNT;
         // d q / d xi  and  d q / d eta reconstructed to the f-face
-        T qxi = C * (f == 0 ? t0[OP_E1 * L] : t0[OP_V1 * L]) * (f == 1 ? t1[OP_E0 * L] : t1[OP_V0 * L]);
-        T qeta = C * (f == 0 ? t0[OP_E0 * L] : t0[OP_V0 * L]) * (f == 1 ? t1[OP_E1 * L] : t1[OP_V1 * L]);
+        T qxi = C * (f == 0 ? t0[OP_E1] : t0[OP_V1]) * (f == 1 ? t1[OP_E0] : t1[OP_V0]);
+        T qeta = C * (f == 0 ? t0[OP_E0] : t0[OP_V0]) * (f == 1 ? t1[OP_E1] : t1[OP_V1]);
         if (q == 0) {
           Gh[1][1] += qxi;
           Gh[0][1] -= qeta;
@@ -660,11 +722,11 @@ __global__ void k_mapped_metrics1d(Dims D, MTerms TM, const T* __restrict__ ftab
     T Fv[2] = {0, 0}, F1[2] = {0, 0}, F2[2] = {0, 0};
     for (int m = 0; m < TM.n; ++m)
       for (int c = 0; c < 2; ++c) {
-        const T* a = ftab + ((int64_t)(m * 3) * 4) * L1 + i + c;
+        const T* a = ftab + ((int64_t)(m * 3) * L1 + i + c) * 4;
         const T cf = T(TM.t[m].coef);
-        Fv[c] += cf * a[1 * L1];
-        F1[c] += cf * a[2 * L1];
-        F2[c] += cf * a[3 * L1];
+        Fv[c] += cf * a[1];
+        F1[c] += cf * a[2];
+        F2[c] += cf * a[3];
       }
     if (what & 1) {
       if (O.cell_fwd) { O.cell_fwd[2 * i] = Fv[0]; O.cell_fwd[2 * i + 1] = Fv[0]; }
@@ -780,9 +842,11 @@ inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, dou
   U.coef = 1.0;
   for (int d = 0; d < 3; ++d) { U.kind[d] = 0; U.a[d] = U.b[d] = 0.0; }
   M.pairs.n = 0;
+  for (int c = 0; c < 4; ++c) M.pairs.cstart[c] = 0;
   if (D.dim == 3) {
     for (int col = 0; col < 3; ++col) {
       const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+      M.pairs.cstart[col] = M.pairs.n;
       for (int m1 = 0; m1 < nt; ++m1)
         for (int m2 = 0; m2 < nt; ++m2)
           if (M.terms.t[m1].coord == q1 && M.terms.t[m2].coord == q2) {
@@ -790,6 +854,9 @@ inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, dou
             M.pairs.p[M.pairs.n++] = MPair{m1, m2, col};
           }
     }
+    M.pairs.cstart[3] = M.pairs.n;
+    for (int p = 0; p < M.pairs.n; ++p) M.pairs.coef[p] = M.terms.t[M.pairs.p[p].m1].coef * M.terms.t[M.pairs.p[p].m2].coef;
+    M.pairs.coef[M.pairs.n] = 0.0;
   } else if (D.dim == 2) {
     for (int m1 = 0; m1 < nt; ++m1) {
       if (M.pairs.n >= M_MAXP) return 2;
