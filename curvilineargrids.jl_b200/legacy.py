@@ -121,3 +121,47 @@ def set_node_coordinates(mesh, x, y, z):
     import torch
     for t, a in zip(mesh._nodes, (x, y, z)):
         t.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).transpose(2, 1, 0))))
+
+
+class SphericalBasisCurvilinearGrid3D(CurvilinearGrid3D):
+    """SphericalBasisCurvilinearGrid3D(r, θ, ϕ, :meg6 | :meg6_symmetric) — 3d_spherical_basis.jl:51-215.
+
+    The reference stores (r, θ, ϕ) as the node coordinates and runs the SAME MEG6 pipeline on them
+    (`update!`, 3d_spherical_basis.jl:191-215: centroid kernel :269-315 = the eight-node mean, then
+    `update_metrics!`): the metrics are taken in the stored coordinates.  The only extra is
+    `cartesian_node_coordinates` (x = r sinθ cosϕ, y = r sinθ sinϕ, z = r cosθ, :217-252), refreshed by
+    `update`.  Here: the device pipeline of CurvilinearGrid3D on the (r, θ, ϕ) arrays plus that conversion as
+    device tensor arithmetic (a read-side convenience, not a metric kernel)."""
+
+    def __init__(self, r, theta, phi, discretization_scheme="meg6", **kw):
+        super().__init__(r, theta, phi, discretization_scheme, **kw)
+        self._refresh_cartesian()
+
+    def _refresh_cartesian(self):
+        import torch
+        r, th, ph = self._nodes
+        st = torch.sin(th)
+        self._xyz = (r * st * torch.cos(ph), r * st * torch.sin(ph), r * torch.cos(th))
+
+    @property
+    def node_coordinates(self):
+        return {"r": self._nodes[0], "θ": self._nodes[1], "ϕ": self._nodes[2]}
+
+    @property
+    def centroid_coordinates(self):
+        return {"r": self._v(self._cent[0]), "θ": self._v(self._cent[1]), "ϕ": self._v(self._cent[2])}
+
+    @property
+    def cartesian_node_coordinates(self):
+        return {"x": self._xyz[0], "y": self._xyz[1], "z": self._xyz[2]}
+
+
+_update_3d = update
+
+
+def update(mesh, force=False, include_halo_region=False):  # noqa: F811
+    """update!(mesh, force, include_halo_region) — 3d.jl:472-493 / 3d_spherical_basis.jl:191-215."""
+    out = _update_3d(mesh, force, include_halo_region)
+    if isinstance(mesh, SphericalBasisCurvilinearGrid3D) and hasattr(mesh, "_xyz") and (not mesh.is_static or force):
+        mesh._refresh_cartesian()
+    return out

@@ -76,3 +76,32 @@ def test_legacy_errors_and_static(cg):
     with pytest.warns(UserWarning):
         cg.legacy.update(mesh, False, False)
     assert mesh.launches > 0
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_legacy_spherical_basis_grid(cg, oracle, symmetric):
+    """SphericalBasisCurvilinearGrid3D (3d_spherical_basis.jl:191-315): the MEG6 pipeline on the stored (r, θ, ϕ)
+    coordinates + Cartesian node coordinates."""
+    terms = cg.workloads.spherical_rtp_3d_terms((12, 11, 13))
+    nodes = cg.workloads.nodes_from_terms(terms, 0.0, (12, 11, 13), 0)
+    ref = oracle.legacy_meg6_3d(nodes, 5, halo_coords_included=False, symmetric=symmetric)
+    mesh = cg.legacy.SphericalBasisCurvilinearGrid3D(*nodes, "meg6_symmetric" if symmetric else "meg6")
+    sel = _dom(ref["nfull"])
+    assert np.array_equal(mesh._cent.cpu().numpy(), ref["centroid"])
+    for got, want in ((mesh._cell.cpu().numpy(), ref["cell"]), (mesh._edge.cpu().numpy(), ref["edge"])):
+        g, w = got[..., sel], want[..., sel]
+        scale = np.abs(w).max(axis=-1, keepdims=True)
+        scale[scale == 0] = 1.0
+        assert (np.abs(g - w) / scale).max() <= 1e-13
+    r, th, ph = (np.asarray(a).transpose(2, 1, 0) for a in nodes)
+    c = mesh.cartesian_node_coordinates
+    np.testing.assert_allclose(c["x"].cpu().numpy(), r * np.sin(th) * np.cos(ph), rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(c["y"].cpu().numpy(), r * np.sin(th) * np.sin(ph), rtol=1e-14, atol=1e-15)
+    np.testing.assert_allclose(c["z"].cpu().numpy(), r * np.cos(th), rtol=1e-14, atol=1e-15)
+    assert set(mesh.centroid_coordinates) == {"r", "θ", "ϕ"}
+    # the centroid radius is the eight-node mean
+    assert abs(float(mesh.centroid_coordinates["r"][5, 5, 5]) - r[0:2, 0:2, 0:2].mean()) < 1e-14
+    # moving mesh: new nodes -> update refreshes metrics and Cartesian coordinates
+    cg.legacy.set_node_coordinates(mesh, nodes[0] * 1.5, nodes[1], nodes[2])
+    cg.legacy.update(mesh, True, False)
+    np.testing.assert_allclose(mesh.cartesian_node_coordinates["z"].cpu().numpy(), 1.5 * r * np.cos(th), rtol=1e-14, atol=1e-15)
