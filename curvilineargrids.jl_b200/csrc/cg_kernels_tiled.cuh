@@ -494,6 +494,9 @@ struct Stage {
   T* g;   // global address of the chunk's first value
   T* s;   // shared address of the chunk's first value (same 16-B phase as g)
   CG_D Stage(T* arr, int64_t cl0, T* sbuf) {
+#ifdef CG_STORE_WRAP  // experiment: every store lands in the first 16 MB of its array (L2-resident): SM-side store cost
+    cl0 &= (int64_t)0x1ffff;
+#endif
     g = arr + (int64_t)E * cl0;
     constexpr int A = 16 / (int)sizeof(T);
     if constexpr ((E * sizeof(T)) % 16 == 0) s = sbuf;  // array bases are 16-B aligned (cudaMalloc / checked on bind)
