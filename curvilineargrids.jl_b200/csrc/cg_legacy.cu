@@ -270,6 +270,37 @@ __global__ void k_legacy_div9(LShape S, LBox dom, const double* __restrict__ hat
   }
 }
 
+// 2-D: _centroid_coordinates_kernel! (2d.jl:734-746), same summation order
+__global__ void k_legacy_centroid2d(LShape S, LBox dom, const double* __restrict__ xn, const double* __restrict__ yn,
+                                    int off, int nn0, double* cx, double* cy) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const long long sn1 = nn0;
+    const long long b = (c_[0] - off) + sn1 * (c_[1] - off);
+    const double *ax = xn + b, *ay = yn + b;
+    cx[I] = 0.25 * (ax[0] + ax[1] + ax[1 + sn1] + ax[sn1]);
+    cy[I] = 0.25 * (ay[0] + ay[1] + ay[1 + sn1] + ay[sn1]);
+  }
+}
+
+// inverse_metric_2d_kernel! (conservative_metrics.jl:218-236, StaticArrays det / inv of [x_xi x_eta; y_xi y_eta]) and
+// the hatted metrics = inverse * J (:205-210); fwd = [x_xi, x_eta, y_xi, y_eta][nc]
+__global__ void k_legacy_inv2d(LShape S, LBox dom, const double* __restrict__ fwd, long long nc, double* __restrict__ J,
+                               double* __restrict__ inv, double* __restrict__ hat) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const double a11 = fwd[I], a12 = fwd[nc + I], a21 = fwd[2 * nc + I], a22 = fwd[3 * nc + I];
+    const double d = a11 * a22 - a12 * a21;
+    const double v[4] = {a22 / d, -(a12 / d), -(a21 / d), a11 / d};  // xi_x, xi_y, eta_x, eta_y
+    J[I] = d;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      inv[m * nc + I] = v[m];
+      hat[m * nc + I] = v[m] * d;
+    }
+  }
+}
+
 int blocks_for(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = 148LL * 32;
@@ -384,6 +415,94 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
     }
   }
   (void)tmp;
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "legacy kernels: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  if (launches) *launches = nl;
+  return CG_OK;
+}
+
+// see include/curvigrid_cuda.h
+extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const double* y, const int64_t* nnode, int nhalo,
+                                        int halo_coords_included, double* cell, double* edge, double* centroid,
+                                        double* scratch, size_t scratch_bytes, void* stream, uint64_t* launches) {
+  g_legacy_err[0] = 0;
+  if (!x || !y || !nnode || !cell || !edge || !scratch) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_meg6_update_2d: NULL argument");
+    return CG_ERR_ARG;
+  }
+  if (nhalo < 5) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "MEG6 needs nhalo >= 5 (DiscretizationSchemes.jl:53-60)");
+    return CG_ERR_ARG;
+  }
+  LShape S;
+  LBox full, dom;
+  for (int d = 0; d < 2; ++d) {
+    const int64_t nf = (halo_coords_included ? nnode[d] : nnode[d] + 2 * nhalo) - 1;
+    if (nf - 2 * nhalo < 6) {
+      snprintf(g_legacy_err, sizeof g_legacy_err, "MEG6 one-sided edge stencils need >= 6 interior cells per axis");
+      return CG_ERR_ARG;
+    }
+    S.n[d] = (int)nf;
+    full.lo[d] = 0;
+    full.hi[d] = (int)nf;
+    dom.lo[d] = nhalo;
+    dom.hi[d] = (int)nf - nhalo;
+  }
+  S.n[2] = 1;
+  full.lo[2] = dom.lo[2] = 0;
+  full.hi[2] = dom.hi[2] = 1;
+  S.st[0] = 1;
+  S.st[1] = S.n[0];
+  S.st[2] = (long long)S.n[0] * S.n[1];
+  const long long nc = (long long)S.n[0] * S.n[1];
+  if (scratch_bytes < (size_t)(4 * nc) * sizeof(double)) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "scratch too small: need %lld bytes", (long long)(4 * nc * 8));
+    return CG_ERR_ARG;
+  }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cudaSetDevice: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const LBox md = halo_coords_included ? full : dom;
+  const int whole = halo_coords_included ? 1 : 0;
+  uint64_t nl = 0;
+  double *cx = scratch, *cy = scratch + nc, *d1 = scratch + 2 * nc, *d2 = scratch + 3 * nc;
+  cudaMemsetAsync(cell, 0, (size_t)13 * nc * sizeof(double), st);
+  cudaMemsetAsync(edge, 0, (size_t)18 * nc * sizeof(double), st);
+  cudaMemsetAsync(scratch, 0, (size_t)4 * nc * sizeof(double), st);
+  const int bl = blocks_for(box_count(md));
+  k_legacy_centroid2d<<<bl, 256, 0, st>>>(S, md, x, y, halo_coords_included ? 0 : nhalo, (int)nnode[0], cx, cy);
+  ++nl;
+  if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)2 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  double* C[2] = {cx, cy};
+  double* J = cell;
+  double* fwd = cell + nc;      // [q*2+axis]
+  double* inv = cell + 5 * nc;  // xi_x, xi_y, eta_x, eta_y
+  double* hat = cell + 9 * nc;
+  for (int q = 0; q < 2; ++q)
+    for (int ax = 0; ax < 2; ++ax) {  // forward_metrics.jl:36-60
+      k_legacy_first<<<bl, 256, 0, st>>>(S, md, ax, C[q], d1);
+      k_legacy_second<<<bl, 256, 0, st>>>(S, md, ax, C[q], d1, d2);
+      k_legacy_meg<0><<<bl, 256, 0, st>>>(S, md, ax, C[q], d1, d2, fwd + (long long)(q * 2 + ax) * nc, 1.0);
+      nl += 3;
+    }
+  k_legacy_inv2d<<<bl, 256, 0, st>>>(S, md, fwd, nc, J, inv, hat);
+  ++nl;
+  for (int ax = 0; ax < 2; ++ax) {  // MetricDiscretizationSchemes.jl:58-89
+    double* E = edge + (long long)ax * 9 * nc;
+    for (int m = 0; m < 9; ++m) {
+      const double* phi = m == 0 ? J : cell + (long long)(4 + m) * nc;  // J, inv 0..3, hat 0..3
+      k_legacy_first<<<bl, 256, 0, st>>>(S, md, ax, phi, d1);
+      k_legacy_second<<<bl, 256, 0, st>>>(S, md, ax, phi, d1, d2);
+      k_legacy_interp<<<bl, 256, 0, st>>>(S, md, ax, whole, phi, d1, d2, E + (long long)m * nc);
+      nl += 3;
+    }
+  }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     snprintf(g_legacy_err, sizeof g_legacy_err, "legacy kernels: %s", cudaGetErrorString(ce));

@@ -165,3 +165,102 @@ def update(mesh, force=False, include_halo_region=False):  # noqa: F811
     if isinstance(mesh, SphericalBasisCurvilinearGrid3D) and hasattr(mesh, "_xyz") and (not mesh.is_static or force):
         mesh._refresh_cartesian()
     return out
+
+
+class CurvilinearGrid2D:
+    """CurvilinearGrid2D(x, y, :meg6 | :meg6_symmetric; halo_coords_included) — 2d.jl:120-200, `update!` :616-637.
+
+    Device pipeline: cg_legacy_meg6_update_2d (centroids, MEG6 forward metrics, inverse = inv [x_ξ x_η; y_ξ y_η],
+    hatted = inverse * J, edge interpolation).  In 2-D the symmetric scheme is the same computation
+    (conservative_metrics.jl:417-421).  SoA views in the reference's naming, arrays shaped [nj, ni]."""
+    nhalo = 5
+
+    def __init__(self, x, y, discretization_scheme="meg6", *, device=None, halo_coords_included=False, is_static=False,
+                 init_metrics=True):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("curvigrid: a CUDA device is required (no CPU fallback)")
+        key = str(discretization_scheme).lower().lstrip(":")
+        if key not in _SCHEMES:
+            raise ValueError(f"Unknown or unsupported discretization scheme {discretization_scheme!r}; "
+                             "use :meg6 or :meg6_symmetric")
+        self.symmetric = _SCHEMES[key]
+        self.discretization_scheme_name = key
+        self.device = int(torch.cuda.current_device() if device is None else device)
+        self.halo_coords_included = bool(halo_coords_included)
+        self.is_static = bool(is_static)
+        shp = tuple(np.shape(x))
+        if tuple(np.shape(y)) != shp or len(shp) != 2:
+            raise ValueError("Size mismatch for the given x, y coordinate arrays, they must all be the same")
+        self.nnodes = shp
+        h = self.nhalo
+        self.celldims_full = tuple(s - 1 + (0 if halo_coords_included else 2 * h) for s in shp)
+        dev = f"cuda:{self.device}"
+        self._nodes = [torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)).to(dev) for a in (x, y)]
+        nc = int(np.prod(self.celldims_full))
+        self._cell = torch.zeros((13, nc), dtype=torch.float64, device=dev)
+        self._edge = torch.zeros((2, 9, nc), dtype=torch.float64, device=dev)
+        self._cent = torch.zeros((2, nc), dtype=torch.float64, device=dev)
+        self._scratch = torch.empty((4, nc), dtype=torch.float64, device=dev)
+        self.launches = 0
+        if init_metrics:
+            update2d(self, True, self.halo_coords_included)
+
+    def _v(self, t):
+        return t.view(tuple(reversed(self.celldims_full)))
+
+    @property
+    def centroid_coordinates(self):
+        return {"x": self._v(self._cent[0]), "y": self._v(self._cent[1])}
+
+    @property
+    def cell_center_metrics(self):
+        c = self._cell
+        out = {"J": self._v(c[0])}
+        for q in range(2):
+            out[_X[q]] = {_AX[a]: self._v(c[1 + 2 * q + a]) for a in range(2)}
+        for r in range(2):
+            out[_AX[r]] = {_X[k]: self._v(c[5 + 2 * r + k]) for k in range(2)}
+            out[_AX[r] + "̂"] = {_X[k]: self._v(c[9 + 2 * r + k]) for k in range(2)}
+        return out
+
+    @property
+    def edge_metrics(self):
+        names = ("i₊½", "j₊½")
+        out = {}
+        for ax in range(2):
+            e = self._edge[ax]
+            d = {"J": self._v(e[0])}
+            for r in range(2):
+                d[_AX[r]] = {_X[k]: self._v(e[1 + 2 * r + k]) for k in range(2)}
+                d[_AX[r] + "̂"] = {_X[k]: self._v(e[5 + 2 * r + k]) for k in range(2)}
+            out[names[ax]] = d
+        return out
+
+
+def update2d(mesh, force=False, include_halo_region=False):
+    """update!(mesh::AbstractCurvilinearGrid2D, force, include_halo_region) — 2d.jl:616-637 (a static grid without
+    `force` is an error there, unlike the 3-D warning)."""
+    import torch
+    if mesh.is_static and not force:
+        raise RuntimeError("Attempting to update grid metrics when grid.is_static = true!")
+    if bool(include_halo_region) != mesh.halo_coords_included:
+        raise ValueError("include_halo_region must match halo_coords_included")
+    nn = (ctypes.c_int64 * 2)(*mesh.nnodes)
+    nl = ctypes.c_uint64()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream(mesh.device).cuda_stream)
+    rc = L.lib().cg_legacy_meg6_update_2d(
+        mesh.device, p(mesh._nodes[0]), p(mesh._nodes[1]), nn, mesh.nhalo, int(mesh.halo_coords_included),
+        p(mesh._cell), p(mesh._edge), p(mesh._cent), p(mesh._scratch), ctypes.c_size_t(mesh._scratch.numel() * 8), st,
+        ctypes.byref(nl))
+    if rc != L.CG_OK:
+        msg = L.lib().cg_legacy_last_error().decode()
+        raise (L.CurvigridArgumentError if rc == L.CG_ERR_ARG else L.CurvigridError)(rc, msg)
+    # _check_valid_metrics (2d.jl:748-751): the Jacobian must be finite on cell.domain
+    h = mesh.nhalo
+    J = mesh._v(mesh._cell[0])
+    if not bool(torch.isfinite(J[h:-h, h:-h]).all()):
+        raise AssertionError("non-finite cell-centre Jacobian on cell.domain")
+    mesh.launches = int(nl.value)
+    return None

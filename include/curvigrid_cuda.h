@@ -225,6 +225,19 @@ int cg_legacy_meg6_update_3d(int device, const double* x, const double* y, const
                              int nhalo, int halo_coords_included, int symmetric, double* cell, double* edge,
                              double* centroid, double* scratch, size_t scratch_bytes, void* stream,
                              uint64_t* launches);
+/*
+ * Legacy 2-D path: CurvilinearGrid2D(x, y, :meg6 | :meg6_symmetric) `update!(mesh, force, include_halo_region)`
+ * (src/grids/curvilinear_mapped_grids/2d.jl:616-637, centroids :734-746; forward_metrics.jl:36-84; the 2-D
+ * conservative metrics are inverse * J, conservative_metrics.jl:177-236, and the symmetric scheme forwards to them,
+ * :417-421).  x, y: DEVICE node arrays of extents nnode[2].  With ncell = prod(cell.full dims):
+ *   cell     [13][ncell]   0 J | 1..4 d x_q/d xi_a at [1+2q+a] | 5..8 xi_x, xi_y, eta_x, eta_y | 9..12 hatted
+ *   edge     [2][9][ncell] per axis: 0 J | 1..4 inverse | 5..8 hatted; storage index I = face I+1/2
+ *   centroid [2][ncell]    (may be NULL)
+ *   scratch  >= 4*ncell doubles of device memory
+ */
+int cg_legacy_meg6_update_2d(int device, const double* x, const double* y, const int64_t* nnode, int nhalo,
+                             int halo_coords_included, double* cell, double* edge, double* centroid, double* scratch,
+                             size_t scratch_bytes, void* stream, uint64_t* launches);
 const char* cg_legacy_last_error(void);
 
 #ifdef __cplusplus

@@ -328,4 +328,77 @@ inline void legacy_meg6_3d(const double* xn, const double* yn, const double* zn,
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// 2-D legacy grid: CurvilinearGrid2D(x, y, :meg6 | :meg6_symmetric) `update!` (2d.jl:616-637, centroids :734-746):
+// forward_metrics! (forward_metrics.jl:36-84), conservative_metrics! 2-D (conservative_metrics.jl:177-236; the
+// symmetric variant forwards to it, :417-421) and update_edge_metrics! (MetricDiscretizationSchemes.jl:58-89).
+// The arrays are handled as (ni, nj, 1) boxes by the same passes as the 3-D pipeline.
+//   cell [13][ncell]:   0 J | 1..4 fwd[q*2+axis] | 5..8 inv (xi_x, xi_y, eta_x, eta_y) | 9..12 hat = inv * J
+//   edge [2][9][ncell]: 0 J | 1..4 inv | 5..8 hat      (storage index I = face I + 1/2; `.t` arrays omitted)
+// ---------------------------------------------------------------------------
+enum { L2_J = 0, L2_FWD = 1, L2_INV = 5, L2_HAT = 9, L2_NCELL = 13, L2_NEDGE = 9 };
+
+inline void legacy_meg6_2d(const double* xn, const double* yn, const int64_t* nnode, int nhalo, bool halo_coords_included,
+                           double* cell, double* edge, double* cent) {
+  Grid g;
+  for (int d = 0; d < 2; ++d) g.S.n[d] = (halo_coords_included ? nnode[d] : nnode[d] + 2 * nhalo) - 1;
+  g.S.n[2] = 1;
+  g.S.st[0] = 1;
+  g.S.st[1] = g.S.n[0];
+  g.S.st[2] = g.S.n[0] * g.S.n[1];
+  const int64_t nc = g.S.total();
+  Box full, dom;
+  for (int d = 0; d < 2; ++d) {
+    full.lo[d] = 0;
+    full.hi[d] = g.S.n[d];
+    dom.lo[d] = nhalo;
+    dom.hi[d] = g.S.n[d] - nhalo;
+  }
+  full.lo[2] = dom.lo[2] = 0;
+  full.hi[2] = dom.hi[2] = 1;
+  const Box md = halo_coords_included ? full : dom;
+  const int64_t off = halo_coords_included ? 0 : nhalo;
+  const int64_t nn0 = nnode[0];
+  auto node = [&](const double* a, int64_t i, int64_t j) { return a[(i - off) + nn0 * (j - off)]; };
+  std::vector<double> cx(nc, 0.0), cy(nc, 0.0);
+  const double* N[2] = {xn, yn};
+  double* C[2] = {cx.data(), cy.data()};
+  for (int q = 0; q < 2; ++q) {
+    const double* a = N[q];
+    double* c = C[q];
+    for (int64_t j = md.lo[1]; j < md.hi[1]; ++j)  // 2d.jl:734-746
+      for (int64_t i = md.lo[0]; i < md.hi[0]; ++i)
+        c[g.at(i, j, 0)] = 0.25 * (node(a, i, j) + node(a, i + 1, j) + node(a, i + 1, j + 1) + node(a, i, j + 1));
+    if (cent)
+      for (int64_t I = 0; I < nc; ++I) cent[q * nc + I] = c[I];
+  }
+  for (int64_t I = 0; I < (int64_t)L2_NCELL * nc; ++I) cell[I] = 0.0;
+  for (int64_t I = 0; I < (int64_t)2 * L2_NEDGE * nc; ++I) edge[I] = 0.0;
+  std::vector<double> d1(nc, 0.0), d2(nc, 0.0);
+  auto fwd = [&](int q, int ax) { return cell + (int64_t)(L2_FWD + q * 2 + ax) * nc; };
+  double* J = cell;
+  for (int q = 0; q < 2; ++q)
+    for (int ax = 0; ax < 2; ++ax) cell_center_derivatives(g, fwd(q, ax), d2.data(), d1.data(), C[q], ax, md);
+  double* inv = cell + (int64_t)L2_INV * nc;
+  double* hat = cell + (int64_t)L2_HAT * nc;
+  g.each(md, [&](int64_t I) {
+    // StaticArrays det / inv of [x_xi x_eta; y_xi y_eta] (inverse_metric_2d_kernel!, conservative_metrics.jl:218-236)
+    const double a11 = fwd(0, 0)[I], a12 = fwd(0, 1)[I], a21 = fwd(1, 0)[I], a22 = fwd(1, 1)[I];
+    const double d = a11 * a22 - a12 * a21;
+    J[I] = d;
+    inv[0 * nc + I] = a22 / d;      // xi_x
+    inv[1 * nc + I] = -(a12 / d);   // xi_y
+    inv[2 * nc + I] = -(a21 / d);   // eta_x
+    inv[3 * nc + I] = a11 / d;      // eta_y
+    for (int m = 0; m < 4; ++m) hat[m * nc + I] = inv[m * nc + I] * d;
+  });
+  for (int ax = 0; ax < 2; ++ax) {
+    double* E = edge + (int64_t)ax * L2_NEDGE * nc;
+    interpolate_to_edge(g, E, d2.data(), d1.data(), J, ax, md);
+    for (int m = 0; m < 8; ++m)
+      interpolate_to_edge(g, E + (int64_t)(1 + m) * nc, d2.data(), d1.data(), cell + (int64_t)(L2_INV + m) * nc, ax, md);
+  }
+}
+
 }  // namespace cgl

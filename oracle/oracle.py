@@ -183,3 +183,20 @@ def legacy_meg6_3d(nodes, nhalo=5, halo_coords_included=False, symmetric=False):
                              ctypes.c_int(int(halo_coords_included)), ctypes.c_int(int(symmetric)), _dp(cell),
                              _dp(edge), _dp(cent))
     return {"cell": cell, "edge": edge, "centroid": cent, "nfull": nfull}
+
+
+def legacy_meg6_2d(nodes, nhalo=5, halo_coords_included=False):
+    """Legacy CurvilinearGrid2D(x,y,:meg6[_symmetric]) update! (oracle/legacy_meg6.hpp; the symmetric scheme is the
+    same computation in 2-D).  Returns dict: cell [13, ncell] (J, fwd 4, inv 4, hat 4), edge [2, 9, ncell]
+    (J, inv 4, hat 4), centroid [2, ncell], nfull; arrays are Fortran-ordered over cells."""
+    nodes = [np.asarray(a, dtype=np.float64) for a in nodes]
+    flat = [np.ascontiguousarray(a.ravel(order="F")) for a in nodes]
+    nn = np.array(nodes[0].shape, dtype=np.int64)
+    nfull = tuple(int(s - 1 + (0 if halo_coords_included else 2 * nhalo)) for s in nodes[0].shape)
+    nc = int(np.prod(nfull))
+    cell = np.zeros((13, nc))
+    edge = np.zeros((2, 9, nc))
+    cent = np.zeros((2, nc))
+    lib().cgo_legacy_meg6_2d(_dp(flat[0]), _dp(flat[1]), _ip(nn), ctypes.c_int(nhalo),
+                             ctypes.c_int(int(halo_coords_included)), _dp(cell), _dp(edge), _dp(cent))
+    return {"cell": cell, "edge": edge, "centroid": cent, "nfull": nfull}

@@ -105,3 +105,50 @@ def test_legacy_spherical_basis_grid(cg, oracle, symmetric):
     cg.legacy.set_node_coordinates(mesh, nodes[0] * 1.5, nodes[1], nodes[2])
     cg.legacy.update(mesh, True, False)
     np.testing.assert_allclose(mesh.cartesian_node_coordinates["z"].cpu().numpy(), 1.5 * r * np.cos(th), rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("halo_included", [False, True])
+def test_legacy_2d_matches_oracle(cg, oracle, halo_included):
+    """CurvilinearGrid2D :meg6 (2d.jl:616-746) against the array-pass oracle."""
+    n = (23, 19) if halo_included else (14, 12)
+    x, y = cg.workloads.wavy_nodes_2d(*n)
+    ref = oracle.legacy_meg6_2d((x, y), 5, halo_coords_included=halo_included)
+    mesh = cg.legacy.CurvilinearGrid2D(x, y, "meg6", halo_coords_included=halo_included)
+    assert mesh.celldims_full == ref["nfull"]
+    assert np.array_equal(mesh._cent.cpu().numpy(), ref["centroid"])
+    for name, got, want in (("cell", mesh._cell.cpu().numpy(), ref["cell"]), ("edge", mesh._edge.cpu().numpy(), ref["edge"])):
+        scale = np.abs(want).max(axis=-1, keepdims=True)
+        scale[scale == 0] = 1.0
+        err = (np.abs(got - want) / scale).max()
+        assert err <= 1e-13, (name, err)
+        assert (got == want).mean() > 0.99, (name, (got == want).mean())
+    sym = cg.legacy.CurvilinearGrid2D(x, y, "meg6_symmetric", halo_coords_included=halo_included)
+    assert np.array_equal(sym._cell.cpu().numpy(), mesh._cell.cpu().numpy())   # conservative_metrics.jl:417-421
+
+
+def test_legacy_2d_known_answers_and_errors(cg):
+    """test_discretizations.jl:148-191 style: x = i, y = 2 j -> x_xi = 1, y_eta = 2, xi_x = 1, eta_y = 1/2, J = 2."""
+    ni, nj = 12, 10
+    x = np.arange(ni, dtype=float)[:, None] * np.ones((1, nj))
+    y = 2.0 * np.arange(nj, dtype=float)[None, :] * np.ones((ni, 1))
+    mesh = cg.legacy.CurvilinearGrid2D(x, y, "meg6")
+    m, h = mesh.cell_center_metrics, 5
+    sl = (slice(h, -h),) * 2
+    assert abs(m["x₁"]["ξ"][sl].cpu().numpy() - 1).max() < 1e-13
+    assert abs(m["x₂"]["η"][sl].cpu().numpy() - 2).max() < 1e-13
+    assert abs(m["x₁"]["η"][sl].cpu().numpy()).max() == 0.0
+    assert abs(m["J"][sl].cpu().numpy() - 2).max() < 1e-13
+    assert abs(m["ξ"]["x₁"][sl].cpu().numpy() - 1).max() < 1e-13
+    assert abs(m["η"]["x₂"][sl].cpu().numpy() - 0.5).max() < 1e-13
+    assert abs(m["ξ̂"]["x₁"][sl].cpu().numpy() - 2).max() < 1e-13
+    assert abs(m["η̂"]["x₂"][sl].cpu().numpy() - 1).max() < 1e-13
+    e = mesh.edge_metrics["j₊½"]
+    assert abs(e["η̂"]["x₂"][sl].cpu().numpy() - 1).max() < 1e-13
+    assert abs(e["J"][sl].cpu().numpy() - 2).max() < 1e-13
+    with pytest.raises(ValueError):
+        cg.legacy.CurvilinearGrid2D(x, y[:-1], "meg6")
+    with pytest.raises(cg.CurvigridArgumentError):
+        cg.legacy.CurvilinearGrid2D(x[:5], y[:5], "meg6")   # < 6 interior cells
+    static = cg.legacy.CurvilinearGrid2D(x, y, "meg6", is_static=True)
+    with pytest.raises(RuntimeError):
+        cg.legacy.update2d(static, False, False)

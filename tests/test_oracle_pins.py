@@ -241,3 +241,37 @@ def test_legacy_wavy_gcl_small(oracle, symmetric):
             tot = tot + A[tuple(hi)] - A[tuple(lo)]
         worst = max(worst, np.abs(tot).max())
     assert worst < 5e-14
+
+
+def test_legacy_2d_known_answers(oracle):
+    """CurvilinearGrid2D legacy pipeline: x = i, y = 2 j (test_discretizations.jl:148-191) and a rotated / sheared
+    affine map (every stencil is exact on linear fields): forward metrics, J, inverse and hatted metrics, edges."""
+    ni, nj, h = 12, 11, 5
+    i = np.arange(ni, dtype=float)[:, None] * np.ones((1, nj))
+    j = np.arange(nj, dtype=float)[None, :] * np.ones((ni, 1))
+    A = np.array([[1.3, 0.4], [-0.2, 0.9]])
+    x, y = A[0, 0] * i + A[0, 1] * j + 0.7, A[1, 0] * i + A[1, 1] * j - 1.1
+    r = oracle.legacy_meg6_2d((x, y), h)
+    nf = r["nfull"]
+    dom = (np.arange(h, nf[0] - h)[:, None] + nf[0] * np.arange(h, nf[1] - h)[None, :]).ravel()
+    c = r["cell"][:, dom]
+    det = np.linalg.det(A)
+    Ainv = np.linalg.inv(A)
+    assert np.abs(c[0] - det).max() < 1e-13
+    for q in range(2):
+        for a in range(2):
+            assert np.abs(c[1 + 2 * q + a] - A[q, a]).max() < 1e-13
+    for row in range(2):
+        for k in range(2):
+            assert np.abs(c[5 + 2 * row + k] - Ainv[row, k]).max() < 1e-13
+            assert np.abs(c[9 + 2 * row + k] - Ainv[row, k] * det).max() < 1e-13
+    for ax in range(2):
+        e = r["edge"][ax][:, dom]
+        # the one-sided 6-point stencils next to the domain edge amplify round-off of the (constant) input: 1e-12
+        assert np.abs(e[0] - det).max() < 1e-12
+        for m in range(4):
+            assert np.abs(e[1 + m] - Ainv.ravel()[m]).max() < 1e-12
+            assert np.abs(e[5 + m] - Ainv.ravel()[m] * det).max() < 1e-12
+    # centroids are the four-node mean (2d.jl:734-746)
+    cx = r["centroid"][0][dom].reshape(nf[1] - 2 * h, nf[0] - 2 * h)
+    assert abs(cx[0, 0] - 0.25 * (x[0, 0] + x[1, 0] + x[1, 1] + x[0, 1])) < 1e-15
