@@ -256,3 +256,68 @@ def test_host_buffer_entry_point(cg, oracle):
                                           p(out["face_cons"]))
     L.check(rc)
     assert_metrics_close(out, ref, label="host entry point")
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json full sizes (configs 2 and 3): size-independent properties + sampled oracle cells.  The arrays stay on
+# the device (122 GB at 512^3); sampled cells are gathered there.
+# ---------------------------------------------------------------------------
+def _sampled(cg, grid, sample):
+    import torch
+    idx = torch.from_numpy(sample).to(f"cuda:{grid.device}")
+    N = grid.dim
+    K = N * N + 1
+    cm, fm = cg.cell_metrics(grid), cg.face_metrics(grid)
+    pick = lambda t, k: t.reshape(-1, k)[idx].cpu().numpy()
+    return {"cell_fwd": pick(cm.forward, K), "cell_inv": pick(cm.inverse, K),
+            "face_fwd": np.stack([pick(fm[a].forward, K) for a in range(N)]),
+            "face_inv": np.stack([pick(fm[a].inverse, K) for a in range(N)]),
+            "face_cons": np.stack([pick(fm[a].conserved, N * N) for a in range(N)])}
+
+
+def test_3d_512_full_size_properties(cg, oracle):
+    """BASELINE config 3 (3-D DiscreteGrid 512^3 wavy, FULL cell+face, Curvature): GCL at round-off over the whole
+    domain, 64 random cells of cell.full against the oracle, and the exact scaling law of the metrics under
+    x -> 2x (a power of two commutes with every floating-point operation: J -> 8 J, conserved rows -> 4 x, bitwise)."""
+    import torch
+    nodes = cg.workloads.wavy_nodes_3d(513, 513, 513)
+    g = cg.DiscreteGrid(*nodes, 5, cache_mode="lazy")
+    cg.refresh_metrics(g)
+    assert max(cg.gcl(g)) < 5e-13
+    rng = np.random.default_rng(7)
+    nfull = tuple(n + 10 for n in (512, 512, 512))
+    sample = np.sort(rng.choice(int(np.prod(nfull)), size=64, replace=False))
+    got = _sampled(cg, g, sample)
+    ref = oracle.discrete_eval(nodes, 5, "curvature", sample=sample)
+    # 1e-11, not 1e-12: the conserved metrics are O(dx^2) differences of products of O(|x|) coordinates, so BOTH
+    # evaluations carry round-off of order eps * |x| / dx per operation (|x| / dx ~ 500 here; 5.9e-12 observed on
+    # cell.domain).  The tolerance of the north star is met where the mesh is not that fine (tests above, 1e-12).
+    assert_metrics_close(got, ref, rtol=1e-11, label="512^3 sampled")
+    del g
+    torch.cuda.empty_cache()
+    g1 = cg.DiscreteGrid(*nodes, 5, cache_mode="lazy", profile="compact")
+    g2 = cg.DiscreteGrid(*[2.0 * a for a in nodes], 5, cache_mode="lazy", profile="compact")
+    assert torch.equal(cg.cell_metrics(g2), 8.0 * cg.cell_metrics(g1))
+    for a in range(3):
+        assert torch.equal(cg.face_metrics(g2)[a], 4.0 * cg.face_metrics(g1)[a])
+
+
+def test_2d_4096_full_size_properties(cg, oracle):
+    """BASELINE config 2 (2-D DiscreteGrid 4096^2, GradientCorrected): GCL bound of test_2d.jl:183-238 on the whole
+    domain, 256 random cells against the oracle, and the bitwise scaling law under x -> 2x."""
+    import torch
+    nodes = cg.workloads.wavy_nodes_2d(4097, 4097)
+    g = cg.DiscreteGrid(*nodes, 5, conserved_metric_scheme="gradient", cache_mode="lazy")
+    cg.refresh_metrics(g)
+    assert max(cg.gcl(g)) < 5e-15
+    rng = np.random.default_rng(8)
+    sample = np.sort(rng.choice(4106 * 4106, size=256, replace=False))
+    got = _sampled(cg, g, sample)
+    ref = oracle.discrete_eval(nodes, 5, "gradient", sample=sample)
+    assert_metrics_close(got, ref, rtol=1e-11, label="4096^2 sampled")
+    g2 = cg.DiscreteGrid(*[2.0 * a for a in nodes], 5, conserved_metric_scheme="gradient", cache_mode="lazy")
+    f1, f2 = cg.face_metrics(g), cg.face_metrics(g2)
+    for a in range(2):
+        assert torch.equal(f2[a].conserved, 2.0 * f1[a].conserved)      # J inv(F): one power of the scale in 2-D
+        assert torch.equal(f2[a].forward[..., :4], 2.0 * f1[a].forward[..., :4])
+        assert torch.equal(f2[a].forward[..., 4], 4.0 * f1[a].forward[..., 4])
