@@ -264,3 +264,41 @@ def update2d(mesh, force=False, include_halo_region=False):
         raise AssertionError("non-finite cell-centre Jacobian on cell.domain")
     mesh.launches = int(nl.value)
     return None
+
+
+class AxisymmetricGrid2D(CurvilinearGrid2D):
+    """AxisymmetricGrid2D(x, y, snap_to_axis, rotational_axis, :meg6 | :meg6_symmetric) — 2d.jl:511-600; `update!`
+    :644-671: centroids, THEN (if `snap_to_axis`) the first node row / column of node.domain is put on the axis
+    (`_snap_nodes_to_axis`, :814-827: y = 0 for rotational_axis = :x, x = 0 for :y), then the metrics from the
+    centroids.  The snap therefore acts on the node coordinates a later update reads."""
+
+    def __init__(self, x, y, snap_to_axis=True, rotational_axis="x", discretization_scheme="meg6", **kw):
+        axis = str(rotational_axis).lstrip(":")
+        if axis not in ("x", "y"):
+            raise ValueError("rotational_axis must be :x or :y")
+        self.snap_to_axis = bool(snap_to_axis)
+        self.rotational_axis = axis
+        super().__init__(x, y, discretization_scheme, **kw)
+
+    def _snap_nodes_to_axis(self):
+        o = 0 if not self.halo_coords_included else self.nhalo  # node.domain inside the stored node arrays [j, i]
+        n_i, n_j = self.nnodes
+        if self.rotational_axis == "x":
+            self._nodes[1][o, o:n_i - o] = 0.0   # y[domain[:, 1]]
+        else:
+            self._nodes[0][o:n_j - o, o] = 0.0   # x[domain[1, :]]
+
+    @property
+    def node_coordinates(self):
+        return {"x": self._nodes[0], "y": self._nodes[1]}
+
+
+_update_2d = update2d
+
+
+def update2d(mesh, force=False, include_halo_region=False):  # noqa: F811
+    """update!(mesh, force, include_halo_region) for CurvilinearGrid2D (2d.jl:616-637) and AxisymmetricGrid2D (:644-671)."""
+    out = _update_2d(mesh, force, include_halo_region)
+    if isinstance(mesh, AxisymmetricGrid2D) and mesh.snap_to_axis:
+        mesh._snap_nodes_to_axis()
+    return out

@@ -152,3 +152,32 @@ def test_legacy_2d_known_answers_and_errors(cg):
     static = cg.legacy.CurvilinearGrid2D(x, y, "meg6", is_static=True)
     with pytest.raises(RuntimeError):
         cg.legacy.update2d(static, False, False)
+
+
+@pytest.mark.parametrize("axis", ["x", "y"])
+def test_legacy_axisymmetric_2d_snaps_after_centroids(cg, oracle, axis):
+    """AxisymmetricGrid2D update! (2d.jl:644-671): centroids from the nodes as given, then the axis row / column of
+    node.domain is snapped, then the metrics; a second update sees the snapped nodes."""
+    x, y = cg.workloads.wavy_nodes_2d(15, 13)
+    x, y = x + 0.01, y + 0.02                      # first row / column slightly off the axis
+    mesh = cg.legacy.AxisymmetricGrid2D(x, y, True, axis, "meg6")
+    ref = oracle.legacy_meg6_2d((x, y), 5)
+    assert np.array_equal(mesh._cell.cpu().numpy(), cg.legacy.CurvilinearGrid2D(x, y, "meg6")._cell.cpu().numpy())
+    scale = np.abs(ref["cell"]).max(axis=-1, keepdims=True)
+    scale[scale == 0] = 1.0
+    assert (np.abs(mesh._cell.cpu().numpy() - ref["cell"]) / scale).max() <= 1e-13
+    n = mesh.node_coordinates
+    xs, ys = x.copy(), y.copy()
+    if axis == "x":
+        assert float(n["y"][0].abs().max()) == 0.0 and float(n["x"][0].abs().max()) > 0.0
+        ys[:, 0] = 0.0
+    else:
+        assert float(n["x"][:, 0].abs().max()) == 0.0
+        xs[0, :] = 0.0
+    cg.legacy.update2d(mesh, True, False)          # now the metrics of the snapped mesh
+    ref2 = oracle.legacy_meg6_2d((xs, ys), 5)
+    scale = np.abs(ref2["cell"]).max(axis=-1, keepdims=True)
+    scale[scale == 0] = 1.0
+    assert (np.abs(mesh._cell.cpu().numpy() - ref2["cell"]) / scale).max() <= 1e-13
+    with pytest.raises(ValueError):
+        cg.legacy.AxisymmetricGrid2D(x, y, True, "z", "meg6")
