@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the slab axis keeps N cells in total (N^3 split over the GPUs) instead of "
+                         "one slab per GPU; the JSON line says \"scaling\": \"strong\"")
     return ap.parse_args()
 
 
@@ -286,6 +289,9 @@ def run_ours(args, spec):
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     nslab = spec.get("nslab", n)
     ncell_slab = nslab * world  # weak scaling: the grid grows along the slab axis
+    if args.strong:
+        ncell_slab = n          # strong scaling: n cells along the slab axis in total, split over the ranks
+        nslab = n // world
     plan = cg.slabs.make_plan(rank, world, ncell_slab, h)
     lo, hi = plan.required
     if dim == 3:
@@ -438,9 +444,9 @@ def run_ours(args, spec):
         line = {
             "metric": "metric-eval Mcells/s (cell+face, FP64)" if args.dtype == "f64" else "metric-eval Mcells/s (cell+face, FP32)",
             "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": spec["desc"] + (f"; k-slabs over {world} GPUs, grid {n}x{n}x{nslab * world}" if world > 1 and dim == 3 else ""),
+            "config": {"workload": spec["desc"] + (f"; k-slabs over {world} GPUs, grid {n}x{n}x{ncell_slab}" if world > 1 and dim == 3 else ""),
                        "scheme": spec["scheme"], "profile": args.profile, "cells_written": cells_total,
                        "kernel": "tiled" if args.kernel == 1 else "gather",
                        "l2": "inputs+outputs per step far exceed the 126 MB L2 (no flush needed)",

@@ -4,12 +4,12 @@
 // Replaces /root/reference/src/grids/unified_grids/metrics.jl:1850-1877 (cell
 // fill) and :1962-2053 (three face fills) with three warp-autonomous kernels, one
 // per face axis (the xi kernel also writes the cell metrics):
-//   * a warp owns 29 consecutive cells of one j-row (lanes 1..29; lane 0 and lanes
-//     30/31 are the -1 / +1,+2 neighbours the stencil needs) and marches along k;
-//   * xi-neighbours come from warp shuffles, eta-neighbours are recomputed from
-//     the node rows (L1 hits), zeta-neighbours are carried in registers from the
-//     previous plane or looked ahead one plane;
-//   * no shared memory, no block barriers: warps never wait for each other.
+//   * a warp owns 29 (xi kernel) or 31 (eta / zeta kernels) consecutive cells of one row; the remaining lanes are
+//     the -1 / +1,+2 neighbours the stencils need; it marches along k (the eta kernel along j);
+//   * xi-neighbours come from warp shuffles, the neighbours along the marching axis are carried in registers from
+//     the previous step or looked ahead one plane, the third axis is recomputed from the node rows;
+//   * nodes arrive through a per-warp cp.async ring in shared memory, outputs leave through per-warp staging
+//     buffers and TMA bulk stores; no block barriers: warps never wait for each other.
 // Math: DESIGN.md §3 (edge scalars Psi + 4-cell line stencils), same closed forms
 // as tests/closed_form_numpy.py and the gather kernels in cg_kernels_ref.cuh.
 #pragma once
@@ -99,14 +99,6 @@ struct NodeP {
 };
 
 template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
-// L1 prefetch of the node at linear index b for the three coordinates (the marching kernels run at
-// 8 warps/SM: the node rows the NEXT iteration touches first are fetched now)
-template <class T, class IX>
-CG_D void pf3(const NodeP<T, IX>& N, IX b) {
-#pragma unroll
-  for (int q = 0; q < 3; ++q) asm volatile("prefetch.global.L1 [%0];" ::"l"(N.q[q] + b));
-}
-
 // RAW bilinear form of 4 face nodes n[bu][bv] (no normalisation: pure sums and differences)
 //   c0 = 4 * (true c0), cu = 2 * (true cu), cv = 2 * (true cv), cuv = true cuv
 // Every consumer below is bilinear in form coefficients, so the powers of two fold into its constants.
@@ -153,66 +145,14 @@ CG_D PF<T> pair_form(const ZPair<T>& a, const ZPair<T>& b) {
 }
 // ---------------------------------------------------------------------------
 // Per-warp ring of node planes in shared memory.  The marching kernels run at 8 warps/SM, too few to hide a
-// global-load miss, and prefetch.global.L1 does not shorten it (measured).  Each lane therefore copies the
-// node column it owns (plus one spare column, by lane 0) of the plane that is first needed in the NEXT step
-// with cp.async, asynchronously, while the current step computes; all node reads of a step are LDS.
-// Layout [slot][row][coordinate][column]: lanes read consecutive columns (conflict-free).
+// global-load miss, and prefetch.global.L1 does not shorten it (measured).  The plane that is first needed in the
+// NEXT step is therefore copied with cp.async, asynchronously, while the current step computes; all node reads of
+// a step are LDS.  Layout [slot][row][coordinate][column]: lanes read consecutive columns (conflict-free).
 // ---------------------------------------------------------------------------
-constexpr int RING_COLS = 34;  // 32 lanes + the spare columns 32, 33
-template <int ROWS, int SLOTS> constexpr int ring_vals = SLOTS * ROWS * 3 * RING_COLS;
-template <class T> CG_D void cp_async_val(T* sdst, const T* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst);
-  if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
 CG_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 CG_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-template <class T, int ROWS, int SLOTS>
-struct Ring {
-  T* base;
-  CG_D T* row(int plane, int r, int q) const {
-    const int slot = SLOTS == 4 ? (plane & 3) : plane % SLOTS;
-    return base + ((slot * ROWS + r) * 3 + q) * RING_COLS;
-  }
-  // copy all ring rows of one plane: g0 = index of (this lane's column, ring row 0, that plane); lanes
-  // 0 .. NX-1 also copy the spare columns 32 .. 32+NX-1 from gx (same row and plane)
-  template <int NX, class IX>
-  CG_D void fetch(const NodeP<T, IX>& N, int plane, IX g0, IX gx, int lane) const {
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        T* dst = row(plane, r, q);
-        cp_async_val(dst + lane, N.q[q] + g0 + (IX)r * N.s1);
-        if (lane < NX) cp_async_val(dst + 32 + lane, N.q[q] + gx + (IX)r * N.s1);
-      }
-  }
-  // raw form of the zeta-plane `plane`, rows r, r+1, columns lane, lane+1
-  CG_D PF<T> zplane(int plane, int r, int lane) const {
-    PF<T> f;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const T* a = row(plane, r, q) + lane;
-      const T* b = row(plane, r + 1, q) + lane;
-      f.q[q] = raw_form(a[0], a[1], b[0], b[1]);
-    }
-    return f;
-  }
-  // zeta-pair (planes plane, plane+1) of the node column (row r, column c)
-  CG_D ZPair<T> zpair(int plane, int r, int c) const {
-    ZPair<T> p;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const T lo = row(plane, r, q)[c], hi = row(plane + 1, r, q)[c];
-      p.s[q] = hi + lo;
-      p.d[q] = hi - lo;
-    }
-    return p;
-  }
-};
 
-// Ring of the eta / zeta kernels: same layout, but a plane row is fetched with 16-byte cp.async by the first NL
-// lanes.  The padded node arrays have a row pitch that is a multiple of 16 bytes (cg_api.cu: dims()), so the
+// A plane row is fetched with 16-byte cp.async by the first NL lanes.  The padded node arrays have a row pitch that is a multiple of 16 bytes (cg_api.cu: dims()), so the
 // row segment starting at the column i0 rounded DOWN to a 16-byte boundary is aligned; `ph` = i0 mod VEC is the
 // warp-uniform column phase every read adds.  Columns past the end of a row belong to lanes without output.
 template <class T, int ROWS, int SLOTS>
@@ -549,12 +489,6 @@ CG_D void put9(T* o, const T (&M)[3][3]) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) o[r + 3 * c] = M[r][c];
 }
-
-struct March {
-  int64_t i, ic, j;
-  int lane;
-  bool out_ok;
-};
 
 // ===========================================================================
 // Kernel A: cell metrics + xi-face metrics.  f = xi, s = eta, t = zeta.
