@@ -6,7 +6,7 @@ as `curvigrid_b200` (repo-root shim) because of the dot in the name.
 from . import _lib, legacy, slabs, workloads  # noqa: F401
 from ._lib import CurvigridArgumentError, CurvigridError  # noqa: F401
 from .grids import (  # noqa: F401
-    CurvatureCorrectedReconstruction, DiscreteGrid, EndpointAverageReconstruction, GradientCorrectedReconstruction,
+    ADThomasLombardMetric, CurvatureCorrectedReconstruction, DiscreteGrid, EndpointAverageReconstruction, GradientCorrectedReconstruction,
     MappedGrid, cell_metrics, cell_metrics_valid, cellvolume, cellvolumes, face_flux_geometry, face_flux_geometry_arrays, face_metrics, face_metrics_valid,
     gcl, invalidate_cell_metrics, invalidate_face_metrics, local_grid, refresh_cell_metrics, refresh_face_metrics,
     refresh_metrics, update)

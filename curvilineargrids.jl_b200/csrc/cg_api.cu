@@ -46,6 +46,7 @@ struct Buf {
 
 struct cg_grid {
   int device = 0, dim = 0, dtype = 0, nhalo = 0, scheme = 2, profile = 0;
+  bool adtl = false;  // ADThomasLombardMetric (3-D MappedGrid): Curvature evaluation + k_mapped_adtl_faces
   int64_t ncell[3] = {1, 1, 1};
   int64_t nw[3] = {1, 1, 1}, w0[3] = {0, 0, 0}, goff[3] = {0, 0, 0};
   int kind = 0;  // 0 unset, 1 discrete, 2 mapped
@@ -257,7 +258,7 @@ template <class T>
 int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
   const int N = g->dim;
   cg::Dims D = g->dims();
-  int rc = cg::mapped_prepare<T>(g->mtab, g->terms, g->t, D, g->scheme, st);
+  int rc = cg::mapped_prepare<T>(g->mtab, g->terms, g->t, D, g->scheme, st, g->adtl);
   if (rc == 1) return fail(CG_ERR_ARG, "mapping has too many terms (max %d)", cg::M_MAXT - 1);
   if (rc == 2) return fail(CG_ERR_ARG, "mapping has too many term pairs (max %d)", cg::M_MAXP);
   if (rc) return fail(CG_ERR_CUDA, "mapped_prepare: %s", cudaGetErrorString(cudaGetLastError()));
@@ -291,6 +292,11 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
     cg::k_mapped_metrics3d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
                                                                       g->scheme, what);
   g_launches++;
+  if (g->adtl && (what & CG_WHAT_FACE) && N == 3 && g->profile == CG_PROFILE_FULL) {
+    cg::k_mapped_adtl_faces<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, ftab, (const T*)g->mtab.fhalf,
+                                                                       g->mtab.L + 1, O);
+    g_launches++;
+  }
   CG_CUDA(cudaGetLastError());
   CG_CUDA(cudaEventRecord(g->ev1, st));
   g->timed = true;
@@ -396,7 +402,7 @@ int cg_grid_create(int device, int dim, int dtype, const int64_t* ncell, int nha
   if (dim < 1 || dim > 3) return fail(CG_ERR_ARG, "Unsupported metric dimension N=%d", dim);
   if (dtype != CG_F64 && dtype != CG_F32) return fail(CG_ERR_ARG, "unsupported dtype %d", dtype);
   if (nhalo < 0) return fail(CG_ERR_ARG, "nhalo must be >= 0");
-  if (scheme < 0 || scheme > 2) return fail(CG_ERR_ARG, "unknown conserved_metric_scheme %d", scheme);
+  if (scheme < 0 || scheme > 3) return fail(CG_ERR_ARG, "unknown conserved_metric_scheme %d", scheme);
   if (profile != CG_PROFILE_FULL && profile != CG_PROFILE_COMPACT) return fail(CG_ERR_ARG, "unknown profile %d", profile);
   if (!ncell) return fail(CG_ERR_ARG, "ncell is NULL");
   int ndev = 0;
@@ -407,7 +413,9 @@ int cg_grid_create(int device, int dim, int dtype, const int64_t* ncell, int nha
   g->dim = dim;
   g->dtype = dtype;
   g->nhalo = nhalo;
-  g->scheme = scheme;
+  // ADThomasLombardMetric: 3-D only; in 1-D / 2-D it simplifies to the direct CurvatureCorrected form (metrics.jl:1669-1673)
+  g->adtl = scheme == CG_AD_THOMAS_LOMBARD && dim == 3;
+  g->scheme = scheme == CG_AD_THOMAS_LOMBARD ? CG_CURVATURE_CORRECTED : scheme;
   g->profile = profile;
   for (int d = 0; d < dim; ++d) {
     if (ncell[d] < 1) {
@@ -491,6 +499,7 @@ int cg_grid_set_nodes(cg_grid* g, const void* x, const void* y, const void* z, i
   const void* in[3] = {x, y, z};
   for (int q = 0; q < g->dim; ++q)
     if (!in[q]) return fail(CG_ERR_ARG, "coordinate array %d is NULL", q);
+  if (g->adtl) return fail(CG_ERR_ARG, "ADThomasLombardMetric is available for MappedGrid only (the reference runs it on analytic mappings, CPU-only)");
   CG_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = (cudaStream_t)stream;
   int64_t origin[3] = {0, 0, 0}, count[3] = {1, 1, 1};

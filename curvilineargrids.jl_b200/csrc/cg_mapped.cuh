@@ -146,7 +146,7 @@ __global__ void k_mapped_tables(Dims D, MTerms TM, MPairs PR, double lam1, doubl
 // factor derivative tables for the analytic Jacobian: ftab[((m*3 + d)*L1 + I)*4 + order], I in [0, nw_d]
 // (the four derivative orders of one position are contiguous: two 16-byte loads)
 template <class T>
-__global__ void k_mapped_factors(Dims D, MTerms TM, T* ftab, int64_t L1) {
+__global__ void k_mapped_factors(Dims D, MTerms TM, T* ftab, int64_t L1, double shift = 0.0) {
   const int64_t ntot = (int64_t)TM.n * 3 * L1;
   for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
        lin += (int64_t)gridDim.x * blockDim.x) {
@@ -160,7 +160,7 @@ __global__ void k_mapped_factors(Dims D, MTerms TM, T* ftab, int64_t L1) {
     }
     if (I > D.nw[d]) continue;
     const MTerm& t = TM.t[m];
-    const double s = cell_centre(D, d, I);
+    const double s = cell_centre(D, d, I) + shift;  // shift = 1/2: the high-side face of the cell (ADThomasLombardMetric)
     for (int o = 0; o < 4; ++o) base[o] = T(fac_der(t.kind[d], t.a[d], t.b[d], s, o));
   }
 }
@@ -653,6 +653,69 @@ inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, cons
       D, TM, coord_terms(TM), PR, tab, ftab, L, O, scheme, kchunk);
 }
 
+
+// ---------------------------------------------------------------------------
+// ADThomasLombardMetric (metrics.jl:607-668, fill :3082-3188) on top of the CurvatureCorrected evaluation: the face
+// forward metric is the mapping's Jacobian AT THE FACE CENTRE, inverse = inv(F), J = det(F) (:3162-3168), and the
+// conserved matrix keeps only its active row (:3174-3182; the active row equals the CurvatureCorrected one, asserted
+// by the reference at 1e-12, test_3d_continuous.jl:296-297).  fhalf = the factor tables at centre + 1/2.
+// ---------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(128) k_mapped_adtl_faces(Dims D, MTerms TM, const T* __restrict__ ftab,
+                                                           const T* __restrict__ fhalf, int64_t L1, MetricOut<T> O) {
+  const int64_t nc = D.nw[0] * D.nw[1] * D.nw[2];
+  for (int64_t cl = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; cl < nc; cl += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ix[3] = {cl % D.nw[0], (cl / D.nw[0]) % D.nw[1], cl / (D.nw[0] * D.nw[1])};
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      T F[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, G[3][3];
+      for (int m = 0; m < TM.n; ++m) {
+        const int q = TM.t[m].coord;
+        T a[3][2];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const T* tb = (d == f ? fhalf : ftab) + ((int64_t)(m * 3 + d) * L1 + ix[d]) * 4;
+          a[d][0] = tb[0];
+          a[d][1] = tb[1];
+        }
+        const T c = T(TM.t[m].coef);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const T v = c * a[d][1] * a[(d + 1) % 3][0] * a[(d + 2) % 3][0];
+#pragma unroll
+          for (int qq = 0; qq < 3; ++qq)
+            if (qq == q) F[qq][d] += v;
+        }
+      }
+      const T J = inv3(F, G);
+      if (O.face_fwd[f]) {
+        T* o = O.face_fwd[f] + 10 * cl;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) o[r + 3 * c] = F[r][c];
+        o[9] = J;
+      }
+      if (O.face_inv[f]) {
+        T* o = O.face_inv[f] + 10 * cl;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int r = 0; r < 3; ++r) o[r + 3 * c] = G[r][c];
+        o[9] = J;
+      }
+      if (O.face_cons[f]) {
+        T* o = O.face_cons[f] + 9 * cl;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            if (r != f) o[r + 3 * c] = T(0);
+      }
+    }
+  }
+}
+
 // =============================== 2-D ========================================
 // Ghat = J inv(F) = [[y_eta, -x_eta], [-y_xi, x_xi]] reconstructed entry-wise (metrics.jl:276-282,
 // 577-582); pairs are (term, unit term), so V1/E1 hold the differentiated factor.
@@ -805,22 +868,24 @@ struct MappedTables {
   int launches = 0;
   void* tab = nullptr;
   void* ftab = nullptr;
-  size_t tab_bytes = 0, ftab_bytes = 0;
+  void* fhalf = nullptr;  // factor tables at centre + 1/2 (ADThomasLombardMetric only)
+  size_t tab_bytes = 0, ftab_bytes = 0, fhalf_bytes = 0;
   int64_t L = 0;
   MTerms terms;
   MPairs pairs;
   void free_all() {
     if (tab) cudaFree(tab);
     if (ftab) cudaFree(ftab);
-    tab = ftab = nullptr;
-    tab_bytes = ftab_bytes = 0;
+    if (fhalf) cudaFree(fhalf);
+    tab = ftab = fhalf = nullptr;
+    tab_bytes = ftab_bytes = fhalf_bytes = 0;
   }
 };
 
 // returns 0 ok, 1 too many terms, 2 too many pairs, 3 cuda error
 template <class T>
 inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, double t, const Dims& D, int scheme,
-                          cudaStream_t st) {
+                          cudaStream_t st, bool want_half = false) {
   if (!M.dirty && M.tab) return 0;
   const int nt = (int)(table.size() / 15);
   if (nt + 1 > M_MAXT) return 1;
@@ -890,6 +955,15 @@ inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, dou
     const int64_t n = (int64_t)nt * 3 * (L + 1);
     k_mapped_factors<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(D, TMd, (T*)M.ftab, L + 1);
     M.launches++;
+    if (want_half) {
+      if (fb > M.fhalf_bytes) {
+        if (M.fhalf) cudaFree(M.fhalf);
+        if (cudaMalloc(&M.fhalf, fb) != cudaSuccess) return 3;
+        M.fhalf_bytes = fb;
+      }
+      k_mapped_factors<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(D, TMd, (T*)M.fhalf, L + 1, 0.5);
+      M.launches++;
+    }
   }
   if (cudaGetLastError() != cudaSuccess) return 3;
   M.dirty = false;

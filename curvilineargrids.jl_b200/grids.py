@@ -29,7 +29,10 @@ from . import _lib as L
 EndpointAverageReconstruction = "endpoint"
 GradientCorrectedReconstruction = "gradient"
 CurvatureCorrectedReconstruction = "curvature"
-_SCHEMES = {"endpoint": 0, "gradient": 1, "curvature": 2}
+# ADThomasLombardMetric (metrics.jl:135): 3-D MappedGrid; face forward metric = Jacobian at the face centre, conserved =
+# active row only (equal to the CurvatureCorrected row); in 1-D / 2-D it simplifies to CurvatureCorrected (:1669-1673)
+ADThomasLombardMetric = "adtl"
+_SCHEMES = {"endpoint": 0, "gradient": 1, "curvature": 2, "adtl": 3}
 
 CellMetrics = namedtuple("CellMetrics", "forward inverse")
 FaceMetrics = namedtuple("FaceMetrics", "forward inverse conserved")
@@ -359,6 +362,9 @@ class MappedGrid(_UnifiedGrid):
                 raise ValueError(f"global_cell_indices must describe the local non-halo cell domain with size "
                                  f"{tuple(celldims)}; got {sizes}")
             goff = tuple(lo for lo, _ in global_cell_indices)
+        if conserved_metric_scheme == ADThomasLombardMetric and dim < 3:
+            import warnings
+            warnings.warn("ADThomasLombardMetric simplifies to the direct metric form in 1-D/2-D.")  # metrics.jl:1670
         super().__init__(dim, celldims, nhalo, device=device, T=T, scheme=conserved_metric_scheme, profile=profile,
                          cache_mode=cache_mode, compute_metrics=compute_metrics,
                          coordinate_system=coordinate_system, basis=basis, window=None, global_offset=goff)

@@ -43,7 +43,15 @@ enum cg_status {
 };
 
 /* conserved_metric_scheme (metrics.jl:111-126) */
-enum cg_scheme { CG_ENDPOINT_AVERAGE = 0, CG_GRADIENT_CORRECTED = 1, CG_CURVATURE_CORRECTED = 2 };
+enum cg_scheme {
+  CG_ENDPOINT_AVERAGE = 0,
+  CG_GRADIENT_CORRECTED = 1,
+  CG_CURVATURE_CORRECTED = 2,
+  /* ADThomasLombardMetric (metrics.jl:135, 607-668, 3082-3188): 3-D MappedGrid, FULL profile: face forward metric =
+   * Jacobian at the face centre, inverse = inv, J = det; conserved = active row only (= the CurvatureCorrected row).
+   * In 1-D / 2-D it is the CurvatureCorrected scheme (metrics.jl:1669-1673).  Not available for DiscreteGrid. */
+  CG_AD_THOMAS_LOMBARD = 3
+};
 enum cg_dtype { CG_F64 = 0, CG_F32 = 1 };
 /* FULL: the reference's 107 doubles/cell (3-D).  COMPACT: J of the cell + the active conserved
  * row per axis = what face_flux_geometry/cellvolume read (face_geometry.jl:393-416). */

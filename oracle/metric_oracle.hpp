@@ -405,6 +405,32 @@ inline void face_metric(const M& m, double t, int axis, const Pt<double>& p, dou
   inv[N * N] = J;
 }
 
+// ADThomasLombardMetric, 3-D (metrics.jl:607-668 closures, fill :3082-3188).  Face forward metric = the mapping's
+// Jacobian AT THE FACE CENTRE (edge.jacobian(t, xi_f, eta_f, zeta_f), :3162-3168), inverse = inv(F), J = det(F);
+// the conserved matrix carries only the active row (:3174-3182).  The active row is restated through the
+// equivalence the reference's own test asserts against CurvatureCorrectedReconstruction
+// (test_3d_continuous.jl:296-297, |difference| < 1e-12), not through the pair-table assembly (:2336-3080).
+template <class M>
+inline void face_metric_adtl3(const M& m, double t, int axis, const Pt<double>& p, double* fwd, double* inv, double* cons) {
+  double G[9], Ghat[9];
+  Cache3<M, 2> c{m, t};
+  c.face(axis, p, G, Ghat);
+  Pt<double> pf = p;
+  pf[axis] += 0.5;  // _face_center_3d (:3271-3283): the cell centre moved half a cell along the face axis
+  const Vals<double, 9> F = ad_jacobian<3>(m, t, pf);
+  double Fm[9], Gm[9];
+  for (int k = 0; k < 9; ++k) Fm[k] = F.e[k];
+  invN<3>(Fm, Gm);
+  const double J = detN<3>(Fm);
+  for (int k = 0; k < 9; ++k) {
+    fwd[k] = Fm[k];
+    inv[k] = Gm[k];
+    cons[k] = (k % 3 == axis) ? Ghat[k] : 0.0;  // column-major: row index = k % 3
+  }
+  fwd[9] = J;
+  inv[9] = J;
+}
+
 // ---------------------------------------------------------------------------
 // DiscreteGrid mapping: discrete_grid.jl:63-71 + Interpolations.jl semantics
 // (SURVEY.md Appendix A.1).  `a[c]` is the INTERIOR node array of coordinate c,

@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-SCHEMES = {"endpoint": 0, "gradient": 1, "curvature": 2}
+SCHEMES = {"endpoint": 0, "gradient": 1, "curvature": 2, "adtl": 3}
 
 
 def build():

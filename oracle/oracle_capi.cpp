@@ -44,9 +44,19 @@ void eval_cells(const M& m, double t, const int64_t* nfull, int nhalo, const int
     for (int d = 0; d < N; ++d) p[d] = double(idx[d] + 1 + goff[d] - nhalo) + 0.5;
     if (what & 1) cell_metric<N>(m, t, p, cell_fwd + s * KM, cell_inv + s * KM);
     if (what & 2) {
-      for (int ax = 0; ax < N; ++ax)
-        face_metric<N, SCH>(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
-                            face_cons + (ax * nout + s) * KC);
+      for (int ax = 0; ax < N; ++ax) {
+        if constexpr (SCH == 3) {  // ADThomasLombardMetric (3-D only; 1-D / 2-D fall back to Curvature, metrics.jl:1669-1673)
+          if constexpr (N == 3)
+            face_metric_adtl3(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
+                              face_cons + (ax * nout + s) * KC);
+          else
+            face_metric<N, 2>(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
+                              face_cons + (ax * nout + s) * KC);
+        } else {
+          face_metric<N, SCH>(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
+                              face_cons + (ax * nout + s) * KC);
+        }
+      }
     }
   }
 }
@@ -60,6 +70,7 @@ int dispatch(const M& m, int dim, int scheme, double t, const int64_t* nfull, in
   CGO_CASE(1, 0) CGO_CASE(1, 1) CGO_CASE(1, 2)
   CGO_CASE(2, 0) CGO_CASE(2, 1) CGO_CASE(2, 2)
   CGO_CASE(3, 0) CGO_CASE(3, 1) CGO_CASE(3, 2)
+  CGO_CASE(1, 3) CGO_CASE(2, 3) CGO_CASE(3, 3)
 #undef CGO_CASE
   return 1;
 }

@@ -109,3 +109,36 @@ def test_mapped_fp32_and_compact(cg, oracle):
         got = cg.face_metrics(comp)[a].reshape(-1, 3).cpu().numpy()
         want = np.stack([ref["face_cons"][a][:, a + 3 * c] for c in range(3)], axis=1)
         assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name", ["wavy3d", "sphere3d", "rtp3d"])
+def test_mapped_ad_thomas_lombard(cg, oracle, name):
+    """ADThomasLombardMetric (metrics.jl:607-668, 3082-3188; test_3d_continuous.jl:167-300): GCL < 1e-12, active rows
+    equal to the CurvatureCorrected rows, inactive rows zero, face forward metric = Jacobian at the face centre."""
+    terms, celldims, h = _cases(cg.workloads)[name]
+    t = 0.37
+    ref = oracle.mapped_eval(terms, t, celldims, h, "adtl")
+    g = cg.MappedGrid(terms, {}, celldims, h, conserved_metric_scheme=cg.ADThomasLombardMetric, t=t)
+    got = grid_outputs(cg, g)
+    assert_metrics_close(got, ref, rtol=RTOL_F64, label=f"{name} adtl")
+    assert max(cg.gcl(g)) < 1e-12                                  # test_3d_continuous.jl:296
+    cur = grid_outputs(cg, cg.MappedGrid(terms, {}, celldims, h, conserved_metric_scheme="curvature", t=t))
+    for ax in range(3):
+        a = got["face_cons"][ax].reshape(-1, 3, 3, order="F") if False else got["face_cons"][ax]
+        c = cur["face_cons"][ax]
+        rows = np.arange(9) % 3                                    # column-major: row index of entry k
+        assert np.array_equal(a[..., rows == ax], c[..., rows == ax])   # :297 (< 1e-12 there; identical here)
+        assert not a[..., rows != ax].any()
+    # the face forward metric differs from the reconstructed one of the Curvature scheme on a curved mesh
+    assert np.abs(got["face_fwd"] - cur["face_fwd"]).max() > 0
+
+
+def test_ad_thomas_lombard_dimension_and_grid_kind(cg, oracle):
+    wl = cg.workloads
+    terms, celldims, h = _cases(wl)["wavy2d"]
+    with pytest.warns(UserWarning):                                # metrics.jl:1669-1673
+        g = cg.MappedGrid(terms, {}, celldims, h, conserved_metric_scheme="adtl", t=0.1)
+    ref = oracle.mapped_eval(terms, 0.1, celldims, h, "curvature")
+    assert_metrics_close(grid_outputs(cg, g), ref, rtol=RTOL_F64, label="adtl 2d = curvature")
+    with pytest.raises(cg.CurvigridArgumentError):
+        cg.DiscreteGrid(*wl.wavy_nodes_3d(9, 9, 9), 2, conserved_metric_scheme="adtl")
