@@ -3,7 +3,7 @@
 The directory is named after the reference (`curvilineargrids.jl_b200`); import it
 as `curvigrid_b200` (repo-root shim) because of the dot in the name.
 """
-from . import _lib, legacy, slabs, workloads  # noqa: F401
+from . import _lib, legacy, multiblock, slabs, workloads  # noqa: F401
 from ._lib import CurvigridArgumentError, CurvigridError  # noqa: F401
 from .grids import (  # noqa: F401
     ADThomasLombardMetric, CurvatureCorrectedReconstruction, DiscreteGrid, EndpointAverageReconstruction, GradientCorrectedReconstruction,

@@ -797,6 +797,37 @@ int cg_grid_cell_volumes(cg_grid* g, int coordsys, void* volume, void* stream) {
                             : cell_volumes_t<float>(g, coordsys, volume, (cudaStream_t)stream);
 }
 
+extern "C++" {
+namespace {
+// dst[dst_idx[p]] = src[src_idx[p]] for p < n: the scalar ghost-cell fill of a multiblock interface
+// (exchange_interface!, src/multiblock/transfer.jl:25-117, with the pairs of interface_index_plan :157-195)
+template <class E>
+__global__ void __launch_bounds__(256) k_copy_index_pairs(E* __restrict__ dst, const E* __restrict__ src,
+                                                          const int64_t* __restrict__ dst_idx,
+                                                          const int64_t* __restrict__ src_idx, int64_t n) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+    dst[dst_idx[p]] = src[src_idx[p]];
+}
+}  // namespace
+}  // extern "C++"
+
+int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const void* src_idx, int64_t n, int elem_bytes,
+                        void* stream) {
+  if (n < 0 || (n > 0 && (!dst || !src || !dst_idx || !src_idx))) return fail(CG_ERR_ARG, "bad argument");
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(CG_ERR_ARG, "element size must be 4 or 8 bytes");
+  if (n == 0) return CG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elem_bytes == 8)
+    k_copy_index_pairs<double><<<launch_blocks(n, 256), 256, 0, st>>>((double*)dst, (const double*)src,
+                                                                      (const int64_t*)dst_idx, (const int64_t*)src_idx, n);
+  else
+    k_copy_index_pairs<float><<<launch_blocks(n, 256), 256, 0, st>>>((float*)dst, (const float*)src,
+                                                                     (const int64_t*)dst_idx, (const int64_t*)src_idx, n);
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
 int cg_grid_gcl_max(cg_grid* g, double* out, void* stream) {
   if (!g || !out) return fail(CG_ERR_ARG, "bad argument");
   if (!g->valid_face) return fail(CG_ERR_STATE, "face metrics are not valid; call cg_grid_eval first");

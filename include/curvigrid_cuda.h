@@ -206,6 +206,15 @@ int cg_grid_face_flux_geometry(cg_grid* g, int axis, int coordsys, void* metric_
                                void* stream);
 int cg_grid_cell_volumes(cg_grid* g, int coordsys, void* volume, void* stream);
 
+/*
+ * Scalar ghost-cell fill of a multiblock interface on the device (exchange_interface!, src/multiblock/transfer.jl:25-117):
+ * dst[dst_idx[p]] = src[src_idx[p]], p < n, with the ordered pairs of interface_index_plan (transfer.jl:157-236) as
+ * 0-based linear indices (int64, device memory).  elem_bytes = 4 or 8.  With dst_idx / src_idx = 0..n-1 the same call
+ * packs / unpacks the values of a cross-rank exchange (ncclSend / ncclRecv of the packed buffer in between).
+ */
+int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const void* src_idx, int64_t n, int elem_bytes,
+                        void* stream);
+
 int cg_grid_sync(cg_grid* g, void* stream);
 /* device time of the last cg_grid_eval on this handle in ms (CUDA events; synchronises) */
 int cg_grid_last_eval_ms(cg_grid* g, float* ms);
