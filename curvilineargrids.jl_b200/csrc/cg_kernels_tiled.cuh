@@ -42,6 +42,9 @@ constexpr int NT = 32 * WY;     // threads per block
 // The eta / zeta kernels run ONE warp per block: row index, chunk and every staging / TMA address are then functions
 // of blockIdx alone, i.e. they live in uniform registers (UBLKCP straight from UR operands, no R2UR loops).
 constexpr int ZWY = CG_ZWY;
+#ifndef CG_PICK_CHUNK
+#define CG_PICK_CHUNK 0  // 1 = wave-aware chunk lengths (pick_chunk; mixed results: 384^3 +2 %, 512^3 and 300^3 -1..2 %); 0 = the ~30-waves policy
+#endif
 #ifndef CG_XWY
 #define CG_XWY 4
 #endif
@@ -1015,6 +1018,28 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
 }
 
+// Chunk length along the marching axis for `tiles` warp tiles of `per_block` warps each, `slots` resident blocks on the
+// GPU: among 1 .. extent / min_chunk chunks per tile, the count with the best (wave quantisation) x (prologue
+// amortisation) efficiency; `prologue` = cost of a chunk's set-up in steps.
+inline int pick_chunk(int64_t tiles, int64_t extent, int64_t slots, int min_chunk, double prologue) {
+  int best_n = 1;
+  double best = -1.0;
+  const int64_t max_n = extent / min_chunk > 0 ? extent / min_chunk : 1;
+  for (int64_t n = 1; n <= max_n && n <= 64; ++n) {
+    const double waves = (double)(tiles * n) / (double)slots;
+    const double full = (double)(int64_t)waves + ((double)(int64_t)waves < waves ? 1.0 : 0.0);
+    const double len = (double)((extent + n - 1) / n);
+    // quantisation of the last wave x amortisation of the chunk prologue x half a wave of ragged tail
+    const double eff = waves / full * len / (len + prologue) * waves / (waves + 0.5);
+    if (eff > best + 1e-9) {
+      best = eff;
+      best_n = (int)n;
+    }
+  }
+  int c = (int)((extent + best_n - 1) / best_n);
+  return c < 1 ? 1 : c;
+}
+
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
@@ -1393,7 +1418,8 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   }
   if ((mask & 1) && ((what & 1) || face)) {
     const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + XWY - 1) / XWY);
-    const int kchunk = chunk_of((int64_t)gx * gy, nplanes);
+    const int64_t xslots = 148LL * (mode == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) * 4 / XWY;
+    const int kchunk = CG_PICK_CHUNK ? pick_chunk((int64_t)gx * gy, nplanes, xslots, 64, 1.5) : chunk_of((int64_t)gx * gy, nplanes);
     const dim3 grid(gx, gy, (unsigned)((nplanes + kchunk - 1) / kchunk));
     if (mode == MODE_FULL) launch_xi(k_face_xi<T, SCH, MODE_FULL>, xi_warp_vals<T, MODE_FULL>, grid, kchunk);
     else if (mode == MODE_COMPACT) launch_xi(k_face_xi<T, SCH, MODE_COMPACT>, xi_warp_vals<T, MODE_COMPACT>, grid, kchunk);
@@ -1403,11 +1429,12 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     ++n;
   }
   const unsigned gxz = (unsigned)((D.nw[0] + ZETA_OUT - 1) / ZETA_OUT);
+  const int64_t zslots = 148LL * (zmode == MODE_COMPACT ? CG_COMPACT_MINB : CG_ZETA_MINB) * 4 / ZWY;
   if ((mask & 2) && face) {
     if (fk) zst = fk->s[0];
     // eta faces with the zeta kernel's code, marching along j: rows = k planes
     const unsigned gy = (unsigned)((nplanes + ZWY - 1) / ZWY);
-    const int jchunk = chunk_of((int64_t)gxz * gy, D.nw[1]);
+    const int jchunk = CG_PICK_CHUNK ? pick_chunk((int64_t)gxz * gy, D.nw[1], zslots, 64, 3.0) : chunk_of((int64_t)gxz * gy, D.nw[1]);
     const dim3 grid(gxz, gy, (unsigned)((D.nw[1] + jchunk - 1) / jchunk));
     if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, true, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, jchunk);
     else if (zmode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, true, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, jchunk);
@@ -1417,7 +1444,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   if ((mask & 4) && face) {
     if (fk) zst = fk->s[1];
     const unsigned gy = (unsigned)((D.nw[1] + ZWY - 1) / ZWY);
-    const int kchunk = chunk_of((int64_t)gxz * gy, nplanes);
+    const int kchunk = CG_PICK_CHUNK ? pick_chunk((int64_t)gxz * gy, nplanes, zslots, 64, 3.0) : chunk_of((int64_t)gxz * gy, nplanes);
     const dim3 grid(gxz, gy, (unsigned)((nplanes + kchunk - 1) / kchunk));
     if (zmode == MODE_FULL) launch_zeta(k_face_zeta<T, SCH, false, MODE_FULL>, zeta_warp_vals<T, MODE_FULL>, grid, kchunk);
     else if (zmode == MODE_COMPACT) launch_zeta(k_face_zeta<T, SCH, false, MODE_COMPACT>, zeta_warp_vals<T, MODE_COMPACT>, grid, kchunk);

@@ -639,14 +639,8 @@ template <class T>
 inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
                                            int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
   const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + MWY - 1) / MWY);
-  const int64_t tiles = (int64_t)gx * gy, want = 148LL * 16;
-  int kchunk = (int)D.nw[2];
-  if (tiles < want) {
-    const int64_t nch = (want + tiles - 1) / tiles;
-    kchunk = (int)((D.nw[2] + nch - 1) / nch);
-    if (kchunk < 8) kchunk = 8;
-    if (kchunk > D.nw[2]) kchunk = (int)D.nw[2];
-  }
+  // 8 warps per SM: chunks along k so that the last wave is (nearly) full (7.5 waves -> 15 at 512^3)
+  const int kchunk = pick_chunk((int64_t)gx * gy, D.nw[2], 148LL * 8 / MWY, 32, 0.4);
   const int smem = MWY * mapped_stage_vals<T> * (int)sizeof(T);
   cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, MWY), smem, st>>>(
