@@ -484,9 +484,16 @@ constexpr int MAPPED_OUT = 31;
 #endif
 // one warp per block: row, plane and every staging / TMA address are uniform (see ZWY in cg_kernels_tiled.cuh)
 constexpr int MWY = CG_MWY;
-template <class T> constexpr int mapped_stage_vals = 8 * stage_len<T, 10> + 3 * stage_len<T, 9>;
+// Staging in four phases per step (cell arrays, then one face axis at a time, all in the same three buffers): 7.5 KB
+// per warp instead of 27.5 KB, which leaves ~190 KB of L1 for the operator-table rows (they missed L1 on every step
+// with 220 KB of shared memory per SM: 44.6 -> 41.2 ms with two phases).  The wait before a phase's first
+// staging store follows the arithmetic of that phase, so the TMA unit has had time to read the previous one.
+template <class T> constexpr int mapped_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9>;
+#ifndef CG_MAPPED_MINB
+#define CG_MAPPED_MINB 8
+#endif
 template <class T>
-__global__ void __launch_bounds__(32 * MWY, 8 / MWY) k_mapped_metrics3d_staged(Dims D, MTerms TM, MCoordTerms CT, MPairs PR,
+__global__ void __launch_bounds__(32 * MWY, CG_MAPPED_MINB / MWY) k_mapped_metrics3d_staged(Dims D, MTerms TM, MCoordTerms CT, MPairs PR,
                                                                   const T* __restrict__ tab, const T* __restrict__ ftab,
                                                                   int64_t L, MetricOut<T> O, int scheme, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
@@ -532,9 +539,18 @@ __global__ void __launch_bounds__(32 * MWY, 8 / MWY) k_mapped_metrics3d_staged(D
     const int64_t cl0 = i0 + nw0 * (j + nw1 * m);
     bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers (lanes > 0 own no groups)
     __syncwarp();
-    Stage<T, 10> Scf(O.cell_fwd, cl0, sg), Sci(O.cell_inv, cl0, sg + stage_len<T, 10>);
-    put10(Scf.slot(lane), Fc, Jc);  // every lane stages (no branch); slots >= nvalid are never sent
-    put10(Sci.slot(lane), Gc, Jc);
+    T* const b10 = sg;                          // two Metric buffers and one ConservedMetric buffer, four phases
+    T* const b9 = sg + 2 * stage_len<T, 10>;
+    {
+      Stage<T, 10> Scf(O.cell_fwd, cl0, b10), Sci(O.cell_inv, cl0, b10 + stage_len<T, 10>);
+      put10(Scf.slot(lane), Fc, Jc);  // every lane stages (no branch); slots >= nvalid are never sent
+      put10(Sci.slot(lane), Gc, Jc);
+      fence_async_smem();
+      __syncwarp();
+      Scf.issue(nvalid, lane);
+      Sci.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    }
     // ---- conserved metrics: sums over term pairs of triple products of 1-D table values ----
     T Gh[3][3][3];  // [face][row][col]
 #pragma unroll
@@ -580,10 +596,6 @@ __global__ void __launch_bounds__(32 * MWY, 8 / MWY) k_mapped_metrics3d_staged(D
     // ---- reconstructed inverse Jacobian on the three faces ----
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-      T* const sf = sg + (2 + 2 * f) * stage_len<T, 10>;
-      Stage<T, 10> Sff(O.face_fwd[f], cl0, sf), Sfi(O.face_inv[f], cl0, sf + stage_len<T, 10>);
-      Stage<T, 9> Sfc(O.face_cons[f], cl0, sg + 8 * stage_len<T, 10> + f * stage_len<T, 9>);
-      put9(Sfc.slot(lane), Gh[f]);
       T Gf[3][3], Ff[3][3];
       if (f == 0) {  // +xi neighbour: its R state by shuffle
         T L0[3][3], R0[3][3];
@@ -615,22 +627,21 @@ __global__ void __launch_bounds__(32 * MWY, 8 / MWY) k_mapped_metrics3d_staged(D
           }
       }
       T J = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
+      // one phase per face axis: wait until the TMA unit has read the previous phase, stage, hand over
+      bulk_wait_read();
+      __syncwarp();
+      Stage<T, 10> Sff(O.face_fwd[f], cl0, b10), Sfi(O.face_inv[f], cl0, b10 + stage_len<T, 10>);
+      Stage<T, 9> Sfc(O.face_cons[f], cl0, b9);
+      put9(Sfc.slot(lane), Gh[f]);
       put10(Sff.slot(lane), Ff, J);
       put10(Sfi.slot(lane), Gf, J);
+      fence_async_smem();
+      __syncwarp();
+      Sff.issue(nvalid, lane);
+      Sfi.issue(nvalid, lane);
+      Sfc.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
     }
-    // ---- one flush point: staged arrays -> TMA ----
-    fence_async_smem();
-    __syncwarp();
-    Scf.issue(nvalid, lane);
-    Sci.issue(nvalid, lane);
-#pragma unroll
-    for (int f = 0; f < 3; ++f) {
-      T* const sf = sg + (2 + 2 * f) * stage_len<T, 10>;
-      Stage<T, 10>(O.face_fwd[f], cl0, sf).issue(nvalid, lane);
-      Stage<T, 10>(O.face_inv[f], cl0, sf + stage_len<T, 10>).issue(nvalid, lane);
-      Stage<T, 9>(O.face_cons[f], cl0, sg + 8 * stage_len<T, 10> + f * stage_len<T, 9>).issue(nvalid, lane);
-    }
-    if (lane == 0) bulk_commit();
   }
   if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
 }
@@ -640,7 +651,7 @@ inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, cons
                                            int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
   const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + MWY - 1) / MWY);
   // 8 warps per SM: chunks along k so that the last wave is (nearly) full (7.5 waves -> 15 at 512^3)
-  const int kchunk = pick_chunk((int64_t)gx * gy, D.nw[2], 148LL * 8 / MWY, 32, 0.4);
+  const int kchunk = pick_chunk((int64_t)gx * gy, D.nw[2], 148LL * CG_MAPPED_MINB / MWY, 32, 0.4);
   const int smem = MWY * mapped_stage_vals<T> * (int)sizeof(T);
   cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, MWY), smem, st>>>(
