@@ -419,7 +419,17 @@ def run_ours(args, spec):
                 "kernel": ("k_face_xi + k_face_zeta<SWAP> (eta) + k_face_zeta (one cell+face evaluation = 3 launches)"
                            if dim == 3 and args.kernel == 1 else ("metrics3d" if dim == 3 else "metrics2d")),
                 "kernel_ms": k_ms,
-                "algorithmic_bytes_per_cell": bpc, "peak_source": f"MEASURED_PEAKS.json ({peak_src}, copy burst)"}
+                "algorithmic_bytes_per_cell": bpc, "peak_source": f"MEASURED_PEAKS.json ({peak_src}, copy burst)",
+                # also against the nominal ~8 TB/s of the north star
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+    if dim == 3 and args.kernel == 1 and args.profile == "full" and args.dtype == "f64" and spec["scheme"] == "curvature":
+        # second ceiling: FP64 instructions of the three marching kernels per cell (SASS of the loop
+        # bodies: xi 736 per 29 cells, eta / zeta 697 per 31) against the measured FP64 issue rate (59 per clock and SM)
+        ipc = 32.0 * (736.0 / 29.0 + 2.0 * 697.0 / 31.0)  # thread instructions: a warp instruction occupies 32 lanes
+        rate = ipc * cells_local / (k_ms * 1e-3)
+        roofline["fp64"] = {"instr_per_cell": ipc, "achieved_Tinstr_s": rate / 1e12,
+                            "peak_Tinstr_s": 59.0 * 148 * 1.965e9 / 1e12,
+                            "frac": rate / (59.0 * 148 * 1.965e9), "note": "peak at the maximum SM clock"}
 
     e2e = None
     if not args.no_e2e:
