@@ -651,7 +651,11 @@ inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, cons
                                            int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
   const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + MWY - 1) / MWY);
   // 8 warps per SM: chunks along k so that the last wave is (nearly) full (7.5 waves -> 15 at 512^3)
+#ifdef CG_MAPPED_NCHUNK  // experiment: fixed number of chunks along k
+  const int kchunk = (int)((D.nw[2] + CG_MAPPED_NCHUNK - 1) / CG_MAPPED_NCHUNK);
+#else
   const int kchunk = pick_chunk((int64_t)gx * gy, D.nw[2], 148LL * CG_MAPPED_MINB / MWY, 32, 0.4);
+#endif
   const int smem = MWY * mapped_stage_vals<T> * (int)sizeof(T);
   cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, MWY), smem, st>>>(
