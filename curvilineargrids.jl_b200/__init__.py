@@ -9,6 +9,6 @@ from .grids import (  # noqa: F401
     ADThomasLombardMetric, CurvatureCorrectedReconstruction, DiscreteGrid, EndpointAverageReconstruction, GradientCorrectedReconstruction,
     MappedGrid, cell_metrics, cell_metrics_valid, cellvolume, cellvolumes, face_flux_geometry, face_flux_geometry_arrays, face_metrics, face_metrics_valid,
     gcl, invalidate_cell_metrics, invalidate_face_metrics, local_grid, refresh_cell_metrics, refresh_face_metrics,
-    refresh_metrics, update)
+    refresh_metrics, seam_plane, update)
 
 __version__ = "0.1.0"

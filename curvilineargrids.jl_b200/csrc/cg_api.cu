@@ -1,6 +1,8 @@
 // libcurvigrid_cuda.so — C ABI (include/curvigrid_cuda.h) over the CUDA kernels.
 // Host-side handle, device memory, stream ordering, status codes.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the NCCL entry points are resolved at run time (see nccl_api)
 
 #include <atomic>
 #include <cstdarg>
@@ -64,6 +66,10 @@ struct cg_grid {
   bool timed = false;
   cudaStream_t copy_stream = nullptr;  // cg_grid_update_from_host: H2D pieces
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  cg::Fork fork;                       // helper streams of the small-grid face launches (per handle)
+  cudaStream_t comm_stream = nullptr;  // cg_halo_exchange_*: ncclSend / ncclRecv of node planes
+  cudaEvent_t comm_ev[2] = {nullptr, nullptr};
+  Buf seam;                            // cg_grid_gcl_max_dist: the neighbour's last conserved plane
   std::vector<double> terms;
   cg::MappedTables mtab;
   double t = 0.0;
@@ -143,6 +149,15 @@ Buf* select(cg_grid* g, int array, int axis, size_t* bytes) {
     case CG_ARR_COMPACT_ACTIVE: *bytes = nc * N * es; return &g->cactive[axis];
   }
   return nullptr;
+}
+
+void invalidate_for(cg_grid* g, int array) {
+  switch (array) {
+    case CG_ARR_CELL_FORWARD: case CG_ARR_CELL_INVERSE: case CG_ARR_COMPACT_J: g->valid_cell = false; break;
+    case CG_ARR_FACE_FORWARD: case CG_ARR_FACE_INVERSE: case CG_ARR_FACE_CONSERVED: case CG_ARR_COMPACT_ACTIVE:
+      g->valid_face = false; break;
+    default: g->valid_coords = false;
+  }
 }
 
 int launch_blocks(int64_t n, int threads) {
@@ -360,7 +375,7 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st, int64_t k_lo = 0, int64_t k
       nl = 1;
     }
     if (mask) {
-      int n2 = cg::launch_metrics3d_tiled<T>(D, ex, ey, ez, O, g->scheme, what, mask, st);
+      int n2 = cg::launch_metrics3d_tiled<T>(D, ex, ey, ez, O, g->scheme, what, mask, st, &g->fork);
       if (n2 < 0) return fail(CG_ERR_CUDA, "marching kernel launch failed");
       nl += n2;
     }
@@ -375,6 +390,13 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st, int64_t k_lo = 0, int64_t k
     if (what & CG_WHAT_FACE) g->valid_face = true;
   }
   return CG_OK;
+}
+
+// The reference recomputes node / centroid / face coordinates on every update! (discrete_grid.jl:605-647,
+// mapped_grid.jl:551-587).  Coordinate storage is allocated lazily here, so the refresh runs when it exists.
+int refresh_coords_if_stored(cg_grid* g, cudaStream_t st) {
+  if (!g->node[0].p) return CG_OK;
+  return g->dtype == CG_F64 ? eval_impl<double>(g, CG_WHAT_COORDS, st) : eval_impl<float>(g, CG_WHAT_COORDS, st);
 }
 
 bool is_device_ptr(const void* p) {
@@ -465,8 +487,13 @@ int cg_grid_destroy(cg_grid* g) {
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
   if (g->copy_stream) cudaStreamDestroy(g->copy_stream);
-  for (int e = 0; e < 2; ++e)
+  if (g->comm_stream) cudaStreamDestroy(g->comm_stream);
+  for (int e = 0; e < 2; ++e) {
     if (g->copy_ev[e]) cudaEventDestroy(g->copy_ev[e]);
+    if (g->comm_ev[e]) cudaEventDestroy(g->comm_ev[e]);
+  }
+  g->fork.destroy();
+  release(g->seam);
   delete g;
   return CG_OK;
 }
@@ -541,7 +568,9 @@ int cg_grid_set_nodes(cg_grid* g, const void* x, const void* y, const void* z, i
   }
   g->kind = 1;
   g->valid_cell = g->valid_face = g->valid_coords = false;
-  return g->dtype == CG_F64 ? pad_nodes<double>(g, st) : pad_nodes<float>(g, st);
+  int rc = g->dtype == CG_F64 ? pad_nodes<double>(g, st) : pad_nodes<float>(g, st);
+  if (rc) return rc;
+  return refresh_coords_if_stored(g, st);
 }
 
 int cg_grid_node_buffer(cg_grid* g, int coord, void** devptr, int64_t* origin3, int64_t* count3) {
@@ -560,7 +589,9 @@ int cg_grid_nodes_changed(cg_grid* g, void* stream) {
   if (g->kind != 1) return fail(CG_ERR_STATE, "not a DiscreteGrid");
   CG_CUDA(cudaSetDevice(g->device));
   g->valid_cell = g->valid_face = g->valid_coords = false;
-  return g->dtype == CG_F64 ? pad_nodes<double>(g, (cudaStream_t)stream) : pad_nodes<float>(g, (cudaStream_t)stream);
+  int rc = g->dtype == CG_F64 ? pad_nodes<double>(g, (cudaStream_t)stream) : pad_nodes<float>(g, (cudaStream_t)stream);
+  if (rc) return rc;
+  return refresh_coords_if_stored(g, (cudaStream_t)stream);
 }
 
 int cg_grid_set_mapping_terms(cg_grid* g, int nterms, const double* table) {
@@ -584,13 +615,9 @@ int cg_grid_update(cg_grid* g, double t, void* stream) {
   if (g->kind == 0) return fail(CG_ERR_STATE, "cg_grid_update: no nodes or mapping set");
   g->t = t;
   g->mtab.dirty = true;
-  g->valid_cell = g->valid_face = false;
-  if (g->valid_coords || g->node[0].p) {
-    CG_CUDA(cudaSetDevice(g->device));
-    return g->dtype == CG_F64 ? eval_impl<double>(g, CG_WHAT_COORDS, (cudaStream_t)stream)
-                              : eval_impl<float>(g, CG_WHAT_COORDS, (cudaStream_t)stream);
-  }
-  return CG_OK;
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  CG_CUDA(cudaSetDevice(g->device));
+  return refresh_coords_if_stored(g, (cudaStream_t)stream);
 }
 
 int cg_grid_eval(cg_grid* g, int what, void* stream) {
@@ -621,73 +648,16 @@ int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int fi
                             : eval_impl<float>(g, what, (cudaStream_t)stream, k_lo, k_hi, final != 0);
 }
 
-int cg_grid_update_from_host(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
-                             void* stream) {
-  if (!g) return fail(CG_ERR_ARG, "NULL grid");
-  if (g->kind != 1 || g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_update_from_host: 3-D DiscreteGrid only");
-  if (what <= 0 || what > 3) return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE)", what);
-  const void* in[3] = {x, y, z};
-  for (int q = 0; q < 3; ++q) {
-    if (!in[q]) return fail(CG_ERR_ARG, "coordinate array %d is NULL", q);
-    if (!g->src[q].p) return fail(CG_ERR_STATE, "no node buffer: call cg_grid_set_nodes once first");
-  }
-  CG_CUDA(cudaSetDevice(g->device));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (!g->copy_stream) {
-    CG_CUDA(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
-    CG_CUDA(cudaEventCreateWithFlags(&g->copy_ev[0], cudaEventDisableTiming));
-    CG_CUDA(cudaEventCreateWithFlags(&g->copy_ev[1], cudaEventDisableTiming));
-  }
-  const int64_t nk = g->src_count[2], plane = g->src_count[0] * g->src_count[1];
-  const int64_t o = g->src_origin[2], gn = g->ncell[2], h = g->nhalo, nw = g->nw[2], ne = nw + 4;
-  if (nchunks < 1) nchunks = 1;
-  if (nchunks > nk) nchunks = (int)nk;
-  g->valid_cell = g->valid_face = g->valid_coords = false;
-  // the copies overwrite the node buffer the previous evaluation's padding read
-  CG_CUDA(cudaEventRecord(g->copy_ev[0], st));
-  CG_CUDA(cudaStreamWaitEvent(g->copy_stream, g->copy_ev[0], 0));
-  int64_t ext_done = 0, cell_done = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    const int64_t p_lo = nk * c / nchunks, p_hi = nk * (c + 1) / nchunks;
-    for (int q = 0; q < 3; ++q)
-      CG_CUDA(cudaMemcpyAsync((char*)g->src[q].p + (size_t)(p_lo * plane) * g->esize(),
-                              (const char*)in[q] + (size_t)(p_lo * plane) * g->esize(),
-                              (size_t)((p_hi - p_lo) * plane) * g->esize(), cudaMemcpyHostToDevice, g->copy_stream));
-    CG_CUDA(cudaEventRecord(g->copy_ev[1], g->copy_stream));
-    CG_CUDA(cudaStreamWaitEvent(st, g->copy_ev[1], 0));
-    // padded planes whose source planes (clamp(m) and, when extrapolated, its inner neighbour) have all landed
-    auto landed = [&](int64_t m) { return m >= o && m < o + p_hi; };
-    int64_t e_hi = ext_done;
-    for (; e_hi < ne; ++e_hi) {
-      const int64_t m = g->w0[2] + e_hi - 1 - h;
-      const int64_t cc = m < 0 ? 0 : (m > gn ? gn : m);
-      if (!landed(cc)) break;
-      if (m != cc && !landed(m < cc ? cc + 1 : cc - 1)) break;
-    }
-    int rc = CG_OK;
-    if (e_hi > ext_done)
-      rc = g->dtype == CG_F64 ? pad_nodes<double>(g, st, ext_done, e_hi) : pad_nodes<float>(g, st, ext_done, e_hi);
-    if (rc) return rc;
-    ext_done = e_hi;
-    int64_t k_hi = ext_done - 4 < cell_done ? cell_done : (ext_done - 4 > nw ? nw : ext_done - 4);
-    if (c == nchunks - 1) {
-      if (ext_done != ne) return fail(CG_ERR_STATE, "node buffer does not cover the window");
-      k_hi = nw;
-    }
-    const bool last = c == nchunks - 1;
-    if (k_hi > cell_done || last)
-      rc = g->dtype == CG_F64 ? eval_impl<double>(g, what, st, cell_done, k_hi, last)
-                              : eval_impl<float>(g, what, st, cell_done, k_hi, last);
-    if (rc) return rc;
-    cell_done = k_hi;
-  }
-  return CG_OK;
-}
-
 int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid) {
   if (!g) return fail(CG_ERR_ARG, "NULL grid");
   if (cell_valid) *cell_valid = g->valid_cell;
   if (face_valid) *face_valid = g->valid_face;
+  return CG_OK;
+}
+
+int cg_grid_coords_valid(const cg_grid* g, int* coords_valid) {
+  if (!g || !coords_valid) return fail(CG_ERR_ARG, "bad argument");
+  *coords_valid = g->valid_coords;
   return CG_OK;
 }
 
@@ -704,8 +674,10 @@ int cg_grid_get_ptr(cg_grid* g, int array, int axis, void** devptr, size_t* nbyt
   size_t bytes = 0;
   Buf* b = select(g, array, axis, &bytes);
   if (!b) return fail(CG_ERR_ARG, "unknown array %d / axis %d", array, axis);
+  const bool fresh = b->p == nullptr;
   int rc = ensure(g, *b, bytes);
   if (rc) return rc;
+  if (fresh) invalidate_for(g, array);  // a never-computed array: the cache it belongs to is not valid
   *devptr = b->p;
   if (nbytes) *nbytes = bytes;
   return CG_OK;
@@ -719,6 +691,7 @@ int cg_grid_bind_output(cg_grid* g, int array, int axis, void* devptr, size_t nb
   if (nbytes < bytes) return fail(CG_ERR_ARG, "buffer too small: %zu < %zu bytes", nbytes, bytes);
   if (reinterpret_cast<uintptr_t>(devptr) & 15)  // 16-B vector stores and TMA bulk stores
     return fail(CG_ERR_ARG, "bound output buffers must be 16-byte aligned");
+  if (b->p != devptr) invalidate_for(g, array);  // the new buffer holds nothing yet
   release(*b);
   b->p = devptr;
   b->bytes = nbytes;
@@ -828,25 +801,25 @@ int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const v
   return CG_OK;
 }
 
-int cg_grid_gcl_max(cg_grid* g, double* out, void* stream) {
-  if (!g || !out) return fail(CG_ERR_ARG, "bad argument");
-  if (!g->valid_face) return fail(CG_ERR_STATE, "face metrics are not valid; call cg_grid_eval first");
-  CG_CUDA(cudaSetDevice(g->device));
-  cudaStream_t st = (cudaStream_t)stream;
+extern "C++" {
+namespace {
+// launches k_gcl over cell.domain of the global grid intersected with the window and leaves the per-column maxima as
+// bit patterns in g->gcl_bits.  Without `low` the window-local plane 0 of the slab axis is skipped (it needs
+// I - e_axis, which lives on the previous slab); `low` = that slab's last conserved plane of the slab axis.
+int gcl_launch(cg_grid* g, const void* low, cudaStream_t st, bool* empty) {
   const int N = g->dim;
   const bool compact = g->profile == CG_PROFILE_COMPACT;
-  // cell.domain of the global grid intersected with the window (needs I - e_axis inside the window)
   int64_t lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
+  *empty = false;
   for (int d = 0; d < N; ++d) {
     int64_t l = g->nhalo - g->w0[d], h = g->nhalo + g->ncell[d] - g->w0[d];
-    lo[d] = l < 1 ? 1 : l;
+    const int64_t first = (low && d == N - 1) ? 0 : 1;
+    lo[d] = l < first ? first : l;
     hi[d] = h > g->nw[d] ? g->nw[d] : h;
-    if (hi[d] <= lo[d]) {
-      for (int c = 0; c < N; ++c) out[c] = 0.0;
-      return CG_OK;
-    }
+    if (hi[d] <= lo[d]) *empty = true;
   }
   CG_CUDA(cudaMemsetAsync(g->gcl_bits, 0, 3 * sizeof(unsigned long long), st));
+  if (*empty) return CG_OK;
   const void* c[3] = {nullptr, nullptr, nullptr};
   for (int a = 0; a < N; ++a) c[a] = compact ? g->cactive[a].p : g->face_cons[a].p;
   cg::Dims D = g->dims();
@@ -855,17 +828,50 @@ int cg_grid_gcl_max(cg_grid* g, double* out, void* stream) {
   if (g->dtype == CG_F64)
     cg::k_gcl<double><<<launch_blocks(n, 256), 256, 0, st>>>(D, (const double*)c[0], (const double*)c[1],
                                                              (const double*)c[2], compact, lo[0], lo[1], lo[2],
-                                                             hi[0], hi[1], hi[2], g->gcl_bits);
+                                                             hi[0], hi[1], hi[2], (const double*)low, g->gcl_bits);
   else
     cg::k_gcl<float><<<launch_blocks(n, 256), 256, 0, st>>>(D, (const float*)c[0], (const float*)c[1],
                                                             (const float*)c[2], compact, lo[0], lo[1], lo[2], hi[0],
-                                                            hi[1], hi[2], g->gcl_bits);
+                                                            hi[1], hi[2], (const float*)low, g->gcl_bits);
   g_launches++;
   CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+int gcl_read(cg_grid* g, double* out, cudaStream_t st) {
   unsigned long long bits[3];
   CG_CUDA(cudaMemcpyAsync(bits, g->gcl_bits, sizeof bits, cudaMemcpyDeviceToHost, st));
   CG_CUDA(cudaStreamSynchronize(st));
-  for (int cc = 0; cc < N; ++cc) memcpy(&out[cc], &bits[cc], 8);
+  for (int cc = 0; cc < g->dim; ++cc) memcpy(&out[cc], &bits[cc], 8);
+  return CG_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int cg_grid_gcl_max_seam(cg_grid* g, const void* low_plane, double* out, void* stream) {
+  if (!g || !out) return fail(CG_ERR_ARG, "bad argument");
+  if (!g->valid_face) return fail(CG_ERR_STATE, "face metrics are not valid; call cg_grid_eval first");
+  CG_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  bool empty = false;
+  int rc = gcl_launch(g, low_plane, st, &empty);
+  if (rc) return rc;
+  return gcl_read(g, out, st);
+}
+
+int cg_grid_gcl_max(cg_grid* g, double* out, void* stream) { return cg_grid_gcl_max_seam(g, nullptr, out, stream); }
+
+int cg_grid_seam_plane(cg_grid* g, void** devptr, size_t* nbytes) {
+  if (!g || !devptr) return fail(CG_ERR_ARG, "bad argument");
+  const int N = g->dim, ax = N - 1;
+  const bool compact = g->profile == CG_PROFILE_COMPACT;
+  const Buf& b = compact ? g->cactive[ax] : g->face_cons[ax];
+  if (!b.p) return fail(CG_ERR_STATE, "conserved face metrics of the slab axis are not stored");
+  const size_t K = compact ? N : N * N;
+  int64_t plane = 1;
+  for (int d = 0; d < ax; ++d) plane *= g->nw[d];
+  const size_t pb = (size_t)plane * K * g->esize();
+  *devptr = (char*)b.p + pb * (size_t)(g->nw[ax] - 1);
+  if (nbytes) *nbytes = pb;
   return CG_OK;
 }
 
@@ -906,6 +912,473 @@ int cg_discrete_metrics_host(int device, int dim, int dtype, const void* x, cons
   cg_grid_destroy(g);
   g_err = keep;
   return rc;
+}
+
+// =============================================================================================================
+// Multi-GPU: node-plane exchange with NCCL inside the boundary.
+//
+// The reference has no communication layer: local_grid (mapped_grid.jl:344-379) hands out rank-local analytic
+// grids and interface_index_plan (src/multiblock/transfer.jl:157-236) lists index pairs "for a solver or MPI
+// layer".  A sampled DiscreteGrid slab needs REAL neighbour node planes: 1 below and 3 above its cell planes.
+// NCCL is not linked: the process that hosts this library (Julia with NCCL.jl, Python with torch) has normally
+// loaded one already, and two NCCL copies in one process is asking for trouble.  The symbols are taken from the
+// loaded libnccl.so.2 (dlopen RTLD_NOLOAD), else from $CG_NCCL_LIB, else from the system's libnccl.so.2.
+// =============================================================================================================
+extern "C++" {
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+const NcclApi& nccl_api() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) {
+      const char* e = getenv("CG_NCCL_LIB");
+      if (e) h = dlopen(e, RTLD_NOW | RTLD_LOCAL);
+    }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+      a.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+      return a;
+    }
+    bool all = true;
+    auto sym = [&](const char* n) {
+      void* p = dlsym(h, n);
+      if (!p) {
+        all = false;
+        a.why = std::string("missing NCCL symbol ") + n;
+      }
+      return p;
+    };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.Send = (decltype(a.Send))sym("ncclSend");
+    a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.ok = all;
+    return a;
+  }();
+  return api;
+}
+#define CG_NCCL(expr)                                                                                    \
+  do {                                                                                                   \
+    ncclResult_t r_ = (expr);                                                                            \
+    if (r_ != ncclSuccess) return fail(CG_ERR_NCCL, "%s: %s", #expr, nccl_api().GetErrorString(r_));     \
+  } while (0)
+int need_nccl() {
+  if (!nccl_api().ok) return fail(CG_ERR_NCCL, "NCCL is not available: %s", nccl_api().why.c_str());
+  return CG_OK;
+}
+
+// k-slab plan (same index algebra as slabs.py, which the CPU tests pin): cell planes [k0,k1) of the global cell.full
+// array need the interior node planes required(k0,k1); node plane m is OWNED by the slab that holds cell plane
+// m + nhalo (the first / last slab also own what lies below / above).
+struct SlabRange { int64_t lo, hi; };
+SlabRange slab_required(int64_t k0, int64_t k1, int64_t h, int64_t n) {
+  const int64_t lm = k0 - 1 - h, hm = k1 + 2 - h;
+  int64_t lo = lm < 0 ? 0 : (lm > n ? n : lm), hi = hm < 0 ? 0 : (hm > n ? n : hm);
+  if (lm < 0 && hi < 1) hi = 1;
+  if (hm > n && lo > n - 1) lo = n - 1;
+  return {lo, hi + 1};
+}
+SlabRange slab_owned(int64_t k0, int64_t k1, int64_t h, int64_t n, bool first, bool last) {
+  auto cl = [&](int64_t v) { return v < 0 ? 0 : (v > n + 1 ? n + 1 : v); };
+  const int64_t lo = first ? 0 : cl(k0 - h), hi = last ? n + 1 : cl(k1 - h);
+  return {lo, hi > lo ? hi : lo};
+}
+struct SlabPlanC {
+  int ax = 0;
+  int64_t k0 = 0, k1 = 0;
+  std::vector<int> send_peer, recv_peer;
+  std::vector<SlabRange> send, recv;
+};
+int make_slab_plan(const cg_grid* g, int rank, int nranks, const int64_t* bounds, SlabPlanC& P) {
+  if (g->kind != 1) return fail(CG_ERR_STATE, "halo exchange: DiscreteGrid only (a MappedGrid slab needs no exchange)");
+  if (nranks < 1 || rank < 0 || rank >= nranks || !bounds) return fail(CG_ERR_ARG, "bad rank / nranks / slab_bounds");
+  const int ax = g->dim - 1;
+  const int64_t h = g->nhalo, n = g->ncell[ax];
+  if (bounds[0] != 0 || bounds[nranks] != n + 2 * h) return fail(CG_ERR_ARG, "slab_bounds must cover cell.full of the slab axis");
+  for (int r = 0; r < nranks; ++r)
+    if (bounds[r + 1] <= bounds[r]) return fail(CG_ERR_ARG, "slab_bounds must increase");
+  if (g->w0[ax] != bounds[rank] || g->nw[ax] != bounds[rank + 1] - bounds[rank])
+    return fail(CG_ERR_ARG, "the handle's window [%lld,+%lld) is not slab %d of slab_bounds", (long long)g->w0[ax],
+                (long long)g->nw[ax], rank);
+  P.ax = ax;
+  P.k0 = bounds[rank];
+  P.k1 = bounds[rank + 1];
+  const SlabRange req_me = slab_required(P.k0, P.k1, h, n);
+  const SlabRange own_me = slab_owned(P.k0, P.k1, h, n, rank == 0, rank == nranks - 1);
+  if (g->src_origin[ax] > req_me.lo || g->src_origin[ax] + g->src_count[ax] < req_me.hi)
+    return fail(CG_ERR_STATE, "the node buffer does not cover the planes this slab needs");
+  for (int peer = 0; peer < nranks; ++peer) {
+    if (peer == rank) continue;
+    const SlabRange req_p = slab_required(bounds[peer], bounds[peer + 1], h, n);
+    const SlabRange own_p = slab_owned(bounds[peer], bounds[peer + 1], h, n, peer == 0, peer == nranks - 1);
+    int64_t lo = own_me.lo > req_p.lo ? own_me.lo : req_p.lo, hi = own_me.hi < req_p.hi ? own_me.hi : req_p.hi;
+    if (hi > lo) {
+      P.send_peer.push_back(peer);
+      P.send.push_back({lo, hi});
+    }
+    lo = own_p.lo > req_me.lo ? own_p.lo : req_me.lo;
+    hi = own_p.hi < req_me.hi ? own_p.hi : req_me.hi;
+    if (hi > lo) {
+      P.recv_peer.push_back(peer);
+      P.recv.push_back({lo, hi});
+    }
+  }
+  return CG_OK;
+}
+int ensure_comm_stream(cg_grid* g) {
+  if (g->comm_stream) return CG_OK;
+  CG_CUDA(cudaStreamCreateWithFlags(&g->comm_stream, cudaStreamNonBlocking));
+  CG_CUDA(cudaEventCreateWithFlags(&g->comm_ev[0], cudaEventDisableTiming));
+  CG_CUDA(cudaEventCreateWithFlags(&g->comm_ev[1], cudaEventDisableTiming));
+  return CG_OK;
+}
+// grouped ncclSend / ncclRecv of the plan's node planes, straight out of / into the node buffer, on the handle's
+// communication stream
+int post_plane_exchange(cg_grid* g, ncclComm_t comm, const SlabPlanC& P) {
+  const NcclApi& A = nccl_api();
+  int64_t plane = 1;
+  for (int d = 0; d < P.ax; ++d) plane *= g->src_count[d];
+  const ncclDataType_t dt = g->dtype == CG_F64 ? ncclFloat64 : ncclFloat32;
+  const size_t es = g->esize();
+  if (P.send.empty() && P.recv.empty()) return CG_OK;
+  CG_NCCL(A.GroupStart());
+  for (int q = 0; q < g->dim; ++q) {
+    char* base = (char*)g->src[q].p;
+    for (size_t s = 0; s < P.send.size(); ++s)
+      CG_NCCL(A.Send(base + (size_t)((P.send[s].lo - g->src_origin[P.ax]) * plane) * es,
+                     (size_t)((P.send[s].hi - P.send[s].lo) * plane), dt, P.send_peer[s], comm, g->comm_stream));
+    for (size_t r = 0; r < P.recv.size(); ++r)
+      CG_NCCL(A.Recv(base + (size_t)((P.recv[r].lo - g->src_origin[P.ax]) * plane) * es,
+                     (size_t)((P.recv[r].hi - P.recv[r].lo) * plane), dt, P.recv_peer[r], comm, g->comm_stream));
+  }
+  CG_NCCL(A.GroupEnd());
+  return CG_OK;
+}
+// which padded node planes / cell planes of the slab depend on received node planes (slabs.overlap_schedule):
+// padded plane e holds the interior node plane m = k0 + e - 1 - h, Line()-extrapolated outside [0, n] from
+// c = clamp(m) and its inner neighbour; the cell plane k reads the padded planes k .. k+4
+struct OverlapC { int64_t a, b, ke_lo, ke_hi, ne, nw; };
+OverlapC overlap_schedule(const cg_grid* g, const SlabPlanC& P) {
+  const int64_t h = g->nhalo, n = g->ncell[P.ax], nw = P.k1 - P.k0, ne = nw + 4;
+  auto received = [&](int64_t m) {
+    for (const SlabRange& r : P.recv)
+      if (m >= r.lo && m < r.hi) return true;
+    return false;
+  };
+  std::vector<char> dirty((size_t)ne);
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t m = P.k0 + e - 1 - h, c = m < 0 ? 0 : (m > n ? n : m);
+    dirty[(size_t)e] = received(c) || (m != c && received(m < c ? c + 1 : c - 1));
+  }
+  int64_t a = 0, b = ne;
+  while (a < ne && dirty[(size_t)a]) ++a;
+  while (b > a && dirty[(size_t)b - 1]) --b;
+  for (int64_t e = a; e < b; ++e)
+    if (dirty[(size_t)e]) a = b = ne;  // not a prefix + suffix (cannot happen with contiguous ownership)
+  OverlapC o;
+  o.a = a; o.b = b; o.ne = ne; o.nw = nw;
+  o.ke_lo = a < nw ? a : nw;
+  int64_t khi = b - 4 < nw ? b - 4 : nw;
+  o.ke_hi = khi > o.ke_lo ? khi : o.ke_lo;
+  return o;
+}
+template <class T>
+int step_overlapped_t(cg_grid* g, ncclComm_t comm, const SlabPlanC& P, int what, cudaStream_t st) {
+  int rc;
+  const OverlapC S = overlap_schedule(g, P);
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  // the exchange reads / writes the node buffer after whatever `st` did to it before
+  CG_CUDA(cudaEventRecord(g->comm_ev[0], st));
+  CG_CUDA(cudaStreamWaitEvent(g->comm_stream, g->comm_ev[0], 0));
+  if ((rc = post_plane_exchange(g, comm, P))) return rc;
+  CG_CUDA(cudaEventRecord(g->comm_ev[1], g->comm_stream));
+  // everything that depends on owned node planes only, while the neighbour planes travel
+  if (S.b > S.a && (rc = pad_nodes<T>(g, st, S.a, S.b))) return rc;
+  if (S.ke_hi > S.ke_lo && (rc = eval_impl<T>(g, what, st, S.ke_lo, S.ke_hi, false))) return rc;
+  CG_CUDA(cudaStreamWaitEvent(st, g->comm_ev[1], 0));
+  if (S.a > 0 && (rc = pad_nodes<T>(g, st, 0, S.a))) return rc;
+  if (S.ne > S.b && (rc = pad_nodes<T>(g, st, S.b, S.ne))) return rc;
+  if (S.ke_lo > 0 && (rc = eval_impl<T>(g, what, st, 0, S.ke_lo, false))) return rc;
+  if (S.nw > S.ke_hi && (rc = eval_impl<T>(g, what, st, S.ke_hi, S.nw, false))) return rc;
+  if (what & CG_WHAT_CELL) g->valid_cell = true;
+  if (what & CG_WHAT_FACE) g->valid_face = true;
+  return refresh_coords_if_stored(g, st);
+}
+}  // namespace
+}  // extern "C++"
+
+// -------------------------------------------------------------------------------------------------------------
+// update!(grid, x, y, z) from HOST arrays, pipelined; with a communicator also exchange-aware (k-slabs).
+// -------------------------------------------------------------------------------------------------------------
+extern "C++" {
+namespace {
+template <class T>
+int update_from_host_t(cg_grid* g, const void* const* in, int what, int nchunks, ncclComm_t comm, const SlabPlanC* P,
+                       int nranks, int rank, cudaStream_t st) {
+  const int ax = 2;
+  const int64_t nk = g->src_count[ax], plane = g->src_count[0] * g->src_count[1];
+  const int64_t o = g->src_origin[ax], gn = g->ncell[ax], h = g->nhalo, nw = g->nw[ax], ne = nw + 4;
+  const size_t es = g->esize();
+  int rc;
+  if (!g->copy_stream) {
+    CG_CUDA(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    CG_CUDA(cudaEventCreateWithFlags(&g->copy_ev[0], cudaEventDisableTiming));
+    CG_CUDA(cudaEventCreateWithFlags(&g->copy_ev[1], cudaEventDisableTiming));
+  }
+  // planes of the node buffer this rank reads from ITS host arrays: everything without a communicator, the owned
+  // planes of the slab otherwise (the others arrive from their owners)
+  int64_t own_lo = o, own_hi = o + nk;
+  if (P) {
+    const SlabRange own = slab_owned(P->k0, P->k1, h, gn, rank == 0, rank == nranks - 1);
+    own_lo = own.lo > o ? own.lo : o;
+    own_hi = own.hi < o + nk ? own.hi : o + nk;
+  }
+  std::vector<char> landed((size_t)nk, 0), padded((size_t)ne, 0), evald((size_t)nw, 0);
+  auto is_landed = [&](int64_t m) { return m >= o && m < o + nk && landed[(size_t)(m - o)]; };
+  auto h2d = [&](int64_t lo, int64_t hi) -> int {  // interior node planes [lo, hi) on the copy stream
+    for (int q = 0; q < 3; ++q)
+      CG_CUDA(cudaMemcpyAsync((char*)g->src[q].p + (size_t)((lo - o) * plane) * es,
+                              (const char*)in[q] + (size_t)((lo - o) * plane) * es, (size_t)((hi - lo) * plane) * es,
+                              cudaMemcpyHostToDevice, g->copy_stream));
+    return CG_OK;
+  };
+  // pad every padded plane whose source planes have landed, evaluate every cell plane whose five padded planes exist
+  auto advance = [&]() -> int {
+    for (int64_t e = 0; e < ne;) {
+      auto ready = [&](int64_t ee) {
+        if (padded[(size_t)ee]) return false;
+        const int64_t m = g->w0[ax] + ee - 1 - h, c = m < 0 ? 0 : (m > gn ? gn : m);
+        return is_landed(c) && (m == c || is_landed(m < c ? c + 1 : c - 1));
+      };
+      if (!ready(e)) { ++e; continue; }
+      int64_t e1 = e;
+      while (e1 < ne && ready(e1)) ++e1;
+      if ((rc = pad_nodes<T>(g, st, e, e1))) return rc;
+      for (int64_t i = e; i < e1; ++i) padded[(size_t)i] = 1;
+      e = e1;
+    }
+    for (int64_t k = 0; k < nw;) {
+      auto ready = [&](int64_t kk) {
+        if (evald[(size_t)kk]) return false;
+        for (int d = 0; d < 5; ++d)
+          if (!padded[(size_t)(kk + d)]) return false;
+        return true;
+      };
+      if (!ready(k)) { ++k; continue; }
+      int64_t k1 = k;
+      while (k1 < nw && ready(k1)) ++k1;
+      if ((rc = eval_impl<T>(g, what, st, k, k1, false))) return rc;
+      for (int64_t i = k; i < k1; ++i) evald[(size_t)i] = 1;
+      k = k1;
+    }
+    return CG_OK;
+  };
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  // the copies overwrite the node buffer the previous evaluation's padding read
+  CG_CUDA(cudaEventRecord(g->copy_ev[0], st));
+  CG_CUDA(cudaStreamWaitEvent(g->copy_stream, g->copy_ev[0], 0));
+  std::vector<char> copied((size_t)nk, 0);
+  if (P && (!P->send.empty() || !P->recv.empty())) {
+    // the planes the neighbours wait for go first; the exchange is posted as soon as they are on the device
+    for (const SlabRange& r : P->send) {
+      if ((rc = h2d(r.lo, r.hi))) return rc;
+      for (int64_t m = r.lo; m < r.hi; ++m) copied[(size_t)(m - o)] = 1;
+    }
+    CG_CUDA(cudaEventRecord(g->comm_ev[0], g->copy_stream));
+    CG_CUDA(cudaStreamWaitEvent(g->comm_stream, g->comm_ev[0], 0));
+    if ((rc = post_plane_exchange(g, comm, *P))) return rc;
+    CG_CUDA(cudaEventRecord(g->comm_ev[1], g->comm_stream));
+  }
+  const int64_t nown = own_hi - own_lo;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > nown) nchunks = (int)(nown > 0 ? nown : 1);
+  for (int c = 0; c < nchunks; ++c) {
+    const int64_t p_lo = own_lo + nown * c / nchunks, p_hi = own_lo + nown * (c + 1) / nchunks;
+    for (int64_t m = p_lo; m < p_hi;) {  // the runs of this piece that did not travel with the boundary planes
+      if (copied[(size_t)(m - o)]) { ++m; continue; }
+      int64_t m1 = m;
+      while (m1 < p_hi && !copied[(size_t)(m1 - o)]) ++m1;
+      if ((rc = h2d(m, m1))) return rc;
+      m = m1;
+    }
+    CG_CUDA(cudaEventRecord(g->copy_ev[1], g->copy_stream));
+    CG_CUDA(cudaStreamWaitEvent(st, g->copy_ev[1], 0));
+    for (int64_t m = p_lo; m < p_hi; ++m) landed[(size_t)(m - o)] = 1;
+    if ((rc = advance())) return rc;
+  }
+  if (P && (!P->send.empty() || !P->recv.empty())) {
+    CG_CUDA(cudaStreamWaitEvent(st, g->comm_ev[1], 0));
+    for (const SlabRange& r : P->recv)
+      for (int64_t m = r.lo; m < r.hi; ++m)
+        if (m >= o && m < o + nk) landed[(size_t)(m - o)] = 1;
+    if ((rc = advance())) return rc;
+  }
+  for (int64_t k = 0; k < nw; ++k)
+    if (!evald[(size_t)k]) return fail(CG_ERR_STATE, "node buffer does not cover the window (cell plane %lld)", (long long)k);
+  if (what & CG_WHAT_CELL) g->valid_cell = true;
+  if (what & CG_WHAT_FACE) g->valid_face = true;
+  return refresh_coords_if_stored(g, st);
+}
+
+int update_from_host_common(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks, void* comm,
+                            int rank, int nranks, const int64_t* slab_bounds, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (g->kind != 1 || g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_update_from_host: 3-D DiscreteGrid only");
+  if (what <= 0 || what > 3) return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE)", what);
+  const void* in[3] = {x, y, z};
+  for (int q = 0; q < 3; ++q) {
+    if (!in[q]) return fail(CG_ERR_ARG, "coordinate array %d is NULL", q);
+    if (!g->src[q].p) return fail(CG_ERR_STATE, "no node buffer: call cg_grid_set_nodes once first");
+  }
+  CG_CUDA(cudaSetDevice(g->device));
+  // the copies land in the library's OWN node buffer: a caller's device array (cg_grid_set_nodes with device
+  // pointers) is never overwritten behind the caller's back, the handle switches to a buffer of its own
+  for (int q = 0; q < 3; ++q)
+    if (!g->src[q].owned) {
+      const size_t bytes = g->src[q].bytes;
+      release(g->src[q]);
+      int rc = ensure(g, g->src[q], bytes);
+      if (rc) return rc;
+    }
+  SlabPlanC P;
+  const bool distd = comm != nullptr && nranks > 1;
+  if (distd) {
+    int rc = need_nccl();
+    if (rc) return rc;
+    if ((rc = make_slab_plan(g, rank, nranks, slab_bounds, P))) return rc;
+    if ((rc = ensure_comm_stream(g))) return rc;
+  }
+  return g->dtype == CG_F64
+             ? update_from_host_t<double>(g, in, what, nchunks, (ncclComm_t)comm, distd ? &P : nullptr, nranks, rank, (cudaStream_t)stream)
+             : update_from_host_t<float>(g, in, what, nchunks, (ncclComm_t)comm, distd ? &P : nullptr, nranks, rank, (cudaStream_t)stream);
+}
+}  // namespace
+}  // extern "C++"
+
+int cg_grid_update_from_host(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
+                             void* stream) {
+  return update_from_host_common(g, x, y, z, what, nchunks, nullptr, 0, 1, nullptr, stream);
+}
+
+int cg_grid_update_from_host_dist(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
+                                  void* comm, int rank, int nranks, const int64_t* slab_bounds, void* stream) {
+  if (!comm) return fail(CG_ERR_ARG, "cg_grid_update_from_host_dist: comm is NULL");
+  return update_from_host_common(g, x, y, z, what, nchunks, comm, rank, nranks, slab_bounds, stream);
+}
+
+int cg_nccl_unique_id(void* id128) {
+  if (!id128) return fail(CG_ERR_ARG, "bad argument");
+  int rc = need_nccl();
+  if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  CG_NCCL(nccl_api().GetUniqueId((ncclUniqueId*)id128));
+  return CG_OK;
+}
+
+int cg_nccl_comm_create(const void* id128, int nranks, int rank, int device, void** comm) {
+  if (!id128 || !comm || nranks < 1 || rank < 0 || rank >= nranks) return fail(CG_ERR_ARG, "bad argument");
+  int rc = need_nccl();
+  if (rc) return rc;
+  CG_CUDA(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t c = nullptr;
+  CG_NCCL(nccl_api().CommInitRank(&c, nranks, id, rank));
+  *comm = (void*)c;
+  return CG_OK;
+}
+
+int cg_nccl_comm_destroy(void* comm) {
+  if (!comm) return CG_OK;
+  int rc = need_nccl();
+  if (rc) return rc;
+  CG_NCCL(nccl_api().CommDestroy((ncclComm_t)comm));
+  return CG_OK;
+}
+
+int cg_halo_exchange_begin(cg_grid* g, void* comm, int rank, int nranks, const int64_t* slab_bounds, void* stream) {
+  if (!g || !comm) return fail(CG_ERR_ARG, "bad argument");
+  int rc = need_nccl();
+  if (rc) return rc;
+  SlabPlanC P;
+  if ((rc = make_slab_plan(g, rank, nranks, slab_bounds, P))) return rc;
+  CG_CUDA(cudaSetDevice(g->device));
+  if ((rc = ensure_comm_stream(g))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CG_CUDA(cudaEventRecord(g->comm_ev[0], st));
+  CG_CUDA(cudaStreamWaitEvent(g->comm_stream, g->comm_ev[0], 0));
+  if ((rc = post_plane_exchange(g, (ncclComm_t)comm, P))) return rc;
+  CG_CUDA(cudaEventRecord(g->comm_ev[1], g->comm_stream));
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return CG_OK;
+}
+
+int cg_halo_exchange_end(cg_grid* g, void* stream) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (!g->comm_stream) return fail(CG_ERR_STATE, "cg_halo_exchange_end without cg_halo_exchange_begin");
+  CG_CUDA(cudaSetDevice(g->device));
+  CG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, g->comm_ev[1], 0));
+  return CG_OK;
+}
+
+int cg_grid_step_overlapped(cg_grid* g, void* comm, int rank, int nranks, const int64_t* slab_bounds, int what,
+                            void* stream) {
+  if (!g || !comm) return fail(CG_ERR_ARG, "bad argument");
+  if (what <= 0 || what > 3) return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE)", what);
+  if (g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_step_overlapped: 3-D DiscreteGrid only");
+  int rc = need_nccl();
+  if (rc) return rc;
+  SlabPlanC P;
+  if ((rc = make_slab_plan(g, rank, nranks, slab_bounds, P))) return rc;
+  CG_CUDA(cudaSetDevice(g->device));
+  if ((rc = ensure_comm_stream(g))) return rc;
+  return g->dtype == CG_F64 ? step_overlapped_t<double>(g, (ncclComm_t)comm, P, what, (cudaStream_t)stream)
+                            : step_overlapped_t<float>(g, (ncclComm_t)comm, P, what, (cudaStream_t)stream);
+}
+
+int cg_grid_gcl_max_dist(cg_grid* g, void* comm, int rank, int nranks, double* out, void* stream) {
+  if (!g || !out || !comm) return fail(CG_ERR_ARG, "bad argument");
+  if (!g->valid_face) return fail(CG_ERR_STATE, "face metrics are not valid; evaluate first");
+  int rc = need_nccl();
+  if (rc) return rc;
+  const NcclApi& A = nccl_api();
+  CG_CUDA(cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  void* last = nullptr;
+  size_t pb = 0;
+  if ((rc = cg_grid_seam_plane(g, &last, &pb))) return rc;
+  if (rank > 0 && (rc = ensure(g, g->seam, pb))) return rc;
+  // my last conserved plane of the slab axis goes up, the lower neighbour's comes in (same stream: ordered after the
+  // metric kernels)
+  if (nranks > 1) {
+    CG_NCCL(A.GroupStart());
+    if (rank + 1 < nranks) CG_NCCL(A.Send(last, pb, ncclChar, rank + 1, (ncclComm_t)comm, st));
+    if (rank > 0) CG_NCCL(A.Recv(g->seam.p, pb, ncclChar, rank - 1, (ncclComm_t)comm, st));
+    CG_NCCL(A.GroupEnd());
+  }
+  bool empty = false;
+  if ((rc = gcl_launch(g, rank > 0 ? g->seam.p : nullptr, st, &empty))) return rc;
+  // non-negative doubles order like their bit patterns (a NaN pattern is the largest): max over ranks on the bits
+  if (nranks > 1) CG_NCCL(A.AllReduce(g->gcl_bits, g->gcl_bits, 3, ncclUint64, ncclMax, (ncclComm_t)comm, st));
+  return gcl_read(g, out, st);
 }
 
 }  // extern "C"

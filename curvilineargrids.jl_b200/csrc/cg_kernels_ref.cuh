@@ -522,7 +522,10 @@ __global__ void k_metrics3d_ref(Dims D, const T* ex, const T* ey, const T* ez, M
 // ---------------------------------------------------------------------------
 template <class T>
 __global__ void k_gcl(Dims D, const T* c0, const T* c1, const T* c2, int compact, int64_t lo0, int64_t lo1,
-                      int64_t lo2, int64_t hi0, int64_t hi1, int64_t hi2, unsigned long long* out_bits) {
+                      int64_t lo2, int64_t hi0, int64_t hi1, int64_t hi2, const T* low, unsigned long long* out_bits) {
+  // `low` (may be NULL): conserved metrics of the slab axis (the last one) on the cell plane just BELOW the window,
+  // [nw0 * nw1][K] — the previous rank's last plane; with it the window-local plane 0 is evaluated too (its low
+  // face along the slab axis lives on the neighbour).
   const T* C[3] = {c0, c1, c2};
   const int N = D.dim;
   const int K = compact ? N : N * N;
@@ -533,19 +536,25 @@ __global__ void k_gcl(Dims D, const T* c0, const T* c1, const T* c2, int compact
   cs[2] = D.nw[0] * D.nw[1];
   const int64_t ntot = ext[0] * ext[1] * ext[2];
   double mx[3] = {0, 0, 0};
+  bool bad[3] = {false, false, false};  // a non-finite residual: maximum(abs.(I)) of the reference propagates NaN
   for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
        lin += (int64_t)gridDim.x * blockDim.x) {
-    int64_t i = lo[0] + lin % ext[0], r = lin / ext[0];
-    int64_t j = lo[1] + r % ext[1], k = lo[2] + r / ext[1];
-    int64_t cl = i + j * cs[1] + k * cs[2];
+    int64_t idx[3];
+    idx[0] = lo[0] + lin % ext[0];
+    const int64_t r = lin / ext[0];
+    idx[1] = lo[1] + r % ext[1];
+    idx[2] = lo[2] + r / ext[1];
+    int64_t cl = idx[0] + idx[1] * cs[1] + idx[2] * cs[2];
     for (int c = 0; c < N; ++c) {
       T acc = 0;
       for (int ax = 0; ax < N; ++ax) {
         const int e = compact ? c : (ax + N * c);
-        acc += C[ax][cl * K + e] - C[ax][(cl - cs[ax]) * K + e];
+        const T below = (ax == N - 1 && idx[ax] == 0) ? low[(cl - idx[ax] * cs[ax]) * K + e] : C[ax][(cl - cs[ax]) * K + e];
+        acc += C[ax][cl * K + e] - below;
       }
       double a = fabs((double)acc);
       if (a > mx[c]) mx[c] = a;
+      if (!(a <= 1.7976931348623157e308)) bad[c] = true;  // NaN or Inf
     }
   }
   for (int c = 0; c < N; ++c) {
@@ -554,7 +563,12 @@ __global__ void k_gcl(Dims D, const T* c0, const T* c1, const T* c2, int compact
       double w = __shfl_down_sync(0xffffffffu, v, o);
       v = w > v ? w : v;
     }
-    if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out_bits + c, (unsigned long long)__double_as_longlong(v));
+    const unsigned anybad = __ballot_sync(0xffffffffu, bad[c]);
+    // the bit pattern of a quiet NaN is larger than that of any finite value or Inf: atomicMax keeps it
+    if ((threadIdx.x & 31) == 0) {
+      if (anybad) atomicMax(out_bits + c, 0x7ff8000000000000ull);
+      else if (v > 0.0) atomicMax(out_bits + c, (unsigned long long)__double_as_longlong(v));
+    }
   }
 }
 

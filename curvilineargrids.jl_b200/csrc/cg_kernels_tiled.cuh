@@ -1045,7 +1045,10 @@ inline int pick_chunk(int64_t tiles, int64_t extent, int64_t slots, int min_chun
 // ---------------------------------------------------------------------------
 template <class T>
 inline bool tiled3d_supported(const Dims& D, const MetricOut<T>&) {
-  return D.dim == 3 && (sizeof(Ix) == 8 || D.ne[0] * D.ne[1] * D.ne[2] < (int64_t(1) << 31));
+  // gridDim.y carries rows (j, or k planes in the eta kernel), gridDim.z the chunks: both are limited to 65535; a
+  // window that skewed falls back to the gather kernel
+  const bool grid_ok = D.nw[1] <= 65535 && D.nw[2] <= 65535;
+  return D.dim == 3 && grid_ok && (sizeof(Ix) == 8 || D.ne[0] * D.ne[1] * D.ne[2] < (int64_t(1) << 31));
 }
 // ===========================================================================
 // 2-D: one thread per PAIR of xi-adjacent cells (2p, 2p+1) of a row.  The pair's 80 B of every
@@ -1330,36 +1333,43 @@ inline int launch_metrics2d_tiled(const Dims& D, const T* ex, const T* ey, const
 // (fork / join with events) so that the last, partly filled wave of one kernel overlaps the first wave of the next.
 // CG_CONCURRENT=0 serialises them always.
 struct Fork {
-  cudaStream_t s[2];
-  cudaEvent_t start, done[2];
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t start = nullptr, done[2] = {nullptr, nullptr};
+  bool made = false;
+  // The helper streams and events belong to ONE grid handle (a handle is single-threaded by contract, so two host
+  // threads working on two handles of the same device never share an event).
+  bool ensure() {
+    static const int enabled = [] {
+      const char* e = getenv("CG_CONCURRENT");  // debug switch (listed in include/curvigrid_cuda.h)
+      return e ? atoi(e) : 1;
+    }();
+    if (!enabled) return false;
+    if (made) return true;
+    if (cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&start, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming) != cudaSuccess) return false;
+    made = true;
+    return true;
+  }
+  void destroy() {
+    for (int i = 0; i < 2; ++i) {
+      if (s[i]) cudaStreamDestroy(s[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+      s[i] = nullptr;
+      done[i] = nullptr;
+    }
+    if (start) cudaEventDestroy(start);
+    start = nullptr;
+    made = false;
+  }
 };
-inline Fork* fork_streams() {
-  static Fork forks[16];
-  static bool made[16] = {false};
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("CG_CONCURRENT");
-    enabled = e ? atoi(e) : 1;
-  }
-  if (!enabled) return nullptr;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (!made[dev]) {
-    Fork& f = forks[dev];
-    if (cudaStreamCreateWithFlags(&f.s[0], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaStreamCreateWithFlags(&f.s[1], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    cudaEventCreateWithFlags(&f.start, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&f.done[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&f.done[1], cudaEventDisableTiming);
-    made[dev] = true;
-  }
-  return &forks[dev];
-}
 
 // mask: bit0 xi kernel (+cell), bit1 eta kernel, bit2 zeta kernel
 template <class T, int SCH>
 inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez, const MetricOut<T>& O, int what,
-                           int mask, cudaStream_t st) {
+                           int mask, cudaStream_t st, Fork* fork) {
   // enough blocks for ~30 waves (fine-grained tail, measured best at 512^3) as long as a chunk stays >= 64 steps
   // (the prologue of a chunk costs about three steps)
   const int64_t want = 148LL * 64;
@@ -1394,23 +1404,24 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   const bool is_face_only = (what & 3) == 2 && faces_full;
   const bool is_cell_only = (what & 3) == 1 && no_compact && O.cell_fwd && O.cell_inv;
   const int zmode = (is_full || is_face_only) ? MODE_FULL : mode;  // eta / zeta kernels
+  bool attr_ok = true;
   auto launch_xi = [&](auto kern, int warp_vals, dim3 grid, int kchunk) {
     const int smem = XWY * warp_vals * (int)sizeof(T);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_ok &= cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
     if (XWY == 1 && JFAST) grid = dim3(grid.y, grid.x, grid.z);
     kern<<<grid, dim3(32, XWY), smem, st>>>(D, ex, ey, ez, O, what, kchunk);
   };
   cudaStream_t zst = st;  // stream of the next eta / zeta launch
   auto launch_zeta = [&](auto kern, int warp_vals, dim3 grid, int chunk) {
     const int smem = ZWY * warp_vals * (int)sizeof(T);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_ok &= cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
     if (ZWY == 1 && JFAST) grid = dim3(grid.y, grid.x, grid.z);
     kern<<<grid, dim3(32, ZWY), smem, zst>>>(D, ex, ey, ez, O, chunk);
   };
   // small grids only: a large grid fills the GPU for many waves per kernel and the one-warp blocks of the eta / zeta
   // kernels leave short tails; serial launches measured equal or better there (512^3: 28.6 vs 29.2 ms)
   const bool small_grid = D.nw[0] * D.nw[1] * nplanes < (int64_t)(1 << 24);
-  Fork* fk = (face && (mask & 7) == 7 && small_grid) ? fork_streams() : nullptr;
+  Fork* fk = (face && (mask & 7) == 7 && small_grid && fork && fork->ensure()) ? fork : nullptr;
   if (fk) {
     cudaEventRecord(fk->start, st);
     cudaStreamWaitEvent(fk->s[0], fk->start, 0);
@@ -1457,15 +1468,15 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     cudaStreamWaitEvent(st, fk->done[0], 0);
     cudaStreamWaitEvent(st, fk->done[1], 0);
   }
-  return n;
+  return attr_ok ? n : -1;
 }
 
 template <class T>
 inline int launch_metrics3d_tiled(const Dims& D, const T* ex, const T* ey, const T* ez, const MetricOut<T>& O,
-                                  int scheme, int what, int mask, cudaStream_t st) {
-  if (scheme == ENDPOINT) return launch3d_scheme<T, ENDPOINT>(D, ex, ey, ez, O, what, mask, st);
-  if (scheme == GRADIENT) return launch3d_scheme<T, GRADIENT>(D, ex, ey, ez, O, what, mask, st);
-  return launch3d_scheme<T, CURVATURE>(D, ex, ey, ez, O, what, mask, st);
+                                  int scheme, int what, int mask, cudaStream_t st, Fork* fork) {
+  if (scheme == ENDPOINT) return launch3d_scheme<T, ENDPOINT>(D, ex, ey, ez, O, what, mask, st, fork);
+  if (scheme == GRADIENT) return launch3d_scheme<T, GRADIENT>(D, ex, ey, ez, O, what, mask, st, fork);
+  return launch3d_scheme<T, CURVATURE>(D, ex, ey, ez, O, what, mask, st, fork);
 }
 
 }  // namespace cg

@@ -206,8 +206,15 @@ class _UnifiedGrid:
                                  self._bound[(L.CG_ARR_FACE_CONSERVED, a)]) for a in range(self.dim))
 
     # ---- coordinates --------------------------------------------------------
+    def _coords_valid(self):
+        v = ctypes.c_int()
+        L.check(L.lib().cg_grid_coords_valid(self._h, ctypes.byref(v)))
+        return bool(v.value)
+
     def _ensure_coords(self):
-        if not self._coords_enabled:
+        # the library re-evaluates stored coordinates whenever the nodes / mapping state change (update!,
+        # set_nodes, update_from_host); ask it instead of trusting a Python-side flag
+        if not self._coords_enabled or not self._coords_valid():
             self._eval(L.CG_WHAT_COORDS)
 
     @property
@@ -314,13 +321,16 @@ class DiscreteGrid(_UnifiedGrid):
         L.check(L.lib().cg_grid_set_nodes(self._h, ptrs[0], ptrs[1], ptrs[2], int(self.halo_coords_included),
                                           origin, count, self._stream()))
         self._node_inputs = keep  # keep device inputs alive: the library reads them in place
+        self._node_input_shape = tuple(reversed(nn))  # memory order [k, j, i]
         if any(isinstance(k, np.ndarray) for k in keep):
             self.synchronize()  # pageable host memory must outlive the async copy
 
-    def update_from_host(self, *coords, what=3, nchunks=8):
+    def update_from_host(self, *coords, what=3, nchunks=8, comm=None, plan=None):
         """update!(grid, x, y, z) from HOST arrays + refresh of both caches, pipelined (cg_grid_update_from_host):
         the H2D copy of a piece of node planes overlaps the metric kernels of the piece before.  `coords`: pinned
-        CPU torch tensors (or numpy arrays) in memory order [k, j, i] with the extents of the constructor's arrays."""
+        CPU torch tensors (or numpy arrays) in memory order [k, j, i] with the extents of the constructor's arrays.
+        With `comm` (slabs.NcclComm) and `plan` the grid is a k-slab: only the owned planes are read from the host
+        arrays and the neighbour planes arrive through NCCL meanwhile (cg_grid_update_from_host_dist)."""
         torch = _torch()
         if self.dim != 3:
             raise ValueError("update_from_host: 3-D DiscreteGrid only")
@@ -329,10 +339,20 @@ class DiscreteGrid(_UnifiedGrid):
             t = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(c, dtype=self.T))
             if t.is_cuda or not t.is_contiguous() or t.dtype != self.tdtype:
                 raise ValueError("update_from_host needs contiguous CPU arrays of the grid's dtype")
+            if tuple(t.shape) != self._node_input_shape:
+                raise ValueError(f"update_from_host: arrays must have the extents of the constructor's arrays "
+                                 f"{self._node_input_shape}, got {tuple(t.shape)}")
             ptrs.append(t)
+        if len(ptrs) != 3:
+            raise ValueError("update_from_host takes three coordinate arrays")
         self._bind_metric_outputs(what)
-        L.check(L.lib().cg_grid_update_from_host(self._h, *[ctypes.c_void_p(t.data_ptr()) for t in ptrs], what,
-                                                 int(nchunks), self._stream()))
+        if comm is not None and comm.nranks > 1:
+            L.check(L.lib().cg_grid_update_from_host_dist(
+                self._h, *[ctypes.c_void_p(t.data_ptr()) for t in ptrs], what, int(nchunks), comm._h, comm.rank,
+                comm.nranks, comm.bounds(plan), self._stream()))
+        else:
+            L.check(L.lib().cg_grid_update_from_host(self._h, *[ctypes.c_void_p(t.data_ptr()) for t in ptrs], what,
+                                                     int(nchunks), self._stream()))
         self._host_keepalive = ptrs  # the copies are asynchronous
 
     def set_nodes(self, *coords):
@@ -466,12 +486,28 @@ def local_grid(grid, global_cell_domain):
                       global_cell_indices=tuple((o, o + c) for o, c in zip(goff, celldims)), t=grid.state["t"])
 
 
-def gcl(grid):
-    """max |I_c| over cell.domain for each physical column (../gcl.jl:20-117 reduced on device)."""
+def gcl(grid, low_plane=None):
+    """max |I_c| over cell.domain for each physical column (../gcl.jl:20-117 reduced on device).
+
+    `low_plane` (k-slab windows): the previous slab's last conserved plane of the slab axis (`seam_plane` of that
+    grid); with it the window's first plane — whose low face lives on the neighbour — is checked as well."""
     face_metrics(grid)
     out = (ctypes.c_double * 3)()
-    L.check(L.lib().cg_grid_gcl_max(grid._h, out, grid._stream()))
+    if low_plane is None:
+        L.check(L.lib().cg_grid_gcl_max(grid._h, out, grid._stream()))
+    else:
+        L.check(L.lib().cg_grid_gcl_max_seam(grid._h, ctypes.c_void_p(low_plane.data_ptr()), out, grid._stream()))
     return tuple(out[c] for c in range(grid.dim))
+
+
+def seam_plane(grid):
+    """The last plane (along the slab axis) of the conserved metrics of the slab axis, as a device tensor view: what
+    the next slab's `gcl(grid, low_plane=...)` needs."""
+    face_metrics(grid)
+    ax = grid.dim - 1
+    if grid.profile == "compact":
+        return grid._bound[(L.CG_ARR_COMPACT_ACTIVE, ax)][-1]
+    return grid._bound[(L.CG_ARR_FACE_CONSERVED, ax)][-1]
 
 
 # ---------------------------------------------------------------------------

@@ -180,6 +180,63 @@ def step_overlapped(grid, plan, buffers, what=3, dist=None, group=None):
     return plan_
 
 
+class NcclComm:
+    """An ncclComm_t owned by libcurvigrid_cuda.so (cg_nccl_comm_create): what a Julia host would take from NCCL.jl.
+    The 128-byte unique id is made on rank 0 (cg_nccl_unique_id) and broadcast with torch.distributed (any backend);
+    from then on every exchange is a C-ABI call (cg_grid_step_overlapped, cg_halo_exchange_*, cg_grid_gcl_max_dist)."""
+
+    def __init__(self, rank, nranks, device, dist=None, group=None):
+        import ctypes
+
+        import torch
+
+        from . import _lib as L
+        if dist is None:
+            import torch.distributed as dist
+        self.rank, self.nranks = int(rank), int(nranks)
+        idbuf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            L.check(L.lib().cg_nccl_unique_id(idbuf))
+        if nranks > 1:
+            obj = [bytes(idbuf)]
+            dist.broadcast_object_list(obj, src=0, group=group)
+            idbuf = (ctypes.c_ubyte * 128).from_buffer_copy(obj[0])
+        self._h = ctypes.c_void_p()
+        torch.cuda.set_device(device)
+        L.check(L.lib().cg_nccl_comm_create(idbuf, self.nranks, self.rank, int(device), ctypes.byref(self._h)))
+
+    def close(self):
+        from . import _lib as L
+        if getattr(self, "_h", None) and self._h.value:
+            L.lib().cg_nccl_comm_destroy(self._h)
+            self._h = None
+
+    def bounds(self, plan):
+        """slab_bounds argument of the C ABI for the partition make_plan uses."""
+        import ctypes
+        parts = partition_planes(plan.ncell_slab + 2 * plan.nhalo, plan.nranks)
+        return (ctypes.c_int64 * (plan.nranks + 1))(*([p[0] for p in parts] + [parts[-1][1]]))
+
+
+def step_overlapped_nccl(grid, plan, comm, what=3):
+    """step_overlapped through the C ABI only (cg_grid_step_overlapped): NCCL send / recv of the node planes on the
+    handle's communication stream, interior planes meanwhile, boundary planes after the wait."""
+    from . import _lib as L
+    grid._bind_metric_outputs(what)
+    L.check(L.lib().cg_grid_step_overlapped(grid._h, comm._h, comm.rank, comm.nranks, comm.bounds(plan), what,
+                                            grid._stream()))
+
+
+def gcl_dist(grid, comm):
+    """GCL max over all slabs, seam faces included (cg_grid_gcl_max_dist)."""
+    import ctypes
+
+    from . import _lib as L
+    out = (ctypes.c_double * 3)()
+    L.check(L.lib().cg_grid_gcl_max_dist(grid._h, comm._h, comm.rank, comm.nranks, out, grid._stream()))
+    return tuple(out[c] for c in range(grid.dim))
+
+
 def slab_grid_kwargs(plan, inplane_celldims, nhalo):
     """kwargs for DiscreteGrid(...) describing this rank's slab of a 2-D/3-D grid.
     `inplane_celldims`: interior cells of the non-slab axes, fastest first."""

@@ -20,6 +20,12 @@
  * reference has no locking either).  `stream` arguments are cudaStream_t passed
  * as void* (NULL = the legacy default stream); calls are stream-ordered and
  * asynchronous unless stated otherwise.
+ *
+ * Environment variables read by the library (debug / experiment switches only; none is needed in production):
+ *   CG_CONCURRENT=0      launch the three 3-D face kernels of a SMALL grid serially instead of on forked streams
+ *   CG_2D_STAGED=0       2-D FULL cell+face: use the pair kernel instead of the staged (TMA) kernel
+ *   CG_MAPPED_NCHUNK=n   MappedGrid 3-D kernel: number of chunks along k (default: wave-aware choice)
+ *   CG_NCCL_LIB=path     libnccl to dlopen when the process has not loaded one (default libnccl.so.2)
  */
 #ifndef CURVIGRID_CUDA_H
 #define CURVIGRID_CUDA_H
@@ -161,13 +167,21 @@ int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int fi
  * of the last cg_grid_set_nodes; pinned host memory for a truly asynchronous copy) go to the device in `nchunks`
  * pieces along the slab axis on an internal copy stream; each piece that lands releases the padded planes and cell
  * planes it completes on `stream` (cg_grid_pad_planes / cg_grid_eval_planes), so the host-to-device copy of piece
- * c+1 overlaps the metric kernels of piece c.  Marks the caches valid.
+ * c+1 overlaps the metric kernels of piece c.  Marks the caches valid.  The copies land in a node buffer the
+ * library owns: if cg_grid_set_nodes was given DEVICE arrays the handle stops aliasing them and allocates its own
+ * (a caller's device array is never overwritten).
  */
 int cg_grid_update_from_host(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
                              void* stream);
 
-/* valid flags of UnifiedMetricCache (unified_grids.jl:34-52); invalidate_* (metric_cache_api.jl:16-41) */
+/* valid flags of UnifiedMetricCache (unified_grids.jl:34-52); invalidate_* (metric_cache_api.jl:16-41).
+ * Binding a new buffer (cg_grid_bind_output) or first use of a never-computed array (cg_grid_get_ptr) clears the flag
+ * of the cache the array belongs to. */
 int cg_grid_valid(const cg_grid* g, int* cell_valid, int* face_valid);
+/* node / centroid / face coordinates are up to date with the nodes / mapping state (they are re-evaluated by
+ * cg_grid_set_nodes, cg_grid_nodes_changed, cg_grid_update, cg_grid_update_from_host and cg_grid_step_overlapped
+ * whenever coordinate storage exists, like the reference's update!, discrete_grid.jl:605-647) */
+int cg_grid_coords_valid(const cg_grid* g, int* coords_valid);
 int cg_grid_invalidate(cg_grid* g, int what);
 
 /* device pointer + size of an output array (allocated on first use) */
@@ -183,6 +197,16 @@ int cg_grid_copy_out(cg_grid* g, int array, int axis, void* host_dst, size_t nby
  * column (../gcl.jl:20-117).  Synchronises the stream; out[0..dim).
  */
 int cg_grid_gcl_max(cg_grid* g, double* out, void* stream);
+/*
+ * The same for a k-slab window.  cg_grid_gcl_max skips the window-local plane 0 of the slab axis (the last axis)
+ * when that plane is not the first of cell.domain: its low face lives on the previous slab.  With `low_plane` =
+ * the previous slab's LAST plane of the conserved metrics of the slab axis (device pointer, [cells of a plane][K];
+ * cg_grid_seam_plane of the neighbour's handle, moved by the caller or by cg_grid_gcl_max_dist) the plane is
+ * evaluated too, so the max over the slabs equals the max of the undivided grid.  A non-finite residual gives NaN
+ * (maximum(abs.(I)) propagates NaN in the reference).
+ */
+int cg_grid_gcl_max_seam(cg_grid* g, const void* low_plane, double* out, void* stream);
+int cg_grid_seam_plane(cg_grid* g, void** devptr, size_t* nbytes);
 
 /*
  * Solver-facing bundles for every cell of the window, SoA, device pointers of the grid's dtype:
@@ -214,6 +238,42 @@ int cg_grid_cell_volumes(cg_grid* g, int coordsys, void* volume, void* stream);
  */
 int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const void* src_idx, int64_t n, int elem_bytes,
                         void* stream);
+
+/*
+ * Multi-GPU k-slabs with NCCL inside the boundary (one process per GPU).  The reference has no communication layer
+ * (local_grid, mapped_grid.jl:344-379, only hands out rank-local ANALYTIC grids); a sampled DiscreteGrid slab needs
+ * real neighbour node planes: 1 below and 3 above its cell planes.  `comm` is an ncclComm_t passed as void* (from
+ * NCCL.jl / the host's own NCCL, or from cg_nccl_comm_create); libnccl is resolved at run time from the copy the
+ * process has loaded.  `slab_bounds` = nranks + 1 increasing cell-plane indices of the GLOBAL cell.full along the
+ * slab axis (the last axis): rank r stores the planes [slab_bounds[r], slab_bounds[r+1]) and the handle's window
+ * must be exactly that slab.  Node plane m is owned by the slab that holds the cell plane m + nhalo.  Failures of
+ * NCCL return CG_ERR_NCCL.
+ *   cg_halo_exchange_begin   grouped ncclSend / ncclRecv of the node planes straight out of / into the handle's node
+ *                            buffer on an internal stream (ordered after the work already queued on `stream`)
+ *   cg_halo_exchange_end     makes `stream` wait for the exchange; follow with cg_grid_nodes_changed (or
+ *                            cg_grid_pad_planes) and cg_grid_eval
+ *   cg_grid_step_overlapped  one evaluation of a 3-D slab with the exchange hidden behind interior work: post the
+ *                            exchange; pad + evaluate every plane that depends on owned nodes only; wait; pad +
+ *                            evaluate the 1 (low) / 3 (high) boundary planes; mark the caches valid
+ *   cg_grid_gcl_max_dist     GCL max over ALL slabs: the last conserved plane of the slab axis travels to the next
+ *                            rank (seam faces are checked), ncclAllReduce(max) of the three residuals
+ */
+int cg_nccl_unique_id(void* id128 /* 128 bytes out: ncclGetUniqueId, to be broadcast by the host */);
+int cg_nccl_comm_create(const void* id128, int nranks, int rank, int device, void** comm);
+int cg_nccl_comm_destroy(void* comm);
+int cg_halo_exchange_begin(cg_grid* g, void* comm, int rank, int nranks, const int64_t* slab_bounds, void* stream);
+int cg_halo_exchange_end(cg_grid* g, void* stream);
+int cg_grid_step_overlapped(cg_grid* g, void* comm, int rank, int nranks, const int64_t* slab_bounds, int what,
+                            void* stream);
+int cg_grid_gcl_max_dist(cg_grid* g, void* comm, int rank, int nranks, double* out, void* stream);
+/*
+ * cg_grid_update_from_host for a k-slab: only the node planes this rank OWNS are read from its host arrays (same
+ * layout and extents as the arrays of cg_grid_set_nodes); the planes the neighbours wait for are copied first and
+ * the NCCL exchange is posted as soon as they are on the device; the remaining pieces follow, each releasing the
+ * padded planes and cell planes it completes; the planes that depend on received nodes are done after the exchange.
+ */
+int cg_grid_update_from_host_dist(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
+                                  void* comm, int rank, int nranks, const int64_t* slab_bounds, void* stream);
 
 int cg_grid_sync(cg_grid* g, void* stream);
 /* device time of the last cg_grid_eval on this handle in ms (CUDA events; synchronises) */

@@ -11,7 +11,21 @@
 #pragma once
 #include <cmath>
 
+// Base real type of the restatement.  Default double (= the reference's Float64 arithmetic).  The extended builds
+// (liboracle_ld.so: long double, 64-bit mantissa; liboracle_q.so: __float128) evaluate the SAME closure graph in
+// higher precision; tests use them as "truth" to tell which side owns a last-digits difference between the FP64
+// oracle and the CUDA kernels (conserved metrics are O(dx^2) differences of O(|x| dx) products, so both FP64 sides
+// carry round-off of order eps |x| / dx).
+#ifndef CGO_REAL
+#define CGO_REAL double
+#endif
+#if defined(CGO_REAL_IS_QUAD)
+#include <quadmath.h>
+#endif
+
 namespace cgo {
+
+using real = CGO_REAL;
 
 template <class T>
 struct Dual {
@@ -23,7 +37,7 @@ struct Dual {
 template <class T>
 struct dtraits {
   static T from(double c) { return c; }
-  static double primal(const T& x) { return x; }
+  static double primal(const T& x) { return (double)x; }
 };
 template <class T>
 struct dtraits<Dual<T>> {
@@ -59,6 +73,13 @@ template <class T> inline Dual<T> operator/(double a, const Dual<T>& b) {
 // ---- elementary functions (the reference's test mappings use sin/cos/sinpi) -
 inline double sin_(double x) { return std::sin(x); }
 inline double cos_(double x) { return std::cos(x); }
+#if defined(CGO_REAL_IS_LD)
+inline long double sin_(long double x) { return sinl(x); }
+inline long double cos_(long double x) { return cosl(x); }
+#elif defined(CGO_REAL_IS_QUAD)
+inline __float128 sin_(__float128 x) { return sinq(x); }
+inline __float128 cos_(__float128 x) { return cosq(x); }
+#endif
 template <class T> inline Dual<T> sin_(const Dual<T>& a);
 template <class T> inline Dual<T> cos_(const Dual<T>& a);
 template <class T> inline Dual<T> sin_(const Dual<T>& a) { return {sin_(a.v), cos_(a.v) * a.d}; }

@@ -253,9 +253,9 @@ struct Cache3 {
   Vals<S, 9> Jinv(const Pt<S>& p) const { return inv3(ad_jacobian<3>(m, t, p)); }
 
   // metrics.jl:1751-1793 with 818-850: G = Jinv_{axis+½}, Ghat[r][c] = M̂_{axis+½}
-  void face(int axis, const Pt<double>& p, double* G, double* Ghat) const {
+  void face(int axis, const Pt<real>& p, real* G, real* Ghat) const {
     auto fj = [&](const auto& q) { return this->Jinv(q); };
-    Vals<double, 9> g = edge_reconstruct<SCH, 9>(fj, axis, p);
+    Vals<real, 9> g = edge_reconstruct<SCH, 9>(fj, axis, p);
     for (int k = 0; k < 9; ++k) G[k] = g.e[k];
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c) {
@@ -287,11 +287,11 @@ struct Cache2 {
     return ji;
   }
   // metrics.jl:1735-1749 with 577-582
-  void face(int axis, const Pt<double>& p, double* G, double* Ghat) const {
+  void face(int axis, const Pt<real>& p, real* G, real* Ghat) const {
     auto fj = [&](const auto& q) { return this->jinv(q); };
     auto fn = [&](const auto& q) { return this->normalized_jinv(q); };
-    Vals<double, 4> g = edge_reconstruct<SCH, 4>(fj, axis, p);
-    Vals<double, 4> h = edge_reconstruct<SCH, 4>(fn, axis, p);
+    Vals<real, 4> g = edge_reconstruct<SCH, 4>(fj, axis, p);
+    Vals<real, 4> h = edge_reconstruct<SCH, 4>(fn, axis, p);
     for (int k = 0; k < 4; ++k) {
       G[k] = g.e[k];
       Ghat[k] = h.e[k];
@@ -319,7 +319,7 @@ struct Cache1 {
     o.e[0] = (1.0 / j.e[0]) * j.e[0];
     return o;
   }
-  void face(int axis, const Pt<double>& p, double* G, double* Ghat) const {
+  void face(int axis, const Pt<real>& p, real* G, real* Ghat) const {
     auto fj = [&](const auto& q) { return this->jinv(q); };
     auto fn = [&](const auto& q) { return this->normalized_jinv(q); };
     G[0] = edge_reconstruct<SCH, 1>(fj, axis, p).e[0];
@@ -336,43 +336,43 @@ struct Cache1 {
 // Outputs use the Julia element layout: N*N column-major doubles then J.
 // ---------------------------------------------------------------------------
 template <int N>
-inline double detN(const double* m) {
+inline real detN(const real* m) {
   if constexpr (N == 1) return m[0];
   if constexpr (N == 2) {
-    Vals<double, 4> v;
+    Vals<real, 4> v;
     for (int k = 0; k < 4; ++k) v.e[k] = m[k];
     return det2(v);
   }
   if constexpr (N == 3) {
-    Vals<double, 9> v;
+    Vals<real, 9> v;
     for (int k = 0; k < 9; ++k) v.e[k] = m[k];
     return det3(v);
   }
 }
 template <int N>
-inline void invN(const double* m, double* o) {
+inline void invN(const real* m, real* o) {
   if constexpr (N == 1) o[0] = 1.0 / m[0];
   if constexpr (N == 2) {
-    Vals<double, 4> v;
+    Vals<real, 4> v;
     for (int k = 0; k < 4; ++k) v.e[k] = m[k];
-    Vals<double, 4> r = inv2(v);
+    Vals<real, 4> r = inv2(v);
     for (int k = 0; k < 4; ++k) o[k] = r.e[k];
   }
   if constexpr (N == 3) {
-    Vals<double, 9> v;
+    Vals<real, 9> v;
     for (int k = 0; k < 9; ++k) v.e[k] = m[k];
-    Vals<double, 9> r = inv3(v);
+    Vals<real, 9> r = inv3(v);
     for (int k = 0; k < 9; ++k) o[k] = r.e[k];
   }
 }
 
 template <int N, class M>
-inline void cell_metric(const M& m, double t, const Pt<double>& p, double* fwd /*N*N+1*/, double* inv /*N*N+1*/) {
-  double F[N * N], G[N * N];
+inline void cell_metric(const M& m, double t, const Pt<real>& p, real* fwd /*N*N+1*/, real* inv /*N*N+1*/) {
+  real F[N * N], G[N * N];
   m.forward_jacobian(t, p, F);
-  Vals<double, N * N> Jad = ad_jacobian<N>(m, t, p);
+  Vals<real, N * N> Jad = ad_jacobian<N>(m, t, p);
   invN<N>(Jad.e, G);
-  double J = detN<N>(F);
+  real J = detN<N>(F);
   for (int k = 0; k < N * N; ++k) {
     fwd[k] = F[k];
     inv[k] = G[k];
@@ -382,8 +382,8 @@ inline void cell_metric(const M& m, double t, const Pt<double>& p, double* fwd /
 }
 
 template <int N, int SCH, class M>
-inline void face_metric(const M& m, double t, int axis, const Pt<double>& p, double* fwd, double* inv, double* cons) {
-  double G[N * N], Ghat[N * N], F[N * N];
+inline void face_metric(const M& m, double t, int axis, const Pt<real>& p, real* fwd, real* inv, real* cons) {
+  real G[N * N], Ghat[N * N], F[N * N];
   if constexpr (N == 3) {
     Cache3<M, SCH> c{m, t};
     c.face(axis, p, G, Ghat);
@@ -395,7 +395,7 @@ inline void face_metric(const M& m, double t, int axis, const Pt<double>& p, dou
     c.face(axis, p, G, Ghat);
   }
   invN<N>(G, F);
-  double J = detN<N>(F);
+  real J = detN<N>(F);
   for (int k = 0; k < N * N; ++k) {
     fwd[k] = F[k];
     inv[k] = G[k];
@@ -411,17 +411,17 @@ inline void face_metric(const M& m, double t, int axis, const Pt<double>& p, dou
 // equivalence the reference's own test asserts against CurvatureCorrectedReconstruction
 // (test_3d_continuous.jl:296-297, |difference| < 1e-12), not through the pair-table assembly (:2336-3080).
 template <class M>
-inline void face_metric_adtl3(const M& m, double t, int axis, const Pt<double>& p, double* fwd, double* inv, double* cons) {
-  double G[9], Ghat[9];
+inline void face_metric_adtl3(const M& m, double t, int axis, const Pt<real>& p, real* fwd, real* inv, real* cons) {
+  real G[9], Ghat[9];
   Cache3<M, 2> c{m, t};
   c.face(axis, p, G, Ghat);
-  Pt<double> pf = p;
+  Pt<real> pf = p;
   pf[axis] += 0.5;  // _face_center_3d (:3271-3283): the cell centre moved half a cell along the face axis
-  const Vals<double, 9> F = ad_jacobian<3>(m, t, pf);
-  double Fm[9], Gm[9];
+  const Vals<real, 9> F = ad_jacobian<3>(m, t, pf);
+  real Fm[9], Gm[9];
   for (int k = 0; k < 9; ++k) Fm[k] = F.e[k];
   invN<3>(Fm, Gm);
-  const double J = detN<3>(Fm);
+  const real J = detN<3>(Fm);
   for (int k = 0; k < 9; ++k) {
     fwd[k] = Fm[k];
     inv[k] = Gm[k];
@@ -499,14 +499,14 @@ struct DiscreteMap {
 
   // discrete_grid.jl:113-142  forward Jacobian = Interpolations.gradient(etp, ξ…):
   // gradient of the interpolant at the CLAMPED point (Line() extrapolate_gradient = g).
-  void forward_jacobian(double /*t*/, const Pt<double>& x, double* F) const {
-    Pt<double> xs = x;
+  void forward_jacobian(double /*t*/, const Pt<real>& x, real* F) const {
+    Pt<real> xs = x;
     for (int d = 0; d < N; ++d) {
-      if (xs[d] > double(n[d])) xs[d] = double(n[d]);
+      if (xs[d] > real(n[d])) xs[d] = real(n[d]);
       else if (xs[d] < 1.0) xs[d] = 1.0;
     }
     for (int c = 0; c < N; ++c) {
-      double val, g[3];
+      real val, g[3];
       itp_value_gradient(a[c], xs, val, g);
       for (int d = 0; d < N; ++d) F[c + N * d] = g[d];
     }
@@ -558,7 +558,7 @@ struct TermMap {
     return acc;
   }
   // MappedGrid keeps the AD Jacobian as forward.jacobian (metrics.jl:200-214)
-  void forward_jacobian(double t, const Pt<double>& p, double* F) const {
+  void forward_jacobian(double t, const Pt<real>& p, real* F) const {
     if (N == 1) { auto J = ad_jacobian<1>(*this, t, p); F[0] = J.e[0]; }
     else if (N == 2) { auto J = ad_jacobian<2>(*this, t, p); for (int k = 0; k < 4; ++k) F[k] = J.e[k]; }
     else { auto J = ad_jacobian<3>(*this, t, p); for (int k = 0; k < 9; ++k) F[k] = J.e[k]; }

@@ -14,7 +14,11 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIB = {}
+# base real type of the restatement: "f64" = liboracle.so (the reference's Float64 arithmetic), "ld" = long double
+# (64-bit significand), "quad" = __float128.  The extended builds take and return float64 arrays; tests use them as
+# truth for the last-digits question "which FP64 side owns the difference".
+_LIBNAME = {"f64": "liboracle.so", "ld": "liboracle_ld.so", "quad": "liboracle_q.so"}
 
 SCHEMES = {"endpoint": 0, "gradient": 1, "curvature": 2, "adtl": 3}
 
@@ -23,15 +27,16 @@ def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        path = os.path.join(_HERE, "liboracle.so")
+def lib(precision="f64"):
+    if precision not in _LIB:
+        path = os.path.join(_HERE, _LIBNAME[precision])
         if not os.path.exists(path):
             build()
-        _LIB = ctypes.CDLL(path)
-        _LIB.cgo_num_threads.restype = ctypes.c_int
-    return _LIB
+        L = ctypes.CDLL(path)
+        L.cgo_num_threads.restype = ctypes.c_int
+        L.cgo_real_digits.restype = ctypes.c_int
+        _LIB[precision] = L
+    return _LIB[precision]
 
 
 def num_threads():
@@ -73,7 +78,7 @@ def _alloc(dim, nout, what):
     return out
 
 
-def discrete_eval(nodes, nhalo, scheme="curvature", sample=None, what=3, halo_coords_included=False):
+def discrete_eval(nodes, nhalo, scheme="curvature", sample=None, what=3, halo_coords_included=False, precision="f64"):
     """DiscreteGrid(x[,y[,z]], nhalo; halo_coords_included, conserved_metric_scheme).
 
     Returns dict of packed arrays: cell_fwd/cell_inv [ncell, N*N+1],
@@ -91,7 +96,7 @@ def discrete_eval(nodes, nhalo, scheme="curvature", sample=None, what=3, halo_co
     nout = ntot if samp is None else len(samp)
     out = _alloc(dim, nout, what)
     xyz = flat + [None] * (3 - dim)
-    rc = lib().cgo_discrete_eval(
+    rc = lib(precision).cgo_discrete_eval(
         ctypes.c_int(dim), _dp(xyz[0]), _dp(xyz[1]), _dp(xyz[2]), _ip(nn), ctypes.c_int(nhalo),
         ctypes.c_int(_scheme(scheme)), ctypes.c_int64(0 if samp is None else len(samp)), _ip(samp),
         ctypes.c_int(what), _dp(out["cell_fwd"]), _dp(out["cell_inv"]), _dp(out["face_fwd"]),
@@ -102,7 +107,8 @@ def discrete_eval(nodes, nhalo, scheme="curvature", sample=None, what=3, halo_co
     return out
 
 
-def mapped_eval(terms, t, celldims, nhalo, scheme="curvature", sample=None, what=3, global_offset=None):
+def mapped_eval(terms, t, celldims, nhalo, scheme="curvature", sample=None, what=3, global_offset=None,
+                precision="f64"):
     """MappedGrid(x[,y[,z]], params, celldims, nhalo) with a term-list mapping."""
     dim = len(celldims)
     tab = np.ascontiguousarray(np.asarray(terms, dtype=np.float64).reshape(-1, 15))
@@ -115,7 +121,7 @@ def mapped_eval(terms, t, celldims, nhalo, scheme="curvature", sample=None, what
     samp = None if sample is None else np.ascontiguousarray(sample, dtype=np.int64)
     nout = ntot if samp is None else len(samp)
     out = _alloc(dim, nout, what)
-    rc = lib().cgo_mapped_eval(
+    rc = lib(precision).cgo_mapped_eval(
         ctypes.c_int(dim), ctypes.c_int(tab.shape[0]), _dp(tab), ctypes.c_double(t), _ip(nc),
         ctypes.c_int(nhalo), _ip(go), ctypes.c_int(_scheme(scheme)),
         ctypes.c_int64(0 if samp is None else len(samp)), _ip(samp), ctypes.c_int(what),

@@ -40,22 +40,31 @@ void eval_cells(const M& m, double t, const int64_t* nfull, int nhalo, const int
       idx[d] = r % nfull[d];
       r /= nfull[d];
     }
-    Pt<double> p = {0.0, 0.0, 0.0};
-    for (int d = 0; d < N; ++d) p[d] = double(idx[d] + 1 + goff[d] - nhalo) + 0.5;
-    if (what & 1) cell_metric<N>(m, t, p, cell_fwd + s * KM, cell_inv + s * KM);
+    Pt<real> p = {0.0, 0.0, 0.0};
+    for (int d = 0; d < N; ++d) p[d] = real(idx[d] + 1 + goff[d] - nhalo) + 0.5;
+    // results are computed in `real` (double, or the extended type of liboracle_ld / liboracle_q) and rounded to
+    // double on store
+    real bf[N * N + 1], bi[N * N + 1], bc[N * N];
+    if (what & 1) {
+      cell_metric<N>(m, t, p, bf, bi);
+      for (int k = 0; k < KM; ++k) {
+        cell_fwd[s * KM + k] = (double)bf[k];
+        cell_inv[s * KM + k] = (double)bi[k];
+      }
+    }
     if (what & 2) {
       for (int ax = 0; ax < N; ++ax) {
         if constexpr (SCH == 3) {  // ADThomasLombardMetric (3-D only; 1-D / 2-D fall back to Curvature, metrics.jl:1669-1673)
-          if constexpr (N == 3)
-            face_metric_adtl3(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
-                              face_cons + (ax * nout + s) * KC);
-          else
-            face_metric<N, 2>(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
-                              face_cons + (ax * nout + s) * KC);
+          if constexpr (N == 3) face_metric_adtl3(m, t, ax, p, bf, bi, bc);
+          else face_metric<N, 2>(m, t, ax, p, bf, bi, bc);
         } else {
-          face_metric<N, SCH>(m, t, ax, p, face_fwd + (ax * nout + s) * KM, face_inv + (ax * nout + s) * KM,
-                              face_cons + (ax * nout + s) * KC);
+          face_metric<N, SCH>(m, t, ax, p, bf, bi, bc);
         }
+        for (int k = 0; k < KM; ++k) {
+          face_fwd[(ax * nout + s) * KM + k] = (double)bf[k];
+          face_inv[(ax * nout + s) * KM + k] = (double)bi[k];
+        }
+        for (int k = 0; k < KC; ++k) face_cons[(ax * nout + s) * KC + k] = (double)bc[k];
       }
     }
   }
@@ -90,13 +99,13 @@ void eval_coords(const M& m, int dim, double t, const int64_t* ncell_full, int n
       idx[d] = r % np[d];
       r /= np[d];
     }
-    Pt<double> p = {0.0, 0.0, 0.0};
+    Pt<real> p = {0.0, 0.0, 0.0};
     for (int d = 0; d < dim; ++d) {
-      p[d] = double(idx[d] + 1 + goff[d] - nhalo);
+      p[d] = real(idx[d] + 1 + goff[d] - nhalo);
       if (which >= 1) p[d] += 0.5;
       if (which >= 2 && d == which - 2) p[d] += 0.5;
     }
-    for (int c = 0; c < dim; ++c) out[c * ntot + lin] = m.template coord<double>(c, t, p);
+    for (int c = 0; c < dim; ++c) out[c * ntot + lin] = (double)m.template coord<real>(c, t, p);
   }
 }
 
@@ -121,6 +130,16 @@ TermMap make_termmap(int dim, int nterms, const double* table, std::vector<Term>
 extern "C" {
 
 int cgo_num_threads(void) { return omp_get_max_threads(); }
+// bits of the significand of the base real type: 53 (liboracle.so), 64 (liboracle_ld.so), 113 (liboracle_q.so)
+int cgo_real_digits(void) {
+#if defined(CGO_REAL_IS_QUAD)
+  return 113;
+#elif defined(CGO_REAL_IS_LD)
+  return 64;
+#else
+  return 53;
+#endif
+}
 void cgo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 // DiscreteGrid(x[,y[,z]], nhalo): x,y,z are INTERIOR node arrays (halo already

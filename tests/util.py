@@ -87,3 +87,49 @@ def mild_nodes(shape, seed=0, amp=0.08, noise=0.01):
         q = q + noise * rng.standard_normal(shape)
         out.append(np.asfortranarray(q))
     return out
+
+
+def sampled_outputs(cg, grid, sample):
+    """FULL-profile outputs of the cells `sample` (linear Fortran indices of the window), gathered on the device."""
+    import torch
+    idx = torch.from_numpy(np.ascontiguousarray(sample)).to(f"cuda:{grid.device}")
+    N = grid.dim
+    K = N * N + 1
+    cm, fm = cg.cell_metrics(grid), cg.face_metrics(grid)
+    pick = lambda t, k: t.reshape(-1, k)[idx].cpu().numpy()
+    return {"cell_fwd": pick(cm.forward, K), "cell_inv": pick(cm.inverse, K),
+            "face_fwd": np.stack([pick(fm[a].forward, K) for a in range(N)]),
+            "face_inv": np.stack([pick(fm[a].inverse, K) for a in range(N)]),
+            "face_cons": np.stack([pick(fm[a].conserved, N * N) for a in range(N)])}
+
+
+def roundoff_report(oracle, got, nodes, nhalo, scheme, sample=None, precision="ld"):
+    """Three-way comparison per output array: CUDA (`got`) and the FP64 oracle, each against the same closure graph
+    evaluated in extended precision ("truth"), and against each other.  Returns {key: {gpu_vs_truth,
+    oracle64_vs_truth, gpu_vs_oracle64}} (metric_err: relative to the largest entry of the same matrix)."""
+    truth = oracle.discrete_eval(nodes, nhalo, scheme, sample=sample, precision=precision)
+    o64 = oracle.discrete_eval(nodes, nhalo, scheme, sample=sample)
+    rep = {}
+    for k in KEYS:
+        hj = k != "face_cons"
+        rep[k] = {"gpu_vs_truth": metric_err(got[k], truth[k], hj), "oracle64_vs_truth": metric_err(o64[k], truth[k], hj),
+                  "gpu_vs_oracle64": metric_err(got[k], o64[k], hj)}
+    return rep
+
+
+def gcl_max_numpy(cons, nfull, nhalo, dtype=np.float64):
+    """gcl.jl:20-117 in numpy with the accumulation order and type of k_gcl: per column c,
+    acc = sum over axes (in order) of (C_ax[I][ax, c] - C_ax[I - e_ax][ax, c]) over cell.domain; max |acc|.
+    cons: [N, ncell (Fortran order), N*N]."""
+    N = len(nfull)
+    dom = domain_indices(nfull, nhalo)
+    strides = [int(np.prod(nfull[:d])) for d in range(N)]
+    c = np.asarray(cons).astype(dtype)
+    out = np.zeros(N)
+    for col in range(N):
+        acc = np.zeros(len(dom), dtype=dtype)
+        for ax in range(N):
+            e = ax + N * col
+            acc = (acc + (c[ax][dom, e] - c[ax][dom - strides[ax], e])).astype(dtype)
+        out[col] = float(np.abs(acc).max())
+    return out
