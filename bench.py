@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE configs (other_configs)")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the slab axis keeps N cells in total (N^3 split over the GPUs) instead of "
                          "one slab per GPU; the JSON line says \"scaling\": \"strong\"")
@@ -199,11 +200,18 @@ def measured_peak_gbs():
 
 
 # ---------------------------------------------------------------------------
-def cpu_oracle_rate(spec, nodes_host_global, seconds, nthreads=None):
-    """Oracle (CPU restatement of the reference) on a bounded random sample of cell.full."""
+def _host_threads():
+    """All host threads, whatever OMP_NUM_THREADS says (torchrun sets it to 1, which shrank the CPU arm 29x in r1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_oracle_rate(spec, nodes_host_global, seconds):
+    """Oracle (CPU restatement of the reference) on a bounded random sample of cell.full, all host threads."""
     from oracle import oracle as O
-    if nthreads:
-        O.set_num_threads(nthreads)
+    O.set_num_threads(_host_threads())
     cores = O.num_threads()
     dim = 3 if spec["kind"] == "3d" else 2
     nodes = nodes_host_global
@@ -221,44 +229,50 @@ def cpu_oracle_rate(spec, nodes_host_global, seconds, nthreads=None):
     t0 = time.perf_counter()
     O.discrete_eval(nodes, spec["nhalo"], spec["scheme"], sample=sample)
     dt = time.perf_counter() - t0
-    return n / dt / 1e6, cores, f"{n} random cells of cell.full ({dim}-D, {spec['scheme']}), {dt:.1f} s wall"
+    return n / dt / 1e6, cores, f"{n} random cells of cell.full ({dim}-D, {spec['scheme']}), {dt:.1f} s wall", ntot
 
 
-def global_nodes_for_cpu(spec, nranks):
-    """Host node arrays of the whole workload as numpy [i,j,k]-indexed views (for the oracle)."""
+def global_nodes_for_cpu(spec):
+    """Host node arrays of the one-GPU workload as numpy [i,j,k]-indexed views (for the oracle)."""
     n = spec["n"]
     if spec.get("gen") == "sph":
         ns = spec["nslab"]
-        arrs = sph_slab_3d(n + 1, n + 1, ns * nranks + 1, 0, ns * nranks + 1)
+        arrs = sph_slab_3d(n + 1, n + 1, ns + 1, 0, ns + 1)
         return [a.transpose(2, 1, 0) for a in arrs]
     if spec["kind"] == "3d":
-        arrs = wavy_slab_3d(n + 1, n + 1, n * nranks + 1, 0, n * nranks + 1)
+        arrs = wavy_slab_3d(n + 1, n + 1, n + 1, 0, n + 1)
         return [a.transpose(2, 1, 0) for a in arrs]
-    arrs = wavy_slab_2d(n + 1, n * nranks + 1, 0, n * nranks + 1)
+    arrs = wavy_slab_2d(n + 1, n + 1, 0, n + 1)
     return [a.transpose(1, 0) for a in arrs]
 
 
 def run_reference(args, spec):
+    """The reference arm: the CPU oracle ("port": the Julia package cannot run here) on ALL host threads over a bounded
+    sample of the one-GPU workload.  Under torchrun rank 0 alone runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample per step so that K steps + W warm-ups end within minutes
-    nodes = global_nodes_for_cpu(spec, 1 if spec["kind"] == "3d" and spec["n"] > 256 else 1)
+    if spec["kind"] == "m3d":
+        spec = workload_spec("3d%d" % spec["n"], spec["scheme"])
+    nodes = global_nodes_for_cpu(spec)
     per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
-    vals, sample_desc, cores = [], "", 1
+    vals, sample_desc, cores, ntot = [], "", 1, 1
     for s in range(args.warmup + args.steps):
-        v, cores, sample_desc = cpu_oracle_rate(spec, nodes, per_step)
+        v, cores, sample_desc, ntot = cpu_oracle_rate(spec, nodes, per_step)
         if s >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": "metric-eval Mcells/s (cell+face, FP64)", "value": value, "unit": "Mcells/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        # one step of the workload = every cell of cell.full: extrapolated from the sampled rate
+        "ms_per_step": ntot / (value * 1e6) * 1e3, "sample_seconds_per_step": per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["desc"], "scheme": spec["scheme"], "profile": "full",
                    "note": "CPU oracle = C++ restatement of the reference algorithm (nested forward-mode AD through "
-                           "the interpolant); the Julia package cannot run here (no Julia toolchain)"},
+                           "the interpolant); the Julia package cannot run here (no Julia toolchain).  value = sampled "
+                           "cells per second on all host threads; ms_per_step = the whole step extrapolated from it"},
         "cpu_baseline": {"value": value, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -267,33 +281,150 @@ def run_reference(args, spec):
 
 
 # ---------------------------------------------------------------------------
-def run_ours(args, spec):
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """Process-wide state of one bench run: ranks, device, the NCCL communicator of the C ABI."""
 
-    import curvigrid_b200 as cg
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device(f"cuda:{self.local_rank}")
+        self.comm = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+            import curvigrid_b200 as cg
+            # ncclComm_t owned by libcurvigrid_cuda.so: the node-plane exchange, the seam plane of the GCL functional and
+            # its max-reduction are C-ABI calls; torch.distributed only carries the 128-byte id and the bench's timing
+            self.comm = cg.slabs.NcclComm(self.rank, self.world, self.local_rank)
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device(f"cuda:{local_rank}")
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
+    def allmax(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum_int(self, x):
+        if self.world == 1:
+            return int(x)
+        t = self.torch.tensor([int(x)], device=self.dev, dtype=self.torch.int64)
+        self.dist.all_reduce(t)
+        return int(t.item())
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def parity_block(cg, ctx, grid, host, plan, spec, profile, dtype, nsamples=64):
+    """Sampled cells of this rank's slab against the oracle, inside the bench run: the CUDA values
+    against the FP64 oracle (the reference's arithmetic) and both against the same closure graph in long double
+    ("truth").  The oracle's grid is the rank's own node planes; sampled cells keep two planes away from slab seams so
+    that the sub-grid's extrapolated halo is never what they read.  Max over ranks."""
+    from oracle import oracle as O
+    torch = ctx.torch
+    O.set_num_threads(_host_threads())
+    dim, h = grid.dim, spec["nhalo"]
+    lo, hi = plan.required
+    k0, k1 = plan.cells
+    nw = list(grid.window_cells)
+    rng = np.random.default_rng(1000 + ctx.rank)
+    idx = [rng.integers(0, nw[d], nsamples) for d in range(dim - 1)]
+    s_lo = 0 if ctx.rank == 0 else 2
+    s_hi = nw[dim - 1] if ctx.rank == ctx.world - 1 else nw[dim - 1] - 3
+    ks = rng.integers(s_lo, max(s_lo + 1, s_hi), nsamples)                     # window-local plane
+    perm = list(range(dim - 1, -1, -1))
+    sub_nodes = [np.asarray(a).transpose(*perm).astype(np.float64) for a in host]   # [i,j,k] views of the rank's planes
+    nf = [nw[d] for d in range(dim - 1)] + [(hi - lo) - 1 + 2 * h]
+    ko = ks + k0 - lo                                                          # the oracle grid's full cell plane
+    lin_o = np.zeros(nsamples, dtype=np.int64)
+    lin_w = np.zeros(nsamples, dtype=np.int64)
+    so = sw = 1
+    for d in range(dim):
+        c = idx[d] if d < dim - 1 else None
+        lin_o += (c if c is not None else ko) * so
+        lin_w += (c if c is not None else ks) * sw
+        so *= nf[d]
+        sw *= nw[d]
+    order = np.argsort(lin_o)
+    lin_o, lin_w = lin_o[order], lin_w[order]
+    o64 = O.discrete_eval(sub_nodes, h, spec["scheme"], sample=lin_o)
+    truth = O.discrete_eval(sub_nodes, h, spec["scheme"], sample=lin_o, precision="ld") if dtype == "f64" else o64
+    N = dim
+    widx = torch.from_numpy(lin_w).to(ctx.dev)
+
+    def rel(a, b, has_j):
+        K = a.shape[-1] - (1 if has_j else 0)
+        sc = np.abs(b[..., :K]).max(axis=-1, keepdims=True)
+        sc = np.where(sc == 0, 1.0, sc)
+        e = float((np.abs(a[..., :K] - b[..., :K]) / sc).max())
+        if has_j:
+            e = max(e, float((np.abs(a[..., K] - b[..., K]) / np.abs(b[..., K])).max()))
+        return e
+
+    out = {}
+    if profile == "full":
+        cm, fm = cg.cell_metrics(grid), cg.face_metrics(grid)
+        pick = lambda t, k: t.reshape(-1, k)[widx].double().cpu().numpy()
+        got = {"cell_fwd": pick(cm.forward, N * N + 1), "cell_inv": pick(cm.inverse, N * N + 1),
+               "face_fwd": np.stack([pick(fm[a].forward, N * N + 1) for a in range(N)]),
+               "face_inv": np.stack([pick(fm[a].inverse, N * N + 1) for a in range(N)]),
+               "face_cons": np.stack([pick(fm[a].conserved, N * N) for a in range(N)])}
+        jac = ("cell_fwd", "cell_inv", "face_fwd", "face_inv")
+        out["jacobians_vs_truth"] = max(rel(got[k], truth[k], True) for k in jac)
+        out["jacobians_vs_oracle64"] = max(rel(got[k], o64[k], True) for k in jac)
+        out["conserved_vs_truth"] = rel(got["face_cons"], truth["face_cons"], False)
+        out["conserved_vs_oracle64"] = rel(got["face_cons"], o64["face_cons"], False)
+        out["oracle64_conserved_vs_truth"] = rel(o64["face_cons"], truth["face_cons"], False)
+    else:
+        J = cg.cell_metrics(grid).reshape(-1)[widx].double().cpu().numpy()
+        out["jacobians_vs_truth"] = float(np.abs(J / truth["cell_fwd"][:, N * N] - 1).max())
+        out["jacobians_vs_oracle64"] = float(np.abs(J / o64["cell_fwd"][:, N * N] - 1).max())
+        ev = eo = et = 0.0
+        for a in range(N):
+            g_ = cg.face_metrics(grid)[a].reshape(-1, N)[widx].double().cpu().numpy()
+            t_ = np.stack([truth["face_cons"][a][:, a + N * c] for c in range(N)], axis=1)
+            o_ = np.stack([o64["face_cons"][a][:, a + N * c] for c in range(N)], axis=1)
+            sc = np.abs(truth["face_cons"][a]).max(axis=1, keepdims=True)
+            ev, eo, et = max(ev, float((np.abs(g_ - t_) / sc).max())), max(eo, float((np.abs(g_ - o_) / sc).max())), \
+                max(et, float((np.abs(o_ - t_) / sc).max()))
+        out["conserved_vs_truth"], out["conserved_vs_oracle64"], out["oracle64_conserved_vs_truth"] = ev, eo, et
+    out = {k: ctx.allmax(v) for k, v in out.items()}
+    # `max_rel_err`: CUDA against the exact value of the reference's algorithm on the same inputs (long-double truth)
+    out["max_rel_err"] = max(out["jacobians_vs_truth"], out["conserved_vs_truth"])
+    out["cells"] = nsamples * ctx.world
+    out["truth"] = "oracle closure graph in long double" if dtype == "f64" else "FP64 oracle on the FP32-rounded nodes"
+    return out
+
+
+def measure_discrete(cg, ctx, args, spec, *, profile, dtype, steps, warmup, strong=False, do_e2e=True, do_cpu=True,
+                     do_parity=True, workload_name=""):
+    """One workload on the ranks of this run; returns the JSON line as a dict (rank 0 prints it or nests it)."""
+    torch, lib = ctx.torch, cg._lib.lib()
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
     n, h = spec["n"], spec["nhalo"]
     dim = 3 if spec["kind"] == "3d" else 2
-    T = np.float64 if args.dtype == "f64" else np.float32
-    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    T = np.float64 if dtype == "f64" else np.float32
     nslab = spec.get("nslab", n)
     ncell_slab = nslab * world  # weak scaling: the grid grows along the slab axis
-    if args.strong:
-        ncell_slab = n          # strong scaling: n cells along the slab axis in total, split over the ranks
-        nslab = n // world
+    if strong:
+        ncell_slab = nslab      # strong scaling: the one-GPU grid split over the ranks
     plan = cg.slabs.make_plan(rank, world, ncell_slab, h)
     lo, hi = plan.required
+    olo, ohi = plan.owned
     if dim == 3:
         gen = sph_slab_3d if spec.get("gen") == "sph" else wavy_slab_3d
         host = gen(n + 1, n + 1, ncell_slab + 1, lo, hi)
@@ -301,187 +432,164 @@ def run_ours(args, spec):
     else:
         host = wavy_slab_2d(n + 1, ncell_slab + 1, lo, hi)
         inplane = (n,)
-    host_pinned = [torch.from_numpy(a.astype(T)).pin_memory() for a in host]
-    # truth for non-owned planes comes from their owners; blank them so the exchange is real
-    olo, ohi = plan.owned
-    dev_nodes = [t.to(dev, non_blocking=True) for t in host_pinned]
+    host = [np.ascontiguousarray(a, dtype=T) for a in host]
     if world > 1:
-        for t in dev_nodes:
-            t[:olo - lo].zero_()
-            t[ohi - lo:].zero_()
+        # the truth for the non-owned planes comes from their owners through the exchange: blank them on this rank
+        for a in host:
+            a[:olo - lo] = 0
+            a[ohi - lo:] = 0
+    perm = tuple(range(dim - 1, -1, -1))
     kw = cg.slabs.slab_grid_kwargs(plan, inplane, h) if world > 1 else {}
-    grid = cg.DiscreteGrid(*dev_nodes, h, T=T, conserved_metric_scheme=spec["scheme"], cache_mode="lazy",
-                           profile=args.profile, **kw)
+    # built from HOST arrays ([i,j,k]-indexed views of the [k,j,i] memory): the library owns the device node buffer
+    grid = cg.DiscreteGrid(*[a.transpose(*perm) for a in host], h, T=T, conserved_metric_scheme=spec["scheme"],
+                           cache_mode="lazy", profile=profile, **kw)
+    host_pinned = [torch.from_numpy(a).pin_memory() for a in host] if do_e2e else None
     grid.set_kernel(args.kernel)
-    lib = cg._lib.lib()
-    import ctypes
+    comm = ctx.comm
     cells_local = int(np.prod(grid.window_cells))
-    cells_total = cells_local
-    if world > 1:
-        tcount = torch.tensor([cells_local], device=dev, dtype=torch.int64)
-        dist.all_reduce(tcount)
-        cells_total = int(tcount.item())
-
+    cells_total = ctx.allsum_int(cells_local)
     overlap = world > 1 and dim == 3 and args.kernel == 1
+    pipelined = dim == 3 and args.kernel == 1
+    st = grid._stream
 
-    def step_plain():
-        if world > 1:
-            cg.slabs.exchange_node_planes(plan, dev_nodes)
-        cg._lib.check(lib.cg_grid_nodes_changed(grid._h, grid._stream()))
+    def exchange_then_eval():
+        if world > 1:  # C ABI: grouped ncclSend / ncclRecv into the node buffer, then the stream waits
+            cg._lib.check(lib.cg_halo_exchange_begin(grid._h, comm._h, rank, world, comm.bounds(plan), st()))
+            cg._lib.check(lib.cg_halo_exchange_end(grid._h, st()))
+        cg._lib.check(lib.cg_grid_nodes_changed(grid._h, st()))
         cg.refresh_metrics(grid)
 
     def step_resident():
         if overlap:
-            # exchange posted first; planes that depend on owned nodes only are padded + evaluated while the
-            # neighbour planes travel over NVLink; the 1 (low) / 3 (high) boundary planes follow the wait
-            cg.slabs.step_overlapped(grid, plan, dev_nodes)
+            # cg_grid_step_overlapped: exchange posted first; planes that depend on owned nodes only are padded +
+            # evaluated while the neighbour planes travel over NVLink; the boundary planes follow the wait
+            cg.slabs.step_overlapped_nccl(grid, plan, comm)
         else:
-            step_plain()
+            exchange_then_eval()
 
-    pipelined = world == 1 and dim == 3 and args.kernel == 1
+    def gcl_all():
+        return cg.slabs.gcl_dist(grid, comm) if world > 1 else cg.gcl(grid)
 
     def step_e2e():
         if pipelined:
-            # cg_grid_update_from_host: node planes in pieces, the H2D copy of a piece overlaps the kernels of the
-            # piece before (pinned host arrays -> padded nodes -> metrics)
-            grid.update_from_host(*host_pinned, nchunks=args.h2d_chunks)
+            # cg_grid_update_from_host[_dist]: the owned node planes go to the device in pieces on a copy stream; the
+            # planes the neighbours wait for first, then the NCCL exchange; each piece that lands releases the padded
+            # planes and cell planes it completes
+            grid.update_from_host(*host_pinned, nchunks=args.h2d_chunks, comm=comm, plan=plan)
         else:
-            for d, hsrc in zip(dev_nodes, host_pinned):
-                d[olo - lo:ohi - lo].copy_(hsrc[olo - lo:ohi - lo], non_blocking=True)
-            step_resident()
-        res = cg.gcl(grid)  # device reduction + D2H of the residuals (synchronises)
-        return res
+            grid.set_nodes(*host_pinned)
+            if world > 1:
+                exchange_then_eval()
+            else:
+                cg.refresh_metrics(grid)
+        return gcl_all()  # device reduction (+ seam plane and max over ranks) + D2H of the residuals (synchronises)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
+    def timed(fn, steps_):
+        ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        for _ in range(steps_):
             fn()
         e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            tm = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ms = float(tm.item())
-        return ms
+        ctx.barrier()
+        return ctx.allmax(e0.elapsed_time(e1))
 
-    for _ in range(max(args.warmup, 3)):
+    exchange_then_eval()  # the first evaluation fills the non-owned planes
+    for _ in range(max(warmup, 3)):
         step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank)
     sampler.start()
     launches0 = lib.cg_launch_count()
-    kernel_ms = []
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-        kernel_ms.append(None)
-    e1.record()
-    barrier()
+    total_ms = timed(step_resident, steps)
     launches = lib.cg_launch_count() - launches0
-    total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    if world > 1:
-        tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        total_ms = float(tm.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = total_ms / steps
     value = cells_total / (ms_per_step * 1e-3) / 1e6
 
-    # dominant kernel: the fused metric kernel, timed with CUDA events on its own stream
+    # dominant kernel(s): one cg_grid_eval over the whole slab, timed with CUDA events on its own stream
     kms = []
-    for _ in range(min(args.steps, 5)):
-        step_plain()  # one cg_grid_eval over the whole slab (the overlapped step splits it into plane ranges)
+    for _ in range(min(steps, 5)):
+        exchange_then_eval()
         kms.append(grid.last_eval_ms())
     k_ms = float(np.mean(kms))
-    bpc = BYTES_PER_CELL[(spec["kind"], args.profile)] * (1.0 if args.dtype == "f64" else 0.5)
+    bpc = BYTES_PER_CELL[(spec["kind"], profile)] * (1.0 if dtype == "f64" else 0.5)
     peak, peak_src = measured_peak_gbs()
     achieved = bpc * cells_local / (k_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # DRAM bytes of the metric kernels from the committed `ncu --set full` capture of this workload
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic_3d512.json")) as f:
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of the metric kernels: a CITATION of the committed `ncu --set full` capture, not measured in this run
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic_3d512.json")
+        with open(tp) as f:
             tj = json.load(f)
-        if (args.workload, args.profile, args.dtype, spec["scheme"], args.kernel) == ("3d512", "full", "f64", "curvature", 1):
+        if (workload_name, profile, dtype, spec["scheme"], args.kernel, world) == ("3d512", "full", "f64", "curvature", 1, 1):
             traffic = tj["total"]
+            traffic_src = "ncu --set full capture committed as profiles/ncu_traffic_3d512.json (%s)" % tj.get("capture", "round 1")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes": bpc * cells_local,
-                "kernel": ("k_face_xi + k_face_zeta<SWAP> (eta) + k_face_zeta (one cell+face evaluation = 3 launches)"
-                           if dim == 3 and args.kernel == 1 else ("metrics3d" if dim == 3 else "metrics2d")),
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": bpc * cells_local,
+                "kernel": (cg.kernel_names_3d() if dim == 3 and args.kernel == 1 else ("metrics3d" if dim == 3 else "k_metrics2d_staged")),
                 "kernel_ms": k_ms,
                 "algorithmic_bytes_per_cell": bpc, "peak_source": f"MEASURED_PEAKS.json ({peak_src}, copy burst)",
                 # also against the nominal ~8 TB/s of the north star
                 "frac_of_nominal_8TBs": achieved / 8000.0}
-    if dim == 3 and args.kernel == 1 and args.profile == "full" and args.dtype == "f64" and spec["scheme"] == "curvature":
-        # second ceiling: FP64 instructions of the three marching kernels per cell (SASS of the loop
-        # bodies: xi 736 per 29 cells, eta / zeta 697 per 31) against the measured FP64 issue rate (59 per clock and SM)
-        ipc = 32.0 * (736.0 / 29.0 + 2.0 * 697.0 / 31.0)  # thread instructions: a warp instruction occupies 32 lanes
-        rate = ipc * cells_local / (k_ms * 1e-3)
-        roofline["fp64"] = {"instr_per_cell": ipc, "achieved_Tinstr_s": rate / 1e12,
-                            "peak_Tinstr_s": 59.0 * 148 * 1.965e9 / 1e12,
-                            "frac": rate / (59.0 * 148 * 1.965e9), "note": "peak at the maximum SM clock"}
 
     e2e = None
-    if not args.no_e2e:
+    if do_e2e:
         for _ in range(2):
             step_e2e()
-        ms = timed(step_e2e, args.steps) / args.steps
-        h2d = sum(int(t[olo - lo:ohi - lo].numel() * t.element_size()) for t in host_pinned)
+        ms = timed(step_e2e, steps) / steps
+        h2d = sum(int(t[olo - lo:ohi - lo].numel() * t.element_size()) for t in host_pinned)  # owned planes only
         e2e = {"value": cells_total / (ms * 1e-3) / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": 8 * dim, "ms_per_step": ms,
-               "note": ("pinned host nodes -> H2D in %d pieces overlapped with pad + metrics of the piece before "
-                        "(cg_grid_update_from_host)" % args.h2d_chunks if pipelined else
-                        "pinned host nodes -> H2D -> pad -> metrics") + " -> device GCL max -> D2H; metric arrays "
-                       "stay on the device like a KernelAbstractions GPU backend's storage"}
+               "d2h_bytes_per_step": 8 * dim, "ms_per_step": ms, "h2d_GBs_per_rank_if_copy_bound": h2d / (ms * 1e-3) / 1e9,
+               "note": ("pinned host nodes -> H2D of the owned planes in %d pieces (boundary planes first, then the NCCL "
+                        "exchange), each piece overlapped with pad + metrics of the planes it completes "
+                        "(cg_grid_update_from_host%s)" % (args.h2d_chunks, "_dist" if world > 1 else "") if pipelined else
+                        "pinned host nodes -> H2D -> pad -> metrics") + " -> device GCL max (seam planes and max over "
+                       "ranks inside the C ABI) -> D2H of 3 doubles; the metric arrays stay on the device like a "
+                       "KernelAbstractions GPU backend's storage"}
+
+    parity = None
+    if do_parity:
+        step_resident()
+        parity = parity_block(cg, ctx, grid, host, plan, spec, profile, dtype)
+        parity["gcl_max"] = max(gcl_all())
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and do_cpu:
         nodes_cpu = [a.transpose(*reversed(range(dim))) for a in host]  # [i,j,k] views of the full node arrays
-        v, cores, desc = cpu_oracle_rate(spec, nodes_cpu, args.cpu_seconds)
+        v, cores, desc, _ = cpu_oracle_rate(spec, nodes_cpu, args.cpu_seconds)
         cpu = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": "port", "sample": desc}
 
-    if rank == 0:
-        line = {
-            "metric": "metric-eval Mcells/s (cell+face, FP64)" if args.dtype == "f64" else "metric-eval Mcells/s (cell+face, FP32)",
-            "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": spec["desc"] + (f"; k-slabs over {world} GPUs, grid {n}x{n}x{ncell_slab}" if world > 1 and dim == 3 else ""),
-                       "scheme": spec["scheme"], "profile": args.profile, "cells_written": cells_total,
-                       "kernel": "tiled" if args.kernel == 1 else "gather",
-                       "l2": "inputs+outputs per step far exceed the 126 MB L2 (no flush needed)",
-                       "parallelism": f"slab{world}" if world > 1 else "single",
-                       "halo_exchange": ("NCCL node planes, overlapped with interior planes" if overlap else
-                                         ("NCCL node planes" if world > 1 else "none"))},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    line = {
+        "metric": "metric-eval Mcells/s (cell+face, FP64)" if dtype == "f64" else "metric-eval Mcells/s (cell+face, FP32)",
+        "value": value, "unit": "Mcells/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic",
+        "config": {"workload": spec["desc"] + (f"; k-slabs over {world} GPUs, grid {n}x{n}x{ncell_slab}" if world > 1 and dim == 3 else ""),
+                   "scheme": spec["scheme"], "profile": profile, "cells_written": cells_total,
+                   "kernel": "tiled" if args.kernel == 1 else "gather",
+                   "l2": "inputs+outputs per step far exceed the 126 MB L2 (no flush needed)",
+                   "parallelism": f"slab{world}" if world > 1 else "single",
+                   "halo_exchange": ("NCCL node planes inside the C ABI (cg_grid_step_overlapped), overlapped with interior planes"
+                                     if overlap else ("NCCL node planes (cg_halo_exchange_begin/end)" if world > 1 else "none"))},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    grid.close()
+    del grid, host_pinned, host
+    torch.cuda.empty_cache()
+    return line
 
 
-def run_mapped(args, spec):
-    """BASELINE config 4: MappedGrid, update!(grid, t_k) + refresh of both metric caches every step (1 GPU)."""
-    import torch
-
-    import curvigrid_b200 as cg
-
-    torch.cuda.set_device(0)
+def measure_mapped(cg, ctx, args, spec, steps, warmup, do_parity=True):
+    """BASELINE config 4: MappedGrid, update!(grid, t_k) — which refreshes the node / centroid / face coordinates like
+    mapped_grid.jl:551-587 — + refresh of both metric caches every step (1 GPU; every rank runs its own replica)."""
+    torch, lib = ctx.torch, cg._lib.lib()
     n, h = spec["n"], spec["nhalo"]
     terms = cg.workloads.wavy_3d_terms((n, n, n), time_amp=0.1)
     grid = cg.MappedGrid(terms, {}, (n, n, n), h, cache_mode="lazy", conserved_metric_scheme=spec["scheme"])
-    lib = cg._lib.lib()
+    _ = grid.node_coordinates   # coordinate storage exists from here on: every update! rewrites the 15 coordinate arrays
     cells = int(np.prod(grid.window_cells))
     tk = [0]
 
@@ -490,41 +598,136 @@ def run_mapped(args, spec):
         cg.update(grid, 0.01 * tk[0])
         cg.refresh_metrics(grid)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(ctx.local_rank)
     sampler.start()
     launches0 = lib.cg_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
     launches = lib.cg_launch_count() - launches0
-    ms_per_step = e0.elapsed_time(e1) / args.steps
+    ms_per_step = e0.elapsed_time(e1) / steps
     clocks = sampler.stop()
     kms = []
-    for _ in range(min(args.steps, 5)):
+    for _ in range(min(steps, 5)):
         step()
         kms.append(grid.last_eval_ms())
     k_ms = float(np.mean(kms))
     peak, peak_src = measured_peak_gbs()
-    bpc = 856.0  # the metric kernel writes the FULL profile and reads only the 1-D tables
-    achieved = bpc * cells / (k_ms * 1e-3) / 1e9
+    bpc = float(BYTES_PER_CELL[("m3d", "full")])  # 976: coordinates (24 + 24 + 72) + FULL metrics (856), no node read
+    achieved = bpc * cells / (ms_per_step * 1e-3) / 1e9
+    parity = None
+    if do_parity:
+        from oracle import oracle as O
+        O.set_num_threads(_host_threads())
+        t = 0.01 * tk[0]
+        rng = np.random.default_rng(11)
+        sample = np.sort(rng.choice(cells, size=32, replace=False))
+        idx = torch.from_numpy(sample).to(ctx.dev)
+        cm, fm = cg.cell_metrics(grid), cg.face_metrics(grid)
+        pick = lambda a, k: a.reshape(-1, k)[idx].cpu().numpy()
+        got = {"cell_fwd": pick(cm.forward, 10), "cell_inv": pick(cm.inverse, 10),
+               "face_fwd": np.stack([pick(fm[a].forward, 10) for a in range(3)]),
+               "face_inv": np.stack([pick(fm[a].inverse, 10) for a in range(3)]),
+               "face_cons": np.stack([pick(fm[a].conserved, 9) for a in range(3)])}
+        truth = O.mapped_eval(terms, t, (n, n, n), h, spec["scheme"], sample=sample, precision="ld")
+        o64 = O.mapped_eval(terms, t, (n, n, n), h, spec["scheme"], sample=sample)
+
+        def rel(a, b, has_j):
+            K = a.shape[-1] - (1 if has_j else 0)
+            sc = np.abs(b[..., :K]).max(axis=-1, keepdims=True)
+            e = float((np.abs(a[..., :K] - b[..., :K]) / sc).max())
+            return max(e, float((np.abs(a[..., K] - b[..., K]) / np.abs(b[..., K])).max())) if has_j else e
+        jac = ("cell_fwd", "cell_inv", "face_fwd", "face_inv")
+        parity = {"jacobians_vs_truth": max(rel(got[k], truth[k], True) for k in jac),
+                  "conserved_vs_truth": rel(got["face_cons"], truth["face_cons"], False),
+                  "conserved_vs_oracle64": rel(got["face_cons"], o64["face_cons"], False),
+                  "oracle64_conserved_vs_truth": rel(o64["face_cons"], truth["face_cons"], False),
+                  "cells": len(sample), "gcl_max": max(cg.gcl(grid)), "truth": "oracle closure graph in long double"}
+        parity["max_rel_err"] = max(parity["jacobians_vs_truth"], parity["conserved_vs_truth"])
     line = {
         "metric": "metric-eval Mcells/s (cell+face, FP64)", "value": cells / (ms_per_step * 1e-3) / 1e6, "unit": "Mcells/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "n_gpus": 1, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": spec["desc"], "scheme": spec["scheme"], "profile": "full", "cells_written": cells,
-                   "l2": "outputs per step far exceed the 126 MB L2 (no flush needed)", "parallelism": "single"},
+                   "l2": "outputs per step far exceed the 126 MB L2 (no flush needed)", "parallelism": "single",
+                   "coordinates": "node / centroid / face coordinates are rewritten by every update! (inside the timed step)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_mapped_metrics3d_staged", "kernel_ms": k_ms,
+                     "traffic": None, "kernel": "k_mapped_coords + k_mapped_tables/factors + k_mapped_metrics3d_staged (the whole update! + refresh step)",
+                     "kernel_ms": ms_per_step, "metric_kernel_ms": k_ms,
                      "algorithmic_bytes_per_cell": bpc, "peak_source": f"MEASURED_PEAKS.json ({peak_src}, copy burst)"},
-        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        "cpu_baseline": None, "e2e": None, "parity": parity, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    grid.close()
+    del grid
+    torch.cuda.empty_cache()
+    return line
+
+
+def brief(line):
+    """What an `other_configs` entry keeps of a full line."""
+    r = line["roofline"]
+    out = {"workload": line["config"]["workload"], "scheme": line["config"]["scheme"], "profile": line["config"]["profile"],
+           "dtype": line["dtype"], "n_gpus": line["n_gpus"], "scaling": line["scaling"], "steps": line["steps"],
+           "value": line["value"], "unit": line["unit"], "ms_per_step": line["ms_per_step"], "kernel_ms": r["kernel_ms"],
+           "frac": r["frac"], "achieved_GBs": r["achieved"], "algorithmic_bytes_per_cell": r["algorithmic_bytes_per_cell"],
+           "parity": line.get("parity"), "clocks": line["clocks"], "gpu_launches": line["gpu_launches"]}
+    if line.get("e2e"):
+        out["e2e"] = {"value": line["e2e"]["value"], "ms_per_step": line["e2e"]["ms_per_step"]}
+    return out
+
+
+def run_ours(args, spec):
+    import curvigrid_b200 as cg
+    ctx = Ctx(args)
+    world = ctx.world
+    steps, warmup = args.steps, args.warmup
+    if spec["kind"] == "m3d":
+        line = measure_mapped(cg, ctx, args, spec, steps, warmup)
+    else:
+        line = measure_discrete(cg, ctx, args, spec, profile=args.profile, dtype=args.dtype, steps=steps, warmup=warmup,
+                                strong=args.strong, do_e2e=not args.no_e2e, do_cpu=not args.no_cpu_baseline,
+                                workload_name=args.workload)
+        if line["roofline"].get("kernel_ms") and args.workload == "3d512" and args.profile == "full" and args.dtype == "f64" \
+                and spec["scheme"] == "curvature" and args.kernel == 1:
+            fp = cg.fp64_instr_per_cell()
+            if fp:
+                cells_local = line["config"]["cells_written"] / world
+                rate = fp * cells_local / (line["roofline"]["kernel_ms"] * 1e-3)
+                line["roofline"]["fp64"] = {"instr_per_cell": fp, "achieved_Tinstr_s": rate / 1e12,
+                                            "peak_Tinstr_s": 59.0 * 148 * 1.965e9 / 1e12,
+                                            "frac": rate / (59.0 * 148 * 1.965e9), "note": "peak at the maximum SM clock"}
+    # the other BASELINE configs in the same driver-visible line (short runs; VERDICT r1 item 5)
+    if not args.no_others and args.workload == "3d512" and args.profile == "full" and args.dtype == "f64" and not args.strong:
+        others = {}
+        k = max(3, min(5, steps))
+
+        def other(name, sp, **kw):
+            try:
+                others[name] = brief(measure_discrete(cg, ctx, args, sp, steps=k, warmup=3, do_cpu=False, workload_name=name, **kw))
+            except Exception as e:  # a failed extra never takes the headline line with it
+                others[name] = {"error": repr(e)[:300]}
+        if world == 1:
+            other("2d4096 (BASELINE config 2)", workload_spec("2d4096", None), profile="full", dtype="f64", do_e2e=False)
+            try:
+                others["m3d512 (BASELINE config 4)"] = brief(measure_mapped(cg, ctx, args, workload_spec("m3d512", None), k, 3))
+            except Exception as e:
+                others["m3d512 (BASELINE config 4)"] = {"error": repr(e)[:300]}
+            other("3d512 compact", workload_spec("3d512", None), profile="compact", dtype="f64", do_e2e=False)
+            other("3d512 f32", workload_spec("3d512", None), profile="full", dtype="f32", do_e2e=False)
+        else:
+            other("sph1536 compact weak (BASELINE config 5)", workload_spec("sph1536", None), profile="compact", dtype="f64",
+                  do_e2e=False)
+            other("3d512 strong", workload_spec("3d512", None), profile="full", dtype="f64", strong=True, do_e2e=False)
+        line["other_configs"] = others
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 def main():
@@ -532,8 +735,6 @@ def main():
     spec = workload_spec(args.workload, args.scheme)
     if args.impl == "reference":
         run_reference(args, spec)
-    elif spec["kind"] == "m3d":
-        run_mapped(args, spec)
     else:
         run_ours(args, spec)
 

@@ -322,8 +322,8 @@ class DiscreteGrid(_UnifiedGrid):
                                           origin, count, self._stream()))
         self._node_inputs = keep  # keep device inputs alive: the library reads them in place
         self._node_input_shape = tuple(reversed(nn))  # memory order [k, j, i]
-        if any(isinstance(k, np.ndarray) for k in keep):
-            self.synchronize()  # pageable host memory must outlive the async copy
+        if any(isinstance(k, np.ndarray) or not k.is_cuda for k in keep):
+            self.synchronize()  # host memory must outlive the async copy
 
     def update_from_host(self, *coords, what=3, nchunks=8, comm=None, plan=None):
         """update!(grid, x, y, z) from HOST arrays + refresh of both caches, pipelined (cg_grid_update_from_host):
@@ -484,6 +484,17 @@ def local_grid(grid, global_cell_domain):
                       coordinate_system=grid.coordinate_system, basis=grid.basis, cache_mode=grid.cache_mode,
                       conserved_metric_scheme=grid.scheme, profile=grid.profile,
                       global_cell_indices=tuple((o, o + c) for o, c in zip(goff, celldims)), t=grid.state["t"])
+
+
+def kernel_names_3d():
+    """The launches of one 3-D DiscreteGrid cell+face evaluation (bench.py `roofline.kernel`)."""
+    return "k_face_xi + k_face_zeta<SWAP> (eta) + k_face_zeta (one cell+face evaluation = 3 launches)"
+
+
+def fp64_instr_per_cell():
+    """FP64 thread instructions per cell of the three marching kernels, FULL profile, Curvature (SASS of the loop
+    bodies: xi 736 per warp step and 29 cells, eta / zeta 697 per 31)."""
+    return 32.0 * (736.0 / 29.0 + 2.0 * 697.0 / 31.0)
 
 
 def gcl(grid, low_plane=None):

@@ -3,7 +3,7 @@ evaluation of the same analytic closures.  Tolerance 1e-12 relative (per-matrix 
 import numpy as np
 import pytest
 
-from util import RTOL_F64, assert_metrics_close, domain_indices, grid_outputs
+from util import RTOL_F64, assert_fp32_close, assert_metrics_close, domain_indices, grid_outputs
 
 pytestmark = pytest.mark.gpu
 SCHEMES = ("endpoint", "gradient", "curvature")
@@ -101,7 +101,8 @@ def test_mapped_fp32_and_compact(cg, oracle):
     ref = oracle.mapped_eval(terms, 0.0, celldims, h, "curvature")
     g32 = cg.MappedGrid(terms, {}, celldims, h, T=np.float32)
     dom = domain_indices(ref["nfull"], h)
-    assert_metrics_close(grid_outputs(cg, g32), ref, rtol=2e-4, where=dom, keys=("cell_fwd", "face_cons"), label="fp32")
+    # analytic mapping in FP32: eps32 x conditioning (coordinates up to 6, spacing ~1.3 on this 9 x 8 x 7 mesh)
+    assert_fp32_close(grid_outputs(cg, g32), ref, wl.nodes_from_terms(terms, 0.0, celldims, h), dom, label="mapped fp32", dx=1.3)
     comp = cg.MappedGrid(terms, {}, celldims, h, profile="compact")
     J = cg.cell_metrics(comp).reshape(-1).cpu().numpy()
     assert np.abs(J - ref["cell_fwd"][:, 9]).max() < 1e-12 * np.abs(J).max()

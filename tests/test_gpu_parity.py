@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from util import RTOL_F64, assert_metrics_close, domain_indices, grid_outputs, metric_err, mild_nodes
+from util import RTOL_F64, assert_fp32_close, assert_metrics_close, domain_indices, grid_outputs, metric_err, mild_nodes
 
 pytestmark = pytest.mark.gpu
 
@@ -66,14 +66,12 @@ def test_halo_coords_included_discards_caller_halo(cg, oracle, kernel):
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("shape,nhalo", [((12, 9), 3), ((8, 7, 6), 2)])
 def test_fp32_variant(cg, oracle, shape, nhalo, kernel):
-    nodes = mild_nodes(shape, seed=11, noise=0.0)
-    ref = oracle.discrete_eval(nodes, nhalo, "curvature")
-    g = _make(cg, [a.astype(np.float32) for a in nodes], nhalo, "curvature", kernel, T=np.float32)
+    nodes32 = [a.astype(np.float32) for a in mild_nodes(shape, seed=11, noise=0.0)]
+    ref = oracle.discrete_eval([a.astype(np.float64) for a in nodes32], nhalo, "curvature")  # same (rounded) inputs
+    g = _make(cg, nodes32, nhalo, "curvature", kernel, T=np.float32)
     got = grid_outputs(cg, g)
     dom = domain_indices(ref["nfull"], nhalo)
-    # FP32: conserved/forward entries to ~1e-5 relative on the interior; tolerance stated here
-    assert_metrics_close(got, ref, rtol=2e-4, where=dom, keys=("cell_fwd", "face_cons"), label="fp32")
-    assert_metrics_close(got, ref, rtol=5e-3, where=dom, keys=("cell_inv", "face_fwd", "face_inv"), label="fp32")
+    assert_fp32_close(got, ref, nodes32, dom, label="fp32")   # eps32 x conditioning (util.fp32_tolerances)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
