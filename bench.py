@@ -98,6 +98,16 @@ def workload_spec(name, scheme):
 # ---------------------------------------------------------------------------
 # node generators for one slab (numpy, host) — the reference's wavy meshes
 # ---------------------------------------------------------------------------
+def _full(a, shp):
+    """A writable C-contiguous array of shape `shp` holding `a` (broadcast)."""
+    a = np.asarray(a)
+    if a.shape == tuple(shp) and a.flags.c_contiguous and a.flags.writeable:
+        return a
+    out = np.empty(shp, dtype=a.dtype)
+    out[...] = a
+    return out
+
+
 def wavy_slab_3d(ni, nj, nk_total, k_lo, k_hi, L=4.0):
     """Node planes [k_lo,k_hi) of wavy_nodes_3d(ni,nj,nk_total) in memory order [k,j,i]."""
     dx, dy, dz = L / ni, L / nj, L / nk_total
@@ -109,7 +119,7 @@ def wavy_slab_3d(ni, nj, nk_total, k_lo, k_hi, L=4.0):
     x = -L / 2 + dx * (i + sp(j * dy) * sp(k * dz))
     y = -L / 2 + dy * (j + sp(k * dz) * sp(i * dx))
     z = -L / 2 + dz * (k + sp(i * dx) * sp(j * dy))
-    return [np.ascontiguousarray(np.broadcast_to(a, shp)) for a in (x, y, z)]
+    return [_full(a, shp) for a in (x, y, z)]
 
 
 def sph_slab_3d(ni, nj, nk_total, k_lo, k_hi):
@@ -126,7 +136,7 @@ def sph_slab_3d(ni, nj, nk_total, k_lo, k_hi):
     r = r0 + dr * i + 0.012 * s2j * s1k
     th = th0 + dth * j + 0.008 * s2i
     ph = ph0 + dph * k + 0.006 * s2i * s2j
-    return [np.ascontiguousarray(np.broadcast_to(a, shp)) for a in (r, th, ph)]
+    return [_full(a, shp) for a in (r, th, ph)]
 
 
 def wavy_slab_2d(nx, ny_total, j_lo, j_hi, a0=0.1):
@@ -135,7 +145,7 @@ def wavy_slab_2d(nx, ny_total, j_lo, j_hi, a0=0.1):
     x1d, y1d = i / (nx - 1), j / (ny_total - 1)
     w = a0 * np.sin(2 * np.pi * x1d) * np.sin(2 * np.pi * y1d)
     shp = (j_hi - j_lo, nx)
-    return [np.ascontiguousarray(np.broadcast_to(x1d + w, shp)), np.ascontiguousarray(np.broadcast_to(y1d + w, shp))]
+    return [_full(x1d + w, shp), _full(y1d + w, shp)]
 
 
 # ---------------------------------------------------------------------------
@@ -375,6 +385,16 @@ def parity_block(cg, ctx, grid, host, plan, spec, profile, dtype, nsamples=64):
             e = max(e, float((np.abs(a[..., K] - b[..., K]) / np.abs(b[..., K])).max()))
         return e
 
+    # cell.domain (where BASELINE.md defines parity) and the halo region separately: halo nodes are Line()
+    # extrapolations ROUNDED to the working precision, so both FP64 evaluations carry eps (|x|/dx)^2 there
+    dom = np.ones(nsamples, dtype=bool)
+    gidx = [idx[d][order] + grid.window_origin[d] for d in range(dim - 1)] + [ks[order] + k0]
+    for d in range(dim):
+        dom &= (gidx[d] >= h) & (gidx[d] < grid.nfull[d] - h)
+
+    def region(a, b, has_j, m):
+        return rel(a[..., m, :], b[..., m, :], has_j) if m.any() else 0.0
+
     out = {}
     if profile == "full":
         cm, fm = cg.cell_metrics(grid), cg.face_metrics(grid)
@@ -384,28 +404,32 @@ def parity_block(cg, ctx, grid, host, plan, spec, profile, dtype, nsamples=64):
                "face_inv": np.stack([pick(fm[a].inverse, N * N + 1) for a in range(N)]),
                "face_cons": np.stack([pick(fm[a].conserved, N * N) for a in range(N)])}
         jac = ("cell_fwd", "cell_inv", "face_fwd", "face_inv")
-        out["jacobians_vs_truth"] = max(rel(got[k], truth[k], True) for k in jac)
-        out["jacobians_vs_oracle64"] = max(rel(got[k], o64[k], True) for k in jac)
-        out["conserved_vs_truth"] = rel(got["face_cons"], truth["face_cons"], False)
+        for nm, m in (("domain", dom), ("halo", ~dom)):
+            out[nm + "_jacobians_vs_truth"] = max(region(got[k], truth[k], True, m) for k in jac)
+            out[nm + "_conserved_vs_truth"] = region(got["face_cons"], truth["face_cons"], False, m)
+            out[nm + "_oracle64_conserved_vs_truth"] = region(o64["face_cons"], truth["face_cons"], False, m)
         out["conserved_vs_oracle64"] = rel(got["face_cons"], o64["face_cons"], False)
-        out["oracle64_conserved_vs_truth"] = rel(o64["face_cons"], truth["face_cons"], False)
     else:
         J = cg.cell_metrics(grid).reshape(-1)[widx].double().cpu().numpy()
-        out["jacobians_vs_truth"] = float(np.abs(J / truth["cell_fwd"][:, N * N] - 1).max())
-        out["jacobians_vs_oracle64"] = float(np.abs(J / o64["cell_fwd"][:, N * N] - 1).max())
-        ev = eo = et = 0.0
-        for a in range(N):
-            g_ = cg.face_metrics(grid)[a].reshape(-1, N)[widx].double().cpu().numpy()
-            t_ = np.stack([truth["face_cons"][a][:, a + N * c] for c in range(N)], axis=1)
-            o_ = np.stack([o64["face_cons"][a][:, a + N * c] for c in range(N)], axis=1)
-            sc = np.abs(truth["face_cons"][a]).max(axis=1, keepdims=True)
-            ev, eo, et = max(ev, float((np.abs(g_ - t_) / sc).max())), max(eo, float((np.abs(g_ - o_) / sc).max())), \
-                max(et, float((np.abs(o_ - t_) / sc).max()))
-        out["conserved_vs_truth"], out["conserved_vs_oracle64"], out["oracle64_conserved_vs_truth"] = ev, eo, et
+        act = [cg.face_metrics(grid)[a].reshape(-1, N)[widx].double().cpu().numpy() for a in range(N)]
+        for nm, m in (("domain", dom), ("halo", ~dom)):
+            if not m.any():
+                out[nm + "_jacobians_vs_truth"] = out[nm + "_conserved_vs_truth"] = out[nm + "_oracle64_conserved_vs_truth"] = 0.0
+                continue
+            out[nm + "_jacobians_vs_truth"] = float(np.abs(J[m] / truth["cell_fwd"][m, N * N] - 1).max())
+            ev = et = 0.0
+            for a in range(N):
+                t_ = np.stack([truth["face_cons"][a][m][:, a + N * c] for c in range(N)], axis=1)
+                o_ = np.stack([o64["face_cons"][a][m][:, a + N * c] for c in range(N)], axis=1)
+                sc = np.abs(truth["face_cons"][a][m]).max(axis=1, keepdims=True)
+                ev, et = max(ev, float((np.abs(act[a][m] - t_) / sc).max())), max(et, float((np.abs(o_ - t_) / sc).max()))
+            out[nm + "_conserved_vs_truth"], out[nm + "_oracle64_conserved_vs_truth"] = ev, et
     out = {k: ctx.allmax(v) for k, v in out.items()}
     # `max_rel_err`: CUDA against the exact value of the reference's algorithm on the same inputs (long-double truth)
-    out["max_rel_err"] = max(out["jacobians_vs_truth"], out["conserved_vs_truth"])
+    # on cell.domain, where BASELINE.md §4 defines parity
+    out["max_rel_err"] = max(out["domain_jacobians_vs_truth"], out["domain_conserved_vs_truth"])
     out["cells"] = nsamples * ctx.world
+    out["cells_in_domain"] = ctx.allsum_int(int(dom.sum()))
     out["truth"] = "oracle closure graph in long double" if dtype == "f64" else "FP64 oracle on the FP32-rounded nodes"
     return out
 
@@ -432,7 +456,7 @@ def measure_discrete(cg, ctx, args, spec, *, profile, dtype, steps, warmup, stro
     else:
         host = wavy_slab_2d(n + 1, ncell_slab + 1, lo, hi)
         inplane = (n,)
-    host = [np.ascontiguousarray(a, dtype=T) for a in host]
+    host = [a if a.dtype == T else a.astype(T) for a in host]
     if world > 1:
         # the truth for the non-owned planes comes from their owners through the exchange: blank them on this rank
         for a in host:

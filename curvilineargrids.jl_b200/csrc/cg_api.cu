@@ -283,7 +283,10 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
   if (what & CG_WHAT_COORDS) {
     cg::CoordOut<T> C;
     if ((rc = bind_coord_outputs<T>(g, C))) return rc;
-    cg::k_mapped_coords<T><<<launch_blocks(g->nnodes(), 128), 128, 0, st>>>(D, TM, C);
+    if (cg::mapped_prepare_coords<T>(g->mtab, D, st)) return fail(CG_ERR_CUDA, "mapped_prepare_coords: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches += g->mtab.launches;
+    g->mtab.launches = 0;
+    cg::k_mapped_coords<T><<<launch_blocks(g->nnodes(), 256), 256, 0, st>>>(D, TM, (const T*)g->mtab.ctab, g->mtab.L + 1, C);
     g_launches++;
     CG_CUDA(cudaGetLastError());
     g->valid_coords = true;

@@ -331,7 +331,9 @@ CG_HD void cell_taylor(const T* A, const int64_t (&st)[3], int64_t b, T (&c)[8])
   c[1] = T(0.5) * (lo.cu + hi.cu);
   c[2] = T(0.5) * (lo.cv + hi.cv);
   c[3] = T(0.5) * (lo.cuv + hi.cuv);
-  c[4] = hi.c0 - lo.c0;
+  // first zeta-difference: the four zeta-edges of the cell (not a difference of plane sums, see cg_math.cuh)
+  c[4] = T(0.25) * (((A[bz] - A[b]) + (A[bz + st[0]] - A[b + st[0]])) +
+                    ((A[bz + st[1]] - A[b + st[1]]) + (A[bz + st[0] + st[1]] - A[b + st[0] + st[1]])));
   c[5] = hi.cu - lo.cu;
   c[6] = hi.cv - lo.cv;
   c[7] = hi.cuv - lo.cuv;

@@ -105,10 +105,11 @@ template <class T> CG_D T ldn(const T* p) { return __ldg(p); }
 // RAW bilinear form of 4 face nodes n[bu][bv] (no normalisation: pure sums and differences)
 //   c0 = 4 * (true c0), cu = 2 * (true cu), cv = 2 * (true cv), cuv = true cuv
 // Every consumer below is bilinear in form coefficients, so the powers of two fold into its constants.
+// First differences are taken between neighbouring nodes (cg_math.cuh: round-off rule), never between node sums.
 template <class T>
 CG_D Form4<T> raw_form(T n00, T n10, T n01, T n11) {
   T s0 = n10 + n00, d0 = n10 - n00, s1 = n11 + n01, d1 = n11 - n01;
-  return {s0 + s1, d0 + d1, s1 - s0, d1 - d0};
+  return {s0 + s1, d0 + d1, (n01 - n00) + (n11 - n10), d1 - d0};
 }
 // zeta-plane forms (fixed k), transverse (xi, eta)
 template <class T, class IX>
@@ -124,7 +125,7 @@ CG_D PF<T> zplane(const NodeP<T, IX>& N, IX b) {
 // sum / difference of a node column across two consecutive zeta planes, per coordinate
 template <class T>
 struct ZPair {
-  T s[3], d[3];
+  T s[3], d[3], lo[3];  // sum, difference (exact) and lower node of the column
 };
 template <class T, class IX>
 CG_D ZPair<T> zpair(const NodeP<T, IX>& N, IX b) {
@@ -134,16 +135,21 @@ CG_D ZPair<T> zpair(const NodeP<T, IX>& N, IX b) {
     const T lo = ldn(N.q[q] + b), hi = ldn(N.q[q] + b + N.s2);
     p.s[q] = hi + lo;
     p.d[q] = hi - lo;
+    p.lo[q] = lo;
   }
   return p;
 }
 // raw form of the plane through two node columns a, b (u = from a to b, v = zeta): an eta-plane from two
-// xi-adjacent columns, a xi-plane from two eta-adjacent columns; 4 additions per coordinate
+// xi-adjacent columns, a xi-plane from two eta-adjacent columns; 5 operations per coordinate.  The u-difference
+// (b.hi - a.hi) + (b.lo - a.lo) is formed as 2 (b.lo - a.lo) + (b.d - a.d): neighbour differences only.
 template <class T>
 CG_D PF<T> pair_form(const ZPair<T>& a, const ZPair<T>& b) {
   PF<T> f;
 #pragma unroll
-  for (int q = 0; q < 3; ++q) f.q[q] = {a.s[q] + b.s[q], b.s[q] - a.s[q], a.d[q] + b.d[q], b.d[q] - a.d[q]};
+  for (int q = 0; q < 3; ++q) {
+    const T cuv = b.d[q] - a.d[q];
+    f.q[q] = {a.s[q] + b.s[q], fma(T(2), b.lo[q] - a.lo[q], cuv), a.d[q] + b.d[q], cuv};
+  }
   return f;
 }
 // ---------------------------------------------------------------------------
@@ -199,6 +205,7 @@ struct RingV {
       const T lo = row(plane, r, q)[c], hi = row(plane + 1, r, q)[c];
       p.s[q] = hi + lo;
       p.d[q] = hi - lo;
+      p.lo[q] = lo;
     }
     return p;
   }
@@ -212,37 +219,23 @@ CG_D PF<T> swap_uv(const PF<T>& p) {
   return o;
 }
 
-// cell Taylor coefficients (true values) from the two RAW zeta-planes of the cell (bitmask: 1 xi, 2 eta, 4 zeta)
+// cell Taylor coefficients (true values) from the two RAW zeta-planes of the cell (bitmask: 1 xi, 2 eta, 4 zeta);
+// dz[q] = sum of the cell's four zeta-edge differences (the first zeta-difference is NOT taken between the plane sums:
+// round-off rule, cg_math.cuh)
 template <class T>
-CG_D void taylor_from_z(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
+CG_D void taylor_from_z(const PF<T>& lo, const PF<T>& hi, const T (&dz)[3], T (&c)[3][8]) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     c[q][0] = T(0.125) * (lo.q[q].c0 + hi.q[q].c0);
     c[q][1] = T(0.25) * (lo.q[q].cu + hi.q[q].cu);
     c[q][2] = T(0.25) * (lo.q[q].cv + hi.q[q].cv);
     c[q][3] = T(0.5) * (lo.q[q].cuv + hi.q[q].cuv);
-    c[q][4] = T(0.25) * (hi.q[q].c0 - lo.q[q].c0);
+    c[q][4] = T(0.25) * dz[q];
     c[q][5] = T(0.5) * (hi.q[q].cu - lo.q[q].cu);
     c[q][6] = T(0.5) * (hi.q[q].cv - lo.q[q].cv);
     c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
   }
 }
-// the same from the two RAW eta-planes (u = xi, v = zeta) of the cell
-template <class T>
-CG_D void taylor_from_e(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    c[q][0] = T(0.125) * (lo.q[q].c0 + hi.q[q].c0);
-    c[q][1] = T(0.25) * (lo.q[q].cu + hi.q[q].cu);
-    c[q][2] = T(0.25) * (hi.q[q].c0 - lo.q[q].c0);
-    c[q][3] = T(0.5) * (hi.q[q].cu - lo.q[q].cu);
-    c[q][4] = T(0.25) * (lo.q[q].cv + hi.q[q].cv);
-    c[q][5] = T(0.5) * (lo.q[q].cuv + hi.q[q].cuv);
-    c[q][6] = T(0.5) * (hi.q[q].cv - lo.q[q].cv);
-    c[q][7] = hi.q[q].cuv - lo.q[q].cuv;
-  }
-}
-
 // Half states W+-_f of the six E^a polynomials on the a-face between cells c and
 // c+a.  P0/P1/P2: RAW forms on the low face of c, the shared face, the high face of
 // c+a, Form4 ordered (u = f, v = t).  Raw products carry 8 (cu c0, cv c0), 4 (cu cu, cv cu, cuv c0) or
@@ -370,13 +363,14 @@ CG_D LineS<T> line_from_taylor(const T (&c)[3][8], int q1, int q2, int f, int b,
 // RAW Taylor sums of the cell from its two RAW eta-planes: craw[q][S] = 2^(3 - |S|) * (true coefficient), pure
 // sums / differences.  Every consumer in the eta / zeta kernels is a product of two coefficients (line scalars) or
 // homogeneous in F (inverse Jacobian states), so the powers of two fold into compile-time weights.
+// de[q] = sum of the cell's four eta-edge differences (round-off rule, cg_math.cuh).
 template <class T>
-CG_D void taylor_raw_e(const PF<T>& lo, const PF<T>& hi, T (&c)[3][8]) {
+CG_D void taylor_raw_e(const PF<T>& lo, const PF<T>& hi, const T (&de)[3], T (&c)[3][8]) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
     c[q][0] = lo.q[q].c0 + hi.q[q].c0;
     c[q][1] = lo.q[q].cu + hi.q[q].cu;
-    c[q][2] = hi.q[q].c0 - lo.q[q].c0;
+    c[q][2] = de[q];
     c[q][3] = hi.q[q].cu - lo.q[q].cu;
     c[q][4] = lo.q[q].cv + hi.q[q].cv;
     c[q][5] = lo.q[q].cuv + hi.q[q].cuv;
@@ -575,8 +569,16 @@ __global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
     Stage<T, 10> Scf(O.cell_fwd, cl0, sg_cf), Sci(O.cell_inv, cl0, sg_ci), Sff(O.face_fwd[0], cl0, sg_ff),
         Sfi(O.face_inv[0], cl0, sg_fi);
     Stage<T, 9> Sfc(O.face_cons[0], cl0, sg_fc);
+    // eta-planes j, j+1 of the cell (u = xi, v = zeta) from the zeta-pairs of its four node columns
+    const PF<T> e1 = pair_form(R.zpair(pm, 1, lane), R.zpair(pm, 1, lane + 1)),
+                e2 = pair_form(R.zpair(pm, 2, lane), R.zpair(pm, 2, lane + 1));
     T c[3][8];
-    taylor_from_z(z0, z1, c);
+    {
+      T dz[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) dz[q] = e1.q[q].cv + e2.q[q].cv;
+      taylor_from_z(z0, z1, dz, c);
+    }
     if (do_cell || do_gf) {
       T F[3][3], G[3][3];
 #pragma unroll
@@ -639,18 +641,9 @@ __global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
       // ---- eta-direction edge scalars on both eta faces of the cell ----
       T dpsi_eta[6];
       {
-        // eta-planes j-1 .. j+2 (u = xi, v = zeta): the outer two from the zeta-pairs of the node columns
-        // i, i+1; the cell's own two eta-faces from the carried zeta-planes (same 8 nodes, no reloads)
-        PF<T> e0 = pair_form(R.zpair(pm, 0, lane), R.zpair(pm, 0, lane + 1)),
-              e3 = pair_form(R.zpair(pm, 3, lane), R.zpair(pm, 3, lane + 1)), e1, e2;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const Form4<T>&lo = z0.q[q], &hi = z1.q[q];
-          const T s0 = lo.c0 + hi.c0, su = lo.cu + hi.cu, sv = lo.cv + hi.cv, suv = lo.cuv + hi.cuv;
-          const T d0 = hi.c0 - lo.c0, du = hi.cu - lo.cu, dv = hi.cv - lo.cv, duv = hi.cuv - lo.cuv;
-          e1.q[q] = {T(0.5) * (s0 - sv), T(0.5) * (su - suv), T(0.5) * (d0 - dv), T(0.5) * (du - duv)};
-          e2.q[q] = {T(0.5) * (s0 + sv), T(0.5) * (su + suv), T(0.5) * (d0 + dv), T(0.5) * (du + duv)};
-        }
+        // eta-planes j-1 .. j+2 (u = xi, v = zeta) from the zeta-pairs of the node columns i, i+1
+        const PF<T> e0 = pair_form(R.zpair(pm, 0, lane), R.zpair(pm, 0, lane + 1)),
+                    e3 = pair_form(R.zpair(pm, 3, lane), R.zpair(pm, 3, lane + 1));
         T wp[6], wm[6];
         eface6_diff<T, SCH>(e0, e1, e2, e3, wp, wm);  // (face j + 1/2) - (face j - 1/2)
 #pragma unroll
@@ -736,11 +729,17 @@ struct RingSrc {
   CG_D PF<T> zpl(int d) const { return R.zplane(p + d, 1, lane); }
 };
 
-// the six zeta-line scalars of the cell at plane offset d of the source (index = bb*3 + col; bb 0: b = xi, 1: b = eta)
+// the six zeta-line scalars of the cell whose lower plane is the source's plane (index = bb*3 + col; bb 0: b = xi, 1: b = eta)
 template <class T, class SRC>
-CG_D void zlines(const SRC& S, int d, T lam1, T lam2, LineS<T> (&ln)[6]) {
+CG_D void zlines(const SRC& S, T lam1, T lam2, LineS<T> (&ln)[6]) {
   T c[3][8];
-  taylor_from_z(S.zpl(d), S.zpl(d + 1), c);
+  {
+    const ZPair<T> p00 = S.zp(0, 0), p01 = S.zp(0, 1), p10 = S.zp(1, 0), p11 = S.zp(1, 1);
+    T dz[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) dz[q] = (p00.d[q] + p01.d[q]) + (p10.d[q] + p11.d[q]);
+    taylor_from_z(S.zpl(0), S.zpl(1), dz, c);
+  }
 #pragma unroll
   for (int col = 0; col < 3; ++col) {
     const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
@@ -760,14 +759,17 @@ CG_D void cellz_compute(const SRC& S, bool full, T lam1, T lam2, CellZ<T>& o) {
     const PF<T> E0 = pair_form(S.zp(-1, 0), S.zp(-1, 1)), E3 = pair_form(S.zp(2, 0), S.zp(2, 1));
     eface6_diff<T, SCH>(swap_uv(E0), swap_uv(E1), swap_uv(E2), swap_uv(E3), o.wpe, o.wme);
   }
+  T de[3];  // sum of the cell's four eta-edge differences
   {
     // xi face i+1/2: xi-planes i, i+1, i+2, forms (eta,zeta) -> need (u,v) = (zeta, eta)
     const PF<T> X0 = pair_form(p00, p10), X1 = pair_form(p01, p11), X2 = pair_form(S.zp(0, 2), S.zp(1, 2));
     eface6<T, SCH>(swap_uv(X0), swap_uv(X1), swap_uv(X2), o.wpx, o.wmx);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) de[q] = X0.q[q].cu + X1.q[q].cu;
   }
   if (!full) return;
   T c[3][8];
-  taylor_raw_e(E1, E2, c);  // one (raw) Taylor expansion of the cell serves the line scalars and the L / R states
+  taylor_raw_e(E1, E2, de, c);  // one (raw) Taylor expansion of the cell serves the line scalars and the L / R states
 #pragma unroll
   for (int col = 0; col < 3; ++col) {
     const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
@@ -856,7 +858,7 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
     const GlobalSrc<T> S0{N, nbase + (Ix)k0 * N.s2};
     if (full) {
       LineS<T> lm[6];  // cell k0 - 1
-      zlines(S0, -1, lam1, lam2, lm);
+      zlines(GlobalSrc<T>{N, nbase + (Ix)(k0 - 1) * N.s2}, lam1, lam2, lm);
 #pragma unroll
       for (int e = 0; e < 6; ++e) F2[e] = lm[e].vp;
     }
@@ -1005,7 +1007,7 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
     __syncwarp();
     const GlobalSrc<T> S1{N, nbase + (Ix)(k1 + 1) * N.s2};
     LineS<T> l2[6];
-    zlines(S1, 0, lam1, lam2, l2);
+    zlines(S1, lam1, lam2, l2);
     T vm[6];
 #pragma unroll
     for (int e = 0; e < 6; ++e) vm[e] = l2[e].vm;

@@ -825,9 +825,36 @@ __global__ void k_mapped_metrics1d(Dims D, MTerms TM, const T* __restrict__ ftab
 }
 
 // coordinates of a MappedGrid: the mapping evaluated at node / centroid / face-centre positions
-// (generation.jl:187-309)
+// (generation.jl:187-309).  The mapping is separable, and all evaluation points are node positions (integer xi) or
+// cell centres (xi + 1/2) per axis — the high-side face centre on axis a is the centre moved half a cell along a,
+// i.e. the NODE position I_a + 1 there.  k_mapped_ctab tabulates every factor at the nodes and centres of its axis
+// once per update! (O(N) sin / cos); the O(N^3) kernel is products of table values and 120 B of coalesced stores
+// per cell (the first version evaluated ~90 sincos per node: 21 ms at 512^3).
+//   ctab[((m*3 + d)*L1 + I)*2 + w],  w = 0: f_md(node I),  w = 1: f_md(centre I),  I in [0, nw_d]
 template <class T>
-__global__ void k_mapped_coords(Dims D, MTerms TM, CoordOut<T> O) {
+__global__ void k_mapped_ctab(Dims D, MTerms TM, T* ctab, int64_t L1) {
+  const int64_t ntot = (int64_t)TM.n * 3 * L1;
+  for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
+       lin += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t I = lin % L1;
+    const int d = (int)((lin / L1) % 3);
+    const int m = (int)(lin / (3 * L1));
+    T* base = ctab + ((int64_t)(m * 3 + d) * L1 + I) * 2;
+    if (d >= D.dim) {
+      base[0] = base[1] = T(1);
+      continue;
+    }
+    if (I > D.nw[d]) continue;
+    const MTerm& t = TM.t[m];
+    const double s = double(D.w0[d] + I + 1 - D.nhalo);  // node I of the window (generation.jl:209-221)
+    base[0] = T(fac_der(t.kind[d], t.a[d], t.b[d], s, 0));
+    base[1] = T(fac_der(t.kind[d], t.a[d], t.b[d], s + 0.5, 0));
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) k_mapped_coords(Dims D, MTerms TM, const T* __restrict__ ctab, int64_t L1,
+                                                       CoordOut<T> O) {
   int64_t nn[3] = {1, 1, 1};
   for (int d = 0; d < D.dim; ++d) nn[d] = D.nw[d] + 1;
   const int64_t ntot = nn[0] * nn[1] * nn[2];
@@ -845,26 +872,36 @@ __global__ void k_mapped_coords(Dims D, MTerms TM, CoordOut<T> O) {
       clin += n[d] * cst;
       cst *= D.nw[d];
     }
-    // which: 0 node, 1 centroid, 2+a face a
-    for (int which = 0; which < 2 + D.dim; ++which) {
-      if (which > 0 && !is_cell) break;
-      double s[3] = {0, 0, 0};
-      for (int d = 0; d < D.dim; ++d) {
-        s[d] = double(D.w0[d] + n[d] + 1 - D.nhalo);
-        if (which >= 1) s[d] += 0.5;
-        if (which >= 2 && d == which - 2) s[d] += 0.5;
+    T qn[3] = {0, 0, 0}, qc[3] = {0, 0, 0}, qf[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int m = 0; m < TM.n; ++m) {
+      T fn[3], fc[3], fh[3];  // factor at node I, centre I, node I + 1 (the face position) per axis
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const T* b = ctab + ((int64_t)(m * 3 + d) * L1 + n[d]) * 2;
+        fn[d] = b[0];
+        fc[d] = b[1];
+        fh[d] = (d < D.dim && n[d] < D.nw[d]) ? b[2] : T(1);
       }
-      double q[3] = {0, 0, 0};
-      for (int m = 0; m < TM.n; ++m) {
-        double v = TM.t[m].coef;
-        for (int d = 0; d < D.dim; ++d) v *= fac_der(TM.t[m].kind[d], TM.t[m].a[d], TM.t[m].b[d], s[d], 0);
-        q[TM.t[m].coord] += v;
-      }
-      for (int c = 0; c < D.dim; ++c) {
-        if (which == 0) { if (O.node[c]) O.node[c][lin] = T(q[c]); }
-        else if (which == 1) { if (O.centroid[c]) O.centroid[c][clin] = T(q[c]); }
-        else if (O.face[which - 2][c]) O.face[which - 2][c][clin] = T(q[c]);
-      }
+      const T c = T(TM.t[m].coef);
+      const int q = TM.t[m].coord;
+      const T vn = c * fn[0] * fn[1] * fn[2], vc = c * fc[0] * fc[1] * fc[2];
+      const T v0 = c * fh[0] * fc[1] * fc[2], v1 = c * fc[0] * fh[1] * fc[2], v2 = c * fc[0] * fc[1] * fh[2];
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq)
+        if (qq == q) {
+          qn[qq] += vn;
+          qc[qq] += vc;
+          qf[0][qq] += v0;
+          qf[1][qq] += v1;
+          qf[2][qq] += v2;
+        }
+    }
+    for (int c = 0; c < D.dim; ++c) {
+      if (O.node[c]) O.node[c][lin] = qn[c];
+      if (!is_cell) continue;
+      if (O.centroid[c]) O.centroid[c][clin] = qc[c];
+      for (int a = 0; a < D.dim; ++a)
+        if (O.face[a][c]) O.face[a][c][clin] = qf[a][c];
     }
   }
 }
@@ -878,7 +915,9 @@ struct MappedTables {
   void* tab = nullptr;
   void* ftab = nullptr;
   void* fhalf = nullptr;  // factor tables at centre + 1/2 (ADThomasLombardMetric only)
-  size_t tab_bytes = 0, ftab_bytes = 0, fhalf_bytes = 0;
+  void* ctab = nullptr;   // factor values at nodes and centres (coordinates)
+  size_t tab_bytes = 0, ftab_bytes = 0, fhalf_bytes = 0, ctab_bytes = 0;
+  bool ctab_dirty = true;
   int64_t L = 0;
   MTerms terms;
   MPairs pairs;
@@ -886,8 +925,9 @@ struct MappedTables {
     if (tab) cudaFree(tab);
     if (ftab) cudaFree(ftab);
     if (fhalf) cudaFree(fhalf);
-    tab = ftab = fhalf = nullptr;
-    tab_bytes = ftab_bytes = fhalf_bytes = 0;
+    if (ctab) cudaFree(ctab);
+    tab = ftab = fhalf = ctab = nullptr;
+    tab_bytes = ftab_bytes = fhalf_bytes = ctab_bytes = 0;
   }
 };
 
@@ -976,6 +1016,27 @@ inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, dou
   }
   if (cudaGetLastError() != cudaSuccess) return 3;
   M.dirty = false;
+  M.ctab_dirty = true;
+  return 0;
+}
+
+// the coordinate tables of the current terms (after mapped_prepare); returns 0 ok, 3 cuda error
+template <class T>
+inline int mapped_prepare_coords(MappedTables& M, const Dims& D, cudaStream_t st) {
+  if (!M.ctab_dirty && M.ctab) return 0;
+  const int nt = M.terms.n;
+  const int64_t L1 = M.L + 1;
+  const size_t cb = (size_t)nt * 3 * 2 * (L1 + 1) * sizeof(T);  // one entry of slack: the kernel reads node I + 1
+  if (cb > M.ctab_bytes) {
+    if (M.ctab) cudaFree(M.ctab);
+    if (cudaMalloc(&M.ctab, cb) != cudaSuccess) return 3;
+    M.ctab_bytes = cb;
+  }
+  const int64_t n = (int64_t)nt * 3 * L1;
+  k_mapped_ctab<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(D, M.terms, (T*)M.ctab, L1);
+  M.launches++;
+  if (cudaGetLastError() != cudaSuccess) return 3;
+  M.ctab_dirty = false;
   return 0;
 }
 

@@ -144,8 +144,9 @@ def discrete_3d(nodes, nhalo, scheme="curvature"):
         per_q = []
         for q in range(3):
             N = Q[q]
+            # first differences between neighbouring nodes, THEN averages (round-off rule of the kernels, cg_math.cuh)
             per_q.append({"0": _avg(_avg(N, u), v), "u": _avg(_dif(N, u), v),
-                          "v": _dif(_avg(N, u), v), "uv": _dif(_dif(N, u), v)})
+                          "v": _avg(_dif(N, v), u), "uv": _dif(_dif(N, u), v)})
         FA.append(per_q)
 
     # cell Taylor forms T[q][frozenset(axes)]
@@ -155,7 +156,7 @@ def discrete_3d(nodes, nhalo, scheme="curvature"):
         u, v = 1, 2
         F = FA[a][q]
         T.append({(): _avg(F["0"], a), (u,): _avg(F["u"], a), (v,): _avg(F["v"], a), (u, v): _avg(F["uv"], a),
-                  (a,): _dif(F["0"], a), (a, u): _dif(F["u"], a), (a, v): _dif(F["v"], a),
+                  (a,): _avg(_avg(_dif(Q[q], a), u), v), (a, u): _dif(F["u"], a), (a, v): _dif(F["v"], a),
                   (a, u, v): _dif(F["uv"], a)})
 
     def tc(q, *axes):

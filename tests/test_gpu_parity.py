@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import pytest
 
-from util import RTOL_F64, assert_fp32_close, assert_metrics_close, domain_indices, grid_outputs, metric_err, mild_nodes
+from util import RTOL_F64, assert_fp32_close, assert_metrics_close, assert_three_way, domain_indices, grid_outputs, metric_err, mild_nodes
 
 pytestmark = pytest.mark.gpu
 
@@ -172,9 +172,10 @@ def test_3d_128_sampled_oracle_and_kernel_crosscheck(cg, oracle):
     rng = np.random.default_rng(0)
     ntot = int(np.prod(o1["nfull"]))
     sample = np.sort(rng.choice(ntot, size=96, replace=False))
-    ref = oracle.discrete_eval(nodes, h, "curvature", sample=sample)
     got = {k: (o1[k][..., sample, :]) for k in ("cell_fwd", "cell_inv", "face_fwd", "face_inv", "face_cons")}
-    assert_metrics_close(got, ref, rtol=1e-11, label="128^3 sampled")  # coarse wavy halo cells are ill-conditioned
+    # cell.domain within 1e-12 of the long-double evaluation of the reference's algorithm (util.assert_three_way)
+    rep = assert_three_way(oracle, got, nodes, h, "curvature", sample, o1["nfull"], label="128^3 sampled")
+    assert rep["face_cons"]["domain_gpu_vs_truth"] <= 1e-12
     g0 = _make(cg, nodes, h, "curvature", 0)
     o0 = grid_outputs(cg, g0)
     dom = domain_indices(o1["nfull"], h)
@@ -190,9 +191,8 @@ def test_2d_1024_gradient_properties(cg, oracle):
     assert max(cg.gcl(g)) < 5e-15
     rng = np.random.default_rng(1)
     sample = np.sort(rng.choice(int(np.prod(o["nfull"])), size=256, replace=False))
-    ref = oracle.discrete_eval(nodes, 5, "gradient", sample=sample)
     got = {k: (o[k][..., sample, :]) for k in ("cell_fwd", "cell_inv", "face_fwd", "face_inv", "face_cons")}
-    assert_metrics_close(got, ref, rtol=1e-11, label="1024^2 sampled")
+    assert_three_way(oracle, got, nodes, 5, "gradient", sample, o["nfull"], label="1024^2 sampled")
 
 
 # ---------------------------------------------------------------------------
@@ -286,11 +286,17 @@ def test_3d_512_full_size_properties(cg, oracle):
     nfull = tuple(n + 10 for n in (512, 512, 512))
     sample = np.sort(rng.choice(int(np.prod(nfull)), size=64, replace=False))
     got = _sampled(cg, g, sample)
-    ref = oracle.discrete_eval(nodes, 5, "curvature", sample=sample)
-    # 1e-11, not 1e-12: the conserved metrics are O(dx^2) differences of products of O(|x|) coordinates, so BOTH
-    # evaluations carry round-off of order eps * |x| / dx per operation (|x| / dx ~ 500 here; 5.9e-12 observed on
-    # cell.domain).  The tolerance of the north star is met where the mesh is not that fine (tests above, 1e-12).
-    assert_metrics_close(got, ref, rtol=1e-11, label="512^3 sampled")
+    # North-star tolerance at the BASELINE size: on cell.domain every entry is within 1e-12 of the EXACT value of the
+    # reference's algorithm on these inputs (long-double oracle).  The reference's own Float64 arithmetic (FP64 oracle)
+    # is 7e-12 from that value here — eps (|x|/dx)^2, |x|/dx = 256 — so a direct 1e-12 comparison of two FP64
+    # evaluations is not meaningful at this size; the kernels take first differences between neighbouring nodes and
+    # stay at eps |x|/dx (6e-14 measured, tools/roundoff_gpu.py).
+    rep = assert_three_way(oracle, got, nodes, 5, "curvature", sample, nfull, label="512^3 sampled")
+    assert rep["face_cons"]["domain_gpu_vs_truth"] < rep["face_cons"]["domain_oracle64_vs_truth"]
+    # a second sample inside cell.domain only, near the corners of the box where |x| / dx is largest
+    far = np.concatenate([rng.integers(nfull[0] - 40, nfull[0] - 6, (24, 3)), rng.integers(6, 40, (24, 3))])
+    s2 = np.sort(far[:, 0] + nfull[0] * (far[:, 1] + nfull[1] * far[:, 2])).astype(np.int64)
+    assert_three_way(oracle, _sampled(cg, g, s2), nodes, 5, "curvature", s2, nfull, label="512^3 corners")
     del g
     torch.cuda.empty_cache()
     g1 = cg.DiscreteGrid(*nodes, 5, cache_mode="lazy", profile="compact")
@@ -311,8 +317,7 @@ def test_2d_4096_full_size_properties(cg, oracle):
     rng = np.random.default_rng(8)
     sample = np.sort(rng.choice(4106 * 4106, size=256, replace=False))
     got = _sampled(cg, g, sample)
-    ref = oracle.discrete_eval(nodes, 5, "gradient", sample=sample)
-    assert_metrics_close(got, ref, rtol=1e-11, label="4096^2 sampled")
+    assert_three_way(oracle, got, nodes, 5, "gradient", sample, (4106, 4106), label="4096^2 sampled")
     g2 = cg.DiscreteGrid(*[2.0 * a for a in nodes], 5, conserved_metric_scheme="gradient", cache_mode="lazy")
     f1, f2 = cg.face_metrics(g), cg.face_metrics(g2)
     for a in range(2):
