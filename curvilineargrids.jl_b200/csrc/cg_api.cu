@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/curvigrid_cuda.h"
@@ -286,7 +287,8 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
     if (cg::mapped_prepare_coords<T>(g->mtab, D, st)) return fail(CG_ERR_CUDA, "mapped_prepare_coords: %s", cudaGetErrorString(cudaGetLastError()));
     g_launches += g->mtab.launches;
     g->mtab.launches = 0;
-    cg::k_mapped_coords<T><<<launch_blocks(g->nnodes(), 256), 256, 0, st>>>(D, TM, (const T*)g->mtab.ctab, g->mtab.L + 1, C);
+    if (g->nw[1] + 1 > 65535 || g->nw[2] + 1 > 65535) return fail(CG_ERR_ARG, "MappedGrid coordinates: more than 65534 cells along eta / zeta");
+    cg::launch_mapped_coords<T>(D, TM, (const T*)g->mtab.ctab, g->mtab.L + 1, C, st);
     g_launches++;
     CG_CUDA(cudaGetLastError());
     g->valid_coords = true;
@@ -826,16 +828,26 @@ int gcl_launch(cg_grid* g, const void* low, cudaStream_t st, bool* empty) {
   const void* c[3] = {nullptr, nullptr, nullptr};
   for (int a = 0; a < N; ++a) c[a] = compact ? g->cactive[a].p : g->face_cons[a].p;
   cg::Dims D = g->dims();
-  int64_t n = 1;
-  for (int d = 0; d < N; ++d) n *= hi[d] - lo[d];
-  if (g->dtype == CG_F64)
-    cg::k_gcl<double><<<launch_blocks(n, 256), 256, 0, st>>>(D, (const double*)c[0], (const double*)c[1],
-                                                             (const double*)c[2], compact, lo[0], lo[1], lo[2],
-                                                             hi[0], hi[1], hi[2], (const double*)low, g->gcl_bits);
-  else
-    cg::k_gcl<float><<<launch_blocks(n, 256), 256, 0, st>>>(D, (const float*)c[0], (const float*)c[1],
-                                                            (const float*)c[2], compact, lo[0], lo[1], lo[2], hi[0],
-                                                            hi[1], hi[2], (const float*)low, g->gcl_bits);
+  int64_t nrows = 1;
+  for (int d = 1; d < N; ++d) nrows *= hi[d] - lo[d];
+  const int64_t ext0 = hi[0] - lo[0];
+  const dim3 grid((unsigned)((ext0 + 255) / 256 > 64 ? 64 : (ext0 + 255) / 256), (unsigned)(nrows > 65535 ? 65535 : nrows));
+  auto go = [&](auto tag, auto ntag, auto ctag) {
+    using T = decltype(tag);
+    cg::k_gcl<T, decltype(ntag)::value, decltype(ctag)::value><<<grid, 256, 0, st>>>(
+        D, (const T*)c[0], (const T*)c[1], (const T*)c[2], lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], (const T*)low, g->gcl_bits);
+  };
+  auto by_profile = [&](auto tag, auto ntag) {
+    if (compact) go(tag, ntag, std::true_type{});
+    else go(tag, ntag, std::false_type{});
+  };
+  auto by_dim = [&](auto tag) {
+    if (N == 1) by_profile(tag, std::integral_constant<int, 1>{});
+    else if (N == 2) by_profile(tag, std::integral_constant<int, 2>{});
+    else by_profile(tag, std::integral_constant<int, 3>{});
+  };
+  if (g->dtype == CG_F64) by_dim(double{});
+  else by_dim(float{});
   g_launches++;
   CG_CUDA(cudaGetLastError());
   return CG_OK;

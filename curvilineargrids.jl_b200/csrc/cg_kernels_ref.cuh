@@ -522,43 +522,57 @@ __global__ void k_metrics3d_ref(Dims D, const T* ex, const T* ey, const T* ez, M
 // or on the COMPACT profile (active[axis][cell][N], entry [c]).
 // Non-negative doubles order like their bit patterns, so atomicMax on the bits.
 // ---------------------------------------------------------------------------
-template <class T>
-__global__ void k_gcl(Dims D, const T* c0, const T* c1, const T* c2, int compact, int64_t lo0, int64_t lo1,
-                      int64_t lo2, int64_t hi0, int64_t hi1, int64_t hi2, const T* low, unsigned long long* out_bits) {
+template <class T, int N, bool COMPACT>
+__global__ void __launch_bounds__(256) k_gcl(Dims D, const T* __restrict__ c0, const T* __restrict__ c1,
+                                             const T* __restrict__ c2, int64_t lo0, int64_t lo1, int64_t lo2,
+                                             int64_t hi0, int64_t hi1, int64_t hi2, const T* __restrict__ low,
+                                             unsigned long long* out_bits) {
   // `low` (may be NULL): conserved metrics of the slab axis (the last one) on the cell plane just BELOW the window,
   // [nw0 * nw1][K] — the previous rank's last plane; with it the window-local plane 0 is evaluated too (its low
-  // face along the slab axis lives on the neighbour).
+  // face along the slab axis lives on the neighbour).  N and the profile are template parameters: every per-axis
+  // quantity stays in a register (a run-time dimension count put them in local memory: 10.3 ms at 512^3).
   const T* C[3] = {c0, c1, c2};
-  const int N = D.dim;
-  const int K = compact ? N : N * N;
-  int64_t lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
-  int64_t ext[3] = {1, 1, 1}, cs[3] = {1, 1, 1};
-  for (int d = 0; d < N; ++d) ext[d] = hi[d] - lo[d];
-  cs[1] = D.nw[0];
-  cs[2] = D.nw[0] * D.nw[1];
-  const int64_t ntot = ext[0] * ext[1] * ext[2];
-  double mx[3] = {0, 0, 0};
-  bool bad[3] = {false, false, false};  // a non-finite residual: maximum(abs.(I)) of the reference propagates NaN
-  for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
-       lin += (int64_t)gridDim.x * blockDim.x) {
-    int64_t idx[3];
-    idx[0] = lo[0] + lin % ext[0];
-    const int64_t r = lin / ext[0];
-    idx[1] = lo[1] + r % ext[1];
-    idx[2] = lo[2] + r / ext[1];
-    int64_t cl = idx[0] + idx[1] * cs[1] + idx[2] * cs[2];
-    for (int c = 0; c < N; ++c) {
-      T acc = 0;
+  constexpr int K = COMPACT ? N : N * N;
+  const int64_t lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+  const int64_t ext0 = hi[0] - lo[0], ext1 = N > 1 ? hi[1] - lo[1] : 1, ext2 = N > 2 ? hi[2] - lo[2] : 1;
+  const int64_t cs[3] = {1, D.nw[0], D.nw[0] * D.nw[1]};
+  const int64_t nrows = ext1 * ext2;
+  double mx[N];
+  bool bad[N];  // a non-finite residual: maximum(abs.(I)) of the reference propagates NaN
+#pragma unroll
+  for (int c = 0; c < N; ++c) {
+    mx[c] = 0.0;
+    bad[c] = false;
+  }
+  // a block walks along rows (i fastest: coalesced), rows are distributed over blockIdx.y
+  for (int64_t row = blockIdx.y; row < nrows; row += gridDim.y) {
+    const int64_t j = N > 1 ? lo[1] + row % ext1 : 0, k = N > 2 ? lo[2] + row / ext1 : 0;
+    for (int64_t ii = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ii < ext0; ii += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t idx[3] = {lo[0] + ii, j, k};
+      const int64_t cl = idx[0] + idx[1] * cs[1] + idx[2] * cs[2];
+      T acc[N];
+#pragma unroll
+      for (int c = 0; c < N; ++c) acc[c] = T(0);
+#pragma unroll
       for (int ax = 0; ax < N; ++ax) {
-        const int e = compact ? c : (ax + N * c);
-        const T below = (ax == N - 1 && idx[ax] == 0) ? low[(cl - idx[ax] * cs[ax]) * K + e] : C[ax][(cl - cs[ax]) * K + e];
-        acc += C[ax][cl * K + e] - below;
+        const bool seam = ax == N - 1 && idx[ax] == 0;
+        const T* hi_p = C[ax] + cl * K;
+        const T* lo_p = seam ? low + (cl - idx[ax] * cs[ax]) * K : C[ax] + (cl - cs[ax]) * K;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          const int e = COMPACT ? c : (ax + N * c);
+          acc[c] += hi_p[e] - lo_p[e];  // same order as the reference: per column, axes in order
+        }
       }
-      double a = fabs((double)acc);
-      if (a > mx[c]) mx[c] = a;
-      if (!(a <= 1.7976931348623157e308)) bad[c] = true;  // NaN or Inf
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        const double a = fabs((double)acc[c]);
+        if (a > mx[c]) mx[c] = a;
+        if (!(a <= 1.7976931348623157e308)) bad[c] = true;  // NaN or Inf
+      }
     }
   }
+#pragma unroll
   for (int c = 0; c < N; ++c) {
     double v = mx[c];
     for (int o = 16; o > 0; o >>= 1) {

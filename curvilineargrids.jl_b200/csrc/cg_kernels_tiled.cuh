@@ -1020,6 +1020,372 @@ __global__ void __launch_bounds__(ZNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB :
   if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
 }
 
+// ===========================================================================
+// Kernel XZ (round 2): cell metrics + xi-face metrics + zeta-face metrics in ONE k-marching kernel (FULL profile).
+//
+// The xi kernel and the zeta kernel both march along k over the same node rows and both rebuild, per cell, the
+// eta- and xi-plane forms, the Taylor expansion and inv(F).  Fused, that work is done once (about 1300 FP64
+// instructions per warp step against 766 + 718), and — more important — the combined kernel writes 624 B per
+// cell for that arithmetic, which moves it from the FP64 issue limit to the HBM limit.  The eta faces stay in
+// k_face_zeta<SWAP> (marching along j).
+//
+// Step m of a chunk [k0, k1) works on the FRONT cell p = m + 1 (its node planes p, p+1 and the looked-ahead p+2
+// are in the ring) and writes
+//     the cell arrays and the xi-face arrays of cell p            (skipped in the last step: p = k1 is the next chunk's)
+//     the zeta-face forward / inverse metrics of the face m+1/2   (skipped in the first step m = k0 - 1)
+//     the conserved metrics of the zeta face (m-1)+1/2            (completed by the front cell's V-, one step late)
+// so a chunk runs k1 - k0 + 1 steps, m = k0-1 .. k1-1; every chunk is alike (no special first / last chunk).
+// Outputs leave in two staging phases per step through the same buffers (cell + xi, then zeta).
+// ===========================================================================
+// Shared memory per warp: node ring (3 slots) | staging (two Metric buffers + one ConservedMetric buffer, used in
+// three phases per step: cell arrays, xi-face arrays, zeta-face arrays) | parking of carried state.  The kernel
+// carries 54 values per lane from step to step; with the 72 live values of an eface6_diff that is more than 255
+// registers hold (the first version spilled 53 values per step into a 28 KB L1: 26.8 ms).  The 36 values that are
+// touched once per step (partial conserved metrics of the face below, L state of the cell below, the line-stencil
+// pipeline) are therefore parked in per-lane shared-memory slots; the ring keeps 3 slots (the plane of the NEXT
+// step is fetched once the last read of the front cell's lower plane is done) so that 8 one-warp blocks still fit
+// an SM (27 KB each).  Measured at 512^3: 21.2 ms (three TMA round trips per step; parking in an L2-resident
+// global scratch with six staging buffers instead: 24.5 ms) against 19.1 ms for k_face_xi + k_face_zeta.
+template <class T> constexpr int xz_stage_vals = 2 * stage_len<T, 10> + stage_len<T, 9>;
+constexpr int XZ_PARK = 36;  // GhP 0..8 | Lpk 9..17 | F0 18..23 | F1 24..29 | F2 30..35
+template <class T> constexpr int xz_warp_vals = RingV<T, 4, 3>::VALS + xz_stage_vals<T> + XZ_PARK * 32;
+// parked values: per-lane shared-memory slots ([value][lane]: conflict-free, no synchronisation, a lane only touches
+// its own)
+template <class T> CG_D T park_ld(const T* p) { return *p; }
+template <class T> CG_D void park_st(T* p, T v) { *p = v; }
+#ifndef CG_XZ_MINB
+#define CG_XZ_MINB 8
+#endif
+template <class T, int SCH>
+__global__ void __launch_bounds__(32, CG_XZ_MINB) k_face_xz(Dims D, const T* ex, const T* ey, const T* ez, MetricOut<T> O,
+                                                            int kchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  // carried from step to step in registers:
+  //   psi_bot : Psi^{zeta->xi} on the zeta face below the front cell (xi-face conserved metrics)
+  //   wpe, wpx : W+ of the cell below the zeta face (as in k_face_zeta)
+  // parked in shared memory: GhP (conserved metrics of the face below without the V- term), Lpk (L state below),
+  // F0, F1, F2 (line-stencil pipeline of k_face_zeta)
+  T psi_bot[6], wpe[6], wpx[6];
+  T* const wsm = reinterpret_cast<T*>(cg_dyn_smem);
+  using RingT = RingV<T, 4, 3>;
+  T* const stg = wsm + RingT::VALS;
+  T* const sg_a = stg, * const sg_b = stg + stage_len<T, 10>, * const sg_9 = stg + 2 * stage_len<T, 10>;
+  T* const sg_c = sg_a, * const sg_d = sg_b, * const sg_9b = sg_9;  // one set of buffers, three phases
+  const int lane = threadIdx.x;
+  T* const park = stg + xz_stage_vals<T> + lane;  // value v of this lane: park[32 * v]
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1];
+  const int64_t j = (int64_t)blockIdx.y;
+  if (j >= nw1) return;
+  const int64_t i0 = (int64_t)blockIdx.x * WARP_OUT;  // first output cell of the warp (lane 1)
+  const int64_t i = i0 + lane - 1;
+  const int64_t ic = i > nw0 + 1 ? nw0 + 1 : i;
+  const int nvalid = (int)(nw0 - i0 < WARP_OUT ? nw0 - i0 : WARP_OUT);
+  const int srel = lane == 0 ? 31 : lane - 1;  // staging slot: every lane writes; slots 29 .. 31 are never sent
+  const int64_t k0 = D.r0 + (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < D.r1 ? k0 + kchunk : D.r1;
+  NodeP<T> N;
+  N.q[0] = ex; N.q[1] = ey; N.q[2] = ez;
+  N.s1 = (Ix)D.se[1]; N.s2 = (Ix)D.se[2];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const Ix nbase = (Ix)(ic + 1) + (Ix)(j + 1) * N.s1 + N.s2;  // node (ic, j, plane 0)
+  const int64_t cs1 = nw0, cs2 = nw0 * nw1;
+  const int ph = (int)(i0 & (RingT::VEC - 1));
+  const RingT R{wsm + ph};
+  const Ix rg0 = (Ix)(i0 - ph + RingT::VEC * lane) + (Ix)j * N.s1 + N.s2;  // plane 0, row j-1
+  // the first step (front cell k0) needs the planes k0, k0+1, k0+2
+#pragma unroll
+  for (int pp = 0; pp < 3; ++pp) R.fetch(N, (int)(k0 + pp), rg0 + (Ix)(k0 + pp) * N.s2, lane, ph);
+  cp_async_commit();
+  const T dl0 = clamp_delta<T>(D.w0[0] + i, D.nhalo, D.gn[0]), dl1 = clamp_delta<T>(D.w0[1] + j, D.nhalo, D.gn[1]);
+  // zeta coordinate of the front cell's centre (clamp_delta in floating point: no 64-bit integers in the loop)
+  T xi_z = T(D.w0[2] + k0 + 1 - D.nhalo) + T(0.5);
+  const T hi_z = T(D.gn[2] + 1);
+  // carried state at the entry of the first step (m = k0 - 1, front cell k0): V+ of the cell k0 - 1 and the edge
+  // scalars on the zeta face below the cell k0; the zeta-face state of "cell k0 - 1" is not used (its face belongs
+  // to the previous chunk)
+  {
+    LineS<T> lm[6];
+    zlines(GlobalSrc<T>{N, nbase + (Ix)(k0 - 1) * N.s2}, lam1, lam2, lm);
+#pragma unroll
+    for (int v = 0; v < 30; ++v) park_st(park + 32 * v, T(0));
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      park_st(park + 32 * (30 + e), lm[e].vp);  // F2
+      wpe[e] = wpx[e] = T(0);
+    }
+    T wp[6], wm[6];
+    const Ix b = nbase + (Ix)(k0 - 1) * N.s2;
+    eface6<T, SCH>(zplane(N, b), zplane(N, b + N.s2), zplane(N, b + 2 * N.s2), wp, wm);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) psi_bot[e] = wp[e] + shfl_dn(wm[e], 1);
+  }
+  for (int64_t m = k0 - 1; m < k1; ++m) {
+    const int64_t p = m + 1;              // front cell
+    const bool do_x = p < k1;             // cell + xi-face outputs of the cell p
+    const bool do_z = m >= k0;            // zeta face m + 1/2 (and the conserved metrics of the face below it)
+    const int64_t cl0p = i0 + j * cs1 + p * cs2;  // first output cell of the warp in the plane p
+    const int64_t cl0m = cl0p - cs2;
+    // the node planes p .. p+2 have landed (the wait for last step's staging buffers comes right before the first
+    // staging store of this step: by then the TMA unit has long finished reading them)
+    cp_async_wait_all();
+    __syncwarp();
+    const int pp = (int)p;
+    T Gh_x[3][3], Gh_z[3][3];  // conserved metrics of the xi face of the cell p / of the zeta face m (rows 0 xi, 1 eta, 2 zeta)
+    // ---- (1) zeta faces p-1/2 (carried) and p+1/2 of the cell, for the xi face: zeta-planes p, p+1, p+2 ---------
+    if (do_x) {
+      T wp[6], wm[6];
+      eface6<T, SCH>(R.zplane(pp, 1, lane), R.zplane(pp + 1, 1, lane), R.zplane(pp + 2, 1, lane), wp, wm);
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        const T top = wp[e] + shfl_dn(wm[e], 1);
+        const T d = top - psi_bot[e];
+        psi_bot[e] = top;
+        if (e >= 3) Gh_x[0][e - 3] = d;    // active row: + (psi_top - psi_bot)[b = eta]
+        else Gh_x[1][e] = -d;              // row eta:    - (psi_top - psi_bot)[b = xi]
+      }
+    }
+    // ---- (2) eta faces j-1/2 and j+1/2 of the cell: eta-planes j-1 .. j+2, once with (u, v) = (xi, zeta) for the xi
+    //          face and once with (zeta, xi) for the zeta face; the Taylor sums of the cell from the inner two --------
+    T c[3][8];  // RAW Taylor sums of the front cell
+    {
+      const ZPair<T> p00 = R.zpair(pp, 1, lane), p01 = R.zpair(pp, 1, lane + 1), p10 = R.zpair(pp, 2, lane),
+                     p11 = R.zpair(pp, 2, lane + 1);
+      const PF<T> E1 = pair_form(p00, p01), E2 = pair_form(p10, p11);  // eta-planes j, j+1 (u = xi, v = zeta)
+      T de[3];  // sum of the four eta-edge differences: 2 (lo) + (d) of the two column pairs (round-off rule)
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        de[q] = fma(T(2), (p10.lo[q] - p00.lo[q]) + (p11.lo[q] - p01.lo[q]), (p10.d[q] - p00.d[q]) + (p11.d[q] - p01.d[q]));
+      const PF<T> E0 = pair_form(R.zpair(pp, 0, lane), R.zpair(pp, 0, lane + 1)),
+                  E3 = pair_form(R.zpair(pp, 3, lane), R.zpair(pp, 3, lane + 1));
+      T wp[6], wm[6];
+      if (do_x) {
+        eface6_diff<T, SCH>(E0, E1, E2, E3, wp, wm);  // (face j + 1/2) - (face j - 1/2), f = xi
+#pragma unroll
+        for (int col = 0; col < 3; ++col) {
+          Gh_x[0][col] -= wp[3 + col] + shfl_dn(wm[3 + col], 1);
+          Gh_x[2][col] = wp[col] + shfl_dn(wm[col], 1);
+        }
+      }
+      eface6_diff<T, SCH>(swap_uv(E0), swap_uv(E1), swap_uv(E2), swap_uv(E3), wp, wm);  // f = zeta
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        // a = eta (sigma +1, a' = xi): bsel 1 is b = xi, bsel 0 is b = zeta
+        Gh_z[2][col] = wpe[3 + col] + wm[3 + col];
+        Gh_z[0][col] = -(wpe[col] + wm[col]);
+      }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) wpe[e] = wp[e];
+      taylor_raw_e(E1, E2, de, c);  // last use of the inner eta-planes
+    }
+    // ---- (3) xi face i+1/2 for the zeta face: xi-planes i, i+1, i+2 with (u, v) = (zeta, eta) --------------------
+    {
+      const ZPair<T> a0 = R.zpair(pp, 1, lane), a1 = R.zpair(pp, 1, lane + 1), a2 = R.zpair(pp, 1, lane + 2),
+                     b0 = R.zpair(pp, 2, lane), b1 = R.zpair(pp, 2, lane + 1), b2 = R.zpair(pp, 2, lane + 2);
+      T wp[6], wm[6];
+      eface6<T, SCH>(swap_uv(pair_form(a0, b0)), swap_uv(pair_form(a1, b1)), swap_uv(pair_form(a2, b2)), wp, wm);
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        // a = xi (sigma -1, a' = eta): bsel 1 is b = eta, bsel 0 is b = zeta
+        const T px_a = wpx[3 + col] + wm[3 + col];
+        const T px_f = wpx[col] + wm[col];
+        Gh_z[2][col] -= px_a - shfl_up(px_a, 1);
+        Gh_z[1][col] = px_f - shfl_up(px_f, 1);
+      }
+#pragma unroll
+      for (int e = 0; e < 6; ++e) wpx[e] = wp[e];
+    }
+    // the front cell's lower plane has been read for the last time: the plane the NEXT step lacks goes into its slot
+    __syncwarp();
+    if (m + 1 < k1) {
+      R.fetch(N, (int)(p + 3), rg0 + (Ix)(p + 3) * N.s2, lane, ph);
+      cp_async_commit();
+    }
+    // ---- (4) inverse Jacobian of the cell: raw F = 4 F, inv gives G / 4 -------------------------------------------
+    T G[3][3], detF;
+    {
+      T F[3][3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) F[q][d] = c[q][1 << d];
+      detF = T(1.0 / 64.0) * inv3(F, G);
+    }
+    if (do_x) {
+      // ================= phase A1: cell arrays of the cell p =======================================================
+      {
+        Stage<T, 10> Scf(O.cell_fwd, cl0p, sg_a), Sci(O.cell_inv, cl0p, sg_b);
+        // cell.forward is evaluated at the clamped point (discrete_grid.jl:113-142): only halo cells differ from the
+        // centre value, so the correction is skipped by warps that hold interior cells only
+        T Ff[3][3], Gt[3][3], J = detF;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            Ff[q][d] = T(0.25) * c[q][1 << d];
+            Gt[q][d] = T(4) * G[q][d];
+          }
+        const T dl2 = (xi_z < T(1) ? T(1) : (xi_z > hi_z ? hi_z : xi_z)) - xi_z;
+        if (__any_sync(FULLMASK, dl0 != T(0)) || dl1 != T(0) || dl2 != T(0)) {
+          const T dl[3] = {dl0, dl1, dl2};
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const int e = (d + 1) % 3, g = (d + 2) % 3;
+              Ff[q][d] = T(0.25) * c[q][1 << d] + T(0.5) * (c[q][(1 << d) | (1 << e)] * dl[e] + c[q][(1 << d) | (1 << g)] * dl[g]) +
+                         c[q][7] * dl[e] * dl[g];
+            }
+          J = det3(Ff);
+        }
+        bulk_wait_read();  // last step's groups have left the staging buffers (issued most of a step ago)
+        __syncwarp();
+        put10(Scf.slot(srel), Ff, J);
+        put10(Sci.slot(srel), Gt, J);
+        fence_async_smem();
+        __syncwarp();
+        Scf.issue(nvalid, lane);
+        Sci.issue(nvalid, lane);
+        if (lane == 0) bulk_commit();
+      }
+      // ================= phase A2: xi-face arrays of the cell p ====================================================
+      T Gf[3][3], Ff[3][3], Jf;
+      {
+        // reconstructed inverse Jacobian on the xi face (states carry 1/4, see cellz_compute)
+        T Fa[3], Fb[3], L[3][3], Rr[3][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          Fa[q] = c[q][3];  // column eta of dF/d(xi)
+          Fb[q] = c[q][5];  // column zeta
+        }
+        ginv_states3_ax<0>(G, Fa, Fb, T(2) * lam1, T(4) * lam2, L, Rr);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(2) * (L[r][cc] + shfl_dn(Rr[r][cc], 1));
+        Jf = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
+      }
+      // xi line stencils (neighbours by shuffle): rows eta (+, b = zeta) and zeta (-, b = eta)
+#pragma unroll
+      for (int col = 0; col < 3; ++col) {
+        const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+#pragma unroll
+        for (int bb = 1; bb <= 2; ++bb) {
+          const LineS<T> sc = line_from_taylor_raw(c, q1, q2, 0, bb, lam1, lam2);
+          const T v = (sc.vp - T(2) * sc.u) - shfl_up(sc.vp, 1) + shfl_dn(T(2) * sc.u - sc.vm, 1) + shfl_dn(sc.vm, 2);
+          if (bb == 2) Gh_x[1][col] += T(0.5) * v;
+          else Gh_x[2][col] -= T(0.5) * v;
+        }
+      }
+      bulk_wait_read();  // the cell arrays have left the two Metric buffers
+      __syncwarp();
+      Stage<T, 10> Sff(O.face_fwd[0], cl0p, sg_c), Sfi(O.face_inv[0], cl0p, sg_d);
+      Stage<T, 9> Sfc(O.face_cons[0], cl0p, sg_9);
+      put10(Sff.slot(srel), Ff, Jf);
+      put10(Sfi.slot(srel), Gf, Jf);
+      put9(Sfc.slot(srel), Gh_x);
+      fence_async_smem();
+      __syncwarp();
+      Sff.issue(nvalid, lane);
+      Sfi.issue(nvalid, lane);
+      Sfc.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    }
+    // ================= phase B: zeta face m + 1/2 ================================================================
+    // zeta-line scalars of the front cell and its zeta-axis L / R states
+    LineS<T> ln[6];
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+      const int q1 = (col + 1) % 3, q2 = (col + 2) % 3;
+      ln[col] = line_from_taylor_raw(c, q1, q2, 2, 0, lam1, lam2);
+      ln[3 + col] = line_from_taylor_raw(c, q1, q2, 2, 1, lam1, lam2);
+    }
+    T Lz[3][3], Rz[3][3];
+    {
+      T Fa[3], Fb[3];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        Fa[q] = c[q][5];  // column xi of dF/d(zeta)
+        Fb[q] = c[q][6];  // column eta
+      }
+      ginv_states3_ax<2>(G, Fa, Fb, T(2) * lam1, T(4) * lam2, Lz, Rz);
+    }
+    if (do_z) {
+      T Go[3][3], Gf[3][3], Ff[3][3];
+      // the front cell's V- completes the conserved metrics of the face m - 1 (stored one step late)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Go[r][cc] = park_ld(park + 32 * (3 * r + cc));
+#pragma unroll
+      for (int e = 0; e < 6; ++e) {
+        const T v = T(0.5) * (park_ld(park + 32 * (18 + e)) + ln[e].vm);  // F0
+        if (e >= 3) Go[0][e - 3] += v;  // row xi: + line[b = eta]
+        else Go[1][e] -= v;             // row eta: - line[b = xi]
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Gf[r][cc] = T(2) * (park_ld(park + 32 * (9 + 3 * r + cc)) + Rz[r][cc]);
+      const T Jf = rcp(inv3(Gf, Ff));
+      bulk_wait_read();  // the xi-face arrays (or, in the last step, the previous step's arrays) have left the buffers
+      __syncwarp();
+      Stage<T, 10> Sf(O.face_fwd[2], cl0m, sg_a), Si(O.face_inv[2], cl0m, sg_b);
+      Stage<T, 9> Sc(O.face_cons[2], cl0m - cs2, sg_9b);
+      put9(Sc.slot(srel), Go);
+      put10(Sf.slot(srel), Ff, Jf);
+      put10(Si.slot(srel), Gf, Jf);
+      fence_async_smem();
+      __syncwarp();
+      Sf.issue(nvalid, lane);
+      Si.issue(nvalid, lane);
+      if (m > k0) Sc.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    }
+    // ---- carried state of the next step ----
+    xi_z += T(1);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const T f1 = park_ld(park + 32 * (24 + e)), f2 = park_ld(park + 32 * (30 + e));
+      park_st(park + 32 * (18 + e), f1 + (T(2) * ln[e].u - ln[e].vm));        // F0
+      park_st(park + 32 * (24 + e), (ln[e].vp - T(2) * ln[e].u) - f2);        // F1
+      park_st(park + 32 * (30 + e), ln[e].vp);                                // F2
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        park_st(park + 32 * (3 * r + cc), Gh_z[r][cc]);
+        park_st(park + 32 * (9 + 3 * r + cc), Lz[r][cc]);
+      }
+  }
+  {
+    // the last zeta face of the chunk needs V- of the cell k1 + 1
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
+    const GlobalSrc<T> S1{N, nbase + (Ix)(k1 + 1) * N.s2};
+    LineS<T> l2[6];
+    zlines(S1, lam1, lam2, l2);
+    T Go[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Go[r][cc] = park_ld(park + 32 * (3 * r + cc));
+#pragma unroll
+    for (int e = 0; e < 6; ++e) {
+      const T v = T(0.5) * (park_ld(park + 32 * (18 + e)) + l2[e].vm);
+      if (e >= 3) Go[0][e - 3] += v;
+      else Go[1][e] -= v;
+    }
+    Stage<T, 9> Sc(O.face_cons[2], i0 + j * cs1 + (k1 - 1) * cs2, sg_9b);
+    put9(Sc.slot(srel), Go);
+    fence_async_smem();
+    __syncwarp();
+    Sc.issue(nvalid, lane);
+    if (lane == 0) bulk_commit();
+  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
+}
+
 // Chunk length along the marching axis for `tiles` warp tiles of `per_block` warps each, `slots` resident blocks on the
 // GPU: among 1 .. extent / min_chunk chunks per tile, the count with the best (wave quantisation) x (prologue
 // amortisation) efficiency; `prologue` = cost of a chunk's set-up in steps.
@@ -1429,7 +1795,22 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     cudaStreamWaitEvent(fk->s[0], fk->start, 0);
     cudaStreamWaitEvent(fk->s[1], fk->start, 0);
   }
-  if ((mask & 1) && ((what & 1) || face)) {
+  // FULL cell+face evaluation with the xi and zeta kernels fused (k_face_xz): an experiment, OFF by default.  It is
+  // correct (the whole GPU suite passes on it) and executes 6 % fewer instructions, but it needs three staging phases
+  // per step in the shared memory that is left and measures 21.2 ms at 512^3 against 10.7 + 8.4 ms for the two
+  // kernels it replaces.  CG_FUSE_XZ=1 selects it.
+  static const bool fuse_env = getenv("CG_FUSE_XZ") && atoi(getenv("CG_FUSE_XZ")) == 1;
+  const bool fuse_xz = fuse_env && mode == MODE_FULL && (mask & 5) == 5;
+  if (fuse_xz) {
+    const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)D.nw[1];
+    const int kchunk = chunk_of((int64_t)gx * gy, nplanes);
+    const dim3 grid(gx, gy, (unsigned)((nplanes + kchunk - 1) / kchunk));
+    const int smem = xz_warp_vals<T> * (int)sizeof(T);
+    attr_ok &= cudaFuncSetAttribute(k_face_xz<T, SCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+    k_face_xz<T, SCH><<<grid, 32, smem, st>>>(D, ex, ey, ez, O, kchunk);
+    ++n;
+  }
+  if (!fuse_xz && (mask & 1) && ((what & 1) || face)) {
     const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + XWY - 1) / XWY);
     const int64_t xslots = 148LL * (mode == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) * 4 / XWY;
     const int kchunk = CG_PICK_CHUNK ? pick_chunk((int64_t)gx * gy, nplanes, xslots, 64, 1.5) : chunk_of((int64_t)gx * gy, nplanes);
@@ -1454,7 +1835,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
     else launch_zeta(k_face_zeta<T, SCH, true, MODE_GENERIC>, zeta_warp_vals<T, MODE_GENERIC>, grid, jchunk);
     ++n;
   }
-  if ((mask & 4) && face) {
+  if (!fuse_xz && (mask & 4) && face) {
     if (fk) zst = fk->s[1];
     const unsigned gy = (unsigned)((D.nw[1] + ZWY - 1) / ZWY);
     const int kchunk = CG_PICK_CHUNK ? pick_chunk((int64_t)gxz * gy, nplanes, zslots, 64, 3.0) : chunk_of((int64_t)gxz * gy, nplanes);

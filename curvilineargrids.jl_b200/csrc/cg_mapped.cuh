@@ -852,58 +852,84 @@ __global__ void k_mapped_ctab(Dims D, MTerms TM, T* ctab, int64_t L1) {
   }
 }
 
-template <class T>
-__global__ void __launch_bounds__(256) k_mapped_coords(Dims D, MTerms TM, const T* __restrict__ ctab, int64_t L1,
+// one thread per node; blockIdx.y / .z are the node row and plane (no divisions), DIM is a template parameter so
+// that every per-axis quantity stays in a register
+template <class T, int DIM>
+__global__ void __launch_bounds__(128) k_mapped_coords(Dims D, MTerms TM, const T* __restrict__ ctab, int L1,
                                                        CoordOut<T> O) {
-  int64_t nn[3] = {1, 1, 1};
-  for (int d = 0; d < D.dim; ++d) nn[d] = D.nw[d] + 1;
-  const int64_t ntot = nn[0] * nn[1] * nn[2];
-  for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
-       lin += (int64_t)gridDim.x * blockDim.x) {
-    int64_t n[3], r = lin;
-    n[0] = r % nn[0];
-    r /= nn[0];
-    n[1] = r % nn[1];
-    n[2] = r / nn[1];
-    bool is_cell = true;
-    int64_t clin = 0, cst = 1;
-    for (int d = 0; d < D.dim; ++d) {
-      if (n[d] >= D.nw[d]) is_cell = false;
-      clin += n[d] * cst;
-      cst *= D.nw[d];
-    }
-    T qn[3] = {0, 0, 0}, qc[3] = {0, 0, 0}, qf[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int m = 0; m < TM.n; ++m) {
-      T fn[3], fc[3], fh[3];  // factor at node I, centre I, node I + 1 (the face position) per axis
+  const int n0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n1 = DIM > 1 ? (int)blockIdx.y : 0, n2 = DIM > 2 ? (int)blockIdx.z : 0;
+  const int nw0 = (int)D.nw[0], nw1 = DIM > 1 ? (int)D.nw[1] : 1, nw2 = DIM > 2 ? (int)D.nw[2] : 1;
+  if (n0 > nw0) return;
+  const int n[3] = {n0, n1, n2};
+  const bool is_cell = n0 < nw0 && (DIM < 2 || n1 < nw1) && (DIM < 3 || n2 < nw2);
+  const int64_t lin = n0 + (int64_t)(nw0 + 1) * (n1 + (int64_t)(DIM > 1 ? nw1 + 1 : 1) * n2);
+  const int64_t clin = n0 + (int64_t)nw0 * (n1 + (int64_t)nw1 * n2);
+  T qn[DIM], qc[DIM], qf[DIM][DIM];
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const T* b = ctab + ((int64_t)(m * 3 + d) * L1 + n[d]) * 2;
+  for (int c = 0; c < DIM; ++c) {
+    qn[c] = qc[c] = T(0);
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) qf[a][c] = T(0);
+  }
+  for (int m = 0; m < TM.n; ++m) {
+    T fn[DIM], fc[DIM], fh[DIM];  // factor at node I, centre I, node I + 1 (the face position) per axis
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      const T* b = ctab + ((m * 3 + d) * L1 + n[d]) * 2;
+      if constexpr (sizeof(T) == 8) {
+        const double2 v = *reinterpret_cast<const double2*>(b);  // (node I, centre I): 16-B aligned pair
+        fn[d] = v.x;
+        fc[d] = v.y;
+      } else {
         fn[d] = b[0];
         fc[d] = b[1];
-        fh[d] = (d < D.dim && n[d] < D.nw[d]) ? b[2] : T(1);
       }
-      const T c = T(TM.t[m].coef);
-      const int q = TM.t[m].coord;
-      const T vn = c * fn[0] * fn[1] * fn[2], vc = c * fc[0] * fc[1] * fc[2];
-      const T v0 = c * fh[0] * fc[1] * fc[2], v1 = c * fc[0] * fh[1] * fc[2], v2 = c * fc[0] * fc[1] * fh[2];
-#pragma unroll
-      for (int qq = 0; qq < 3; ++qq)
-        if (qq == q) {
-          qn[qq] += vn;
-          qc[qq] += vc;
-          qf[0][qq] += v0;
-          qf[1][qq] += v1;
-          qf[2][qq] += v2;
-        }
+      fh[d] = b[2];  // node I + 1 (one entry of slack follows the last node)
     }
-    for (int c = 0; c < D.dim; ++c) {
-      if (O.node[c]) O.node[c][lin] = qn[c];
-      if (!is_cell) continue;
+    const T c = T(TM.t[m].coef);
+    const int q = TM.t[m].coord;
+    T vn = c, vc = c;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+      vn *= fn[d];
+      vc *= fc[d];
+    }
+    T vf[DIM];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+      vf[a] = c;
+#pragma unroll
+      for (int d = 0; d < DIM; ++d) vf[a] *= (d == a ? fh[d] : fc[d]);
+    }
+#pragma unroll
+    for (int qq = 0; qq < DIM; ++qq)
+      if (qq == q) {
+        qn[qq] += vn;
+        qc[qq] += vc;
+#pragma unroll
+        for (int a = 0; a < DIM; ++a) qf[a][qq] += vf[a];
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < DIM; ++c) {
+    if (O.node[c]) O.node[c][lin] = qn[c];
+    if (is_cell) {
       if (O.centroid[c]) O.centroid[c][clin] = qc[c];
-      for (int a = 0; a < D.dim; ++a)
+#pragma unroll
+      for (int a = 0; a < DIM; ++a)
         if (O.face[a][c]) O.face[a][c][clin] = qf[a][c];
     }
   }
+}
+template <class T>
+inline void launch_mapped_coords(const Dims& D, const MTerms& TM, const T* ctab, int64_t L1, const CoordOut<T>& O,
+                                 cudaStream_t st) {
+  const dim3 grid((unsigned)((D.nw[0] + 1 + 127) / 128), D.dim > 1 ? (unsigned)(D.nw[1] + 1) : 1u,
+                  D.dim > 2 ? (unsigned)(D.nw[2] + 1) : 1u);
+  if (D.dim == 3) k_mapped_coords<T, 3><<<grid, 128, 0, st>>>(D, TM, ctab, (int)L1, O);
+  else if (D.dim == 2) k_mapped_coords<T, 2><<<grid, 128, 0, st>>>(D, TM, ctab, (int)L1, O);
+  else k_mapped_coords<T, 1><<<grid, 128, 0, st>>>(D, TM, ctab, (int)L1, O);
 }
 
 // ---------------------------------------------------------------------------
