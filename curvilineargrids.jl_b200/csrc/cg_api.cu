@@ -300,19 +300,32 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
   const int64_t nc = g->ncells();
   const T* tab = (const T*)g->mtab.tab;
   const T* ftab = (const T*)g->mtab.ftab;
+  bool adtl_done = false;
   if (N == 1)
     cg::k_mapped_metrics1d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, ftab, g->mtab.L, O, g->scheme, what);
   else if (N == 2)
     cg::k_mapped_metrics2d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
                                                                       g->scheme, what);
-  else if ((what & 3) == 3 && O.cell_fwd && O.cell_inv && O.face_cons[0] && O.face_fwd[0] && O.face_inv[0] && !O.cjac &&
-           !O.cactive[0])
-    cg::launch_mapped_metrics3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
-  else
-    cg::k_mapped_metrics3d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
-                                                                      g->scheme, what);
+  else {
+    const bool full_cf = (what & 3) == 3 && O.cell_fwd && O.cell_inv && O.face_cons[0] && O.face_fwd[0] && O.face_inv[0] &&
+                         !O.cjac && !O.cactive[0];
+    bool ok = true;
+    if (full_cf && g->adtl) {
+      // ADThomasLombardMetric: its own kernel (active rows + face-centre Jacobians, no reconstruction of inv F)
+      ok = cg::launch_mapped_adtl3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, (const T*)g->mtab.fhalf, g->mtab.L, O, st);
+      adtl_done = true;
+    } else if (full_cf) {
+      ok = cg::launch_mapped_metrics3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
+    } else {
+      cg::k_mapped_metrics3d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
+                                                                        g->scheme, what);
+    }
+    if (!ok) return fail(CG_ERR_CUDA, "MappedGrid kernel: cannot set the shared-memory size");
+  }
   g_launches++;
-  if (g->adtl && (what & CG_WHAT_FACE) && N == 3 && g->profile == CG_PROFILE_FULL) {
+  // other output configurations of ADThomasLombardMetric (face-only refresh, COMPACT): CurvatureCorrected
+  // evaluation, then the face arrays are overwritten (COMPACT stores the active rows only: nothing to overwrite)
+  if (g->adtl && !adtl_done && (what & CG_WHAT_FACE) && N == 3 && g->profile == CG_PROFILE_FULL) {
     cg::k_mapped_adtl_faces<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, ftab, (const T*)g->mtab.fhalf,
                                                                        g->mtab.L + 1, O);
     g_launches++;

@@ -31,6 +31,10 @@ namespace cg {
 #ifndef CG_COMPACT_MINB
 #define CG_COMPACT_MINB 3
 #endif
+#ifndef CG_XI_COMPACT_MINB
+#define CG_XI_COMPACT_MINB 2  // blocks (of 4 warps) per SM of the COMPACT xi kernel: at 3 (168 registers) it spills since the
+                              // forms take first differences between neighbouring nodes (6.2 -> 5.0 ms at 512^3)
+#endif
 #ifndef CG_WY
 #define CG_WY 4
 #endif
@@ -495,7 +499,7 @@ CG_D void put9(T* o, const T (&M)[3][3]) {
 template <class T, int MODE> constexpr int xi_warp_vals =
     RingV<T, 4, 4>::VALS + (MODE == MODE_COMPACT ? 0 : 4 * stage_len<T, 10> + stage_len<T, 9>);
 template <class T, int SCH, int MODE>
-__global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) * 4 / XWY) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
+__global__ void __launch_bounds__(XNT, (MODE == MODE_COMPACT ? CG_XI_COMPACT_MINB : CG_MINB) * 4 / XWY) k_face_xi(Dims D, const T* ex, const T* ey, const T* ez,
                                                          MetricOut<T> O, int what, int kchunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
   const int lane = threadIdx.x;
@@ -1812,7 +1816,7 @@ inline int launch3d_scheme(const Dims& D, const T* ex, const T* ey, const T* ez,
   }
   if (!fuse_xz && (mask & 1) && ((what & 1) || face)) {
     const unsigned gx = (unsigned)((D.nw[0] + WARP_OUT - 1) / WARP_OUT), gy = (unsigned)((D.nw[1] + XWY - 1) / XWY);
-    const int64_t xslots = 148LL * (mode == MODE_COMPACT ? CG_COMPACT_MINB : CG_MINB) * 4 / XWY;
+    const int64_t xslots = 148LL * (mode == MODE_COMPACT ? CG_XI_COMPACT_MINB : CG_MINB) * 4 / XWY;
     const int kchunk = CG_PICK_CHUNK ? pick_chunk((int64_t)gx * gy, nplanes, xslots, 64, 1.5) : chunk_of((int64_t)gx * gy, nplanes);
     const dim3 grid(gx, gy, (unsigned)((nplanes + kchunk - 1) / kchunk));
     if (mode == MODE_FULL) launch_xi(k_face_xi<T, SCH, MODE_FULL>, xi_warp_vals<T, MODE_FULL>, grid, kchunk);

@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(32 * MWY, CG_MAPPED_MINB / MWY) k_mapped_metri
 }
 
 template <class T>
-inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
+inline bool launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
                                            int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
   const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT), gy = (unsigned)((D.nw[1] + MWY - 1) / MWY);
   // 8 warps per SM: chunks along k so that the last wave is (nearly) full (7.5 waves -> 15 at 512^3)
@@ -657,11 +657,159 @@ inline void launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, cons
   const int kchunk = pick_chunk((int64_t)gx * gy, D.nw[2], 148LL * CG_MAPPED_MINB / MWY, 32, 0.4);
 #endif
   const int smem = MWY * mapped_stage_vals<T> * (int)sizeof(T);
-  cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (cudaFuncSetAttribute(k_mapped_metrics3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
   k_mapped_metrics3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), dim3(32, MWY), smem, st>>>(
       D, TM, coord_terms(TM), PR, tab, ftab, L, O, scheme, kchunk);
+  return true;
 }
 
+
+// ---------------------------------------------------------------------------
+// ADThomasLombardMetric as its OWN kernel (metrics.jl:607-668 closures, pair tables :2336-3080, fill :3082-3188), FULL
+// profile.  What the scheme stores per face is less than the reconstruction schemes and needs no neighbour cell:
+//   forward = the mapping's Jacobian AT THE FACE CENTRE (:3162-3168), inverse = inv, J = det,
+//   conserved = the active row only (:3174-3182), rows of the other two axes are zero.
+// The active row is the same sum over term pairs of triple products of 1-D operator-table values as in
+// k_mapped_metrics3d_staged (outer reconstruction along the face axis and the two cell-centred differences act on
+// different axes, so their order does not matter: the reference's pair tables reconstruct first, its closure graph
+// differences first, and its test asserts the two to agree at 1e-12, test_3d_continuous.jl:296-297).  No inverse-
+// Jacobian reconstruction, no inactive rows: about a third of the arithmetic of the CurvatureCorrected kernel, no
+// carried state, 16 one-warp blocks per SM; the kernel is bound by its 856 B of output per cell.
+// fhalf = the factor tables at centre + 1/2 (the high-side face position along an axis).
+// ---------------------------------------------------------------------------
+#ifndef CG_ADTL_MINB
+#define CG_ADTL_MINB 16
+#endif
+template <class T>
+__global__ void __launch_bounds__(32, CG_ADTL_MINB) k_mapped_adtl3d_staged(Dims D, MTerms TM, MPairs PR,
+                                                                            const T* __restrict__ tab,
+                                                                            const T* __restrict__ ftab,
+                                                                            const T* __restrict__ fhalf, int64_t L,
+                                                                            MetricOut<T> O, int kchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  const int64_t L1 = L + 1;
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.y;
+  if (j >= nw1) return;
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int nvalid = (int)(nw0 - i0 < 32 ? nw0 - i0 : 32);
+  const int64_t i = i0 + lane < nw0 ? i0 + lane : nw0 - 1;  // lanes past the row end repeat the last cell (never sent)
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  T* const b10 = reinterpret_cast<T*>(cg_dyn_smem);
+  T* const b9 = b10 + 2 * stage_len<T, 10>;
+  // F[q][d] = sum over the terms of coordinate q of coef * prod_ax f_ax^(ax == d) with the factor values of axis `fa`
+  // taken at the face position (fhalf) when fa >= 0
+  auto jacobian = [&](const int64_t (&ix)[3], int fa, T (&F)[3][3]) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) F[q][d] = T(0);
+    for (int m = 0; m < TM.n; ++m) {
+      T a[3][2];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const T* tb = (d == fa ? fhalf : ftab) + ((int64_t)(m * 3 + d) * L1 + ix[d]) * 4;
+        if constexpr (sizeof(T) == 8) {
+          const double2 w = __ldg(reinterpret_cast<const double2*>(tb));
+          a[d][0] = w.x;
+          a[d][1] = w.y;
+        } else {
+          a[d][0] = __ldg(tb);
+          a[d][1] = __ldg(tb + 1);
+        }
+      }
+      const T c = T(TM.t[m].coef);
+      const int q = TM.t[m].coord;
+      const T v0 = c * a[0][1] * a[1][0] * a[2][0], v1 = c * a[0][0] * a[1][1] * a[2][0], v2 = c * a[0][0] * a[1][0] * a[2][1];
+#pragma unroll
+      for (int qq = 0; qq < 3; ++qq)
+        if (qq == q) {
+          F[qq][0] += v0;
+          F[qq][1] += v1;
+          F[qq][2] += v2;
+        }
+    }
+  };
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t ix[3] = {i, j, m};
+    const int64_t cl0 = i0 + nw0 * (j + nw1 * m);
+    T F[3][3], G[3][3];
+    // ---- cell arrays ----
+    jacobian(ix, -1, F);
+    T J = inv3(F, G);
+    bulk_wait_read();  // the TMA unit has finished reading the previous phase (lanes > 0 own no groups)
+    __syncwarp();
+    {
+      Stage<T, 10> Scf(O.cell_fwd, cl0, b10), Sci(O.cell_inv, cl0, b10 + stage_len<T, 10>);
+      put10(Scf.slot(lane), F, J);
+      put10(Sci.slot(lane), G, J);
+      fence_async_smem();
+      __syncwarp();
+      Scf.issue(nvalid, lane);
+      Sci.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    }
+    // ---- active rows: sums over the term pairs of triple products of 1-D table values ----
+    T act[3][3];  // [face][col]
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) act[f][cc] = T(0);
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      for (int p = PR.cstart[cc]; p < PR.cstart[cc + 1]; ++p) {
+        T tv[3][OP_COUNT];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) ldg_vec<T, OP_COUNT>(tab + ((int64_t)(p * 3 + d) * L + ix[d]) * OP_COUNT, tv[d]);
+        const T C = T(PR.coef[p]);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          const int s = (f + 1) % 3, t = (f + 2) % 3;
+          act[f][cc] += C * tv[f][OP_E0] * (tv[s][OP_V1] * tv[t][OP_D0] - tv[s][OP_D0] * tv[t][OP_V1]);
+        }
+      }
+    }
+    // ---- one phase per face axis ----
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      jacobian(ix, f, F);
+      J = inv3(F, G);
+      T Gh[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Gh[r][cc] = r == f ? act[f][cc] : T(0);
+      bulk_wait_read();
+      __syncwarp();
+      Stage<T, 10> Sff(O.face_fwd[f], cl0, b10), Sfi(O.face_inv[f], cl0, b10 + stage_len<T, 10>);
+      Stage<T, 9> Sfc(O.face_cons[f], cl0, b9);
+      put9(Sfc.slot(lane), Gh);
+      put10(Sff.slot(lane), F, J);
+      put10(Sfi.slot(lane), G, J);
+      fence_async_smem();
+      __syncwarp();
+      Sff.issue(nvalid, lane);
+      Sfi.issue(nvalid, lane);
+      Sfc.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    }
+  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
+}
+
+template <class T>
+inline bool launch_mapped_adtl3d_staged(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
+                                        const T* fhalf, int64_t L, const MetricOut<T>& O, cudaStream_t st) {
+  const unsigned gx = (unsigned)((D.nw[0] + 31) / 32), gy = (unsigned)D.nw[1];
+  const int kchunk = pick_chunk((int64_t)gx * gy, D.nw[2], 148LL * CG_ADTL_MINB, 32, 0.2);
+  const int smem = mapped_stage_vals<T> * (int)sizeof(T);
+  if (cudaFuncSetAttribute(k_mapped_adtl3d_staged<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
+  k_mapped_adtl3d_staged<T><<<dim3(gx, gy, (unsigned)((D.nw[2] + kchunk - 1) / kchunk)), 32, smem, st>>>(
+      D, TM, PR, tab, ftab, fhalf, L, O, kchunk);
+  return true;
+}
 
 // ---------------------------------------------------------------------------
 // ADThomasLombardMetric (metrics.jl:607-668, fill :3082-3188) on top of the CurvatureCorrected evaluation: the face

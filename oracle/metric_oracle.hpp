@@ -405,16 +405,100 @@ inline void face_metric(const M& m, double t, int axis, const Pt<real>& p, real*
   inv[N * N] = J;
 }
 
-// ADThomasLombardMetric, 3-D (metrics.jl:607-668 closures, fill :3082-3188).  Face forward metric = the mapping's
-// Jacobian AT THE FACE CENTRE (edge.jacobian(t, xi_f, eta_f, zeta_f), :3162-3168), inverse = inv(F), J = det(F);
-// the conserved matrix carries only the active row (:3174-3182).  The active row is restated through the
-// equivalence the reference's own test asserts against CurvatureCorrectedReconstruction
-// (test_3d_continuous.jl:296-297, |difference| < 1e-12), not through the pair-table assembly (:2336-3080).
+// ADThomasLombardMetric, 3-D (metrics.jl:607-668 closures, pair tables :2336-3080, fill :3082-3188).
+//
+// The reference does NOT evaluate the Thomas-Lombard closure graph here.  Per potential P = (d_b' q1) q2
+// (_ad_thomas_lombard_potential_from_values, :2377-2399), face-normal axis a and difference axis b it tabulates, at
+// every CELL CENTRE, the nine mixed derivatives (P, P_a, P_aa, P_b, P_ab, P_aab, P_bb, P_abb, P_aabb) by seeding
+// ForwardDiff duals along a and b (:2676-2701), then
+//   1. reconstructs value / b-derivative / second b-derivative to the a-face from the cells I and I + e_a
+//      (_edge_potential_values_from_pair_table :2889-2905 with _edge_reconstruct, CurvatureCorrected),
+//   2. takes the array derivative along b: edge_high - edge_low of those face values at I - e_b, I, I + e_b
+//      (_array_derivative_from_pair_table :2907-2935).
+// i.e. outer reconstruction first, cell-centred difference second — the opposite order of Cache3 (which is why the
+// reference's test asserts the two to agree at 1e-12, test_3d_continuous.jl:296-297).  This struct restates THAT
+// order; tests compare it with Cache3<M, CURVATURE> (the equivalence the reference asserts) and with the CUDA path.
+template <class M>
+struct AdtlPairTable {
+  const M& m;
+  double t;
+
+  // potential (d_bp q1) q2 at p, for any (nested dual) number type
+  template <class S>
+  S potential(int q1, int bp, int q2, const Pt<S>& p) const {
+    Cache3<M, CURVATURE> c{m, t};
+    return c.template potential<S>(q1, bp, q2, p);
+  }
+
+  // the nine numbers at a cell centre: out[n][k] = d_b^k d_a^n P,  n, k in 0..2
+  void nine(int q1, int bp, int q2, int a, int b, const Pt<real>& p, real (&out)[3][3]) const {
+    // h_n(p) = d_a^n P(p) as a callable on any number type, by AD along a
+    auto jets_a = [&](const auto& q) {
+      using Q = typename std::decay<decltype(q[0])>::type;
+      auto f = [&](const auto& r) {
+        using R = typename std::decay<decltype(r[0])>::type;
+        Vals<R, 1> v;
+        v.e[0] = this->template potential<R>(q1, bp, q2, r);
+        return v;
+      };
+      Vals<Q, 1> v0, v1, v2;
+      value_derivative_and_second_derivative<1>(f, a, q, v0, v1, v2);
+      Vals<Q, 3> o;
+      o.e[0] = v0.e[0];
+      o.e[1] = v1.e[0];
+      o.e[2] = v2.e[0];
+      return o;
+    };
+    Vals<real, 3> v, d, dd;
+    value_derivative_and_second_derivative<3>(jets_a, b, p, v, d, dd);
+    for (int n = 0; n < 3; ++n) {
+      out[n][0] = v.e[n];
+      out[n][1] = d.e[n];
+      out[n][2] = dd.e[n];
+    }
+  }
+
+  static real recon(real v0, real d0, real dd0, real v1, real d1, real dd1) {  // metrics.jl:141-178, Curvature
+    const double w = 1.0 / 12.0;
+    return 0.5 * ((v0 + 0.5 * d0 + w * dd0) + (v1 - 0.5 * d1 + w * dd1));
+  }
+
+  // (Q, Q_b, Q_bb) on the a-face between the cells at p and p + e_a
+  void face_vals(int q1, int bp, int q2, int a, int b, const Pt<real>& p, real (&Q)[3]) const {
+    real lo[3][3], hi[3][3];
+    Pt<real> pa = p;
+    pa[a] = pa[a] + 1.0;
+    nine(q1, bp, q2, a, b, p, lo);
+    nine(q1, bp, q2, a, b, pa, hi);
+    for (int k = 0; k < 3; ++k) Q[k] = recon(lo[0][k], lo[1][k], lo[2][k], hi[0][k], hi[1][k], hi[2][k]);
+  }
+
+  // array derivative along b of the face-reconstructed potential (:2907-2935)
+  real term(int q1, int bp, int q2, int a, int b, const Pt<real>& p) const {
+    Pt<real> pm = p, pp = p;
+    pm[b] = pm[b] - 1.0;
+    pp[b] = pp[b] + 1.0;
+    real Q0[3], Qp[3], Qm[3];
+    face_vals(q1, bp, q2, a, b, p, Q0);
+    face_vals(q1, bp, q2, a, b, pp, Qp);
+    face_vals(q1, bp, q2, a, b, pm, Qm);
+    return recon(Q0[0], Q0[1], Q0[2], Qp[0], Qp[1], Qp[2]) - recon(Qm[0], Qm[1], Qm[2], Q0[0], Q0[1], Q0[2]);
+  }
+
+  // active row of the conserved metrics on the face `axis`: row r = axis of metrics.jl:774-782,
+  //   M^[r][c] = D_u[(d_s q1) q2] - D_s[(d_u q1) q2],  s = r + 1, u = r + 2 (cyclic), (q1, q2) = (c + 1, c + 2)
+  real active(int axis, int c, const Pt<real>& p) const {
+    const int q1 = (c + 1) % 3, q2 = (c + 2) % 3, s = (axis + 1) % 3, u = (axis + 2) % 3;
+    return term(q1, s, q2, axis, u, p) - term(q1, u, q2, axis, s, p);
+  }
+};
+
+// Face forward metric = the mapping's Jacobian AT THE FACE CENTRE (edge.jacobian(t, xi_f, eta_f, zeta_f), :3162-3168),
+// inverse = inv(F), J = det(F); the conserved matrix carries only the active row (:3174-3182), assembled from the
+// pair tables above.
 template <class M>
 inline void face_metric_adtl3(const M& m, double t, int axis, const Pt<real>& p, real* fwd, real* inv, real* cons) {
-  real G[9], Ghat[9];
-  Cache3<M, 2> c{m, t};
-  c.face(axis, p, G, Ghat);
+  AdtlPairTable<M> tab{m, t};
   Pt<real> pf = p;
   pf[axis] += 0.5;  // _face_center_3d (:3271-3283): the cell centre moved half a cell along the face axis
   const Vals<real, 9> F = ad_jacobian<3>(m, t, pf);
@@ -425,7 +509,7 @@ inline void face_metric_adtl3(const M& m, double t, int axis, const Pt<real>& p,
   for (int k = 0; k < 9; ++k) {
     fwd[k] = Fm[k];
     inv[k] = Gm[k];
-    cons[k] = (k % 3 == axis) ? Ghat[k] : 0.0;  // column-major: row index = k % 3
+    cons[k] = (k % 3 == axis) ? tab.active(axis, k / 3, p) : real(0.0);  // column-major: row = k % 3, column = k / 3
   }
   fwd[9] = J;
   inv[9] = J;

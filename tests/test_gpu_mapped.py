@@ -114,8 +114,11 @@ def test_mapped_fp32_and_compact(cg, oracle):
 
 @pytest.mark.parametrize("name", ["wavy3d", "sphere3d", "rtp3d"])
 def test_mapped_ad_thomas_lombard(cg, oracle, name):
-    """ADThomasLombardMetric (metrics.jl:607-668, 3082-3188; test_3d_continuous.jl:167-300): GCL < 1e-12, active rows
-    equal to the CurvatureCorrected rows, inactive rows zero, face forward metric = Jacobian at the face centre."""
+    """ADThomasLombardMetric (metrics.jl:607-668, pair tables :2336-3080, fill :3082-3188; test_3d_continuous.jl:167-300)
+    through its own kernel (k_mapped_adtl3d_staged) against the oracle's INDEPENDENT restatement of the pair-table
+    assembly (outer reconstruction first, array difference second: oracle/metric_oracle.hpp AdtlPairTable): GCL < 1e-12,
+    active rows equal to the CurvatureCorrected rows at the reference's 1e-12, inactive rows zero, face forward metric =
+    Jacobian at the face centre."""
     terms, celldims, h = _cases(cg.workloads)[name]
     t = 0.37
     ref = oracle.mapped_eval(terms, t, celldims, h, "adtl")
@@ -124,14 +127,27 @@ def test_mapped_ad_thomas_lombard(cg, oracle, name):
     assert_metrics_close(got, ref, rtol=RTOL_F64, label=f"{name} adtl")
     assert max(cg.gcl(g)) < 1e-12                                  # test_3d_continuous.jl:296
     cur = grid_outputs(cg, cg.MappedGrid(terms, {}, celldims, h, conserved_metric_scheme="curvature", t=t))
+    ocur = oracle.mapped_eval(terms, t, celldims, h, "curvature", what=2)
+    rows = np.arange(9) % 3                                        # column-major: row index of entry k
     for ax in range(3):
-        a = got["face_cons"][ax].reshape(-1, 3, 3, order="F") if False else got["face_cons"][ax]
-        c = cur["face_cons"][ax]
-        rows = np.arange(9) % 3                                    # column-major: row index of entry k
-        assert np.array_equal(a[..., rows == ax], c[..., rows == ax])   # :297 (< 1e-12 there; identical here)
+        a, c = got["face_cons"][ax], cur["face_cons"][ax]
+        scale = np.abs(c).max()
+        assert np.abs(a[..., rows == ax] - c[..., rows == ax]).max() <= 1e-12 * scale   # :297
         assert not a[..., rows != ax].any()
+        # the two restatements of the oracle (pair tables / closure graph) agree as well
+        assert np.abs(ref["face_cons"][ax][..., rows == ax] - ocur["face_cons"][ax][..., rows == ax]).max() <= 1e-12 * scale
     # the face forward metric differs from the reconstructed one of the Curvature scheme on a curved mesh
     assert np.abs(got["face_fwd"] - cur["face_fwd"]).max() > 0
+    # a face-only refresh and the COMPACT profile go through the CurvatureCorrected evaluation + overwrite
+    g2 = cg.MappedGrid(terms, {}, celldims, h, conserved_metric_scheme=cg.ADThomasLombardMetric, t=t, cache_mode="lazy")
+    cg.refresh_cell_metrics(g2)
+    cg.refresh_face_metrics(g2)
+    assert_metrics_close(grid_outputs(cg, g2), ref, rtol=RTOL_F64, label=f"{name} adtl separate refreshes")
+    gc = cg.MappedGrid(terms, {}, celldims, h, conserved_metric_scheme=cg.ADThomasLombardMetric, t=t, profile="compact")
+    for ax in range(3):
+        want = np.stack([ref["face_cons"][ax][:, ax + 3 * c] for c in range(3)], axis=1)
+        gotc = cg.face_metrics(gc)[ax].reshape(-1, 3).cpu().numpy()
+        assert np.abs(gotc - want).max() <= 1e-12 * np.abs(want).max()
 
 
 def test_ad_thomas_lombard_dimension_and_grid_kind(cg, oracle):
