@@ -30,7 +30,8 @@ EXPORTS = [
     "cg_grid_last_eval_ms", "cg_grid_face_flux_geometry", "cg_grid_cell_volumes", "cg_grid_pad_planes", "cg_grid_eval_planes", "cg_grid_update_from_host", "cg_copy_index_pairs", "cg_discrete_metrics_host", "cg_legacy_meg6_update_3d", "cg_legacy_meg6_update_2d", "cg_legacy_last_error",
     "cg_grid_coords_valid", "cg_grid_gcl_max_seam", "cg_grid_seam_plane", "cg_nccl_unique_id", "cg_nccl_comm_create",
     "cg_nccl_comm_destroy", "cg_halo_exchange_begin", "cg_halo_exchange_end", "cg_grid_step_overlapped",
-    "cg_grid_gcl_max_dist", "cg_grid_update_from_host_dist",
+    "cg_grid_gcl_max_dist", "cg_grid_update_from_host_dist", "cg_transfer_index_pairs", "cg_basis_transfer_matrices",
+    "cg_nccl_sendrecv",
 ]
 
 _lib = None

@@ -821,6 +821,164 @@ int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const v
 
 extern "C++" {
 namespace {
+// Vector / tensor ghost-cell fill (transfer.jl:461-488): element p of the plan carries its own basis-transfer matrix
+// A_p (N x N, column-major like SMatrix); vector: v_dst = A v_src, tensor: T_dst = A T_src A^T.  Fields are AoS like
+// Julia's Array{SVector{N,T}} / Array{SMatrix{N,N,T}}: K = N or N*N consecutive values per cell.  A == nullptr: identity.
+template <class E, int N, int KIND>
+__global__ void __launch_bounds__(256) k_transfer_index_pairs(E* __restrict__ dst, const E* __restrict__ src,
+                                                              const int64_t* __restrict__ dst_idx,
+                                                              const int64_t* __restrict__ src_idx,
+                                                              const E* __restrict__ A, int64_t n) {
+  constexpr int K = KIND == 1 ? N : N * N;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    E v[K], a[N][N];
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = src[src_idx[p] * K + k];
+#pragma unroll
+    for (int c = 0; c < N; ++c)
+#pragma unroll
+      for (int r = 0; r < N; ++r) a[r][c] = A ? A[p * (N * N) + r + N * c] : (r == c ? E(1) : E(0));
+    E o[K];
+    if (KIND == 1) {
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        E acc = E(0);
+#pragma unroll
+        for (int c = 0; c < N; ++c) acc += a[r][c] * v[c];
+        o[r] = acc;
+      }
+    } else {
+      E t[N][N];  // A * T (T column-major: T[r][c] = v[r + N c])
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          E acc = E(0);
+#pragma unroll
+          for (int m = 0; m < N; ++m) acc += a[r][m] * v[m + N * c];
+          t[r][c] = acc;
+        }
+#pragma unroll
+      for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+          E acc = E(0);
+#pragma unroll
+          for (int m = 0; m < N; ++m) acc += t[r][m] * a[c][m];
+          o[r + N * c] = acc;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) dst[dst_idx[p] * K + k] = o[k];
+  }
+}
+
+// basis -> Cartesian matrix Q (grid_traits_api.jl:215-258): identity for a Cartesian basis, the unit vectors
+// (e_r, e_theta, e_phi) for SphericalCS + SphericalBasis (N = 2: [s c; c -s], N = 3: the usual spherical triad)
+template <class E, int N>
+__device__ __forceinline__ void basis_to_cartesian(int basis, const E (&q)[3], E (&Q)[N][N]) {
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int c = 0; c < N; ++c) Q[r][c] = r == c ? E(1) : E(0);
+  if (basis != 1) return;
+  if constexpr (N == 2) {
+    const E s = sin(q[1]), c = cos(q[1]);
+    Q[0][0] = s; Q[0][1] = c;
+    Q[1][0] = c; Q[1][1] = -s;
+  } else if constexpr (N == 3) {
+    const E st = sin(q[1]), ct = cos(q[1]), sp = sin(q[2]), cp = cos(q[2]);
+    Q[0][0] = st * cp; Q[0][1] = ct * cp; Q[0][2] = -sp;
+    Q[1][0] = st * sp; Q[1][1] = ct * sp; Q[1][2] = cp;
+    Q[2][0] = ct;      Q[2][1] = -st;     Q[2][2] = E(0);
+  }
+}
+// A_p = transpose(Q_to(q_to)) * Q_from(q_from) (basis_transfer_matrix, grid_traits_api.jl:159-171) for the cell pairs
+// (from_idx[p], to_idx[p]) of the two blocks' centroid arrays (_build_interface_transforms, cache.jl:55-108)
+template <class E, int N>
+__global__ void __launch_bounds__(256) k_basis_transfer(int from_basis, int to_basis, const E* fq0, const E* fq1,
+                                                        const E* fq2, const int64_t* __restrict__ from_idx,
+                                                        const E* tq0, const E* tq1, const E* tq2,
+                                                        const int64_t* __restrict__ to_idx, E* __restrict__ A, int64_t n) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t fi = from_idx[p], ti = to_idx[p];
+    const E qf[3] = {fq0 ? fq0[fi] : E(0), fq1 ? fq1[fi] : E(0), fq2 ? fq2[fi] : E(0)};
+    const E qt[3] = {tq0 ? tq0[ti] : E(0), tq1 ? tq1[ti] : E(0), tq2 ? tq2[ti] : E(0)};
+    E Qf[N][N], Qt[N][N];
+    basis_to_cartesian<E, N>(from_basis, qf, Qf);
+    basis_to_cartesian<E, N>(to_basis, qt, Qt);
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < N; ++c) {
+        E acc = E(0);
+#pragma unroll
+        for (int m = 0; m < N; ++m) acc += Qt[m][r] * Qf[m][c];
+        A[p * (N * N) + r + N * c] = acc;
+      }
+  }
+}
+template <class E>
+int transfer_pairs_t(void* dst, const void* src, const void* di, const void* si, int64_t n, int N, int kind, const void* A,
+                     cudaStream_t st) {
+  const int blocks = launch_blocks(n, 256);
+#define CG_TP(NN, KK)                                                                                                  \
+  if (N == NN && kind == KK) {                                                                                         \
+    k_transfer_index_pairs<E, NN, KK><<<blocks, 256, 0, st>>>((E*)dst, (const E*)src, (const int64_t*)di,              \
+                                                              (const int64_t*)si, (const E*)A, n);                      \
+    return CG_OK;                                                                                                      \
+  }
+  CG_TP(1, 1) CG_TP(2, 1) CG_TP(3, 1) CG_TP(1, 2) CG_TP(2, 2) CG_TP(3, 2)
+#undef CG_TP
+  return fail(CG_ERR_ARG, "cg_transfer_index_pairs: N must be 1..3 and field_kind 1 (vector) or 2 (tensor)");
+}
+}  // namespace
+}  // extern "C++"
+
+int cg_transfer_index_pairs(void* dst, const void* src, const void* dst_idx, const void* src_idx, int64_t n, int dim,
+                            int field_kind, int elem_bytes, const void* transforms, void* stream) {
+  if (n < 0 || (n > 0 && (!dst || !src || !dst_idx || !src_idx))) return fail(CG_ERR_ARG, "bad argument");
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(CG_ERR_ARG, "element size must be 4 or 8 bytes");
+  if (n == 0) return CG_OK;
+  int rc = elem_bytes == 8 ? transfer_pairs_t<double>(dst, src, dst_idx, src_idx, n, dim, field_kind, transforms, (cudaStream_t)stream)
+                           : transfer_pairs_t<float>(dst, src, dst_idx, src_idx, n, dim, field_kind, transforms, (cudaStream_t)stream);
+  if (rc) return rc;
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+int cg_basis_transfer_matrices(int dim, int64_t n, int from_basis, int to_basis, const void* const* from_centroid,
+                               const void* from_idx, const void* const* to_centroid, const void* to_idx, int elem_bytes,
+                               void* transforms, void* stream) {
+  if (dim < 1 || dim > 3 || n < 0 || !transforms || !from_idx || !to_idx || !from_centroid || !to_centroid)
+    return fail(CG_ERR_ARG, "bad argument");
+  if ((from_basis != 0 && from_basis != 1) || (to_basis != 0 && to_basis != 1)) return fail(CG_ERR_ARG, "basis id must be 0 (Cartesian) or 1 (SphericalBasis)");
+  if ((from_basis == 1 || to_basis == 1) && dim < 2)
+    return fail(CG_ERR_ARG, "Unsupported public basis transfer for SphericalBasis and N=1.");  // grid_traits_api.jl:259-269
+  if (elem_bytes != 4 && elem_bytes != 8) return fail(CG_ERR_ARG, "element size must be 4 or 8 bytes");
+  if (n == 0) return CG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = launch_blocks(n, 256);
+  const void* f[3] = {from_centroid[0], dim > 1 ? from_centroid[1] : nullptr, dim > 2 ? from_centroid[2] : nullptr};
+  const void* t[3] = {to_centroid[0], dim > 1 ? to_centroid[1] : nullptr, dim > 2 ? to_centroid[2] : nullptr};
+#define CG_BT(EE, NN)                                                                                                   \
+  k_basis_transfer<EE, NN><<<blocks, 256, 0, st>>>(from_basis, to_basis, (const EE*)f[0], (const EE*)f[1], (const EE*)f[2], \
+                                                   (const int64_t*)from_idx, (const EE*)t[0], (const EE*)t[1],             \
+                                                   (const EE*)t[2], (const int64_t*)to_idx, (EE*)transforms, n)
+  if (elem_bytes == 8) {
+    if (dim == 1) CG_BT(double, 1); else if (dim == 2) CG_BT(double, 2); else CG_BT(double, 3);
+  } else {
+    if (dim == 1) CG_BT(float, 1); else if (dim == 2) CG_BT(float, 2); else CG_BT(float, 3);
+  }
+#undef CG_BT
+  g_launches++;
+  CG_CUDA(cudaGetLastError());
+  return CG_OK;
+}
+
+extern "C++" {
+namespace {
 // launches k_gcl over cell.domain of the global grid intersected with the window and leaves the per-column maxima as
 // bit patterns in g->gcl_bits.  Without `low` the window-local plane 0 of the slab axis is skipped (it needs
 // I - e_axis, which lives on the previous slab); `low` = that slab's last conserved plane of the slab axis.
@@ -1339,6 +1497,19 @@ int cg_nccl_comm_destroy(void* comm) {
   int rc = need_nccl();
   if (rc) return rc;
   CG_NCCL(nccl_api().CommDestroy((ncclComm_t)comm));
+  return CG_OK;
+}
+
+int cg_nccl_sendrecv(void* comm, const void* sendbuf, size_t send_bytes, int send_peer, void* recvbuf, size_t recv_bytes,
+                     int recv_peer, void* stream) {
+  if (!comm) return fail(CG_ERR_ARG, "comm is NULL");
+  int rc = need_nccl();
+  if (rc) return rc;
+  const NcclApi& A = nccl_api();
+  CG_NCCL(A.GroupStart());
+  if (sendbuf && send_bytes > 0 && send_peer >= 0) CG_NCCL(A.Send(sendbuf, send_bytes, ncclChar, send_peer, (ncclComm_t)comm, (cudaStream_t)stream));
+  if (recvbuf && recv_bytes > 0 && recv_peer >= 0) CG_NCCL(A.Recv(recvbuf, recv_bytes, ncclChar, recv_peer, (ncclComm_t)comm, (cudaStream_t)stream));
+  CG_NCCL(A.GroupEnd());
   return CG_OK;
 }
 

@@ -6,10 +6,13 @@ Host side: `interface_index_plan` restates /root/reference/src/multiblock/transf
 indices are 1-based like the reference's `CartesianIndex` (so its known answers, test_multiblock.jl:261-273, can be
 asserted literally).
 
-Device side: `exchange_interface` copies donor interior cells into receiver ghost cells of cell-centred fields that
-live on the GPU (scalar field kind, transfer.jl:25-117) with one launch of `cg_copy_index_pairs` per direction; the
-two blocks may be on the same GPU or, with `pack` / `unpack`, on different ranks (NCCL send / recv of the packed
-values).  Vector / tensor fields additionally need `basis_transfer_matrix` (transfer.jl:461-488) and stay Julia.
+Device side: `exchange_interface` fills receiver ghost cells from donor interior cells of cell-centred fields that live
+on the GPU (transfer.jl:25-117) with one launch per direction: scalar fields by `cg_copy_index_pairs`, vector / tensor
+fields (AoS like Julia's Array{SVector} / Array{SMatrix}) by `cg_transfer_index_pairs` with the per-pair
+`basis_transfer_matrix` (transfer.jl:461-488) that `DevicePlan.build_transforms` tabulates on the device from the two
+blocks' centroid arrays (`cg_basis_transfer_matrices`; multiblock/cache.jl:55-108).  The two blocks may be on the same
+GPU or on different ranks: `exchange_interface_remote` packs the donor values, moves them with NCCL inside the C ABI
+(`cg_nccl_sendrecv`) and applies the transform while unpacking.
 """
 from __future__ import annotations
 
@@ -155,18 +158,120 @@ class DevicePlan:
         self.l2r_src, self.l2r_dst = mk(s), mk(d)
         s, d = linear_indices(plan.right_to_left, right_shape, left_shape)
         self.r2l_src, self.r2l_dst = mk(s), mk(d)
+        self.l2r_A = self.r2l_A = None   # per-pair basis-transfer matrices (None: identity, Cartesian bases)
+        self.dim = len(left_shape)
+
+    def build_transforms(self, left_grid, right_grid):
+        """_build_interface_transforms (multiblock/cache.jl:55-108): for pair i, A_l2r[i] = basis_transfer_matrix(left,
+        centroid(left interior i), right, centroid(right interior i)) and the reverse, on the device.  Grids are this
+        package's MappedGrid / DiscreteGrid (their `basis` / `coordinate_system` select Q); identity when both bases are
+        Cartesian."""
+        import torch
+        if self.l2r_src.numel() != self.r2l_src.numel():
+            raise ValueError("transforms need the same interior cells in both directions (no valid-domain filtering)")
+        bid = lambda g: 1 if (g.basis == "SphericalBasis") else 0
+        for g in (left_grid, right_grid):
+            if g.basis == "SphericalBasis" and g.coordinate_system != "SphericalCS":
+                raise ValueError(f"Unsupported public basis transfer for SphericalBasis with coordinate system {g.coordinate_system}.")
+        if bid(left_grid) == 0 and bid(right_grid) == 0:
+            self.l2r_A = self.r2l_A = None
+            return self
+        N, n = self.dim, self.l2r_src.numel()
+        lc, rc = left_grid.centroid_coordinates, right_grid.centroid_coordinates
+        dt = lc[0].dtype
+        ptrs = lambda cs: (ctypes.c_void_p * 3)(*[ctypes.c_void_p(c.data_ptr()) for c in cs] + [None] * (3 - len(cs)))
+        st = ctypes.c_void_p(torch.cuda.current_stream(lc[0].device).cuda_stream)
+        self.l2r_A = torch.empty((n, N * N), dtype=dt, device=lc[0].device)
+        self.r2l_A = torch.empty((n, N * N), dtype=dt, device=lc[0].device)
+        L.check(L.lib().cg_basis_transfer_matrices(N, ctypes.c_int64(n), bid(left_grid), bid(right_grid), ptrs(lc),
+                                                   ctypes.c_void_p(self.l2r_src.data_ptr()), ptrs(rc),
+                                                   ctypes.c_void_p(self.r2l_src.data_ptr()), lc[0].element_size(),
+                                                   ctypes.c_void_p(self.l2r_A.data_ptr()), st))
+        L.check(L.lib().cg_basis_transfer_matrices(N, ctypes.c_int64(n), bid(right_grid), bid(left_grid), ptrs(rc),
+                                                   ctypes.c_void_p(self.r2l_src.data_ptr()), ptrs(lc),
+                                                   ctypes.c_void_p(self.l2r_src.data_ptr()), lc[0].element_size(),
+                                                   ctypes.c_void_p(self.r2l_A.data_ptr()), st))
+        return self
 
 
-def exchange_interface(left_field, right_field, dplan, direction="both"):
-    """exchange_interface!(mb, iface, fields; field_kind=:scalar, direction) — transfer.jl:25-87: donor interior cells
-    into receiver ghost cells, both blocks on this GPU (one launch per direction)."""
+_KINDS = {"scalar": 0, "vector": 1, "tensor": 2}
+
+
+def _transfer_pairs(dst, src, dst_idx, src_idx, dim, kind, A):
+    """dst[dst_idx[p]] = A_p (x) src[src_idx[p]] for AoS vector / tensor fields (cg_transfer_index_pairs)."""
+    import torch
+    K = dim if kind == 1 else dim * dim
+    if not (dst.is_cuda and src.is_cuda and dst.is_contiguous() and src.is_contiguous() and dst.dtype == src.dtype):
+        raise ValueError("exchange needs contiguous CUDA tensors of one dtype")
+    if dst.shape[-1] != K or src.shape[-1] != K:
+        raise ValueError(f"field_kind needs {K} components per cell in the last dimension")
+    if A is not None and (A.dtype != dst.dtype or not A.is_contiguous()):
+        raise ValueError("transforms must be contiguous and of the field's dtype")
+    st = ctypes.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream)
+    L.check(L.lib().cg_transfer_index_pairs(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()),
+                                            ctypes.c_void_p(dst_idx.data_ptr()), ctypes.c_void_p(src_idx.data_ptr()),
+                                            ctypes.c_int64(dst_idx.numel()), dim, kind, dst.element_size(),
+                                            None if A is None else ctypes.c_void_p(A.data_ptr()), st))
+
+
+def exchange_interface(left_field, right_field, dplan, direction="both", field_kind="scalar"):
+    """exchange_interface!(mb, iface, fields; field_kind, direction) — transfer.jl:25-87: donor interior cells into
+    receiver ghost cells, both blocks on this GPU (one launch per direction).  Vector / tensor fields carry their N or
+    N*N components in the last tensor dimension (the memory of Julia's Array{SVector} / Array{SMatrix}) and are rotated
+    by the plan's basis-transfer matrices (`DevicePlan.build_transforms`; identity without them)."""
     if direction not in ("left_to_right", "right_to_left", "both"):
         raise ValueError(f"Invalid `direction={direction}`.")
+    if field_kind not in _KINDS:
+        raise ValueError(f"Invalid `field_kind={field_kind}`.")
+    kind = _KINDS[field_kind]
     if direction in ("left_to_right", "both"):
-        _copy_pairs(right_field, left_field, dplan.l2r_dst, dplan.l2r_src)
+        if kind == 0:
+            _copy_pairs(right_field, left_field, dplan.l2r_dst, dplan.l2r_src)
+        else:
+            _transfer_pairs(right_field, left_field, dplan.l2r_dst, dplan.l2r_src, dplan.dim, kind, dplan.l2r_A)
     if direction in ("right_to_left", "both"):
-        _copy_pairs(left_field, right_field, dplan.r2l_dst, dplan.r2l_src)
+        if kind == 0:
+            _copy_pairs(left_field, right_field, dplan.r2l_dst, dplan.r2l_src)
+        else:
+            _transfer_pairs(left_field, right_field, dplan.r2l_dst, dplan.r2l_src, dplan.dim, kind, dplan.r2l_A)
     return left_field, right_field
+
+
+def exchange_interface_remote(field, dplan, side, comm, peer, field_kind="scalar", direction="both"):
+    """The same exchange with the two blocks on DIFFERENT ranks: this rank holds the `side` ("left" | "right") block's
+    field, `peer` the other one.  Donor values are packed in plan order, cross NVLink with NCCL inside the C ABI
+    (cg_nccl_sendrecv on `comm`, a slabs.NcclComm) and are rotated by the basis-transfer matrices while they are
+    unpacked into the ghost cells.  Both ranks hold the same DevicePlan (index algebra + transforms are cheap)."""
+    import torch
+    if side not in ("left", "right"):
+        raise ValueError("side must be 'left' or 'right'")
+    if field_kind not in _KINDS:
+        raise ValueError(f"Invalid `field_kind={field_kind}`.")
+    kind = _KINDS[field_kind]
+    K = 1 if kind == 0 else (dplan.dim if kind == 1 else dplan.dim ** 2)
+    left = side == "left"
+    send_on = direction in ("both", "left_to_right" if left else "right_to_left")
+    recv_on = direction in ("both", "right_to_left" if left else "left_to_right")
+    src_idx = dplan.l2r_src if left else dplan.r2l_src       # my interior cells the peer wants
+    dst_idx = dplan.r2l_dst if left else dplan.l2r_dst       # my ghost cells
+    A = dplan.r2l_A if left else dplan.l2r_A                 # transform of what I receive
+    n = src_idx.numel()
+    flat = field.reshape(-1, K) if kind else field.reshape(-1)
+    sendbuf = flat[src_idx].contiguous() if send_on else None                  # pack (gather in plan order)
+    recvbuf = torch.empty((n, K) if kind else (n,), dtype=field.dtype, device=field.device) if recv_on else None
+    st = ctypes.c_void_p(torch.cuda.current_stream(field.device).cuda_stream)
+    nbytes = n * K * field.element_size()
+    L.check(L.lib().cg_nccl_sendrecv(comm._h, None if sendbuf is None else ctypes.c_void_p(sendbuf.data_ptr()),
+                                     ctypes.c_size_t(nbytes if send_on else 0), peer if send_on else -1,
+                                     None if recvbuf is None else ctypes.c_void_p(recvbuf.data_ptr()),
+                                     ctypes.c_size_t(nbytes if recv_on else 0), peer if recv_on else -1, st))
+    if recv_on:
+        ar = torch.arange(n, dtype=torch.int64, device=field.device)
+        if kind == 0:
+            _copy_pairs(field, recvbuf, dst_idx, ar)
+        else:
+            _transfer_pairs(field, recvbuf, dst_idx, ar, dplan.dim, kind, A)
+    return field
 
 
 def pack(field, src_idx):

@@ -240,6 +240,23 @@ int cg_grid_cell_volumes(cg_grid* g, int coordsys, void* volume, void* stream);
  */
 int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const void* src_idx, int64_t n, int elem_bytes,
                         void* stream);
+/*
+ * Vector / tensor ghost-cell fill (exchange_interface! with field_kind = :vector | :tensor, transfer.jl:461-488):
+ * fields are AoS like Julia's Array{SVector{N,T}} / Array{SMatrix{N,N,T}} (K = N or N*N consecutive values per cell,
+ * tensors column-major); pair p carries its own basis-transfer matrix A_p (transforms[p][N*N], column-major):
+ *   vector (field_kind 1): dst[dst_idx[p]] = A_p * src[src_idx[p]],  tensor (2): A_p * T * transpose(A_p).
+ * transforms == NULL: identity (Cartesian bases).  With dst_idx / src_idx = 0..n-1 the same call unpacks a packed
+ * buffer that arrived over NCCL (cg_nccl_sendrecv).
+ * cg_basis_transfer_matrices builds A_p = transpose(Q_to(q_to)) * Q_from(q_from) (basis_transfer_matrix,
+ * grid_traits_api.jl:159-171; _build_interface_transforms, multiblock/cache.jl:55-108) from the two blocks' centroid
+ * coordinate arrays (SoA device pointers, one per coordinate) at the paired INTERIOR cells; basis id 0 = Cartesian
+ * basis (Q = I), 1 = SphericalCS + SphericalBasis (Q = (e_r, e_theta, e_phi), N = 2 or 3).
+ */
+int cg_transfer_index_pairs(void* dst, const void* src, const void* dst_idx, const void* src_idx, int64_t n, int dim,
+                            int field_kind, int elem_bytes, const void* transforms, void* stream);
+int cg_basis_transfer_matrices(int dim, int64_t n, int from_basis, int to_basis, const void* const* from_centroid,
+                               const void* from_idx, const void* const* to_centroid, const void* to_idx, int elem_bytes,
+                               void* transforms, void* stream);
 
 /*
  * Multi-GPU k-slabs with NCCL inside the boundary (one process per GPU).  The reference has no communication layer
@@ -263,6 +280,10 @@ int cg_copy_index_pairs(void* dst, const void* src, const void* dst_idx, const v
 int cg_nccl_unique_id(void* id128 /* 128 bytes out: ncclGetUniqueId, to be broadcast by the host */);
 int cg_nccl_comm_create(const void* id128, int nranks, int rank, int device, void** comm);
 int cg_nccl_comm_destroy(void* comm);
+/* grouped ncclSend / ncclRecv of raw bytes on `stream` (either half may be absent: NULL buffer or peer < 0): the
+ * cross-rank leg of a multiblock interface exchange (packed donor values out, packed ghost values in) */
+int cg_nccl_sendrecv(void* comm, const void* sendbuf, size_t send_bytes, int send_peer, void* recvbuf, size_t recv_bytes,
+                     int recv_peer, void* stream);
 int cg_halo_exchange_begin(cg_grid* g, void* comm, int rank, int nranks, const int64_t* slab_bounds, void* stream);
 int cg_halo_exchange_end(cg_grid* g, void* stream);
 int cg_grid_step_overlapped(cg_grid* g, void* comm, int rank, int nranks, const int64_t* slab_bounds, int what,

@@ -114,6 +114,35 @@ def main():
             print(f"multi-GPU parity OK: world={world} profile={profile} gcl={res.tolist()}", flush=True)
         g.close()
         whole.close()
+    # multiblock interface with the two blocks on different ranks (rank 0: left block, rank 1: right block): scalar
+    # and vector fields, packed values over NCCL inside the C ABI, transforms applied while unpacking
+    if world >= 2 and rank < 2:
+        mbk, wl = cg.multiblock, cg.workloads
+        hh, cd = 2, (5, 6, 4)
+        left = cg.MappedGrid(wl.sphere_sector_3d_terms(cd), {}, cd, hh, cache_mode="lazy")
+        right = cg.MappedGrid(wl.spherical_rtp_3d_terms(cd), {}, cd, hh, cache_mode="lazy", coordinate_system="SphericalCS",
+                              basis="SphericalBasis")
+        full = tuple(c + 2 * hh for c in cd)
+        dom = tuple((hh + 1, n - hh) for n in full)
+        plan = mbk.interface_index_plan(dom, mbk.BlockFace(1, 1, "max"), dom, mbk.BlockFace(2, 1, "min"), (1, 2), (False, False))
+        dplan = mbk.DevicePlan(plan, full, full, "cuda").build_transforms(left, right)
+        gen = torch.Generator(device="cpu").manual_seed(5)
+        fl = torch.randn(tuple(reversed(full)) + (3,), generator=gen, dtype=torch.float64).cuda()
+        fr = torch.randn(tuple(reversed(full)) + (3,), generator=gen, dtype=torch.float64).cuda()
+        want_l, want_r = fl.clone(), fr.clone()
+        mbk.exchange_interface(want_l, want_r, dplan, field_kind="vector")          # both blocks on one GPU
+        mine = fl if rank == 0 else fr
+        mbk.exchange_interface_remote(mine, dplan, "left" if rank == 0 else "right", comm, 1 - rank, field_kind="vector")
+        assert torch.equal(mine, want_l if rank == 0 else want_r)
+        sl, sr = fl[..., 0].contiguous(), fr[..., 0].contiguous()
+        ws_l, ws_r = sl.clone(), sr.clone()
+        mbk.exchange_interface(ws_l, ws_r, dplan)
+        ms = sl if rank == 0 else sr
+        mbk.exchange_interface_remote(ms, dplan, "left" if rank == 0 else "right", comm, 1 - rank)
+        assert torch.equal(ms, ws_l if rank == 0 else ws_r)
+        if rank == 0:
+            print("multiblock remote exchange OK (scalar + vector)", flush=True)
+    dist.barrier()
     comm.close()
     dist.destroy_process_group()
 
