@@ -31,7 +31,7 @@ EXPORTS = [
     "cg_grid_coords_valid", "cg_grid_gcl_max_seam", "cg_grid_seam_plane", "cg_nccl_unique_id", "cg_nccl_comm_create",
     "cg_nccl_comm_destroy", "cg_halo_exchange_begin", "cg_halo_exchange_end", "cg_grid_step_overlapped",
     "cg_grid_gcl_max_dist", "cg_grid_update_from_host_dist", "cg_transfer_index_pairs", "cg_basis_transfer_matrices",
-    "cg_nccl_sendrecv",
+    "cg_nccl_sendrecv", "cg_legacy_meg6_update_1d", "cg_legacy_check_valid",
 ]
 
 _lib = None

@@ -511,3 +511,170 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
   if (launches) *launches = nl;
   return CG_OK;
 }
+
+namespace {
+// centroids of a 1-D grid (1d.jl:445-455) on the metric domain
+__global__ void k_legacy_centroid1d(LShape S, LBox dom, const double* __restrict__ xn, int off, double* cx) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const double* a = xn + (c_[0] - off);
+    cx[I] = 0.5 * (a[0] + a[1]);
+  }
+}
+// conservative_metrics! for a 1-D grid (conservative_metrics.jl:239-245): xi_x = 1 / x_xi, J = |x_xi|, hatted = xi_x J
+__global__ void k_legacy_inv1d(LShape S, LBox dom, const double* __restrict__ xxi, double* __restrict__ J,
+                               double* __restrict__ inv, double* __restrict__ hat) {
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    const double f = xxi[I];
+    const double g = 1.0 / f, j = fabs(f);
+    J[I] = j;
+    inv[I] = g;
+    hat[I] = g * j;
+  }
+}
+// _check_valid_metrics (1d.jl:457-482, 2d.jl:748-788, 3d.jl:600-677) as ONE fused reduction: the listed cell rows must
+// be finite on cell.domain (and the row `positive_row` > 0), the listed edge rows of axis a finite on
+// expand(domain, a, -1).  flags[0] |= 1: bad cell metrics, flags[1] |= 1: bad edge metrics.
+struct LRows {
+  int n_cell, cell[32], positive_row, n_edge, edge[32], edge_rows_per_axis, dim;
+};
+__global__ void k_legacy_check_valid(LShape S, LBox dom, LRows R, const double* __restrict__ cell,
+                                     const double* __restrict__ edge, long long nc, int* flags) {
+  bool bad_c = false, bad_e = false;
+  LEGACY_FOR_BOX(dom) {
+    LEGACY_INDEX(dom, S)
+    for (int r = 0; r < R.n_cell; ++r) bad_c |= !isfinite(cell[(long long)R.cell[r] * nc + I]);
+    if (R.positive_row >= 0) bad_c |= !(cell[(long long)R.positive_row * nc + I] > 0.0);
+    for (int a = 0; a < R.dim; ++a) {
+      if (c_[a] <= dom.lo[a] || c_[a] >= dom.hi[a] - 1) continue;  // expand(domain, a, -1)
+      const double* E = edge + (long long)a * R.edge_rows_per_axis * nc;
+      for (int r = 0; r < R.n_edge; ++r) bad_e |= !isfinite(E[(long long)R.edge[r] * nc + I]);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad_c) && (threadIdx.x & 31) == 0) atomicOr(flags, 1);
+  if (__any_sync(0xffffffffu, bad_e) && (threadIdx.x & 31) == 0) atomicOr(flags + 1, 1);
+}
+}  // namespace
+
+// see include/curvigrid_cuda.h
+extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64_t* nnode, int nhalo, int halo_coords_included,
+                                        double* cell, double* edge, double* centroid, double* scratch,
+                                        size_t scratch_bytes, void* stream, uint64_t* launches) {
+  g_legacy_err[0] = 0;
+  if (!x || !nnode || !cell || !edge || !scratch) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_meg6_update_1d: NULL argument");
+    return CG_ERR_ARG;
+  }
+  if (nhalo < 5) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "MEG6 needs nhalo >= 5 (DiscretizationSchemes.jl:53-60)");
+    return CG_ERR_ARG;
+  }
+  const int64_t nf = (halo_coords_included ? nnode[0] : nnode[0] + 2 * nhalo) - 1;
+  if (nf - 2 * nhalo < 6) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "MEG6 one-sided edge stencils need >= 6 interior cells per axis");
+    return CG_ERR_ARG;
+  }
+  LShape S;
+  LBox full, dom;
+  S.n[0] = (int)nf; S.n[1] = S.n[2] = 1;
+  S.st[0] = 1; S.st[1] = S.st[2] = nf;
+  for (int d = 0; d < 3; ++d) {
+    full.lo[d] = dom.lo[d] = 0;
+    full.hi[d] = dom.hi[d] = d == 0 ? (int)nf : 1;
+  }
+  dom.lo[0] = nhalo;
+  dom.hi[0] = (int)nf - nhalo;
+  const long long nc = nf;
+  if (scratch_bytes < (size_t)(3 * nc) * sizeof(double)) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "scratch too small: need %lld bytes", (long long)(3 * nc * 8));
+    return CG_ERR_ARG;
+  }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cudaSetDevice: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const LBox md = halo_coords_included ? full : dom;
+  const int whole = halo_coords_included ? 1 : 0;
+  uint64_t nl = 0;
+  double *cx = scratch, *d1 = scratch + nc, *d2 = scratch + 2 * nc;
+  cudaMemsetAsync(cell, 0, (size_t)4 * nc * sizeof(double), st);
+  cudaMemsetAsync(edge, 0, (size_t)3 * nc * sizeof(double), st);
+  cudaMemsetAsync(scratch, 0, (size_t)3 * nc * sizeof(double), st);
+  const int bl = blocks_for(box_count(md));
+  // 1d.jl:388-408: the centroids are refreshed on cell.domain only (unlike 2-D / 3-D); with halo_coords_included the
+  // node array covers the halo and the metric domain is cell.full
+  k_legacy_centroid1d<<<bl, 256, 0, st>>>(S, md, x, halo_coords_included ? 0 : nhalo, cx);
+  ++nl;
+  if (centroid) cudaMemcpyAsync(centroid, cx, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  double *J = cell, *xxi = cell + nc, *inv = cell + 2 * nc, *hat = cell + 3 * nc;
+  k_legacy_first<<<bl, 256, 0, st>>>(S, md, 0, cx, d1);      // forward_metrics.jl:11-27
+  k_legacy_second<<<bl, 256, 0, st>>>(S, md, 0, cx, d1, d2);
+  k_legacy_meg<0><<<bl, 256, 0, st>>>(S, md, 0, cx, d1, d2, xxi, 1.0);
+  k_legacy_inv1d<<<bl, 256, 0, st>>>(S, md, xxi, J, inv, hat);
+  nl += 4;
+  for (int m = 0; m < 3; ++m) {  // MetricDiscretizationSchemes.jl:58-89: J, xi.x1, xi^.x1 to the i+1/2 edges
+    const double* phi = m == 0 ? J : (m == 1 ? inv : hat);
+    k_legacy_first<<<bl, 256, 0, st>>>(S, md, 0, phi, d1);
+    k_legacy_second<<<bl, 256, 0, st>>>(S, md, 0, phi, d1, d2);
+    k_legacy_interp<<<bl, 256, 0, st>>>(S, md, 0, whole, phi, d1, d2, edge + (long long)m * nc);
+    nl += 3;
+  }
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "legacy kernels: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  if (launches) *launches = nl;
+  return CG_OK;
+}
+
+extern "C" int cg_legacy_check_valid(int device, int dim, const int64_t* nfull, int nhalo, const double* cell,
+                                     const int* cell_rows, int n_cell_rows, int positive_row, const double* edge,
+                                     int edge_rows_per_axis, const int* edge_rows, int n_edge_rows, int* cell_ok,
+                                     int* edge_ok, void* stream) {
+  g_legacy_err[0] = 0;
+  if (dim < 1 || dim > 3 || !nfull || !cell || !cell_ok || !edge_ok || n_cell_rows < 0 || n_cell_rows > 32 ||
+      n_edge_rows < 0 || n_edge_rows > 32 || (n_cell_rows > 0 && !cell_rows) || (n_edge_rows > 0 && (!edge_rows || !edge))) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_check_valid: bad argument");
+    return CG_ERR_ARG;
+  }
+  cudaError_t ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return CG_ERR_CUDA;
+  LShape S;
+  LBox dom;
+  long long nc = 1;
+  for (int d = 0; d < 3; ++d) {
+    S.n[d] = d < dim ? (int)nfull[d] : 1;
+    S.st[d] = nc;
+    nc *= S.n[d];
+    dom.lo[d] = d < dim ? nhalo : 0;
+    dom.hi[d] = d < dim ? (int)nfull[d] - nhalo : 1;
+  }
+  LRows R;
+  R.n_cell = n_cell_rows;
+  R.n_edge = n_edge_rows;
+  R.positive_row = positive_row;
+  R.edge_rows_per_axis = edge_rows_per_axis;
+  R.dim = dim;
+  for (int r = 0; r < n_cell_rows; ++r) R.cell[r] = cell_rows[r];
+  for (int r = 0; r < n_edge_rows; ++r) R.edge[r] = edge_rows[r];
+  cudaStream_t st = (cudaStream_t)stream;
+  int* flags = nullptr;
+  if (cudaMallocAsync((void**)&flags, 2 * sizeof(int), st) != cudaSuccess) return CG_ERR_OOM;
+  cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
+  k_legacy_check_valid<<<blocks_for(box_count(dom)), 256, 0, st>>>(S, dom, R, cell, edge, nc, flags);
+  int h[2] = {0, 0};
+  cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, st);
+  cudaFreeAsync(flags, st);
+  ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_check_valid: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  *cell_ok = !h[0];
+  *edge_ok = !h[1];
+  return CG_OK;
+}

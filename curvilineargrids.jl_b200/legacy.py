@@ -91,6 +91,26 @@ class CurvilinearGrid3D:
         return out
 
 
+def _check_valid_metrics(mesh, dim, cell_rows, positive_row, edge_rows, edge_rows_per_axis):
+    """_check_valid_metrics (1d.jl:457-482, 2d.jl:748-788, 3d.jl:600-677): ONE fused device reduction
+    (cg_legacy_check_valid) instead of the reference's ~60 all(isfinite.(...)) passes; same error messages."""
+    import torch
+    nf = (ctypes.c_int64 * 3)(*(list(mesh.celldims_full) + [1] * (3 - dim)))
+    cr = (ctypes.c_int * max(1, len(cell_rows)))(*cell_rows)
+    er = (ctypes.c_int * max(1, len(edge_rows)))(*edge_rows)
+    c_ok, e_ok = ctypes.c_int(), ctypes.c_int()
+    st = ctypes.c_void_p(torch.cuda.current_stream(mesh.device).cuda_stream)
+    rc = L.lib().cg_legacy_check_valid(mesh.device, dim, nf, mesh.nhalo, ctypes.c_void_p(mesh._cell.data_ptr()), cr,
+                                       len(cell_rows), positive_row, ctypes.c_void_p(mesh._edge.data_ptr()),
+                                       edge_rows_per_axis, er, len(edge_rows), ctypes.byref(c_ok), ctypes.byref(e_ok), st)
+    if rc != L.CG_OK:
+        raise L.CurvigridError(rc, L.lib().cg_legacy_last_error().decode())
+    if not e_ok.value:
+        raise RuntimeError("Invalid edge metrics found")
+    if not c_ok.value:
+        raise RuntimeError("Invalid centroid metrics found")
+
+
 def update(mesh, force=False, include_halo_region=False):
     """update!(mesh::AbstractCurvilinearGrid3D, force, include_halo_region) — 3d.jl:472-493."""
     import torch
@@ -113,6 +133,9 @@ def update(mesh, force=False, include_halo_region=False):
         msg = L.lib().cg_legacy_last_error().decode()
         raise (L.CurvigridArgumentError if rc == L.CG_ERR_ARG else L.CurvigridError)(rc, msg)
     mesh.launches = int(nl.value)
+    # 3d.jl:600-677: J finite and > 0, the 9 forward and 9 inverse metrics finite on cell.domain (rows 0..18 of the
+    # cell SoA); the 9 hatted edge metrics of each axis finite on expand(domain, axis, -1) (rows 10..18)
+    _check_valid_metrics(mesh, 3, list(range(19)), 0, list(range(10, 19)), 19)
     return None
 
 
@@ -257,11 +280,11 @@ def update2d(mesh, force=False, include_halo_region=False):
     if rc != L.CG_OK:
         msg = L.lib().cg_legacy_last_error().decode()
         raise (L.CurvigridArgumentError if rc == L.CG_ERR_ARG else L.CurvigridError)(rc, msg)
-    # _check_valid_metrics (2d.jl:748-751): the Jacobian must be finite on cell.domain
-    h = mesh.nhalo
-    J = mesh._v(mesh._cell[0])
-    if not bool(torch.isfinite(J[h:-h, h:-h]).all()):
-        raise AssertionError("non-finite cell-centre Jacobian on cell.domain")
+    # _check_valid_metrics (2d.jl:748-753): only `@assert all(isfinite.(J[domain]))` is live in the reference
+    try:
+        _check_valid_metrics(mesh, 2, [0], -1, [], 9)
+    except RuntimeError as e:
+        raise AssertionError("non-finite cell-centre Jacobian on cell.domain") from e
     mesh.launches = int(nl.value)
     return None
 
@@ -302,3 +325,74 @@ def update2d(mesh, force=False, include_halo_region=False):  # noqa: F811
     if isinstance(mesh, AxisymmetricGrid2D) and mesh.snap_to_axis:
         mesh._snap_nodes_to_axis()
     return out
+
+
+class CurvilinearGrid1D:
+    """CurvilinearGrid1D(x, :meg6; halo_coords_included) — 1d.jl:73-138; `update!` :388-408: centroids 0.5 (x_i + x_i+1),
+    x_xi by the MEG6 cell-centre derivative (forward_metrics.jl:11-27), xi_x = 1 / x_xi, J = |x_xi|, hatted = xi_x J
+    (conservative_metrics.jl:239-245), J / xi_x / hatted interpolated to the i+1/2 edges, `_check_valid_metrics`."""
+    nhalo = 5
+
+    def __init__(self, x, discretization_scheme="meg6", *, device=None, halo_coords_included=False, is_static=False,
+                 init_metrics=True):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("curvigrid: a CUDA device is required (no CPU fallback)")
+        key = str(discretization_scheme).lower().lstrip(":")
+        if key not in _SCHEMES:
+            raise ValueError(f"Unknown or unsupported discretization scheme {discretization_scheme!r}; use :meg6")
+        self.discretization_scheme_name = key
+        self.device = int(torch.cuda.current_device() if device is None else device)
+        self.halo_coords_included = bool(halo_coords_included)
+        self.is_static = bool(is_static)
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+        self.nnodes = (x.size,)
+        self.celldims_full = (x.size - 1 + (0 if halo_coords_included else 2 * self.nhalo),)
+        dev = f"cuda:{self.device}"
+        nc = self.celldims_full[0]
+        self._nodes = [torch.from_numpy(x).to(dev)]
+        self._cell = torch.zeros((4, nc), dtype=torch.float64, device=dev)
+        self._edge = torch.zeros((1, 3, nc), dtype=torch.float64, device=dev)
+        self._cent = torch.zeros((nc,), dtype=torch.float64, device=dev)
+        self._scratch = torch.empty((3, nc), dtype=torch.float64, device=dev)
+        self.launches = 0
+        if init_metrics:
+            update1d(self, True, self.halo_coords_included)
+
+    @property
+    def centroid_coordinates(self):
+        return {"x": self._cent}
+
+    @property
+    def cell_center_metrics(self):
+        c = self._cell
+        return {"J": c[0], "x₁": {"ξ": c[1]}, "ξ": {"x₁": c[2]}, "ξ̂": {"x₁": c[3]}}
+
+    @property
+    def edge_metrics(self):
+        e = self._edge[0]
+        return {"i₊½": {"J": e[0], "ξ": {"x₁": e[1]}, "ξ̂": {"x₁": e[2]}}}
+
+
+def update1d(mesh, force=False, include_halo_region=False):
+    """update!(mesh::AbstractCurvilinearGrid1D, force, include_halo_region) — 1d.jl:388-408 (a static grid without
+    `force` is silently left alone there)."""
+    import torch
+    if mesh.is_static and not force:
+        return None
+    if bool(include_halo_region) != mesh.halo_coords_included:
+        raise ValueError("include_halo_region must match halo_coords_included")
+    nn = (ctypes.c_int64 * 1)(*mesh.nnodes)
+    nl = ctypes.c_uint64()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream(mesh.device).cuda_stream)
+    rc = L.lib().cg_legacy_meg6_update_1d(mesh.device, p(mesh._nodes[0]), nn, mesh.nhalo, int(mesh.halo_coords_included),
+                                          p(mesh._cell), p(mesh._edge), p(mesh._cent), p(mesh._scratch),
+                                          ctypes.c_size_t(mesh._scratch.numel() * 8), st, ctypes.byref(nl))
+    if rc != L.CG_OK:
+        msg = L.lib().cg_legacy_last_error().decode()
+        raise (L.CurvigridArgumentError if rc == L.CG_ERR_ARG else L.CurvigridError)(rc, msg)
+    mesh.launches = int(nl.value)
+    # 1d.jl:457-482: J finite and > 0, xi.x1 and x1.xi finite on cell.domain; the hatted edge metric on expand(domain, 1, -1)
+    _check_valid_metrics(mesh, 1, [0, 1, 2], 0, [2], 3)
+    return None

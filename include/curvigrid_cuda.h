@@ -338,6 +338,25 @@ int cg_legacy_meg6_update_3d(int device, const double* x, const double* y, const
 int cg_legacy_meg6_update_2d(int device, const double* x, const double* y, const int64_t* nnode, int nhalo,
                              int halo_coords_included, double* cell, double* edge, double* centroid, double* scratch,
                              size_t scratch_bytes, void* stream, uint64_t* launches);
+/*
+ * Legacy 1-D path: CurvilinearGrid1D(x, :meg6) `update!(mesh, force, include_halo_region)`
+ * (src/grids/curvilinear_mapped_grids/1d.jl:388-408; forward_metrics.jl:11-27; conservative_metrics.jl:239-245).
+ * x: DEVICE node array of nnode[0] values.  With ncell = cell.full:
+ *   cell [4][ncell]  0 J = |x_xi| | 1 x_xi | 2 xi_x = 1 / x_xi | 3 hatted = xi_x J
+ *   edge [3][ncell]  J, xi_x, hatted interpolated to i+1/2;  centroid [ncell] (may be NULL);  scratch >= 3 * ncell doubles
+ */
+int cg_legacy_meg6_update_1d(int device, const double* x, const int64_t* nnode, int nhalo, int halo_coords_included,
+                             double* cell, double* edge, double* centroid, double* scratch, size_t scratch_bytes,
+                             void* stream, uint64_t* launches);
+/*
+ * _check_valid_metrics (1d.jl:457-482, 2d.jl:748-788, 3d.jl:600-677) as ONE fused reduction on the device instead of
+ * the reference's ~60 all(isfinite.(...)) passes: the rows `cell_rows` of cell [rows][ncell] must be finite on
+ * cell.domain and the row `positive_row` (-1: none) positive; the rows `edge_rows` of edge [dim][edge_rows_per_axis]
+ * [ncell] finite on expand(domain, axis, -1).  Synchronises; *cell_ok / *edge_ok = 1 when valid.
+ */
+int cg_legacy_check_valid(int device, int dim, const int64_t* nfull, int nhalo, const double* cell, const int* cell_rows,
+                          int n_cell_rows, int positive_row, const double* edge, int edge_rows_per_axis,
+                          const int* edge_rows, int n_edge_rows, int* cell_ok, int* edge_ok, void* stream);
 const char* cg_legacy_last_error(void);
 
 #ifdef __cplusplus

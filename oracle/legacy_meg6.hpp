@@ -401,4 +401,45 @@ inline void legacy_meg6_2d(const double* xn, const double* yn, const int64_t* nn
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Legacy CurvilinearGrid1D(x, :meg6) update! (1d.jl:388-408; forward_metrics.jl:11-27; conservative_metrics.jl:239-245;
+// MetricDiscretizationSchemes.jl:58-89).  cell = [4][nc] (J, x_xi, xi_x, hatted), edge = [3][nc] (J, xi_x, hatted at
+// i+1/2), cent = [nc].
+// ---------------------------------------------------------------------------
+inline void legacy_meg6_1d(const double* xn, const int64_t* nnode, int nhalo, bool halo_coords_included, double* cell,
+                           double* edge, double* cent) {
+  Grid g;
+  g.S.n[0] = (halo_coords_included ? nnode[0] : nnode[0] + 2 * nhalo) - 1;
+  g.S.n[1] = g.S.n[2] = 1;
+  g.S.st[0] = 1;
+  g.S.st[1] = g.S.st[2] = g.S.n[0];
+  const int64_t nc = g.S.total();
+  Box full, dom;
+  for (int d = 0; d < 3; ++d) {
+    full.lo[d] = dom.lo[d] = 0;
+    full.hi[d] = dom.hi[d] = d == 0 ? g.S.n[0] : 1;
+  }
+  dom.lo[0] = nhalo;
+  dom.hi[0] = g.S.n[0] - nhalo;
+  const Box md = halo_coords_included ? full : dom;
+  const int64_t off = halo_coords_included ? 0 : nhalo;
+  std::vector<double> cx(nc, 0.0), d1(nc, 0.0), d2(nc, 0.0);
+  for (int64_t i = md.lo[0]; i < md.hi[0]; ++i) cx[i] = 0.5 * (xn[i - off] + xn[i - off + 1]);  // 1d.jl:445-455
+  if (cent)
+    for (int64_t I = 0; I < nc; ++I) cent[I] = cx[I];
+  for (int64_t I = 0; I < 4 * nc; ++I) cell[I] = 0.0;
+  for (int64_t I = 0; I < 3 * nc; ++I) edge[I] = 0.0;
+  double *J = cell, *xxi = cell + nc, *inv = cell + 2 * nc, *hat = cell + 3 * nc;
+  cell_center_derivatives(g, xxi, d2.data(), d1.data(), cx.data(), 0, md);
+  g.each(md, [&](int64_t I) {
+    inv[I] = 1.0 / xxi[I];
+    J[I] = std::fabs(xxi[I]);
+    hat[I] = inv[I] * J[I];
+  });
+  interpolate_to_edge(g, edge, d2.data(), d1.data(), J, 0, md);
+  interpolate_to_edge(g, edge + nc, d2.data(), d1.data(), inv, 0, md);
+  interpolate_to_edge(g, edge + 2 * nc, d2.data(), d1.data(), hat, 0, md);
+}
+
 }  // namespace cgl

@@ -206,3 +206,15 @@ def legacy_meg6_2d(nodes, nhalo=5, halo_coords_included=False):
     lib().cgo_legacy_meg6_2d(_dp(flat[0]), _dp(flat[1]), _ip(nn), ctypes.c_int(nhalo),
                              ctypes.c_int(int(halo_coords_included)), _dp(cell), _dp(edge), _dp(cent))
     return {"cell": cell, "edge": edge, "centroid": cent, "nfull": nfull}
+
+
+def legacy_meg6_1d(x, nhalo=5, halo_coords_included=False):
+    """Legacy CurvilinearGrid1D(x, :meg6) update! (oracle/legacy_meg6.hpp).  Returns dict: cell [4, ncell] (J, x_xi, xi_x,
+    hatted), edge [3, ncell] (J, xi_x, hatted at i+1/2), centroid [ncell], nfull."""
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+    nn = np.array([x.size], dtype=np.int64)
+    nc = int(x.size - 1 + (0 if halo_coords_included else 2 * nhalo))
+    cell, edge, cent = np.zeros((4, nc)), np.zeros((3, nc)), np.zeros(nc)
+    lib().cgo_legacy_meg6_1d(_dp(x), _ip(nn), ctypes.c_int(nhalo), ctypes.c_int(int(halo_coords_included)), _dp(cell),
+                             _dp(edge), _dp(cent))
+    return {"cell": cell, "edge": edge, "centroid": cent, "nfull": (nc,)}

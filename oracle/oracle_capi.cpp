@@ -243,6 +243,13 @@ int cgo_legacy_meg6_2d(const double* x, const double* y, const int64_t* nnode, i
   return 0;
 }
 
+// Legacy CurvilinearGrid1D(x, :meg6) metric update: cell = [4][ncell.full], edge = [3][ncell.full], cent = [ncell.full].
+int cgo_legacy_meg6_1d(const double* x, const int64_t* nnode, int nhalo, int halo_coords_included, double* cell,
+                       double* edge, double* cent) {
+  cgl::legacy_meg6_1d(x, nnode, nhalo, halo_coords_included != 0, cell, edge, cent);
+  return 0;
+}
+
 // stencil probes for the pins (derivative_stencils.jl:34-45, 97-175, 180-193)
 double cgo_legacy_central6(const double* v) { return cgl::central6(v[0], v[1], v[2], v[3], v[4], v[5]); }
 void cgo_legacy_mixed(const double* v, double* lo3, double* hi3) {

@@ -181,3 +181,49 @@ def test_legacy_axisymmetric_2d_snaps_after_centroids(cg, oracle, axis):
     assert (np.abs(mesh._cell.cpu().numpy() - ref2["cell"]) / scale).max() <= 1e-13
     with pytest.raises(ValueError):
         cg.legacy.AxisymmetricGrid2D(x, y, True, "z", "meg6")
+
+
+@pytest.mark.parametrize("halo_included", [False, True])
+def test_legacy_1d_matches_oracle(cg, oracle, halo_included):
+    """CurvilinearGrid1D(x, :meg6) update! (1d.jl:388-408) against the oracle's array-pass restatement."""
+    n = 41
+    s = np.linspace(0.0, 1.0, n + (10 if halo_included else 0))
+    x = s + 0.04 * np.sin(2 * np.pi * s) + 0.3
+    mesh = cg.legacy.CurvilinearGrid1D(x, "meg6", halo_coords_included=halo_included)
+    ref = oracle.legacy_meg6_1d(x, 5, halo_included)
+    for got, want in ((mesh._cell.cpu().numpy(), ref["cell"]), (mesh._edge[0].cpu().numpy(), ref["edge"]),
+                      (mesh._cent.cpu().numpy(), ref["centroid"])):
+        scale = max(1e-300, np.abs(want).max())
+        assert np.abs(got - want).max() <= 1e-13 * scale
+    # known answers on a uniform mesh: x_xi = dx, xi_x = 1 / dx, J = dx, hatted = 1 (conservative_metrics.jl:239-245)
+    u = cg.legacy.CurvilinearGrid1D(np.linspace(2.0, 4.0, 21), "meg6")
+    d = u.cell_center_metrics
+    dom = slice(5, -5)
+    assert np.allclose(d["x₁"]["ξ"][dom].cpu().numpy(), 0.1, rtol=0, atol=1e-13)
+    assert np.allclose(d["ξ̂"]["x₁"][dom].cpu().numpy(), 1.0, rtol=0, atol=1e-13)
+    assert np.allclose(u.edge_metrics["i₊½"]["J"][6:-6].cpu().numpy(), 0.1, rtol=0, atol=1e-13)
+    with pytest.raises(cg.CurvigridArgumentError):
+        cg.legacy.CurvilinearGrid1D(np.linspace(0, 1, 5), "meg6")    # < 6 interior cells
+
+
+def test_legacy_check_valid_metrics(cg):
+    """_check_valid_metrics (3d.jl:600-677, 1d.jl:457-482): a folded mesh (negative Jacobian) or a non-finite metric is
+    reported with the reference's messages; the check is one fused device reduction (cg_legacy_check_valid)."""
+    x, y, z = cg.workloads.wavy_nodes_3d(15, 14, 13)
+    ok = cg.legacy.CurvilinearGrid3D(x, y, z, "meg6")           # passes the check inside update
+    assert float(ok.cell_center_metrics["J"][5:-5, 5:-5, 5:-5].min()) > 0
+    with pytest.raises(RuntimeError, match="Invalid centroid metrics found"):
+        cg.legacy.CurvilinearGrid3D(-x, y, z, "meg6")           # mirrored mesh: J < 0 everywhere
+    bad = np.array(x)
+    bad[7, 7, 7] = np.nan
+    with pytest.raises(RuntimeError, match="Invalid (edge|centroid) metrics found"):
+        cg.legacy.CurvilinearGrid3D(bad, y, z, "meg6")
+    b1 = np.linspace(0.0, 1.0, 30)
+    b1[12] = np.inf
+    with pytest.raises(RuntimeError, match="Invalid (edge|centroid) metrics found"):
+        cg.legacy.CurvilinearGrid1D(b1, "meg6")
+
+
+def test_legacy_1d_decreasing_mesh_is_accepted(cg):
+    m = cg.legacy.CurvilinearGrid1D(np.linspace(1.0, 0.0, 30), "meg6")
+    assert float(m.cell_center_metrics["J"][5:-5].min()) > 0 and float(m.cell_center_metrics["x₁"]["ξ"][5:-5].max()) < 0
