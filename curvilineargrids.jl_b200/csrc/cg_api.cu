@@ -315,7 +315,12 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
       ok = cg::launch_mapped_adtl3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, (const T*)g->mtab.fhalf, g->mtab.L, O, st);
       adtl_done = true;
     } else if (full_cf) {
-      ok = cg::launch_mapped_metrics3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
+      // debug switch CG_MAPPED_KERNEL=staged: the round-1 kernel (every lane multiplies all three table rows)
+      static const bool old_kernel = [] { const char* e = getenv("CG_MAPPED_KERNEL"); return e && std::string(e) == "staged"; }();
+      ok = false;
+      if (!old_kernel && TM.n >= 1 && g->mtab.pairs.n >= 1)
+        ok = cg::launch_mapped_metrics3d_uni<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
+      if (!ok) ok = cg::launch_mapped_metrics3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
     } else {
       cg::k_mapped_metrics3d<T><<<launch_blocks(nc, 128), 128, 0, st>>>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O,
                                                                         g->scheme, what);

@@ -663,6 +663,404 @@ inline bool launch_mapped_metrics3d_staged(const Dims& D, const MTerms& TM, cons
   return true;
 }
 
+// ---------------------------------------------------------------------------
+// Round 2: the FULL-profile kernel with the WARP-UNIFORM part of every product factored out.
+//
+// A warp owns 31 cells of one j-row and walks along k, so of the three 1-D table values that every product
+// multiplies, only the xi one differs between lanes; the eta value (index j) and the zeta value (index m) are the
+// same for all 32 lanes.  k_mapped_metrics3d_staged made every lane load all three rows and multiply them
+// (12 pairs x 9 sixteen-byte loads and ~42 FP64 operations per pair and cell; 6 terms x 6 loads and ~48 operations
+// per term for the Jacobian derivatives; the kernel sat at 8 warps/SM waiting for those loads: 33 % FP64 pipe,
+// 2.4 long-scoreboard stalls per issue).  Here, once per warp step,
+//   * lane p multiplies the eta and zeta rows of pair p into the 15 coefficients U_p that the nine conserved entries
+//     need (pair_uniform: 24 operations on one lane instead of ~27 on every lane), and
+//   * lane s multiplies the eta and zeta factor-derivative rows of term s into the 7 products c f_eta^(a) f_zeta^(b)
+//     that F, dF/dxi_f and d2F/dxi_f^2 need, for the three cell positions of a step (term_uniform),
+// into a small shared-memory table; every lane then reads the coefficients as 16-byte broadcasts and does ONE
+// multiply-add per (xi value, coefficient): 15 per pair, 9-12 per term and position.  Per-lane global loads are the
+// xi rows only; they are the same for every step of the march AND for every j, so the blocks are ordered j-fastest:
+// the warps resident on an SM work on the same xi tile and share its rows in L1 (24 KB instead of 24 KB per warp).
+// The zeta rows of the next step are requested one phase before they are multiplied.
+// FP64 operations per cell: ~1840 -> ~1300 (the L / R states of inv F are now half of them).
+// ---------------------------------------------------------------------------
+template <class T, int N>
+__device__ __forceinline__ void lds_vec(const T* p, T (&v)[N]) {
+  if constexpr (sizeof(T) == 8) {
+    static_assert(N % 2 == 0, "16-byte pieces");
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) {
+      const double2 w = reinterpret_cast<const double2*>(p)[k];
+      v[2 * k] = w.x; v[2 * k + 1] = w.y;
+    }
+  } else {
+    static_assert(N % 4 == 0, "16-byte pieces");
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) {
+      const float4 w = reinterpret_cast<const float4*>(p)[k];
+      v[4 * k] = w.x; v[4 * k + 1] = w.y; v[4 * k + 2] = w.z; v[4 * k + 3] = w.w;
+    }
+  }
+}
+template <class T, int N>
+__device__ __forceinline__ void sts_vec(T* p, const T (&v)[N]) {
+  if constexpr (sizeof(T) == 8) {
+#pragma unroll
+    for (int k = 0; k < N / 2; ++k) reinterpret_cast<double2*>(p)[k] = make_double2(v[2 * k], v[2 * k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < N / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+}
+constexpr int UNI_PAIR = 16;  // coefficients per pair (15 + 1 of padding)
+constexpr int UNI_TERM = 8;   // products per term and cell position (7 + 1 of padding)
+// staging: two Metric buffers (four phases per step) and one ConservedMetric buffer per face axis (the three
+// conserved arrays leave together with the cell arrays, so the 27 accumulators are dead before the Jacobian phases)
+template <class T> constexpr int uni_stage_vals = 2 * stage_len<T, 10> + 3 * stage_len<T, 9>;
+#ifndef CG_UNI_MINB
+#define CG_UNI_MINB 8
+#endif
+template <class T, int SCH>
+__global__ void __launch_bounds__(32, CG_UNI_MINB) k_mapped_metrics3d_uni(Dims D, MCoordTerms CT, MPairs PR,
+                                                                           const T* __restrict__ tab,
+                                                                           const T* __restrict__ ftab, int64_t L,
+                                                                           MetricOut<T> O, int nt, int kchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const int64_t L1 = L + 1;
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.x;  // j-fastest block order: resident warps share the xi rows in L1
+  const int64_t i0 = (int64_t)blockIdx.y * MAPPED_OUT;
+  const int nvalid = (int)(nw0 - i0 < MAPPED_OUT ? nw0 - i0 : MAPPED_OUT);
+  // lane 31 (and lanes past the row end) evaluate the cell nw0, i.e. the +xi neighbour of the last cell: the
+  // factor tables hold nw + 1 entries per axis; the operator tables hold nw (their values are not sent)
+  const int64_t i = i0 + lane < nw0 ? i0 + lane : nw0;
+  const int64_t ic = i < nw0 ? i : nw0 - 1;
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  const int np = PR.n;
+  T* const sg = reinterpret_cast<T*>(cg_dyn_smem);
+  T* const b10 = sg;
+  T* const b9 = sg + 2 * stage_len<T, 10>;
+  T* const pairU = sg + uni_stage_vals<T>;          // [np][UNI_PAIR]
+  T* const termU = pairU + (int64_t)np * UNI_PAIR;  // [3 positions][nt][UNI_TERM], flat (coordinate-ordered) term index
+  const T* const xrow = tab + ic * OP_COUNT;                   // + (p * 3) * L * OP_COUNT : xi row of pair p
+  const T* const yrow = tab + (L + j) * OP_COUNT;              // + (p * 3) * L * OP_COUNT : eta row of pair p
+  const T* const zrow = tab + 2 * L * OP_COUNT;                // + ((p * 3) * L + m) * OP_COUNT
+  const T* const fx = ftab + i * 4;                            // + (m * 3) * L1 * 4 : xi factor row of term m
+  const int64_t pstride = 3 * L * OP_COUNT, tstride = 3 * L1 * 4;
+
+  // ---- warp-uniform coefficient tables -------------------------------------------------------------------------
+  // pair p: U[0..14] such that, with x = the pair's xi row,
+  //   Gh[xi][xi]    += x.E0 U0               Gh[xi][eta]   += x.FD0 U1 + x.E1 U3    Gh[xi][zeta]  += x.FD0 U2 + x.E1 U4
+  //   Gh[eta][eta]  += x.D0 U5 + x.V1 U9     Gh[eta][zeta] += x.D0 U6 + x.V1 U10    Gh[eta][xi]   += x.V0 U13
+  //   Gh[zeta][zeta]+= x.D0 U7 + x.V1 U11    Gh[zeta][eta] += x.D0 U8 + x.V1 U12    Gh[zeta][xi]  += x.V0 U14
+  // ([face][row]; the column is the pair's).  zpre = the zeta row of the pair `lane`, loaded earlier.
+  auto pair_uniform = [&](int64_t mz, const T (&zpre)[OP_COUNT]) {
+    for (int p = lane; p < np; p += 32) {
+      T y[OP_COUNT], z[OP_COUNT];
+      ldg_vec<T, OP_COUNT>(yrow + p * pstride, y);
+      if (p == lane) {
+#pragma unroll
+        for (int o = 0; o < OP_COUNT; ++o) z[o] = zpre[o];
+      } else {
+        ldg_vec<T, OP_COUNT>(zrow + p * pstride + mz * OP_COUNT, z);
+      }
+      const T C = T(PR.coef[p]);
+#pragma unroll
+      for (int o = 0; o < OP_COUNT; ++o) z[o] *= C;
+      T u[UNI_PAIR];
+      u[0] = y[OP_V1] * z[OP_D0] - y[OP_D0] * z[OP_V1];
+      u[1] = y[OP_V0] * z[OP_V1];
+      u[2] = -(z[OP_V0] * y[OP_V1]);
+      u[3] = -(y[OP_V0] * z[OP_D0]);
+      u[4] = z[OP_V0] * y[OP_D0];
+      u[5] = y[OP_E0] * z[OP_V1];
+      u[6] = -(z[OP_V0] * y[OP_E1]);
+      u[7] = -(z[OP_E0] * y[OP_V1]);
+      u[8] = y[OP_V0] * z[OP_E1];
+      u[9] = -(y[OP_E0] * z[OP_D0]);
+      u[10] = z[OP_V0] * y[OP_FD0];
+      u[11] = z[OP_E0] * y[OP_D0];
+      u[12] = -(y[OP_V0] * z[OP_FD0]);
+      u[13] = y[OP_E1] * z[OP_D0] - y[OP_FD0] * z[OP_V1];
+      u[14] = z[OP_FD0] * y[OP_V1] - z[OP_E1] * y[OP_D0];
+      u[15] = T(0);
+      sts_vec<T, UNI_PAIR>(pairU + p * UNI_PAIR, u);
+    }
+  };
+  // term s (flat index), products P(a, b) = coef f_eta^(a) f_zeta^(b):
+  //   position 0 = (j, mA)     : [P00 P10 P01 P20 P11 P30 P21 -]   dF/dxi, d2F/dxi2, dF/deta, d2F/deta2 of the cell
+  //   position 1 = (j + 1, mA) : same products                      F, dF/deta, d2F/deta2 of the +eta neighbour
+  //   position 2 = (j, mC)     : [P00 P10 P01 P11 P02 P12 P03 -]   F, dF/dzeta, d2F/dzeta2 of the +zeta neighbour
+  // zA / zC: the zeta factor rows (4 derivative orders) of the term `lane` at mA / mC, loaded earlier.
+  auto term_uniform = [&](int64_t mA, int64_t mC, const T (&zA_pre)[4], const T (&zC_pre)[4]) {
+    for (int s = lane; s < nt; s += 32) {
+      const int m = CT.flat[s];
+      const T* const base = ftab + (int64_t)m * tstride;
+      T ya[4], yb[4], zA[4], zC[4];
+      ldg_vec<T, 4>(base + (L1 + j) * 4, ya);
+      ldg_vec<T, 4>(base + (L1 + j + 1) * 4, yb);
+      if (s == lane) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { zA[o] = zA_pre[o]; zC[o] = zC_pre[o]; }
+      } else {
+        ldg_vec<T, 4>(base + (2 * L1 + mA) * 4, zA);
+        ldg_vec<T, 4>(base + (2 * L1 + mC) * 4, zC);
+      }
+      const T c = T(CT.coef[s]);
+      T u[UNI_TERM];
+      {
+        const T z0 = c * zA[0], z1 = c * zA[1];
+        u[0] = ya[0] * z0; u[1] = ya[1] * z0; u[2] = ya[0] * z1; u[3] = ya[2] * z0;
+        u[4] = ya[1] * z1; u[5] = ya[3] * z0; u[6] = ya[2] * z1; u[7] = T(0);
+        sts_vec<T, UNI_TERM>(termU + (0 * nt + s) * UNI_TERM, u);
+        u[0] = yb[0] * z0; u[1] = yb[1] * z0; u[2] = yb[0] * z1; u[3] = yb[2] * z0;
+        u[4] = yb[1] * z1; u[5] = yb[3] * z0; u[6] = yb[2] * z1;
+        sts_vec<T, UNI_TERM>(termU + (1 * nt + s) * UNI_TERM, u);
+      }
+      {
+        const T y0 = c * ya[0], y1 = c * ya[1];
+        u[0] = y0 * zC[0]; u[1] = y1 * zC[0]; u[2] = y0 * zC[1]; u[3] = y1 * zC[1];
+        u[4] = y0 * zC[2]; u[5] = y1 * zC[2]; u[6] = y0 * zC[3];
+        sts_vec<T, UNI_TERM>(termU + (2 * nt + s) * UNI_TERM, u);
+      }
+    }
+  };
+  // the zeta rows a lane multiplies in the next uniform phase (first pass of the loops above)
+  auto load_zpair = [&](int64_t mz, T (&z)[OP_COUNT]) {
+    const int p = lane < np ? lane : np - 1;
+    ldg_vec<T, OP_COUNT>(zrow + p * pstride + mz * OP_COUNT, z);
+  };
+  auto load_zterm = [&](int64_t mz, T (&z)[4]) {
+    const int s = lane < nt ? lane : nt - 1;
+    ldg_vec<T, 4>(ftab + (int64_t)CT.flat[s] * tstride + (2 * L1 + mz) * 4, z);
+  };
+
+  // ---- per-lane accumulation over the terms: one multiply-add per (xi factor value, uniform product) -------------
+  // F, dF/dxi_2, d2F/dxi_2^2 at the +zeta position (termU position 2)
+  auto jac_zeta = [&](T (&F)[3][3], T (&Fp)[3][3], T (&Fpp)[3][3]) {
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) F[q][d] = Fp[q][d] = Fpp[q][d] = T(0);
+      for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
+        T a[4], u[UNI_TERM];
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
+        lds_vec<T, UNI_TERM>(termU + (2 * nt + s) * UNI_TERM, u);
+        F[q][0] += a[1] * u[0]; F[q][1] += a[0] * u[1]; F[q][2] += a[0] * u[2];
+        Fp[q][0] += a[1] * u[2]; Fp[q][1] += a[0] * u[3]; Fp[q][2] += a[0] * u[4];
+        Fpp[q][0] += a[1] * u[4]; Fpp[q][1] += a[0] * u[5]; Fpp[q][2] += a[0] * u[6];
+      }
+    }
+  };
+  // dF/dxi, d2F/dxi^2 of the cell (termU position 0)
+  auto jac_xi = [&](T (&Fp)[3][3], T (&Fpp)[3][3]) {
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Fp[q][d] = Fpp[q][d] = T(0);
+      for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
+        T a[4], u[4];
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
+        lds_vec<T, 4>(termU + (0 * nt + s) * UNI_TERM, u);
+        Fp[q][0] += a[2] * u[0]; Fp[q][1] += a[1] * u[1]; Fp[q][2] += a[1] * u[2];
+        Fpp[q][0] += a[3] * u[0]; Fpp[q][1] += a[2] * u[1]; Fpp[q][2] += a[2] * u[2];
+      }
+    }
+  };
+  // dF/deta, d2F/deta^2 of the cell (position 0) and F, dF/deta, d2F/deta^2 of the +eta neighbour (position 1)
+  auto jac_eta = [&](T (&Fp)[3][3], T (&Fpp)[3][3], T (&Fn)[3][3], T (&Fpn)[3][3], T (&Fppn)[3][3]) {
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Fp[q][d] = Fpp[q][d] = Fn[q][d] = Fpn[q][d] = Fppn[q][d] = T(0);
+      for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
+        T a[4], u[UNI_TERM], v[UNI_TERM];
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
+        lds_vec<T, UNI_TERM>(termU + (0 * nt + s) * UNI_TERM, u);
+        lds_vec<T, UNI_TERM>(termU + (1 * nt + s) * UNI_TERM, v);
+        Fp[q][0] += a[1] * u[1]; Fp[q][1] += a[0] * u[3]; Fp[q][2] += a[0] * u[4];
+        Fpp[q][0] += a[1] * u[3]; Fpp[q][1] += a[0] * u[5]; Fpp[q][2] += a[0] * u[6];
+        Fn[q][0] += a[1] * v[0]; Fn[q][1] += a[0] * v[1]; Fn[q][2] += a[0] * v[2];
+        Fpn[q][0] += a[1] * v[1]; Fpn[q][1] += a[0] * v[3]; Fpn[q][2] += a[0] * v[4];
+        Fppn[q][0] += a[1] * v[3]; Fppn[q][1] += a[0] * v[5]; Fppn[q][2] += a[0] * v[6];
+      }
+    }
+  };
+
+  // carried along zeta: F, G = inv F, det F and the zeta-axis L state of the cell of the current step
+  T Fc[3][3], Gc[3][3], Jc, Lz[3][3];
+  T zt_cur[4];  // zeta factor row of the term `lane` at the plane after the current one
+  {
+    // prologue: position 2 at (j, k0) gives the first cell; then the tables of step k0
+    T zp[OP_COUNT], za[4], zc[4];
+    load_zterm(k0, za);
+    term_uniform(k0, k0, za, za);
+    __syncwarp();
+    T Fp[3][3], Fpp[3][3], R2[3][3];
+    jac_zeta(Fc, Fp, Fpp);
+    Jc = inv3(Fc, Gc);
+    mapped_states3_g(Gc, Fp, Fpp, lam1, lam2, Lz, R2);
+    __syncwarp();
+    load_zpair(k0, zp);
+    load_zterm(k0 + 1, zc);
+    pair_uniform(k0, zp);
+    term_uniform(k0, k0 + 1, za, zc);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) zt_cur[o] = zc[o];
+    __syncwarp();
+  }
+  for (int64_t m = k0; m < k1; ++m) {
+    const int64_t cl0 = i0 + nw0 * (j + nw1 * m);
+    const bool more = m + 1 < k1;
+    // the zeta rows of the next step's pairs: requested now, multiplied after the conserved sums
+    T zp[OP_COUNT];
+    load_zpair(more ? m + 1 : m, zp);
+    // ---- conserved metrics: 15 multiply-adds per pair -------------------------------------------------------------
+    T Gh[3][3][3];  // [face][row][col]
+#pragma unroll
+    for (int f = 0; f < 3; ++f)
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Gh[f][rr][cc] = T(0);
+    {
+      T x[OP_COUNT], xn[OP_COUNT];
+      ldg_vec<T, OP_COUNT>(xrow, x);
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+#pragma unroll(MAPPED_UNROLL_P)
+        for (int p = PR.cstart[cc]; p < PR.cstart[cc + 1]; ++p) {
+          const int pn = p + 1 < np ? p + 1 : p;  // the last prefetch re-reads the last pair
+          ldg_vec<T, OP_COUNT>(xrow + pn * pstride, xn);
+          T u[UNI_PAIR];
+          lds_vec<T, UNI_PAIR>(pairU + p * UNI_PAIR, u);
+          Gh[0][0][cc] += x[OP_E0] * u[0];
+          Gh[0][1][cc] += x[OP_FD0] * u[1] + x[OP_E1] * u[3];
+          Gh[0][2][cc] += x[OP_FD0] * u[2] + x[OP_E1] * u[4];
+          Gh[1][1][cc] += x[OP_D0] * u[5] + x[OP_V1] * u[9];
+          Gh[1][2][cc] += x[OP_D0] * u[6] + x[OP_V1] * u[10];
+          Gh[1][0][cc] += x[OP_V0] * u[13];
+          Gh[2][2][cc] += x[OP_D0] * u[7] + x[OP_V1] * u[11];
+          Gh[2][1][cc] += x[OP_D0] * u[8] + x[OP_V1] * u[12];
+          Gh[2][0][cc] += x[OP_V0] * u[14];
+#pragma unroll
+          for (int o = 0; o < OP_COUNT; ++o) x[o] = xn[o];
+        }
+      }
+    }
+    // ---- phase 0: cell arrays + the three conserved arrays ------------------------------------------------------------
+    bulk_wait_read();  // the TMA unit has finished reading last step's staging buffers (lanes > 0 own no groups)
+    __syncwarp();      // ... and every lane has read pairU
+    {
+      Stage<T, 10> Scf(O.cell_fwd, cl0, b10), Sci(O.cell_inv, cl0, b10 + stage_len<T, 10>);
+      Stage<T, 9> Sc0(O.face_cons[0], cl0, b9), Sc1(O.face_cons[1], cl0, b9 + stage_len<T, 9>),
+          Sc2(O.face_cons[2], cl0, b9 + 2 * stage_len<T, 9>);
+      put10(Scf.slot(lane), Fc, Jc);  // every lane stages (no branch); slots >= nvalid are never sent
+      put10(Sci.slot(lane), Gc, Jc);
+      put9(Sc0.slot(lane), Gh[0]);
+      put9(Sc1.slot(lane), Gh[1]);
+      put9(Sc2.slot(lane), Gh[2]);
+      if (more) pair_uniform(m + 1, zp);  // next step's pair coefficients (pairU is free: barrier above)
+      fence_async_smem();
+      __syncwarp();
+      Scf.issue(nvalid, lane);
+      Sci.issue(nvalid, lane);
+      Sc0.issue(nvalid, lane);
+      Sc1.issue(nvalid, lane);
+      Sc2.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    }
+    // the zeta factor rows the next step's term products need (plane m + 2)
+    T zt_next[4];
+    load_zterm(m + 2 <= nw2 ? m + 2 : nw2, zt_next);
+    // ---- reconstructed inverse Jacobian on the three faces ----------------------------------------------------------
+    auto face_out = [&](int f, const T (&Gf)[3][3]) {
+      T Ff[3][3];
+      const T J = rcp(inv3(Gf, Ff));  // det(F_face) = 1 / det(G_face)
+      bulk_wait_read();               // the previous phase has left the two Metric buffers
+      __syncwarp();
+      Stage<T, 10> Sff(O.face_fwd[f], cl0, b10), Sfi(O.face_inv[f], cl0, b10 + stage_len<T, 10>);
+      put10(Sff.slot(lane), Ff, J);
+      put10(Sfi.slot(lane), Gf, J);
+      fence_async_smem();
+      __syncwarp();
+      Sff.issue(nvalid, lane);
+      Sfi.issue(nvalid, lane);
+      if (lane == 0) bulk_commit();
+    };
+    {  // xi face: the +xi neighbour's R state by shuffle
+      T Fp[3][3], Fpp[3][3], L0[3][3], R0[3][3], Gf[3][3];
+      jac_xi(Fp, Fpp);
+      mapped_states3_g(Gc, Fp, Fpp, lam1, lam2, L0, R0);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (L0[a][b] + __shfl_down_sync(FULLMASK, R0[a][b], 1));
+      face_out(0, Gf);
+    }
+    {  // eta face: the +eta neighbour is recomputed (9 multiply-adds per term)
+      T Fp[3][3], Fpp[3][3], Fn[3][3], Fpn[3][3], Fppn[3][3], L1s[3][3], R1s[3][3], Gn[3][3], Ln[3][3], Rn[3][3], Gf[3][3];
+      jac_eta(Fp, Fpp, Fn, Fpn, Fppn);
+      mapped_states3_g(Gc, Fp, Fpp, lam1, lam2, L1s, R1s);
+      inv3(Fn, Gn);
+      mapped_states3_g(Gn, Fpn, Fppn, lam1, lam2, Ln, Rn);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (L1s[a][b] + Rn[a][b]);
+      face_out(1, Gf);
+    }
+    {  // zeta face: the +zeta neighbour is the cell of the next step; its F, G, J and L state are carried
+      T Fp[3][3], Fpp[3][3], Ln[3][3], Rn[3][3], Gf[3][3];
+      jac_zeta(Fc, Fp, Fpp);
+      Jc = inv3(Fc, Gc);
+      mapped_states3_g(Gc, Fp, Fpp, lam1, lam2, Ln, Rn);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          Gf[a][b] = T(0.5) * (Lz[a][b] + Rn[a][b]);
+          Lz[a][b] = Ln[a][b];
+        }
+      face_out(2, Gf);
+    }
+    // ---- next step's term products ------------------------------------------------------------------------------------
+    __syncwarp();  // every lane has read termU
+    if (more) term_uniform(m + 1, m + 2 <= nw2 ? m + 2 : nw2, zt_cur, zt_next);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) zt_cur[o] = zt_next[o];
+    __syncwarp();
+  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
+}
+
+template <class T>
+inline bool launch_mapped_metrics3d_uni(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* ftab,
+                                        int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
+  const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT);
+  if (gx > 65535u || D.nw[1] <= 0) return false;
+  const int smem = (int)((uni_stage_vals<T> + (int64_t)PR.n * UNI_PAIR + 3 * (int64_t)TM.n * UNI_TERM) * sizeof(T));
+  int per_sm = (int)(200 * 1024 / (smem + 1024));
+  if (per_sm > CG_UNI_MINB) per_sm = CG_UNI_MINB;
+  if (per_sm < 1) return false;
+  const int kchunk = pick_chunk((int64_t)gx * D.nw[1], D.nw[2], 148LL * per_sm, 32, 1.0);
+  const dim3 grid((unsigned)D.nw[1], gx, (unsigned)((D.nw[2] + kchunk - 1) / kchunk));
+  const MCoordTerms CT = coord_terms(TM);
+  auto go = [&](auto kern) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
+    kern<<<grid, 32, smem, st>>>(D, CT, PR, tab, ftab, L, O, TM.n, kchunk);
+    return true;
+  };
+  if (scheme == ENDPOINT) return go(k_mapped_metrics3d_uni<T, ENDPOINT>);
+  if (scheme == GRADIENT) return go(k_mapped_metrics3d_uni<T, GRADIENT>);
+  return go(k_mapped_metrics3d_uni<T, CURVATURE>);
+}
+
 
 // ---------------------------------------------------------------------------
 // ADThomasLombardMetric as its OWN kernel (metrics.jl:607-668 closures, pair tables :2336-3080, fill :3082-3188), FULL
