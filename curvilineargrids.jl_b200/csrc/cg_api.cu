@@ -16,6 +16,7 @@
 #include "cg_kernels_ref.cuh"
 #include "cg_kernels_tiled.cuh"
 #include "cg_mapped.cuh"
+#include "cg_mapped_split.cuh"
 
 namespace {
 
@@ -315,10 +316,20 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
       ok = cg::launch_mapped_adtl3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, (const T*)g->mtab.fhalf, g->mtab.L, O, st);
       adtl_done = true;
     } else if (full_cf) {
-      // debug switch CG_MAPPED_KERNEL=staged: the round-1 kernel (every lane multiplies all three table rows)
-      static const bool old_kernel = [] { const char* e = getenv("CG_MAPPED_KERNEL"); return e && std::string(e) == "staged"; }();
+      // debug switch CG_MAPPED_KERNEL: staged = the round-1 kernel (every lane multiplies all three table rows), uni = one
+      // kernel with the warp-uniform products factored out; default = the four light kernels of cg_mapped_split.cuh
+      static const int which = [] {
+        const char* e = getenv("CG_MAPPED_KERNEL");
+        return !e ? 0 : (std::string(e) == "staged" ? 2 : (std::string(e) == "uni" ? 1 : 0));
+      }();
       ok = false;
-      if (!old_kernel && TM.n >= 1 && g->mtab.pairs.n >= 1)
+      if (which == 0) {
+        const int nl = cg::launch_mapped_metrics3d_split<T>(D, TM, g->mtab.pairs, tab, (const T*)g->mtab.tabx, ftab, g->mtab.L, O, g->scheme, st);
+        if (nl < 0) return fail(CG_ERR_CUDA, "MappedGrid kernels: cannot set the shared-memory size");
+        ok = nl > 0;
+        if (ok) g_launches += nl - 1;
+      }
+      if (!ok && which <= 1 && TM.n >= 1 && g->mtab.pairs.n >= 1)
         ok = cg::launch_mapped_metrics3d_uni<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
       if (!ok) ok = cg::launch_mapped_metrics3d_staged<T>(D, TM, g->mtab.pairs, tab, ftab, g->mtab.L, O, g->scheme, st);
     } else {

@@ -92,7 +92,7 @@ __host__ __device__ inline double cell_centre(const Dims& D, int d, int64_t idx)
 // aligned), so a cell reads them with three 16-byte loads per axis
 // ---------------------------------------------------------------------------
 template <class T>
-__global__ void k_mapped_tables(Dims D, MTerms TM, MPairs PR, double lam1, double lam2, T* tab, int64_t L) {
+__global__ void k_mapped_tables(Dims D, MTerms TM, MPairs PR, double lam1, double lam2, T* tab, int64_t L, T* tabx = nullptr, int64_t Lx = 0) {
   const int64_t ntot = (int64_t)PR.n * 3 * L;
   for (int64_t lin = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lin < ntot;
        lin += (int64_t)gridDim.x * blockDim.x) {
@@ -139,6 +139,13 @@ __global__ void k_mapped_tables(Dims D, MTerms TM, MPairs PR, double lam1, doubl
         base[OP_V1] = T(hn[1][0]);
         base[OP_E1] = T(En[1][0]);
       }
+    }
+    // xi axis, transposed copy tabx[(p * OP_COUNT + op) * Lx + I] (Lx = L rounded up to 16 values, so every row starts
+    // on a 128-byte line): a warp whose lanes are consecutive cells reads one operator value of a pair as one
+    // contiguous, aligned 256-byte segment (k_mapped_cons_uni)
+    if (tabx && d == 0) {
+      const T* base = tab + ((int64_t)(p * 3) * L + I) * OP_COUNT;
+      for (int o = 0; o < OP_COUNT; ++o) tabx[((int64_t)p * OP_COUNT + o) * Lx + I] = base[o];
     }
   }
 }
@@ -719,6 +726,13 @@ template <class T> constexpr int uni_stage_vals = 2 * stage_len<T, 10> + 3 * sta
 #ifndef CG_UNI_MINB
 #define CG_UNI_MINB 8
 #endif
+#ifndef CG_UNI_UNROLL_T
+#define CG_UNI_UNROLL_T 2
+#endif
+#ifndef CG_UNI_UNROLL_P
+#define CG_UNI_UNROLL_P 2
+#endif
+constexpr int UNI_UNROLL_T = CG_UNI_UNROLL_T, UNI_UNROLL_P = CG_UNI_UNROLL_P;
 template <class T, int SCH>
 __global__ void __launch_bounds__(32, CG_UNI_MINB) k_mapped_metrics3d_uni(Dims D, MCoordTerms CT, MPairs PR,
                                                                            const T* __restrict__ tab,
@@ -841,53 +855,74 @@ __global__ void __launch_bounds__(32, CG_UNI_MINB) k_mapped_metrics3d_uni(Dims D
   // F, dF/dxi_2, d2F/dxi_2^2 at the +zeta position (termU position 2)
   auto jac_zeta = [&](T (&F)[3][3], T (&Fp)[3][3], T (&Fpp)[3][3]) {
     int s = 0;
+    T a[4], an[4], u[UNI_TERM], un[UNI_TERM];
+    ldg_vec<T, 4>(fx + (int64_t)CT.flat[0] * tstride, a);
+    lds_vec<T, UNI_TERM>(termU + (2 * nt) * UNI_TERM, u);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) F[q][d] = Fp[q][d] = Fpp[q][d] = T(0);
+#pragma unroll(UNI_UNROLL_T)
       for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
-        T a[4], u[UNI_TERM];
-        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
-        lds_vec<T, UNI_TERM>(termU + (2 * nt + s) * UNI_TERM, u);
+        // the rows of the NEXT term are requested before this one is accumulated (flat[] and termU carry a sentinel)
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s + 1] * tstride, an);
+        lds_vec<T, UNI_TERM>(termU + (2 * nt + s + 1) * UNI_TERM, un);
         F[q][0] += a[1] * u[0]; F[q][1] += a[0] * u[1]; F[q][2] += a[0] * u[2];
         Fp[q][0] += a[1] * u[2]; Fp[q][1] += a[0] * u[3]; Fp[q][2] += a[0] * u[4];
         Fpp[q][0] += a[1] * u[4]; Fpp[q][1] += a[0] * u[5]; Fpp[q][2] += a[0] * u[6];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a[o] = an[o];
+#pragma unroll
+        for (int o = 0; o < UNI_TERM; ++o) u[o] = un[o];
       }
     }
   };
   // dF/dxi, d2F/dxi^2 of the cell (termU position 0)
   auto jac_xi = [&](T (&Fp)[3][3], T (&Fpp)[3][3]) {
     int s = 0;
+    T a[4], an[4], u[4], un[4];
+    ldg_vec<T, 4>(fx + (int64_t)CT.flat[0] * tstride, a);
+    lds_vec<T, 4>(termU, u);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) Fp[q][d] = Fpp[q][d] = T(0);
+#pragma unroll(UNI_UNROLL_T)
       for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
-        T a[4], u[4];
-        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
-        lds_vec<T, 4>(termU + (0 * nt + s) * UNI_TERM, u);
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s + 1] * tstride, an);
+        lds_vec<T, 4>(termU + (0 * nt + s + 1) * UNI_TERM, un);
         Fp[q][0] += a[2] * u[0]; Fp[q][1] += a[1] * u[1]; Fp[q][2] += a[1] * u[2];
         Fpp[q][0] += a[3] * u[0]; Fpp[q][1] += a[2] * u[1]; Fpp[q][2] += a[2] * u[2];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { a[o] = an[o]; u[o] = un[o]; }
       }
     }
   };
   // dF/deta, d2F/deta^2 of the cell (position 0) and F, dF/deta, d2F/deta^2 of the +eta neighbour (position 1)
   auto jac_eta = [&](T (&Fp)[3][3], T (&Fpp)[3][3], T (&Fn)[3][3], T (&Fpn)[3][3], T (&Fppn)[3][3]) {
     int s = 0;
+    T a[4], an[4], u[UNI_TERM], un[UNI_TERM], v[UNI_TERM], vn[UNI_TERM];
+    ldg_vec<T, 4>(fx + (int64_t)CT.flat[0] * tstride, a);
+    lds_vec<T, UNI_TERM>(termU, u);
+    lds_vec<T, UNI_TERM>(termU + nt * UNI_TERM, v);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
 #pragma unroll
       for (int d = 0; d < 3; ++d) Fp[q][d] = Fpp[q][d] = Fn[q][d] = Fpn[q][d] = Fppn[q][d] = T(0);
+#pragma unroll(UNI_UNROLL_T)
       for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
-        T a[4], u[UNI_TERM], v[UNI_TERM];
-        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
-        lds_vec<T, UNI_TERM>(termU + (0 * nt + s) * UNI_TERM, u);
-        lds_vec<T, UNI_TERM>(termU + (1 * nt + s) * UNI_TERM, v);
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s + 1] * tstride, an);
+        lds_vec<T, UNI_TERM>(termU + (0 * nt + s + 1) * UNI_TERM, un);
+        lds_vec<T, UNI_TERM>(termU + (1 * nt + s + 1) * UNI_TERM, vn);
         Fp[q][0] += a[1] * u[1]; Fp[q][1] += a[0] * u[3]; Fp[q][2] += a[0] * u[4];
         Fpp[q][0] += a[1] * u[3]; Fpp[q][1] += a[0] * u[5]; Fpp[q][2] += a[0] * u[6];
         Fn[q][0] += a[1] * v[0]; Fn[q][1] += a[0] * v[1]; Fn[q][2] += a[0] * v[2];
         Fpn[q][0] += a[1] * v[1]; Fpn[q][1] += a[0] * v[3]; Fpn[q][2] += a[0] * v[4];
         Fppn[q][0] += a[1] * v[3]; Fppn[q][1] += a[0] * v[5]; Fppn[q][2] += a[0] * v[6];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a[o] = an[o];
+#pragma unroll
+        for (int o = 0; o < UNI_TERM; ++o) { u[o] = un[o]; v[o] = vn[o]; }
       }
     }
   };
@@ -929,16 +964,16 @@ __global__ void __launch_bounds__(32, CG_UNI_MINB) k_mapped_metrics3d_uni(Dims D
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) Gh[f][rr][cc] = T(0);
     {
-      T x[OP_COUNT], xn[OP_COUNT];
+      T x[OP_COUNT], xn[OP_COUNT], u[UNI_PAIR], un[UNI_PAIR];
       ldg_vec<T, OP_COUNT>(xrow, x);
+      lds_vec<T, UNI_PAIR>(pairU, u);
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
-#pragma unroll(MAPPED_UNROLL_P)
+#pragma unroll(UNI_UNROLL_P)
         for (int p = PR.cstart[cc]; p < PR.cstart[cc + 1]; ++p) {
           const int pn = p + 1 < np ? p + 1 : p;  // the last prefetch re-reads the last pair
           ldg_vec<T, OP_COUNT>(xrow + pn * pstride, xn);
-          T u[UNI_PAIR];
-          lds_vec<T, UNI_PAIR>(pairU + p * UNI_PAIR, u);
+          lds_vec<T, UNI_PAIR>(pairU + pn * UNI_PAIR, un);
           Gh[0][0][cc] += x[OP_E0] * u[0];
           Gh[0][1][cc] += x[OP_FD0] * u[1] + x[OP_E1] * u[3];
           Gh[0][2][cc] += x[OP_FD0] * u[2] + x[OP_E1] * u[4];
@@ -950,6 +985,8 @@ __global__ void __launch_bounds__(32, CG_UNI_MINB) k_mapped_metrics3d_uni(Dims D
           Gh[2][0][cc] += x[OP_V0] * u[14];
 #pragma unroll
           for (int o = 0; o < OP_COUNT; ++o) x[o] = xn[o];
+#pragma unroll
+          for (int o = 0; o < UNI_PAIR; ++o) u[o] = un[o];
         }
       }
     }
@@ -1044,7 +1081,7 @@ inline bool launch_mapped_metrics3d_uni(const Dims& D, const MTerms& TM, const M
                                         int64_t L, const MetricOut<T>& O, int scheme, cudaStream_t st) {
   const unsigned gx = (unsigned)((D.nw[0] + MAPPED_OUT - 1) / MAPPED_OUT);
   if (gx > 65535u || D.nw[1] <= 0) return false;
-  const int smem = (int)((uni_stage_vals<T> + (int64_t)PR.n * UNI_PAIR + 3 * (int64_t)TM.n * UNI_TERM) * sizeof(T));
+  const int smem = (int)((uni_stage_vals<T> + (int64_t)PR.n * UNI_PAIR + (3 * (int64_t)TM.n + 1) * UNI_TERM) * sizeof(T));
   int per_sm = (int)(200 * 1024 / (smem + 1024));
   if (per_sm > CG_UNI_MINB) per_sm = CG_UNI_MINB;
   if (per_sm < 1) return false;
@@ -1485,6 +1522,7 @@ struct MappedTables {
   bool dirty = true;
   int launches = 0;
   void* tab = nullptr;
+  void* tabx = nullptr;   // xi rows of `tab`, transposed (one array per operator)
   void* ftab = nullptr;
   void* fhalf = nullptr;  // factor tables at centre + 1/2 (ADThomasLombardMetric only)
   void* ctab = nullptr;   // factor values at nodes and centres (coordinates)
@@ -1495,14 +1533,16 @@ struct MappedTables {
   MPairs pairs;
   void free_all() {
     if (tab) cudaFree(tab);
+    if (tabx) cudaFree(tabx);
     if (ftab) cudaFree(ftab);
     if (fhalf) cudaFree(fhalf);
     if (ctab) cudaFree(ctab);
-    tab = ftab = fhalf = ctab = nullptr;
+    tab = tabx = ftab = fhalf = ctab = nullptr;
     tab_bytes = ftab_bytes = fhalf_bytes = ctab_bytes = 0;
   }
 };
 
+inline int64_t mapped_lx(int64_t L) { return (L + 15) & ~int64_t(15); }  // row stride of the transposed xi table
 // returns 0 ok, 1 too many terms, 2 too many pairs, 3 cuda error
 template <class T>
 inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, double t, const Dims& D, int scheme,
@@ -1556,7 +1596,11 @@ inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, dou
   const size_t fb = (size_t)nt * 3 * 4 * (L + 1) * sizeof(T);
   if (tb > M.tab_bytes) {
     if (M.tab) cudaFree(M.tab);
+    if (M.tabx) cudaFree(M.tabx);
+    M.tab = M.tabx = nullptr;
+    M.tab_bytes = 0;
     if (cudaMalloc(&M.tab, tb) != cudaSuccess) return 3;
+    if (cudaMalloc(&M.tabx, (tb / 3 / L) * mapped_lx(L)) != cudaSuccess) return 3;
     M.tab_bytes = tb;
   }
   if (fb > M.ftab_bytes) {
@@ -1569,7 +1613,7 @@ inline int mapped_prepare(MappedTables& M, const std::vector<double>& table, dou
   TMd.n = nt;  // device loops over real terms only; the unit term is addressed by index nt
   if (M.pairs.n > 0) {
     const int64_t n = (int64_t)M.pairs.n * 3 * L;
-    k_mapped_tables<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(D, TMd, M.pairs, lam1, lam2, (T*)M.tab, L);
+    k_mapped_tables<T><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(D, TMd, M.pairs, lam1, lam2, (T*)M.tab, L, D.dim == 3 ? (T*)M.tabx : nullptr, mapped_lx(L));
     M.launches++;
   }
   {

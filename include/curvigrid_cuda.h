@@ -25,8 +25,9 @@
  *   CG_CONCURRENT=0      launch the three 3-D face kernels of a SMALL grid serially instead of on forked streams
  *   CG_2D_STAGED=0       2-D FULL cell+face: use the pair kernel instead of the staged (TMA) kernel
  *   CG_MAPPED_NCHUNK=n   MappedGrid 3-D kernel: number of chunks along k (default: wave-aware choice)
- *   CG_MAPPED_KERNEL=staged  MappedGrid 3-D FULL: the round-1 kernel (every lane multiplies all three table rows)
- *                        instead of k_mapped_metrics3d_uni (warp-uniform eta/zeta products)
+ *   CG_MAPPED_KERNEL=staged|uni  MappedGrid 3-D FULL: the round-1 kernel (every lane multiplies all three table rows) or
+ *                        the single kernel with warp-uniform eta/zeta products, instead of the four light kernels
+ *                        (k_mapped_cons_uni + k_mapped_face_uni<0,1,2>)
  *   CG_FUSE_XZ=1         3-D FULL cell+face: the fused xi+zeta kernel (k_face_xz, an experiment: slower than the
  *                        two kernels it replaces) instead of k_face_xi + k_face_zeta
  *   CG_NCCL_LIB=path     libnccl to dlopen when the process has not loaded one (default libnccl.so.2)
