@@ -22,6 +22,7 @@
 #include <cfloat>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/curvigrid_cuda.h"
 
@@ -58,9 +59,26 @@ __device__ __forceinline__ bool isapprox(double a, double b, double rtol, double
   if (!isfinite(a) || !isfinite(b)) return false;
   return fabs(a - b) <= fmax(atol, rtol * fmax(fabs(a), fabs(b)));
 }
+// tol_diff(a, b) = isapprox(a, b; rtol = sqrt(eps), atol = 10 eps) ? (a - b) * 0 : a - b   (derivative_stencils.jl).
+// Branch-free form with the same value for every input: isapprox is "a == b, or both finite and
+// |a - b| <= max(atol, rtol max(|a|, |b|))".  max(|a|, |b|) is taken on the bit patterns (for non-negative doubles the
+// unsigned integer order is the numeric order; sm_100a has no FP64 min/max instruction, fmax expands into ~10), a NaN
+// or an infinity shows as an all-ones exponent of that maximum; a == b finite gives d = 0 <= atol, a == b infinite
+// gives d = NaN on either path.
 __device__ __forceinline__ double tol_diff(double a, double b) {
-  double d = a - b;
-  return isapprox(a, b, 1.4901161193847656e-08 /* sqrt(eps) */, 10 * DBL_EPSILON) ? d * 0.0 : d;
+  const double d = a - b;
+  const unsigned ahi = (unsigned)__double2hiint(a) & 0x7fffffffu, bhi = (unsigned)__double2hiint(b) & 0x7fffffffu;
+  const unsigned alo = (unsigned)__double2loint(a), blo = (unsigned)__double2loint(b);
+  const bool agt = ahi > bhi || (ahi == bhi && alo > blo);
+  const unsigned mhi = agt ? ahi : bhi, mlo = agt ? alo : blo;  // bits of max(|a|, |b|)
+  const bool fin = mhi < 0x7ff00000u;
+  const double thr = 1.4901161193847656e-08 /* sqrt(eps) */ * __hiloint2double((int)mhi, (int)mlo);
+  unsigned near;  // |d| <= thr || |d| <= atol as two predicated compares (the compiler would build max(thr, atol))
+  asm("{\n\t.reg .pred p;\n\t.reg .f64 ad;\n\tabs.f64 ad, %1;\n\tsetp.le.f64 p, ad, %2;\n\t"
+      "setp.le.or.f64 p, ad, %3, p;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(near)
+      : "d"(d), "d"(thr), "d"(10 * DBL_EPSILON));
+  return (fin && near) ? d * 0.0 : d;
 }
 __device__ __forceinline__ double clip(double v, double e) { return fabs(v) >= e ? v : v * 0.0; }
 __device__ __forceinline__ double central6(double m3, double m2, double m1, double p1, double p2, double p3) {
@@ -301,6 +319,317 @@ __global__ void k_legacy_inv2d(LShape S, LBox dom, const double* __restrict__ fw
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fused passes (round 2).  One block owns a tile of T cells along the derivative axis x LN lines and runs the three
+// array passes of a derivative (first derivative, second derivative, MEG reconstruction or edge interpolation) through
+// shared memory: the source field is read ONCE (products a*b / a*b - c*d formed on the fly, never materialised), d1 and
+// the half-jump h = 1/2 d1 + 1/12 d2 never touch global memory.  Every value is produced by the same device functions,
+// in the same order, as the pass-by-pass kernels above (bit-identical by construction; CG_LEGACY_FUSED=0 runs the old
+// path, tests compare the two bit for bit).  The stencils are selected from the ABSOLUTE position along the axis, so a
+// tile near the ends of the domain extends its ranges to the six-point one-sided windows:
+//   h  on [t0-1, t1+1)                        (interp: [t0, t1+1))
+//   d1 on the h range +-1,  and [0,6) / [n-6,n) when the h range touches the first / last three cells
+//   phi on the d1 range +-3, and [0,6) / [n-6,n) likewise                       (all clamped to [0, n))
+// axis != 0: lines = 32 consecutive xi (lanes, coalesced), T = 56 positions walked by the 8 warps;
+// axis == 0: lines = 8 consecutive eta rows (warps), T = 118 positions along xi (lanes, coalesced).
+// Several fields (jobs) share one launch through blockIdx.y.
+// ---------------------------------------------------------------------------
+// one-sided six-point stencils as ONE code path: row 0..2 = mixed_lo(which = row), row 3..5 = mixed_hi(which = row - 3).
+// The products are the same doubles as in mixed_lo / mixed_hi (x * 1 and x * -1 are exact), so the result is bit-identical,
+// but lanes of one warp that need different rows do not serialise three variants.
+__constant__ double LEGACY_EDGE[6][6] = {
+    {-137.0 / 60.0, 5.0, -5.0, 10.0 / 3.0, -(5.0 / 4.0), 1.0 / 5.0},
+    {-1.0 / 5.0, -(13.0 / 12.0), 2.0, -1.0, 1.0 / 3.0, -(1.0 / 20.0)},
+    {1.0 / 20.0, -(1.0 / 2.0), -(1.0 / 3.0), 1.0, -(1.0 / 4.0), 1.0 / 30.0},
+    {-1.0 / 30.0, 1.0 / 4.0, -1.0, 1.0 / 3.0, 1.0 / 2.0, -(1.0 / 20.0)},
+    {1.0 / 20.0, -(1.0 / 3.0), 1.0, -2.0, 13.0 / 12.0, 1.0 / 5.0},
+    {-1.0 / 5.0, 5.0 / 4.0, -(10.0 / 3.0), 5.0, -5.0, 137.0 / 60.0}};
+__device__ __forceinline__ double mixed_edge(const double* w, int row) {
+  double v[6];
+#pragma unroll
+  for (int m = 0; m < 6; ++m) v[m] = LEGACY_EDGE[row][m] * w[m];
+  return clip(kahan6(v), 50 * DBL_EPSILON);
+}
+
+struct LJob {
+  const double *a, *b, *c, *d;  // source = a | a*b | a*b - c*d
+  double* out;
+};
+constexpr int LMAXJ = 19;
+struct LJobs {
+  LJob j[LMAXJ];
+};
+enum { OP_CCD = 0, OP_CCD_POST = 1, OP_INTERP = 2 };
+
+template <bool AX0, int SRC, int OP>
+__global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int axis, int whole, LJobs jobs, double scale) {
+  constexpr int T = AX0 ? 118 : 56, LN = AX0 ? 8 : 32, PS = AX0 ? 32 : 8;
+  constexpr int WP = T + 10, WD = T + 5, WH = T + 2;
+  constexpr int LS = AX0 ? 1 : LN;  // shared-memory stride between consecutive positions of a line
+  constexpr int IT_P = (WP + PS - 1) / PS, IT_D = (WD + PS - 1) / PS, IT_H = (WH + PS - 1) / PS, IT_O = (T + PS - 1) / PS;
+  __shared__ double sphi[LN * WP], sd1[LN * WD], sh[LN * WH];
+  const LJob J = jobs.j[blockIdx.y];
+  const int n = dom.hi[axis] - dom.lo[axis];
+  const int ntile = (n + T - 1) / T;
+  const int la = AX0 ? 1 : 0;                      // axis the lines are counted along
+  const int oa = AX0 ? 2 : (axis == 1 ? 2 : 1);    // the remaining axis
+  const int nl = dom.hi[la] - dom.lo[la], ngr = (nl + LN - 1) / LN;
+  unsigned bb = blockIdx.x;
+  const int tile = (int)(bb % (unsigned)ntile);
+  bb /= (unsigned)ntile;
+  const int gr = (int)(bb % (unsigned)ngr), oi = (int)(bb / (unsigned)ngr);
+  const int t0 = tile * T, t1 = min(t0 + T, n);
+  // ranges (absolute positions along the axis, [lo, hi))
+  const int hl = OP == OP_INTERP ? t0 : max(0, t0 - 1), hh = min(n, t1 + 1);
+  int dl = max(0, hl - 1), dh = min(n, hh + 1);
+  if (hl < 3) dh = max(dh, 6);
+  if (hh > n - 3) dl = min(dl, n - 6);
+  int pl = max(0, dl - 3), ph = min(n, dh + 3);
+  if (dl < 3) ph = max(ph, 6);
+  if (dh > n - 3) pl = min(pl, n - 6);
+  const int line = AX0 ? threadIdx.y : threadIdx.x, p0 = AX0 ? threadIdx.x : threadIdx.y;
+  const int li = gr * LN + line;
+  const bool lok = li < nl;
+  const long long s = S.st[axis];
+  const long long base = (long long)(dom.lo[la] + li) * S.st[la] + (long long)(dom.lo[oa] + oi) * S.st[oa] +
+                         (long long)dom.lo[axis] * s;  // array index of position 0 of this line
+  // per-line shared-memory rows; X_at(p) = address of absolute position p
+  double* const phi_l = sphi + (AX0 ? line * WP : line) - pl * LS;
+  double* const d1_l = sd1 + (AX0 ? line * WD : line) - dl * LS;
+  double* const h_l = sh + (AX0 ? line * WH : line) - hl * LS;
+  // ---- phase 1: source field ----
+  if (lok) {
+    long long I = base + (long long)(pl + p0) * s;
+#pragma unroll
+    for (int k = 0; k < IT_P; ++k, I += PS * s) {
+      const int p = pl + p0 + PS * k;
+      if (p < ph) phi_l[p * LS] = src_val<SRC>(J.a, J.b, J.c, J.d, I);
+    }
+  }
+  __syncthreads();
+  // Compute phases.  AX0 = false: warp w owns the CHUNK of 8 consecutive positions lo + 8 w .. lo + 8 w + 7 of its 32
+  // lines; a chunk that lies in the central-stencil region reads its window once into registers (14 values for 8 first
+  // derivatives instead of 48) — the register-blocked sweep along the derivative axis.  Chunks that touch the one-sided
+  // regions or the end of a range, and the AX0 = true layout (lanes along the axis), take the per-position path.
+  constexpr int CK = 8;
+  auto d1_at = [&](int p) {  // k_legacy_first at absolute position p
+    double r;
+    if (p >= 3 && p < n - 3) {
+      const double* q = phi_l + p * LS;
+      r = central6(q[-3 * LS], q[-2 * LS], q[-LS], q[LS], q[2 * LS], q[3 * LS]);
+    } else {
+      const bool low = p < 3;
+      const double* q = phi_l + (low ? 0 : n - 6) * LS;
+      double w[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) w[m] = q[m * LS];
+      r = mixed_edge(w, low ? p : p - (n - 6));
+    }
+    d1_l[p * LS] = r;
+  };
+  auto h_at = [&](int p) {  // k_legacy_second at p and the half-jump of the MEG states: phiL = f + h, phiR = f - h
+    const double* d = d1_l + p * LS;
+    double r;
+    if (p >= 3 && p < n - 3) {
+      const double* q = phi_l + p * LS;
+      const double dd = -tol_diff(d[LS], d[-LS]) / 2;
+      r = kahan3(2 * (q[LS] + q[-LS]), -4 * q[0], dd);
+    } else {
+      const bool low = p < 3;
+      const double* q = d1_l + (low ? 0 : n - 6) * LS;
+      double w[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) w[m] = q[m * LS];
+      r = mixed_edge(w, low ? p : p - (n - 6));
+    }
+    h_l[p * LS] = (1.0 / 2.0) * d[0] + (1.0 / 12.0) * r;
+  };
+  const double e50 = 50 * DBL_EPSILON;
+  const int first = whole ? 1 : 0, last = whole ? n - 2 : n - 1;  // interp: positions written (k_legacy_interp)
+  auto out_at = [&](int p) {  // k_legacy_meg / k_legacy_interp at p
+    const double* q = phi_l + p * LS;
+    const double* h = h_l + p * LS;
+    double* o = J.out + base + (long long)p * s;
+    const double L0 = q[0] + h[0];
+    if (OP == OP_INTERP) {
+      if (p < first || p > last) return;
+      if (p == last) o[0] = L0;
+      else o[0] = (L0 + (q[LS] - h[LS])) / 2;
+      if (p == first) o[-s] = q[0] - h[0];
+    } else {
+      const double R0 = q[0] - h[0];
+      double hi, lw;
+      if (p == n - 1) hi = L0;
+      else hi = (L0 + (q[LS] - h[LS])) / 2;
+      if (p == 0) lw = R0;
+      else lw = ((q[-LS] + h[-LS]) + R0) / 2;
+      const double v = clip(hi - lw, e50);
+      if (OP == OP_CCD) o[0] = v;
+      else o[0] = clip(scale * (o[0] - v), e50);
+    }
+  };
+  // ---- phase 2: first derivative ----
+  if (lok) {
+    if (!AX0) {
+      const int pb = dl + CK * p0;
+      if (pb >= 3 && pb + CK <= min(dh, n - 3)) {
+        const double* q = phi_l + pb * LS;
+        double v[CK + 6];
+#pragma unroll
+        for (int m = 0; m < CK + 6; ++m) v[m] = q[(m - 3) * LS];
+#pragma unroll
+        for (int k = 0; k < CK; ++k)
+          d1_l[(pb + k) * LS] = central6(v[k], v[k + 1], v[k + 2], v[k + 4], v[k + 5], v[k + 6]);
+      } else {
+        for (int p = pb; p < min(pb + CK, dh); ++p) d1_at(p);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < IT_D; ++k) {
+        const int p = dl + p0 + PS * k;
+        if (p >= dh) break;
+        d1_at(p);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: second derivative and half-jump ----
+  if (lok) {
+    if (!AX0) {
+      const int pb = hl + CK * p0;
+      if (pb >= 3 && pb + CK <= min(hh, n - 3)) {
+        const double *q = phi_l + pb * LS, *d = d1_l + pb * LS;
+        double f[CK + 2], g[CK + 2];
+#pragma unroll
+        for (int m = 0; m < CK + 2; ++m) {
+          f[m] = q[(m - 1) * LS];
+          g[m] = d[(m - 1) * LS];
+        }
+#pragma unroll
+        for (int k = 0; k < CK; ++k) {
+          const double dd = -tol_diff(g[k + 2], g[k]) / 2;
+          const double r = kahan3(2 * (f[k + 2] + f[k]), -4 * f[k + 1], dd);
+          h_l[(pb + k) * LS] = (1.0 / 2.0) * g[k + 1] + (1.0 / 12.0) * r;
+        }
+      } else {
+        for (int p = pb; p < min(pb + CK, hh); ++p) h_at(p);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < IT_H; ++k) {
+        const int p = hl + p0 + PS * k;
+        if (p >= hh) break;
+        h_at(p);
+      }
+    }
+  }
+  __syncthreads();
+  if (!lok) return;
+  // ---- phase 4: MEG cell-centre derivative (k_legacy_meg) or edge interpolation (k_legacy_interp) ----
+  if (!AX0) {
+    const int pb = t0 + CK * p0;
+    if (pb >= t1) return;
+    const bool fast = OP == OP_INTERP ? (pb >= first + 1 && pb + CK <= min(t1, last)) : (pb >= 1 && pb + CK <= min(t1, n - 1));
+    if (fast) {
+      const double *q = phi_l + pb * LS, *h = h_l + pb * LS;
+      double* o = J.out + base + (long long)pb * s;
+      double Lm[CK + 2], Rm[CK + 2];  // states of the positions pb-1 .. pb+CK
+#pragma unroll
+      for (int m = OP == OP_INTERP ? 1 : 0; m < CK + 2; ++m) {  // (interp has no use for the state below the chunk)
+        const double f = q[(m - 1) * LS], hh_ = h[(m - 1) * LS];
+        Lm[m] = f + hh_;
+        Rm[m] = f - hh_;
+      }
+#pragma unroll
+      for (int k = 0; k < CK; ++k, o += s) {
+        const double hi = (Lm[k + 1] + Rm[k + 2]) / 2;
+        if (OP == OP_INTERP) {
+          o[0] = hi;
+        } else {
+          const double lw = (Lm[k] + Rm[k + 1]) / 2;
+          const double v = clip(hi - lw, e50);
+          if (OP == OP_CCD) o[0] = v;
+          else o[0] = clip(scale * (o[0] - v), e50);
+        }
+      }
+    } else {
+      for (int p = pb; p < min(pb + CK, t1); ++p) out_at(p);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < IT_O; ++k) {
+      const int p = t0 + p0 + PS * k;
+      if (p >= t1) break;
+      out_at(p);
+    }
+  }
+}
+
+// zero every cell of the arrays arr + blockIdx.z * nc that lies outside `keep` (the outputs are defined as zero outside
+// the metric domain; the fused path overwrites everything inside, so only the shell has to be cleared).  One warp per
+// (j, k) row: rows outside keep are cleared whole, the others only left and right of keep.
+__global__ void k_legacy_zero_outside(LShape S, LBox keep, double* arr, long long nc) {
+  double* a = arr + (long long)blockIdx.z * nc;
+  const int lane = threadIdx.x & 31;
+  const long long nrow = (long long)S.n[1] * S.n[2];
+  for (long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); row < nrow;
+       row += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int j = (int)(row % S.n[1]), k = (int)(row / S.n[1]);
+    double* r = a + row * S.n[0];
+    const bool in = j >= keep.lo[1] && j < keep.hi[1] && k >= keep.lo[2] && k < keep.hi[2];
+    const int e0 = in ? keep.lo[0] : S.n[0];  // [0, e0) and [b1, n0) are cleared
+    const int b1 = in ? keep.hi[0] : S.n[0];
+    for (int i = lane; i < e0; i += 32) r[i] = 0.0;
+    for (int i = b1 + lane; i < S.n[0]; i += 32) r[i] = 0.0;
+  }
+}
+
+template <int SRC, int OP>
+void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs, int njobs, double scale,
+                  cudaStream_t st) {
+  const int n = md.hi[axis] - md.lo[axis];
+  const dim3 blk = axis == 0 ? dim3(32, 8) : dim3(32, 8);
+  if (axis == 0) {
+    const long long nt = (n + 117) / 118, ng = (md.hi[1] - md.lo[1] + 7) / 8, no = md.hi[2] - md.lo[2];
+    k_legacy_fused<true, SRC, OP><<<dim3((unsigned)(nt * ng * no), njobs), blk, 0, st>>>(S, md, axis, whole, jobs, scale);
+  } else {
+    const int oa = axis == 1 ? 2 : 1;
+    const long long nt = (n + 55) / 56, ng = (md.hi[0] - md.lo[0] + 31) / 32, no = md.hi[oa] - md.lo[oa];
+    k_legacy_fused<false, SRC, OP><<<dim3((unsigned)(nt * ng * no), njobs), blk, 0, st>>>(S, md, axis, whole, jobs, scale);
+  }
+}
+bool legacy_fused() {
+  const char* e = getenv("CG_LEGACY_FUSED");  // debug switch (listed in include/curvigrid_cuda.h)
+  return !(e && atoi(e) == 0);
+}
+bool box_equal(const LBox& a, const LBox& b) {
+  for (int d = 0; d < 3; ++d)
+    if (a.lo[d] != b.lo[d] || a.hi[d] != b.hi[d]) return false;
+  return true;
+}
+// clear the shell outside `keep` of narr consecutive arrays (nothing to do when keep is the whole array)
+void zero_outside(const LShape& S, const LBox& full, const LBox& keep, double* arr, int narr, long long nc, cudaStream_t st,
+                  uint64_t& nl) {
+  if (box_equal(full, keep) || narr == 0) return;
+  long long b = ((long long)S.n[1] * S.n[2] + 7) / 8;
+  if (b > 148LL * 8) b = 148LL * 8;
+  k_legacy_zero_outside<<<dim3((unsigned)b, 1, narr), 256, 0, st>>>(S, keep, arr, nc);
+  ++nl;
+}
+// the 19 (3-D) / 9 (2-D) / 3 (1-D) edge interpolations of one axis in one launch
+void interp_axis_fused(const LShape& S, const LBox& full, const LBox& md, int axis, int whole, const double* const* phi,
+                       int nphi, double* E, long long nc, cudaStream_t st, uint64_t& nl) {
+  // written: md along the other axes; along `axis` positions [first-1, last] of md
+  LBox keep = md;
+  if (whole) keep.hi[axis] = md.hi[axis] - 1;
+  else keep.lo[axis] = md.lo[axis] - 1;
+  zero_outside(S, full, keep, E, nphi, nc, st, nl);
+  LJobs jobs{};
+  for (int m = 0; m < nphi; ++m) jobs.j[m] = {phi[m], nullptr, nullptr, nullptr, E + (long long)m * nc};
+  launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st);
+  ++nl;
+}
+
 int blocks_for(long long n) {
   long long b = (n + 255) / 256;
   const long long cap = 148LL * 32;
@@ -363,19 +692,64 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
   uint64_t nl = 0;
   double *cx = scratch, *cy = scratch + nc, *cz = scratch + 2 * nc;
   double *d1 = scratch + 3 * nc, *d2 = scratch + 4 * nc, *src = scratch + 5 * nc, *tmp = scratch + 6 * nc;
-  cudaMemsetAsync(cell, 0, (size_t)28 * nc * sizeof(double), st);
-  cudaMemsetAsync(edge, 0, (size_t)57 * nc * sizeof(double), st);
-  cudaMemsetAsync(scratch, 0, (size_t)7 * nc * sizeof(double), st);
-  const int bl = blocks_for(box_count(md)), bw = blocks_for(nc);
-  k_legacy_centroid<<<bl, 256, 0, st>>>(S, md, x, y, z, halo_coords_included ? 0 : nhalo, (int)nnode[0], (int)nnode[1],
-                                         cx, cy, cz);
-  ++nl;
-  if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)3 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
   double* C[3] = {cx, cy, cz};
   double* J = cell;
   double* fwd = cell + nc;       // [q*3+axis]
   double* inv = cell + 10 * nc;  // [row*3+col]
   double* hat = cell + 19 * nc;
+  const int bl = blocks_for(box_count(md)), bw = blocks_for(nc);
+  if (legacy_fused()) {
+    // 15 launches: every derivative is one fused launch (first + second derivative + MEG reconstruction through shared
+    // memory), the fields that share an axis share the launch; only the shell outside the metric domain is cleared
+    zero_outside(S, full, md, cell, 28, nc, st, nl);
+    zero_outside(S, full, md, scratch, 3, nc, st, nl);
+    k_legacy_centroid<<<bl, 256, 0, st>>>(S, md, x, y, z, halo_coords_included ? 0 : nhalo, (int)nnode[0], (int)nnode[1],
+                                           cx, cy, cz);
+    ++nl;
+    if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)3 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    for (int ax = 0; ax < 3; ++ax) {  // forward metrics: d x_q / d xi_ax, q = 0..2
+      LJobs jobs{};
+      for (int q = 0; q < 3; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 3 + ax) * nc};
+      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st);
+      ++nl;
+    }
+    k_legacy_det<<<bl, 256, 0, st>>>(S, md, fwd, nc, J);
+    ++nl;
+    for (int r = 0; r < 3; ++r) {  // conservative metrics, row r: the three columns share both launches
+      const int s = (r + 1) % 3, u = (r + 2) % 3;
+      LJobs j1{}, j2{};
+      for (int c = 0; c < 3; ++c) {
+        const int q1 = (c + 1) % 3, q2 = (c + 2) % 3;
+        double* h = hat + (long long)(r * 3 + c) * nc;
+        const double *a_s = fwd + (long long)(q1 * 3 + s) * nc, *a_u = fwd + (long long)(q1 * 3 + u) * nc;
+        const double *b_s = fwd + (long long)(q2 * 3 + s) * nc, *b_u = fwd + (long long)(q2 * 3 + u) * nc;
+        j1.j[c] = {a_s, C[q2], symmetric ? b_s : nullptr, symmetric ? C[q1] : nullptr, h};
+        j2.j[c] = {a_u, C[q2], symmetric ? b_u : nullptr, symmetric ? C[q1] : nullptr, h};
+      }
+      if (symmetric) {
+        launch_fused<2, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
+        launch_fused<2, OP_CCD_POST>(S, md, s, whole, j2, 3, 1.0 / 2.0, st);
+      } else {
+        launch_fused<1, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
+        launch_fused<1, OP_CCD_POST>(S, md, s, whole, j2, 3, 1.0, st);
+      }
+      nl += 2;
+    }
+    k_legacy_div9<<<bl, 256, 0, st>>>(S, md, hat, J, nc, inv);
+    ++nl;
+    for (int ax = 0; ax < 3; ++ax) {
+      const double* phi[19];
+      for (int m = 0; m < 19; ++m) phi[m] = m == 0 ? J : cell + (long long)(9 + m) * nc;  // J, inv 0..8, hat 0..8
+      interp_axis_fused(S, full, md, ax, whole, phi, 19, edge + (long long)ax * 19 * nc, nc, st, nl);
+    }
+  } else {
+  cudaMemsetAsync(cell, 0, (size_t)28 * nc * sizeof(double), st);
+  cudaMemsetAsync(edge, 0, (size_t)57 * nc * sizeof(double), st);
+  cudaMemsetAsync(scratch, 0, (size_t)7 * nc * sizeof(double), st);
+  k_legacy_centroid<<<bl, 256, 0, st>>>(S, md, x, y, z, halo_coords_included ? 0 : nhalo, (int)nnode[0], (int)nnode[1],
+                                         cx, cy, cz);
+  ++nl;
+  if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)3 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
   auto ccd = [&](const double* phi, int axis, double* out, int post, double scale) {
     k_legacy_first<<<bl, 256, 0, st>>>(S, md, axis, phi, d1);
     k_legacy_second<<<bl, 256, 0, st>>>(S, md, axis, phi, d1, d2);
@@ -413,6 +787,7 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
       k_legacy_interp<<<bl, 256, 0, st>>>(S, md, ax, whole, phi, d1, d2, E + (long long)m * nc);
       nl += 3;
     }
+  }
   }
   (void)tmp;
   ce = cudaGetLastError();
@@ -472,18 +847,38 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
   const int whole = halo_coords_included ? 1 : 0;
   uint64_t nl = 0;
   double *cx = scratch, *cy = scratch + nc, *d1 = scratch + 2 * nc, *d2 = scratch + 3 * nc;
-  cudaMemsetAsync(cell, 0, (size_t)13 * nc * sizeof(double), st);
-  cudaMemsetAsync(edge, 0, (size_t)18 * nc * sizeof(double), st);
-  cudaMemsetAsync(scratch, 0, (size_t)4 * nc * sizeof(double), st);
-  const int bl = blocks_for(box_count(md));
-  k_legacy_centroid2d<<<bl, 256, 0, st>>>(S, md, x, y, halo_coords_included ? 0 : nhalo, (int)nnode[0], cx, cy);
-  ++nl;
-  if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)2 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
   double* C[2] = {cx, cy};
   double* J = cell;
   double* fwd = cell + nc;      // [q*2+axis]
   double* inv = cell + 5 * nc;  // xi_x, xi_y, eta_x, eta_y
   double* hat = cell + 9 * nc;
+  const int bl = blocks_for(box_count(md));
+  if (legacy_fused()) {
+    zero_outside(S, full, md, cell, 13, nc, st, nl);
+    zero_outside(S, full, md, scratch, 2, nc, st, nl);
+    k_legacy_centroid2d<<<bl, 256, 0, st>>>(S, md, x, y, halo_coords_included ? 0 : nhalo, (int)nnode[0], cx, cy);
+    ++nl;
+    if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)2 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    for (int ax = 0; ax < 2; ++ax) {  // forward_metrics.jl:36-60
+      LJobs jobs{};
+      for (int q = 0; q < 2; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 2 + ax) * nc};
+      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 2, 1.0, st);
+      ++nl;
+    }
+    k_legacy_inv2d<<<bl, 256, 0, st>>>(S, md, fwd, nc, J, inv, hat);
+    ++nl;
+    for (int ax = 0; ax < 2; ++ax) {  // MetricDiscretizationSchemes.jl:58-89
+      const double* phi[9];
+      for (int m = 0; m < 9; ++m) phi[m] = m == 0 ? J : cell + (long long)(4 + m) * nc;  // J, inv 0..3, hat 0..3
+      interp_axis_fused(S, full, md, ax, whole, phi, 9, edge + (long long)ax * 9 * nc, nc, st, nl);
+    }
+  } else {
+  cudaMemsetAsync(cell, 0, (size_t)13 * nc * sizeof(double), st);
+  cudaMemsetAsync(edge, 0, (size_t)18 * nc * sizeof(double), st);
+  cudaMemsetAsync(scratch, 0, (size_t)4 * nc * sizeof(double), st);
+  k_legacy_centroid2d<<<bl, 256, 0, st>>>(S, md, x, y, halo_coords_included ? 0 : nhalo, (int)nnode[0], cx, cy);
+  ++nl;
+  if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)2 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
   for (int q = 0; q < 2; ++q)
     for (int ax = 0; ax < 2; ++ax) {  // forward_metrics.jl:36-60
       k_legacy_first<<<bl, 256, 0, st>>>(S, md, ax, C[q], d1);
@@ -502,6 +897,7 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
       k_legacy_interp<<<bl, 256, 0, st>>>(S, md, ax, whole, phi, d1, d2, E + (long long)m * nc);
       nl += 3;
     }
+  }
   }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) {
@@ -600,16 +996,30 @@ extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64
   const int whole = halo_coords_included ? 1 : 0;
   uint64_t nl = 0;
   double *cx = scratch, *d1 = scratch + nc, *d2 = scratch + 2 * nc;
+  double *J = cell, *xxi = cell + nc, *inv = cell + 2 * nc, *hat = cell + 3 * nc;
+  const int bl = blocks_for(box_count(md));
+  if (legacy_fused()) {
+    zero_outside(S, full, md, cell, 4, nc, st, nl);
+    zero_outside(S, full, md, scratch, 1, nc, st, nl);
+    k_legacy_centroid1d<<<bl, 256, 0, st>>>(S, md, x, halo_coords_included ? 0 : nhalo, cx);
+    ++nl;
+    if (centroid) cudaMemcpyAsync(centroid, cx, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    LJobs jobs{};
+    jobs.j[0] = {cx, nullptr, nullptr, nullptr, xxi};  // forward_metrics.jl:11-27
+    launch_fused<0, OP_CCD>(S, md, 0, whole, jobs, 1, 1.0, st);
+    k_legacy_inv1d<<<bl, 256, 0, st>>>(S, md, xxi, J, inv, hat);
+    nl += 2;
+    const double* phi[3] = {J, inv, hat};  // MetricDiscretizationSchemes.jl:58-89
+    interp_axis_fused(S, full, md, 0, whole, phi, 3, edge, nc, st, nl);
+  } else {
   cudaMemsetAsync(cell, 0, (size_t)4 * nc * sizeof(double), st);
   cudaMemsetAsync(edge, 0, (size_t)3 * nc * sizeof(double), st);
   cudaMemsetAsync(scratch, 0, (size_t)3 * nc * sizeof(double), st);
-  const int bl = blocks_for(box_count(md));
   // 1d.jl:388-408: the centroids are refreshed on cell.domain only (unlike 2-D / 3-D); with halo_coords_included the
   // node array covers the halo and the metric domain is cell.full
   k_legacy_centroid1d<<<bl, 256, 0, st>>>(S, md, x, halo_coords_included ? 0 : nhalo, cx);
   ++nl;
   if (centroid) cudaMemcpyAsync(centroid, cx, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
-  double *J = cell, *xxi = cell + nc, *inv = cell + 2 * nc, *hat = cell + 3 * nc;
   k_legacy_first<<<bl, 256, 0, st>>>(S, md, 0, cx, d1);      // forward_metrics.jl:11-27
   k_legacy_second<<<bl, 256, 0, st>>>(S, md, 0, cx, d1, d2);
   k_legacy_meg<0><<<bl, 256, 0, st>>>(S, md, 0, cx, d1, d2, xxi, 1.0);
@@ -621,6 +1031,7 @@ extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64
     k_legacy_second<<<bl, 256, 0, st>>>(S, md, 0, phi, d1, d2);
     k_legacy_interp<<<bl, 256, 0, st>>>(S, md, 0, whole, phi, d1, d2, edge + (long long)m * nc);
     nl += 3;
+  }
   }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) {
@@ -662,13 +1073,16 @@ extern "C" int cg_legacy_check_valid(int device, int dim, const int64_t* nfull, 
   for (int r = 0; r < n_cell_rows; ++r) R.cell[r] = cell_rows[r];
   for (int r = 0; r < n_edge_rows; ++r) R.edge[r] = edge_rows[r];
   cudaStream_t st = (cudaStream_t)stream;
-  int* flags = nullptr;
-  if (cudaMallocAsync((void**)&flags, 2 * sizeof(int), st) != cudaSuccess) return CG_ERR_OOM;
+  // one persistent 8-byte flag word pair per device and host thread (a stream-ordered allocation per call made the
+  // memory pool trim and re-grow at every synchronisation: sporadic stalls of hundreds of ms)
+  thread_local int* flag_cache[64] = {};
+  if (device < 0 || device >= 64) return CG_ERR_ARG;
+  if (!flag_cache[device] && cudaMalloc((void**)&flag_cache[device], 2 * sizeof(int)) != cudaSuccess) return CG_ERR_OOM;
+  int* flags = flag_cache[device];
   cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
   k_legacy_check_valid<<<blocks_for(box_count(dom)), 256, 0, st>>>(S, dom, R, cell, edge, nc, flags);
   int h[2] = {0, 0};
   cudaMemcpyAsync(h, flags, sizeof h, cudaMemcpyDeviceToHost, st);
-  cudaFreeAsync(flags, st);
   ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) {
     snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_check_valid: %s", cudaGetErrorString(ce));

@@ -30,6 +30,8 @@
  *                        (k_mapped_cons_uni + k_mapped_face_uni<0,1,2>)
  *   CG_FUSE_XZ=1         3-D FULL cell+face: the fused xi+zeta kernel (k_face_xz, an experiment: slower than the
  *                        two kernels it replaces) instead of k_face_xi + k_face_zeta
+ *   CG_LEGACY_FUSED=0    legacy MEG6 pipeline: the pass-by-pass launches (273 per 3-D update) instead of the fused
+ *                        ones (20); both produce the same bits (tests/test_gpu_legacy.py)
  *   CG_NCCL_LIB=path     libnccl to dlopen when the process has not loaded one (default libnccl.so.2)
  */
 #ifndef CURVIGRID_CUDA_H

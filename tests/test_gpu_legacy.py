@@ -227,3 +227,56 @@ def test_legacy_check_valid_metrics(cg):
 def test_legacy_1d_decreasing_mesh_is_accepted(cg):
     m = cg.legacy.CurvilinearGrid1D(np.linspace(1.0, 0.0, 30), "meg6")
     assert float(m.cell_center_metrics["J"][5:-5].min()) > 0 and float(m.cell_center_metrics["x₁"]["ξ"][5:-5].max()) < 0
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+@pytest.mark.parametrize("halo_included", [False, True])
+@pytest.mark.parametrize("shape", [(131, 58, 63), (120, 62, 115)])
+def test_legacy_fused_equals_pass_by_pass_bitwise(cg, monkeypatch, shape, symmetric, halo_included):
+    """The fused launches (first + second derivative + MEG reconstruction / edge interpolation through shared memory,
+    shell-only clearing) reproduce the pass-by-pass pipeline (CG_LEGACY_FUSED=0) bit for bit, on grids that need
+    several tiles per axis and end in short tiles (57 = 56 + 1, 119 = 118 + 1 cells), from poisoned output buffers."""
+    import torch
+    nodes = mild_nodes(shape, seed=7)
+    scheme = "meg6_symmetric" if symmetric else "meg6"
+    mesh = cg.legacy.CurvilinearGrid3D(*nodes, scheme, halo_coords_included=halo_included)
+    assert mesh.launches <= 20
+    fused = [t.clone() for t in (mesh._cell, mesh._edge, mesh._cent)]
+    for t in (mesh._cell, mesh._edge, mesh._cent, mesh._scratch):
+        t.fill_(float("nan"))   # nothing may survive from the caller's buffers
+    cg.legacy.update(mesh, True, halo_included)
+    for a, b in zip(fused, (mesh._cell, mesh._edge, mesh._cent)):
+        assert torch.equal(a, b)
+    monkeypatch.setenv("CG_LEGACY_FUSED", "0")
+    cg.legacy.update(mesh, True, halo_included)
+    assert mesh.launches > 200
+    for name, a, b in zip(("cell", "edge", "centroid"), fused, (mesh._cell, mesh._edge, mesh._cent)):
+        assert torch.equal(a, b), name
+
+
+@pytest.mark.parametrize("halo_included", [False, True])
+def test_legacy_fused_2d_1d_equal_pass_by_pass_bitwise(cg, monkeypatch, halo_included):
+    import torch
+    x, y = cg.workloads.wavy_nodes_2d(150, 131)
+    m2 = cg.legacy.CurvilinearGrid2D(x, y, "meg6", halo_coords_included=halo_included)
+    s = np.linspace(0.0, 1.0, 400)
+    m1 = cg.legacy.CurvilinearGrid1D(s + 0.04 * np.sin(2 * np.pi * s) + 0.3, "meg6", halo_coords_included=halo_included)
+    fused = [t.clone() for m in (m2, m1) for t in (m._cell, m._edge, m._cent)]
+    monkeypatch.setenv("CG_LEGACY_FUSED", "0")
+    cg.legacy.update2d(m2, True, halo_included)
+    cg.legacy.update1d(m1, True, halo_included)
+    for a, b in zip(fused, [t for m in (m2, m1) for t in (m._cell, m._edge, m._cent)]):
+        assert torch.equal(a, b)
+
+
+def test_legacy_fused_matches_oracle_multi_tile(cg, oracle):
+    """Oracle parity of the fused path on a grid with several tiles per axis (the small cases above fit one tile)."""
+    nodes = mild_nodes((125, 64, 70), seed=5)
+    ref = oracle.legacy_meg6_3d(nodes, 5, halo_coords_included=False, symmetric=False)
+    mesh = cg.legacy.CurvilinearGrid3D(*nodes, "meg6")
+    sel = _dom(ref["nfull"])
+    for name, got, want in (("cell", mesh._cell.cpu().numpy(), ref["cell"]), ("edge", mesh._edge.cpu().numpy(), ref["edge"])):
+        scale = np.abs(want).max(axis=-1, keepdims=True)
+        scale[scale == 0] = 1.0
+        assert (np.abs(got - want) / scale).max() <= 1e-13, name
+        assert (got[..., sel] == want[..., sel]).mean() > 0.99, name
