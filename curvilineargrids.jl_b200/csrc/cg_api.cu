@@ -17,6 +17,7 @@
 #include "cg_kernels_tiled.cuh"
 #include "cg_mapped.cuh"
 #include "cg_mapped_split.cuh"
+#include "cg_generic.cuh"
 
 namespace {
 
@@ -24,7 +25,7 @@ thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
-  char buf[512];
+  char buf[4096];  // room for an NVRTC log
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
@@ -74,6 +75,7 @@ struct cg_grid {
   Buf seam;                            // cg_grid_gcl_max_dist: the neighbour's last conserved plane
   std::vector<double> terms;
   cg::MappedTables mtab;
+  cg::GenericMap gmap;  // generic (NVRTC-compiled) mapping: cg_grid_set_mapping_source
   double t = 0.0;
 
   size_t esize() const { return dtype == CG_F64 ? 8 : 4; }
@@ -270,10 +272,77 @@ int start_timer(cg_grid* g, cudaStream_t st) {
   return CG_OK;
 }
 
+// MappedGrid with a generic (non-separable) mapping: the NVRTC-compiled kernels of cg_generic_prelude.h
+template <class T>
+int eval_generic(cg_grid* g, int what, cudaStream_t st) {
+  const int fi = sizeof(T) == 8 ? 0 : 1;
+  cg::GD D;
+  D.dim = g->dim;
+  D.nhalo = g->nhalo;
+  D.scheme = g->scheme;
+  D.what = what;
+  for (int d = 0; d < 3; ++d) {
+    D.nw[d] = g->nw[d];
+    D.w0[d] = g->w0[d] + g->goff[d];
+  }
+  double t = g->t;
+  const double* prm = g->gmap.d_params;
+  int rc;
+  if (what & CG_WHAT_COORDS) {
+    cg::CoordOut<T> C;
+    if ((rc = bind_coord_outputs<T>(g, C))) return rc;
+    cg::GCoord GC;
+    for (int a = 0; a < 3; ++a) {
+      GC.node[a] = C.node[a];
+      GC.centroid[a] = C.centroid[a];
+      for (int q = 0; q < 3; ++q) GC.face[a][q] = C.face[a][q];
+    }
+    void* args[] = {&D, &t, &prm, &GC};
+    const std::string e = cg::generic_launch(g->gmap.coords[fi], g->nnodes(), 128, args, st);
+    if (!e.empty()) return fail(CG_ERR_CUDA, "generic mapping, coordinates: %s", e.c_str());
+    g_launches++;
+    g->valid_coords = true;
+  }
+  if (!(what & (CG_WHAT_CELL | CG_WHAT_FACE))) return CG_OK;
+  cg::MetricOut<T> O;
+  if ((rc = bind_metric_outputs<T>(g, what, O))) return rc;
+  if ((rc = start_timer(g, st))) return rc;
+  cg::GOut GO;
+  GO.cell_fwd = O.cell_fwd;
+  GO.cell_inv = O.cell_inv;
+  GO.cjac = O.cjac;
+  for (int a = 0; a < 3; ++a) {
+    GO.face_fwd[a] = O.face_fwd[a];
+    GO.face_inv[a] = O.face_inv[a];
+    GO.face_cons[a] = O.face_cons[a];
+    GO.cactive[a] = O.cactive[a];
+  }
+  void* args[] = {&D, &t, &prm, &GO};
+  if (what & CG_WHAT_CELL) {
+    const std::string e = cg::generic_launch(g->gmap.cell[fi], g->ncells(), 128, args, st);
+    if (!e.empty()) return fail(CG_ERR_CUDA, "generic mapping, cell metrics: %s", e.c_str());
+    g_launches++;
+  }
+  if (what & CG_WHAT_FACE) {
+    const std::string e = cg::generic_launch(g->gmap.face[fi], g->ncells() * g->dim, 128, args, st);
+    if (!e.empty()) return fail(CG_ERR_CUDA, "generic mapping, face metrics: %s", e.c_str());
+    g_launches++;
+  }
+  CG_CUDA(cudaEventRecord(g->ev1, st));
+  g->timed = true;
+  if (what & CG_WHAT_CELL) g->valid_cell = true;
+  if (what & CG_WHAT_FACE) g->valid_face = true;
+  return CG_OK;
+}
+
 // MappedGrid: 1-D operator tables (once per update) + the table-driven metric kernel
 template <class T>
 int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
   const int N = g->dim;
+  if (g->gmap.active) {
+    if (g->adtl) return fail(CG_ERR_ARG, "ADThomasLombardMetric needs a term-list mapping (cg_grid_set_mapping_terms)");
+    return eval_generic<T>(g, what, st);
+  }
   cg::Dims D = g->dims();
   int rc = cg::mapped_prepare<T>(g->mtab, g->terms, g->t, D, g->scheme, st, g->adtl);
   if (rc == 1) return fail(CG_ERR_ARG, "mapping has too many terms (max %d)", cg::M_MAXT - 1);
@@ -517,6 +586,7 @@ int cg_grid_destroy(cg_grid* g) {
   release(g->cell_inv);
   release(g->cjac);
   g->mtab.free_all();
+  g->gmap.destroy();
   if (g->gcl_bits) cudaFree(g->gcl_bits);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
@@ -638,9 +708,47 @@ int cg_grid_set_mapping_terms(cg_grid* g, int nterms, const double* table) {
       if (r[6 + 3 * d] < 0 || r[6 + 3 * d] > 3) return fail(CG_ERR_ARG, "term %d: bad factor kind", m);
   }
   g->terms.assign(table, table + 15 * (size_t)nterms);
+  g->gmap.active = false;
   g->kind = 2;
   g->mtab.dirty = true;
   g->valid_cell = g->valid_face = g->valid_coords = false;
+  return CG_OK;
+}
+
+int cg_grid_set_mapping_source(cg_grid* g, const char* cuda_source) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (!cuda_source || !*cuda_source) return fail(CG_ERR_ARG, "empty mapping source");
+  CG_CUDA(cudaSetDevice(g->device));
+  const std::string err = cg::generic_load(g->gmap, cuda_source);
+  if (!err.empty()) return fail(err.rfind("NVRTC:", 0) == 0 ? CG_ERR_ARG : CG_ERR_CUDA, "cg_grid_set_mapping_source: %s", err.c_str());
+  g->kind = 2;
+  g->terms.clear();
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return CG_OK;
+}
+
+int cg_grid_set_mapping_params(cg_grid* g, const double* params, int nparams) {
+  if (!g) return fail(CG_ERR_ARG, "NULL grid");
+  if (nparams < 0 || (nparams > 0 && !params)) return fail(CG_ERR_ARG, "bad mapping parameters");
+  CG_CUDA(cudaSetDevice(g->device));
+  if (nparams > g->gmap.nparams || !g->gmap.d_params) {
+    if (g->gmap.d_params) cudaFree(g->gmap.d_params);
+    g->gmap.d_params = nullptr;
+    CG_CUDA(cudaMalloc((void**)&g->gmap.d_params, sizeof(double) * (size_t)(nparams > 0 ? nparams : 1)));
+  }
+  g->gmap.nparams = nparams;
+  // pageable source: the copy is synchronous with respect to the host buffer, ordered on the legacy default stream
+  if (nparams > 0) CG_CUDA(cudaMemcpy(g->gmap.d_params, params, sizeof(double) * (size_t)nparams, cudaMemcpyHostToDevice));
+  g->valid_cell = g->valid_face = g->valid_coords = false;
+  return CG_OK;
+}
+
+int cg_generic_compile_check(const char* cuda_source, char* log, size_t log_bytes) {
+  if (!cuda_source) return fail(CG_ERR_ARG, "NULL source");
+  std::vector<char> cubin;
+  const std::string err = cg::generic_compile(cuda_source, cubin);
+  if (log && log_bytes) snprintf(log, log_bytes, "%s", err.c_str());
+  if (!err.empty()) return fail(CG_ERR_ARG, "%s", err.c_str());
   return CG_OK;
 }
 

@@ -364,9 +364,13 @@ class DiscreteGrid(_UnifiedGrid):
 class MappedGrid(_UnifiedGrid):
     """MappedGrid(mapping_terms, params, celldims, nhalo; ...) — mapped_grid.jl:421-540.
 
-    The mapping is a separable term list (workloads.py) or a callable
-    `params, t -> term list`; arbitrary Julia closures cannot cross a C ABI
-    (DESIGN.md §2).
+    The mapping is a separable term list (workloads.py), a callable `params -> term list`, or — for mappings that
+    are not separable — a `str` holding the CUDA C++ source of
+
+        template <class S> __device__ void cg_map(S xi, S eta, S zeta, double t, const double* p, S& x, S& y, S& z);
+
+    which the library compiles with NVRTC (cg_grid_set_mapping_source; `params` is then a sequence of floats, the `p`
+    array).  Arbitrary Julia closures cannot cross a C ABI.
     """
 
     def __init__(self, mapping, params, celldims, nhalo, *, device=None, T=np.float64, compute_metrics=True,
@@ -396,6 +400,15 @@ class MappedGrid(_UnifiedGrid):
             self._eval(L.CG_WHAT_CELL | L.CG_WHAT_FACE)
 
     def _push_mapping(self):
+        if isinstance(self.mapping, str):  # generic mapping: compiled once, parameters on every update!
+            if not getattr(self, "_source_loaded", False):
+                L.check(L.lib().cg_grid_set_mapping_source(self._h, self.mapping.encode()))
+                self._source_loaded = True
+            prm = self.state["params"]
+            arr = np.ascontiguousarray(np.asarray([] if prm is None else prm, dtype=np.float64).ravel())
+            L.check(L.lib().cg_grid_set_mapping_params(self._h, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                       int(arr.size)))
+            return
         terms = self.mapping(self.state["params"]) if callable(self.mapping) else self.mapping
         tab = np.ascontiguousarray(np.asarray(terms, dtype=np.float64).reshape(-1, 15))
         L.check(L.lib().cg_grid_set_mapping_terms(self._h, tab.shape[0],

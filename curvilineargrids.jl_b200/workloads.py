@@ -235,3 +235,27 @@ def generic_3d_terms(celldims):
 def affine_terms(dim, origin, spacing):
     """Rectilinear MappedGrid: q_c = origin_c + (xi_c - 1) * spacing_c."""
     return [term(c, 1.0, {c: (AFFINE, origin[c] - spacing[c], spacing[c])}) for c in range(dim)]
+
+
+def terms_to_cuda_source(terms):
+    """CUDA C++ source of `cg_map` (MappedGrid generic path, cg_grid_set_mapping_source) for a term list: lets any
+    separable mapping run through the NVRTC-compiled kernels as well (cross-checks of the two MappedGrid paths)."""
+    rows = np.asarray(terms, dtype=np.float64).reshape(-1, 15)
+    names = ("xi", "eta", "zeta")
+    expr = {0: ["0.0 * xi"], 1: ["0.0 * eta"], 2: ["0.0 * zeta"]}
+    for r in rows:
+        coef = f"({float(r[1])!r} + {float(r[2])!r} * t + {float(r[3])!r} * sin({float(r[4])!r} * t + {float(r[5])!r}))"
+        fac = []
+        for d in range(3):
+            kind, a, b = int(r[6 + 3 * d]), float(r[7 + 3 * d]), float(r[8 + 3 * d])
+            arg = f"({a!r} + {b!r} * {names[d]})"
+            if kind == AFFINE:
+                fac.append(arg)
+            elif kind == SIN:
+                fac.append(f"sin{arg}")
+            elif kind == COS:
+                fac.append(f"cos{arg}")
+        expr[int(r[0])].append(" * ".join([coef] + fac))
+    body = "\n".join(f"  {q} = {' + '.join(expr[c])};" for c, q in enumerate("xyz"))
+    return ("template <class S> __device__ void cg_map(S xi, S eta, S zeta, double t, const double* p, S& x, S& y, S& z) {\n"
+            + body + "\n}\n")

@@ -33,6 +33,7 @@
  *   CG_LEGACY_FUSED=0    legacy MEG6 pipeline: the pass-by-pass launches (273 per 3-D update) instead of the fused
  *                        ones (20); both produce the same bits (tests/test_gpu_legacy.py)
  *   CG_NCCL_LIB=path     libnccl to dlopen when the process has not loaded one (default libnccl.so.2)
+ *   CG_NVRTC_LIB=path    libnvrtc to dlopen for cg_grid_set_mapping_source (default libnvrtc.so.12, then the CUDA toolkit's)
  */
 #ifndef CURVIGRID_CUDA_H
 #define CURVIGRID_CUDA_H
@@ -139,6 +140,26 @@ int cg_grid_required_node_range(const cg_grid* g, int axis, int64_t* lo, int64_t
  *   kind: 0 = 1, 1 = a+b*s, 2 = sin(a+b*s), 3 = cos(a+b*s)
  */
 int cg_grid_set_mapping_terms(cg_grid* g, int nterms, const double* table);
+/*
+ * MappedGrid with an ARBITRARY analytic mapping (the reference's MappedGrid takes any Julia closures,
+ * src/grids/unified_grids/mapped_grid.jl:421-540, and differentiates them with ForwardDiff; a closure cannot cross a C
+ * ABI, CUDA C++ source can).  `cuda_source` defines
+ *
+ *     template <class S> __device__ void cg_map(S xi, S eta, S zeta, double t, const double* p, S& x, S& y, S& z);
+ *
+ * (2-D / 1-D mappings ignore the unused arguments and outputs; + - * / sin cos exp log sqrt tanh and mixed arithmetic with
+ * double are available on S).  The library compiles it with NVRTC for sm_100a together with truncated-Taylor number types
+ * and generic coordinate / cell / face kernels (csrc/cg_generic_prelude.h) and evaluates the same closure graph as for a
+ * term-list mapping: all three schemes, FULL and COMPACT profiles, FP64 / FP32 storage (the arithmetic is FP64),
+ * windows (local_grid).  A fallback for mappings that are not separable, about two orders of magnitude slower than the
+ * table-driven kernels.  A compile error returns CG_ERR_ARG with the NVRTC log in cg_last_error(); a missing libnvrtc /
+ * libcuda returns CG_ERR_CUDA.  `params` (the reference's `params` argument of update!) are copied to the device;
+ * t comes from cg_grid_update.  ADThomasLombardMetric needs a term-list mapping.
+ */
+int cg_grid_set_mapping_source(cg_grid* g, const char* cuda_source);
+int cg_grid_set_mapping_params(cg_grid* g, const double* params, int nparams);
+/* compile only (no GPU needed): CG_OK, or CG_ERR_ARG with the NVRTC log copied to `log` (may be NULL) */
+int cg_generic_compile_check(const char* cuda_source, char* log, size_t log_bytes);
 
 /*
  * update!(grid, t, params) (mapped_grid.jl:551-593, discrete_grid.jl:605-647):

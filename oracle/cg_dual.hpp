@@ -80,6 +80,23 @@ inline long double cos_(long double x) { return cosl(x); }
 inline __float128 sin_(__float128 x) { return sinq(x); }
 inline __float128 cos_(__float128 x) { return cosq(x); }
 #endif
+inline double exp_(double x) { return std::exp(x); }
+inline double sqrt_(double x) { return std::sqrt(x); }
+#if defined(CGO_REAL_IS_LD)
+inline long double exp_(long double x) { return expl(x); }
+inline long double sqrt_(long double x) { return sqrtl(x); }
+#elif defined(CGO_REAL_IS_QUAD)
+inline __float128 exp_(__float128 x) { return expq(x); }
+inline __float128 sqrt_(__float128 x) { return sqrtq(x); }
+#endif
+template <class T> inline Dual<T> exp_(const Dual<T>& a) {
+  T e = exp_(a.v);
+  return {e, e * a.d};
+}
+template <class T> inline Dual<T> sqrt_(const Dual<T>& a) {
+  T s = sqrt_(a.v);
+  return {s, a.d / (2.0 * s)};
+}
 template <class T> inline Dual<T> sin_(const Dual<T>& a);
 template <class T> inline Dual<T> cos_(const Dual<T>& a);
 template <class T> inline Dual<T> sin_(const Dual<T>& a) { return {sin_(a.v), cos_(a.v) * a.d}; }

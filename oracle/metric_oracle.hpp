@@ -649,4 +649,39 @@ struct TermMap {
   }
 };
 
+// ---------------------------------------------------------------------------
+// Non-separable analytic test mappings (the reference's MappedGrid takes ANY closures, mapped_grid.jl:421-540): the
+// checker's side of tests/test_gpu_generic_mapping.py, where the same formulas are given to the library as CUDA source
+// (cg_grid_set_mapping_source).  Evaluated on dual numbers like every other closure here.
+//   id 1 (3-D): x = xi + p0 sin(p1 (eta + zeta / 2) + 0.3 t)
+//               y = eta (1 + p2 xi) / (1 + p3 zeta^2)
+//               z = zeta + p0 exp(-p4 (xi - eta)^2) cos(t) + sqrt(1 + 0.01 xi^2)
+//   id 2 (2-D): x = xi + p0 sin(p1 xi eta + t),  y = eta + p2 sqrt(1 + p3 xi^2 + eta^2 / 2)
+//   id 3 (1-D): x = xi + p0 sin(p1 xi) exp(-p2 xi) + p3 t
+// ---------------------------------------------------------------------------
+struct FuncMap {
+  int N, id;
+  const double* prm;
+  int dim() const { return N; }
+  template <class S>
+  S coord(int c, double t, const Pt<S>& p) const {
+    const S &xi = p[0], &eta = p[1], &zeta = p[2];
+    if (id == 1) {
+      if (c == 0) return xi + prm[0] * sin_(prm[1] * (eta + 0.5 * zeta) + 0.3 * t);
+      if (c == 1) return eta * (1.0 + prm[2] * xi) / (1.0 + prm[3] * zeta * zeta);
+      return zeta + prm[0] * exp_(-prm[4] * (xi - eta) * (xi - eta)) * std::cos(t) + sqrt_(1.0 + 0.01 * xi * xi);
+    }
+    if (id == 2) {
+      if (c == 0) return xi + prm[0] * sin_(prm[1] * xi * eta + t);
+      return eta + prm[2] * sqrt_(1.0 + prm[3] * xi * xi + 0.5 * eta * eta);
+    }
+    return xi + prm[0] * sin_(prm[1] * xi) * exp_(-prm[2] * xi) + prm[3] * t;
+  }
+  void forward_jacobian(double t, const Pt<real>& p, real* F) const {
+    if (N == 1) { auto J = ad_jacobian<1>(*this, t, p); F[0] = J.e[0]; }
+    else if (N == 2) { auto J = ad_jacobian<2>(*this, t, p); for (int k = 0; k < 4; ++k) F[k] = J.e[k]; }
+    else { auto J = ad_jacobian<3>(*this, t, p); for (int k = 0; k < 9; ++k) F[k] = J.e[k]; }
+  }
+};
+
 }  // namespace cgo

@@ -163,6 +163,41 @@ def mapped_coords(terms, t, celldims, nhalo, which, global_offset=None):
     return out
 
 
+def funcmap_eval(dim, map_id, params, t, celldims, nhalo, scheme="curvature", sample=None, what=3, global_offset=None,
+                 precision="f64"):
+    """MappedGrid with one of the NON-separable analytic test mappings of metric_oracle.hpp (FuncMap ids 1-3)."""
+    prm = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
+    nc = np.array(list(celldims) + [1] * (3 - dim), dtype=np.int64)
+    go = np.zeros(3, dtype=np.int64)
+    if global_offset is not None:
+        go[:dim] = global_offset
+    nfull = tuple(int(c + 2 * nhalo) for c in celldims)
+    samp = None if sample is None else np.ascontiguousarray(sample, dtype=np.int64)
+    nout = int(np.prod(nfull)) if samp is None else len(samp)
+    out = _alloc(dim, nout, what)
+    rc = lib(precision).cgo_funcmap_eval(
+        ctypes.c_int(dim), ctypes.c_int(map_id), _dp(prm), ctypes.c_double(t), _ip(nc), ctypes.c_int(nhalo), _ip(go),
+        ctypes.c_int(_scheme(scheme)), ctypes.c_int64(0 if samp is None else len(samp)), _ip(samp), ctypes.c_int(what),
+        _dp(out["cell_fwd"]), _dp(out["cell_inv"]), _dp(out["face_fwd"]), _dp(out["face_inv"]), _dp(out["face_cons"]))
+    if rc != 0:
+        raise ValueError("cgo_funcmap_eval: unsupported dim/scheme")
+    out["nfull"] = nfull
+    return out
+
+
+def funcmap_coords(dim, map_id, params, t, celldims, nhalo, which, global_offset=None):
+    prm = np.ascontiguousarray(np.asarray(params, dtype=np.float64))
+    nc = np.array(list(celldims) + [1] * (3 - dim), dtype=np.int64)
+    go = np.zeros(3, dtype=np.int64)
+    if global_offset is not None:
+        go[:dim] = global_offset
+    npts = int(np.prod([c + 2 * nhalo + (1 if which == 0 else 0) for c in celldims]))
+    out = np.zeros((dim, npts))
+    lib().cgo_funcmap_coords(ctypes.c_int(dim), ctypes.c_int(map_id), _dp(prm), ctypes.c_double(t), _ip(nc),
+                             ctypes.c_int(nhalo), _ip(go), ctypes.c_int(which), _dp(out))
+    return out
+
+
 def gcl_max(face_cons, nfull, nhalo):
     """gcl.jl:20-117: max |I_c| over cell.domain per physical column c."""
     dim = len(nfull)

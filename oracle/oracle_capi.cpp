@@ -176,6 +176,31 @@ int cgo_mapped_eval(int dim, int nterms, const double* termtable, double t, cons
                   face_cons);
 }
 
+// MappedGrid with one of the non-separable test mappings of metric_oracle.hpp (FuncMap)
+int cgo_funcmap_eval(int dim, int id, const double* prm, double t, const int64_t* ncell, int nhalo, const int64_t* goff,
+                     int scheme, int64_t nsample, const int64_t* sample, int what, double* cell_fwd, double* cell_inv,
+                     double* face_fwd, double* face_inv, double* face_cons) {
+  FuncMap m{dim, id, prm};
+  int64_t nfull[3] = {1, 1, 1}, g[3] = {0, 0, 0};
+  for (int d = 0; d < dim; ++d) {
+    nfull[d] = ncell[d] + 2 * nhalo;
+    if (goff) g[d] = goff[d];
+  }
+  return dispatch(m, dim, scheme, t, nfull, nhalo, g, nsample, sample, what, cell_fwd, cell_inv, face_fwd, face_inv,
+                  face_cons);
+}
+int cgo_funcmap_coords(int dim, int id, const double* prm, double t, const int64_t* ncell, int nhalo, const int64_t* goff,
+                       int which, double* out) {
+  FuncMap m{dim, id, prm};
+  int64_t nfull[3] = {1, 1, 1}, g[3] = {0, 0, 0};
+  for (int d = 0; d < dim; ++d) {
+    nfull[d] = ncell[d] + 2 * nhalo;
+    if (goff) g[d] = goff[d];
+  }
+  eval_coords(m, dim, t, nfull, nhalo, g, which, out);
+  return 0;
+}
+
 int cgo_discrete_coords(int dim, const double* x, const double* y, const double* z, const int64_t* nn, int nhalo,
                         int which, double* out) {
   DiscreteMap m;

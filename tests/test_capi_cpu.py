@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "curvigrid_cuda.h")).read()
     declared = set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"cg_status", "cg_scheme"}
+    declared -= {"cg_status", "cg_scheme", "cg_map"}   # cg_map: the caller-supplied device function of the generic mapping
     lib = cg._lib.lib()
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
@@ -50,3 +50,21 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower() or f == "cg_mapped.cuh" or "oracle" in src.lower() and all(
                     "import" not in ln and "#include" not in ln for ln in src.splitlines() if "oracle" in ln.lower()), f
+
+
+def test_generic_mapping_source_compiles_without_a_gpu():
+    """cg_generic_compile_check: NVRTC turns prelude + mapping + generic kernels into an sm_100a cubin on the CPU box;
+    a broken mapping comes back as CG_ERR_ARG with the compiler's message.  (Skipped when libnvrtc is absent.)"""
+    import pytest
+    L = cg._lib
+    lib = L.lib()
+    good = cg.workloads.terms_to_cuda_source(cg.workloads.wavy_3d_terms((8, 8, 8), time_amp=0.1)).encode()
+    log = ctypes.create_string_buffer(4096)
+    rc = lib.cg_generic_compile_check(good, log, 4096)
+    if rc != L.CG_OK and b"libnvrtc not found" in log.value:
+        pytest.skip("libnvrtc is not installed here")
+    assert rc == L.CG_OK, log.value.decode()
+    bad = b"template <class S> __device__ void cg_map(S a, S b, S c, double t, const double* p, S& x, S& y, S& z) { x = undefined_fn(a); }"
+    assert lib.cg_generic_compile_check(bad, log, 4096) == L.CG_ERR_ARG
+    assert b"undefined_fn" in log.value and b"cg_map.cu" in log.value
+    assert lib.cg_grid_set_mapping_source(None, good) == L.CG_ERR_ARG
