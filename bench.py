@@ -706,6 +706,59 @@ def brief(line):
     return out
 
 
+def measure_legacy(cg, n=256, reps=5):
+    """Legacy MEG6 pipeline (CurvilinearGrid3D(x, y, z, :meg6) update!) on an n^3-cell wavy mesh: the
+    fused launches, CUDA events around each update (validity reduction included), median."""
+    import torch
+    x, y, z = cg.workloads.wavy_nodes_3d(n + 1, n + 1, n + 1)
+    mesh = cg.legacy.CurvilinearGrid3D(x, y, z, "meg6")
+    for _ in range(3):
+        cg.legacy.update(mesh, True, False)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cg.legacy.update(mesh, True, False)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    out = {"workload": f"legacy CurvilinearGrid3D {n}^3 wavy, :meg6, update! (centroids + 28 cell + 57 edge arrays)",
+           "dtype": "f64", "steps": reps, "value": n ** 3 / ms / 1e3, "unit": "Mcells/s", "ms_per_step": ms,
+           "gpu_launches": mesh.launches + 1, "algorithmic_bytes_per_cell": 848.0,
+           "frac": 848.0 * n ** 3 / (ms * 1e-3) / 1e9 / measured_peak_gbs()[0],
+           "bound": "FP64 issue (Kahan sums / isapprox thresholds of the reference, order-sensitive): DESIGN.md §10"}
+    del mesh
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_generic(cg, n=128, reps=3):
+    """MappedGrid with a NON-separable mapping through the NVRTC-compiled generic kernels: update! +
+    cell+face refresh, device time of the evaluation."""
+    src = """
+template <class S> __device__ void cg_map(S xi, S eta, S zeta, double t, const double* p, S& x, S& y, S& z) {
+  x = xi + p[0] * sin(p[1] * (eta + 0.5 * zeta) + 0.3 * t);
+  y = eta * (1.0 + p[2] * xi) / (1.0 + p[3] * zeta * zeta);
+  z = zeta + p[0] * exp(-p[4] * (xi - eta) * (xi - eta)) * cos(t) + sqrt(1.0 + 0.01 * xi * xi);
+}"""
+    g = cg.MappedGrid(src, [0.3, 0.4, 0.001, 1e-5, 0.02], (n, n, n), 5, cache_mode="lazy")
+    ts = []
+    for i in range(reps + 1):
+        cg.update(g, 0.1 * i)
+        cg.refresh_metrics(g)
+        ts.append(g.last_eval_ms())
+    ms = sorted(ts[1:])[len(ts[1:]) // 2]
+    gcl = max(cg.gcl(g))
+    out = {"workload": f"3-D MappedGrid {n}^3, non-separable mapping as CUDA source (NVRTC), update! + cell+face",
+           "scheme": "curvature", "dtype": "f64", "steps": reps, "value": (n + 10) ** 3 / ms / 1e3, "unit": "Mcells/s",
+           "ms_per_step": ms, "gpu_launches": 2, "gcl_max": gcl,
+           "bound": "FP64 issue: 108 mapping evaluations on 18-component jets per cell (fallback path)"}
+    g.close()
+    return out
+
+
 def run_ours(args, spec):
     import curvigrid_b200 as cg
     ctx = Ctx(args)
@@ -744,6 +797,12 @@ def run_ours(args, spec):
                 others["m3d512 (BASELINE config 4)"] = {"error": repr(e)[:300]}
             other("3d512 compact", workload_spec("3d512", None), profile="compact", dtype="f64", do_e2e=False)
             other("3d512 f32", workload_spec("3d512", None), profile="full", dtype="f32", do_e2e=False)
+            for name, fn in (("legacy meg6 256^3 (SURVEY rows a17-a21)", measure_legacy),
+                             ("generic mapping 128^3 (NVRTC)", measure_generic)):
+                try:
+                    others[name] = fn(cg)
+                except Exception as e:
+                    others[name] = {"error": repr(e)[:300]}
         else:
             other("sph1536 compact weak (BASELINE config 5)", workload_spec("sph1536", None), profile="compact", dtype="f64",
                   do_e2e=False)
