@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--h2d-chunks", type=int, default=16, help="pieces of the pipelined host->device update (e2e)")
+    ap.add_argument("--h2d-chunks", type=int, default=32, help="pieces of the pipelined host->device update (e2e)")
     ap.add_argument("--workload", default="3d512",
                     help="3d<N> | 2d<N> DiscreteGrid, m3d<N> MappedGrid with update! every step (interior cells per axis)")
     ap.add_argument("--scheme", default=None)
@@ -499,7 +499,7 @@ def measure_discrete(cg, ctx, args, spec, *, profile, dtype, steps, warmup, stro
             # cg_grid_update_from_host[_dist]: the owned node planes go to the device in pieces on a copy stream; the
             # planes the neighbours wait for first, then the NCCL exchange; each piece that lands releases the padded
             # planes and cell planes it completes
-            grid.update_from_host(*host_pinned, nchunks=args.h2d_chunks, comm=comm, plan=plan)
+            grid.update_from_host(*host_pinned, nchunks=args.h2d_chunks, comm=comm, plan=plan, gcl=True)
         else:
             grid.set_nodes(*host_pinned)
             if world > 1:

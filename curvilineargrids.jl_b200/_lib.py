@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("CG_LIB_PATH") or os.path.join(_HERE, "libcurvigrid_cu
 CG_OK, CG_ERR_ARG, CG_ERR_OOM, CG_ERR_CUDA, CG_ERR_STATE, CG_ERR_NCCL = range(6)
 CG_F64, CG_F32 = 0, 1
 CG_PROFILE_FULL, CG_PROFILE_COMPACT = 0, 1
-CG_WHAT_CELL, CG_WHAT_FACE, CG_WHAT_COORDS = 1, 2, 4
+CG_WHAT_CELL, CG_WHAT_FACE, CG_WHAT_COORDS, CG_WHAT_GCL = 1, 2, 4, 8
 (CG_ARR_CELL_FORWARD, CG_ARR_CELL_INVERSE, CG_ARR_FACE_FORWARD, CG_ARR_FACE_INVERSE, CG_ARR_FACE_CONSERVED,
  CG_ARR_NODE_COORD, CG_ARR_CENTROID_COORD, CG_ARR_FACE_COORD, CG_ARR_COMPACT_J, CG_ARR_COMPACT_ACTIVE) = range(10)
 CG_OPT_KERNEL = 0

@@ -76,6 +76,9 @@ struct cg_grid {
   std::vector<double> terms;
   cg::MappedTables mtab;
   cg::GenericMap gmap;  // generic (NVRTC-compiled) mapping: cg_grid_set_mapping_source
+  // GCL residuals accumulated plane by plane during cg_grid_update_from_host (CG_WHAT_GCL): valid while no other
+  // evaluation has rewritten the face metrics (face_epoch counts them)
+  uint64_t face_epoch = 0, gcl_epoch = ~0ull;
   double t = 0.0;
 
   size_t esize() const { return dtype == CG_F64 ? 8 : 4; }
@@ -331,7 +334,7 @@ int eval_generic(cg_grid* g, int what, cudaStream_t st) {
   CG_CUDA(cudaEventRecord(g->ev1, st));
   g->timed = true;
   if (what & CG_WHAT_CELL) g->valid_cell = true;
-  if (what & CG_WHAT_FACE) g->valid_face = true;
+  if (what & CG_WHAT_FACE) { g->valid_face = true; g->face_epoch++; }
   return CG_OK;
 }
 
@@ -419,7 +422,7 @@ int eval_mapped(cg_grid* g, int what, cudaStream_t st) {
   CG_CUDA(cudaEventRecord(g->ev1, st));
   g->timed = true;
   if (what & CG_WHAT_CELL) g->valid_cell = true;
-  if (what & CG_WHAT_FACE) g->valid_face = true;
+  if (what & CG_WHAT_FACE) { g->valid_face = true; g->face_epoch++; }
   return CG_OK;
 }
 
@@ -490,7 +493,7 @@ int eval_impl(cg_grid* g, int what, cudaStream_t st, int64_t k_lo = 0, int64_t k
   g->timed = true;
   if (final) {
     if (what & CG_WHAT_CELL) g->valid_cell = true;
-    if (what & CG_WHAT_FACE) g->valid_face = true;
+    if (what & CG_WHAT_FACE) { g->valid_face = true; g->face_epoch++; }
   }
   return CG_OK;
 }
@@ -1106,7 +1109,9 @@ namespace {
 // launches k_gcl over cell.domain of the global grid intersected with the window and leaves the per-column maxima as
 // bit patterns in g->gcl_bits.  Without `low` the window-local plane 0 of the slab axis is skipped (it needs
 // I - e_axis, which lives on the previous slab); `low` = that slab's last conserved plane of the slab axis.
-int gcl_launch(cg_grid* g, const void* low, cudaStream_t st, bool* empty) {
+// [p_lo, p_hi): restriction to window planes of the last axis (p_hi < 0: all); reset = clear the maxima first
+int gcl_launch(cg_grid* g, const void* low, cudaStream_t st, bool* empty, int64_t p_lo = 0, int64_t p_hi = -1,
+               bool reset = true) {
   const int N = g->dim;
   const bool compact = g->profile == CG_PROFILE_COMPACT;
   int64_t lo[3] = {0, 0, 0}, hi[3] = {1, 1, 1};
@@ -1116,9 +1121,13 @@ int gcl_launch(cg_grid* g, const void* low, cudaStream_t st, bool* empty) {
     const int64_t first = (low && d == N - 1) ? 0 : 1;
     lo[d] = l < first ? first : l;
     hi[d] = h > g->nw[d] ? g->nw[d] : h;
+    if (d == N - 1 && p_hi >= 0) {
+      if (lo[d] < p_lo) lo[d] = p_lo;
+      if (hi[d] > p_hi) hi[d] = p_hi;
+    }
     if (hi[d] <= lo[d]) *empty = true;
   }
-  CG_CUDA(cudaMemsetAsync(g->gcl_bits, 0, 3 * sizeof(unsigned long long), st));
+  if (reset) CG_CUDA(cudaMemsetAsync(g->gcl_bits, 0, 3 * sizeof(unsigned long long), st));
   if (*empty) return CG_OK;
   const void* c[3] = {nullptr, nullptr, nullptr};
   for (int a = 0; a < N; ++a) c[a] = compact ? g->cactive[a].p : g->face_cons[a].p;
@@ -1163,7 +1172,9 @@ int cg_grid_gcl_max_seam(cg_grid* g, const void* low_plane, double* out, void* s
   CG_CUDA(cudaSetDevice(g->device));
   cudaStream_t st = (cudaStream_t)stream;
   bool empty = false;
-  int rc = gcl_launch(g, low_plane, st, &empty);
+  // cg_grid_update_from_host with CG_WHAT_GCL has already reduced the planes >= 1: only the seam plane is left
+  const bool acc = g->gcl_epoch == g->face_epoch;
+  int rc = acc ? (low_plane ? gcl_launch(g, low_plane, st, &empty, 0, 1, false) : CG_OK) : gcl_launch(g, low_plane, st, &empty);
   if (rc) return rc;
   return gcl_read(g, out, st);
 }
@@ -1429,7 +1440,7 @@ int step_overlapped_t(cg_grid* g, ncclComm_t comm, const SlabPlanC& P, int what,
   if (S.ke_lo > 0 && (rc = eval_impl<T>(g, what, st, 0, S.ke_lo, false))) return rc;
   if (S.nw > S.ke_hi && (rc = eval_impl<T>(g, what, st, S.ke_hi, S.nw, false))) return rc;
   if (what & CG_WHAT_CELL) g->valid_cell = true;
-  if (what & CG_WHAT_FACE) g->valid_face = true;
+  if (what & CG_WHAT_FACE) { g->valid_face = true; g->face_epoch++; }
   return refresh_coords_if_stored(g, st);
 }
 }  // namespace
@@ -1461,7 +1472,13 @@ int update_from_host_t(cg_grid* g, const void* const* in, int what, int nchunks,
     own_lo = own.lo > o ? own.lo : o;
     own_hi = own.hi < o + nk ? own.hi : o + nk;
   }
-  std::vector<char> landed((size_t)nk, 0), padded((size_t)ne, 0), evald((size_t)nw, 0);
+  const bool do_gcl = (what & CG_WHAT_GCL) && (what & CG_WHAT_FACE);
+  what &= CG_WHAT_CELL | CG_WHAT_FACE;
+  std::vector<char> landed((size_t)nk, 0), padded((size_t)ne, 0), evald((size_t)nw, 0), gcld((size_t)nw, 0);
+  if (do_gcl) {
+    if (!g->gcl_bits) CG_CUDA(cudaMalloc((void**)&g->gcl_bits, 3 * sizeof(unsigned long long)));
+    CG_CUDA(cudaMemsetAsync(g->gcl_bits, 0, 3 * sizeof(unsigned long long), st));
+  }
   auto is_landed = [&](int64_t m) { return m >= o && m < o + nk && landed[(size_t)(m - o)]; };
   auto h2d = [&](int64_t lo, int64_t hi) -> int {  // interior node planes [lo, hi) on the copy stream
     for (int q = 0; q < 3; ++q)
@@ -1497,6 +1514,17 @@ int update_from_host_t(cg_grid* g, const void* const* in, int what, int nchunks,
       while (k1 < nw && ready(k1)) ++k1;
       if ((rc = eval_impl<T>(g, what, st, k, k1, false))) return rc;
       for (int64_t i = k; i < k1; ++i) evald[(size_t)i] = 1;
+      k = k1;
+    }
+    // GCL residuals of the planes whose own and lower conserved planes exist (plane 0 is the seam: cg_grid_gcl_max*)
+    for (int64_t k = 1; do_gcl && k < nw;) {
+      auto ready = [&](int64_t kk) { return !gcld[(size_t)kk] && evald[(size_t)kk] && evald[(size_t)(kk - 1)]; };
+      if (!ready(k)) { ++k; continue; }
+      int64_t k1 = k;
+      while (k1 < nw && ready(k1)) ++k1;
+      bool empty = false;
+      if ((rc = gcl_launch(g, nullptr, st, &empty, k, k1, false))) return rc;
+      for (int64_t i = k; i < k1; ++i) gcld[(size_t)i] = 1;
       k = k1;
     }
     return CG_OK;
@@ -1544,7 +1572,8 @@ int update_from_host_t(cg_grid* g, const void* const* in, int what, int nchunks,
   for (int64_t k = 0; k < nw; ++k)
     if (!evald[(size_t)k]) return fail(CG_ERR_STATE, "node buffer does not cover the window (cell plane %lld)", (long long)k);
   if (what & CG_WHAT_CELL) g->valid_cell = true;
-  if (what & CG_WHAT_FACE) g->valid_face = true;
+  if (what & CG_WHAT_FACE) { g->valid_face = true; g->face_epoch++; }
+  if (do_gcl) g->gcl_epoch = g->face_epoch;
   return refresh_coords_if_stored(g, st);
 }
 
@@ -1552,7 +1581,8 @@ int update_from_host_common(cg_grid* g, const void* x, const void* y, const void
                             int rank, int nranks, const int64_t* slab_bounds, void* stream) {
   if (!g) return fail(CG_ERR_ARG, "NULL grid");
   if (g->kind != 1 || g->dim != 3) return fail(CG_ERR_STATE, "cg_grid_update_from_host: 3-D DiscreteGrid only");
-  if (what <= 0 || what > 3) return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE)", what);
+  if (what <= 0 || (what & ~(CG_WHAT_CELL | CG_WHAT_FACE | CG_WHAT_GCL)) || !(what & 3))
+    return fail(CG_ERR_ARG, "bad what mask %d (CELL | FACE [| GCL])", what);
   const void* in[3] = {x, y, z};
   for (int q = 0; q < 3; ++q) {
     if (!in[q]) return fail(CG_ERR_ARG, "coordinate array %d is NULL", q);
@@ -1698,7 +1728,9 @@ int cg_grid_gcl_max_dist(cg_grid* g, void* comm, int rank, int nranks, double* o
     CG_NCCL(A.GroupEnd());
   }
   bool empty = false;
-  if ((rc = gcl_launch(g, rank > 0 ? g->seam.p : nullptr, st, &empty))) return rc;
+  if (g->gcl_epoch == g->face_epoch) {  // planes >= 1 were reduced while the host update ran: seam plane only
+    if (rank > 0 && (rc = gcl_launch(g, g->seam.p, st, &empty, 0, 1, false))) return rc;
+  } else if ((rc = gcl_launch(g, rank > 0 ? g->seam.p : nullptr, st, &empty))) return rc;
   // non-negative doubles order like their bit patterns (a NaN pattern is the largest): max over ranks on the bits
   if (nranks > 1) CG_NCCL(A.AllReduce(g->gcl_bits, g->gcl_bits, 3, ncclUint64, ncclMax, (ncclComm_t)comm, st));
   return gcl_read(g, out, st);

@@ -325,12 +325,13 @@ class DiscreteGrid(_UnifiedGrid):
         if any(isinstance(k, np.ndarray) or not k.is_cuda for k in keep):
             self.synchronize()  # host memory must outlive the async copy
 
-    def update_from_host(self, *coords, what=3, nchunks=8, comm=None, plan=None):
+    def update_from_host(self, *coords, what=3, nchunks=8, comm=None, plan=None, gcl=False):
         """update!(grid, x, y, z) from HOST arrays + refresh of both caches, pipelined (cg_grid_update_from_host):
         the H2D copy of a piece of node planes overlaps the metric kernels of the piece before.  `coords`: pinned
         CPU torch tensors (or numpy arrays) in memory order [k, j, i] with the extents of the constructor's arrays.
         With `comm` (slabs.NcclComm) and `plan` the grid is a k-slab: only the owned planes are read from the host
-        arrays and the neighbour planes arrive through NCCL meanwhile (cg_grid_update_from_host_dist)."""
+        arrays and the neighbour planes arrive through NCCL meanwhile (cg_grid_update_from_host_dist).  `gcl=True`
+        (CG_WHAT_GCL): the GCL residuals are reduced plane by plane behind the kernels; the next gcl(grid) only reads them."""
         torch = _torch()
         if self.dim != 3:
             raise ValueError("update_from_host: 3-D DiscreteGrid only")
@@ -346,6 +347,8 @@ class DiscreteGrid(_UnifiedGrid):
         if len(ptrs) != 3:
             raise ValueError("update_from_host takes three coordinate arrays")
         self._bind_metric_outputs(what)
+        if gcl:
+            what = what | L.CG_WHAT_GCL
         if comm is not None and comm.nranks > 1:
             L.check(L.lib().cg_grid_update_from_host_dist(
                 self._h, *[ctypes.c_void_p(t.data_ptr()) for t in ptrs], what, int(nchunks), comm._h, comm.rank,

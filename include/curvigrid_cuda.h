@@ -70,7 +70,7 @@ enum cg_dtype { CG_F64 = 0, CG_F32 = 1 };
 /* FULL: the reference's 107 doubles/cell (3-D).  COMPACT: J of the cell + the active conserved
  * row per axis = what face_flux_geometry/cellvolume read (face_geometry.jl:393-416). */
 enum cg_profile { CG_PROFILE_FULL = 0, CG_PROFILE_COMPACT = 1 };
-enum cg_what { CG_WHAT_CELL = 1, CG_WHAT_FACE = 2, CG_WHAT_COORDS = 4 };
+enum cg_what { CG_WHAT_CELL = 1, CG_WHAT_FACE = 2, CG_WHAT_COORDS = 4, CG_WHAT_GCL = 8 /* cg_grid_update_from_host* only */ };
 
 /* array selectors for cg_grid_get_ptr / cg_grid_copy_out / cg_grid_bind_output */
 enum cg_array {
@@ -197,7 +197,9 @@ int cg_grid_eval_planes(cg_grid* g, int what, int64_t k_lo, int64_t k_hi, int fi
  * planes it completes on `stream` (cg_grid_pad_planes / cg_grid_eval_planes), so the host-to-device copy of piece
  * c+1 overlaps the metric kernels of piece c.  Marks the caches valid.  The copies land in a node buffer the
  * library owns: if cg_grid_set_nodes was given DEVICE arrays the handle stops aliasing them and allocates its own
- * (a caller's device array is never overwritten).
+ * (a caller's device array is never overwritten).  With CG_WHAT_GCL in `what` the GCL residuals of every plane are
+ * reduced as soon as the plane and the one below it are complete, overlapped with the copy of the later pieces; the next
+ * cg_grid_gcl_max / _seam / _dist then only adds the seam plane and reads the three maxima (same values, bit for bit).
  */
 int cg_grid_update_from_host(cg_grid* g, const void* x, const void* y, const void* z, int what, int nchunks,
                              void* stream);

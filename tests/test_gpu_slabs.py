@@ -119,3 +119,26 @@ def test_update_from_host_pipelined(cg, nchunks, profile):
             a, b = cg.face_metrics(g)[ax].cpu().numpy(), cg.face_metrics(ref_g)[ax].cpu().numpy()
             assert np.abs(a - b).max() <= 5e-13 * np.abs(b).max()
     assert max(cg.gcl(g)) < 1e-12
+
+
+@pytest.mark.parametrize("profile", ["full", "compact"])
+def test_update_from_host_accumulates_gcl_plane_by_plane(cg, profile):
+    """CG_WHAT_GCL: the residuals reduced behind the pieces of the pipelined host update are the residuals of one
+    reduction over the finished arrays, bit for bit (a max does not depend on the order), a poisoned conserved entry still
+    comes back as NaN from a fresh reduction, and any later evaluation drops the accumulated values."""
+    h = 3
+    nodes = mild_nodes((20, 9, 26), seed=4)
+    pinned = [torch.from_numpy(np.ascontiguousarray(a.transpose(2, 1, 0))).pin_memory() for a in nodes]
+    g = cg.DiscreteGrid(*nodes, h, profile=profile, cache_mode="lazy", conserved_metric_scheme="endpoint")
+    cg.refresh_metrics(g)
+    want = cg.gcl(g)                       # one reduction over the whole grid
+    launches0 = cg._lib.lib().cg_launch_count()
+    g.update_from_host(*pinned, nchunks=5, gcl=True)
+    n_update = cg._lib.lib().cg_launch_count() - launches0
+    got = cg.gcl(g)                        # reads the accumulated maxima: no further launch
+    assert cg._lib.lib().cg_launch_count() - launches0 == n_update
+    assert got == want and max(got) > 0.0
+    cg.refresh_metrics(g)                  # another evaluation: the accumulated values are stale, gcl reduces again
+    launches1 = cg._lib.lib().cg_launch_count()
+    assert cg.gcl(g) == want
+    assert cg._lib.lib().cg_launch_count() == launches1 + 1
