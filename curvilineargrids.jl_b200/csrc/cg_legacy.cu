@@ -17,12 +17,15 @@
 // folded into the neighbouring pass, and all temporaries live in four scratch arrays.  The
 // thresholds (tol_diff, eps clips) are discontinuous, so this translation unit is compiled with
 // -fmad=false and keeps the reference's operation order (Kahan sums included).
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cfloat>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/curvigrid_cuda.h"
 
@@ -330,7 +333,7 @@ __global__ void k_legacy_inv2d(LShape S, LBox dom, const double* __restrict__ fw
 //   h  on [t0-1, t1+1)                        (interp: [t0, t1+1))
 //   d1 on the h range +-1,  and [0,6) / [n-6,n) when the h range touches the first / last three cells
 //   phi on the d1 range +-3, and [0,6) / [n-6,n) likewise                       (all clamped to [0, n))
-// axis != 0: lines = 32 consecutive xi (lanes, coalesced), T = 56 positions walked by the 8 warps;
+// axis != 0: lines = 32 consecutive xi (lanes, coalesced), T = 54 positions walked by the 8 warps;
 // axis == 0: lines = 8 consecutive eta rows (warps), T = 118 positions along xi (lanes, coalesced).
 // Several fields (jobs) share one launch through blockIdx.y.
 // ---------------------------------------------------------------------------
@@ -354,6 +357,14 @@ __device__ __forceinline__ double mixed_edge(const double* w, int row) {
 struct LJob {
   const double *a, *b, *c, *d;  // source = a | a*b | a*b - c*d
   double* out;
+  int map, idx;                 // TMA path: `a` is row `idx` of the array block behind tensor map `map`
+};
+// The two array blocks a plain source field can live in ([rows][ncell]: the cell SoA and the centroid scratch), for the
+// TMA tensor maps of a launch.
+struct LTmaCtx {
+  const double* base[2];
+  int rows[2];
+  long long nc;
 };
 constexpr int LMAXJ = 19;
 struct LJobs {
@@ -361,13 +372,26 @@ struct LJobs {
 };
 enum { OP_CCD = 0, OP_CCD_POST = 1, OP_INTERP = 2 };
 
-template <bool AX0, int SRC, int OP>
-__global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int axis, int whole, LJobs jobs, double scale) {
-  constexpr int T = AX0 ? 118 : 56, LN = AX0 ? 8 : 32, PS = AX0 ? 32 : 8;
+// TMA = true (plain source fields, even row length): the brick of the source field — 32 lines x 66 positions, or 8 lines
+// x 128 positions along xi — arrives by ONE tensor-map TMA load (cp.async.bulk.tensor.4d, SASS UTMALDG) issued by one
+// thread and signalled on an mbarrier, instead of a load + store per element; the tensor map covers the whole array
+// block [row][k][j][i], out-of-range parts of a box are zero-filled by the hardware (they are never read).
+template <bool AX0, int SRC, int OP, bool TMA>
+__global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int axis, int whole, LJobs jobs, double scale,
+                                                         const __grid_constant__ CUtensorMap tm0,
+                                                         const __grid_constant__ CUtensorMap tm1) {
+  constexpr int T = AX0 ? 118 : 54, LN = AX0 ? 8 : 32, PS = AX0 ? 32 : 8;
   constexpr int WP = T + 10, WD = T + 5, WH = T + 2;
-  constexpr int LS = AX0 ? 1 : LN;  // shared-memory stride between consecutive positions of a line
+  constexpr int LS = AX0 ? 1 : LN;  // shared-memory stride between consecutive positions of a line (d1, h)
+  // The source brick has room for one more element at either end of the xi extent: a TMA box must start at a 16-byte
+  // aligned address, i.e. at an EVEN xi index, so the box starts one cell early when the tile starts at an odd one
+  // (`sft`); row pitch 34 (lines along xi) / 130 (positions along xi).
+  constexpr int PLN = AX0 ? LN : LN + 2, PWP = AX0 ? WP + 2 : WP;
+  constexpr int LSP = AX0 ? 1 : PLN;  // stride between consecutive positions of a line in the source brick
   constexpr int IT_P = (WP + PS - 1) / PS, IT_D = (WD + PS - 1) / PS, IT_H = (WH + PS - 1) / PS, IT_O = (T + PS - 1) / PS;
-  __shared__ double sphi[LN * WP], sd1[LN * WD], sh[LN * WH];
+  __shared__ __align__(128) double sphi[PLN * PWP];
+  __shared__ double sd1[LN * WD], sh[LN * WH];
+  __shared__ __align__(8) unsigned long long mbar;
   const LJob J = jobs.j[blockIdx.y];
   const int n = dom.hi[axis] - dom.lo[axis];
   const int ntile = (n + T - 1) / T;
@@ -383,7 +407,10 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   const int hl = OP == OP_INTERP ? t0 : max(0, t0 - 1), hh = min(n, t1 + 1);
   int dl = max(0, hl - 1), dh = min(n, hh + 1);
   if (hl < 3) dh = max(dh, 6);
-  if (hh > n - 3) dl = min(dl, n - 6);
+  if (hh > n - 3) {  // a one-sided second derivative reads ALL of d1[n-6 .. n-1]
+    dl = min(dl, n - 6);
+    dh = n;
+  }
   int pl = max(0, dl - 3), ph = min(n, dh + 3);
   if (dl < 3) ph = max(ph, 6);
   if (dh > n - 3) pl = min(pl, n - 6);
@@ -394,16 +421,45 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   const long long base = (long long)(dom.lo[la] + li) * S.st[la] + (long long)(dom.lo[oa] + oi) * S.st[oa] +
                          (long long)dom.lo[axis] * s;  // array index of position 0 of this line
   // per-line shared-memory rows; X_at(p) = address of absolute position p
-  double* const phi_l = sphi + (AX0 ? line * WP : line) - pl * LS;
+  const int sft = TMA ? ((dom.lo[0] + (AX0 ? pl : gr * LN)) & 1) : 0;
+  double* const phi_l = sphi + (AX0 ? line * PWP : line) + sft - pl * LSP;
   double* const d1_l = sd1 + (AX0 ? line * WD : line) - dl * LS;
   double* const h_l = sh + (AX0 ? line * WH : line) - hl * LS;
   // ---- phase 1: source field ----
-  if (lok) {
+  if (TMA) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(&mbar);
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // box origin: lines from dom.lo[la] + gr * LN, positions from dom.lo[axis] + pl, the third index, the array row
+      int c[3];
+      c[axis] = dom.lo[axis] + pl;
+      c[la] = dom.lo[la] + gr * LN;
+      c[oa] = dom.lo[oa] + oi;
+      c[0] -= sft;
+      const CUtensorMap* tm = J.map == 0 ? &tm0 : &tm1;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(PLN * PWP * sizeof(double)))
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+              (unsigned)__cvta_generic_to_shared(sphi)),
+          "l"(tm), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(J.idx), "r"(mb)
+          : "memory");
+    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tCG_TMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra CG_TMA_DONE;\n\t"
+        "bra CG_TMA_WAIT;\n\tCG_TMA_DONE:\n\t}" ::"r"(mb)
+        : "memory");
+  } else if (lok) {
     long long I = base + (long long)(pl + p0) * s;
 #pragma unroll
     for (int k = 0; k < IT_P; ++k, I += PS * s) {
       const int p = pl + p0 + PS * k;
-      if (p < ph) phi_l[p * LS] = src_val<SRC>(J.a, J.b, J.c, J.d, I);
+      if (p < ph) phi_l[p * LSP] = src_val<SRC>(J.a, J.b, J.c, J.d, I);
     }
   }
   __syncthreads();
@@ -415,14 +471,14 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   auto d1_at = [&](int p) {  // k_legacy_first at absolute position p
     double r;
     if (p >= 3 && p < n - 3) {
-      const double* q = phi_l + p * LS;
-      r = central6(q[-3 * LS], q[-2 * LS], q[-LS], q[LS], q[2 * LS], q[3 * LS]);
+      const double* q = phi_l + p * LSP;
+      r = central6(q[-3 * LSP], q[-2 * LSP], q[-LSP], q[LSP], q[2 * LSP], q[3 * LSP]);
     } else {
       const bool low = p < 3;
-      const double* q = phi_l + (low ? 0 : n - 6) * LS;
+      const double* q = phi_l + (low ? 0 : n - 6) * LSP;
       double w[6];
 #pragma unroll
-      for (int m = 0; m < 6; ++m) w[m] = q[m * LS];
+      for (int m = 0; m < 6; ++m) w[m] = q[m * LSP];
       r = mixed_edge(w, low ? p : p - (n - 6));
     }
     d1_l[p * LS] = r;
@@ -431,9 +487,9 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
     const double* d = d1_l + p * LS;
     double r;
     if (p >= 3 && p < n - 3) {
-      const double* q = phi_l + p * LS;
+      const double* q = phi_l + p * LSP;
       const double dd = -tol_diff(d[LS], d[-LS]) / 2;
-      r = kahan3(2 * (q[LS] + q[-LS]), -4 * q[0], dd);
+      r = kahan3(2 * (q[LSP] + q[-LSP]), -4 * q[0], dd);
     } else {
       const bool low = p < 3;
       const double* q = d1_l + (low ? 0 : n - 6) * LS;
@@ -447,22 +503,22 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   const double e50 = 50 * DBL_EPSILON;
   const int first = whole ? 1 : 0, last = whole ? n - 2 : n - 1;  // interp: positions written (k_legacy_interp)
   auto out_at = [&](int p) {  // k_legacy_meg / k_legacy_interp at p
-    const double* q = phi_l + p * LS;
+    const double* q = phi_l + p * LSP;
     const double* h = h_l + p * LS;
     double* o = J.out + base + (long long)p * s;
     const double L0 = q[0] + h[0];
     if (OP == OP_INTERP) {
       if (p < first || p > last) return;
       if (p == last) o[0] = L0;
-      else o[0] = (L0 + (q[LS] - h[LS])) / 2;
+      else o[0] = (L0 + (q[LSP] - h[LS])) / 2;
       if (p == first) o[-s] = q[0] - h[0];
     } else {
       const double R0 = q[0] - h[0];
       double hi, lw;
       if (p == n - 1) hi = L0;
-      else hi = (L0 + (q[LS] - h[LS])) / 2;
+      else hi = (L0 + (q[LSP] - h[LS])) / 2;
       if (p == 0) lw = R0;
-      else lw = ((q[-LS] + h[-LS]) + R0) / 2;
+      else lw = ((q[-LSP] + h[-LS]) + R0) / 2;
       const double v = clip(hi - lw, e50);
       if (OP == OP_CCD) o[0] = v;
       else o[0] = clip(scale * (o[0] - v), e50);
@@ -473,10 +529,10 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
     if (!AX0) {
       const int pb = dl + CK * p0;
       if (pb >= 3 && pb + CK <= min(dh, n - 3)) {
-        const double* q = phi_l + pb * LS;
+        const double* q = phi_l + pb * LSP;
         double v[CK + 6];
 #pragma unroll
-        for (int m = 0; m < CK + 6; ++m) v[m] = q[(m - 3) * LS];
+        for (int m = 0; m < CK + 6; ++m) v[m] = q[(m - 3) * LSP];
 #pragma unroll
         for (int k = 0; k < CK; ++k)
           d1_l[(pb + k) * LS] = central6(v[k], v[k + 1], v[k + 2], v[k + 4], v[k + 5], v[k + 6]);
@@ -498,11 +554,11 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
     if (!AX0) {
       const int pb = hl + CK * p0;
       if (pb >= 3 && pb + CK <= min(hh, n - 3)) {
-        const double *q = phi_l + pb * LS, *d = d1_l + pb * LS;
+        const double *q = phi_l + pb * LSP, *d = d1_l + pb * LS;
         double f[CK + 2], g[CK + 2];
 #pragma unroll
         for (int m = 0; m < CK + 2; ++m) {
-          f[m] = q[(m - 1) * LS];
+          f[m] = q[(m - 1) * LSP];
           g[m] = d[(m - 1) * LS];
         }
 #pragma unroll
@@ -531,12 +587,12 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
     if (pb >= t1) return;
     const bool fast = OP == OP_INTERP ? (pb >= first + 1 && pb + CK <= min(t1, last)) : (pb >= 1 && pb + CK <= min(t1, n - 1));
     if (fast) {
-      const double *q = phi_l + pb * LS, *h = h_l + pb * LS;
+      const double *q = phi_l + pb * LSP, *h = h_l + pb * LS;
       double* o = J.out + base + (long long)pb * s;
       double Lm[CK + 2], Rm[CK + 2];  // states of the positions pb-1 .. pb+CK
 #pragma unroll
       for (int m = OP == OP_INTERP ? 1 : 0; m < CK + 2; ++m) {  // (interp has no use for the state below the chunk)
-        const double f = q[(m - 1) * LS], hh_ = h[(m - 1) * LS];
+        const double f = q[(m - 1) * LSP], hh_ = h[(m - 1) * LS];
         Lm[m] = f + hh_;
         Rm[m] = f - hh_;
       }
@@ -584,18 +640,67 @@ __global__ void k_legacy_zero_outside(LShape S, LBox keep, double* arr, long lon
   }
 }
 
+typedef CUresult (*LEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+LEncodeFn tensor_map_encoder() {
+  const char* e = getenv("CG_LEGACY_TMA");  // debug switch (listed in include/curvigrid_cuda.h), read at every launch
+  if (e && atoi(e) == 0) return nullptr;
+  static const LEncodeFn fn = [] {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    return h ? (LEncodeFn)dlsym(h, "cuTensorMapEncodeTiled") : (LEncodeFn) nullptr;
+  }();
+  return fn;
+}
+// tensor map of an array block [rows][n2][n1][n0] with the box of a tile of the fused kernel along `axis`
+bool make_tile_map(CUtensorMap& tm, const double* base, int rows, const LShape& S, int axis) {
+  const LEncodeFn enc = tensor_map_encoder();
+  if (!enc || !base || rows < 1 || (S.n[0] & 1) || (reinterpret_cast<uintptr_t>(base) & 15)) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)S.n[0], (cuuint64_t)S.n[1], (cuuint64_t)S.n[2], (cuuint64_t)rows};
+  const cuuint64_t strides[3] = {(cuuint64_t)S.n[0] * 8, (cuuint64_t)S.n[0] * S.n[1] * 8, (cuuint64_t)S.n[0] * S.n[1] * S.n[2] * 8};
+  cuuint32_t box[4] = {1, 1, 1, 1};
+  if (axis == 0) { box[0] = 130; box[1] = 8; }   // PWP x LN of k_legacy_fused<true>
+  else { box[0] = 34; box[axis] = 64; }          // PLN x WP of k_legacy_fused<false>
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int SRC, int OP>
-void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs, int njobs, double scale,
-                  cudaStream_t st) {
+void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs_in, int njobs, double scale,
+                  cudaStream_t st, const LTmaCtx* tma = nullptr) {
   const int n = md.hi[axis] - md.lo[axis];
-  const dim3 blk = axis == 0 ? dim3(32, 8) : dim3(32, 8);
+  const dim3 blk(32, 8);
+  LJobs jobs = jobs_in;
+  CUtensorMap tm[2];
+  memset(tm, 0, sizeof tm);
+  bool use_tma = SRC == 0 && tma != nullptr;
+  bool need[2] = {false, false};
+  for (int m = 0; m < njobs && use_tma; ++m) {  // every source field must be a row of one of the two array blocks
+    bool found = false;
+    for (int b = 0; b < 2 && !found; ++b) {
+      const long long off = jobs.j[m].a - tma->base[b];
+      if (tma->base[b] && off >= 0 && off % tma->nc == 0 && off / tma->nc < tma->rows[b]) {
+        jobs.j[m].map = b;
+        jobs.j[m].idx = (int)(off / tma->nc);
+        need[b] = found = true;
+      }
+    }
+    use_tma = found;
+  }
+  for (int b = 0; b < 2 && use_tma; ++b)
+    if (need[b]) use_tma = make_tile_map(tm[b], tma->base[b], tma->rows[b], S, axis);
   if (axis == 0) {
     const long long nt = (n + 117) / 118, ng = (md.hi[1] - md.lo[1] + 7) / 8, no = md.hi[2] - md.lo[2];
-    k_legacy_fused<true, SRC, OP><<<dim3((unsigned)(nt * ng * no), njobs), blk, 0, st>>>(S, md, axis, whole, jobs, scale);
+    const dim3 grid((unsigned)(nt * ng * no), njobs);
+    if (use_tma) k_legacy_fused<true, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
+    else k_legacy_fused<true, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
   } else {
     const int oa = axis == 1 ? 2 : 1;
-    const long long nt = (n + 55) / 56, ng = (md.hi[0] - md.lo[0] + 31) / 32, no = md.hi[oa] - md.lo[oa];
-    k_legacy_fused<false, SRC, OP><<<dim3((unsigned)(nt * ng * no), njobs), blk, 0, st>>>(S, md, axis, whole, jobs, scale);
+    const long long nt = (n + 53) / 54, ng = (md.hi[0] - md.lo[0] + 31) / 32, no = md.hi[oa] - md.lo[oa];
+    const dim3 grid((unsigned)(nt * ng * no), njobs);
+    if (use_tma) k_legacy_fused<false, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
+    else k_legacy_fused<false, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
   }
 }
 bool legacy_fused() {
@@ -618,15 +723,15 @@ void zero_outside(const LShape& S, const LBox& full, const LBox& keep, double* a
 }
 // the 19 (3-D) / 9 (2-D) / 3 (1-D) edge interpolations of one axis in one launch
 void interp_axis_fused(const LShape& S, const LBox& full, const LBox& md, int axis, int whole, const double* const* phi,
-                       int nphi, double* E, long long nc, cudaStream_t st, uint64_t& nl) {
+                       int nphi, double* E, long long nc, cudaStream_t st, uint64_t& nl, const LTmaCtx* tma = nullptr) {
   // written: md along the other axes; along `axis` positions [first-1, last] of md
   LBox keep = md;
   if (whole) keep.hi[axis] = md.hi[axis] - 1;
   else keep.lo[axis] = md.lo[axis] - 1;
   zero_outside(S, full, keep, E, nphi, nc, st, nl);
   LJobs jobs{};
-  for (int m = 0; m < nphi; ++m) jobs.j[m] = {phi[m], nullptr, nullptr, nullptr, E + (long long)m * nc};
-  launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st);
+  for (int m = 0; m < nphi; ++m) jobs.j[m] = {phi[m], nullptr, nullptr, nullptr, E + (long long)m * nc, 0, 0};
+  launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st, tma);
   ++nl;
 }
 
@@ -699,6 +804,7 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
   double* hat = cell + 19 * nc;
   const int bl = blocks_for(box_count(md)), bw = blocks_for(nc);
   if (legacy_fused()) {
+    const LTmaCtx tma = {{cell, scratch}, {28, 3}, nc};  // source fields are rows of the cell SoA or the centroid scratch
     // 15 launches: every derivative is one fused launch (first + second derivative + MEG reconstruction through shared
     // memory), the fields that share an axis share the launch; only the shell outside the metric domain is cleared
     zero_outside(S, full, md, cell, 28, nc, st, nl);
@@ -709,8 +815,8 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
     if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)3 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     for (int ax = 0; ax < 3; ++ax) {  // forward metrics: d x_q / d xi_ax, q = 0..2
       LJobs jobs{};
-      for (int q = 0; q < 3; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 3 + ax) * nc};
-      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st);
+      for (int q = 0; q < 3; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 3 + ax) * nc, 0, 0};
+      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st, &tma);
       ++nl;
     }
     k_legacy_det<<<bl, 256, 0, st>>>(S, md, fwd, nc, J);
@@ -723,8 +829,8 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
         double* h = hat + (long long)(r * 3 + c) * nc;
         const double *a_s = fwd + (long long)(q1 * 3 + s) * nc, *a_u = fwd + (long long)(q1 * 3 + u) * nc;
         const double *b_s = fwd + (long long)(q2 * 3 + s) * nc, *b_u = fwd + (long long)(q2 * 3 + u) * nc;
-        j1.j[c] = {a_s, C[q2], symmetric ? b_s : nullptr, symmetric ? C[q1] : nullptr, h};
-        j2.j[c] = {a_u, C[q2], symmetric ? b_u : nullptr, symmetric ? C[q1] : nullptr, h};
+        j1.j[c] = {a_s, C[q2], symmetric ? b_s : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0};
+        j2.j[c] = {a_u, C[q2], symmetric ? b_u : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0};
       }
       if (symmetric) {
         launch_fused<2, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
@@ -740,7 +846,7 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
     for (int ax = 0; ax < 3; ++ax) {
       const double* phi[19];
       for (int m = 0; m < 19; ++m) phi[m] = m == 0 ? J : cell + (long long)(9 + m) * nc;  // J, inv 0..8, hat 0..8
-      interp_axis_fused(S, full, md, ax, whole, phi, 19, edge + (long long)ax * 19 * nc, nc, st, nl);
+      interp_axis_fused(S, full, md, ax, whole, phi, 19, edge + (long long)ax * 19 * nc, nc, st, nl, &tma);
     }
   } else {
   cudaMemsetAsync(cell, 0, (size_t)28 * nc * sizeof(double), st);
@@ -854,6 +960,7 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
   double* hat = cell + 9 * nc;
   const int bl = blocks_for(box_count(md));
   if (legacy_fused()) {
+    const LTmaCtx tma = {{cell, scratch}, {13, 2}, nc};
     zero_outside(S, full, md, cell, 13, nc, st, nl);
     zero_outside(S, full, md, scratch, 2, nc, st, nl);
     k_legacy_centroid2d<<<bl, 256, 0, st>>>(S, md, x, y, halo_coords_included ? 0 : nhalo, (int)nnode[0], cx, cy);
@@ -861,8 +968,8 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
     if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)2 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     for (int ax = 0; ax < 2; ++ax) {  // forward_metrics.jl:36-60
       LJobs jobs{};
-      for (int q = 0; q < 2; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 2 + ax) * nc};
-      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 2, 1.0, st);
+      for (int q = 0; q < 2; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 2 + ax) * nc, 0, 0};
+      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 2, 1.0, st, &tma);
       ++nl;
     }
     k_legacy_inv2d<<<bl, 256, 0, st>>>(S, md, fwd, nc, J, inv, hat);
@@ -870,7 +977,7 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
     for (int ax = 0; ax < 2; ++ax) {  // MetricDiscretizationSchemes.jl:58-89
       const double* phi[9];
       for (int m = 0; m < 9; ++m) phi[m] = m == 0 ? J : cell + (long long)(4 + m) * nc;  // J, inv 0..3, hat 0..3
-      interp_axis_fused(S, full, md, ax, whole, phi, 9, edge + (long long)ax * 9 * nc, nc, st, nl);
+      interp_axis_fused(S, full, md, ax, whole, phi, 9, edge + (long long)ax * 9 * nc, nc, st, nl, &tma);
     }
   } else {
   cudaMemsetAsync(cell, 0, (size_t)13 * nc * sizeof(double), st);
@@ -999,18 +1106,19 @@ extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64
   double *J = cell, *xxi = cell + nc, *inv = cell + 2 * nc, *hat = cell + 3 * nc;
   const int bl = blocks_for(box_count(md));
   if (legacy_fused()) {
+    const LTmaCtx tma = {{cell, scratch}, {4, 1}, nc};
     zero_outside(S, full, md, cell, 4, nc, st, nl);
     zero_outside(S, full, md, scratch, 1, nc, st, nl);
     k_legacy_centroid1d<<<bl, 256, 0, st>>>(S, md, x, halo_coords_included ? 0 : nhalo, cx);
     ++nl;
     if (centroid) cudaMemcpyAsync(centroid, cx, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     LJobs jobs{};
-    jobs.j[0] = {cx, nullptr, nullptr, nullptr, xxi};  // forward_metrics.jl:11-27
-    launch_fused<0, OP_CCD>(S, md, 0, whole, jobs, 1, 1.0, st);
+    jobs.j[0] = {cx, nullptr, nullptr, nullptr, xxi, 0, 0};  // forward_metrics.jl:11-27
+    launch_fused<0, OP_CCD>(S, md, 0, whole, jobs, 1, 1.0, st, &tma);
     k_legacy_inv1d<<<bl, 256, 0, st>>>(S, md, xxi, J, inv, hat);
     nl += 2;
     const double* phi[3] = {J, inv, hat};  // MetricDiscretizationSchemes.jl:58-89
-    interp_axis_fused(S, full, md, 0, whole, phi, 3, edge, nc, st, nl);
+    interp_axis_fused(S, full, md, 0, whole, phi, 3, edge, nc, st, nl, &tma);
   } else {
   cudaMemsetAsync(cell, 0, (size_t)4 * nc * sizeof(double), st);
   cudaMemsetAsync(edge, 0, (size_t)3 * nc * sizeof(double), st);

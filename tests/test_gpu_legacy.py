@@ -231,11 +231,13 @@ def test_legacy_1d_decreasing_mesh_is_accepted(cg):
 
 @pytest.mark.parametrize("symmetric", [False, True])
 @pytest.mark.parametrize("halo_included", [False, True])
-@pytest.mark.parametrize("shape", [(131, 58, 63), (120, 62, 115)])
+@pytest.mark.parametrize("shape", [(131, 58, 63), (122, 62, 115)])
 def test_legacy_fused_equals_pass_by_pass_bitwise(cg, monkeypatch, shape, symmetric, halo_included):
     """The fused launches (first + second derivative + MEG reconstruction / edge interpolation through shared memory,
     shell-only clearing) reproduce the pass-by-pass pipeline (CG_LEGACY_FUSED=0) bit for bit, on grids that need
-    several tiles per axis and end in short tiles (57 = 56 + 1, 119 = 118 + 1 cells), from poisoned output buffers."""
+    several tiles per axis and end in short tiles (57 = 54 + 3 and 121 = 118 + 3 cells: the one-sided stencils of the last
+    three cells reach back into the tile before; 114 = 2 x 54 + 6), with the TMA brick load (even row length) and
+    without it, from poisoned output buffers."""
     import torch
     nodes = mild_nodes(shape, seed=7)
     scheme = "meg6_symmetric" if symmetric else "meg6"
