@@ -27,6 +27,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/curvigrid_cuda.h"
 
 namespace {
@@ -755,6 +757,7 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
                                         const int64_t* nnode, int nhalo, int halo_coords_included, int symmetric,
                                         double* cell, double* edge, double* centroid, double* scratch,
                                         size_t scratch_bytes, void* stream, uint64_t* launches) {
+  struct R { R() { nvtxRangePushA("cg_legacy_meg6_update_3d"); } ~R() { nvtxRangePop(); } } nvtx_range_;
   g_legacy_err[0] = 0;
   if (!x || !y || !z || !nnode || !cell || !edge || !scratch) {
     snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_meg6_update_3d: NULL argument");
@@ -909,6 +912,7 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
 extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const double* y, const int64_t* nnode, int nhalo,
                                         int halo_coords_included, double* cell, double* edge, double* centroid,
                                         double* scratch, size_t scratch_bytes, void* stream, uint64_t* launches) {
+  struct R { R() { nvtxRangePushA("cg_legacy_meg6_update_2d"); } ~R() { nvtxRangePop(); } } nvtx_range_;
   g_legacy_err[0] = 0;
   if (!x || !y || !nnode || !cell || !edge || !scratch) {
     snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_meg6_update_2d: NULL argument");
@@ -1064,6 +1068,7 @@ __global__ void k_legacy_check_valid(LShape S, LBox dom, LRows R, const double* 
 extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64_t* nnode, int nhalo, int halo_coords_included,
                                         double* cell, double* edge, double* centroid, double* scratch,
                                         size_t scratch_bytes, void* stream, uint64_t* launches) {
+  struct R { R() { nvtxRangePushA("cg_legacy_meg6_update_1d"); } ~R() { nvtxRangePop(); } } nvtx_range_;
   g_legacy_err[0] = 0;
   if (!x || !nnode || !cell || !edge || !scratch) {
     snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_meg6_update_1d: NULL argument");
