@@ -339,6 +339,274 @@ __global__ void __launch_bounds__(32, CG_SPLIT_FACE_MINB) k_mapped_face_uni(Dims
   if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
 }
 
+// ---------------------------------------------------------------------------
+// Round 2, third step (EXPERIMENT, off by default: measured slower, see the launcher): the conserved metrics of face axis
+// AX folded into that axis' face kernel (THREE kernels instead of four).  k_mapped_cons_uni is bound by the load / store unit: per pair and plane it fetches six xi values per lane.
+// But a lane's xi values never change while its warp marches, and one face axis needs only THREE of the six per pair
+// (E0, FD0, E1 for the xi faces; D0, V1, V0 for the eta / zeta faces).  Here they are loaded ONCE per chunk into
+// registers (3 x NP doubles, NP <= FOLD_NP pairs), lane p multiplies the warp-uniform row / march products of pair p
+// into the five coefficients its face needs, and every lane does five multiply-adds per pair on broadcast reads.  The
+// pair loop is fully unrolled (compile-time register indices); the column a pair belongs to is a warp-uniform branch.
+// ---------------------------------------------------------------------------
+constexpr int FOLD_NP = 12;  // pairs whose xi values fit the registers
+constexpr int FOLD_PU = 8;   // coefficients per pair in shared memory (5 + padding to a 16-byte multiple for FP32 too)
+#ifndef CG_FOLD_MINB
+#define CG_FOLD_MINB 8
+#endif
+template <class T, int SCH, int AX>
+__global__ void __launch_bounds__(32, CG_FOLD_MINB) k_mapped_facecons_uni(Dims D, MCoordTerms CT, MPairs PR, const T* __restrict__ ftab,
+                                                                           const T* __restrict__ tab, const T* __restrict__ tabx,
+                                                                           int64_t L, int64_t Lx, MetricOut<T> O, int nt, int chunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  constexpr int MA = AX == 1 ? 1 : 2;  // marching axis
+  constexpr int RA = AX == 1 ? 2 : 1;  // row axis
+  constexpr int OUT = AX == 0 ? 31 : 32;
+  const T lam1 = lam1_of<T>(SCH), lam2 = lam2_of<T>(SCH);
+  const int64_t L1 = L + 1;
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1];
+  const int64_t row = (int64_t)blockIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * OUT;
+  const int nvalid = (int)(nw0 - i0 < OUT ? nw0 - i0 : OUT);
+  const int64_t i = i0 + lane < nw0 ? i0 + lane : nw0;
+  const int64_t m0 = (int64_t)blockIdx.z * chunk;
+  const int64_t m1 = m0 + chunk < D.nw[MA] ? m0 + chunk : D.nw[MA];
+  const int np = PR.n, cs1 = PR.cstart[1], cs2 = PR.cstart[2];
+  T* const b10 = reinterpret_cast<T*>(cg_dyn_smem);     // two Metric staging buffers
+  T* const b9 = b10 + 2 * stage_len<T, 10>;              // one ConservedMetric staging buffer
+  T* const termU = b9 + stage_len<T, 9>;                 // [nt][UNI_TERM]
+  T* const pairU = termU + (int64_t)nt * UNI_TERM;       // [np][FOLD_PU]
+  const int64_t tstride = 3 * L1 * 4;
+  const T* const fx = ftab + i * 4;
+  const int su = lane < nt ? lane : nt - 1;
+  const T* const ubase = ftab + (int64_t)CT.flat[su] * tstride;
+  T yr[4];
+  ldg_vec<T, 4>(ubase + (RA * L1 + row) * 4, yr);
+  {
+    const T c = T(CT.coef[su]);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) yr[o] *= c;
+  }
+  // ---- conserved part: per-lane xi values (registers), per-pair row values of lane p (registers) ----
+  const int64_t icx = i0 + lane < nw0 ? i0 + lane : nw0 - 1;
+  T xr[FOLD_NP][3];
+#pragma unroll
+  for (int p = 0; p < FOLD_NP; ++p) {
+    const int pp = p < np ? p : np - 1;
+    const T* xp = tabx + (int64_t)pp * OP_COUNT * Lx + icx;
+    if (AX == 0) { xr[p][0] = __ldg(xp + OP_E0 * Lx); xr[p][1] = __ldg(xp + OP_FD0 * Lx); xr[p][2] = __ldg(xp + OP_E1 * Lx); }
+    else { xr[p][0] = __ldg(xp + OP_D0 * Lx); xr[p][1] = __ldg(xp + OP_V1 * Lx); xr[p][2] = __ldg(xp + OP_V0 * Lx); }
+  }
+  const int pu = lane < np ? lane : np - 1;
+  const int64_t pstride = 3 * L * OP_COUNT;
+  const T* const prow = tab + (int64_t)pu * pstride;  // + (axis * L + index) * OP_COUNT
+  T fr[OP_COUNT];  // operator values of pair `pu` on the ROW axis (fixed), times the pair's coefficient
+  ldg_vec<T, OP_COUNT>(prow + (RA * L + row) * OP_COUNT, fr);
+  {
+    const T C = T(PR.coef[pu]);
+#pragma unroll
+    for (int o = 0; o < OP_COUNT; ++o) fr[o] *= C;
+  }
+  auto load_pz = [&](int64_t mm, T (&z)[OP_COUNT]) { ldg_vec<T, OP_COUNT>(prow + (MA * L + mm) * OP_COUNT, z); };
+  // the five coefficients of this face axis (k_mapped_cons_uni: u0..u4 | u5,u6,u9,u10,u13 | u7,u8,u11,u12,u14);
+  // y = eta row, z = zeta row of the pair
+  auto pair_uniform = [&](const T (&mr)[OP_COUNT]) {
+    if (lane < np) {
+      const T* const y = AX == 1 ? mr : fr;
+      const T* const z = AX == 1 ? fr : mr;
+      T u[FOLD_PU];
+      if (AX == 0) {
+        u[0] = y[OP_V1] * z[OP_D0] - y[OP_D0] * z[OP_V1];
+        u[1] = y[OP_V0] * z[OP_V1];
+        u[2] = -(z[OP_V0] * y[OP_V1]);
+        u[3] = -(y[OP_V0] * z[OP_D0]);
+        u[4] = z[OP_V0] * y[OP_D0];
+      } else if (AX == 1) {
+        u[0] = y[OP_E0] * z[OP_V1];
+        u[1] = -(z[OP_V0] * y[OP_E1]);
+        u[2] = -(y[OP_E0] * z[OP_D0]);
+        u[3] = z[OP_V0] * y[OP_FD0];
+        u[4] = y[OP_E1] * z[OP_D0] - y[OP_FD0] * z[OP_V1];
+      } else {
+        u[0] = -(z[OP_E0] * y[OP_V1]);
+        u[1] = y[OP_V0] * z[OP_E1];
+        u[2] = z[OP_E0] * y[OP_D0];
+        u[3] = -(y[OP_V0] * z[OP_FD0]);
+        u[4] = z[OP_FD0] * y[OP_V1] - z[OP_E1] * y[OP_D0];
+      }
+      u[5] = u[6] = u[7] = T(0);
+      sts_vec<T, FOLD_PU>(pairU + lane * FOLD_PU, u);
+    }
+  };
+  // nine conserved entries of this lane's cell from the table in shared memory; Gc[r][c], rows xi / eta / zeta
+  auto conserved = [&](T (&Gc)[3][3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Gc[a][b] = T(0);
+#pragma unroll
+    for (int p = 0; p < FOLD_NP; ++p) {
+      if (p < np) {
+        T u[FOLD_PU];
+        lds_vec<T, FOLD_PU>(pairU + p * FOLD_PU, u);
+        T e0, e1, e2;  // the three rows of the pair's column
+        if (AX == 0) {
+          e0 = xr[p][0] * u[0];
+          e1 = xr[p][1] * u[1] + xr[p][2] * u[3];
+          e2 = xr[p][1] * u[2] + xr[p][2] * u[4];
+        } else if (AX == 1) {
+          e1 = xr[p][0] * u[0] + xr[p][1] * u[2];
+          e2 = xr[p][0] * u[1] + xr[p][1] * u[3];
+          e0 = xr[p][2] * u[4];
+        } else {
+          e2 = xr[p][0] * u[0] + xr[p][1] * u[2];
+          e1 = xr[p][0] * u[1] + xr[p][1] * u[3];
+          e0 = xr[p][2] * u[4];
+        }
+        if (p < cs1) { Gc[0][0] += e0; Gc[1][0] += e1; Gc[2][0] += e2; }
+        else if (p < cs2) { Gc[0][1] += e0; Gc[1][1] += e1; Gc[2][1] += e2; }
+        else { Gc[0][2] += e0; Gc[1][2] += e1; Gc[2][2] += e2; }
+      }
+    }
+  };
+  auto load_z = [&](int64_t mm, T (&z)[4]) { ldg_vec<T, 4>(ubase + (MA * L1 + mm) * 4, z); };
+  auto term_uniform = [&](const T (&z)[4]) {
+    if (lane < nt) {
+      T u[UNI_TERM];
+      u[0] = yr[0] * z[0]; u[1] = yr[1] * z[0]; u[2] = yr[0] * z[1];
+      if (AX == 0) {
+        u[3] = T(0);
+        T v[4] = {u[0], u[1], u[2], u[3]};
+        sts_vec<T, 4>(termU + lane * UNI_TERM, v);
+      } else {
+        u[3] = yr[1] * z[1]; u[4] = yr[0] * z[2]; u[5] = yr[1] * z[2]; u[6] = yr[0] * z[3]; u[7] = T(0);
+        sts_vec<T, UNI_TERM>(termU + lane * UNI_TERM, u);
+      }
+    }
+  };
+  auto jacobian = [&](T (&F)[3][3], T (&Fp)[3][3], T (&Fpp)[3][3]) {
+    int s = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) F[q][d] = Fp[q][d] = Fpp[q][d] = T(0);
+#pragma unroll(2)
+      for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
+        T a[4];
+        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
+        if (AX == 0) {
+          T u[4];
+          lds_vec<T, 4>(termU + s * UNI_TERM, u);
+          F[q][0] += a[1] * u[0]; F[q][RA] += a[0] * u[1]; F[q][MA] += a[0] * u[2];
+          Fp[q][0] += a[2] * u[0]; Fp[q][RA] += a[1] * u[1]; Fp[q][MA] += a[1] * u[2];
+          Fpp[q][0] += a[3] * u[0]; Fpp[q][RA] += a[2] * u[1]; Fpp[q][MA] += a[2] * u[2];
+        } else {
+          T u[UNI_TERM];
+          lds_vec<T, UNI_TERM>(termU + s * UNI_TERM, u);
+          F[q][0] += a[1] * u[0]; F[q][RA] += a[0] * u[1]; F[q][MA] += a[0] * u[2];
+          Fp[q][0] += a[1] * u[2]; Fp[q][RA] += a[0] * u[3]; Fp[q][MA] += a[0] * u[4];
+          Fpp[q][0] += a[1] * u[4]; Fpp[q][RA] += a[0] * u[5]; Fpp[q][MA] += a[0] * u[6];
+        }
+      }
+    }
+  };
+  auto cell0 = [&](int64_t mm) { return AX == 1 ? i0 + nw0 * (mm + nw1 * row) : i0 + nw0 * (row + nw1 * mm); };
+  auto stage_pair = [&](T* arr_a, T* arr_b, int64_t cl0, const T (&A)[3][3], const T (&B)[3][3], T J) {
+    bulk_wait_read();
+    __syncwarp();
+    Stage<T, 10> Sa(arr_a, cl0, b10), Sb(arr_b, cl0, b10 + stage_len<T, 10>);
+    put10(Sa.slot(lane), A, J);
+    put10(Sb.slot(lane), B, J);
+    fence_async_smem();
+    __syncwarp();
+    Sa.issue(nvalid, lane);
+    Sb.issue(nvalid, lane);
+    if (lane == 0) bulk_commit();
+  };
+  // face arrays + the face's conserved metrics in one group (three TMA stores)
+  auto stage_face = [&](int64_t cl0, const T (&Ff)[3][3], const T (&Gf)[3][3], T J, const T (&Gc)[3][3]) {
+    bulk_wait_read();
+    __syncwarp();
+    Stage<T, 10> Sa(O.face_fwd[AX], cl0, b10), Sb(O.face_inv[AX], cl0, b10 + stage_len<T, 10>);
+    Stage<T, 9> Sc(O.face_cons[AX], cl0, b9);
+    put10(Sa.slot(lane), Ff, J);
+    put10(Sb.slot(lane), Gf, J);
+    put9(Sc.slot(lane), Gc);
+    fence_async_smem();
+    __syncwarp();
+    Sa.issue(nvalid, lane);
+    Sb.issue(nvalid, lane);
+    Sc.issue(nvalid, lane);
+    if (lane == 0) bulk_commit();
+  };
+
+  T pz[OP_COUNT];  // march-axis operator row of pair `pu` at the position of the NEXT conserved evaluation
+  load_pz(m0, pz);
+  if constexpr (AX == 0) {
+    T z[4];
+    load_z(m0, z);
+    for (int64_t m = m0; m < m1; ++m) {
+      __syncwarp();  // every lane has read last step's tables
+      term_uniform(z);
+      pair_uniform(pz);
+      __syncwarp();
+      load_z(m + 1 < m1 ? m + 1 : m, z);
+      load_pz(m + 1 < m1 ? m + 1 : m, pz);
+      T Gc[3][3];
+      conserved(Gc);
+      T F[3][3], Fp[3][3], Fpp[3][3], G[3][3], Lc[3][3], Rc[3][3], Gf[3][3], Ff[3][3];
+      jacobian(F, Fp, Fpp);
+      inv3(F, G);
+      mapped_states3_g(G, Fp, Fpp, lam1, lam2, Lc, Rc);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Gf[a][b] = T(0.5) * (Lc[a][b] + __shfl_down_sync(FULLMASK, Rc[a][b], 1));
+      const T J = rcp(inv3(Gf, Ff));
+      stage_face(cell0(m), Ff, Gf, J, Gc);
+    }
+  } else {
+    T Lm[3][3];
+    T z[4];
+    load_z(m0, z);
+    term_uniform(z);
+    __syncwarp();
+    load_z(m0 + 1, z);
+    {
+      T F[3][3], Fp[3][3], Fpp[3][3], G[3][3], Rm[3][3];
+      jacobian(F, Fp, Fpp);
+      const T J = inv3(F, G);
+      mapped_states3_g(G, Fp, Fpp, lam1, lam2, Lm, Rm);
+      if (AX == 2) stage_pair(O.cell_fwd, O.cell_inv, cell0(m0), F, G, J);
+    }
+    for (int64_t m = m0; m < m1; ++m) {
+      __syncwarp();
+      term_uniform(z);   // Jacobian tables: position m + 1
+      pair_uniform(pz);  // conserved tables: position m
+      __syncwarp();
+      load_z(m + 2 <= D.nw[MA] ? m + 2 : D.nw[MA], z);
+      load_pz(m + 1 < m1 ? m + 1 : m, pz);
+      T Gc[3][3];
+      conserved(Gc);
+      T F[3][3], Fp[3][3], Fpp[3][3], G[3][3], Ln[3][3], Rn[3][3], Gf[3][3], Ff[3][3];
+      jacobian(F, Fp, Fpp);
+      const T Jn = inv3(F, G);
+      if (AX == 2 && m + 1 < m1) stage_pair(O.cell_fwd, O.cell_inv, cell0(m + 1), F, G, Jn);
+      mapped_states3_g(G, Fp, Fpp, lam1, lam2, Ln, Rn);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          Gf[a][b] = T(0.5) * (Lm[a][b] + Rn[a][b]);
+          Lm[a][b] = Ln[a][b];
+        }
+      const T J = rcp(inv3(Gf, Ff));
+      stage_face(cell0(m), Ff, Gf, J, Gc);
+    }
+  }
+  if (lane == 0) bulk_wait_read();
+}
+
 // launches the four kernels on `st`; returns the number of launches, 0 when the configuration is not covered
 template <class T>
 inline int launch_mapped_metrics3d_split(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* tabx,
@@ -350,6 +618,29 @@ inline int launch_mapped_metrics3d_split(const Dims& D, const MTerms& TM, const 
   if (g31 > 65535u) return 0;
   const MCoordTerms CT = coord_terms(TM);
   bool ok = true;
+  // experiment switch CG_MAPPED_FOLD=1 (listed in include/curvigrid_cuda.h): the conserved metrics folded into the three
+  // face kernels.  Correct (the MappedGrid tests pass on it) but SLOWER than the four kernels: 212-254 registers leave 8
+  // warps per SM and each face kernel grows by 3.6-5.0 ms (9.3 + 9.1 + 10.7 = 29.1 ms against 9.9 + 4.9 + 4.1 + 7.1 =
+  // 26.0 ms at 512^3), more than its 3.3 ms share of k_mapped_cons_uni.  OFF by default.
+  static const bool fold_env = getenv("CG_MAPPED_FOLD") && atoi(getenv("CG_MAPPED_FOLD")) == 1;
+  if (fold_env && np <= FOLD_NP && PR.cstart[1] <= PR.cstart[2]) {
+    const int fsm = (int)((2 * stage_len<T, 10> + stage_len<T, 9> + (int64_t)nt * UNI_TERM + (int64_t)np * FOLD_PU) * sizeof(T));
+    auto fface = [&](auto kern, unsigned gx, int64_t rows, int64_t extent) {
+      const int chunk = pick_chunk((int64_t)gx * rows, extent, 148LL * CG_FOLD_MINB, 32, 1.0);
+      ok &= cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fsm) == cudaSuccess;
+      kern<<<dim3((unsigned)rows, gx, (unsigned)((extent + chunk - 1) / chunk)), 32, fsm, st>>>(D, CT, PR, ftab, tab, tabx, L, mapped_lx(L), O, nt, chunk);
+    };
+    auto fall = [&](auto sch) {
+      constexpr int S = decltype(sch)::value;
+      fface(k_mapped_facecons_uni<T, S, 0>, g31, nw1, nw2);
+      fface(k_mapped_facecons_uni<T, S, 1>, g32, nw2, nw1);
+      fface(k_mapped_facecons_uni<T, S, 2>, g32, nw1, nw2);
+    };
+    if (scheme == ENDPOINT) fall(std::integral_constant<int, ENDPOINT>{});
+    else if (scheme == GRADIENT) fall(std::integral_constant<int, GRADIENT>{});
+    else fall(std::integral_constant<int, CURVATURE>{});
+    return ok ? 3 : -1;
+  }
   {
     const int smem = (int)(CONS_KS * (3 * stage_len<T, 9> + (int64_t)np * UNI_PAIR) * sizeof(T));
     int per_sm = (int)(200 * 1024 / (smem + 1024));
