@@ -32,7 +32,7 @@ EXPORTS = [
     "cg_nccl_comm_destroy", "cg_halo_exchange_begin", "cg_halo_exchange_end", "cg_grid_step_overlapped",
     "cg_grid_gcl_max_dist", "cg_grid_update_from_host_dist", "cg_transfer_index_pairs", "cg_basis_transfer_matrices",
     "cg_nccl_sendrecv", "cg_legacy_meg6_update_1d", "cg_legacy_check_valid",
-    "cg_grid_set_mapping_source", "cg_grid_set_mapping_params", "cg_generic_compile_check",
+    "cg_grid_set_mapping_source", "cg_grid_set_mapping_params", "cg_generic_compile_check", "cg_legacy_validity",
 ]
 
 _lib = None

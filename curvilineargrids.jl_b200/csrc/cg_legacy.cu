@@ -272,24 +272,44 @@ __global__ void k_legacy_centroid(LShape S, LBox dom, const double* __restrict__
   }
 }
 
+// _check_valid_metrics (3d.jl:600-677) folded into the producers (fused path): a kernel that writes a checked array tests
+// its own values inside the check box (cell.domain; for edge arrays shrunk by one cell along the edge axis) and raises
+// vflags[0] (cell metrics) / vflags[1] (edge metrics); no separate pass over 46 arrays.  vflags == nullptr: no check.
+struct LCheck {
+  int* vflags;
+  LBox box;
+};
+__device__ __forceinline__ bool in_box(const LBox& b, int c0, int c1, int c2) {
+  return c0 >= b.lo[0] && c0 < b.hi[0] && c1 >= b.lo[1] && c1 < b.hi[1] && c2 >= b.lo[2] && c2 < b.hi[2];
+}
+
 // jacobian_3d_kernel! (forward_metrics.jl:155-167): StaticArrays det = x0 . (x1 x x2) over the columns
-__global__ void k_legacy_det(LShape S, LBox dom, const double* __restrict__ fwd, long long nc, double* __restrict__ J) {
+__global__ void k_legacy_det(LShape S, LBox dom, const double* __restrict__ fwd, long long nc, double* __restrict__ J,
+                             LCheck chk = LCheck{nullptr, {}}) {
   LEGACY_FOR_BOX(dom) {
     LEGACY_INDEX(dom, S)
     const double a0 = fwd[0 * nc + I], b0 = fwd[1 * nc + I], c0 = fwd[2 * nc + I];   // x_xi, x_eta, x_zeta
     const double a1 = fwd[3 * nc + I], b1 = fwd[4 * nc + I], c1 = fwd[5 * nc + I];   // y_*
     const double a2 = fwd[6 * nc + I], b2 = fwd[7 * nc + I], c2 = fwd[8 * nc + I];   // z_*
-    J[I] = a0 * (b1 * c2 - b2 * c1) + a1 * (b2 * c0 - b0 * c2) + a2 * (b0 * c1 - b1 * c0);
+    const double j = a0 * (b1 * c2 - b2 * c1) + a1 * (b2 * c0 - b0 * c2) + a2 * (b0 * c1 - b1 * c0);
+    J[I] = j;
+    if (chk.vflags && in_box(chk.box, c_[0], c_[1], c_[2]) && !(isfinite(j) && j > 0.0)) atomicOr(chk.vflags, 1);  // J finite and > 0
   }
 }
 
 __global__ void k_legacy_div9(LShape S, LBox dom, const double* __restrict__ hat, const double* __restrict__ J,
-                              long long nc, double* __restrict__ inv) {
+                              long long nc, double* __restrict__ inv, LCheck chk = LCheck{nullptr, {}}) {
   LEGACY_FOR_BOX(dom) {
     LEGACY_INDEX(dom, S)
     const double j = J[I];
+    bool bad = false;
 #pragma unroll
-    for (int m = 0; m < 9; ++m) inv[m * nc + I] = hat[m * nc + I] / j;
+    for (int m = 0; m < 9; ++m) {
+      const double v = hat[m * nc + I] / j;
+      inv[m * nc + I] = v;
+      bad |= !isfinite(v);
+    }
+    if (chk.vflags && bad && in_box(chk.box, c_[0], c_[1], c_[2])) atomicOr(chk.vflags, 1);
   }
 }
 
@@ -360,6 +380,7 @@ struct LJob {
   const double *a, *b, *c, *d;  // source = a | a*b | a*b - c*d
   double* out;
   int map, idx;                 // TMA path: `a` is row `idx` of the array block behind tensor map `map`
+  int chk;                      // 0: output not checked, 1: finite inside the check box -> cell flag, 2: -> edge flag
 };
 // The two array blocks a plain source field can live in ([rows][ncell]: the cell SoA and the centroid scratch), for the
 // TMA tensor maps of a launch.
@@ -381,7 +402,7 @@ enum { OP_CCD = 0, OP_CCD_POST = 1, OP_INTERP = 2 };
 template <bool AX0, int SRC, int OP, bool TMA>
 __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int axis, int whole, LJobs jobs, double scale,
                                                          const __grid_constant__ CUtensorMap tm0,
-                                                         const __grid_constant__ CUtensorMap tm1) {
+                                                         const __grid_constant__ CUtensorMap tm1, LCheck chk) {
   constexpr int T = AX0 ? 118 : 54, LN = AX0 ? 8 : 32, PS = AX0 ? 32 : 8;
   constexpr int WP = T + 10, WD = T + 5, WH = T + 2;
   constexpr int LS = AX0 ? 1 : LN;  // shared-memory stride between consecutive positions of a line (d1, h)
@@ -504,6 +525,13 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   };
   const double e50 = 50 * DBL_EPSILON;
   const int first = whole ? 1 : 0, last = whole ? n - 2 : n - 1;  // interp: positions written (k_legacy_interp)
+  // validity of a value just written at position p of this line (folded _check_valid_metrics)
+  const bool checked = chk.vflags != nullptr && J.chk != 0;
+  const int cl_ = dom.lo[la] + li, co_ = dom.lo[oa] + oi;
+  const bool line_in = checked && cl_ >= chk.box.lo[la] && cl_ < chk.box.hi[la] && co_ >= chk.box.lo[oa] && co_ < chk.box.hi[oa];
+  const int chk_lo = line_in ? chk.box.lo[axis] - dom.lo[axis] : 0, chk_hi = line_in ? chk.box.hi[axis] - dom.lo[axis] : 0;
+  bool bad = false;  // raised in a register; ONE atomic per thread after the loops (an atomic inside them pins their order)
+  auto check = [&](int p, double v) { bad |= p >= chk_lo && p < chk_hi && !(fabs(v) <= DBL_MAX); };
   auto out_at = [&](int p) {  // k_legacy_meg / k_legacy_interp at p
     const double* q = phi_l + p * LSP;
     const double* h = h_l + p * LS;
@@ -511,8 +539,9 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
     const double L0 = q[0] + h[0];
     if (OP == OP_INTERP) {
       if (p < first || p > last) return;
-      if (p == last) o[0] = L0;
-      else o[0] = (L0 + (q[LSP] - h[LS])) / 2;
+      const double v = p == last ? L0 : (L0 + (q[LSP] - h[LS])) / 2;
+      o[0] = v;
+      check(p, v);
       if (p == first) o[-s] = q[0] - h[0];
     } else {
       const double R0 = q[0] - h[0];
@@ -522,8 +551,9 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
       if (p == 0) lw = R0;
       else lw = ((q[-LSP] + h[-LS]) + R0) / 2;
       const double v = clip(hi - lw, e50);
-      if (OP == OP_CCD) o[0] = v;
-      else o[0] = clip(scale * (o[0] - v), e50);
+      const double w = OP == OP_CCD ? v : clip(scale * (o[0] - v), e50);
+      o[0] = w;
+      check(p, w);
     }
   };
   // ---- phase 2: first derivative ----
@@ -586,9 +616,9 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   // ---- phase 4: MEG cell-centre derivative (k_legacy_meg) or edge interpolation (k_legacy_interp) ----
   if (!AX0) {
     const int pb = t0 + CK * p0;
-    if (pb >= t1) return;
     const bool fast = OP == OP_INTERP ? (pb >= first + 1 && pb + CK <= min(t1, last)) : (pb >= 1 && pb + CK <= min(t1, n - 1));
-    if (fast) {
+    if (pb >= t1) {
+    } else if (fast) {
       const double *q = phi_l + pb * LSP, *h = h_l + pb * LS;
       double* o = J.out + base + (long long)pb * s;
       double Lm[CK + 2], Rm[CK + 2];  // states of the positions pb-1 .. pb+CK
@@ -603,11 +633,13 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
         const double hi = (Lm[k + 1] + Rm[k + 2]) / 2;
         if (OP == OP_INTERP) {
           o[0] = hi;
+          check(pb + k, hi);
         } else {
           const double lw = (Lm[k] + Rm[k + 1]) / 2;
           const double v = clip(hi - lw, e50);
-          if (OP == OP_CCD) o[0] = v;
-          else o[0] = clip(scale * (o[0] - v), e50);
+          const double w = OP == OP_CCD ? v : clip(scale * (o[0] - v), e50);
+          o[0] = w;
+          check(pb + k, w);
         }
       }
     } else {
@@ -621,6 +653,7 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
       out_at(p);
     }
   }
+  if (bad) atomicOr(chk.vflags + (J.chk - 1), 1);
 }
 
 // zero every cell of the arrays arr + blockIdx.z * nc that lies outside `keep` (the outputs are defined as zero outside
@@ -670,13 +703,15 @@ bool make_tile_map(CUtensorMap& tm, const double* base, int rows, const LShape& 
 
 template <int SRC, int OP>
 void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs_in, int njobs, double scale,
-                  cudaStream_t st, const LTmaCtx* tma = nullptr) {
+                  cudaStream_t st, const LTmaCtx* tma = nullptr, const LCheck chk = LCheck{nullptr, {}}) {
   const int n = md.hi[axis] - md.lo[axis];
   const dim3 blk(32, 8);
   LJobs jobs = jobs_in;
   CUtensorMap tm[2];
   memset(tm, 0, sizeof tm);
-  bool use_tma = SRC == 0 && tma != nullptr;
+  // xi derivatives keep the per-element loads: their 8-row x 130-value box measured slower than the loads it replaces
+  // (256^3 interpolation launch 3.14 -> 3.36 ms), the 34 x 64 bricks of the eta / zeta derivatives faster (2.82 -> 2.40 ms)
+  bool use_tma = SRC == 0 && tma != nullptr && axis != 0;
   bool need[2] = {false, false};
   for (int m = 0; m < njobs && use_tma; ++m) {  // every source field must be a row of one of the two array blocks
     bool found = false;
@@ -695,14 +730,14 @@ void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJ
   if (axis == 0) {
     const long long nt = (n + 117) / 118, ng = (md.hi[1] - md.lo[1] + 7) / 8, no = md.hi[2] - md.lo[2];
     const dim3 grid((unsigned)(nt * ng * no), njobs);
-    if (use_tma) k_legacy_fused<true, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
-    else k_legacy_fused<true, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
+    if (use_tma) k_legacy_fused<true, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
+    else k_legacy_fused<true, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
   } else {
     const int oa = axis == 1 ? 2 : 1;
     const long long nt = (n + 53) / 54, ng = (md.hi[0] - md.lo[0] + 31) / 32, no = md.hi[oa] - md.lo[oa];
     const dim3 grid((unsigned)(nt * ng * no), njobs);
-    if (use_tma) k_legacy_fused<false, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
-    else k_legacy_fused<false, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1]);
+    if (use_tma) k_legacy_fused<false, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
+    else k_legacy_fused<false, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
   }
 }
 bool legacy_fused() {
@@ -725,15 +760,18 @@ void zero_outside(const LShape& S, const LBox& full, const LBox& keep, double* a
 }
 // the 19 (3-D) / 9 (2-D) / 3 (1-D) edge interpolations of one axis in one launch
 void interp_axis_fused(const LShape& S, const LBox& full, const LBox& md, int axis, int whole, const double* const* phi,
-                       int nphi, double* E, long long nc, cudaStream_t st, uint64_t& nl, const LTmaCtx* tma = nullptr) {
+                       int nphi, double* E, long long nc, cudaStream_t st, uint64_t& nl, const LTmaCtx* tma = nullptr,
+                       LCheck chk = LCheck{nullptr, {}}, int first_checked = 1 << 30) {
   // written: md along the other axes; along `axis` positions [first-1, last] of md
   LBox keep = md;
   if (whole) keep.hi[axis] = md.hi[axis] - 1;
   else keep.lo[axis] = md.lo[axis] - 1;
   zero_outside(S, full, keep, E, nphi, nc, st, nl);
   LJobs jobs{};
-  for (int m = 0; m < nphi; ++m) jobs.j[m] = {phi[m], nullptr, nullptr, nullptr, E + (long long)m * nc, 0, 0};
-  launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st, tma);
+  for (int m = 0; m < nphi; ++m) jobs.j[m] = {phi[m], nullptr, nullptr, nullptr, E + (long long)m * nc, 0, 0, m >= first_checked ? 2 : 0};
+  chk.box.lo[axis] += 1;  // expand(domain, axis, -1)
+  chk.box.hi[axis] -= 1;
+  launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st, tma, chk);
   ++nl;
 }
 
@@ -750,7 +788,44 @@ thread_local char g_legacy_err[256];
 
 }  // namespace
 
+// one persistent pair of flag words per device and host thread for cg_legacy_check_valid, another for the validity
+// the fused update accumulates (a stream-ordered allocation per call made the memory pool trim and re-grow at every
+// synchronisation: sporadic stalls of hundreds of ms)
+namespace {
+int* legacy_flag_words(int device, int which) {
+  thread_local int* cache[2][64] = {};
+  if (device < 0 || device >= 64) return nullptr;
+  if (!cache[which][device] && cudaMalloc((void**)&cache[which][device], 2 * sizeof(int)) != cudaSuccess) return nullptr;
+  return cache[which][device];
+}
+thread_local bool g_validity_ready[64] = {};
+}  // namespace
+
 extern "C" const char* cg_legacy_last_error(void) { return g_legacy_err; }
+
+// see include/curvigrid_cuda.h
+extern "C" int cg_legacy_validity(int device, int* cell_ok, int* edge_ok, void* stream) {
+  g_legacy_err[0] = 0;
+  if (!cell_ok || !edge_ok || device < 0 || device >= 64) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_validity: bad argument");
+    return CG_ERR_ARG;
+  }
+  if (!g_validity_ready[device]) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_validity: no fused 3-D update has run on this thread and device");
+    return CG_ERR_STATE;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return CG_ERR_CUDA;
+  int h[2] = {1, 1};
+  cudaMemcpyAsync(h, legacy_flag_words(device, 1), sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  const cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream);
+  if (ce != cudaSuccess) {
+    snprintf(g_legacy_err, sizeof g_legacy_err, "cg_legacy_validity: %s", cudaGetErrorString(ce));
+    return CG_ERR_CUDA;
+  }
+  *cell_ok = !h[0];
+  *edge_ok = !h[1];
+  return CG_OK;
+}
 
 // see include/curvigrid_cuda.h
 extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const double* y, const double* z,
@@ -808,6 +883,11 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
   const int bl = blocks_for(box_count(md)), bw = blocks_for(nc);
   if (legacy_fused()) {
     const LTmaCtx tma = {{cell, scratch}, {28, 3}, nc};  // source fields are rows of the cell SoA or the centroid scratch
+    // folded _check_valid_metrics (3d.jl:600-677): J finite and > 0, forward and inverse metrics finite on cell.domain,
+    // hatted edge metrics finite on expand(domain, axis, -1); read back with cg_legacy_validity
+    LCheck chk{legacy_flag_words(device, 1), dom};
+    if (chk.vflags) cudaMemsetAsync(chk.vflags, 0, 2 * sizeof(int), st);
+    g_validity_ready[device < 64 && device >= 0 ? device : 0] = chk.vflags != nullptr;
     // 15 launches: every derivative is one fused launch (first + second derivative + MEG reconstruction through shared
     // memory), the fields that share an axis share the launch; only the shell outside the metric domain is cleared
     zero_outside(S, full, md, cell, 28, nc, st, nl);
@@ -818,11 +898,11 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
     if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)3 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     for (int ax = 0; ax < 3; ++ax) {  // forward metrics: d x_q / d xi_ax, q = 0..2
       LJobs jobs{};
-      for (int q = 0; q < 3; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 3 + ax) * nc, 0, 0};
-      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st, &tma);
+      for (int q = 0; q < 3; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 3 + ax) * nc, 0, 0, 1};
+      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st, &tma, chk);
       ++nl;
     }
-    k_legacy_det<<<bl, 256, 0, st>>>(S, md, fwd, nc, J);
+    k_legacy_det<<<bl, 256, 0, st>>>(S, md, fwd, nc, J, chk);
     ++nl;
     for (int r = 0; r < 3; ++r) {  // conservative metrics, row r: the three columns share both launches
       const int s = (r + 1) % 3, u = (r + 2) % 3;
@@ -832,8 +912,8 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
         double* h = hat + (long long)(r * 3 + c) * nc;
         const double *a_s = fwd + (long long)(q1 * 3 + s) * nc, *a_u = fwd + (long long)(q1 * 3 + u) * nc;
         const double *b_s = fwd + (long long)(q2 * 3 + s) * nc, *b_u = fwd + (long long)(q2 * 3 + u) * nc;
-        j1.j[c] = {a_s, C[q2], symmetric ? b_s : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0};
-        j2.j[c] = {a_u, C[q2], symmetric ? b_u : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0};
+        j1.j[c] = {a_s, C[q2], symmetric ? b_s : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0, 0};
+        j2.j[c] = {a_u, C[q2], symmetric ? b_u : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0, 0};
       }
       if (symmetric) {
         launch_fused<2, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
@@ -844,14 +924,15 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
       }
       nl += 2;
     }
-    k_legacy_div9<<<bl, 256, 0, st>>>(S, md, hat, J, nc, inv);
+    k_legacy_div9<<<bl, 256, 0, st>>>(S, md, hat, J, nc, inv, chk);
     ++nl;
     for (int ax = 0; ax < 3; ++ax) {
       const double* phi[19];
       for (int m = 0; m < 19; ++m) phi[m] = m == 0 ? J : cell + (long long)(9 + m) * nc;  // J, inv 0..8, hat 0..8
-      interp_axis_fused(S, full, md, ax, whole, phi, 19, edge + (long long)ax * 19 * nc, nc, st, nl, &tma);
+      interp_axis_fused(S, full, md, ax, whole, phi, 19, edge + (long long)ax * 19 * nc, nc, st, nl, &tma, chk, 10);
     }
   } else {
+  if (device >= 0 && device < 64) g_validity_ready[device] = false;  // the pass-by-pass path does not accumulate validity
   cudaMemsetAsync(cell, 0, (size_t)28 * nc * sizeof(double), st);
   cudaMemsetAsync(edge, 0, (size_t)57 * nc * sizeof(double), st);
   cudaMemsetAsync(scratch, 0, (size_t)7 * nc * sizeof(double), st);
@@ -972,7 +1053,7 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
     if (centroid) cudaMemcpyAsync(centroid, scratch, (size_t)2 * nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     for (int ax = 0; ax < 2; ++ax) {  // forward_metrics.jl:36-60
       LJobs jobs{};
-      for (int q = 0; q < 2; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 2 + ax) * nc, 0, 0};
+      for (int q = 0; q < 2; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 2 + ax) * nc, 0, 0, 0};
       launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 2, 1.0, st, &tma);
       ++nl;
     }
@@ -1118,7 +1199,7 @@ extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64
     ++nl;
     if (centroid) cudaMemcpyAsync(centroid, cx, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     LJobs jobs{};
-    jobs.j[0] = {cx, nullptr, nullptr, nullptr, xxi, 0, 0};  // forward_metrics.jl:11-27
+    jobs.j[0] = {cx, nullptr, nullptr, nullptr, xxi, 0, 0, 0};  // forward_metrics.jl:11-27
     launch_fused<0, OP_CCD>(S, md, 0, whole, jobs, 1, 1.0, st, &tma);
     k_legacy_inv1d<<<bl, 256, 0, st>>>(S, md, xxi, J, inv, hat);
     nl += 2;
@@ -1186,12 +1267,9 @@ extern "C" int cg_legacy_check_valid(int device, int dim, const int64_t* nfull, 
   for (int r = 0; r < n_cell_rows; ++r) R.cell[r] = cell_rows[r];
   for (int r = 0; r < n_edge_rows; ++r) R.edge[r] = edge_rows[r];
   cudaStream_t st = (cudaStream_t)stream;
-  // one persistent 8-byte flag word pair per device and host thread (a stream-ordered allocation per call made the
-  // memory pool trim and re-grow at every synchronisation: sporadic stalls of hundreds of ms)
-  thread_local int* flag_cache[64] = {};
   if (device < 0 || device >= 64) return CG_ERR_ARG;
-  if (!flag_cache[device] && cudaMalloc((void**)&flag_cache[device], 2 * sizeof(int)) != cudaSuccess) return CG_ERR_OOM;
-  int* flags = flag_cache[device];
+  int* flags = legacy_flag_words(device, 0);
+  if (!flags) return CG_ERR_OOM;
   cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
   k_legacy_check_valid<<<blocks_for(box_count(dom)), 256, 0, st>>>(S, dom, R, cell, edge, nc, flags);
   int h[2] = {0, 0};

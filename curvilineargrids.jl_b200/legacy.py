@@ -11,6 +11,7 @@ pipeline is cg_legacy_meg6_update_3d in libcurvigrid_cuda.so (csrc/cg_legacy.cu)
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -135,6 +136,17 @@ def update(mesh, force=False, include_halo_region=False):
     mesh.launches = int(nl.value)
     # 3d.jl:600-677: J finite and > 0, the 9 forward and 9 inverse metrics finite on cell.domain (rows 0..18 of the
     # cell SoA); the 9 hatted edge metrics of each axis finite on expand(domain, axis, -1) (rows 10..18)
+    if os.environ.get("CG_LEGACY_FUSED", "1") != "0":
+        # the fused launches tested their own values while writing them (cg_legacy_validity): two flag words to read
+        c_ok, e_ok = ctypes.c_int(), ctypes.c_int()
+        rc = L.lib().cg_legacy_validity(mesh.device, ctypes.byref(c_ok), ctypes.byref(e_ok), st)
+        if rc != L.CG_OK:
+            raise L.CurvigridError(rc, L.lib().cg_legacy_last_error().decode())
+        if not e_ok.value:
+            raise RuntimeError("Invalid edge metrics found")
+        if not c_ok.value:
+            raise RuntimeError("Invalid centroid metrics found")
+        return None
     _check_valid_metrics(mesh, 3, list(range(19)), 0, list(range(10, 19)), 19)
     return None
 

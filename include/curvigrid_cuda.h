@@ -388,6 +388,13 @@ int cg_legacy_meg6_update_1d(int device, const double* x, const int64_t* nnode, 
 int cg_legacy_check_valid(int device, int dim, const int64_t* nfull, int nhalo, const double* cell, const int* cell_rows,
                           int n_cell_rows, int positive_row, const double* edge, int edge_rows_per_axis,
                           const int* edge_rows, int n_edge_rows, int* cell_ok, int* edge_ok, void* stream);
+/*
+ * Validity of the LAST fused cg_legacy_meg6_update_3d of this host thread on `device`: the producers test their own
+ * values while they write them (J finite and > 0, forward and inverse metrics finite on cell.domain; hatted edge metrics
+ * finite on expand(domain, axis, -1): 3d.jl:600-677), so no pass over the arrays is needed.  Synchronises `stream`;
+ * CG_ERR_STATE when the last update ran pass-by-pass (CG_LEGACY_FUSED=0) — use cg_legacy_check_valid then.
+ */
+int cg_legacy_validity(int device, int* cell_ok, int* edge_ok, void* stream);
 const char* cg_legacy_last_error(void);
 
 #ifdef __cplusplus
