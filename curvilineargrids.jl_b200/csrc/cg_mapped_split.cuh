@@ -607,6 +607,126 @@ __global__ void __launch_bounds__(32, CG_FOLD_MINB) k_mapped_facecons_uni(Dims D
   if (lane == 0) bulk_wait_read();
 }
 
+// ---------------------------------------------------------------------------
+// Conserved metrics of ONE face axis (second session of round 2): k_mapped_cons_uni split by face axis.  A face axis needs
+// only three of a pair's six xi values (E0, FD0, E1 for the xi faces; D0, V1, V0 for the eta / zeta faces) and five of the
+// fifteen warp-uniform coefficients, and a lane's xi values never change while its warp marches along k: they are loaded
+// ONCE per chunk into registers (3 x FOLD_NP doubles), so the loop has no table loads at all — per pair three broadcast
+// LDS.128 and five multiply-adds.  ~100 registers, 16 one-warp blocks per SM; LSU wavefronts per cell and plane over the
+// three launches 162 against 222 of k_mapped_cons_uni.  (Folding the same loop into the face kernels lost, see
+// k_mapped_facecons_uni: there the 36 doubles came on top of the Jacobian states.)
+// ---------------------------------------------------------------------------
+#ifndef CG_CONSF_MINB
+#define CG_CONSF_MINB 16
+#endif
+template <class T, int AX>
+__global__ void __launch_bounds__(32, CG_CONSF_MINB) k_mapped_cons_face(Dims D, MPairs PR, const T* __restrict__ tab,
+                                                                         const T* __restrict__ tabx, int64_t L, int64_t Lx,
+                                                                         MetricOut<T> O, int kchunk) {
+  extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
+  const int lane = threadIdx.x;
+  const int64_t nw0 = D.nw[0], nw1 = D.nw[1], nw2 = D.nw[2];
+  const int64_t j = (int64_t)blockIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * 32;
+  const int nvalid = (int)(nw0 - i0 < 32 ? nw0 - i0 : 32);
+  const int64_t ic = i0 + lane < nw0 ? i0 + lane : nw0 - 1;  // lanes past the row end repeat the last cell (never sent)
+  const int64_t k0 = (int64_t)blockIdx.z * kchunk;
+  const int64_t k1 = k0 + kchunk < nw2 ? k0 + kchunk : nw2;
+  constexpr int PU = sizeof(T) == 8 ? 6 : 8;  // coefficients per pair in shared memory (5 + padding to 16-byte pieces)
+  const int np = PR.n, cs1 = PR.cstart[1], cs2 = PR.cstart[2];
+  T* const b9 = reinterpret_cast<T*>(cg_dyn_smem);  // TWO ConservedMetric staging buffers (a step never waits for the
+  T* const pairU = b9 + 2 * stage_len<T, 9>;         // TMA read of the step before) | [np][PU]
+  T xr[FOLD_NP][3];
+#pragma unroll
+  for (int p = 0; p < FOLD_NP; ++p) {
+    const int pp = p < np ? p : np - 1;
+    const T* xp = tabx + (int64_t)pp * OP_COUNT * Lx + ic;
+    if (AX == 0) { xr[p][0] = __ldg(xp + OP_E0 * Lx); xr[p][1] = __ldg(xp + OP_FD0 * Lx); xr[p][2] = __ldg(xp + OP_E1 * Lx); }
+    else { xr[p][0] = __ldg(xp + OP_D0 * Lx); xr[p][1] = __ldg(xp + OP_V1 * Lx); xr[p][2] = __ldg(xp + OP_V0 * Lx); }
+  }
+  const int pu = lane < np ? lane : np - 1;
+  const T* const prow = tab + (int64_t)pu * 3 * L * OP_COUNT;
+  T y[OP_COUNT];  // eta row of pair `pu` (fixed for the block), times the pair's coefficient
+  ldg_vec<T, OP_COUNT>(prow + (L + j) * OP_COUNT, y);
+  {
+    const T C = T(PR.coef[pu]);
+#pragma unroll
+    for (int o = 0; o < OP_COUNT; ++o) y[o] *= C;
+  }
+  T z[OP_COUNT];
+  ldg_vec<T, OP_COUNT>(prow + (2 * L + k0) * OP_COUNT, z);
+  for (int64_t m = k0; m < k1; ++m) {
+    __syncwarp();  // every lane has read last step's coefficients
+    if (lane < np) {
+      T u[PU];
+      if (AX == 0) {
+        u[0] = y[OP_V1] * z[OP_D0] - y[OP_D0] * z[OP_V1];
+        u[1] = y[OP_V0] * z[OP_V1];
+        u[2] = -(z[OP_V0] * y[OP_V1]);
+        u[3] = -(y[OP_V0] * z[OP_D0]);
+        u[4] = z[OP_V0] * y[OP_D0];
+      } else if (AX == 1) {
+        u[0] = y[OP_E0] * z[OP_V1];
+        u[1] = -(z[OP_V0] * y[OP_E1]);
+        u[2] = -(y[OP_E0] * z[OP_D0]);
+        u[3] = z[OP_V0] * y[OP_FD0];
+        u[4] = y[OP_E1] * z[OP_D0] - y[OP_FD0] * z[OP_V1];
+      } else {
+        u[0] = -(z[OP_E0] * y[OP_V1]);
+        u[1] = y[OP_V0] * z[OP_E1];
+        u[2] = z[OP_E0] * y[OP_D0];
+        u[3] = -(y[OP_V0] * z[OP_FD0]);
+        u[4] = z[OP_FD0] * y[OP_V1] - z[OP_E1] * y[OP_D0];
+      }
+#pragma unroll
+      for (int o = 5; o < PU; ++o) u[o] = T(0);
+      sts_vec<T, PU>(pairU + lane * PU, u);
+    }
+    __syncwarp();
+    ldg_vec<T, OP_COUNT>(prow + (2 * L + (m + 1 < k1 ? m + 1 : m)) * OP_COUNT, z);  // next step's zeta row travels now
+    T Gc[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Gc[a][b] = T(0);
+#pragma unroll
+    for (int p = 0; p < FOLD_NP; ++p) {
+      if (p < np) {
+        T u[PU];
+        lds_vec<T, PU>(pairU + p * PU, u);
+        // the pair's column is warp-uniform; multiply-adds straight into that column's three rows (xi / eta / zeta)
+        auto acc = [&](T& g0, T& g1, T& g2) {
+          if (AX == 0) {
+            g0 += xr[p][0] * u[0];
+            g1 += xr[p][1] * u[1] + xr[p][2] * u[3];
+            g2 += xr[p][1] * u[2] + xr[p][2] * u[4];
+          } else if (AX == 1) {
+            g1 += xr[p][0] * u[0] + xr[p][1] * u[2];
+            g2 += xr[p][0] * u[1] + xr[p][1] * u[3];
+            g0 += xr[p][2] * u[4];
+          } else {
+            g2 += xr[p][0] * u[0] + xr[p][1] * u[2];
+            g1 += xr[p][0] * u[1] + xr[p][1] * u[3];
+            g0 += xr[p][2] * u[4];
+          }
+        };
+        if (p < cs1) acc(Gc[0][0], Gc[1][0], Gc[2][0]);
+        else if (p < cs2) acc(Gc[0][1], Gc[1][1], Gc[2][1]);
+        else acc(Gc[0][2], Gc[1][2], Gc[2][2]);
+      }
+    }
+    bulk_wait_read1();  // the TMA unit has finished reading the buffer of TWO steps ago (lanes > 0 own no groups)
+    __syncwarp();
+    Stage<T, 9> Sc(O.face_cons[AX], i0 + nw0 * (j + nw1 * m), b9 + (int)((m - k0) & 1) * stage_len<T, 9>);
+    put9(Sc.slot(lane), Gc);  // every lane stages (no branch); slots >= nvalid are never sent
+    fence_async_smem();
+    __syncwarp();
+    Sc.issue(nvalid, lane);
+    if (lane == 0) bulk_commit();
+  }
+  if (lane == 0) bulk_wait_read();  // shared memory must outlive the TMA reads
+}
+
 // launches the four kernels on `st`; returns the number of launches, 0 when the configuration is not covered
 template <class T>
 inline int launch_mapped_metrics3d_split(const Dims& D, const MTerms& TM, const MPairs& PR, const T* tab, const T* tabx,
@@ -641,7 +761,20 @@ inline int launch_mapped_metrics3d_split(const Dims& D, const MTerms& TM, const 
     else fall(std::integral_constant<int, CURVATURE>{});
     return ok ? 3 : -1;
   }
-  {
+  // debug switch CG_MAPPED_CONS=uni (listed in include/curvigrid_cuda.h): the single conserved kernel of all three face axes
+  static const bool cons_uni_env = getenv("CG_MAPPED_CONS") && std::string(getenv("CG_MAPPED_CONS")) == "uni";
+  if (!cons_uni_env && np <= FOLD_NP) {
+    const int smem = (int)((2 * stage_len<T, 9> + (int64_t)np * (sizeof(T) == 8 ? 6 : 8)) * sizeof(T));
+    const int kchunk = pick_chunk((int64_t)g32 * nw1, nw2, 148LL * CG_CONSF_MINB, 32, 0.5);
+    const dim3 grid((unsigned)nw1, g32, (unsigned)((nw2 + kchunk - 1) / kchunk));
+    auto cons = [&](auto kern) {
+      ok &= cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+      kern<<<grid, 32, smem, st>>>(D, PR, tab, tabx, L, mapped_lx(L), O, kchunk);
+    };
+    cons(k_mapped_cons_face<T, 0>);
+    cons(k_mapped_cons_face<T, 1>);
+    cons(k_mapped_cons_face<T, 2>);
+  } else {
     const int smem = (int)(CONS_KS * (3 * stage_len<T, 9> + (int64_t)np * UNI_PAIR) * sizeof(T));
     int per_sm = (int)(200 * 1024 / (smem + 1024));
     if (per_sm > CG_SPLIT_CONS_MINB) per_sm = CG_SPLIT_CONS_MINB;
@@ -666,7 +799,7 @@ inline int launch_mapped_metrics3d_split(const Dims& D, const MTerms& TM, const 
   if (scheme == ENDPOINT) all(std::integral_constant<int, ENDPOINT>{});
   else if (scheme == GRADIENT) all(std::integral_constant<int, GRADIENT>{});
   else all(std::integral_constant<int, CURVATURE>{});
-  return ok ? 4 : -1;
+  return ok ? (!cons_uni_env && np <= FOLD_NP ? 6 : 4) : -1;
 }
 
 }  // namespace cg
