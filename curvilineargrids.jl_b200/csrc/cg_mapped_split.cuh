@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(32, CG_SPLIT_CONS_MINB) k_mapped_cons_uni(Dims
 //   AX = 0 : [P00 P10 P01 -]                      F, dF/dxi, d2F/dxi2 = xi-factor orders (1,0,0 | 2,1,1 | 3,2,2) x these
 //   AX = M : [P00 P10 P01 P11 P02 P12 P03 -]      F | dF/dxi_M | d2F/dxi_M^2
 // ---------------------------------------------------------------------------
-template <class T, int SCH, int AX>
+// RX = true (mappings with at most FACE_NT terms): the lane's xi factor rows — four derivative orders per term, the same
+// for every step of the march — live in registers instead of being re-read from L1 in every step.
+constexpr int FACE_NT = 8;
+template <class T, int SCH, int AX, bool RX>
 __global__ void __launch_bounds__(32, CG_SPLIT_FACE_MINB) k_mapped_face_uni(Dims D, MCoordTerms CT, const T* __restrict__ ftab,
                                                                              int64_t L, MetricOut<T> O, int nt, int chunk) {
   extern __shared__ __align__(128) unsigned char cg_dyn_smem[];
@@ -239,29 +242,52 @@ __global__ void __launch_bounds__(32, CG_SPLIT_FACE_MINB) k_mapped_face_uni(Dims
       }
     }
   };
-  // F, dF/dxi_AX, d2F/dxi_AX^2 at the position the uniform table was built for; columns 0 / RA / MA
-  auto jacobian = [&](T (&F)[3][3], T (&Fp)[3][3], T (&Fpp)[3][3]) {
-    int s = 0;
+  T ar[RX ? FACE_NT : 1][4];
+  const int cn0 = CT.cnt[0], cn1 = cn0 + CT.cnt[1];
+  if (RX) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int sx = 0; sx < FACE_NT; ++sx) ldg_vec<T, 4>(fx + (int64_t)CT.flat[sx < nt ? sx : nt - 1] * tstride, ar[RX ? sx : 0]);
+  }
+  // one term's contribution to the row q of F, dF/dxi_AX, d2F/dxi_AX^2 (columns 0 / RA / MA)
+  auto term_acc = [&](const T (&a)[4], int sx, T (&F)[3], T (&Fp)[3], T (&Fpp)[3]) {
+    if (AX == 0) {
+      T u[4];
+      lds_vec<T, 4>(termU + sx * UNI_TERM, u);
+      F[0] += a[1] * u[0]; F[RA] += a[0] * u[1]; F[MA] += a[0] * u[2];
+      Fp[0] += a[2] * u[0]; Fp[RA] += a[1] * u[1]; Fp[MA] += a[1] * u[2];
+      Fpp[0] += a[3] * u[0]; Fpp[RA] += a[2] * u[1]; Fpp[MA] += a[2] * u[2];
+    } else {
+      T u[UNI_TERM];
+      lds_vec<T, UNI_TERM>(termU + sx * UNI_TERM, u);
+      F[0] += a[1] * u[0]; F[RA] += a[0] * u[1]; F[MA] += a[0] * u[2];
+      Fp[0] += a[1] * u[2]; Fp[RA] += a[0] * u[3]; Fp[MA] += a[0] * u[4];
+      Fpp[0] += a[1] * u[4]; Fpp[RA] += a[0] * u[5]; Fpp[MA] += a[0] * u[6];
+    }
+  };
+  // F, dF/dxi_AX, d2F/dxi_AX^2 at the position the uniform table was built for
+  auto jacobian = [&](T (&F)[3][3], T (&Fp)[3][3], T (&Fpp)[3][3]) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
 #pragma unroll
       for (int d = 0; d < 3; ++d) F[q][d] = Fp[q][d] = Fpp[q][d] = T(0);
+    if (RX) {
+#pragma unroll
+      for (int sx = 0; sx < FACE_NT; ++sx) {
+        if (sx < nt) {  // the coordinate a term belongs to is warp-uniform
+          if (sx < cn0) term_acc(ar[RX ? sx : 0], sx, F[0], Fp[0], Fpp[0]);
+          else if (sx < cn1) term_acc(ar[RX ? sx : 0], sx, F[1], Fp[1], Fpp[1]);
+          else term_acc(ar[RX ? sx : 0], sx, F[2], Fp[2], Fpp[2]);
+        }
+      }
+    } else {
+      int sx = 0;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
 #pragma unroll(2)
-      for (int mm = 0; mm < CT.cnt[q]; ++mm, ++s) {
-        T a[4];
-        ldg_vec<T, 4>(fx + (int64_t)CT.flat[s] * tstride, a);
-        if (AX == 0) {
-          T u[4];
-          lds_vec<T, 4>(termU + s * UNI_TERM, u);
-          F[q][0] += a[1] * u[0]; F[q][RA] += a[0] * u[1]; F[q][MA] += a[0] * u[2];
-          Fp[q][0] += a[2] * u[0]; Fp[q][RA] += a[1] * u[1]; Fp[q][MA] += a[1] * u[2];
-          Fpp[q][0] += a[3] * u[0]; Fpp[q][RA] += a[2] * u[1]; Fpp[q][MA] += a[2] * u[2];
-        } else {
-          T u[UNI_TERM];
-          lds_vec<T, UNI_TERM>(termU + s * UNI_TERM, u);
-          F[q][0] += a[1] * u[0]; F[q][RA] += a[0] * u[1]; F[q][MA] += a[0] * u[2];
-          Fp[q][0] += a[1] * u[2]; Fp[q][RA] += a[0] * u[3]; Fp[q][MA] += a[0] * u[4];
-          Fpp[q][0] += a[1] * u[4]; Fpp[q][RA] += a[0] * u[5]; Fpp[q][MA] += a[0] * u[6];
+        for (int mm = 0; mm < CT.cnt[q]; ++mm, ++sx) {
+          T a[4];
+          ldg_vec<T, 4>(fx + (int64_t)CT.flat[sx] * tstride, a);
+          term_acc(a, sx, F[q], Fp[q], Fpp[q]);
         }
       }
     }
@@ -790,11 +816,19 @@ inline int launch_mapped_metrics3d_split(const Dims& D, const MTerms& TM, const 
     ok &= cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem) == cudaSuccess;
     kern<<<dim3((unsigned)rows, gx, (unsigned)((extent + chunk - 1) / chunk)), 32, fsmem, st>>>(D, CT, ftab, L, O, nt, chunk);
   };
+  // debug switch CG_MAPPED_FACE_RX=0 (listed in include/curvigrid_cuda.h): xi factor rows re-read from L1 in every step
+  static const bool rx_env = !(getenv("CG_MAPPED_FACE_RX") && atoi(getenv("CG_MAPPED_FACE_RX")) == 0);
   auto all = [&](auto sch) {
     constexpr int S = decltype(sch)::value;
-    face(k_mapped_face_uni<T, S, 0>, g31, nw1, nw2);
-    face(k_mapped_face_uni<T, S, 1>, g32, nw2, nw1);
-    face(k_mapped_face_uni<T, S, 2>, g32, nw1, nw2);
+    if (rx_env && nt <= FACE_NT) {
+      face(k_mapped_face_uni<T, S, 0, true>, g31, nw1, nw2);
+      face(k_mapped_face_uni<T, S, 1, true>, g32, nw2, nw1);
+      face(k_mapped_face_uni<T, S, 2, true>, g32, nw1, nw2);
+    } else {
+      face(k_mapped_face_uni<T, S, 0, false>, g31, nw1, nw2);
+      face(k_mapped_face_uni<T, S, 1, false>, g32, nw2, nw1);
+      face(k_mapped_face_uni<T, S, 2, false>, g32, nw1, nw2);
+    }
   };
   if (scheme == ENDPOINT) all(std::integral_constant<int, ENDPOINT>{});
   else if (scheme == GRADIENT) all(std::integral_constant<int, GRADIENT>{});

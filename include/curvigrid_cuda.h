@@ -30,6 +30,8 @@
  *                        (k_mapped_cons_uni + k_mapped_face_uni<0,1,2>)
  *   CG_MAPPED_CONS=uni   MappedGrid 3-D FULL: one conserved kernel for all three face axes (k_mapped_cons_uni) instead of
  *                        one light kernel per face axis (k_mapped_cons_face)
+ *   CG_MAPPED_FACE_RX=0  MappedGrid 3-D face kernels: re-read the xi factor rows from L1 in every step instead of holding
+ *                        them in registers
  *   CG_MAPPED_FOLD=1     MappedGrid 3-D FULL: conserved metrics folded into the three face kernels (an experiment: slower
  *                        than the four light kernels)
  *   CG_FUSE_XZ=1         3-D FULL cell+face: the fused xi+zeta kernel (k_face_xz, an experiment: slower than the
