@@ -30,6 +30,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include "../../include/curvigrid_cuda.h"
+#include "cg_legacy_ranges.h"
 
 namespace {
 
@@ -426,17 +427,9 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   bb /= (unsigned)ntile;
   const int gr = (int)(bb % (unsigned)ngr), oi = (int)(bb / (unsigned)ngr);
   const int t0 = tile * T, t1 = min(t0 + T, n);
-  // ranges (absolute positions along the axis, [lo, hi))
-  const int hl = OP == OP_INTERP ? t0 : max(0, t0 - 1), hh = min(n, t1 + 1);
-  int dl = max(0, hl - 1), dh = min(n, hh + 1);
-  if (hl < 3) dh = max(dh, 6);
-  if (hh > n - 3) {  // a one-sided second derivative reads ALL of d1[n-6 .. n-1]
-    dl = min(dl, n - 6);
-    dh = n;
-  }
-  int pl = max(0, dl - 3), ph = min(n, dh + 3);
-  if (dl < 3) ph = max(ph, 6);
-  if (dh > n - 3) pl = min(pl, n - 6);
+  // ranges (absolute positions along the axis, [lo, hi)): cg_legacy_ranges.h
+  const LegacyRanges rg = legacy_tile_ranges(n, t0, t1, OP == OP_INTERP);
+  const int hl = rg.hl, hh = rg.hh, dl = rg.dl, dh = rg.dh, pl = rg.pl, ph = rg.ph;
   const int line = AX0 ? threadIdx.y : threadIdx.x, p0 = AX0 ? threadIdx.x : threadIdx.y;
   const int li = gr * LN + line;
   const bool lok = li < nl;
