@@ -68,3 +68,17 @@ def test_generic_mapping_source_compiles_without_a_gpu():
     assert lib.cg_generic_compile_check(bad, log, 4096) == L.CG_ERR_ARG
     assert b"undefined_fn" in log.value and b"cg_map.cu" in log.value
     assert lib.cg_grid_set_mapping_source(None, good) == L.CG_ERR_ARG
+
+
+def test_new_entry_points_report_errors_without_a_gpu():
+    L = cg._lib
+    lib = L.lib()
+    assert lib.cg_grid_set_mapping_params(None, None, 0) == L.CG_ERR_ARG
+    assert lib.cg_generic_compile_check(None, None, 0) == L.CG_ERR_ARG
+    c, e = ctypes.c_int(), ctypes.c_int()
+    assert lib.cg_legacy_validity(0, None, ctypes.byref(e), None) == L.CG_ERR_ARG
+    # no fused 3-D update has run on this thread: a state error, not a stale answer
+    assert lib.cg_legacy_validity(0, ctypes.byref(c), ctypes.byref(e), None) == L.CG_ERR_STATE
+    assert b"no fused" in lib.cg_legacy_last_error()
+    # CG_WHAT_GCL is a cg_grid_update_from_host* flag only
+    assert lib.cg_grid_eval(None, L.CG_WHAT_CELL | L.CG_WHAT_GCL, None) == L.CG_ERR_ARG

@@ -10,6 +10,8 @@ python bench.py --workload 3d512 --profile compact --steps 10 --warmup 3 --no-cp
 python bench.py --workload 2d4096 --steps 20 --warmup 3 > $O/bench_${TAG}_2d4096.json 2>> $O/bench_${TAG}.err
 python bench.py --workload m3d512 --steps 5 --warmup 3 > $O/bench_${TAG}_m3d512.json 2>> $O/bench_${TAG}.err
 python bench.py --workload sph1536 --profile compact --steps 8 --warmup 3 --no-cpu-baseline > $O/bench_${TAG}_sph1536_compact.json 2>> $O/bench_${TAG}.err
+python tools/time_legacy.py 256 > $O/legacy_${TAG}_256.json 2>> $O/bench_${TAG}.err      # legacy MEG6: fused vs pass-by-pass
+python tools/time_generic.py 128 > $O/generic_${TAG}_128.json 2>> $O/bench_${TAG}.err   # NVRTC generic mapping vs tables
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_ncu_launches_3d512.csv \
   python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $O/ncu_list_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_face --launch-count 3 -f -o $O/prof_${TAG}_3d512 \
