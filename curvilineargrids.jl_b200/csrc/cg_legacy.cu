@@ -32,6 +32,10 @@
 #include "../../include/curvigrid_cuda.h"
 #include "cg_legacy_ranges.h"
 
+#ifndef CG_LEGACY_MARCH_DEFAULT
+#define CG_LEGACY_MARCH_DEFAULT 1
+#endif
+
 namespace {
 
 struct LBox {
@@ -403,7 +407,8 @@ enum { OP_CCD = 0, OP_CCD_POST = 1, OP_INTERP = 2 };
 template <bool AX0, int SRC, int OP, bool TMA>
 __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int axis, int whole, LJobs jobs, double scale,
                                                          const __grid_constant__ CUtensorMap tm0,
-                                                         const __grid_constant__ CUtensorMap tm1, LCheck chk) {
+                                                         const __grid_constant__ CUtensorMap tm1, LCheck chk, int pos_lo,
+                                                         int pos_hi) {
   constexpr int T = AX0 ? 118 : 54, LN = AX0 ? 8 : 32, PS = AX0 ? 32 : 8;
   constexpr int WP = T + 10, WD = T + 5, WH = T + 2;
   constexpr int LS = AX0 ? 1 : LN;  // shared-memory stride between consecutive positions of a line (d1, h)
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   __shared__ __align__(8) unsigned long long mbar;
   const LJob J = jobs.j[blockIdx.y];
   const int n = dom.hi[axis] - dom.lo[axis];
-  const int ntile = (n + T - 1) / T;
+  const int ntile = (pos_hi - pos_lo + T - 1) / T;  // tiles cover the positions [pos_lo, pos_hi) of the axis
   const int la = AX0 ? 1 : 0;                      // axis the lines are counted along
   const int oa = AX0 ? 2 : (axis == 1 ? 2 : 1);    // the remaining axis
   const int nl = dom.hi[la] - dom.lo[la], ngr = (nl + LN - 1) / LN;
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   const int tile = (int)(bb % (unsigned)ntile);
   bb /= (unsigned)ntile;
   const int gr = (int)(bb % (unsigned)ngr), oi = (int)(bb / (unsigned)ngr);
-  const int t0 = tile * T, t1 = min(t0 + T, n);
+  const int t0 = pos_lo + tile * T, t1 = min(t0 + T, pos_hi);
   // ranges (absolute positions along the axis, [lo, hi)): cg_legacy_ranges.h
   const LegacyRanges rg = legacy_tile_ranges(n, t0, t1, OP == OP_INTERP);
   const int hl = rg.hl, hh = rg.hh, dl = rg.dl, dh = rg.dh, pl = rg.pl, ph = rg.ph;
@@ -649,6 +654,173 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
   if (bad) atomicOr(chk.vflags + (J.chk - 1), 1);
 }
 
+// ---------------------------------------------------------------------------
+// Marching variant for eta / zeta derivatives (CG_LEGACY_MARCH): a warp owns 32 consecutive xi (coalesced) and a segment
+// of the derivative axis and SWEEPS along it with the whole stencil state in registers — seven source values, three first
+// derivatives, two half-jumps, one face value — so every source value is loaded once, every intermediate is computed once
+// (no tile halos), and there is no shared memory and no barrier at all: pushing phi(q) yields d1(q-3), h(q-4), the face
+// value (L(q-5) + R(q-4)) / 2 and the output at q-5.  Only positions whose whole dependency cone uses CENTRAL stencils
+// are marched, [5, n-5); the five cells at either end go through the tile kernel above (one-sided windows).  Same device
+// functions, same operand order: bit-identical to both other paths.
+// ---------------------------------------------------------------------------
+constexpr int MARCH_SEG = 64;
+template <int SRC, int OP>
+__global__ void __launch_bounds__(128) k_legacy_march(LShape S, LBox dom, int axis, LJobs jobs, double scale, LCheck chk) {
+  const LJob J = jobs.j[blockIdx.y];
+  const int n = dom.hi[axis] - dom.lo[axis];
+  const int oa = axis == 1 ? 2 : 1;
+  const int nl = dom.hi[0] - dom.lo[0], ngr = (nl + 31) / 32;
+  const int P0 = 5, P1 = n - 5, nseg = (P1 - P0 + MARCH_SEG - 1) / MARCH_SEG;
+  const int no = dom.hi[oa] - dom.lo[oa];
+  long long w = (long long)blockIdx.x * 4 + threadIdx.y;  // warp index -> (xi group, segment, other index)
+  if (w >= (long long)ngr * nseg * no) return;
+  const int gr = (int)(w % ngr);
+  w /= ngr;
+  const int seg = (int)(w % nseg), oi = (int)(w / nseg);
+  const int li = gr * 32 + threadIdx.x;
+  if (li >= nl) return;
+  const int s0 = P0 + seg * MARCH_SEG, s1 = min(s0 + MARCH_SEG, P1);
+  const long long s = S.st[axis];
+  const long long base = (long long)(dom.lo[0] + li) + (long long)(dom.lo[oa] + oi) * S.st[oa] + (long long)dom.lo[axis] * s;
+  const double e50 = 50 * DBL_EPSILON;
+  // folded validity check (see LCheck)
+  const bool checked = chk.vflags != nullptr && J.chk != 0;
+  const int cl_ = dom.lo[0] + li, co_ = dom.lo[oa] + oi;
+  const bool line_in = checked && cl_ >= chk.box.lo[0] && cl_ < chk.box.hi[0] && co_ >= chk.box.lo[oa] && co_ < chk.box.hi[oa];
+  const int chk_lo = line_in ? chk.box.lo[axis] - dom.lo[axis] : 0, chk_hi = line_in ? chk.box.hi[axis] - dom.lo[axis] : 0;
+  bool bad = false;
+  double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, f6 = 0;  // phi(q-6 .. q)
+  double d0 = 0, d1 = 0, d2 = 0;                                  // d1(q-5 .. q-3)
+  double hA = 0, hB = 0, hiPrev = 0;                              // h(q-5), h(q-4), face value at q-6
+  long long I = base + (long long)(s0 - 5) * s;
+  double nxt = src_val<SRC>(J.a, J.b, J.c, J.d, I);
+  for (int q = s0 - 5; q <= s1 + 4; ++q, I += s) {
+    f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5; f5 = f6; f6 = nxt;
+    if (q < s1 + 4) nxt = src_val<SRC>(J.a, J.b, J.c, J.d, I + s);  // next position travels while this one is computed
+    double prev = 0.0;
+    if (OP == OP_CCD_POST && q >= s0 + 5) prev = J.out[I - 5 * s];
+    if (q >= s0 + 1) {  // d1(q-3)
+      d0 = d1; d1 = d2;
+      d2 = central6(f0, f1, f2, f4, f5, f6);
+    }
+    if (q >= s0 + 3) {  // h(q-4): second derivative from d1(q-5), d1(q-3), phi(q-5 .. q-3)
+      const double dd = -tol_diff(d2, d0) / 2;
+      const double r = kahan3(2 * (f3 + f1), -4 * f2, dd);
+      hA = hB;
+      hB = (1.0 / 2.0) * d1 + (1.0 / 12.0) * r;
+    }
+    if (q >= s0 + 4) {  // face value between q-5 and q-4: (phiL(q-5) + phiR(q-4)) / 2
+      const double hi = ((f1 + hA) + (f2 - hB)) / 2;
+      if (q >= s0 + 5) {
+        const int pp = q - 5;
+        double v;
+        if (OP == OP_INTERP) v = hi;
+        else {
+          v = clip(hi - hiPrev, e50);
+          if (OP == OP_CCD_POST) v = clip(scale * (prev - v), e50);
+        }
+        J.out[I - 5 * s] = v;
+        bad |= pp >= chk_lo && pp < chk_hi && !(fabs(v) <= DBL_MAX);
+      }
+      hiPrev = hi;
+    }
+  }
+  if (bad) atomicOr(chk.vflags + (J.chk - 1), 1);
+}
+
+// The five cells at either end of a marched line (blockIdx.z = 0: positions 0..4, 1: n-5..n-1), one thread per line, all
+// in registers: ten source values, seven first derivatives (three one-sided, four central), six half-jumps (three
+// one-sided, three central), five outputs.  Local index i <-> absolute position a0 + i, a0 = 0 (low end) or n - 10 (high).
+template <int SRC, int OP, bool high>
+__device__ __forceinline__ void legacy_strip_body(const LShape& S, const LBox& dom, int axis, int whole, const LJobs& jobs, double scale,
+                                                  const LCheck& chk) {
+  const LJob J = jobs.j[blockIdx.y];
+  const int n = dom.hi[axis] - dom.lo[axis];
+  const int oa = axis == 1 ? 2 : 1;
+  const int nl = dom.hi[0] - dom.lo[0], ngr = (nl + 31) / 32, no = dom.hi[oa] - dom.lo[oa];
+  const long long w = (long long)blockIdx.x * 4 + threadIdx.y;
+  if (w >= (long long)ngr * no) return;
+  const int gr = (int)(w % ngr), oi = (int)(w / ngr);
+  const int li = gr * 32 + threadIdx.x;
+  if (li >= nl) return;
+  const long long s = S.st[axis];
+  const int a0 = high ? n - 10 : 0;
+  const long long base = (long long)(dom.lo[0] + li) + (long long)(dom.lo[oa] + oi) * S.st[oa] + (long long)dom.lo[axis] * s;
+  double P[10], D[10], H[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) P[i] = src_val<SRC>(J.a, J.b, J.c, J.d, base + (long long)(a0 + i) * s);
+  // first derivatives: local 0..6 (low end) / 3..9 (high end)
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const bool need = high ? i >= 3 : i <= 6;
+    const bool edge = high ? i >= 7 : i < 3;
+    if (!need) { D[i] = 0.0; continue; }
+    if (edge) {
+      double wv[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) wv[m] = P[(high ? 4 : 0) + m];
+      D[i] = mixed_edge(wv, high ? 3 + (i - 7) : i);
+    } else {
+      D[i] = central6(P[i - 3 < 0 ? 0 : i - 3], P[i - 2 < 0 ? 0 : i - 2], P[i - 1 < 0 ? 0 : i - 1], P[i + 1 > 9 ? 9 : i + 1],
+                      P[i + 2 > 9 ? 9 : i + 2], P[i + 3 > 9 ? 9 : i + 3]);
+    }
+  }
+  // half-jumps: local 0..5 (low end) / 4..9 (high end)
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const bool need = high ? i >= 4 : i <= 5;
+    const bool edge = high ? i >= 7 : i < 3;
+    if (!need) { H[i] = 0.0; continue; }
+    double r;
+    if (edge) {
+      double wv[6];
+#pragma unroll
+      for (int m = 0; m < 6; ++m) wv[m] = D[(high ? 4 : 0) + m];
+      r = mixed_edge(wv, high ? 3 + (i - 7) : i);
+    } else {
+      const int im = i - 1 < 0 ? 0 : i - 1, ip = i + 1 > 9 ? 9 : i + 1;
+      const double dd = -tol_diff(D[ip], D[im]) / 2;
+      r = kahan3(2 * (P[ip] + P[im]), -4 * P[i], dd);
+    }
+    H[i] = (1.0 / 2.0) * D[i] + (1.0 / 12.0) * r;
+  }
+  const double e50 = 50 * DBL_EPSILON;
+  const int first = whole ? 1 : 0, last = whole ? n - 2 : n - 1;
+  const bool checked = chk.vflags != nullptr && J.chk != 0;
+  const int cl_ = dom.lo[0] + li, co_ = dom.lo[oa] + oi;
+  const bool line_in = checked && cl_ >= chk.box.lo[0] && cl_ < chk.box.hi[0] && co_ >= chk.box.lo[oa] && co_ < chk.box.hi[oa];
+  const int chk_lo = line_in ? chk.box.lo[axis] - dom.lo[axis] : 0, chk_hi = line_in ? chk.box.hi[axis] - dom.lo[axis] : 0;
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int i = (high ? 5 : 0) + k, p = a0 + i;  // local index, absolute position
+    const int im = i - 1 < 0 ? 0 : i - 1, ip = i + 1 > 9 ? 9 : i + 1;
+    double* o = J.out + base + (long long)p * s;
+    const double L0 = P[i] + H[i];
+    double v;
+    if (OP == OP_INTERP) {
+      if (p < first || p > last) continue;
+      v = p == last ? L0 : (L0 + (P[ip] - H[ip])) / 2;
+      o[0] = v;
+      if (p == first) o[-s] = P[i] - H[i];
+    } else {
+      const double R0 = P[i] - H[i];
+      const double hi = p == n - 1 ? L0 : (L0 + (P[ip] - H[ip])) / 2;
+      const double lw = p == 0 ? R0 : ((P[im] + H[im]) + R0) / 2;
+      v = clip(hi - lw, e50);
+      if (OP == OP_CCD_POST) v = clip(scale * (o[0] - v), e50);
+      o[0] = v;
+    }
+    bad |= p >= chk_lo && p < chk_hi && !(fabs(v) <= DBL_MAX);
+  }
+  if (bad) atomicOr(chk.vflags + (J.chk - 1), 1);
+}
+template <int SRC, int OP>
+__global__ void __launch_bounds__(128) k_legacy_strip(LShape S, LBox dom, int axis, int whole, LJobs jobs, double scale, LCheck chk) {
+  if (blockIdx.z == 0) legacy_strip_body<SRC, OP, false>(S, dom, axis, whole, jobs, scale, chk);
+  else legacy_strip_body<SRC, OP, true>(S, dom, axis, whole, jobs, scale, chk);
+}
+
 // zero every cell of the arrays arr + blockIdx.z * nc that lies outside `keep` (the outputs are defined as zero outside
 // the metric domain; the fused path overwrites everything inside, so only the shell has to be cleared).  One warp per
 // (j, k) row: rows outside keep are cleared whole, the others only left and right of keep.
@@ -695,9 +867,9 @@ bool make_tile_map(CUtensorMap& tm, const double* base, int rows, const LShape& 
 }
 
 template <int SRC, int OP>
-void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs_in, int njobs, double scale,
-                  cudaStream_t st, const LTmaCtx* tma = nullptr, const LCheck chk = LCheck{nullptr, {}}) {
-  const int n = md.hi[axis] - md.lo[axis];
+void launch_tiles(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs_in, int njobs, double scale,
+                  cudaStream_t st, const LTmaCtx* tma, const LCheck chk, int pos_lo, int pos_hi) {
+  const int n = pos_hi - pos_lo;  // positions the tiles cover
   const dim3 blk(32, 8);
   LJobs jobs = jobs_in;
   CUtensorMap tm[2];
@@ -723,15 +895,38 @@ void launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJ
   if (axis == 0) {
     const long long nt = (n + 117) / 118, ng = (md.hi[1] - md.lo[1] + 7) / 8, no = md.hi[2] - md.lo[2];
     const dim3 grid((unsigned)(nt * ng * no), njobs);
-    if (use_tma) k_legacy_fused<true, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
-    else k_legacy_fused<true, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
+    if (use_tma) k_legacy_fused<true, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk, pos_lo, pos_hi);
+    else k_legacy_fused<true, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk, pos_lo, pos_hi);
   } else {
     const int oa = axis == 1 ? 2 : 1;
     const long long nt = (n + 53) / 54, ng = (md.hi[0] - md.lo[0] + 31) / 32, no = md.hi[oa] - md.lo[oa];
     const dim3 grid((unsigned)(nt * ng * no), njobs);
-    if (use_tma) k_legacy_fused<false, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
-    else k_legacy_fused<false, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk);
+    if (use_tma) k_legacy_fused<false, SRC, OP, SRC == 0><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk, pos_lo, pos_hi);
+    else k_legacy_fused<false, SRC, OP, false><<<grid, blk, 0, st>>>(S, md, axis, whole, jobs, scale, tm[0], tm[1], chk, pos_lo, pos_hi);
   }
+}
+bool legacy_march() {
+  const char* e = getenv("CG_LEGACY_MARCH");  // debug switch (listed in include/curvigrid_cuda.h)
+  return e ? atoi(e) != 0 : CG_LEGACY_MARCH_DEFAULT;
+}
+// one derivative pass over the metric domain: tiles everywhere, or (eta / zeta axes, long enough) the marching kernel on
+// the central positions [5, n-5) + tiles on the five cells at either end.  Returns the number of launches.
+template <int SRC, int OP>
+int launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJobs& jobs, int njobs, double scale,
+                 cudaStream_t st, const LTmaCtx* tma = nullptr, const LCheck chk = LCheck{nullptr, {}}) {
+  const int n = md.hi[axis] - md.lo[axis];
+  if (axis != 0 && n >= 42 && legacy_march()) {
+    const int oa = axis == 1 ? 2 : 1;
+    const long long ngr = (md.hi[0] - md.lo[0] + 31) / 32, nseg = (n - 10 + MARCH_SEG - 1) / MARCH_SEG, no = md.hi[oa] - md.lo[oa];
+    // the five cells at either end first (a POST pass reads what the pass before wrote: same stream, any order is fine)
+    k_legacy_strip<SRC, OP><<<dim3((unsigned)((ngr * no + 3) / 4), njobs, 2), dim3(32, 4), 0, st>>>(S, md, axis, whole, jobs, scale, chk);
+    const long long warps = ngr * nseg * no;
+    k_legacy_march<SRC, OP><<<dim3((unsigned)((warps + 3) / 4), njobs), dim3(32, 4), 0, st>>>(S, md, axis, jobs, scale, chk);
+    (void)tma;
+    return 2;
+  }
+  launch_tiles<SRC, OP>(S, md, axis, whole, jobs, njobs, scale, st, tma, chk, 0, n);
+  return 1;
 }
 bool legacy_fused() {
   const char* e = getenv("CG_LEGACY_FUSED");  // debug switch (listed in include/curvigrid_cuda.h)
@@ -764,8 +959,7 @@ void interp_axis_fused(const LShape& S, const LBox& full, const LBox& md, int ax
   for (int m = 0; m < nphi; ++m) jobs.j[m] = {phi[m], nullptr, nullptr, nullptr, E + (long long)m * nc, 0, 0, m >= first_checked ? 2 : 0};
   chk.box.lo[axis] += 1;  // expand(domain, axis, -1)
   chk.box.hi[axis] -= 1;
-  launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st, tma, chk);
-  ++nl;
+  nl += launch_fused<0, OP_INTERP>(S, md, axis, whole, jobs, nphi, 1.0, st, tma, chk);
 }
 
 int blocks_for(long long n) {
@@ -892,8 +1086,7 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
     for (int ax = 0; ax < 3; ++ax) {  // forward metrics: d x_q / d xi_ax, q = 0..2
       LJobs jobs{};
       for (int q = 0; q < 3; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 3 + ax) * nc, 0, 0, 1};
-      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st, &tma, chk);
-      ++nl;
+      nl += launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 3, 1.0, st, &tma, chk);
     }
     k_legacy_det<<<bl, 256, 0, st>>>(S, md, fwd, nc, J, chk);
     ++nl;
@@ -909,13 +1102,12 @@ extern "C" int cg_legacy_meg6_update_3d(int device, const double* x, const doubl
         j2.j[c] = {a_u, C[q2], symmetric ? b_u : nullptr, symmetric ? C[q1] : nullptr, h, 0, 0, 0};
       }
       if (symmetric) {
-        launch_fused<2, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
-        launch_fused<2, OP_CCD_POST>(S, md, s, whole, j2, 3, 1.0 / 2.0, st);
+        nl += launch_fused<2, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
+        nl += launch_fused<2, OP_CCD_POST>(S, md, s, whole, j2, 3, 1.0 / 2.0, st);
       } else {
-        launch_fused<1, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
-        launch_fused<1, OP_CCD_POST>(S, md, s, whole, j2, 3, 1.0, st);
+        nl += launch_fused<1, OP_CCD>(S, md, u, whole, j1, 3, 1.0, st);
+        nl += launch_fused<1, OP_CCD_POST>(S, md, s, whole, j2, 3, 1.0, st);
       }
-      nl += 2;
     }
     k_legacy_div9<<<bl, 256, 0, st>>>(S, md, hat, J, nc, inv, chk);
     ++nl;
@@ -1047,8 +1239,7 @@ extern "C" int cg_legacy_meg6_update_2d(int device, const double* x, const doubl
     for (int ax = 0; ax < 2; ++ax) {  // forward_metrics.jl:36-60
       LJobs jobs{};
       for (int q = 0; q < 2; ++q) jobs.j[q] = {C[q], nullptr, nullptr, nullptr, fwd + (long long)(q * 2 + ax) * nc, 0, 0, 0};
-      launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 2, 1.0, st, &tma);
-      ++nl;
+      nl += launch_fused<0, OP_CCD>(S, md, ax, whole, jobs, 2, 1.0, st, &tma);
     }
     k_legacy_inv2d<<<bl, 256, 0, st>>>(S, md, fwd, nc, J, inv, hat);
     ++nl;
@@ -1193,9 +1384,9 @@ extern "C" int cg_legacy_meg6_update_1d(int device, const double* x, const int64
     if (centroid) cudaMemcpyAsync(centroid, cx, (size_t)nc * sizeof(double), cudaMemcpyDeviceToDevice, st);
     LJobs jobs{};
     jobs.j[0] = {cx, nullptr, nullptr, nullptr, xxi, 0, 0, 0};  // forward_metrics.jl:11-27
-    launch_fused<0, OP_CCD>(S, md, 0, whole, jobs, 1, 1.0, st, &tma);
+    nl += launch_fused<0, OP_CCD>(S, md, 0, whole, jobs, 1, 1.0, st, &tma);
     k_legacy_inv1d<<<bl, 256, 0, st>>>(S, md, xxi, J, inv, hat);
-    nl += 2;
+    ++nl;
     const double* phi[3] = {J, inv, hat};  // MetricDiscretizationSchemes.jl:58-89
     interp_axis_fused(S, full, md, 0, whole, phi, 3, edge, nc, st, nl, &tma);
   } else {

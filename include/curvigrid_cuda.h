@@ -38,6 +38,8 @@
  *                        two kernels it replaces) instead of k_face_xi + k_face_zeta
  *   CG_LEGACY_FUSED=0    legacy MEG6 pipeline: the pass-by-pass launches (273 per 3-D update) instead of the fused
  *                        ones (20); both produce the same bits (tests/test_gpu_legacy.py)
+ *   CG_LEGACY_MARCH=0    legacy MEG6 pipeline: tile kernels for the eta / zeta derivatives too, instead of the marching
+ *                        (register-only) kernel + the end-strip kernel
  *   CG_LEGACY_TMA=0      legacy MEG6 pipeline: per-element loads of the source bricks instead of tensor-map TMA loads
  *   CG_NCCL_LIB=path     libnccl to dlopen when the process has not loaded one (default libnccl.so.2)
  *   CG_NVRTC_LIB=path    libnvrtc to dlopen for cg_grid_set_mapping_source (default libnvrtc.so.12, then the CUDA toolkit's)

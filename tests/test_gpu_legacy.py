@@ -242,7 +242,7 @@ def test_legacy_fused_equals_pass_by_pass_bitwise(cg, monkeypatch, shape, symmet
     nodes = mild_nodes(shape, seed=7)
     scheme = "meg6_symmetric" if symmetric else "meg6"
     mesh = cg.legacy.CurvilinearGrid3D(*nodes, scheme, halo_coords_included=halo_included)
-    assert mesh.launches <= 20
+    assert mesh.launches <= 40   # 20 with the tile kernels, 36 with CG_LEGACY_MARCH=1 (two end strips per marched pass)
     fused = [t.clone() for t in (mesh._cell, mesh._edge, mesh._cent)]
     for t in (mesh._cell, mesh._edge, mesh._cent, mesh._scratch):
         t.fill_(float("nan"))   # nothing may survive from the caller's buffers
