@@ -663,7 +663,10 @@ __global__ void __launch_bounds__(256, 4) k_legacy_fused(LShape S, LBox dom, int
 // are marched, [5, n-5); the five cells at either end go through the tile kernel above (one-sided windows).  Same device
 // functions, same operand order: bit-identical to both other paths.
 // ---------------------------------------------------------------------------
-constexpr int MARCH_SEG = 64;
+#ifndef CG_MARCH_UNROLL
+#define CG_MARCH_UNROLL 1
+#endif
+constexpr int MARCH_SEG = 64, MARCH_UNROLL = CG_MARCH_UNROLL;
 template <int SRC, int OP>
 __global__ void __launch_bounds__(128) k_legacy_march(LShape S, LBox dom, int axis, LJobs jobs, double scale, LCheck chk) {
   const LJob J = jobs.j[blockIdx.y];
@@ -694,6 +697,7 @@ __global__ void __launch_bounds__(128) k_legacy_march(LShape S, LBox dom, int ax
   double hA = 0, hB = 0, hiPrev = 0;                              // h(q-5), h(q-4), face value at q-6
   long long I = base + (long long)(s0 - 5) * s;
   double nxt = src_val<SRC>(J.a, J.b, J.c, J.d, I);
+#pragma unroll(MARCH_UNROLL)
   for (int q = s0 - 5; q <= s1 + 4; ++q, I += s) {
     f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5; f5 = f6; f6 = nxt;
     if (q < s1 + 4) nxt = src_val<SRC>(J.a, J.b, J.c, J.d, I + s);  // next position travels while this one is computed
@@ -728,6 +732,104 @@ __global__ void __launch_bounds__(128) k_legacy_march(LShape S, LBox dom, int ax
   if (bad) atomicOr(chk.vflags + (J.chk - 1), 1);
 }
 
+// Marching along XI (the contiguous axis): a lane cannot own a xi line and stay coalesced, so each warp moves its tile —
+// 32 consecutive eta rows x one xi segment + 5 cells either side — through a warp-private shared-memory buffer: coalesced
+// loads with the lanes along xi, then every lane sweeps ITS row out of shared memory exactly like k_legacy_march (row pitch
+// odd: conflict-free), writes each output over the source value it no longer needs, and the warp stores the rows back
+// coalesced.  Warp-private: __syncwarp only, no block barrier.  Central positions [5, n-5); the ends go to k_legacy_strip.
+constexpr int MARCHX_SEG = 48, MARCHX_PITCH = MARCHX_SEG + 11;  // 59 doubles per row (odd)
+template <int SRC, int OP>
+__global__ void __launch_bounds__(64) k_legacy_march_x(LShape S, LBox dom, LJobs jobs, LCheck chk, int seglen) {
+  static_assert(OP != OP_CCD_POST, "the second outer derivative along xi keeps the tile kernel");
+  __shared__ double sbuf[2][32 * MARCHX_PITCH];
+  double* const buf = sbuf[threadIdx.y];
+  const LJob J = jobs.j[blockIdx.y];
+  const int lane = threadIdx.x;
+  const int n = dom.hi[0] - dom.lo[0];
+  const int nl = dom.hi[1] - dom.lo[1], ngr = (nl + 31) / 32, no = dom.hi[2] - dom.lo[2];
+  const int P0 = 5, P1 = n - 5, nseg = (P1 - P0 + seglen - 1) / seglen;
+  long long w = (long long)blockIdx.x * 2 + threadIdx.y;  // warp index -> (segment, row group, k)
+  if (w >= (long long)nseg * ngr * no) return;
+  const int seg = (int)(w % nseg);
+  w /= nseg;
+  const int gr = (int)(w % ngr), oi = (int)(w / ngr);
+  const int s0 = P0 + seg * seglen, s1 = min(s0 + seglen, P1);
+  const int nrow = min(32, nl - gr * 32);
+  const long long row0 = (long long)(dom.lo[1] + gr * 32) * S.st[1] + (long long)(dom.lo[2] + oi) * S.st[2] + dom.lo[0];
+  const int len = s1 - s0 + 10;  // source values per row: positions s0-5 .. s1+4
+  // ---- coalesced load: lanes along xi ----
+  // (eight rows = sixteen loads in flight per lane: a row-by-row loop exposes the global latency 64 times per tile)
+  static_assert(MARCHX_SEG + 10 <= 64, "two 32-lane pieces per row");
+#pragma unroll 1
+  for (int r0 = 0; r0 < nrow; r0 += 8) {
+    double v[8][2];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long long Ir = row0 + (long long)(r0 + u) * S.st[1] + (s0 - 5);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = lane + 32 * t;
+        v[u][t] = (r0 + u < nrow && c < len) ? src_val<SRC>(J.a, J.b, J.c, J.d, Ir + c) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int c = lane + 32 * t;
+        if (r0 + u < nrow && c < len) buf[(r0 + u) * MARCHX_PITCH + c] = v[u][t];
+      }
+  }
+  __syncwarp();
+  // ---- sweep: lane = row ----
+  bool bad = false;
+  if (lane < nrow) {
+    const double e50 = 50 * DBL_EPSILON;
+    const bool checked = chk.vflags != nullptr && J.chk != 0;
+    const int cl_ = dom.lo[1] + gr * 32 + lane, co_ = dom.lo[2] + oi;
+    const bool line_in = checked && cl_ >= chk.box.lo[1] && cl_ < chk.box.hi[1] && co_ >= chk.box.lo[2] && co_ < chk.box.hi[2];
+    const int chk_lo = line_in ? chk.box.lo[0] - dom.lo[0] : 0, chk_hi = line_in ? chk.box.hi[0] - dom.lo[0] : 0;
+    double* const rowb = buf + lane * MARCHX_PITCH - (s0 - 5);  // rowb[q] = value at position q
+    double f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, f6 = 0, d0 = 0, d1 = 0, d2 = 0, hA = 0, hB = 0, hiPrev = 0;
+    for (int q = s0 - 5; q <= s1 + 4; ++q) {
+      f0 = f1; f1 = f2; f2 = f3; f3 = f4; f4 = f5; f5 = f6; f6 = rowb[q];
+      if (q >= s0 + 1) {
+        d0 = d1; d1 = d2;
+        d2 = central6(f0, f1, f2, f4, f5, f6);
+      }
+      if (q >= s0 + 3) {
+        const double dd = -tol_diff(d2, d0) / 2;
+        const double r = kahan3(2 * (f3 + f1), -4 * f2, dd);
+        hA = hB;
+        hB = (1.0 / 2.0) * d1 + (1.0 / 12.0) * r;
+      }
+      if (q >= s0 + 4) {
+        const double hi = ((f1 + hA) + (f2 - hB)) / 2;
+        if (q >= s0 + 5) {
+          const int pp = q - 5;
+          const double v = OP == OP_INTERP ? hi : clip(hi - hiPrev, e50);
+          rowb[pp] = v;  // the source value of position q-5 lives in f1 by now
+          bad |= pp >= chk_lo && pp < chk_hi && !(fabs(v) <= DBL_MAX);
+        }
+        hiPrev = hi;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- coalesced store ----
+  const int nout = s1 - s0;
+#pragma unroll 4
+  for (int r = 0; r < nrow; ++r) {
+    double* const o = J.out + row0 + (long long)r * S.st[1] + s0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int c = lane + 32 * t;
+      if (c < nout) o[c] = buf[r * MARCHX_PITCH + 5 + c];
+    }
+  }
+  if (bad) atomicOr(chk.vflags + (J.chk - 1), 1);
+}
+
 // The five cells at either end of a marched line (blockIdx.z = 0: positions 0..4, 1: n-5..n-1), one thread per line, all
 // in registers: ten source values, seven first derivatives (three one-sided, four central), six half-jumps (three
 // one-sided, three central), five outputs.  Local index i <-> absolute position a0 + i, a0 = 0 (low end) or n - 10 (high).
@@ -736,8 +838,9 @@ __device__ __forceinline__ void legacy_strip_body(const LShape& S, const LBox& d
                                                   const LCheck& chk) {
   const LJob J = jobs.j[blockIdx.y];
   const int n = dom.hi[axis] - dom.lo[axis];
-  const int oa = axis == 1 ? 2 : 1;
-  const int nl = dom.hi[0] - dom.lo[0], ngr = (nl + 31) / 32, no = dom.hi[oa] - dom.lo[oa];
+  const int la = axis == 0 ? 1 : 0;               // axis the lines are counted along (lanes)
+  const int oa = axis == 0 ? 2 : (axis == 1 ? 2 : 1);
+  const int nl = dom.hi[la] - dom.lo[la], ngr = (nl + 31) / 32, no = dom.hi[oa] - dom.lo[oa];
   const long long w = (long long)blockIdx.x * 4 + threadIdx.y;
   if (w >= (long long)ngr * no) return;
   const int gr = (int)(w % ngr), oi = (int)(w / ngr);
@@ -745,7 +848,7 @@ __device__ __forceinline__ void legacy_strip_body(const LShape& S, const LBox& d
   if (li >= nl) return;
   const long long s = S.st[axis];
   const int a0 = high ? n - 10 : 0;
-  const long long base = (long long)(dom.lo[0] + li) + (long long)(dom.lo[oa] + oi) * S.st[oa] + (long long)dom.lo[axis] * s;
+  const long long base = (long long)(dom.lo[la] + li) * S.st[la] + (long long)(dom.lo[oa] + oi) * S.st[oa] + (long long)dom.lo[axis] * s;
   double P[10], D[10], H[10];
 #pragma unroll
   for (int i = 0; i < 10; ++i) P[i] = src_val<SRC>(J.a, J.b, J.c, J.d, base + (long long)(a0 + i) * s);
@@ -787,8 +890,8 @@ __device__ __forceinline__ void legacy_strip_body(const LShape& S, const LBox& d
   const double e50 = 50 * DBL_EPSILON;
   const int first = whole ? 1 : 0, last = whole ? n - 2 : n - 1;
   const bool checked = chk.vflags != nullptr && J.chk != 0;
-  const int cl_ = dom.lo[0] + li, co_ = dom.lo[oa] + oi;
-  const bool line_in = checked && cl_ >= chk.box.lo[0] && cl_ < chk.box.hi[0] && co_ >= chk.box.lo[oa] && co_ < chk.box.hi[oa];
+  const int cl_ = dom.lo[la] + li, co_ = dom.lo[oa] + oi;
+  const bool line_in = checked && cl_ >= chk.box.lo[la] && cl_ < chk.box.hi[la] && co_ >= chk.box.lo[oa] && co_ < chk.box.hi[oa];
   const int chk_lo = line_in ? chk.box.lo[axis] - dom.lo[axis] : 0, chk_hi = line_in ? chk.box.hi[axis] - dom.lo[axis] : 0;
   bool bad = false;
 #pragma unroll
@@ -924,6 +1027,19 @@ int launch_fused(const LShape& S, const LBox& md, int axis, int whole, const LJo
     k_legacy_march<SRC, OP><<<dim3((unsigned)((warps + 3) / 4), njobs), dim3(32, 4), 0, st>>>(S, md, axis, jobs, scale, chk);
     (void)tma;
     return 2;
+  }
+  if constexpr (OP != OP_CCD_POST) {
+    // experiment switch (header): measured 14.02 against 14.16 ms at 256^3 for the tiles it replaces, i.e. within the noise
+    // (its sweep is as fast as k_legacy_march, the two shared-memory transposes cost what the tile halos cost): OFF
+    static const bool marchx_env = getenv("CG_LEGACY_MARCHX") && atoi(getenv("CG_LEGACY_MARCHX")) == 1;
+    if (axis == 0 && n >= 42 && md.hi[1] - md.lo[1] >= 8 && legacy_march() && marchx_env) {
+      const long long ngr = (md.hi[1] - md.lo[1] + 31) / 32, no = md.hi[2] - md.lo[2];
+      k_legacy_strip<SRC, OP><<<dim3((unsigned)((ngr * no + 3) / 4), njobs, 2), dim3(32, 4), 0, st>>>(S, md, axis, whole, jobs, scale, chk);
+      const int nseg0 = (n - 10 + MARCHX_SEG - 1) / MARCHX_SEG, seglen = (n - 10 + nseg0 - 1) / nseg0;  // balanced segments
+      const long long warps = (long long)((n - 10 + seglen - 1) / seglen) * ngr * no;
+      k_legacy_march_x<SRC, OP><<<dim3((unsigned)((warps + 1) / 2), njobs), dim3(32, 2), 0, st>>>(S, md, jobs, chk, seglen);
+      return 2;
+    }
   }
   launch_tiles<SRC, OP>(S, md, axis, whole, jobs, njobs, scale, st, tma, chk, 0, n);
   return 1;

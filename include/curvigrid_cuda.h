@@ -40,6 +40,8 @@
  *                        ones (20); both produce the same bits (tests/test_gpu_legacy.py)
  *   CG_LEGACY_MARCH=0    legacy MEG6 pipeline: tile kernels for the eta / zeta derivatives too, instead of the marching
  *                        (register-only) kernel + the end-strip kernel
+ *   CG_LEGACY_MARCHX=1   legacy MEG6 pipeline: xi derivatives through the warp-private transpose + sweep kernel
+ *                        (k_legacy_march_x, an experiment: as fast as the tile kernel it replaces)
  *   CG_LEGACY_TMA=0      legacy MEG6 pipeline: per-element loads of the source bricks instead of tensor-map TMA loads
  *   CG_NCCL_LIB=path     libnccl to dlopen when the process has not loaded one (default libnccl.so.2)
  *   CG_NVRTC_LIB=path    libnvrtc to dlopen for cg_grid_set_mapping_source (default libnvrtc.so.12, then the CUDA toolkit's)
