@@ -175,7 +175,14 @@ class ClockSampler:
         try:
             import pynvml as n
             n.nvmlInit()
-            self.nvml = (n, n.nvmlDeviceGetHandleByIndex(self.index))
+            h = None
+            try:  # the CUDA device of this rank by UUID (NVML counts physical GPUs, CUDA_VISIBLE_DEVICES may renumber them)
+                import torch
+                u = str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)
+                h = n.nvmlDeviceGetHandleByUUID(("GPU-" + u) if not u.startswith("GPU-") else u)
+            except Exception:
+                h = None
+            self.nvml = (n, h if h is not None else n.nvmlDeviceGetHandleByIndex(self.index))
             self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
             self.thread.start()
             return
