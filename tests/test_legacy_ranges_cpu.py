@@ -54,3 +54,34 @@ def test_fused_legacy_tile_ranges_are_closed():
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "curvilineargrids.jl_b200", "csrc"), src, "-o", exe])
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def test_branch_free_tol_diff_formula_equals_the_isapprox_definition():
+    """csrc/cg_legacy.cu evaluates tol_diff(a, b) = isapprox(a, b; rtol = sqrt(eps), atol = 10 eps) ? (a - b) * 0 : a - b
+    without branches: max(|a|, |b|) on the bit patterns, "not finite" as an all-ones exponent of that maximum, and
+    |d| <= thr || |d| <= atol instead of |d| <= max(atol, thr).  The same formula in numpy agrees with the plain definition
+    (derivative_stencils.jl:13-16, Base.isapprox) on random, nearly equal, equal, signed-zero, subnormal, infinite and NaN
+    inputs — bit for bit, NaN for NaN."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal(200000) * 10.0 ** rng.integers(-12, 12, 200000)
+    rel = 1.0 + rng.standard_normal(200000) * 10.0 ** rng.integers(-17, -5, 200000)
+    special = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2e-308, 1e-15, 2.3e-15, 1.7e308])
+    a = np.concatenate([base, base, np.repeat(special, len(special))])
+    b = np.concatenate([base * rel, base, np.tile(special, len(special))])
+    rtol, atol = 1.4901161193847656e-08, 10 * np.finfo(np.float64).eps
+    with np.errstate(all="ignore"):
+        d = a - b
+        # plain definition
+        approx = (a == b) | (np.isfinite(a) & np.isfinite(b) & (np.abs(d) <= np.maximum(atol, rtol * np.maximum(np.abs(a), np.abs(b)))))
+        want = np.where(approx, d * 0.0, d)
+        # branch-free formula of the kernel
+        ua, ub = np.abs(a).view(np.uint64), np.abs(b).view(np.uint64)
+        um = np.maximum(ua, ub)
+        fin = (um >> np.uint64(32)) < np.uint64(0x7FF00000)
+        thr = rtol * um.view(np.float64)
+        near = (np.abs(d) <= thr) | (np.abs(d) <= atol)
+        got = np.where(fin & near, d * 0.0, d)
+    both_nan = np.isnan(want) & np.isnan(got)
+    assert np.array_equal(got.view(np.uint64)[~both_nan], want.view(np.uint64)[~both_nan])
+    assert int(approx.sum()) > 1000 and int((~approx).sum()) > 1000
