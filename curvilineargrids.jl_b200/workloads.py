@@ -259,3 +259,22 @@ def terms_to_cuda_source(terms):
     body = "\n".join(f"  {q} = {' + '.join(expr[c])};" for c, q in enumerate("xyz"))
     return ("template <class S> __device__ void cg_map(S xi, S eta, S zeta, double t, const double* p, S& x, S& y, S& z) {\n"
             + body + "\n}\n")
+
+
+# The three NON-separable test mappings (oracle/metric_oracle.hpp FuncMap ids 1-3; tools/julia_goldens.jl states them as
+# Julia closures) as CUDA source for MappedGrid(mapping_source, params, ...): cg_grid_set_mapping_source.
+_MAP_SIG = "template <class S> __device__ void cg_map(S xi, S eta, S zeta, double t, const double* p, S& x, S& y, S& z)"
+GENERIC_TEST_SOURCES = {
+    1: _MAP_SIG + """ {
+  x = xi + p[0] * sin(p[1] * (eta + 0.5 * zeta) + 0.3 * t);
+  y = eta * (1.0 + p[2] * xi) / (1.0 + p[3] * zeta * zeta);
+  z = zeta + p[0] * exp(-p[4] * (xi - eta) * (xi - eta)) * cos(t) + sqrt(1.0 + 0.01 * xi * xi);
+}""",
+    2: _MAP_SIG + """ {
+  x = xi + p[0] * sin(p[1] * xi * eta + t);
+  y = eta + p[2] * sqrt(1.0 + p[3] * xi * xi + 0.5 * eta * eta);
+}""",
+    3: _MAP_SIG + """ {
+  x = xi + p[0] * sin(p[1] * xi) * exp(-p[2] * xi) + p[3] * t;
+}""",
+}

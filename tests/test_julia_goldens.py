@@ -43,6 +43,8 @@ def load_inputs(name):
         nn = tuple(int(v) for v in meta["nn"].split(","))
         nodes = [np.fromfile(os.path.join(INP, name, "xyz"[q] + ".bin"), dtype="<f8").reshape(nn, order="F") for q in range(dim)]
         return meta, dim, h, nodes
+    if meta["kind"] == "funcmap":
+        return meta, dim, h, [float(v) for v in meta["params"].split(",")]
     nt = int(meta["nterms"])
     terms = np.fromfile(os.path.join(INP, name, "terms.bin"), dtype="<f8").reshape((15, nt), order="F").T.copy()
     return meta, dim, h, terms
@@ -84,6 +86,10 @@ def test_oracle_matches_julia_digits(oracle, name, scheme):
     if meta["kind"] == "discrete":
         ref = oracle.discrete_eval(data, h, scheme, halo_coords_included=meta["halo_coords_included"] == "1")
         cen = oracle.discrete_coords(data, h, 1, halo_coords_included=meta["halo_coords_included"] == "1")
+    elif meta["kind"] == "funcmap":
+        celldims = tuple(int(v) for v in meta["celldims"].split(","))
+        ref = oracle.funcmap_eval(dim, int(meta["map_id"]), data, float(meta["t"]), celldims, h, scheme)
+        cen = oracle.funcmap_coords(dim, int(meta["map_id"]), data, float(meta["t"]), celldims, h, 1)
     else:
         celldims = tuple(int(v) for v in meta["celldims"].split(","))
         ref = oracle.mapped_eval(data, float(meta["t"]), celldims, h, scheme)
@@ -102,6 +108,11 @@ def test_cuda_matches_julia_digits(cg, name, scheme):
     if meta["kind"] == "discrete":
         g = cg.DiscreteGrid(*data, h, conserved_metric_scheme=scheme,
                             halo_coords_included=meta["halo_coords_included"] == "1")
+    elif meta["kind"] == "funcmap":   # the NVRTC path against the real package's ForwardDiff evaluation of the closures
+        celldims = tuple(int(v) for v in meta["celldims"].split(","))
+        g = cg.MappedGrid(cg.workloads.GENERIC_TEST_SOURCES[int(meta["map_id"])], data, celldims, h,
+                          conserved_metric_scheme=scheme, cache_mode="lazy")
+        cg.update(g, float(meta["t"]), data)
     else:
         celldims = tuple(int(v) for v in meta["celldims"].split(","))
         g = cg.MappedGrid(data, {}, celldims, h, conserved_metric_scheme=scheme, cache_mode="lazy")

@@ -56,6 +56,23 @@ function term_mapping(terms::Matrix{Float64}, coord::Int, dim::Int)
   return q
 end
 
+# the NON-separable test mappings (same formulas: oracle/metric_oracle.hpp FuncMap ids 1-3, workloads.GENERIC_TEST_SOURCES);
+# p is the parameter vector, passed as the grid's `params`
+function funcmap_closures(id::Int)
+  if id == 1
+    x = (t, ξ, η, ζ, p) -> ξ + p[1] * sin(p[2] * (η + 0.5 * ζ) + 0.3 * t)
+    y = (t, ξ, η, ζ, p) -> η * (1.0 + p[3] * ξ) / (1.0 + p[4] * ζ * ζ)
+    z = (t, ξ, η, ζ, p) -> ζ + p[1] * exp(-p[5] * (ξ - η) * (ξ - η)) * cos(t) + sqrt(1.0 + 0.01 * ξ * ξ)
+    return (x, y, z)
+  elseif id == 2
+    x = (t, ξ, η, p) -> ξ + p[1] * sin(p[2] * ξ * η + t)
+    y = (t, ξ, η, p) -> η + p[3] * sqrt(1.0 + p[4] * ξ * ξ + 0.5 * η * η)
+    return (x, y)
+  else
+    return ((t, ξ, p) -> ξ + p[1] * sin(p[2] * ξ) * exp(-p[3] * ξ) + p[4] * t,)
+  end
+end
+
 dump(path, A) = write(path, collect(reinterpret(Float64, vec(Array(A)))))
 
 function dump_grid(dir, grid, dim)
@@ -96,6 +113,14 @@ for name in sort(readdir(INP))
             conserved_metric_scheme=scheme, coordinate_system=cs_of(meta["coordinate_system"]),
             basis=basis_of(meta["basis"]))
       grid = dim == 1 ? DiscreteGrid(vec(nodes[1]), nhalo; kw...) : DiscreteGrid(nodes..., nhalo; kw...)
+      dump_grid(out, grid, dim)
+    elseif meta["kind"] == "funcmap"
+      celldims = ints(meta["celldims"])
+      p = parse.(Float64, split(meta["params"], ","))
+      t = parse(Float64, meta["t"])
+      grid = MappedGrid(funcmap_closures(parse(Int, meta["map_id"]))..., p, celldims, nhalo; cache_mode=:lazy,
+                        conserved_metric_scheme=scheme, t=0.0)
+      update!(grid, t, p)
       dump_grid(out, grid, dim)
     else
       celldims = ints(meta["celldims"])

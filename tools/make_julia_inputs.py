@@ -4,6 +4,8 @@ CurvilinearGrids.jl API and writes the reference's digits next to them (tests/go
 tests/test_julia_goldens.py checks the oracle and the CUDA path against.  This is SURVEY §8(f) rank 4's purpose (an
 on-disk exchange format for digit-level goldens from a real Julia run) without HDF5, which this image lacks; what must
 round-trip is what /root/reference/src/io/to_h5.jl:103-623 stores: coordinates, nhalo, coordinate system, basis.
+The `funcmap` cases are mappings that are NOT separable (id + parameters; the formulas are stated three times: as Julia
+closures in tools/julia_goldens.jl, as C++ in oracle/metric_oracle.hpp FuncMap, as CUDA source in workloads.py).
 
 Cases cover: curved boundaries (halo = Line() extrapolation, incl. the 2- and 3-face corner regions that settle SURVEY
 Appendix C.1), halo_coords_included, 1-/2-/3-D, every conserved scheme, a time-dependent mapping and ADThomasLombard."""
@@ -53,6 +55,12 @@ def main():
                 "t": repr(float(t)), "nterms": tab.shape[0]}
         write_case(out, name, meta, {"terms": tab.T})   # Julia reads a 15 x nterms matrix
 
+    def funcmap(name, map_id, params, celldims, nhalo, t, schemes=all3):
+        # NON-separable analytic mappings (arbitrary closures on the Julia side, CUDA source on the device side)
+        meta = {"kind": "funcmap", "dim": len(celldims), "nhalo": nhalo, "celldims": csv(celldims), "schemes": schemes,
+                "t": repr(float(t)), "map_id": map_id, "params": ",".join(repr(float(v)) for v in params)}
+        write_case(out, name, meta, {})
+
     discrete("d3_wavy", wl.wavy_nodes_3d(9, 8, 7), 3)                       # curved boundary, corner halo regions
     discrete("d3_mild", mild_nodes((8, 7, 6), seed=3), 2)
     inner = mild_nodes((7, 6, 5), seed=7)
@@ -68,6 +76,9 @@ def main():
     mapped("m2_readme", wl.readme_wavy_2d_terms(), (16, 12), 3, 0.0)
     mapped("m3_wavy_t", wl.wavy_3d_terms((9, 8, 7), time_amp=0.1), (9, 8, 7), 2, 0.37, schemes=all3 + ",adtl")
     mapped("m3_rtp", wl.spherical_rtp_3d_terms((8, 7, 6)), (8, 7, 6), 2, 0.0, schemes="curvature,adtl")
+    funcmap("g3_nonseparable", 1, [0.3, 0.4, 0.01, 0.001, 0.02], (9, 8, 7), 3, 0.7)
+    funcmap("g2_nonseparable", 2, [0.2, 0.05, 0.3, 0.1], (14, 11), 3, 0.7)
+    funcmap("g1_nonseparable", 3, [0.1, 0.6, 0.02, 0.5], (23,), 3, 0.7, schemes="curvature")
     print("wrote", out)
 
 
