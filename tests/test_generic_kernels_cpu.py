@@ -102,3 +102,43 @@ def test_generic_kernels_on_the_host_match_the_oracle(map_id, scheme):
     ref = O.funcmap_eval(N, map_id, prm, t, celldims, h, scheme)
     got["nfull"] = ref["nfull"]
     assert_metrics_close(got, ref, rtol=RTOL_F64, label=f"host build of the generic kernels, map {map_id} {scheme}")
+
+
+def _run_host_build(src_map, N, scheme_id, h, celldims, t, prm):
+    hdr = open(os.path.join(ROOT, "curvilineargrids.jl_b200", "csrc", "cg_generic_prelude.h")).read()
+    prelude = re.search(r'GENERIC_PRELUDE = R"CGSRC\((.*?)\)CGSRC"', hdr, re.S).group(1)
+    kernels = re.search(r'GENERIC_KERNELS = R"CGSRC\((.*?)\)CGSRC"', hdr, re.S).group(1)
+    with tempfile.TemporaryDirectory() as d:
+        cpp, exe, out = os.path.join(d, "g.cpp"), os.path.join(d, "g"), os.path.join(d, "o.bin")
+        open(cpp, "w").write(SHIM + prelude + src_map + kernels + MAIN)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", cpp, "-o", exe])
+        dims = list(celldims) + [1] * (3 - N)
+        subprocess.check_call([exe, str(N), str(scheme_id), str(h)] + [str(v) for v in dims] + [repr(float(t)), str(len(prm))] +
+                              [repr(float(v)) for v in prm] + [out])
+        raw = np.fromfile(out, dtype=np.float64)
+    nc = int(np.prod([c + 2 * h for c in celldims]))
+    KM, KC = N * N + 1, N * N
+    o, got = 0, {}
+    for key, cnt, shape in (("cell_fwd", nc * KM, (nc, KM)), ("cell_inv", nc * KM, (nc, KM)), ("face_fwd", N * nc * KM, (N, nc, KM)),
+                            ("face_inv", N * nc * KM, (N, nc, KM)), ("face_cons", N * nc * KC, (N, nc, KC))):
+        got[key] = raw[o:o + cnt].reshape(shape)
+        o += cnt
+    return got
+
+
+@pytest.mark.parametrize("name", ["readme2d", "wavy3d_t", "rtp3d"])
+def test_term_lists_as_generated_source_match_the_oracle_on_the_host(name):
+    """workloads.terms_to_cuda_source turns any separable term list into `cg_map` source: the reference's own test mappings
+    (README 2-D mapping, the time-dependent wavy 3-D mapping of BASELINE config 4, the spherical (r, theta, phi) mapping) run
+    through the generic kernels — built for the host — and agree with the oracle's evaluation of the term list."""
+    import curvigrid_b200 as cg
+    from oracle import oracle as O
+    wl = cg.workloads
+    terms, celldims, h = {"readme2d": (wl.readme_wavy_2d_terms(), (8, 7), 2),
+                          "wavy3d_t": (wl.wavy_3d_terms((5, 4, 3), time_amp=0.1), (5, 4, 3), 2),
+                          "rtp3d": (wl.spherical_rtp_3d_terms((4, 4, 4)), (4, 4, 4), 2)}[name]
+    t = 0.37
+    got = _run_host_build(wl.terms_to_cuda_source(terms), len(celldims), 2, h, celldims, t, [])
+    ref = O.mapped_eval(terms, t, celldims, h, "curvature")
+    got["nfull"] = ref["nfull"]
+    assert_metrics_close(got, ref, rtol=RTOL_F64, label=f"{name}: generated source on the host vs oracle")
